@@ -1,0 +1,230 @@
+// Context lifetime, error reporting and configuration (NavMap::config, HybridAstar::config/setFootprint).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "mpros_internal.cuh"
+
+namespace mpros
+{
+static thread_local std::string g_last_error = "";
+
+void set_error(const std::string &msg) { g_last_error = msg; }
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    char buf[512];
+    std::snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    set_error(buf);
+    return MPROS_ERR_CUDA;
+}
+
+static int grow(void **p, size_t *cap, size_t bytes)
+{
+    if (bytes <= *cap)
+        return MPROS_OK;
+    if (*p)
+        MPROS_CUDA(cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    MPROS_CUDA(cudaMalloc(p, want));
+    *cap = want;
+    return MPROS_OK;
+}
+int ensure_scratch(Ctx *c, size_t bytes) { return grow(&c->scratch, &c->scratch_bytes, bytes); }
+int ensure_stage(Ctx *c, size_t bytes) { return grow(&c->stage, &c->stage_bytes, bytes); }
+} // namespace mpros
+
+using namespace mpros;
+
+extern "C" const char *mpros_last_error_string(void) { return g_last_error.c_str(); }
+
+extern "C" int mpros_ctx_create(int device, mpros_ctx **out)
+{
+    if (!out)
+    {
+        set_error("mpros_ctx_create: out is NULL");
+        return MPROS_ERR_INVALID;
+    }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+    {
+        // no CPU fallback: the product path requires a CUDA device
+        cuda_fail(e == cudaSuccess ? cudaErrorNoDevice : e, "cudaGetDeviceCount (no CUDA device, no CPU fallback)", __FILE__,
+                  __LINE__);
+        return MPROS_ERR_CUDA;
+    }
+    if (device < 0 || device >= n)
+    {
+        set_error("mpros_ctx_create: device index out of range");
+        return MPROS_ERR_INVALID;
+    }
+    MPROS_CUDA(cudaSetDevice(device));
+    mpros_ctx *c = new (std::nothrow) mpros_ctx();
+    if (!c)
+    {
+        set_error("out of host memory");
+        return MPROS_ERR_INVALID;
+    }
+    c->device = device;
+    mpros_map_params_default(&c->mp);
+    mpros_planner_params_default(&c->pp);
+    std::memset(&c->pv, 0, sizeof(c->pv));
+    cudaError_t se = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (se != cudaSuccess)
+    {
+        delete c;
+        return cuda_fail(se, "cudaStreamCreate", __FILE__, __LINE__);
+    }
+    *out = c;
+    return MPROS_OK;
+}
+
+extern "C" int mpros_ctx_destroy(mpros_ctx *c)
+{
+    if (!c)
+        return MPROS_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    void *bufs[] = {c->raw_bits, c->infl_bits, c->ds_bits, c->goal, c->obs_dist, c->edge_dist,
+                    c->region, c->edge_bits, c->voronoi, c->scratch, c->stage};
+    for (void *b : bufs)
+        if (b)
+            cudaFree(b);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return MPROS_OK;
+}
+
+extern "C" void *mpros_ctx_stream(mpros_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+extern "C" int mpros_ctx_synchronize(mpros_ctx *c)
+{
+    if (!c)
+        return MPROS_ERR_INVALID;
+    MPROS_CUDA(cudaStreamSynchronize(c->stream));
+    return MPROS_OK;
+}
+
+extern "C" uint64_t mpros_ctx_launch_count(mpros_ctx *c) { return c ? c->launches : 0; }
+
+// nav_map.cpp:27-34
+extern "C" void mpros_map_params_default(mpros_map_params *p)
+{
+    p->occupied_thresh = 0.68;
+    p->free_thresh = 0.2;
+    p->voro_fallout_rate = 10.0f;
+    p->voro_max_region = 50.0f;
+    p->downsampling_factor = 1;
+    p->obstacle_inflation_radius = 0.0;
+}
+
+// hybrid_a_star.cpp:128-161
+extern "C" void mpros_planner_params_default(mpros_planner_params *p)
+{
+    p->max_curvature = 0.4;
+    p->width = 2.0;
+    p->wheelbase = 3.0;
+    p->length = 4.2;
+    p->steer_offset = 0.0;
+    p->max_steering_angle = 0.35;
+    p->gear_penalty = 10.0;
+    p->reverse_penalty = 0.0;
+    p->steering_penalty = 0.1;
+    p->steering_change_penalty = 10.0;
+    p->analytic_solution_range = 10.0;
+    p->yaw_discretization = 36;
+    p->step_size = 1.1;
+    p->path_point_distance = 0.2;
+    p->steering_discretization = 3;
+    p->max_iteration = 10000;
+    p->optimal_path = 0;
+    p->interpolation_enable = 1;
+}
+
+extern "C" int mpros_map_config(mpros_ctx *c, const mpros_map_params *p)
+{
+    if (!c || !p)
+    {
+        set_error("mpros_map_config: NULL argument");
+        return MPROS_ERR_INVALID;
+    }
+    if (p->downsampling_factor < 1)
+    {
+        set_error("mpros_map_config: downsampling_factor must be >= 1");
+        return MPROS_ERR_INVALID;
+    }
+    c->mp = *p;
+    return MPROS_OK;
+}
+
+// HybridAstar::config + setFootprint (hybrid_a_star.cpp:120-206)
+extern "C" int mpros_planner_config(mpros_ctx *c, const mpros_planner_params *p)
+{
+    if (!c || !p)
+    {
+        set_error("mpros_planner_config: NULL argument");
+        return MPROS_ERR_INVALID;
+    }
+    if (!c->get_map)
+    {
+        // setFootprint reads map_->map_resolution_orig_ (hybrid_a_star.cpp:204)
+        set_error("mpros_planner_config: no map set (setFootprint needs map_resolution_orig_)");
+        return MPROS_ERR_INVALID;
+    }
+    int num_pos_steer = p->steering_discretization / 2;
+    if (2 * num_pos_steer + 1 > kMaxSteer || p->yaw_discretization < 1)
+    {
+        set_error("mpros_planner_config: steering_discretization / yaw_discretization out of range");
+        return MPROS_ERR_INVALID;
+    }
+    c->pp = *p;
+    PlannerView &v = c->pv;
+    const double L = p->length, Wd = p->width, off = p->steer_offset;
+    // footprint_m_ corners, clockwise (hybrid_a_star.cpp:193-196)
+    v.corner_x[0] = L / 2 + off;
+    v.corner_y[0] = Wd / 2;
+    v.corner_x[1] = L / 2 + off;
+    v.corner_y[1] = -Wd / 2;
+    v.corner_x[2] = -L / 2 + off;
+    v.corner_y[2] = -Wd / 2;
+    v.corner_x[3] = -L / 2 + off;
+    v.corner_y[3] = Wd / 2;
+    // footprint_longi_ (hybrid_a_star.cpp:198-199)
+    v.longi_x0 = L / 2 + off - 1.0 / 2 * Wd;
+    v.longi_x1 = -L / 2 + off + 1.0 / 2 * Wd;
+    // num_checking_step (hybrid_a_star.cpp:632-633)
+    double footprint_len = L - Wd;
+    v.n_check = (int)std::ceil(footprint_len / c->res0);
+    if (v.n_check < 1)
+    {
+        set_error("mpros_planner_config: length - width must be positive");
+        return MPROS_ERR_INVALID;
+    }
+    // steer_set_ (hybrid_a_star.cpp:176-184)
+    v.n_steer = 0;
+    for (int i = 1; i <= num_pos_steer; ++i)
+    {
+        v.steer_set[v.n_steer++] = p->max_steering_angle / num_pos_steer * i;
+        v.steer_set[v.n_steer++] = -p->max_steering_angle / num_pos_steer * i;
+    }
+    v.steer_set[v.n_steer++] = 0.0;
+    v.step_size = p->step_size;
+    v.arc_radius_num = p->wheelbase / 2 + off;
+    v.pen_gear = p->gear_penalty;
+    v.pen_back = p->reverse_penalty;
+    v.pen_steer = p->steering_penalty;
+    v.pen_steer_change = p->steering_change_penalty;
+    v.min_r = 1.0 / p->max_curvature;
+    v.max_steer = p->max_steering_angle;
+    v.rs_range = p->analytic_solution_range;
+    v.num_yaw = p->yaw_discretization;
+    v.yaw_resol = 2 * M_PI / p->yaw_discretization;
+    v.max_iteration = p->max_iteration;
+    c->planner_configured = true;
+    return MPROS_OK;
+}

@@ -1,0 +1,663 @@
+// NavMap preprocessing on bit-packed layers: threshold (N1), down-sampling (N2), disk inflation (N3),
+// plus the NavMap getters that move a layer back to the host in the reference's element types.
+//
+// All three kernels are HBM/L2-streaming integer work. The only full-size HBM read is the int8 occupancy
+// grid itself (1 B/cell, read once with 128-bit loads); everything downstream works on 1 bit/cell.
+#include <cmath>
+#include <cstring>
+
+#include "mpros_internal.cuh"
+
+namespace mpros
+{
+
+// ---- N1: NavMap::setOccupancyMap threshold loop (nav_map.cpp:114-131) ------------------------------------
+// new = (d > free_thres || d < 0) ? 1 : (d < free_thres ? 0 : old). With integer d this is
+// d >= occ_min || d < 0, resp. d <= free_max (thresholds pre-rounded on the host, exact).
+__device__ __forceinline__ uint32_t classify16(uint4 v, int occ_min, int free_max, uint32_t &free_mask)
+{
+    uint32_t occ = 0, fre = 0;
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+        {
+            int d = (int)(int8_t)((w[q] >> (8 * b)) & 0xff);
+            bool o = (d >= occ_min) || (d < 0);
+            bool f = !o && (d <= free_max);
+            occ |= (uint32_t)o << (4 * q + b);
+            fre |= (uint32_t)f << (4 * q + b);
+        }
+    free_mask = fre;
+    return occ;
+}
+
+// Fast path: W % 32 == 0 and 16-byte aligned base. One thread = one output word = 32 cells = two 128-bit loads;
+// a warp covers 1 KiB of contiguous input.
+__global__ void __launch_bounds__(256) threshold_pack_vec_kernel(const int8_t *__restrict__ data, uint32_t *__restrict__ bits,
+                                                                 int H, int W, int pitch, int occ_min, int free_max,
+                                                                 int have_old)
+{
+    const int words_per_row = W >> 5;
+    const size_t total = (size_t)H * words_per_row;
+    for (size_t wd = (size_t)blockIdx.x * blockDim.x + threadIdx.x; wd < total; wd += (size_t)gridDim.x * blockDim.x)
+    {
+        int i = (int)(wd / words_per_row), w = (int)(wd % words_per_row);
+        const uint4 *src = reinterpret_cast<const uint4 *>(data + (size_t)i * W) + 2 * w;
+        uint4 v0 = __ldg(src), v1 = __ldg(src + 1);
+        uint32_t f0, f1;
+        uint32_t occ = classify16(v0, occ_min, free_max, f0);
+        occ |= classify16(v1, occ_min, free_max, f1) << 16;
+        uint32_t fre = f0 | (f1 << 16);
+        size_t widx = (size_t)i * pitch + w;
+        uint32_t old = have_old ? bits[widx] : 0u;
+        bits[widx] = occ | (old & ~fre);
+    }
+}
+
+// General path: one lane per cell, warp ballot forms the word.
+__global__ void __launch_bounds__(256) threshold_pack_kernel(const int8_t *__restrict__ data, uint32_t *__restrict__ bits, int H,
+                                                             int W, int pitch, int occ_min, int free_max, int have_old)
+{
+    const int words_per_row = (W + 31) >> 5;
+    const size_t total_words = (size_t)H * words_per_row;
+    const int lane = threadIdx.x & 31;
+    size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t wd = warp; wd < total_words; wd += nwarps)
+    {
+        int i = (int)(wd / words_per_row);
+        int w = (int)(wd % words_per_row);
+        int j = (w << 5) + lane;
+        bool o = false, f = false;
+        if (j < W)
+        {
+            int d = (int)__ldg(data + (size_t)i * W + j);
+            o = (d >= occ_min) || (d < 0);
+            f = !o && (d <= free_max);
+        }
+        uint32_t occ = __ballot_sync(0xffffffffu, o);
+        uint32_t fre = __ballot_sync(0xffffffffu, f);
+        if (lane == 0)
+        {
+            size_t widx = (size_t)i * pitch + w;
+            uint32_t old = have_old ? bits[widx] : 0u;
+            bits[widx] = occ | (old & ~fre);
+        }
+    }
+}
+
+// std::vector::resize keeps the linear prefix when the map geometry changes (nav_map.cpp:107): cell (i,j) of
+// the new grid starts from the old value at linear index i*W_new + j.
+__global__ void relinearize_kernel(const uint32_t *__restrict__ old_bits, int oldH, int oldW, int old_pitch,
+                                   uint32_t *__restrict__ new_bits, int H, int W, int pitch)
+{
+    const int words_per_row = (W + 31) >> 5;
+    size_t total = (size_t)H * words_per_row;
+    for (size_t wd = (size_t)blockIdx.x * blockDim.x + threadIdx.x; wd < total; wd += (size_t)gridDim.x * blockDim.x)
+    {
+        int i = (int)(wd / words_per_row), w = (int)(wd % words_per_row);
+        uint32_t out = 0;
+        for (int b = 0; b < 32; ++b)
+        {
+            int j = (w << 5) + b;
+            if (j >= W)
+                break;
+            size_t k = (size_t)i * W + j;
+            if (k < (size_t)oldH * oldW)
+            {
+                int oi = (int)(k / oldW), oj = (int)(k % oldW);
+                out |= ((old_bits[(size_t)oi * old_pitch + (oj >> 5)] >> (oj & 31)) & 1u) << b;
+            }
+        }
+        new_bits[(size_t)i * pitch + w] = out;
+    }
+}
+
+// ---- N2: NavMap::downsampleMap / downsampleCellValue (nav_map.cpp:592-652) ------------------------------
+// max-pool ds x ds. Off-by-one quirks kept: old_j == W is allowed and reads linear index i*W + W (first cell
+// of the next row); old_i == H is allowed but every index > size is skipped. Index == size is undefined
+// behaviour in the reference (one past the end); it contributes 0 here.
+__global__ void __launch_bounds__(256) downsample_kernel(const uint32_t *__restrict__ raw, int H0, int W0, int pitch0,
+                                                         uint32_t *__restrict__ out, int H, int W, int pitch, int ds)
+{
+    const int words_per_row = (W + 31) >> 5;
+    const size_t total_words = (size_t)H * words_per_row;
+    const int lane = threadIdx.x & 31;
+    size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const size_t size0 = (size_t)H0 * W0;
+    for (size_t wd = warp; wd < total_words; wd += nwarps)
+    {
+        int i = (int)(wd / words_per_row);
+        int w = (int)(wd % words_per_row);
+        int j = (w << 5) + lane;
+        bool v = false;
+        if (j < W)
+        {
+            int i_off = i * ds, j_off = j * ds;
+            for (int a = 0; a < ds && !v; ++a)
+            {
+                int oi = a + i_off;
+                if (oi > H0)
+                    break;
+                for (int b = 0; b < ds; ++b)
+                {
+                    int oj = b + j_off;
+                    if (oj > W0)
+                        break;
+                    size_t k = (size_t)oi * W0 + oj;
+                    if (k >= size0)
+                        continue; // > size skipped by the reference; == size is UB there, 0 here
+                    int ri = (int)(k / W0), rj = (int)(k % W0);
+                    if ((raw[(size_t)ri * pitch0 + (rj >> 5)] >> (rj & 31)) & 1u)
+                    {
+                        v = true;
+                        break;
+                    }
+                }
+            }
+        }
+        uint32_t word = __ballot_sync(0xffffffffu, v);
+        if (lane == 0)
+            out[(size_t)i * pitch + w] = word;
+    }
+}
+
+// ---- N3: NavMap::inflateObstacle (nav_map.cpp:164-214) ----------------------------------------------------
+// Binary dilation by SE = {(di,dj): (|di|-1/2)^2 + (|dj|-1/2)^2 <= r^2}, clipped to the map. The SE is
+// monotone in |di| and |dj|, so SE = union over column offsets s of the vertical run |di| <= a(|s|).
+// Per output word: V_a = OR of the input rows i-a..i+a (word-aligned, no shifting), grown incrementally
+// while |s| walks from the widest offset to 0, and out |= funnel-shift(V_a(|s|), +-s).
+// ext_tab[k] = a(k) (or -1 when column offset k is outside the SE), in constant memory.
+constexpr int kMaxInflRadius = 255;
+__constant__ int16_t c_ext_tab[kMaxInflRadius + 1];
+
+template <int K, bool SMALL> // K = words of halo on each side; SMALL: smax <= 31, all shifts stay within +-1 word
+__global__ void __launch_bounds__(256) inflate_kernel(const uint32_t *__restrict__ raw, uint32_t *__restrict__ out, int H,
+                                                      int W, int pitch, int smax)
+{
+    const int words_per_row = (W + 31) >> 5;
+    const size_t total = (size_t)H * words_per_row;
+    for (size_t wd = (size_t)blockIdx.x * blockDim.x + threadIdx.x; wd < total; wd += (size_t)gridDim.x * blockDim.x)
+    {
+        int i = (int)(wd / words_per_row), w = (int)(wd % words_per_row);
+        uint32_t V[2 * K + 2]; // V[k] = OR over current rows of word w - K + k; one spare so V[q+1] is always valid
+#pragma unroll
+        for (int k = 0; k < 2 * K + 2; ++k)
+            V[k] = 0;
+        uint32_t acc = 0;
+        int a_cur = -1; // rows |di| <= a_cur are folded into V
+        for (int s = smax; s >= 0; --s)
+        {
+            int a = c_ext_tab[s];
+            if (a < 0)
+                continue;
+            for (int di = a_cur + 1; di <= a; ++di)
+            {
+#pragma unroll
+                for (int sign = 0; sign < 2; ++sign)
+                {
+                    if (di == 0 && sign == 1)
+                        continue;
+                    int r = sign ? i - di : i + di;
+                    if (r < 0 || r >= H)
+                        continue;
+                    const uint32_t *row = raw + (size_t)r * pitch;
+#pragma unroll
+                    for (int k = 0; k < 2 * K + 1; ++k)
+                    {
+                        int ww = w - K + k;
+                        if (ww >= 0 && ww < words_per_row)
+                            V[k] |= __ldg(row + ww);
+                    }
+                }
+            }
+            a_cur = a > a_cur ? a : a_cur;
+            // out[j] |= V[j - s] and V[j + s]
+            int q = (K == 1 && SMALL) ? 0 : (s >> 5), t = s & 31;
+            // left shift by s: bits come from words w-q (high part) and w-q-1 (low part)
+            uint32_t hi = V[K - q];
+            uint32_t lo = (K - q - 1 >= 0) ? V[K - q - 1] : 0u;
+            acc |= __funnelshift_l(lo, hi, t);
+            // right shift by s: words w+q (low part) and w+q+1 (high part)
+            uint32_t lo2 = V[K + q];
+            uint32_t hi2 = (K + q + 1 <= 2 * K) ? V[K + q + 1] : 0u;
+            acc |= __funnelshift_r(lo2, hi2, t);
+        }
+        if (w == words_per_row - 1 && (W & 31))
+            acc &= (1u << (W & 31)) - 1u;
+        out[(size_t)i * pitch + w] = acc;
+    }
+}
+
+// ---- getters: unpack a bit layer to int8, widen u16 -> int32 ------------------------------------------------
+__global__ void unpack_bits_kernel(const uint32_t *__restrict__ bits, int H, int W, int pitch, int8_t *__restrict__ out)
+{
+    size_t total = (size_t)H * W;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x)
+    {
+        int i = (int)(k / W), j = (int)(k % W);
+        out[k] = (int8_t)((bits[(size_t)i * pitch + (j >> 5)] >> (j & 31)) & 1u);
+    }
+}
+__global__ void widen_u16_kernel(const uint16_t *__restrict__ in, size_t n, int32_t *__restrict__ out)
+{
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+        out[k] = (int32_t)in[k];
+}
+__global__ void point_lookup_kernel(const uint32_t *__restrict__ bits, int H, int W, int pitch, const int32_t *__restrict__ ij,
+                                    size_t n, uint8_t *__restrict__ out)
+{
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+    {
+        int i = ij[2 * k], j = ij[2 * k + 1];
+        bool hit = true; // outside the map counts as collision (nav_map.cpp:249-277)
+        if (i >= 0 && i < H && j >= 0 && j < W)
+            hit = (bits[(size_t)i * pitch + (j >> 5)] >> (j & 31)) & 1u;
+        out[k] = hit;
+    }
+}
+
+static int grid_for(size_t work_items, int block = 256)
+{
+    size_t g = (work_items + block - 1) / block;
+    const size_t cap = 148 * 16; // multiples of the SM count; grid-stride loops cover the rest
+    if (g > cap)
+        g = cap;
+    if (g < 1)
+        g = 1;
+    return (int)g;
+}
+
+static int realloc_layers(Ctx *c)
+{
+    size_t words0 = (size_t)c->H0 * c->pitch0, words = (size_t)c->H * c->pitch, cells = (size_t)c->H * c->W;
+    if (words0 > c->cap0_words)
+    {
+        if (c->infl_bits)
+            MPROS_CUDA(cudaFree(c->infl_bits));
+        c->infl_bits = nullptr;
+        MPROS_CUDA(cudaMalloc(&c->infl_bits, words0 * 4));
+        // raw_bits is re-created by the caller (it needs the old content for relinearisation)
+        c->cap0_words = words0;
+    }
+    if (words > c->cap_words)
+    {
+        if (c->ds_bits)
+            MPROS_CUDA(cudaFree(c->ds_bits));
+        if (c->edge_bits)
+            MPROS_CUDA(cudaFree(c->edge_bits));
+        c->ds_bits = c->edge_bits = nullptr;
+        MPROS_CUDA(cudaMalloc(&c->ds_bits, words * 4));
+        MPROS_CUDA(cudaMalloc(&c->edge_bits, words * 4));
+        c->cap_words = words;
+    }
+    if (cells > c->cap_cells)
+    {
+        void **bufs[] = {(void **)&c->goal, (void **)&c->obs_dist, (void **)&c->edge_dist, (void **)&c->region,
+                         (void **)&c->voronoi};
+        size_t esz[] = {2, 2, 2, 4, 4};
+        for (int k = 0; k < 5; ++k)
+        {
+            if (*bufs[k])
+                MPROS_CUDA(cudaFree(*bufs[k]));
+            *bufs[k] = nullptr;
+            MPROS_CUDA(cudaMalloc(bufs[k], cells * esz[k]));
+        }
+        c->cap_cells = cells;
+    }
+    return MPROS_OK;
+}
+
+static int set_occupancy_impl(Ctx *c, const int8_t *d_data, int width, int height, double resolution, double ox, double oy,
+                              double oyaw)
+{
+    cudaStream_t st = c->stream;
+    const bool first = !c->get_map;
+    const bool geom_change = c->get_map && (c->H0 != height || c->W0 != width || c->res0 != resolution || c->ox != ox ||
+                                            c->oy != oy || c->oyaw != oyaw);
+    int have_old = 0;
+    if (first || geom_change)
+    {
+        int oldH = c->H0, oldW = c->W0, old_pitch = c->pitch0;
+        uint32_t *old_bits = c->raw_bits;
+        c->H0 = height;
+        c->W0 = width;
+        c->pitch0 = pitch_words(width);
+        c->res0 = resolution;
+        c->ox = ox;
+        c->oy = oy;
+        c->oyaw = oyaw;
+        c->osin = std::sin(oyaw);
+        c->ocos = std::cos(oyaw);
+        const int ds = c->mp.downsampling_factor;
+        c->H = (int)std::ceil(static_cast<double>(height) / ds);
+        c->W = (int)std::ceil(static_cast<double>(width) / ds);
+        c->pitch = pitch_words(c->W);
+        c->res = resolution * ds;
+        int rc = realloc_layers(c);
+        if (rc)
+            return rc;
+        uint32_t *nb = nullptr;
+        MPROS_CUDA(cudaMalloc(&nb, (size_t)c->H0 * c->pitch0 * 4));
+        if (geom_change && old_bits)
+        {
+            relinearize_kernel<<<grid_for((size_t)c->H0 * c->pitch0), 256, 0, st>>>(old_bits, oldH, oldW, old_pitch, nb, c->H0,
+                                                                                  c->W0, c->pitch0);
+            MPROS_LAUNCH_CHECK(c);
+            MPROS_CUDA(cudaStreamSynchronize(st));
+            have_old = 1;
+        }
+        if (old_bits)
+            MPROS_CUDA(cudaFree(old_bits));
+        c->raw_bits = nb;
+    }
+    else
+        have_old = 1;
+
+    // N1 (exact integer form of the double comparisons against free_thres_)
+    const double t = c->mp.free_thresh;
+    double occ_min_d = std::floor(t) + 1.0, free_max_d = std::ceil(t) - 1.0;
+    int occ_min = occ_min_d > 200 ? 200 : (occ_min_d < -200 ? -200 : (int)occ_min_d);
+    int free_max = free_max_d > 200 ? 200 : (free_max_d < -200 ? -200 : (int)free_max_d);
+    // padding words/bits must stay zero: clear the layer when there is no old state to merge
+    if (!have_old)
+        MPROS_CUDA(cudaMemsetAsync(c->raw_bits, 0, (size_t)c->H0 * c->pitch0 * 4, st));
+    if ((width % 32) == 0 && (reinterpret_cast<uintptr_t>(d_data) % 16) == 0)
+    {
+        size_t words = (size_t)height * (width >> 5);
+        threshold_pack_vec_kernel<<<grid_for(words), 256, 0, st>>>(d_data, c->raw_bits, height, width, c->pitch0, occ_min,
+                                                                      free_max, have_old);
+    }
+    else
+    {
+        size_t words = (size_t)height * ((width + 31) / 32);
+        threshold_pack_kernel<<<grid_for(words * 32), 256, 0, st>>>(d_data, c->raw_bits, height, width, c->pitch0, occ_min,
+                                                                  free_max, have_old);
+    }
+    MPROS_LAUNCH_CHECK(c);
+
+    // N2
+    const int ds = c->mp.downsampling_factor;
+    if (ds == 1)
+        MPROS_CUDA(cudaMemcpyAsync(c->ds_bits, c->raw_bits, (size_t)c->H0 * c->pitch0 * 4, cudaMemcpyDeviceToDevice, st));
+    else
+    {
+        MPROS_CUDA(cudaMemsetAsync(c->ds_bits, 0, (size_t)c->H * c->pitch * 4, st));
+        size_t words = (size_t)c->H * ((c->W + 31) / 32);
+        downsample_kernel<<<grid_for(words * 32), 256, 0, st>>>(c->raw_bits, c->H0, c->W0, c->pitch0, c->ds_bits, c->H, c->W,
+                                                              c->pitch, ds);
+        MPROS_LAUNCH_CHECK(c);
+    }
+
+    // N3: structuring-element table exactly as the reference evaluates it (quarter-integers, exact in double)
+    {
+        int r = (int)std::ceil(c->mp.obstacle_inflation_radius / c->res0);
+        if (r < 0)
+            r = 0;
+        if (r > kMaxInflRadius)
+        {
+            set_error("obstacle_inflation_radius / resolution exceeds 255 pixels (unsupported)");
+            return MPROS_ERR_INVALID;
+        }
+        double r_sq = r * r;
+        int16_t tab[kMaxInflRadius + 1];
+        int smax = -1;
+        for (int s = 0; s <= kMaxInflRadius; ++s)
+        {
+            tab[s] = -1;
+            if (s > r)
+                continue;
+            double j_dist = std::abs(s) - 0.5;
+            for (int a = 0; a <= r; ++a)
+            {
+                double i_dist = std::abs(a) - 0.5;
+                if (i_dist * i_dist + j_dist * j_dist <= r_sq)
+                    tab[s] = (int16_t)a;
+            }
+            if (tab[s] >= 0)
+                smax = s;
+        }
+        MPROS_CUDA(cudaMemcpyToSymbolAsync(c_ext_tab, tab, sizeof(tab), 0, cudaMemcpyHostToDevice, st));
+        MPROS_CUDA(cudaMemsetAsync(c->infl_bits, 0, (size_t)c->H0 * c->pitch0 * 4, st));
+        if (smax >= 0)
+        {
+            size_t words = (size_t)c->H0 * ((c->W0 + 31) / 32);
+            int K = (smax + 31) / 32;
+            if (K < 1)
+                K = 1;
+            int g = grid_for(words);
+            switch (K)
+            {
+            case 1:
+                if (smax <= 31)
+                    inflate_kernel<1, true><<<g, 256, 0, st>>>(c->raw_bits, c->infl_bits, c->H0, c->W0, c->pitch0, smax);
+                else
+                    inflate_kernel<1, false><<<g, 256, 0, st>>>(c->raw_bits, c->infl_bits, c->H0, c->W0, c->pitch0, smax);
+                break;
+            case 2:
+                inflate_kernel<2, false><<<g, 256, 0, st>>>(c->raw_bits, c->infl_bits, c->H0, c->W0, c->pitch0, smax);
+                break;
+            case 3:
+            case 4:
+                inflate_kernel<4, false><<<g, 256, 0, st>>>(c->raw_bits, c->infl_bits, c->H0, c->W0, c->pitch0, smax);
+                break;
+            default:
+                inflate_kernel<8, false><<<g, 256, 0, st>>>(c->raw_bits, c->infl_bits, c->H0, c->W0, c->pitch0, smax);
+                break;
+            }
+            MPROS_LAUNCH_CHECK(c);
+        }
+    }
+    // the reference sets get_map_ at the very end but the sub-steps below only need the geometry
+    c->get_map = true;
+    if (c->planner_configured)
+    {
+        int rc = mpros_planner_config(static_cast<mpros_ctx *>(c), &c->pp); // n_check depends on the resolution
+        if (rc)
+            return rc;
+    }
+    // nav_map.cpp:150-156
+    if (c->get_goal)
+    {
+        int rc = map_build_goal(c);
+        if (rc)
+            return rc;
+    }
+    int rc = map_build_voronoi(c);
+    if (rc)
+        return rc;
+    MPROS_CUDA(cudaStreamSynchronize(st));
+    return MPROS_OK;
+}
+
+} // namespace mpros
+
+using namespace mpros;
+
+extern "C" int mpros_map_set_occupancy_dev(mpros_ctx *c, const int8_t *d_data, int width, int height, double resolution,
+                                           double ox, double oy, double oyaw)
+{
+    if (!c || !d_data || width <= 0 || height <= 0 || !(resolution > 0))
+    {
+        set_error("mpros_map_set_occupancy: invalid argument");
+        return MPROS_ERR_INVALID;
+    }
+    MPROS_CUDA(cudaSetDevice(c->device));
+    return set_occupancy_impl(c, d_data, width, height, resolution, ox, oy, oyaw);
+}
+
+extern "C" int mpros_map_set_occupancy(mpros_ctx *c, const int8_t *data, int width, int height, double resolution, double ox,
+                                       double oy, double oyaw)
+{
+    if (!c || !data || width <= 0 || height <= 0 || !(resolution > 0))
+    {
+        set_error("mpros_map_set_occupancy: invalid argument");
+        return MPROS_ERR_INVALID;
+    }
+    MPROS_CUDA(cudaSetDevice(c->device));
+    size_t bytes = (size_t)width * height;
+    int rc = ensure_stage(c, bytes);
+    if (rc)
+        return rc;
+    MPROS_CUDA(cudaMemcpyAsync(c->stage, data, bytes, cudaMemcpyHostToDevice, c->stream));
+    return set_occupancy_impl(c, static_cast<const int8_t *>(c->stage), width, height, resolution, ox, oy, oyaw);
+}
+
+extern "C" int mpros_map_get_info(mpros_ctx *c, mpros_map_info *o)
+{
+    if (!c || !o)
+    {
+        set_error("mpros_map_get_info: NULL argument");
+        return MPROS_ERR_INVALID;
+    }
+    std::memset(o, 0, sizeof(*o));
+    o->get_map = c->get_map;
+    o->get_goal = c->get_goal;
+    o->map_height = c->H;
+    o->map_width = c->W;
+    o->map_height_orig = c->H0;
+    o->map_width_orig = c->W0;
+    o->map_resolution = c->res;
+    o->map_resolution_orig = c->res0;
+    o->map_origin_x = c->ox;
+    o->map_origin_y = c->oy;
+    o->map_origin_yaw = c->oyaw;
+    o->map_origin_sin = c->osin;
+    o->map_origin_cos = c->ocos;
+    // nav_map.cpp:74-77
+    o->x_max = c->ox + c->res0 * c->W0;
+    o->x_min = c->ox;
+    o->y_max = c->oy + c->res0 * c->H0;
+    o->y_min = c->oy;
+    o->num_regions = c->num_regions;
+    return MPROS_OK;
+}
+
+extern "C" int mpros_map_download(mpros_ctx *c, int layer, void *dst, size_t dst_bytes)
+{
+    if (!c || !dst)
+    {
+        set_error("mpros_map_download: NULL argument");
+        return MPROS_ERR_INVALID;
+    }
+    if (!c->get_map)
+    {
+        set_error("mpros_map_download: no map set");
+        return MPROS_ERR_INVALID;
+    }
+    MPROS_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t cells0 = (size_t)c->H0 * c->W0, cells = (size_t)c->H * c->W;
+    size_t need = 0;
+    const void *src = nullptr;
+    switch (layer)
+    {
+    case MPROS_LAYER_STATIC_ORIG:
+    case MPROS_LAYER_INFLATE_ORIG:
+    case MPROS_LAYER_STATIC:
+    case MPROS_LAYER_ISEDGE:
+    {
+        bool orig = (layer == MPROS_LAYER_STATIC_ORIG || layer == MPROS_LAYER_INFLATE_ORIG);
+        need = orig ? cells0 : cells;
+        if (dst_bytes < need)
+            break;
+        int rc = ensure_scratch(c, need);
+        if (rc)
+            return rc;
+        const uint32_t *bits = layer == MPROS_LAYER_STATIC_ORIG ? c->raw_bits
+                               : layer == MPROS_LAYER_INFLATE_ORIG ? c->infl_bits
+                               : layer == MPROS_LAYER_STATIC ? c->ds_bits
+                                                             : c->edge_bits;
+        unpack_bits_kernel<<<grid_for(need), 256, 0, st>>>(bits, orig ? c->H0 : c->H, orig ? c->W0 : c->W,
+                                                          orig ? c->pitch0 : c->pitch, static_cast<int8_t *>(c->scratch));
+        MPROS_LAUNCH_CHECK(c);
+        src = c->scratch;
+        break;
+    }
+    case MPROS_LAYER_GOAL:
+    case MPROS_LAYER_OBS_DIST:
+    case MPROS_LAYER_EDGE_DIST:
+    {
+        need = cells * 4;
+        if (dst_bytes < need)
+            break;
+        if (layer == MPROS_LAYER_GOAL && !c->get_goal)
+        {
+            set_error("mpros_map_download: goal map not generated (no goal set or goal outside the map)");
+            return MPROS_ERR_INVALID;
+        }
+        int rc = ensure_scratch(c, need);
+        if (rc)
+            return rc;
+        const uint16_t *in = layer == MPROS_LAYER_GOAL ? c->goal : layer == MPROS_LAYER_OBS_DIST ? c->obs_dist : c->edge_dist;
+        widen_u16_kernel<<<grid_for(cells), 256, 0, st>>>(in, cells, static_cast<int32_t *>(c->scratch));
+        MPROS_LAUNCH_CHECK(c);
+        src = c->scratch;
+        break;
+    }
+    case MPROS_LAYER_REGION:
+        need = cells * 4;
+        src = c->region;
+        break;
+    case MPROS_LAYER_VORONOI:
+        need = cells * 4;
+        src = c->voronoi;
+        break;
+    default:
+        set_error("mpros_map_download: unknown layer");
+        return MPROS_ERR_INVALID;
+    }
+    if (dst_bytes < need)
+    {
+        set_error("mpros_map_download: destination buffer too small");
+        return MPROS_ERR_CAPACITY;
+    }
+    MPROS_CUDA(cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, st));
+    MPROS_CUDA(cudaStreamSynchronize(st));
+    return MPROS_OK;
+}
+
+extern "C" int mpros_map_point_in_collision(mpros_ctx *c, int layer, const int32_t *ij, size_t n, uint8_t *out)
+{
+    if (!c || (!ij && n) || (!out && n))
+    {
+        set_error("mpros_map_point_in_collision: NULL argument");
+        return MPROS_ERR_INVALID;
+    }
+    if (!c->get_map)
+    {
+        set_error("mpros_map_point_in_collision: no map set");
+        return MPROS_ERR_INVALID;
+    }
+    if (n == 0)
+        return MPROS_OK;
+    const uint32_t *bits;
+    int H, W, pitch;
+    if (layer == MPROS_LAYER_STATIC)
+        bits = c->ds_bits, H = c->H, W = c->W, pitch = c->pitch;
+    else if (layer == MPROS_LAYER_STATIC_ORIG)
+        bits = c->raw_bits, H = c->H0, W = c->W0, pitch = c->pitch0;
+    else if (layer == MPROS_LAYER_INFLATE_ORIG)
+        bits = c->infl_bits, H = c->H0, W = c->W0, pitch = c->pitch0;
+    else
+    {
+        set_error("mpros_map_point_in_collision: layer must be STATIC, STATIC_ORIG or INFLATE_ORIG");
+        return MPROS_ERR_INVALID;
+    }
+    MPROS_CUDA(cudaSetDevice(c->device));
+    size_t in_bytes = n * 8, total = in_bytes + n;
+    int rc = ensure_stage(c, total);
+    if (rc)
+        return rc;
+    int32_t *d_ij = static_cast<int32_t *>(c->stage);
+    uint8_t *d_out = reinterpret_cast<uint8_t *>(c->stage) + in_bytes;
+    MPROS_CUDA(cudaMemcpyAsync(d_ij, ij, in_bytes, cudaMemcpyHostToDevice, c->stream));
+    point_lookup_kernel<<<grid_for(n), 256, 0, c->stream>>>(bits, H, W, pitch, d_ij, n, d_out);
+    MPROS_LAUNCH_CHECK(c);
+    MPROS_CUDA(cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, c->stream));
+    MPROS_CUDA(cudaStreamSynchronize(c->stream));
+    return MPROS_OK;
+}

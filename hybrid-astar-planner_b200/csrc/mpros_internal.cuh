@@ -1,0 +1,142 @@
+// Internal definitions shared by the CUDA translation units of libmpros_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "mpros_gpu.h"
+
+namespace mpros
+{
+
+constexpr int kHugeInt = 1000; // HUGE_INT, mpros_navigation_map/node.h:4
+
+// ---- HBM layout of one map (all device pointers) -------------------------------------------------------
+// Occupancy layers are BIT-PACKED: bit (j & 31) of word [i * pitch + (j >> 5)] is cell (i, j); bits past
+// the row end are zero. 8192^2 -> 8 MiB per layer, so the two collision layers stay resident in the
+// 126 MB L2 together with everything else. Row pitch is a multiple of 4 words (16 B) so rows can be
+// moved with 128-bit accesses. Byte/int layers in the reference's types exist only transiently, when a
+// caller asks for them through mpros_map_download.
+struct MapView
+{
+    const uint32_t *raw_bits;  // static_map_orig_      [H0 x pitch0]
+    const uint32_t *infl_bits; // inflate_map_orig_     [H0 x pitch0]
+    const uint32_t *ds_bits;   // static_map_           [H  x pitch ]
+    const float *voronoi;      // voronoi_value_map_    [H*W]
+    const uint16_t *goal;      // goal_cost_map_ as u16 [H*W] (single-goal context map)
+    int H0, W0, pitch0;
+    int H, W, pitch;
+    double ox, oy, osin, ocos; // map_origin_x_/y_/sin_/cos_
+    double res0, res;          // map_resolution_orig_, map_resolution_
+};
+
+// ---- per-planner constants (HybridAstar::config / setFootprint, hybrid_a_star.cpp:120-206) -----------
+constexpr int kMaxSteer = 16; // steer_set_ entries
+struct PlannerView
+{
+    // footprint_longi_ x-coordinates (y = 0) and footprint_m_ corners, hybrid_a_star.cpp:193-199
+    double longi_x0, longi_x1;
+    double corner_x[4], corner_y[4];
+    int n_check; // num_checking_step = ceil((L - W) / res_orig), hybrid_a_star.cpp:633
+    // expansion
+    int n_steer; // steer_set_.size()
+    double steer_set[kMaxSteer];
+    double step_size, arc_radius_num; // arc radius numerator: wheelbase/2 + offset (hybrid_a_star.cpp:339)
+    double pen_gear, pen_back, pen_steer, pen_steer_change;
+    double min_r, max_steer, rs_range;
+    int num_yaw;
+    double yaw_resol;
+    int max_iteration;
+};
+
+struct Ctx
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+
+    mpros_map_params mp;
+    mpros_planner_params pp;
+    bool planner_configured = false;
+
+    // NavMap public state
+    bool get_map = false, get_goal = false;
+    int H0 = 0, W0 = 0, pitch0 = 0, H = 0, W = 0, pitch = 0;
+    double res0 = 0, res = 0, ox = 0, oy = 0, oyaw = 0, osin = 0, ocos = 1;
+    double goal_x = 0, goal_y = 0;
+    int num_regions = 0;
+
+    // device buffers
+    uint32_t *raw_bits = nullptr, *infl_bits = nullptr, *ds_bits = nullptr;
+    uint16_t *goal = nullptr, *obs_dist = nullptr, *edge_dist = nullptr;
+    int32_t *region = nullptr;
+    uint32_t *edge_bits = nullptr;
+    float *voronoi = nullptr;
+    size_t cap0_words = 0, cap_words = 0, cap_cells = 0;
+    // generic scratch
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+    void *stage = nullptr; // device staging for host-pointer entry points
+    size_t stage_bytes = 0;
+
+    PlannerView pv;
+
+    MapView view() const
+    {
+        MapView v;
+        v.raw_bits = raw_bits;
+        v.infl_bits = infl_bits;
+        v.ds_bits = ds_bits;
+        v.voronoi = voronoi;
+        v.goal = goal;
+        v.H0 = H0;
+        v.W0 = W0;
+        v.pitch0 = pitch0;
+        v.H = H;
+        v.W = W;
+        v.pitch = pitch;
+        v.ox = ox;
+        v.oy = oy;
+        v.osin = osin;
+        v.ocos = ocos;
+        v.res0 = res0;
+        v.res = res;
+        return v;
+    }
+};
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+int ensure_scratch(Ctx *c, size_t bytes);
+int ensure_stage(Ctx *c, size_t bytes);
+
+#define MPROS_CUDA(expr)                                                   \
+    do                                                                     \
+    {                                                                      \
+        cudaError_t e_ = (expr);                                           \
+        if (e_ != cudaSuccess)                                             \
+            return ::mpros::cuda_fail(e_, #expr, __FILE__, __LINE__);      \
+    } while (0)
+
+#define MPROS_LAUNCH_CHECK(c)                                              \
+    do                                                                     \
+    {                                                                      \
+        (c)->launches++;                                                   \
+        cudaError_t e_ = cudaGetLastError();                               \
+        if (e_ != cudaSuccess)                                             \
+            return ::mpros::cuda_fail(e_, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+inline int pitch_words(int width) { return ((width + 31) / 32 + 3) & ~3; }
+inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// stage entry points implemented in the other translation units
+int map_build_voronoi(Ctx *c);          // N5-N9, voronoi.cu
+int map_build_goal(Ctx *c);             // N4, goal_map.cu
+
+} // namespace mpros
+
+struct mpros_ctx : public mpros::Ctx
+{
+};

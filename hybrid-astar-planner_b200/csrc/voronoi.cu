@@ -1,0 +1,488 @@
+// N5-N9: NavMap::generateVoronoiMap (nav_map.cpp:541-590) on the down-sampled grid.
+//
+//   N5 markObs/floodFillObs (:384-432)  4-connected components of occupied cells, label = rank of the component's
+//                                       first cell in raster order           -> union-find (min-index root) + rank
+//   N6 calObsDist (:434-473)            L1 distance to the nearest in-map occupied cell, cap 999 (else 1000), and
+//                                       the region of a nearest obstacle      -> separable (dist,region) min-plus
+//   N7 findEdge (:475-507)              cells where the nearest-obstacle region changes
+//   N8 calEdgeDist (:509-539)           L1 distance to the nearest edge cell through ALL cells, cap 999
+//   N9 cost loop (:565-582)             float Voronoi-field cost
+//
+// Order-dependent parts of the reference (broken heap) are replaced by canonical, order-free
+// rules: region_ of a free cell = the SMALLEST region id among all nearest obstacle cells (the reference always
+// holds *a* nearest region); obstacle-side edge flags follow the "first differing neighbour" rule without the
+// processing-order condition. obs_dist_ is order-independent and bit-exact.
+#include "mpros_internal.cuh"
+
+namespace mpros
+{
+
+constexpr unsigned long long kOne = 1ull << 32;          // +1 distance in a packed (dist<<32 | region) key
+constexpr unsigned long long kInfKey = (1ull << 24) << 32; // "no source seen yet"
+constexpr int kScanWords = (kHugeInt + 31) / 32 + 1;      // sources further than 999 cells can never matter
+
+// ---- N5 ------------------------------------------------------------------------------------------------
+// start column of the horizontal run of set bits that contains (i, j); bit (i, j) must be set
+__device__ __forceinline__ int run_start(const uint32_t *__restrict__ row, int j)
+{
+    int w = j >> 5, b = j & 31;
+    uint32_t z = ~row[w] & ((b == 31) ? 0x7fffffffu : ((1u << b) - 1u)); // zero bits strictly below b
+    z &= (1u << b) - 1u;
+    if (z)
+        return (w << 5) + (32 - __clz(z));
+    for (--w; w >= 0; --w)
+    {
+        uint32_t zz = ~row[w];
+        if (zz)
+            return (w << 5) + (32 - __clz(zz));
+    }
+    return 0;
+}
+
+__device__ __forceinline__ int uf_find(const int *parent, int a)
+{
+    int p = parent[a];
+    while (p != a)
+    {
+        a = p;
+        p = parent[a];
+    }
+    return a;
+}
+
+__device__ __forceinline__ void uf_union(int *parent, int a, int b)
+{
+    while (true)
+    {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b)
+            return;
+        if (a < b)
+        {
+            int t = a;
+            a = b;
+            b = t;
+        }
+        int old = atomicMin(&parent[a], b); // hook the larger root under the smaller one
+        if (old == a)
+            return;
+        a = old;
+    }
+}
+
+// parent[k] = linear index of the start of k's horizontal run (occupied cells), -1 for free cells
+__global__ void __launch_bounds__(256) ccl_init_kernel(const uint32_t *__restrict__ occ, int H, int W, int pitch,
+                                                       int *__restrict__ parent)
+{
+    size_t total = (size_t)H * W;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x)
+    {
+        int i = (int)(k / W), j = (int)(k % W);
+        const uint32_t *row = occ + (size_t)i * pitch;
+        bool o = (row[j >> 5] >> (j & 31)) & 1u;
+        parent[k] = o ? i * W + run_start(row, j) : -1;
+    }
+}
+
+// merge vertically adjacent runs; one union per contact segment (its left-most column)
+__global__ void __launch_bounds__(256) ccl_merge_kernel(const uint32_t *__restrict__ occ, int H, int W, int pitch,
+                                                        int *__restrict__ parent)
+{
+    size_t total = (size_t)H * W;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x)
+    {
+        int i = (int)(k / W), j = (int)(k % W);
+        if (i == 0)
+            continue;
+        const uint32_t *row = occ + (size_t)i * pitch, *up = row - pitch;
+        bool o = (row[j >> 5] >> (j & 31)) & 1u, u = (up[j >> 5] >> (j & 31)) & 1u;
+        if (!(o && u))
+            continue;
+        if (j > 0)
+        {
+            bool ol = (row[(j - 1) >> 5] >> ((j - 1) & 31)) & 1u, ul = (up[(j - 1) >> 5] >> ((j - 1) & 31)) & 1u;
+            if (ol && ul)
+                continue; // same contact segment as the cell to the left
+        }
+        uf_union(parent, (int)k, (int)k - W);
+    }
+}
+
+// flatten + count roots per 1024-cell tile; local rank of every root inside its tile
+__global__ void __launch_bounds__(1024) ccl_flatten_rank_kernel(int *__restrict__ parent, size_t total, int *__restrict__ local_rank,
+                                                                int *__restrict__ tile_count)
+{
+    __shared__ int warp_sum[32];
+    size_t k = (size_t)blockIdx.x * 1024 + threadIdx.x;
+    bool root = false;
+    if (k < total)
+    {
+        int p = parent[k];
+        if (p >= 0)
+        {
+            p = uf_find(parent, (int)k);
+            root = ((size_t)p == k);
+        }
+        // flattening is finished by ccl_region_kernel (roots are stable here, chains still may exist)
+    }
+    unsigned bal = __ballot_sync(0xffffffffu, root);
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0)
+        warp_sum[wid] = __popc(bal);
+    __syncthreads();
+    if (wid == 0)
+    {
+        int v = warp_sum[lane];
+        int incl = v;
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o)
+                incl += t;
+        }
+        warp_sum[lane] = incl - v; // exclusive
+        if (lane == 31)
+            tile_count[blockIdx.x] = incl;
+    }
+    __syncthreads();
+    if (root)
+        local_rank[k] = warp_sum[wid] + __popc(bal & ((1u << lane) - 1u));
+}
+
+// exclusive scan of tile counts by one block; total written to *n_regions
+__global__ void __launch_bounds__(1024) scan_tiles_kernel(int *__restrict__ tile_count, int n_tiles, int *__restrict__ n_regions)
+{
+    __shared__ int part[1024];
+    int t = threadIdx.x;
+    int chunk = (n_tiles + 1023) / 1024;
+    int b = t * chunk, e = min(n_tiles, b + chunk);
+    int s = 0;
+    for (int k = b; k < e; ++k)
+        s += tile_count[k];
+    part[t] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1)
+    {
+        int v = (t >= o) ? part[t - o] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    int run = part[t] - s;
+    for (int k = b; k < e; ++k)
+    {
+        int v = tile_count[k];
+        tile_count[k] = run;
+        run += v;
+    }
+    if (t == 1023)
+        *n_regions = part[1023];
+}
+
+__global__ void __launch_bounds__(256) ccl_region_kernel(const int *__restrict__ parent, size_t total, const int *__restrict__ local_rank,
+                                                         const int *__restrict__ tile_offset, int *__restrict__ region)
+{
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x)
+    {
+        int p = parent[k];
+        int r = -1;
+        if (p >= 0)
+        {
+            int root = uf_find(parent, (int)k);
+            r = tile_offset[root >> 10] + local_rank[root];
+        }
+        region[k] = r;
+    }
+}
+
+// ---- N6 / N8: separable L1 distance transform carrying the source label -------------------------------------
+// Row pass: for every cell the nearest source in its own row (left or right), as key = dist<<32 | label; ties take
+// the smaller label. label == nullptr -> label 0 (plain distance).
+__global__ void __launch_bounds__(256) dt_row_kernel(const uint32_t *__restrict__ src, int H, int W, int pitch,
+                                                     const int *__restrict__ label, unsigned long long *__restrict__ key)
+{
+    size_t total = (size_t)H * W;
+    const int wpr = (W + 31) >> 5;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x)
+    {
+        int i = (int)(k / W), j = (int)(k % W);
+        const uint32_t *row = src + (size_t)i * pitch;
+        int w = j >> 5, b = j & 31;
+        uint32_t cur = row[w];
+        unsigned long long best = kInfKey;
+        if ((cur >> b) & 1u)
+            best = label ? (unsigned long long)(unsigned)label[k] : 0ull;
+        else
+        {
+            // nearest set bit to the left
+            int jl = -1;
+            uint32_t m = cur & ((1u << b) - 1u);
+            if (m)
+                jl = (w << 5) + 31 - __clz(m);
+            else
+                for (int ww = w - 1; ww >= 0 && ww >= w - kScanWords; --ww)
+                {
+                    uint32_t v = row[ww];
+                    if (v)
+                    {
+                        jl = (ww << 5) + 31 - __clz(v);
+                        break;
+                    }
+                }
+            // nearest set bit to the right
+            int jr = -1;
+            m = (b == 31) ? 0u : (cur & ~((2u << b) - 1u));
+            if (m)
+                jr = (w << 5) + __ffs(m) - 1;
+            else
+                for (int ww = w + 1; ww < wpr && ww <= w + kScanWords; ++ww)
+                {
+                    uint32_t v = row[ww];
+                    if (v)
+                    {
+                        jr = (ww << 5) + __ffs(v) - 1;
+                        break;
+                    }
+                }
+            if (jl >= 0)
+            {
+                unsigned long long lab = label ? (unsigned long long)(unsigned)label[(size_t)i * W + jl] : 0ull;
+                best = ((unsigned long long)(j - jl) << 32) | lab;
+            }
+            if (jr >= 0)
+            {
+                unsigned long long lab = label ? (unsigned long long)(unsigned)label[(size_t)i * W + jr] : 0ull;
+                unsigned long long kr = ((unsigned long long)(jr - j) << 32) | lab;
+                best = kr < best ? kr : best;
+            }
+        }
+        key[k] = best;
+    }
+}
+
+// Column pass: one thread per column, forward then backward sweep of key = min(key, neighbour + 1).
+// Loads do not depend on the recurrence, so the unrolled loop keeps several rows in flight.
+__global__ void __launch_bounds__(128) dt_col_kernel(unsigned long long *__restrict__ key, int H, int W)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= W)
+        return;
+    unsigned long long cur = kInfKey;
+#pragma unroll 8
+    for (int i = 0; i < H; ++i)
+    {
+        unsigned long long v = key[(size_t)i * W + j];
+        cur += kOne;
+        cur = v < cur ? v : cur;
+        key[(size_t)i * W + j] = cur;
+    }
+    cur = kInfKey;
+#pragma unroll 8
+    for (int i = H - 1; i >= 0; --i)
+    {
+        unsigned long long v = key[(size_t)i * W + j];
+        cur += kOne;
+        cur = v < cur ? v : cur;
+        key[(size_t)i * W + j] = cur;
+    }
+}
+
+// N6 epilogue: cap (>= 1000 stays 1000 / region -1), keep obstacle cells' own labels
+__global__ void __launch_bounds__(256) obs_finish_kernel(const unsigned long long *__restrict__ key, size_t total,
+                                                         uint16_t *__restrict__ obs_dist, int *__restrict__ region)
+{
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x)
+    {
+        unsigned long long v = key[k];
+        unsigned d = (unsigned)(v >> 32);
+        if (d >= (unsigned)kHugeInt)
+        {
+            obs_dist[k] = (uint16_t)kHugeInt;
+            region[k] = -1;
+        }
+        else
+        {
+            obs_dist[k] = (uint16_t)d;
+            region[k] = (int)(unsigned)(v & 0xffffffffull);
+        }
+    }
+}
+__global__ void __launch_bounds__(256) edge_finish_kernel(const unsigned long long *__restrict__ key, size_t total,
+                                                          uint16_t *__restrict__ edge_dist)
+{
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x)
+    {
+        unsigned d = (unsigned)(key[k] >> 32);
+        edge_dist[k] = (uint16_t)(d >= (unsigned)kHugeInt ? kHugeInt : d);
+    }
+}
+
+// ---- N7 -------------------------------------------------------------------------------------------------
+// A reached free cell (obs_dist < 1000, not occupied) is an edge iff some in-map 4-neighbour has a different
+// region. Any other cell (obstacle, unreached) is an edge iff it is the FIRST differing neighbour, in the order
+// up (i-1), right (j+1), down (i+1), left (j-1) of nav_map.cpp:351-382, of some reached free neighbour.
+__device__ __forceinline__ int first_differing(const int *__restrict__ region, int H, int W, int i, int j, int r)
+{
+    if (i - 1 >= 0 && region[(size_t)(i - 1) * W + j] != r)
+        return 0;
+    if (j + 1 < W && region[(size_t)i * W + j + 1] != r)
+        return 1;
+    if (i + 1 < H && region[(size_t)(i + 1) * W + j] != r)
+        return 2;
+    if (j - 1 >= 0 && region[(size_t)i * W + j - 1] != r)
+        return 3;
+    return -1;
+}
+
+__global__ void __launch_bounds__(256) edge_kernel(const uint32_t *__restrict__ occ, const uint16_t *__restrict__ obs_dist,
+                                                   const int *__restrict__ region, int H, int W, int pitch,
+                                                   uint32_t *__restrict__ edge_bits)
+{
+    const int wpr = (W + 31) >> 5;
+    const size_t total_words = (size_t)H * wpr;
+    const int lane = threadIdx.x & 31;
+    size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t wd = warp; wd < total_words; wd += nwarps)
+    {
+        int i = (int)(wd / wpr), w = (int)(wd % wpr);
+        int j = (w << 5) + lane;
+        bool e = false;
+        if (j < W)
+        {
+            size_t k = (size_t)i * W + j;
+            bool o = (occ[(size_t)i * pitch + w] >> lane) & 1u;
+            bool reached_free = !o && obs_dist[k] < kHugeInt;
+            int r = region[k];
+            if (reached_free)
+                e = first_differing(region, H, W, i, j, r) >= 0;
+            else
+            {
+                // am I the first differing neighbour of a reached free neighbour? (my direction seen from it)
+                const int di[4] = {1, 0, -1, 0}, dj[4] = {0, -1, 0, 1}; // neighbour n such that I am n's up/right/down/left
+#pragma unroll
+                for (int d = 0; d < 4; ++d)
+                {
+                    int ni = i + di[d], nj = j + dj[d];
+                    if (ni < 0 || ni >= H || nj < 0 || nj >= W)
+                        continue;
+                    size_t nk = (size_t)ni * W + nj;
+                    bool no = (occ[(size_t)ni * pitch + (nj >> 5)] >> (nj & 31)) & 1u;
+                    if (no || obs_dist[nk] >= kHugeInt)
+                        continue;
+                    if (first_differing(region, H, W, ni, nj, region[nk]) == d)
+                        e = true;
+                }
+            }
+        }
+        uint32_t word = __ballot_sync(0xffffffffu, e);
+        if (lane == 0)
+            edge_bits[(size_t)i * pitch + w] = word;
+    }
+}
+
+// ---- N9 -------------------------------------------------------------------------------------------------
+// occupied -> 1; edge -> 0; else (a/(a+do)) * (de/(de+do)) * (do-dmax) * (do-dmax) / dmax / dmax, evaluated left
+// to right in float exactly as nav_map.cpp:577-580 (library is compiled with --fmad=false).
+__global__ void __launch_bounds__(256) voronoi_cost_kernel(const uint32_t *__restrict__ occ, const uint32_t *__restrict__ edge_bits,
+                                                           const uint16_t *__restrict__ obs_dist, const uint16_t *__restrict__ edge_dist,
+                                                           int H, int W, int pitch, float alpha, float dmax, float *__restrict__ cost)
+{
+    size_t total = (size_t)H * W;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x)
+    {
+        int i = (int)(k / W), j = (int)(k % W);
+        size_t wi = (size_t)i * pitch + (j >> 5);
+        float c;
+        if ((occ[wi] >> (j & 31)) & 1u)
+            c = 1.0f;
+        else if ((edge_bits[wi] >> (j & 31)) & 1u)
+            c = 0.0f;
+        else
+        {
+            int dob = obs_dist[k], de = edge_dist[k];
+            float fo = (float)dob;
+            float a = alpha / (alpha + fo);
+            float b = (float)de / (float)(de + dob);
+            float t = a * b;
+            t = t * (fo - dmax);
+            t = t * (fo - dmax);
+            t = t / dmax;
+            t = t / dmax;
+            c = t;
+        }
+        cost[k] = c;
+    }
+}
+
+static int grid_for(size_t items, int block = 256)
+{
+    size_t g = (items + block - 1) / block;
+    if (g > 148 * 16)
+        g = 148 * 16;
+    if (g < 1)
+        g = 1;
+    return (int)g;
+}
+
+int map_build_voronoi(Ctx *c)
+{
+    cudaStream_t st = c->stream;
+    const int H = c->H, W = c->W, pitch = c->pitch;
+    const size_t cells = (size_t)H * W;
+    const int n_tiles = (int)((cells + 1023) / 1024);
+    // scratch: key u64[cells] | parent i32[cells] | local_rank i32[cells] | tile_count i32[n_tiles] | n_regions
+    size_t need = cells * 8 + cells * 4 * 2 + (size_t)n_tiles * 4 + 64;
+    int rc = ensure_scratch(c, need);
+    if (rc)
+        return rc;
+    unsigned long long *key = static_cast<unsigned long long *>(c->scratch);
+    int *parent = reinterpret_cast<int *>(key + cells);
+    int *local_rank = parent + cells;
+    int *tile_count = local_rank + cells;
+    int *d_nreg = tile_count + n_tiles;
+
+    // N5
+    ccl_init_kernel<<<grid_for(cells), 256, 0, st>>>(c->ds_bits, H, W, pitch, parent);
+    MPROS_LAUNCH_CHECK(c);
+    ccl_merge_kernel<<<grid_for(cells), 256, 0, st>>>(c->ds_bits, H, W, pitch, parent);
+    MPROS_LAUNCH_CHECK(c);
+    ccl_flatten_rank_kernel<<<n_tiles, 1024, 0, st>>>(parent, cells, local_rank, tile_count);
+    MPROS_LAUNCH_CHECK(c);
+    scan_tiles_kernel<<<1, 1024, 0, st>>>(tile_count, n_tiles, d_nreg);
+    MPROS_LAUNCH_CHECK(c);
+    ccl_region_kernel<<<grid_for(cells), 256, 0, st>>>(parent, cells, local_rank, tile_count, c->region);
+    MPROS_LAUNCH_CHECK(c);
+    MPROS_CUDA(cudaMemcpyAsync(&c->num_regions, d_nreg, sizeof(int), cudaMemcpyDeviceToHost, st));
+
+    // N6
+    dt_row_kernel<<<grid_for(cells), 256, 0, st>>>(c->ds_bits, H, W, pitch, c->region, key);
+    MPROS_LAUNCH_CHECK(c);
+    dt_col_kernel<<<cdiv(W, 128), 128, 0, st>>>(key, H, W);
+    MPROS_LAUNCH_CHECK(c);
+    obs_finish_kernel<<<grid_for(cells), 256, 0, st>>>(key, cells, c->obs_dist, c->region);
+    MPROS_LAUNCH_CHECK(c);
+
+    // N7
+    size_t words = (size_t)H * ((W + 31) / 32);
+    MPROS_CUDA(cudaMemsetAsync(c->edge_bits, 0, (size_t)H * pitch * 4, st));
+    edge_kernel<<<grid_for(words * 32), 256, 0, st>>>(c->ds_bits, c->obs_dist, c->region, H, W, pitch, c->edge_bits);
+    MPROS_LAUNCH_CHECK(c);
+
+    // N8
+    dt_row_kernel<<<grid_for(cells), 256, 0, st>>>(c->edge_bits, H, W, pitch, nullptr, key);
+    MPROS_LAUNCH_CHECK(c);
+    dt_col_kernel<<<cdiv(W, 128), 128, 0, st>>>(key, H, W);
+    MPROS_LAUNCH_CHECK(c);
+    edge_finish_kernel<<<grid_for(cells), 256, 0, st>>>(key, cells, c->edge_dist);
+    MPROS_LAUNCH_CHECK(c);
+
+    // N9
+    voronoi_cost_kernel<<<grid_for(cells), 256, 0, st>>>(c->ds_bits, c->edge_bits, c->obs_dist, c->edge_dist, H, W, pitch,
+                                                        c->mp.voro_fallout_rate, c->mp.voro_max_region, c->voronoi);
+    MPROS_LAUNCH_CHECK(c);
+    return MPROS_OK;
+}
+
+} // namespace mpros

@@ -1,0 +1,273 @@
+"""ctypes binding of libmpros_b200.so (include/mpros_gpu.h) — the host-side handle used by tests/ and bench.py.
+
+There is no CPU fallback: if the CUDA library is missing or no CUDA device is present every call raises.
+The C++ façade with the reference's class names (NavMap / HybridAstar / RS::RSCurve) lives in host/.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmpros_b200.so")
+
+LAYERS = {
+    "static_orig": (0, np.int8, True),
+    "static": (1, np.int8, False),
+    "inflate_orig": (2, np.int8, True),
+    "goal": (3, np.int32, False),
+    "obs_dist": (4, np.int32, False),
+    "region": (5, np.int32, False),
+    "isedge": (6, np.uint8, False),
+    "edge_dist": (7, np.int32, False),
+    "voronoi": (8, np.float32, False),
+}
+
+
+class MapParams(C.Structure):
+    _fields_ = [
+        ("occupied_thresh", C.c_double),
+        ("free_thresh", C.c_double),
+        ("voro_fallout_rate", C.c_float),
+        ("voro_max_region", C.c_float),
+        ("downsampling_factor", C.c_int),
+        ("obstacle_inflation_radius", C.c_double),
+    ]
+
+
+class PlannerParams(C.Structure):
+    _fields_ = [
+        ("max_curvature", C.c_double),
+        ("width", C.c_double),
+        ("wheelbase", C.c_double),
+        ("length", C.c_double),
+        ("steer_offset", C.c_double),
+        ("max_steering_angle", C.c_double),
+        ("gear_penalty", C.c_double),
+        ("reverse_penalty", C.c_double),
+        ("steering_penalty", C.c_double),
+        ("steering_change_penalty", C.c_double),
+        ("analytic_solution_range", C.c_double),
+        ("yaw_discretization", C.c_int),
+        ("step_size", C.c_double),
+        ("path_point_distance", C.c_double),
+        ("steering_discretization", C.c_int),
+        ("max_iteration", C.c_int),
+        ("optimal_path", C.c_int),
+        ("interpolation_enable", C.c_int),
+    ]
+
+
+class MapInfo(C.Structure):
+    _fields_ = [
+        ("get_map", C.c_int),
+        ("get_goal", C.c_int),
+        ("map_height", C.c_int),
+        ("map_width", C.c_int),
+        ("map_height_orig", C.c_int),
+        ("map_width_orig", C.c_int),
+        ("map_resolution", C.c_double),
+        ("map_resolution_orig", C.c_double),
+        ("map_origin_x", C.c_double),
+        ("map_origin_y", C.c_double),
+        ("map_origin_yaw", C.c_double),
+        ("map_origin_sin", C.c_double),
+        ("map_origin_cos", C.c_double),
+        ("x_max", C.c_double),
+        ("x_min", C.c_double),
+        ("y_max", C.c_double),
+        ("y_min", C.c_double),
+        ("num_regions", C.c_int),
+    ]
+
+
+class MprosError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(path=LIB_PATH):
+    """Load libmpros_b200.so; raises (loudly) when the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise MprosError("CUDA extension missing: %s (run __graft_entry__.build()); there is no CPU fallback" % path)
+    L = C.CDLL(path)
+    vp, i, d, sz = C.c_void_p, C.c_int, C.c_double, C.c_size_t
+    L.mpros_ctx_create.argtypes = [i, C.POINTER(vp)]
+    L.mpros_ctx_destroy.argtypes = [vp]
+    L.mpros_last_error_string.restype = C.c_char_p
+    L.mpros_ctx_stream.restype = vp
+    L.mpros_ctx_stream.argtypes = [vp]
+    L.mpros_ctx_synchronize.argtypes = [vp]
+    L.mpros_ctx_launch_count.restype = C.c_uint64
+    L.mpros_ctx_launch_count.argtypes = [vp]
+    L.mpros_map_params_default.argtypes = [C.POINTER(MapParams)]
+    L.mpros_map_params_default.restype = None
+    L.mpros_planner_params_default.argtypes = [C.POINTER(PlannerParams)]
+    L.mpros_planner_params_default.restype = None
+    L.mpros_map_config.argtypes = [vp, C.POINTER(MapParams)]
+    L.mpros_planner_config.argtypes = [vp, C.POINTER(PlannerParams)]
+    L.mpros_map_set_occupancy.argtypes = [vp, vp, i, i, d, d, d, d]
+    L.mpros_map_set_occupancy_dev.argtypes = [vp, vp, i, i, d, d, d, d]
+    L.mpros_map_update_goal.argtypes = [vp, d, d]
+    L.mpros_map_get_info.argtypes = [vp, C.POINTER(MapInfo)]
+    L.mpros_map_download.argtypes = [vp, i, vp, sz]
+    L.mpros_map_point_in_collision.argtypes = [vp, i, vp, sz, vp]
+    L.mpros_collision_check_poses.argtypes = [vp, vp, sz, vp]
+    L.mpros_collision_check_poses_dev.argtypes = [vp, vp, sz, vp]
+    L.mpros_collision_check_paths.argtypes = [vp, vp, vp, sz, vp]
+    _lib = L
+    return L
+
+
+def exported_symbols():
+    """Names declared in include/mpros_gpu.h (parsed from the header)."""
+    import re
+
+    hdr = os.path.join(os.path.dirname(HERE), "include", "mpros_gpu.h")
+    return sorted(set(re.findall(r"MPROS_API[^;(]*?\b(mpros_\w+)\s*\(", open(hdr).read())))
+
+
+# parameter-server keys of the reference -> struct fields
+_MAP_KEYS = {
+    "/mpros/map/occupied_thresh": "occupied_thresh",
+    "/mpros/map/free_thresh": "free_thresh",
+    "/mpros/map/voro_fallout_rate": "voro_fallout_rate",
+    "/mpros/map/voro_max_region": "voro_max_region",
+    "/mpros/map/downsampling_factor": "downsampling_factor",
+    "/mpros/map/obstacle_inflation_radius": "obstacle_inflation_radius",
+}
+_PLANNER_KEYS = {
+    "/mpros/vehicle/max_curvature": "max_curvature",
+    "/mpros/vehicle/width": "width",
+    "/mpros/vehicle/wheelbase": "wheelbase",
+    "/mpros/vehicle/length": "length",
+    "/mpros/vehicle/center_to_rotate_center_longitudinal": "steer_offset",
+    "/mpros/vehicle/max_steering_angle": "max_steering_angle",
+    "/mpros/planner/gear_penalty": "gear_penalty",
+    "/mpros/planner/reverse_penalty": "reverse_penalty",
+    "/mpros/planner/steering_penalty": "steering_penalty",
+    "/mpros/planner/steering_change_penalty": "steering_change_penalty",
+    "/mpros/planner/analytic_solution_range": "analytic_solution_range",
+    "/mpros/planner/yaw_discretization": "yaw_discretization",
+    "/mpros/planner/step_size": "step_size",
+    "/mpros/planner/path_point_distance": "path_point_distance",
+    "/mpros/planner/steering_discretization": "steering_discretization",
+    "/mpros/planner/max_iteration": "max_iteration",
+    "/mpros/planner/optimal_path": "optimal_path",
+    "/mpros/planner/interpolation_enable": "interpolation_enable",
+}
+
+
+def _fill(struct, keys, params):
+    for k, v in params.items():
+        f = keys.get(k)
+        if f is None:
+            continue
+        ftype = dict(struct._fields_)[f]
+        setattr(struct, f, int(v) if ftype is C.c_int else float(v))
+
+
+class Context:
+    """One GPU context = one NavMap + one planner configuration + one CUDA stream."""
+
+    def __init__(self, device=0):
+        self.L = load_library()
+        h = C.c_void_p()
+        self._check(self.L.mpros_ctx_create(device, C.byref(h)))
+        self.h = h
+
+    def _check(self, rc):
+        if rc != 0:
+            raise MprosError("mpros error %d: %s" % (rc, self.L.mpros_last_error_string().decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.mpros_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- configuration (ROS parameter-server style dict, same keys as the reference) ----
+    def map_config(self, params):
+        p = MapParams()
+        self.L.mpros_map_params_default(C.byref(p))
+        _fill(p, _MAP_KEYS, params)
+        self._check(self.L.mpros_map_config(self.h, C.byref(p)))
+
+    def planner_config(self, params):
+        p = PlannerParams()
+        self.L.mpros_planner_params_default(C.byref(p))
+        _fill(p, _PLANNER_KEYS, params)
+        self._check(self.L.mpros_planner_config(self.h, C.byref(p)))
+        self.planner_params = p
+
+    # ---- NavMap ----
+    def set_occupancy(self, occ, resolution, origin):
+        """occ: int8 HxW (-1/0/100), row 0 = bottom. resolution: the float32 message value widened to double
+        (what NavMap stores); origin: [x, y, yaw]."""
+        occ = np.ascontiguousarray(occ, dtype=np.int8)
+        H, W = occ.shape
+        res = float(np.float32(resolution))
+        self._check(self.L.mpros_map_set_occupancy(self.h, occ.ctypes.data, W, H, res, origin[0], origin[1], origin[2]))
+
+    def set_occupancy_dev(self, dptr, W, H, resolution, origin):
+        res = float(np.float32(resolution))
+        self._check(self.L.mpros_map_set_occupancy_dev(self.h, dptr, W, H, res, origin[0], origin[1], origin[2]))
+
+    def update_goal(self, gx, gy):
+        self._check(self.L.mpros_map_update_goal(self.h, gx, gy))
+
+    def info(self):
+        o = MapInfo()
+        self._check(self.L.mpros_map_get_info(self.h, C.byref(o)))
+        return {f: getattr(o, f) for f, _ in MapInfo._fields_}
+
+    def layer(self, name):
+        lid, dt, orig = LAYERS[name]
+        inf = self.info()
+        shape = (inf["map_height_orig"], inf["map_width_orig"]) if orig else (inf["map_height"], inf["map_width"])
+        out = np.zeros(shape, dtype=dt)
+        self._check(self.L.mpros_map_download(self.h, lid, out.ctypes.data, out.nbytes))
+        return out
+
+    def point_in_collision(self, layer, ij):
+        ij = np.ascontiguousarray(ij, dtype=np.int32).reshape(-1, 2)
+        out = np.zeros(len(ij), dtype=np.uint8)
+        self._check(self.L.mpros_map_point_in_collision(self.h, LAYERS[layer][0], ij.ctypes.data, len(ij), out.ctypes.data))
+        return out
+
+    # ---- collision ----
+    def collision_check(self, poses):
+        poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 3)
+        out = np.zeros(len(poses), dtype=np.uint8)
+        self._check(self.L.mpros_collision_check_poses(self.h, poses.ctypes.data, len(poses), out.ctypes.data))
+        return out
+
+    def collision_check_dev(self, d_poses, n, d_out):
+        self._check(self.L.mpros_collision_check_poses_dev(self.h, d_poses, n, d_out))
+
+    def collision_check_paths(self, poses, offsets):
+        poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 3)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        out = np.zeros(len(offsets) - 1, dtype=np.uint8)
+        self._check(self.L.mpros_collision_check_paths(self.h, poses.ctypes.data, offsets.ctypes.data, len(out), out.ctypes.data))
+        return out
+
+    # ---- plumbing ----
+    def stream(self):
+        return self.L.mpros_ctx_stream(self.h)
+
+    def synchronize(self):
+        self._check(self.L.mpros_ctx_synchronize(self.h))
+
+    def launch_count(self):
+        return int(self.L.mpros_ctx_launch_count(self.h))

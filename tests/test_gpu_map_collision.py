@@ -1,0 +1,94 @@
+"""GPU parity (through the C ABI) of the NavMap layers and footPrintInCollision4 against the unmodified reference."""
+import numpy as np
+import pytest
+
+from helpers import make_pair, random_poses
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ("reverse_parking", 1, (11.5, 2.1)),
+    ("parallel_parking3", 1, (10.7, 4.0)),
+    ("parking4", 1, (10.0, -2.0)),
+    ("ARENA_part", 1, (-20.0, -1.5)),
+    ("ARENA_part", 2, (-20.0, -1.5)),
+    ("ARENA_part", 4, (5.0, 5.0)),
+    ("parkinglot", 1, (50.0, 50.0)),
+    ("map_slalom", 1, (50.0, 5.0)),
+    ("reverse_parking", 2, (11.5, 2.1)),
+    ("reverse_parking", 5, (11.5, 2.1)),
+]
+
+
+@pytest.mark.parametrize("name,ds,goal", CASES)
+def test_integer_layers_bit_exact(reflib, gpu_ctx_factory, name, ds, goal):
+    ctx = gpu_ctx_factory()
+    rm, params, m = make_pair(reflib, ctx, name, ds=ds, goal=goal)
+    inf = rm.info()
+    ginf = ctx.info()
+    assert (ginf["map_height"], ginf["map_width"]) == (inf["H"], inf["W"])
+    assert ginf["map_resolution"] == inf["res"]
+    for layer in ["static_orig", "static", "inflate_orig", "obs_dist"]:
+        a, b = rm.layer(layer), ctx.layer(layer)
+        assert a.shape == b.shape
+        assert np.array_equal(a, b), "%s: %d mismatches" % (layer, int((a != b).sum()))
+    assert inf["get_goal"] == ginf["get_goal"]
+    if inf["get_goal"]:
+        a, b = rm.layer("goal"), ctx.layer("goal")
+        assert np.array_equal(a, b), "goal: %d mismatches" % int((a != b).sum())
+    rm.close()
+
+
+@pytest.mark.parametrize("name,ds,goal", CASES[:6])
+def test_voronoi_contract(reflib, gpu_ctx_factory, name, ds, goal):
+    """region_: canonical min-id tie-break — must be a nearest region; obstacle labels exact.
+    Reports agreement of region / edge / edge_dist / cost with the order-dependent reference."""
+    ctx = gpu_ctx_factory()
+    rm, params, m = make_pair(reflib, ctx, name, ds=ds, goal=goal)
+    occ = rm.layer("static").astype(bool)
+    r_ref, r_gpu = rm.layer("region"), ctx.layer("region")
+    assert np.array_equal(r_ref[occ], r_gpu[occ]), "obstacle component labels differ"
+    assert ctx.info()["num_regions"] == int(r_ref[occ].max()) + 1 if occ.any() else True
+    free = ~occ
+    agree_region = float((r_ref[free] == r_gpu[free]).mean()) if free.any() else 1.0
+    e_ref, e_gpu = rm.layer("isedge").astype(bool), ctx.layer("isedge").astype(bool)
+    d_ref, d_gpu = rm.layer("edge_dist"), ctx.layer("edge_dist")
+    v_ref, v_gpu = rm.layer("voronoi"), ctx.layer("voronoi")
+    agree_edge = float((e_ref == e_gpu).mean())
+    agree_cost = float((v_ref == v_gpu).mean())
+    print("%s ds=%d: region agree %.4f edge agree %.4f edge_dist agree %.4f cost bitwise agree %.4f max|dcost| %.4g" % (
+        name, ds, agree_region, agree_edge, float((d_ref == d_gpu).mean()), agree_cost, float(np.abs(v_ref - v_gpu).max())))
+    # where region and both distance inputs agree with the reference the float cost must be bitwise identical
+    same_in = (d_ref == d_gpu) & (e_ref == e_gpu)
+    assert np.array_equal(v_ref[same_in], v_gpu[same_in])
+    assert agree_region > 0.90
+    rm.close()
+
+
+@pytest.mark.parametrize("name,ds,goal", CASES[:4] + [CASES[6]])
+def test_collision_verdicts_bit_exact(reflib, gpu_ctx_factory, name, ds, goal):
+    from oracle import refapi
+
+    ctx = gpu_ctx_factory()
+    rm, params, m = make_pair(reflib, ctx, name, ds=ds, goal=goal)
+    inf = rm.info()
+    rp = refapi.RefPlanner(rm)
+    rng = np.random.default_rng(1)
+    n = 200000
+    poses = random_poses(rng, n, inf)
+    # lattice-snapped coordinates and axis-aligned yaws (cell-edge cases)
+    k = n // 4
+    poses[:k, 0] = np.round(poses[:k, 0] / m["resolution"]) * m["resolution"]
+    poses[:k, 1] = np.round(poses[:k, 1] / m["resolution"]) * m["resolution"]
+    poses[: k // 2, 2] = rng.choice([0.0, np.pi / 2, -np.pi / 2, np.pi, 1.57, 3.14], k // 2)
+    want = rp.collision4(poses)
+    got = ctx.collision_check(poses)
+    assert 0.02 < want.mean() < 0.999
+    assert np.array_equal(want, got), "%d verdict mismatches of %d" % (int((want != got).sum()), n)
+    # C2: pathInCollision = OR over poses
+    offs = np.arange(0, n + 1, 8, dtype=np.int64)
+    got_paths = ctx.collision_check_paths(poses, offs)
+    want_paths = np.maximum.reduceat(want, offs[:-1])
+    assert np.array_equal(want_paths, got_paths)
+    rp.close()
+    rm.close()
