@@ -620,6 +620,30 @@ extern "C" int mpros_map_download(mpros_ctx *c, int layer, void *dst, size_t dst
     return MPROS_OK;
 }
 
+extern "C" int mpros_map_upload(mpros_ctx *c, int layer, const void *src, size_t src_bytes)
+{
+    if (!c || !src)
+    {
+        set_error("mpros_map_upload: NULL argument");
+        return MPROS_ERR_INVALID;
+    }
+    if (!c->get_map || layer != MPROS_LAYER_VORONOI)
+    {
+        set_error("mpros_map_upload: needs a map; only MPROS_LAYER_VORONOI can be uploaded");
+        return MPROS_ERR_INVALID;
+    }
+    size_t need = (size_t)c->H * c->W * sizeof(float);
+    if (src_bytes != need)
+    {
+        set_error("mpros_map_upload: size mismatch");
+        return MPROS_ERR_CAPACITY;
+    }
+    MPROS_CUDA(cudaSetDevice(c->device));
+    MPROS_CUDA(cudaMemcpyAsync(c->voronoi, src, need, cudaMemcpyHostToDevice, c->stream));
+    MPROS_CUDA(cudaStreamSynchronize(c->stream));
+    return MPROS_OK;
+}
+
 extern "C" int mpros_map_point_in_collision(mpros_ctx *c, int layer, const int32_t *ij, size_t n, uint8_t *out)
 {
     if (!c || (!ij && n) || (!out && n))

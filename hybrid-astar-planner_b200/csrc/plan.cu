@@ -1,0 +1,1175 @@
+// Batched Reeds-Shepp solve / shot (R1-R4), batched node expansion (E1-E5) and the whole-query planner
+// (HybridAstar::initialize + Plan + raw setPath, hybrid_a_star.cpp:52-118, 682-811) for MANY independent queries.
+//
+// Execution model: persistent kernel, one WARP per query, warps pull query indices from a global counter. A* is
+// sequential per query (one popped node per step, strict reference order); the parallelism is across queries
+// (thousands of resident warps) and inside a step across the primitives' footprint probes, the 48 RS candidates
+// and the 4 symmetry images of every OMPL-distance formula. All per-query state (node pool, open heap, closed-set
+// hash, on-demand goal wavefront) lives in a per-warp HBM workspace that is reused without clearing (generation tags).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "planner_device.cuh"
+
+namespace mpros
+{
+
+struct WarpWorkspaceLayout
+{
+    size_t node_off, hkey_off, hid_off, tkey_off, tg_off, tnode_off, blocked_off, f0_off, f1_off, dist_off, rowtag_off, traj_off;
+    size_t stride;
+    int node_cap, table_slots, bfs_rows, bfs_wwords;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static WarpWorkspaceLayout make_layout(int node_cap, int H, int W)
+{
+    WarpWorkspaceLayout L;
+    L.node_cap = node_cap;
+    int slots = 1;
+    while (slots < 2 * node_cap + 16)
+        slots <<= 1;
+    L.table_slots = slots;
+    const int span = 2 * (kHugeInt - 1) + 1;
+    L.bfs_rows = std::min(H, span);
+    int wpr = (W + 31) / 32;
+    L.bfs_wwords = std::min(wpr, span / 32 + 2);
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        size_t at = o;
+        o = align_up(o + bytes, 256);
+        return at;
+    };
+    L.node_off = take((size_t)node_cap * sizeof(PlanNode));
+    L.hkey_off = take((size_t)node_cap * 8);
+    L.hid_off = take((size_t)node_cap * 4);
+    L.tkey_off = take((size_t)slots * 8);
+    L.tg_off = take((size_t)slots * 8);
+    L.tnode_off = take((size_t)slots * 4);
+    size_t bw = (size_t)L.bfs_rows * L.bfs_wwords;
+    L.blocked_off = take(bw * 4);
+    L.f0_off = take(bw * 4);
+    L.f1_off = take(bw * 4);
+    L.dist_off = take(bw * 32 * 2);
+    L.rowtag_off = take((size_t)L.bfs_rows * 4);
+    L.traj_off = take((size_t)kTrajCap * 5 * 8);
+    L.stride = o;
+    return L;
+}
+
+struct PlanBatchArgs
+{
+    const double *starts, *goals; // nq x 3
+    int nq;
+    // outputs
+    int32_t *status;   // nq
+    double *cost;      // nq  (goal_node_->gvalue_)
+    int32_t *path_len; // nq
+    double *paths;     // nq x path_cap x 5 (may be null when path_cap == 0)
+    int path_cap;
+    int64_t *stats; // nq x 4 {iterations, primitives, rs_shots, collision_checks}
+    // work distribution
+    const int32_t *todo; // indices of the queries to run in this pass (null = all)
+    int n_todo;
+    unsigned int *counter;
+    uint32_t tag_base;
+    char *ws;
+    WarpWorkspaceLayout L;
+    RsConfig rs;
+    int optimal;
+};
+
+// status codes of mpros_plan_batch (include/mpros_gpu.h)
+enum
+{
+    ST_FOUND = 1,
+    ST_LIMIT = 0,
+    ST_OPEN_EMPTY = -1,
+    ST_NOT_INIT = -2,
+    ST_OVERFLOW = -3
+};
+
+// heuristic of one node computed by a QUAD of lanes (hybrid_a_star.cpp:248-264); h1 is the goal-map value of the cell
+__device__ __forceinline__ double node_heuristic_quad(const MapView &m, const PlannerView &p, int h1_cells, double x, double y,
+                                                      double yaw, double gx, double gy, double gyaw)
+{
+    double h1 = (double)h1_cells * m.res; // getGoalCost: cost_ * map_resolution_
+    double h2 = ompl_rs_distance_quad(p.min_r, x, y, yaw, gx, gy, gyaw);
+    return fmax(h1, h2) * (1 + 1e-3);
+}
+
+__device__ void plan_one_query(const MapView &m, const PlannerView &p, const PlanBatchArgs &a, int q, char *ws, uint32_t tag)
+{
+    const int lane = threadIdx.x & 31;
+    const WarpWorkspaceLayout &L = a.L;
+    PlanNode *nodes = reinterpret_cast<PlanNode *>(ws + L.node_off);
+    OpenHeap heap;
+    heap.key = reinterpret_cast<unsigned long long *>(ws + L.hkey_off);
+    heap.id = reinterpret_cast<uint32_t *>(ws + L.hid_off);
+    heap.size = 0;
+    heap.cap = L.node_cap;
+    ClosedSet closed;
+    closed.key = reinterpret_cast<unsigned long long *>(ws + L.tkey_off);
+    closed.g = reinterpret_cast<double *>(ws + L.tg_off);
+    closed.node = reinterpret_cast<uint32_t *>(ws + L.tnode_off);
+    closed.mask = (uint32_t)L.table_slots - 1;
+    closed.tag = tag;
+    GoalBfs bfs;
+    bfs.blocked = reinterpret_cast<uint32_t *>(ws + L.blocked_off);
+    bfs.f0 = reinterpret_cast<uint32_t *>(ws + L.f0_off);
+    bfs.f1 = reinterpret_cast<uint32_t *>(ws + L.f1_off);
+    bfs.dist = reinterpret_cast<uint16_t *>(ws + L.dist_off);
+    bfs.row_tag = reinterpret_cast<uint32_t *>(ws + L.rowtag_off);
+    double *traj = reinterpret_cast<double *>(ws + L.traj_off); // kTrajCap x 3 xyz, then kTrajCap x 2 steer/dir
+
+    const double sx = a.starts[3 * q], sy = a.starts[3 * q + 1], syaw = a.starts[3 * q + 2];
+    const double gx = a.goals[3 * q], gy = a.goals[3 * q + 1], gyaw = a.goals[3 * q + 2];
+    long long n_iter = 0, n_prim = 0, n_shots = 0, n_coll = 0;
+    int status = ST_NOT_INIT;
+    double goal_g = -1.0;
+    uint32_t goal_parent = kNoNode;
+    int goal_traj_n = 0;
+    int out_len = 0;
+
+    // ---- initialize (hybrid_a_star.cpp:52-118) ----
+    bool init_ok = true;
+    {
+        double s, c;
+        sincos(syaw, &s, &c);
+        if (warp_footprint_collision(m, p, sx, sy, s, c))
+            init_ok = false; // "Start pose in collision"
+        if (init_ok)
+        {
+            sincos(gyaw, &s, &c);
+            if (warp_footprint_collision(m, p, gx, gy, s, c))
+                init_ok = false; // "Goal pose in collision"
+        }
+    }
+    int si = -1, sj = -1, gi = -1, gj = -1;
+    if (init_ok)
+    {
+        // node cells on the down-sampled grid; the goal map exists only if the goal lies inside the map (nav_map.cpp:297)
+        bool s_in = pos_to_index_ds(m, sx, sy, si, sj);
+        bool g_in = pos_to_index_ds(m, gx, gy, gi, gj);
+        if (!s_in || !g_in)
+            init_ok = false;
+    }
+    if (init_ok)
+    {
+        bfs_start(m, bfs, gi, gj, tag);
+        // start node: steer 0, direction 1, g = 0 (:83, :211-215)
+        int h1 = bfs_lookup_warp(m, bfs, lane == 0, si, sj);
+        h1 = __shfl_sync(kFull, h1, 0);
+        double h = node_heuristic_quad(m, p, h1, sx, sy, syaw, gx, gy, gyaw);
+        h = __shfl_sync(kFull, h, 0);
+        if (lane == 0)
+        {
+            PlanNode n;
+            n.x = sx, n.y = sy, n.yaw = syaw, n.steer = 0.0, n.g = 0.0, n.parent = kNoNode, n.dir = 1, n.closed = 0, n.pad = 0;
+            nodes[0] = n;
+            // cost_set_/node_set_ seeds (:107-112); the goal entry is written second and wins a shared cell
+            bool found;
+            unsigned long long sidx = cal_index(m, p, si, sj, yaw_to_idx(p, syaw), 1.0);
+            uint32_t s0 = closed_find(closed, sidx, found);
+            closed.key[s0] = (closed.tag << 34) | sidx;
+            closed.g[s0] = 0.0;
+            closed.node[s0] = 0;
+            unsigned long long gidx = cal_index(m, p, gi, gj, yaw_to_idx(p, gyaw), 1.0);
+            uint32_t s1 = closed_find(closed, gidx, found);
+            closed.key[s1] = (closed.tag << 34) | gidx;
+            closed.g[s1] = 10000.0;
+            closed.node[s1] = kGoalNode;
+            heap_push_lane0(heap, (unsigned long long)__double_as_longlong(0.0 + h), 0);
+        }
+        heap.size = 1;
+        __syncwarp();
+    }
+    uint32_t n_nodes = 1;
+
+    // ---- Plan() (hybrid_a_star.cpp:682-777) ----
+    if (init_ok)
+    {
+        bool goal_found = false, limit_reached = false, overflow = false;
+        int iteration = 0;
+        while (heap.size > 0)
+        {
+            if (iteration > p.max_iteration)
+            {
+                limit_reached = true;
+                break;
+            }
+            unsigned long long fk;
+            uint32_t cur = heap_pop_warp(heap, fk);
+            const PlanNode cn = nodes[cur];
+            if (cn.closed)
+                continue;
+            // -- genRSPath (:853-900)
+            bool shot_ok = false;
+            {
+                double ddx = cn.x - gx, ddy = cn.y - gy;
+                double goal_dist_sq = ddx * ddx + ddy * ddy;
+                if (goal_dist_sq < p.rs_range * p.rs_range)
+                {
+                    ++n_shots;
+                    RsPath best;
+                    double rs_cost = rs_find_optimal_warp(a.rs, cn.x, cn.y, cn.yaw, (int)cn.dir, cn.steer, gx, gy, gyaw, best);
+                    int np = 0;
+                    if (lane == 0)
+                        np = rs_gen_traj(a.rs, cn.x, cn.y, cn.yaw, best, traj, traj + 3 * kTrajCap, kTrajCap);
+                    np = __shfl_sync(kFull, np, 0);
+                    __syncwarp();
+                    bool hit = false;
+                    int checked = 0;
+                    if (np > kTrajCap)
+                    {
+                        hit = true; // cannot happen inside the shot range; treat as blocked rather than truncate
+                        checked = kTrajCap;
+                    }
+                    for (int base = 0; base < np && !hit; base += 32)
+                    {
+                        // lanes pre-compute sin/cos of their pose's yaw, then the poses are tested one by one
+                        int k = base + lane;
+                        double s = 0, c = 1, px = 0, py = 0;
+                        if (k < np)
+                        {
+                            px = traj[3 * k], py = traj[3 * k + 1];
+                            sincos(traj[3 * k + 2], &s, &c);
+                        }
+                        int cnt = min(32, np - base);
+                        for (int t = 0; t < cnt && !hit; ++t)
+                        {
+                            double tx = __shfl_sync(kFull, px, t), ty = __shfl_sync(kFull, py, t);
+                            double ts = __shfl_sync(kFull, s, t), tc = __shfl_sync(kFull, c, t);
+                            ++checked;
+                            hit = warp_footprint_collision(m, p, tx, ty, ts, tc);
+                        }
+                    }
+                    n_coll += checked;
+                    if (!hit)
+                    {
+                        if (goal_parent == kNoNode || goal_g > cn.g + rs_cost)
+                        {
+                            goal_parent = cur;
+                            goal_g = cn.g + rs_cost;
+                            goal_traj_n = np;
+                        }
+                        shot_ok = true;
+                    }
+                }
+            }
+            if (shot_ok)
+            {
+                goal_found = true;
+                if (!a.optimal)
+                    break;
+            }
+            else
+            {
+                // -- expandNode (:304-402)
+                const int P = 2 * p.n_steer;
+                double s_yaw, c_yaw;
+                sincos(cn.yaw, &s_yaw, &c_yaw);
+                // every lane < P computes its primitive's end pose
+                double nx = 0, ny = 0, nyaw = 0, steer = 0, direc = 1, ns = 0, nc = 1;
+                if (lane < P)
+                {
+                    primitive_end_pose(p, lane, cn.x, cn.y, cn.yaw, s_yaw, c_yaw, nx, ny, nyaw, steer, direc);
+                    sincos(nyaw, &ns, &nc);
+                }
+                n_prim += P;
+                n_coll += P;
+                unsigned free_mask = 0;
+                for (int c = 0; c < P; ++c)
+                {
+                    double tx = __shfl_sync(kFull, nx, c), ty = __shfl_sync(kFull, ny, c);
+                    double ts = __shfl_sync(kFull, ns, c), tc = __shfl_sync(kFull, nc, c);
+                    if (!warp_footprint_collision(m, p, tx, ty, ts, tc))
+                        free_mask |= 1u << c;
+                }
+                // survivors: node cell, g (lane = primitive), goal-map value (on-demand wavefront)
+                bool alive = lane < P && ((free_mask >> lane) & 1u);
+                int ci = -1, cj = -1;
+                if (alive && !pos_to_index_ds(m, nx, ny, ci, cj))
+                    alive = false; // the reference would index outside its arrays here (cannot pass the footprint test)
+                int h1 = bfs_lookup_warp(m, bfs, alive, ci, cj);
+                double g = 0;
+                if (alive)
+                {
+                    double voro = (double)__ldg(m.voronoi + (size_t)ci * m.W + cj);
+                    g = node_cost(p, cn.g, (double)cn.dir, cn.steer, voro, steer, direc);
+                }
+                // heuristics: quad of lanes per primitive, 8 primitives per round
+                double hval = 0;
+                for (int base = 0; base < P; base += 8)
+                {
+                    int src = base + (lane >> 2);
+                    double qx = __shfl_sync(kFull, nx, src), qy = __shfl_sync(kFull, ny, src), qyaw = __shfl_sync(kFull, nyaw, src);
+                    int qh1 = __shfl_sync(kFull, h1, src);
+                    bool qalive = (__shfl_sync(kFull, (int)alive, src) != 0) && src < P;
+                    double hq = 0;
+                    if (__any_sync(kFull, qalive))
+                        hq = node_heuristic_quad(m, p, qh1, qalive ? qx : gx, qalive ? qy : gy, qalive ? qyaw : gyaw, gx, gy, gyaw);
+                    // hand the value back to the primitive's own lane
+                    int owner_quad = (lane - base);
+                    double back = __shfl_sync(kFull, hq, (owner_quad >= 0 && owner_quad < 8) ? owner_quad * 4 : 0);
+                    if (owner_quad >= 0 && owner_quad < 8)
+                        hval = back;
+                }
+                // closed-set compare / open-list insert, strictly in primitive order (lane 0 walks the survivors)
+                unsigned alive_mask = __ballot_sync(kFull, alive);
+                for (int c = 0; c < P; ++c)
+                {
+                    if (!((alive_mask >> c) & 1u))
+                        continue;
+                    double tx = __shfl_sync(kFull, nx, c), ty = __shfl_sync(kFull, ny, c), tyaw = __shfl_sync(kFull, nyaw, c);
+                    double tsteer = __shfl_sync(kFull, steer, c), tdir = __shfl_sync(kFull, direc, c);
+                    double tg = __shfl_sync(kFull, g, c), th = __shfl_sync(kFull, hval, c);
+                    int ti = __shfl_sync(kFull, ci, c), tj = __shfl_sync(kFull, cj, c);
+                    int inserted = 0;
+                    if (lane == 0)
+                    {
+                        unsigned long long idx = cal_index(m, p, ti, tj, yaw_to_idx(p, tyaw), tdir);
+                        bool found;
+                        uint32_t slot = closed_find(closed, idx, found);
+                        double old_cost = found ? closed.g[slot] : __longlong_as_double(0x7ff0000000000000ll);
+                        if (old_cost > tg)
+                        {
+                            if (n_nodes >= (uint32_t)L.node_cap)
+                                inserted = -1;
+                            else
+                            {
+                                if (found)
+                                {
+                                    uint32_t old = closed.node[slot];
+                                    if (old < kGoalNode)
+                                        nodes[old].closed = 1;
+                                }
+                                closed.key[slot] = (closed.tag << 34) | idx;
+                                closed.g[slot] = tg;
+                                closed.node[slot] = n_nodes;
+                                PlanNode nn;
+                                nn.x = tx, nn.y = ty, nn.yaw = tyaw, nn.steer = tsteer, nn.g = tg, nn.parent = cur;
+                                nn.dir = (int8_t)(tdir > 0 ? 1 : -1), nn.closed = 0, nn.pad = 0;
+                                nodes[n_nodes] = nn;
+                                heap_push_lane0(heap, (unsigned long long)__double_as_longlong(tg + th), n_nodes);
+                                inserted = 1;
+                            }
+                        }
+                    }
+                    inserted = __shfl_sync(kFull, inserted, 0);
+                    if (inserted < 0)
+                    {
+                        overflow = true;
+                        break;
+                    }
+                    if (inserted)
+                    {
+                        heap.size++;
+                        n_nodes++;
+                    }
+                    __syncwarp();
+                }
+                if (overflow)
+                    break;
+            }
+            if (a.optimal)
+            {
+                if (hypot(gx - cn.x, gy - cn.y) <= 1.0) // stop_radius (hybrid_a_star.h:345)
+                    break;
+            }
+            ++iteration;
+        }
+        n_iter = iteration;
+        if (overflow)
+            status = ST_OVERFLOW;
+        else if (goal_found)
+            status = ST_FOUND;
+        else if (limit_reached)
+            status = ST_LIMIT;
+        else
+            status = ST_OPEN_EMPTY;
+    }
+
+    // ---- raw path_ of setPath (hybrid_a_star.cpp:779-811): start, expanded nodes, then the RS goal path ----
+    if (status == ST_FOUND)
+    {
+        // non-optimal mode stops at the first successful shot, so `traj` still holds goal_path_. In optimal mode the
+        // best shot may be older; re-generate it (deterministic) from the stored parent.
+        const PlanNode gp = nodes[goal_parent];
+        if (a.optimal)
+        {
+            RsPath best;
+            rs_find_optimal_warp(a.rs, gp.x, gp.y, gp.yaw, (int)gp.dir, gp.steer, gx, gy, gyaw, best);
+            if (lane == 0)
+                goal_traj_n = rs_gen_traj(a.rs, gp.x, gp.y, gp.yaw, best, traj, traj + 3 * kTrajCap, kTrajCap);
+            goal_traj_n = __shfl_sync(kFull, goal_traj_n, 0);
+            __syncwarp();
+        }
+        // chain length (nodes with a parent, walking up from goal's parent)
+        int chain = 0;
+        if (lane == 0)
+        {
+            uint32_t c = goal_parent;
+            while (nodes[c].parent != kNoNode)
+            {
+                ++chain;
+                c = nodes[c].parent;
+            }
+        }
+        chain = __shfl_sync(kFull, chain, 0);
+        out_len = 1 + chain + goal_traj_n;
+        if (a.paths && a.path_cap > 0)
+        {
+            double *dst = a.paths + (size_t)q * a.path_cap * 5;
+            if (lane == 0)
+            {
+                // start point: steer 0, direction of the first path point (:792-807)
+                double start_dir;
+                uint32_t c = goal_parent;
+                int pos = chain; // index of goal_parent's point in the output
+                double last_dir = 1.0;
+                while (nodes[c].parent != kNoNode)
+                {
+                    const PlanNode n = nodes[c];
+                    if (pos < a.path_cap)
+                    {
+                        double *o = dst + 5 * pos;
+                        o[0] = n.x, o[1] = n.y, o[2] = n.yaw, o[3] = n.steer, o[4] = (double)n.dir;
+                    }
+                    last_dir = (double)n.dir; // ends as the direction of the node next to the start
+                    --pos;
+                    c = n.parent;
+                }
+                if (chain > 1)
+                    start_dir = last_dir; // path_.back().back() before the start is pushed
+                else
+                    start_dir = goal_traj_n > 0 ? traj[3 * kTrajCap + 1] : 1.0; // goal_path_.front().back()
+                double *o = dst;
+                o[0] = sx, o[1] = sy, o[2] = syaw, o[3] = 0.0, o[4] = start_dir;
+            }
+            for (int k = lane; k < goal_traj_n; k += 32)
+            {
+                int pos = 1 + chain + k;
+                if (pos < a.path_cap)
+                {
+                    double *o = dst + 5 * pos;
+                    o[0] = traj[3 * k], o[1] = traj[3 * k + 1], o[2] = traj[3 * k + 2];
+                    o[3] = traj[3 * kTrajCap + 2 * k], o[4] = traj[3 * kTrajCap + 2 * k + 1];
+                }
+            }
+        }
+    }
+    if (lane == 0)
+    {
+        a.status[q] = status;
+        a.cost[q] = (status == ST_FOUND) ? goal_g : -1.0;
+        a.path_len[q] = out_len;
+        if (a.stats)
+        {
+            a.stats[4 * q + 0] = n_iter;
+            a.stats[4 * q + 1] = n_prim;
+            a.stats[4 * q + 2] = n_shots;
+            a.stats[4 * q + 3] = n_coll;
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(128) plan_batch_kernel(MapView m, PlannerView p, PlanBatchArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    char *ws = a.ws + (size_t)warp_global * a.L.stride;
+    uint32_t local_gen = 0;
+    const int total = a.todo ? a.n_todo : a.nq;
+    while (true)
+    {
+        unsigned int t = 0;
+        if (lane == 0)
+            t = atomicAdd(a.counter, 1u);
+        t = __shfl_sync(kFull, t, 0);
+        if (t >= (unsigned)total)
+            break;
+        int q = a.todo ? a.todo[t] : (int)t;
+        ++local_gen;
+        plan_one_query(m, p, a, q, ws, a.tag_base + local_gen);
+    }
+}
+
+// ---- standalone batches (R1-R4, E1-E5) ---------------------------------------------------------------------------------
+struct RsBatchArgs
+{
+    const double *starts5; // n x 5 {x, y, yaw, dir, steer}
+    const double *goals3;  // n x 3
+    int n;
+    double *segs;      // n x 15 {len, steer, dir} x 5
+    int32_t *nseg;     // n
+    double *cost;      // n
+    double *traj;      // n x traj_cap x 5 (optional)
+    int32_t *npts;     // n
+    uint8_t *verdicts; // n (optional): pathInCollision of the sampled trajectory (R4)
+    int traj_cap;
+    char *ws;          // per-warp scratch: kTrajCap x 5 doubles
+    RsConfig rs;
+};
+
+__global__ void __launch_bounds__(128) rs_batch_kernel(MapView m, PlannerView p, RsBatchArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    double *scratch = reinterpret_cast<double *>(a.ws) + (size_t)warp_global * kTrajCap * 5;
+    for (int q = warp_global; q < a.n; q += nwarps)
+    {
+        const double *s5 = a.starts5 + 5 * (size_t)q, *g3 = a.goals3 + 3 * (size_t)q;
+        RsPath best;
+        double cost = rs_find_optimal_warp(a.rs, s5[0], s5[1], s5[2], (int)s5[3], s5[4], g3[0], g3[1], g3[2], best);
+        double *txyz = scratch, *tsd = scratch + 3 * kTrajCap;
+        int cap = kTrajCap;
+        int np = 0;
+        if (lane == 0)
+            np = rs_gen_traj(a.rs, s5[0], s5[1], s5[2], best, txyz, tsd, cap);
+        np = __shfl_sync(kFull, np, 0);
+        __syncwarp();
+        int stored = min(np, cap);
+        if (a.traj)
+        {
+            double *dst = a.traj + (size_t)q * a.traj_cap * 5;
+            for (int k = lane; k < stored && k < a.traj_cap; k += 32)
+            {
+                dst[5 * k] = txyz[3 * k], dst[5 * k + 1] = txyz[3 * k + 1], dst[5 * k + 2] = txyz[3 * k + 2];
+                dst[5 * k + 3] = tsd[2 * k], dst[5 * k + 4] = tsd[2 * k + 1];
+            }
+        }
+        if (a.verdicts)
+        {
+            bool hit = np > cap; // longer than the scratch: report blocked rather than judge a truncated path
+            for (int k = 0; k < stored && !hit; ++k)
+            {
+                double s, c;
+                sincos(txyz[3 * k + 2], &s, &c);
+                hit = warp_footprint_collision(m, p, txyz[3 * k], txyz[3 * k + 1], s, c);
+            }
+            if (lane == 0)
+                a.verdicts[q] = hit ? 1 : 0;
+        }
+        if (lane == 0)
+        {
+            a.cost[q] = cost;
+            a.nseg[q] = best.n;
+            a.npts[q] = np;
+            for (int k = 0; k < 5; ++k)
+            {
+                bool v = k < best.n;
+                a.segs[15 * (size_t)q + 3 * k] = v ? best.s[k].len : 0.0;
+                a.segs[15 * (size_t)q + 3 * k + 1] = v ? (double)best.s[k].steer : 0.0;
+                a.segs[15 * (size_t)q + 3 * k + 2] = v ? (double)best.s[k].dir : 0.0;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// OMPL-equivalent RS distance for n pose pairs (R5): one quad of lanes per pair
+__global__ void __launch_bounds__(128) rs_distance_kernel(double rho, const double *__restrict__ a3, const double *__restrict__ b3, int n,
+                                                          double *__restrict__ out)
+{
+    const int quad_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const int nquads = (gridDim.x * blockDim.x) >> 2;
+    const int rounds = (n + nquads - 1) / nquads;
+    for (int r = 0; r < rounds; ++r)
+    {
+        int k = r * nquads + quad_global;
+        bool live = k < n;
+        int kk = live ? k : 0;
+        double d = ompl_rs_distance_quad(rho, a3[3 * kk], a3[3 * kk + 1], a3[3 * kk + 2], b3[3 * kk], b3[3 * kk + 1], b3[3 * kk + 2]);
+        if (live && (threadIdx.x & 3) == 0)
+            out[k] = d;
+    }
+}
+
+// E1-E5 for a batch of parents against the context's goal map (mpros_map_update_goal) with a FRESH closed set per
+// parent (only the start/goal seeds), i.e. what HybridAstar::expandNode does right after initialize().
+struct ExpandArgs
+{
+    const double *parents6; // n x 6 {x, y, yaw, steer, dir, g}
+    int n;
+    double gx, gy, gyaw;
+    double *prims;   // n x P x 7 {x, y, yaw, steer, dir, collision, cell-valid}
+    double *childs;  // n x P x 10 {x, y, yaw, steer, dir, g, h, f, i, j} (inserted children, in order)
+    int32_t *nchild; // n
+    unsigned long long start_idx, goal_idx;
+    double start_g;
+    int have_seeds;
+};
+
+__global__ void __launch_bounds__(128) expand_batch_kernel(MapView m, PlannerView p, ExpandArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int P = 2 * p.n_steer;
+    for (int q = warp_global; q < a.n; q += nwarps)
+    {
+        const double *pr = a.parents6 + 6 * (size_t)q;
+        const double cx = pr[0], cy = pr[1], cyaw = pr[2], psteer = pr[3], pdir = pr[4], pg = pr[5];
+        double s_yaw, c_yaw;
+        sincos(cyaw, &s_yaw, &c_yaw);
+        double nx = 0, ny = 0, nyaw = 0, steer = 0, direc = 1, ns = 0, nc = 1;
+        if (lane < P)
+        {
+            primitive_end_pose(p, lane, cx, cy, cyaw, s_yaw, c_yaw, nx, ny, nyaw, steer, direc);
+            sincos(nyaw, &ns, &nc);
+        }
+        unsigned free_mask = 0;
+        for (int c = 0; c < P; ++c)
+        {
+            double tx = __shfl_sync(kFull, nx, c), ty = __shfl_sync(kFull, ny, c);
+            double ts = __shfl_sync(kFull, ns, c), tc = __shfl_sync(kFull, nc, c);
+            if (!warp_footprint_collision(m, p, tx, ty, ts, tc))
+                free_mask |= 1u << c;
+        }
+        bool alive = lane < P && ((free_mask >> lane) & 1u);
+        int ci = -1, cj = -1;
+        bool cell_ok = true;
+        if (alive && !pos_to_index_ds(m, nx, ny, ci, cj))
+        {
+            alive = false;
+            cell_ok = false;
+        }
+        int h1 = alive ? (int)m.goal[(size_t)ci * m.W + cj] : 0;
+        double g = 0;
+        if (alive)
+            g = node_cost(p, pg, pdir, psteer, (double)__ldg(m.voronoi + (size_t)ci * m.W + cj), steer, direc);
+        double hval = 0;
+        for (int base = 0; base < P; base += 8)
+        {
+            int src = base + (lane >> 2);
+            double qx = __shfl_sync(kFull, nx, src), qy = __shfl_sync(kFull, ny, src), qyaw = __shfl_sync(kFull, nyaw, src);
+            int qh1 = __shfl_sync(kFull, h1, src);
+            bool qalive = (__shfl_sync(kFull, (int)alive, src) != 0) && src < P;
+            double hq = 0;
+            if (__any_sync(kFull, qalive))
+                hq = node_heuristic_quad(m, p, qh1, qalive ? qx : a.gx, qalive ? qy : a.gy, qalive ? qyaw : a.gyaw, a.gx, a.gy, a.gyaw);
+            int owner_quad = lane - base;
+            double back = __shfl_sync(kFull, hq, (owner_quad >= 0 && owner_quad < 8) ? owner_quad * 4 : 0);
+            if (owner_quad >= 0 && owner_quad < 8)
+                hval = back;
+        }
+        if (lane < P)
+        {
+            double *o = a.prims + ((size_t)q * P + lane) * 7;
+            o[0] = nx, o[1] = ny, o[2] = nyaw, o[3] = steer, o[4] = direc, o[5] = ((free_mask >> lane) & 1u) ? 0.0 : 1.0;
+            o[6] = cell_ok ? 1.0 : 0.0;
+        }
+        // prune against the seeded closed set (start g, goal 10000) and against earlier siblings, in primitive order
+        unsigned long long idx = alive ? cal_index(m, p, ci, cj, yaw_to_idx(p, nyaw), direc) : ~0ull;
+        unsigned alive_mask = __ballot_sync(kFull, alive);
+        int count = 0;
+        for (int c = 0; c < P; ++c)
+        {
+            if (!((alive_mask >> c) & 1u))
+                continue;
+            unsigned long long tidx = __shfl_sync(kFull, idx, c);
+            double tg = __shfl_sync(kFull, g, c);
+            // best g already stored for this index by the seeds or by an inserted earlier sibling
+            double old_cost = __longlong_as_double(0x7ff0000000000000ll);
+            if (a.have_seeds)
+            {
+                if (tidx == a.start_idx)
+                    old_cost = a.start_g;
+                if (tidx == a.goal_idx)
+                    old_cost = 10000.0;
+            }
+            // sequential semantics: walk the earlier siblings in order
+            for (int e = 0; e < c; ++e)
+            {
+                if (!((alive_mask >> e) & 1u))
+                    continue;
+                unsigned long long eidx = __shfl_sync(kFull, idx, e);
+                double eg = __shfl_sync(kFull, g, e);
+                // sibling e was inserted iff it beat what was stored before it; replay that decision
+                if (eidx == tidx && eg < old_cost)
+                    old_cost = eg;
+            }
+            bool ins = old_cost > tg;
+            if (ins)
+            {
+                if (lane == c)
+                {
+                    double *o = a.childs + ((size_t)q * P + count) * 10;
+                    o[0] = nx, o[1] = ny, o[2] = nyaw, o[3] = steer, o[4] = direc, o[5] = g, o[6] = hval, o[7] = g + hval;
+                    o[8] = (double)ci, o[9] = (double)cj;
+                }
+                ++count;
+            }
+        }
+        if (lane == 0)
+            a.nchild[q] = count;
+        __syncwarp();
+    }
+}
+
+} // namespace mpros
+
+// =====================================================================================================================
+using namespace mpros;
+
+static RsConfig rs_config_from_planner(const Ctx *c)
+{
+    // hybrid_a_star.cpp:142-143,169-170: setPenalty(GEAR, BACKWARD, STEER_ANGLE, STEER_CHANGE) lands positionally in
+    // RSCurve's (gear, backward, steer_change, steer_angle) slots
+    RsConfig r;
+    r.radius = c->pv.min_r;
+    r.steer_angle = c->pp.max_steering_angle;
+    r.step = c->pp.step_size;
+    r.pen_gear = c->pp.gear_penalty;
+    r.pen_back = c->pp.reverse_penalty;
+    r.pen_steer_change = c->pp.steering_penalty;
+    r.pen_steer_angle = c->pp.steering_change_penalty;
+    return r;
+}
+
+static int check_planner_ready(mpros_ctx *c, const char *who)
+{
+    if (!c)
+    {
+        set_error(std::string(who) + ": NULL context");
+        return MPROS_ERR_INVALID;
+    }
+    if (!c->get_map || !c->planner_configured)
+    {
+        set_error(std::string(who) + ": needs a map (mpros_map_set_occupancy) and mpros_planner_config first");
+        return MPROS_ERR_INVALID;
+    }
+    return MPROS_OK;
+}
+
+extern "C" int mpros_rs_default_config(mpros_ctx *c, mpros_rs_params *out)
+{
+    int rc = check_planner_ready(c, "mpros_rs_default_config");
+    if (rc)
+        return rc;
+    RsConfig r = rs_config_from_planner(c);
+    out->radius = r.radius;
+    out->steering_angle = r.steer_angle;
+    out->step_size = r.step;
+    out->pen_gear = r.pen_gear;
+    out->pen_backward = r.pen_back;
+    out->pen_steer_change = r.pen_steer_change;
+    out->pen_steer_angle = r.pen_steer_angle;
+    return MPROS_OK;
+}
+
+static int rs_batch_impl(mpros_ctx *c, const mpros_rs_params *rp, const double *starts5, const double *goals3, size_t n,
+                         double *segs, int32_t *nseg, double *cost, double *traj, int traj_cap, int32_t *npts, uint8_t *verdicts,
+                         bool with_collision)
+{
+    if (n == 0)
+        return MPROS_OK;
+    if (!starts5 || !goals3 || !segs || !nseg || !cost || !npts || (with_collision && !verdicts) || traj_cap < 0 ||
+        (traj_cap > 0 && !traj) || n > (size_t)INT32_MAX)
+    {
+        set_error("mpros_rs_*_batch: NULL / invalid argument");
+        return MPROS_ERR_INVALID;
+    }
+    MPROS_CUDA(cudaSetDevice(c->device));
+    RsBatchArgs a;
+    if (rp)
+    {
+        a.rs.radius = rp->radius;
+        a.rs.steer_angle = rp->steering_angle;
+        a.rs.step = rp->step_size;
+        a.rs.pen_gear = rp->pen_gear;
+        a.rs.pen_back = rp->pen_backward;
+        a.rs.pen_steer_change = rp->pen_steer_change;
+        a.rs.pen_steer_angle = rp->pen_steer_angle;
+    }
+    else
+        a.rs = rs_config_from_planner(c);
+    const int block = 128, warps_per_block = block / 32;
+    int blocks = (int)std::min<size_t>((n + warps_per_block - 1) / warps_per_block, (size_t)148 * 8);
+    size_t nwarps = (size_t)blocks * warps_per_block;
+    size_t in_bytes = n * 8 * 8, seg_bytes = n * 15 * 8, traj_bytes = n * (size_t)traj_cap * 5 * 8;
+    size_t ws_bytes = nwarps * kTrajCap * 5 * 8;
+    size_t total = in_bytes + seg_bytes + n * 4 + n * 8 + traj_bytes + n * 4 + n + ws_bytes + 1024;
+    int rc = ensure_stage(c, total);
+    if (rc)
+        return rc;
+    char *base = static_cast<char *>(c->stage);
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        char *p = base + o;
+        o = (o + bytes + 255) / 256 * 256;
+        return p;
+    };
+    double *d_s = (double *)take(n * 5 * 8), *d_g = (double *)take(n * 3 * 8), *d_seg = (double *)take(seg_bytes);
+    int32_t *d_nseg = (int32_t *)take(n * 4);
+    double *d_cost = (double *)take(n * 8);
+    double *d_traj = traj_cap ? (double *)take(traj_bytes) : nullptr;
+    int32_t *d_npts = (int32_t *)take(n * 4);
+    uint8_t *d_ver = (uint8_t *)take(n);
+    char *d_ws = take(ws_bytes);
+    if (o > c->stage_bytes)
+    {
+        rc = ensure_stage(c, o + 1024);
+        set_error("internal: staging layout");
+        return MPROS_ERR_INVALID;
+    }
+    cudaStream_t st = c->stream;
+    MPROS_CUDA(cudaMemcpyAsync(d_s, starts5, n * 5 * 8, cudaMemcpyHostToDevice, st));
+    MPROS_CUDA(cudaMemcpyAsync(d_g, goals3, n * 3 * 8, cudaMemcpyHostToDevice, st));
+    a.starts5 = d_s;
+    a.goals3 = d_g;
+    a.n = (int)n;
+    a.segs = d_seg;
+    a.nseg = d_nseg;
+    a.cost = d_cost;
+    a.traj = d_traj;
+    a.npts = d_npts;
+    a.verdicts = with_collision ? d_ver : nullptr;
+    a.traj_cap = traj_cap;
+    a.ws = d_ws;
+    rs_batch_kernel<<<blocks, block, 0, st>>>(c->view(), c->pv, a);
+    MPROS_LAUNCH_CHECK(c);
+    MPROS_CUDA(cudaMemcpyAsync(segs, d_seg, seg_bytes, cudaMemcpyDeviceToHost, st));
+    MPROS_CUDA(cudaMemcpyAsync(nseg, d_nseg, n * 4, cudaMemcpyDeviceToHost, st));
+    MPROS_CUDA(cudaMemcpyAsync(cost, d_cost, n * 8, cudaMemcpyDeviceToHost, st));
+    if (traj_cap)
+        MPROS_CUDA(cudaMemcpyAsync(traj, d_traj, traj_bytes, cudaMemcpyDeviceToHost, st));
+    MPROS_CUDA(cudaMemcpyAsync(npts, d_npts, n * 4, cudaMemcpyDeviceToHost, st));
+    if (with_collision)
+        MPROS_CUDA(cudaMemcpyAsync(verdicts, d_ver, n, cudaMemcpyDeviceToHost, st));
+    MPROS_CUDA(cudaStreamSynchronize(st));
+    return MPROS_OK;
+}
+
+extern "C" int mpros_rs_solve_batch(mpros_ctx *c, const mpros_rs_params *rp, const double *starts5, const double *goals3, size_t n,
+                                    double *segs, int32_t *nseg, double *cost, double *traj, int traj_cap, int32_t *npts)
+{
+    int rc = check_planner_ready(c, "mpros_rs_solve_batch");
+    if (rc)
+        return rc;
+    return rs_batch_impl(c, rp, starts5, goals3, n, segs, nseg, cost, traj, traj_cap, npts, nullptr, false);
+}
+
+extern "C" int mpros_rs_shot_batch(mpros_ctx *c, const double *starts5, const double *goals3, size_t n, double *segs, int32_t *nseg,
+                                   double *cost, double *traj, int traj_cap, int32_t *npts, uint8_t *verdicts)
+{
+    int rc = check_planner_ready(c, "mpros_rs_shot_batch");
+    if (rc)
+        return rc;
+    return rs_batch_impl(c, nullptr, starts5, goals3, n, segs, nseg, cost, traj, traj_cap, npts, verdicts, true);
+}
+
+extern "C" int mpros_rs_distance_batch(mpros_ctx *c, double rho, const double *a3, const double *b3, size_t n, double *out)
+{
+    if (!c)
+    {
+        set_error("mpros_rs_distance_batch: NULL context");
+        return MPROS_ERR_INVALID;
+    }
+    if (n == 0)
+        return MPROS_OK;
+    if (!a3 || !b3 || !out || !(rho > 0) || n > (size_t)INT32_MAX)
+    {
+        set_error("mpros_rs_distance_batch: NULL / invalid argument");
+        return MPROS_ERR_INVALID;
+    }
+    MPROS_CUDA(cudaSetDevice(c->device));
+    int rc = ensure_stage(c, n * 7 * 8 + 1024);
+    if (rc)
+        return rc;
+    double *d_a = static_cast<double *>(c->stage), *d_b = d_a + 3 * n, *d_o = d_b + 3 * n;
+    cudaStream_t st = c->stream;
+    MPROS_CUDA(cudaMemcpyAsync(d_a, a3, n * 24, cudaMemcpyHostToDevice, st));
+    MPROS_CUDA(cudaMemcpyAsync(d_b, b3, n * 24, cudaMemcpyHostToDevice, st));
+    int blocks = (int)std::min<size_t>((n * 4 + 127) / 128, (size_t)148 * 16);
+    rs_distance_kernel<<<blocks, 128, 0, st>>>(rho, d_a, d_b, (int)n, d_o);
+    MPROS_LAUNCH_CHECK(c);
+    MPROS_CUDA(cudaMemcpyAsync(out, d_o, n * 8, cudaMemcpyDeviceToHost, st));
+    MPROS_CUDA(cudaStreamSynchronize(st));
+    return MPROS_OK;
+}
+
+extern "C" int mpros_expand_batch(mpros_ctx *c, const double *start3, const double *goal3, const double *parents6, size_t n,
+                                  double *prims, double *childs, int32_t *nchild)
+{
+    int rc = check_planner_ready(c, "mpros_expand_batch");
+    if (rc)
+        return rc;
+    if (!c->get_goal)
+    {
+        set_error("mpros_expand_batch: no goal map (mpros_map_update_goal first)"); // hybrid_a_star.cpp:96-100
+        return MPROS_ERR_INVALID;
+    }
+    if (n == 0)
+        return MPROS_OK;
+    if (!goal3 || !parents6 || !prims || !childs || !nchild || n > (size_t)INT32_MAX)
+    {
+        set_error("mpros_expand_batch: NULL / invalid argument");
+        return MPROS_ERR_INVALID;
+    }
+    MPROS_CUDA(cudaSetDevice(c->device));
+    const int P = 2 * c->pv.n_steer;
+    ExpandArgs a;
+    a.n = (int)n;
+    a.gx = goal3[0], a.gy = goal3[1], a.gyaw = goal3[2];
+    a.have_seeds = 0;
+    a.start_idx = a.goal_idx = ~0ull;
+    a.start_g = 0.0;
+    // closed-set seeds of initialize() (hybrid_a_star.cpp:107-112), computed like the device does
+    auto cell_index = [&](const double *pose, unsigned long long &idx) {
+        double dx = pose[0] - c->ox, dy = pose[1] - c->oy;
+        double qj = (dx * c->ocos + dy * c->osin) / c->res, qi = (dx * -c->osin + dy * c->ocos) / c->res;
+        if (!(qi > -1.0 && qi < (double)c->H && qj > -1.0 && qj < (double)c->W))
+            return false;
+        double yaw = pose[2], yaw_pos = yaw < 0 ? yaw + 2 * M_PI : yaw;
+        int iyaw = (int)(yaw_pos / c->pv.yaw_resol);
+        idx = ((unsigned long long)((long long)(int)qi * c->W + (int)qj) * c->pv.num_yaw + (unsigned long long)iyaw) * 2ull + 0;
+        return true;
+    };
+    if (start3)
+    {
+        unsigned long long si, gi;
+        if (cell_index(start3, si) && cell_index(goal3, gi))
+        {
+            a.have_seeds = 1;
+            a.start_idx = si;
+            a.goal_idx = gi;
+            if (si == gi)
+                a.start_idx = ~0ull; // the goal seed overwrites a shared cell
+        }
+    }
+    size_t in_b = n * 6 * 8, pr_b = n * P * 7 * 8, ch_b = n * P * 10 * 8;
+    rc = ensure_stage(c, in_b + pr_b + ch_b + n * 4 + 2048);
+    if (rc)
+        return rc;
+    char *base = static_cast<char *>(c->stage);
+    double *d_in = (double *)base;
+    double *d_pr = (double *)(base + align_up(in_b, 256));
+    double *d_ch = (double *)((char *)d_pr + align_up(pr_b, 256));
+    int32_t *d_nc = (int32_t *)((char *)d_ch + align_up(ch_b, 256));
+    cudaStream_t st = c->stream;
+    MPROS_CUDA(cudaMemcpyAsync(d_in, parents6, in_b, cudaMemcpyHostToDevice, st));
+    MPROS_CUDA(cudaMemsetAsync(d_ch, 0, ch_b, st));
+    a.parents6 = d_in;
+    a.prims = d_pr;
+    a.childs = d_ch;
+    a.nchild = d_nc;
+    int blocks = (int)std::min<size_t>((n + 3) / 4, (size_t)148 * 8);
+    expand_batch_kernel<<<blocks, 128, 0, st>>>(c->view(), c->pv, a);
+    MPROS_LAUNCH_CHECK(c);
+    MPROS_CUDA(cudaMemcpyAsync(prims, d_pr, pr_b, cudaMemcpyDeviceToHost, st));
+    MPROS_CUDA(cudaMemcpyAsync(childs, d_ch, ch_b, cudaMemcpyDeviceToHost, st));
+    MPROS_CUDA(cudaMemcpyAsync(nchild, d_nc, n * 4, cudaMemcpyDeviceToHost, st));
+    MPROS_CUDA(cudaStreamSynchronize(st));
+    return MPROS_OK;
+}
+
+// ---- whole-query planner -------------------------------------------------------------------------------------------------
+namespace mpros
+{
+struct PlanScratch
+{
+    char *ws = nullptr;
+    size_t ws_bytes = 0;
+    unsigned int *counter = nullptr;
+    int32_t *todo = nullptr;
+    size_t todo_cap = 0;
+    uint32_t tag_base = 0;
+};
+static PlanScratch g_plan_scratch[16][3]; // per device, per pass (node-pool size class)
+
+static int plan_pass(mpros_ctx *c, PlanBatchArgs &a, int pass, int node_cap, int n_run, const int32_t *d_todo, int max_warps)
+{
+    PlanScratch &S = g_plan_scratch[c->device & 15][pass];
+    WarpWorkspaceLayout L = make_layout(node_cap, c->H, c->W);
+    // resident warps: 4 per CTA, a multiple of the SM count; bounded by the workspace budget
+    cudaDeviceProp prop;
+    MPROS_CUDA(cudaGetDeviceProperties(&prop, c->device));
+    size_t free_b = 0, total_b = 0;
+    MPROS_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = (free_b + S.ws_bytes) / 2;
+    int per_block = 4;
+    int blocks = prop.multiProcessorCount * 4;
+    blocks = std::min(blocks, (n_run + per_block - 1) / per_block);
+    blocks = std::min<long long>(blocks, std::max<long long>(1, (long long)(budget / L.stride) / per_block));
+    if (max_warps > 0)
+        blocks = std::min(blocks, std::max(1, max_warps / per_block));
+    size_t need = (size_t)blocks * per_block * L.stride;
+    if (need > S.ws_bytes)
+    {
+        if (S.ws)
+            MPROS_CUDA(cudaFree(S.ws));
+        S.ws = nullptr;
+        S.ws_bytes = 0;
+        MPROS_CUDA(cudaMalloc(&S.ws, need));
+        MPROS_CUDA(cudaMemsetAsync(S.ws, 0, need, c->stream));
+        S.ws_bytes = need;
+        S.tag_base = 0;
+    }
+    if (!S.counter)
+        MPROS_CUDA(cudaMalloc(&S.counter, 256));
+    // generation tags must stay below 2^30 and unique per (warp, query); every warp handles < n_run queries
+    if ((unsigned long long)S.tag_base + (unsigned long long)n_run + 2ull >= (1ull << 30))
+    {
+        MPROS_CUDA(cudaMemsetAsync(S.ws, 0, S.ws_bytes, c->stream));
+        S.tag_base = 0;
+    }
+    // a different layout re-interprets the same bytes: stale tags could alias, so clear when the layout changes
+    static WarpWorkspaceLayout last_layout[16][3];
+    WarpWorkspaceLayout &prev = last_layout[c->device & 15][pass];
+    if (std::memcmp(&prev, &L, sizeof(L)) != 0)
+    {
+        MPROS_CUDA(cudaMemsetAsync(S.ws, 0, S.ws_bytes, c->stream));
+        S.tag_base = 0;
+        prev = L;
+    }
+    MPROS_CUDA(cudaMemsetAsync(S.counter, 0, 4, c->stream));
+    a.L = L;
+    a.ws = S.ws;
+    a.counter = S.counter;
+    a.tag_base = S.tag_base;
+    a.todo = d_todo;
+    a.n_todo = n_run;
+    plan_batch_kernel<<<blocks, per_block * 32, 0, c->stream>>>(c->view(), c->pv, a);
+    MPROS_LAUNCH_CHECK(c);
+    S.tag_base += (uint32_t)n_run + 1;
+    return MPROS_OK;
+}
+} // namespace mpros
+
+static int plan_batch_dev_impl(mpros_ctx *c, const double *d_starts, const double *d_goals, int nq, int32_t *d_status, double *d_cost,
+                               int32_t *d_path_len, double *d_paths, int path_cap, int64_t *d_stats)
+{
+    PlanBatchArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.starts = d_starts;
+    a.goals = d_goals;
+    a.nq = nq;
+    a.status = d_status;
+    a.cost = d_cost;
+    a.path_len = d_path_len;
+    a.paths = d_paths;
+    a.path_cap = path_cap;
+    a.stats = d_stats;
+    a.rs = rs_config_from_planner(c);
+    a.optimal = c->pp.optimal_path;
+    PlanScratch &S = g_plan_scratch[c->device & 15][0];
+    // pass 1: every query with a small node pool; later passes: only the queries that overflowed, bigger pools
+    const long long max_nodes = (long long)(c->pp.max_iteration + 2) * (2 * c->pv.n_steer) + 16;
+    long long caps[3] = {4096, 131072, max_nodes};
+    int rc = plan_pass(c, a, 0, (int)std::min<long long>(caps[0], max_nodes), nq, nullptr, 0);
+    if (rc)
+        return rc;
+    if (caps[0] >= max_nodes)
+        return MPROS_OK;
+    std::vector<int32_t> h_status(nq);
+    for (int pass = 1; pass < 3; ++pass)
+    {
+        MPROS_CUDA(cudaMemcpyAsync(h_status.data(), d_status, (size_t)nq * 4, cudaMemcpyDeviceToHost, c->stream));
+        MPROS_CUDA(cudaStreamSynchronize(c->stream));
+        std::vector<int32_t> todo;
+        for (int q = 0; q < nq; ++q)
+            if (h_status[q] == ST_OVERFLOW)
+                todo.push_back(q);
+        if (todo.empty())
+            break;
+        if (todo.size() > S.todo_cap)
+        {
+            if (S.todo)
+                MPROS_CUDA(cudaFree(S.todo));
+            S.todo = nullptr;
+            MPROS_CUDA(cudaMalloc(&S.todo, todo.size() * 4 + 1024));
+            S.todo_cap = todo.size() + 256;
+        }
+        MPROS_CUDA(cudaMemcpyAsync(S.todo, todo.data(), todo.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        long long cap = std::min(caps[pass], max_nodes);
+        rc = plan_pass(c, a, pass, (int)cap, (int)todo.size(), S.todo, 0);
+        if (rc)
+            return rc;
+        if (cap >= max_nodes)
+            break;
+    }
+    return MPROS_OK;
+}
+
+extern "C" int mpros_plan_batch_dev(mpros_ctx *c, const double *d_starts3, const double *d_goals3, size_t nq, int32_t *d_status,
+                                    double *d_cost, int32_t *d_path_len, double *d_paths, int path_cap, int64_t *d_stats)
+{
+    int rc = check_planner_ready(c, "mpros_plan_batch_dev");
+    if (rc)
+        return rc;
+    if (nq == 0)
+        return MPROS_OK;
+    if (!d_starts3 || !d_goals3 || !d_status || !d_cost || !d_path_len || path_cap < 0 || (path_cap > 0 && !d_paths) ||
+        nq > (size_t)(1 << 28))
+    {
+        set_error("mpros_plan_batch_dev: NULL / invalid argument");
+        return MPROS_ERR_INVALID;
+    }
+    if ((unsigned long long)c->H * c->W * c->pv.num_yaw * 2ull >= (1ull << 34))
+    {
+        set_error("mpros_plan_batch: H*W*yaw*2 exceeds the closed-set key range (2^34)");
+        return MPROS_ERR_INVALID;
+    }
+    MPROS_CUDA(cudaSetDevice(c->device));
+    return plan_batch_dev_impl(c, d_starts3, d_goals3, (int)nq, d_status, d_cost, d_path_len, d_paths, path_cap, d_stats);
+}
+
+extern "C" int mpros_plan_batch(mpros_ctx *c, const double *starts3, const double *goals3, size_t nq, int32_t *status, double *cost,
+                                int32_t *path_len, double *paths, int path_cap, int64_t *stats)
+{
+    int rc = check_planner_ready(c, "mpros_plan_batch");
+    if (rc)
+        return rc;
+    if (nq == 0)
+        return MPROS_OK;
+    if (!starts3 || !goals3 || !status || !cost || !path_len || path_cap < 0 || (path_cap > 0 && !paths) || nq > (size_t)(1 << 28))
+    {
+        set_error("mpros_plan_batch: NULL / invalid argument");
+        return MPROS_ERR_INVALID;
+    }
+    if ((unsigned long long)c->H * c->W * c->pv.num_yaw * 2ull >= (1ull << 34))
+    {
+        set_error("mpros_plan_batch: H*W*yaw*2 exceeds the closed-set key range (2^34)");
+        return MPROS_ERR_INVALID;
+    }
+    MPROS_CUDA(cudaSetDevice(c->device));
+    size_t pose_b = nq * 24, path_b = nq * (size_t)path_cap * 5 * 8;
+    size_t total = 2 * align_up(pose_b, 256) + align_up(nq * 4, 256) * 2 + align_up(nq * 8, 256) + align_up(path_b, 256) +
+                   align_up(nq * 32, 256) + 1024;
+    rc = ensure_stage(c, total);
+    if (rc)
+        return rc;
+    char *base = static_cast<char *>(c->stage);
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        char *p = base + o;
+        o += align_up(bytes, 256);
+        return p;
+    };
+    double *d_s = (double *)take(pose_b), *d_g = (double *)take(pose_b);
+    int32_t *d_status = (int32_t *)take(nq * 4), *d_len = (int32_t *)take(nq * 4);
+    double *d_cost = (double *)take(nq * 8);
+    double *d_paths = path_cap ? (double *)take(path_b) : nullptr;
+    int64_t *d_stats = (int64_t *)take(nq * 32);
+    cudaStream_t st = c->stream;
+    MPROS_CUDA(cudaMemcpyAsync(d_s, starts3, pose_b, cudaMemcpyHostToDevice, st));
+    MPROS_CUDA(cudaMemcpyAsync(d_g, goals3, pose_b, cudaMemcpyHostToDevice, st));
+    rc = plan_batch_dev_impl(c, d_s, d_g, (int)nq, d_status, d_cost, d_len, d_paths, path_cap, d_stats);
+    if (rc)
+        return rc;
+    MPROS_CUDA(cudaMemcpyAsync(status, d_status, nq * 4, cudaMemcpyDeviceToHost, st));
+    MPROS_CUDA(cudaMemcpyAsync(cost, d_cost, nq * 8, cudaMemcpyDeviceToHost, st));
+    MPROS_CUDA(cudaMemcpyAsync(path_len, d_len, nq * 4, cudaMemcpyDeviceToHost, st));
+    if (path_cap)
+        MPROS_CUDA(cudaMemcpyAsync(paths, d_paths, path_b, cudaMemcpyDeviceToHost, st));
+    if (stats)
+        MPROS_CUDA(cudaMemcpyAsync(stats, d_stats, nq * 32, cudaMemcpyDeviceToHost, st));
+    MPROS_CUDA(cudaStreamSynchronize(st));
+    return MPROS_OK;
+}

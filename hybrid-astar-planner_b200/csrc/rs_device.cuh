@@ -1,0 +1,585 @@
+// Device-side Reeds-Shepp machinery.
+//  * RS generator of mpros_rs_path (rs_curve.cpp / rs_curve_basic.h): the reference's own 12 word formulas x 4
+//    symmetries WITH their quirks (path4's asin, PathSeg sign handling, positional penalty mix-up), penalty-weighted
+//    first-wins minimum, sequential pose integration (GenTraj).
+//  * OMPL-equivalent Reeds-Shepp distance used by the heuristic (rs_statespace.h:50-54).
+// Warp-cooperative: one warp works on one query; lanes spread over candidates / symmetry images.
+#pragma once
+#include <cfloat>
+
+#include "mpros_internal.cuh"
+
+namespace mpros
+{
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kPi2 = 1.57079632679489661923; // M_PI_2
+constexpr unsigned kFull = 0xffffffffu;
+
+struct RsConfig
+{
+    double radius, steer_angle, step;
+    // as RSCurve::setPenalty receives them positionally (rs_curve.cpp:314-323)
+    double pen_gear, pen_back, pen_steer_change, pen_steer_angle;
+};
+
+struct RsSeg
+{
+    double len;
+    int steer, dir;
+};
+struct RsPath
+{
+    RsSeg s[5];
+    int n;
+};
+
+__device__ __forceinline__ void rs_push(RsPath &p, double value, int steer, int dir)
+{
+    // PathSeg ctor (rs_curve_basic.h:84-88): |value|; direction flips unless value > 0 (also for 0 and NaN)
+    p.s[p.n].len = fabs(value);
+    p.s[p.n].steer = steer;
+    p.s[p.n].dir = (value > 0 ? dir : -dir);
+    ++p.n;
+}
+__device__ __forceinline__ double rs_regular_rad(double t) // rs_curve_basic.h:113-124
+{
+    if (t > kPi)
+        return t - 2 * kPi;
+    else if (t < -kPi)
+        return t + 2 * kPi;
+    return t;
+}
+
+// PathFunction::path1..12 (rs_curve.cpp:353-599). dist/theta: PolarCoord of the formula's own argument.
+__device__ __noinline__ void rs_formula(int f, double x, double y, double phi, RsPath &p)
+{
+    p.n = 0;
+    double sphi, cphi;
+    sincos(phi, &sphi, &cphi);
+    const bool typeA = (f == 0 || f == 2 || f == 3 || f == 4 || f == 7 || f == 9);
+    double ax = typeA ? x - sphi : x + sphi;
+    double ay = typeA ? y - 1 + cphi : y - 1 - cphi;
+    double dist = hypot(ax, ay), theta = atan2(ay, ax);
+    const int L_ = 1, S_ = 0, R_ = -1, F_ = 1, B_ = -1;
+    switch (f)
+    {
+    case 0:
+    {
+        double u = dist, t = theta, v = rs_regular_rad(phi - t);
+        rs_push(p, t, L_, F_), rs_push(p, u, S_, F_), rs_push(p, v, L_, F_);
+        break;
+    }
+    case 1:
+        if (dist * dist >= 4)
+        {
+            double u = sqrt(dist * dist - 4);
+            double t = rs_regular_rad(theta + atan2(2.0, u));
+            double v = rs_regular_rad(t - phi);
+            rs_push(p, t, L_, F_), rs_push(p, u, S_, F_), rs_push(p, v, R_, F_);
+        }
+        break;
+    case 2:
+        if (dist <= 4)
+        {
+            double A = acos(dist / 4);
+            double u = rs_regular_rad(kPi - 2 * A);
+            double t = rs_regular_rad(kPi2 + A + theta);
+            double v = rs_regular_rad(phi - t - u);
+            rs_push(p, t, L_, F_), rs_push(p, u, R_, B_), rs_push(p, v, L_, F_);
+        }
+        break;
+    case 3:
+        if (dist <= 4)
+        {
+            double A = acos(dist / 4);
+            double u = rs_regular_rad(kPi - 2 * A);
+            double t = asin(theta + kPi2 + A); // sic, rs_curve.cpp:418
+            double v = rs_regular_rad(t + u - phi);
+            rs_push(p, t, L_, F_), rs_push(p, u, R_, B_), rs_push(p, v, L_, B_);
+        }
+        break;
+    case 4:
+        if (dist <= 4)
+        {
+            double u = acos(1 - dist * dist / 8);
+            double A = asin(2 * sin(u) / dist);
+            double t = rs_regular_rad(theta + kPi2 - A);
+            double v = rs_regular_rad(t - u - phi);
+            rs_push(p, t, L_, F_), rs_push(p, u, R_, F_), rs_push(p, v, L_, B_);
+        }
+        break;
+    case 5:
+        if (dist <= 4)
+        {
+            double A, t, u, v;
+            if (dist <= 2)
+            {
+                A = acos((dist + 2) / 4);
+                t = rs_regular_rad(theta + kPi2 + A);
+                u = rs_regular_rad(A);
+                v = rs_regular_rad(phi - t + 2 * u);
+            }
+            else
+            {
+                A = acos((dist - 2) / 4);
+                t = rs_regular_rad(theta + kPi2 - A);
+                u = rs_regular_rad(kPi - A);
+                v = rs_regular_rad(phi - t + 2 * u);
+            }
+            rs_push(p, t, L_, F_), rs_push(p, u, R_, F_), rs_push(p, u, L_, B_), rs_push(p, v, R_, B_);
+        }
+        break;
+    case 6:
+    {
+        double u1 = (20 - dist * dist) / 16;
+        if (dist <= 6 && u1 >= 0 && u1 <= 1)
+        {
+            double u = acos(u1);
+            double A = asin(2 * sin(u) / dist);
+            double t = rs_regular_rad(theta + kPi2 + A);
+            double v = rs_regular_rad(t - phi);
+            rs_push(p, t, L_, F_), rs_push(p, u, R_, B_), rs_push(p, u, L_, B_), rs_push(p, v, R_, F_);
+        }
+        break;
+    }
+    case 7:
+        if (dist >= 2)
+        {
+            double u = sqrt(dist * dist - 4) - 2;
+            double A = atan2(2.0, u + 2);
+            double t = rs_regular_rad(theta + kPi2 + A);
+            double v = rs_regular_rad(t - phi + kPi2);
+            rs_push(p, t, L_, F_), rs_push(p, kPi2, R_, B_), rs_push(p, u, S_, B_), rs_push(p, v, L_, B_);
+        }
+        break;
+    case 8:
+        if (dist >= 2)
+        {
+            double t = rs_regular_rad(theta + kPi2);
+            double u = dist - 2;
+            double v = rs_regular_rad(phi - t - kPi2);
+            rs_push(p, t, L_, F_), rs_push(p, kPi2, R_, B_), rs_push(p, u, S_, B_), rs_push(p, v, R_, B_);
+        }
+        break;
+    case 9:
+        if (dist >= 2)
+        {
+            double u = sqrt(dist * dist - 4) - 2;
+            double A = atan2(u + 2, 2.0);
+            double t = rs_regular_rad(theta + kPi2 - A);
+            double v = rs_regular_rad(t - phi - kPi2);
+            rs_push(p, t, L_, F_), rs_push(p, u, S_, F_), rs_push(p, kPi2, R_, F_), rs_push(p, v, L_, B_);
+        }
+        break;
+    case 10:
+        if (dist >= 2)
+        {
+            double u = dist - 2;
+            double t = rs_regular_rad(theta);
+            double v = rs_regular_rad(phi - t - kPi2);
+            rs_push(p, t, L_, F_), rs_push(p, u, S_, F_), rs_push(p, kPi2, L_, F_), rs_push(p, v, R_, B_);
+        }
+        break;
+    case 11:
+        if (dist >= 4)
+        {
+            double u = sqrt(dist * dist - 4) - 4;
+            double A = atan2(2.0, u + 4);
+            double t = rs_regular_rad(theta + kPi2 + A);
+            double v = rs_regular_rad(t - phi);
+            rs_push(p, t, L_, F_), rs_push(p, kPi2, R_, B_), rs_push(p, u, S_, B_), rs_push(p, kPi2, L_, B_),
+                rs_push(p, v, R_, F_);
+        }
+        break;
+    default:
+        break;
+    }
+}
+
+// Timeflip / Reflect (rs_curve.cpp:31-49): each segment is re-constructed through the PathSeg ctor with its
+// (non-negative) length, so zero-length and NaN segments flip their direction once more.
+__device__ __forceinline__ void rs_timeflip(RsPath &p)
+{
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+        if (k < p.n)
+        {
+            int d = -p.s[k].dir;
+            p.s[k].dir = (p.s[k].len > 0 ? d : -d);
+        }
+}
+__device__ __forceinline__ void rs_reflect(RsPath &p)
+{
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+        if (k < p.n)
+        {
+            p.s[k].steer = -p.s[k].steer;
+            p.s[k].dir = (p.s[k].len > 0 ? p.s[k].dir : -p.s[k].dir);
+        }
+}
+
+// RSCurve::PathLength (rs_curve.cpp:60-97)
+__device__ __forceinline__ double rs_path_length(const RsConfig &c, const RsPath &path, int start_direc, double start_steer)
+{
+    double length = 0, penalty = 0;
+    int last_steer = (int)start_steer; // int initialised from a double (:64)
+    if (path.n == 0)
+        return 10000;
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+        if (i < path.n)
+        {
+            const RsSeg &seg = path.s[i];
+            if (seg.dir != start_direc)
+                penalty += c.pen_gear;
+            if (seg.dir < 0)
+                penalty += c.pen_back * seg.len * c.radius;
+            if (seg.steer != last_steer)
+                penalty += c.pen_steer_change * (double)abs(seg.steer - last_steer) * c.steer_angle;
+            if (seg.steer != 0)
+                penalty += c.pen_steer_angle * (double)abs(seg.steer) * c.steer_angle;
+            length += seg.len * c.radius;
+            last_steer = seg.steer;
+        }
+    return (length + penalty) * (1.0 + 1e-3);
+}
+
+// RSCurve::FindOptimalPath (rs_curve.cpp:111-163), one warp per shot. Candidate c = 4*f + j (f formula, j symmetry)
+// in the reference's evaluation order; multimap.begin() = smallest cost, first inserted among equals.
+// All lanes return the same best path / cost.
+__device__ __forceinline__ double rs_find_optimal_warp(const RsConfig &c, double sx, double sy, double sphi, int start_direc,
+                                                       double start_steer, double ex, double ey, double ephi, RsPath &best)
+{
+    const int lane = threadIdx.x & 31;
+    // NewGoalPoint (:51-58)
+    double dx = ex - sx, dy = ey - sy;
+    double cs, sn;
+    sincos(sphi, &sn, &cs);
+    double gx = (dx * cs + dy * sn) / c.radius;
+    double gy = (-dx * sn + dy * cs) / c.radius;
+    double gphi = ephi - sphi;
+
+    double my_cost = 0;
+    int my_c = 1 << 20; // "no candidate"
+    RsPath my;
+    my.n = 0;
+#pragma unroll 1
+    for (int round = 0; round < 2; ++round)
+    {
+        int cand = lane + 32 * round;
+        if (cand < 48)
+        {
+            int f = cand >> 2, j = cand & 3;
+            RsPath p;
+            double x = (j == 1 || j == 3) ? -gx : gx;
+            double y = (j == 2 || j == 3) ? -gy : gy;
+            double ph = (j == 1 || j == 2) ? -gphi : gphi;
+            rs_formula(f, x, y, ph, p);
+            if (j == 1 || j == 3)
+                rs_timeflip(p);
+            if (j == 2 || j == 3)
+                rs_reflect(p);
+            double len = rs_path_length(c, p, start_direc, start_steer);
+            bool nan_seg = false;
+#pragma unroll
+            for (int k = 0; k < 5; ++k)
+                if (k < p.n && isnan(p.s[k].len))
+                    nan_seg = true;
+            bool ok = (len != 0.0) && !nan_seg; // :150 (NaN cost counts as true but implies a NaN segment)
+            if (ok && (my_c >= (1 << 20) || len < my_cost))
+            {
+                my_cost = len;
+                my_c = cand;
+                my = p;
+            }
+        }
+    }
+    // warp arg-min over (cost, candidate index); costs are never NaN here
+    double bc = my_cost;
+    int bi = my_c;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        double oc = __shfl_xor_sync(kFull, bc, o);
+        int oi = __shfl_xor_sync(kFull, bi, o);
+        bool take = (oi < (1 << 20)) && (bi >= (1 << 20) || oc < bc || (oc == bc && oi < bi));
+        if (take)
+        {
+            bc = oc;
+            bi = oi;
+        }
+    }
+    // owner lane broadcasts its path
+    int owner = __ffs(__ballot_sync(kFull, my_c == bi && bi < (1 << 20))) - 1;
+    if (owner < 0)
+    {
+        best.n = 0;
+        return 0.0; // unreachable: formula 0 always yields a candidate
+    }
+    best.n = __shfl_sync(kFull, my.n, owner);
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+    {
+        best.s[k].len = __shfl_sync(kFull, my.s[k].len, owner);
+        best.s[k].steer = __shfl_sync(kFull, my.s[k].steer, owner);
+        best.s[k].dir = __shfl_sync(kFull, my.s[k].dir, owner);
+    }
+    return bc;
+}
+
+// RSCurve::GenTraj (rs_curve.cpp:165-222): sequential pose integration, executed by ONE lane.
+// out_xyz: n x 3 {x, y, yaw}; out_sd (optional): n x 2 {steer*steer_angle, direc}. Returns the number of poses the
+// reference would generate (may exceed cap; only the first cap are stored).
+__device__ __noinline__ int rs_gen_traj(const RsConfig &c, double sx, double sy, double syaw, const RsPath &path, double *out_xyz,
+                                        double *out_sd, int cap)
+{
+    const double curve_min_num = 3;
+    double curr_x = sx, curr_y = sy, curr_yaw = syaw;
+    int n = 0;
+#pragma unroll 1
+    for (int k = 0; k < path.n; ++k)
+    {
+        const RsSeg seg = path.s[k];
+        int num_pt = (int)fmax(ceil(seg.len * c.radius / c.step), curve_min_num);
+        double direc = (double)seg.dir;
+        if (seg.steer != 0)
+        {
+            double dyaw = seg.len / num_pt;
+            double sd, cd;
+            sincos(dyaw, &sd, &cd);
+            double dx = sd * c.radius * direc;
+            double dy = (1 - cd) * c.radius * (double)seg.steer;
+#pragma unroll 1
+            for (int i = 0; i < num_pt; ++i)
+            {
+                double sy_, cy_;
+                sincos(curr_yaw, &sy_, &cy_);
+                double nx = curr_x + (dx * cy_ - dy * sy_);
+                double ny = curr_y + (dx * sy_ + dy * cy_);
+                curr_x = nx;
+                curr_y = ny;
+                curr_yaw += dyaw * direc * (double)seg.steer;
+                curr_yaw = rs_regular_rad(curr_yaw);
+                if (n < cap)
+                {
+                    out_xyz[3 * n] = curr_x, out_xyz[3 * n + 1] = curr_y, out_xyz[3 * n + 2] = curr_yaw;
+                    if (out_sd)
+                        out_sd[2 * n] = (double)seg.steer * c.steer_angle, out_sd[2 * n + 1] = direc;
+                }
+                ++n;
+            }
+        }
+        else
+        {
+            double step = seg.len * c.radius / num_pt;
+            double sy_, cy_;
+            sincos(curr_yaw, &sy_, &cy_);
+#pragma unroll 1
+            for (int i = 0; i < num_pt; ++i)
+            {
+                curr_x += step * cy_ * direc;
+                curr_y += step * sy_ * direc;
+                if (n < cap)
+                {
+                    out_xyz[3 * n] = curr_x, out_xyz[3 * n + 1] = curr_y, out_xyz[3 * n + 2] = curr_yaw;
+                    if (out_sd)
+                        out_sd[2 * n] = (double)seg.steer * c.steer_angle, out_sd[2 * n + 1] = direc;
+                }
+                ++n;
+            }
+        }
+    }
+    return n;
+}
+
+// ---- OMPL-equivalent Reeds-Shepp distance ---------------------------------------------------
+// The oracle's stand-in for ompl::base::ReedsSheppStateSpace::distance is the specification (parity unpinned vs real
+// OMPL, see oracle/port/ompl_rs_distance.h); this mirrors it operation for operation.
+__device__ __forceinline__ double ompl_mod2pi(double x)
+{
+    double v = fmod(x, 2.0 * kPi);
+    if (v < -kPi)
+        v += 2.0 * kPi;
+    else if (v > kPi)
+        v -= 2.0 * kPi;
+    return v;
+}
+constexpr double kOmplZero = 10.0 * DBL_EPSILON;
+
+__device__ __forceinline__ void ompl_tau_omega(double u, double v, double xi, double eta, double phi, double &tau, double &omega)
+{
+    double delta = ompl_mod2pi(u - v);
+    double su, cu, sd, cd;
+    sincos(u, &su, &cu);
+    sincos(delta, &sd, &cd);
+    double A = su - sd, B = cu - cd - 1.;
+    double t1 = atan2(eta * A - xi * B, xi * A + eta * B), t2 = 2. * (cd - cos(v) - cu) + 3;
+    tau = (t2 < 0) ? ompl_mod2pi(t1 + kPi) : ompl_mod2pi(t1);
+    omega = ompl_mod2pi(tau - u + v - phi);
+}
+
+// All base formulas on one image (x, y, phi) and its "backwards" point; returns candidate lengths per family:
+//   csc_ccc_cccc = min over CSC, CCC (normal + backwards), CCCC candidates; ccsc = min over CCSC candidates (without the
+//   fixed pi/2); ccscc = CCSCC candidate (without the fixed pi). DBL_MAX = no candidate.
+__device__ __noinline__ void ompl_families(double x, double y, double phi, double xb, double yb, double &m_plain, double &m_ccsc,
+                                           double &m_ccscc)
+{
+    m_plain = DBL_MAX;
+    m_ccsc = DBL_MAX;
+    m_ccscc = DBL_MAX;
+    double sphi, cphi;
+    sincos(phi, &sphi, &cphi);
+    double t, u, v;
+    // ---- arguments shared by several formulas
+    const double xm = x - sphi, ym = y - 1. + cphi; // (xi, eta) of LpSpLp / LpRmL / LpRmSmLm
+    const double xp = x + sphi, yp = y - 1. - cphi; // (xi, eta) of LpSpRp / CCCC / LpRmSmRm / LpRmSLmRp
+    // LpSpLp (8.1)
+    {
+        u = sqrt(xm * xm + ym * ym);
+        t = atan2(ym, xm);
+        if (t >= -kOmplZero)
+        {
+            v = ompl_mod2pi(phi - t);
+            if (v >= -kOmplZero)
+                m_plain = fmin(m_plain, fabs(t) + fabs(u) + fabs(v));
+        }
+    }
+    // LpSpRp (8.2)
+    {
+        double u1 = sqrt(xp * xp + yp * yp), t1 = atan2(yp, xp);
+        u1 = u1 * u1;
+        if (u1 >= 4.)
+        {
+            u = sqrt(u1 - 4.);
+            double theta = atan2(2., u);
+            t = ompl_mod2pi(t1 + theta);
+            v = ompl_mod2pi(t - phi);
+            if (t >= -kOmplZero && v >= -kOmplZero)
+                m_plain = fmin(m_plain, fabs(t) + fabs(u) + fabs(v));
+        }
+    }
+    // LpRmL (8.3/8.4) on the point and on the backwards point
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+    {
+        double xi = b ? xb - sphi : xm, eta = b ? yb - 1. + cphi : ym;
+        double u1 = sqrt(xi * xi + eta * eta), theta = atan2(eta, xi);
+        if (u1 <= 4.)
+        {
+            u = -2. * asin(.25 * u1);
+            t = ompl_mod2pi(theta + .5 * u + kPi);
+            v = ompl_mod2pi(phi - t + u);
+            if (t >= -kOmplZero && u <= kOmplZero)
+                m_plain = fmin(m_plain, fabs(t) + fabs(u) + fabs(v));
+        }
+    }
+    // LpRupLumRm (8.7)
+    {
+        double rho = .25 * (2. + sqrt(xp * xp + yp * yp));
+        if (rho <= 1.)
+        {
+            u = acos(rho);
+            ompl_tau_omega(u, -u, xp, yp, phi, t, v);
+            if (t >= -kOmplZero && v <= kOmplZero)
+                m_plain = fmin(m_plain, fabs(t) + 2. * fabs(u) + fabs(v));
+        }
+    }
+    // LpRumLumRp (8.8)
+    {
+        double rho = (20. - xp * xp - yp * yp) / 16.;
+        if (rho >= 0 && rho <= 1)
+        {
+            u = -acos(rho);
+            if (u >= -.5 * kPi)
+            {
+                ompl_tau_omega(u, u, xp, yp, phi, t, v);
+                if (t >= -kOmplZero && v >= -kOmplZero)
+                    m_plain = fmin(m_plain, fabs(t) + 2. * fabs(u) + fabs(v));
+            }
+        }
+    }
+    // LpRmSmLm (8.9) and LpRmSmRm (8.10), on the point and on the backwards point
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+    {
+        double xi = b ? xb - sphi : xm, eta = b ? yb - 1. + cphi : ym;
+        double rho = sqrt(xi * xi + eta * eta), theta = atan2(eta, xi);
+        if (rho >= 2.)
+        {
+            double r = sqrt(rho * rho - 4.);
+            u = 2. - r;
+            t = ompl_mod2pi(theta + atan2(r, -2.));
+            v = ompl_mod2pi(phi - .5 * kPi - t);
+            if (t >= -kOmplZero && u <= kOmplZero && v <= kOmplZero)
+                m_ccsc = fmin(m_ccsc, fabs(t) + fabs(u) + fabs(v));
+        }
+        double xi2 = b ? xb + sphi : xp, eta2 = b ? yb - 1. - cphi : yp;
+        double rho2 = sqrt(eta2 * eta2 + xi2 * xi2), theta2 = atan2(xi2, -eta2); // polar(-eta, xi)
+        if (rho2 >= 2.)
+        {
+            t = theta2;
+            u = 2. - rho2;
+            v = ompl_mod2pi(t + .5 * kPi - phi);
+            if (t >= -kOmplZero && u <= kOmplZero && v <= kOmplZero)
+                m_ccsc = fmin(m_ccsc, fabs(t) + fabs(u) + fabs(v));
+        }
+    }
+    // LpRmSLmRp (8.11)
+    {
+        double rho = sqrt(xp * xp + yp * yp);
+        if (rho >= 2.)
+        {
+            u = 4. - sqrt(rho * rho - 4.);
+            if (u <= kOmplZero)
+            {
+                t = ompl_mod2pi(atan2((4. - u) * xp - 2. * yp, -2. * xp + (u - 4.) * yp));
+                v = ompl_mod2pi(t - phi);
+                if (t >= -kOmplZero && v >= -kOmplZero)
+                    m_ccscc = fmin(m_ccscc, fabs(t) + fabs(u) + fabs(v));
+            }
+        }
+    }
+}
+
+// Groups of 4 consecutive lanes cooperate on one (start -> goal) pair: lane (q = lane & 3) evaluates symmetry image q
+// of every base formula; the family minima are combined across the group with shuffles. All 4 lanes of the group get
+// the result. Inactive groups must still call this (full-warp shuffles) with any finite arguments.
+__device__ __forceinline__ double ompl_rs_distance_quad(double rho, double x1, double y1, double th1, double x2, double y2,
+                                                        double th2)
+{
+    const int q = threadIdx.x & 3;
+    double dx = x2 - x1, dy = y2 - y1, dth = th2 - th1;
+    double c, s;
+    sincos(th1, &s, &c);
+    double x = (c * dx + s * dy) / rho, y = (-s * dx + c * dy) / rho;
+    // backwards point of the un-flipped image; its images follow the same sign pattern
+    double sphi, cphi;
+    sincos(dth, &sphi, &cphi);
+    double xb = x * cphi + y * sphi, yb = x * sphi - y * cphi;
+    const bool fx = (q == 1 || q == 3), fy = (q == 2 || q == 3), fp = (q == 1 || q == 2);
+    double m_plain, m_ccsc, m_ccscc;
+    ompl_families(fx ? -x : x, fy ? -y : y, fp ? -dth : dth, fx ? -xb : xb, fy ? -yb : yb, m_plain, m_ccsc, m_ccscc);
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1)
+    {
+        m_plain = fmin(m_plain, __shfl_xor_sync(kFull, m_plain, o));
+        m_ccsc = fmin(m_ccsc, __shfl_xor_sync(kFull, m_ccsc, o));
+        m_ccscc = fmin(m_ccscc, __shfl_xor_sync(kFull, m_ccscc, o));
+    }
+    double best = m_plain;
+    {
+        double l0 = best - .5 * kPi;
+        if (m_ccsc < l0)
+            best = m_ccsc + .5 * kPi;
+    }
+    {
+        double l0 = best - kPi;
+        if (m_ccscc < l0)
+            best = m_ccscc + kPi;
+    }
+    return rho * best;
+}
+
+} // namespace mpros

@@ -81,6 +81,21 @@ class MapInfo(C.Structure):
     ]
 
 
+class RsParams(C.Structure):
+    _fields_ = [
+        ("radius", C.c_double),
+        ("steering_angle", C.c_double),
+        ("step_size", C.c_double),
+        ("pen_gear", C.c_double),
+        ("pen_backward", C.c_double),
+        ("pen_steer_change", C.c_double),
+        ("pen_steer_angle", C.c_double),
+    ]
+
+
+PLAN_FOUND, PLAN_LIMIT, PLAN_OPEN_EMPTY, PLAN_NOT_INIT, PLAN_OVERFLOW = 1, 0, -1, -2, -3
+
+
 class MprosError(RuntimeError):
     pass
 
@@ -116,10 +131,18 @@ def load_library(path=LIB_PATH):
     L.mpros_map_update_goal.argtypes = [vp, d, d]
     L.mpros_map_get_info.argtypes = [vp, C.POINTER(MapInfo)]
     L.mpros_map_download.argtypes = [vp, i, vp, sz]
+    L.mpros_map_upload.argtypes = [vp, i, vp, sz]
     L.mpros_map_point_in_collision.argtypes = [vp, i, vp, sz, vp]
     L.mpros_collision_check_poses.argtypes = [vp, vp, sz, vp]
     L.mpros_collision_check_poses_dev.argtypes = [vp, vp, sz, vp]
     L.mpros_collision_check_paths.argtypes = [vp, vp, vp, sz, vp]
+    L.mpros_rs_default_config.argtypes = [vp, C.POINTER(RsParams)]
+    L.mpros_rs_solve_batch.argtypes = [vp, C.POINTER(RsParams), vp, vp, sz, vp, vp, vp, vp, i, vp]
+    L.mpros_rs_shot_batch.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, i, vp, vp]
+    L.mpros_rs_distance_batch.argtypes = [vp, d, vp, vp, sz, vp]
+    L.mpros_expand_batch.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp]
+    L.mpros_plan_batch.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, i, vp]
+    L.mpros_plan_batch_dev.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, i, vp]
     _lib = L
     return L
 
@@ -239,6 +262,10 @@ class Context:
         self._check(self.L.mpros_map_download(self.h, lid, out.ctypes.data, out.nbytes))
         return out
 
+    def upload_voronoi(self, v):
+        v = np.ascontiguousarray(v, dtype=np.float32)
+        self._check(self.L.mpros_map_upload(self.h, LAYERS["voronoi"][0], v.ctypes.data, v.nbytes))
+
     def point_in_collision(self, layer, ij):
         ij = np.ascontiguousarray(ij, dtype=np.int32).reshape(-1, 2)
         out = np.zeros(len(ij), dtype=np.uint8)
@@ -261,6 +288,77 @@ class Context:
         out = np.zeros(len(offsets) - 1, dtype=np.uint8)
         self._check(self.L.mpros_collision_check_paths(self.h, poses.ctypes.data, offsets.ctypes.data, len(out), out.ctypes.data))
         return out
+
+    # ---- Reeds-Shepp ----
+    def rs_default_config(self):
+        p = RsParams()
+        self._check(self.L.mpros_rs_default_config(self.h, C.byref(p)))
+        return p
+
+    def rs_solve_batch(self, starts5, goals3, traj_cap=64, rs=None, shot=False):
+        """RSCurve FindOptimalPath + GetTraj for n shots. Returns dict(segs[n,5,3], nseg, cost, traj[n,cap,5], npts
+        [, verdicts])."""
+        s = np.ascontiguousarray(starts5, dtype=np.float64).reshape(-1, 5)
+        g = np.ascontiguousarray(goals3, dtype=np.float64).reshape(-1, 3)
+        n = len(s)
+        segs = np.zeros((n, 5, 3))
+        nseg = np.zeros(n, dtype=np.int32)
+        cost = np.zeros(n)
+        traj = np.zeros((n, traj_cap, 5))
+        npts = np.zeros(n, dtype=np.int32)
+        out = {"segs": segs, "nseg": nseg, "cost": cost, "traj": traj, "npts": npts}
+        tp = traj.ctypes.data if traj_cap else None
+        if shot:
+            ver = np.zeros(n, dtype=np.uint8)
+            self._check(self.L.mpros_rs_shot_batch(self.h, s.ctypes.data, g.ctypes.data, n, segs.ctypes.data, nseg.ctypes.data,
+                                                   cost.ctypes.data, tp, traj_cap, npts.ctypes.data, ver.ctypes.data))
+            out["verdicts"] = ver
+        else:
+            rp = C.byref(rs) if rs is not None else None
+            self._check(self.L.mpros_rs_solve_batch(self.h, rp, s.ctypes.data, g.ctypes.data, n, segs.ctypes.data, nseg.ctypes.data,
+                                                    cost.ctypes.data, tp, traj_cap, npts.ctypes.data))
+        return out
+
+    def rs_distance_batch(self, rho, a3, b3):
+        a = np.ascontiguousarray(a3, dtype=np.float64).reshape(-1, 3)
+        b = np.ascontiguousarray(b3, dtype=np.float64).reshape(-1, 3)
+        out = np.zeros(len(a))
+        self._check(self.L.mpros_rs_distance_batch(self.h, rho, a.ctypes.data, b.ctypes.data, len(a), out.ctypes.data))
+        return out
+
+    # ---- expansion ----
+    def n_primitives(self):
+        return 2 * (2 * (self.planner_params.steering_discretization // 2) + 1)
+
+    def expand_batch(self, start3, goal3, parents6):
+        p = np.ascontiguousarray(parents6, dtype=np.float64).reshape(-1, 6)
+        n, P = len(p), self.n_primitives()
+        g = np.array(goal3, dtype=np.float64)
+        s = np.array(start3, dtype=np.float64) if start3 is not None else None
+        prims = np.zeros((n, P, 7))
+        childs = np.zeros((n, P, 10))
+        nchild = np.zeros(n, dtype=np.int32)
+        self._check(self.L.mpros_expand_batch(self.h, s.ctypes.data if s is not None else None, g.ctypes.data, p.ctypes.data, n,
+                                              prims.ctypes.data, childs.ctypes.data, nchild.ctypes.data))
+        return prims, childs, nchild
+
+    # ---- planner ----
+    def plan_batch(self, starts3, goals3, path_cap=256):
+        s = np.ascontiguousarray(starts3, dtype=np.float64).reshape(-1, 3)
+        g = np.ascontiguousarray(goals3, dtype=np.float64).reshape(-1, 3)
+        nq = len(s)
+        status = np.zeros(nq, dtype=np.int32)
+        cost = np.zeros(nq)
+        plen = np.zeros(nq, dtype=np.int32)
+        paths = np.zeros((nq, path_cap, 5))
+        stats = np.zeros((nq, 4), dtype=np.int64)
+        self._check(self.L.mpros_plan_batch(self.h, s.ctypes.data, g.ctypes.data, nq, status.ctypes.data, cost.ctypes.data,
+                                            plen.ctypes.data, paths.ctypes.data if path_cap else None, path_cap, stats.ctypes.data))
+        return {"status": status, "cost": cost, "path_len": plen, "paths": paths, "iterations": stats[:, 0],
+                "primitives": stats[:, 1], "rs_shots": stats[:, 2], "collision_checks": stats[:, 3]}
+
+    def plan_batch_dev(self, d_starts, d_goals, nq, d_status, d_cost, d_len, d_paths, path_cap, d_stats):
+        self._check(self.L.mpros_plan_batch_dev(self.h, d_starts, d_goals, nq, d_status, d_cost, d_len, d_paths, path_cap, d_stats))
 
     # ---- plumbing ----
     def stream(self):

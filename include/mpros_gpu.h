@@ -135,6 +135,9 @@ MPROS_API int mpros_map_get_info(mpros_ctx *ctx, mpros_map_info *out);
 /* getGoalMap / getVoronoiMap / the private layers (nav_map.h:261-273): copies one layer to host memory in the
  * reference's element type (see enum mpros_layer). dst_bytes must be >= the layer size. */
 MPROS_API int mpros_map_download(mpros_ctx *ctx, int layer, void *dst, size_t dst_bytes);
+/* Overwrite the Voronoi-field layer (float[H*W], host) with caller-provided values, e.g. a field computed elsewhere.
+ * Only MPROS_LAYER_VORONOI can be uploaded; the next mpros_map_set_occupancy recomputes it. */
+MPROS_API int mpros_map_upload(mpros_ctx *ctx, int layer, const void *src, size_t src_bytes);
 /* NavMap::pointInCollision / pointInCollisionOrig / pointInCollisionINFLOrig (nav_map.cpp:249-277) for a batch of
  * cells; layer is MPROS_LAYER_STATIC, _STATIC_ORIG or _INFLATE_ORIG; ij: host int32[2*n] {i,j}; out: host uint8[n]. */
 MPROS_API int mpros_map_point_in_collision(mpros_ctx *ctx, int layer, const int32_t *ij, size_t n, uint8_t *out);
@@ -148,6 +151,68 @@ MPROS_API int mpros_collision_check_poses_dev(mpros_ctx *ctx, const double *d_xy
  * [offsets[p], offsets[p+1]); verdicts: uint8[n_paths]. */
 MPROS_API int mpros_collision_check_paths(mpros_ctx *ctx, const double *xyyaw, const int64_t *offsets, size_t n_paths,
                                 uint8_t *verdicts);
+
+/* ---- Reeds-Shepp (R1-R5) ----------------------------------------------------------------------------- */
+/* RS::RSCurve configuration: SetRadius / setSteeringAngle / setStepSize / setPenalty (rs_curve.h:58-100).
+ * The four penalties are in RSCurve::setPenalty's DECLARED order (gear, backward, steer_change, steer_angle);
+ * note the planner passes its steering_penalty / steering_change_penalty swapped (hybrid_a_star.cpp:170) —
+ * mpros_rs_default_config returns the values as the planner's RSCurve actually holds them. */
+typedef struct mpros_rs_params
+{
+    double radius;          /* min_radius_      */
+    double steering_angle;  /* steer_angle_     */
+    double step_size;       /* step_size_       */
+    double pen_gear, pen_backward, pen_steer_change, pen_steer_angle;
+} mpros_rs_params;
+MPROS_API int mpros_rs_default_config(mpros_ctx *ctx, mpros_rs_params *out);
+/* RSCurve::SetStart/SetEnd/FindOptimalPath/GetLength/GetTraj (rs_curve.cpp:111-222, 275-284) for n shots.
+ * starts5: double[5n] {x, y, yaw, direction, steer} (SetStart's arguments); goals3: double[3n].
+ * segs: double[15n] = 5 x {length, steer(-1/0/1), direction(+-1)} of optimal_path_; nseg: int32[n];
+ * cost: double[n] = GetLength(); traj: double[n * traj_cap * 5] {x, y, yaw, steer*steer_angle, direction}
+ * (may be NULL when traj_cap == 0); npts: int32[n] = GetTraj().size() (poses beyond traj_cap are not stored;
+ * the device generates at most 256 poses per shot). rs == NULL uses the planner's configuration. */
+MPROS_API int mpros_rs_solve_batch(mpros_ctx *ctx, const mpros_rs_params *rs, const double *starts5, const double *goals3,
+                                   size_t n, double *segs, int32_t *nseg, double *cost, double *traj, int traj_cap,
+                                   int32_t *npts);
+/* HybridAstar::genRSPath without the range test (hybrid_a_star.cpp:872-880): solve + sampled-path collision.
+ * verdicts: uint8[n], 1 = pathInCollision(rs_path). */
+MPROS_API int mpros_rs_shot_batch(mpros_ctx *ctx, const double *starts5, const double *goals3, size_t n, double *segs,
+                                  int32_t *nseg, double *cost, double *traj, int traj_cap, int32_t *npts, uint8_t *verdicts);
+/* RSStateSpace(rho).setStart/setEnd/getCost (rs_statespace.h:37-54): OMPL-equivalent Reeds-Shepp distance. */
+MPROS_API int mpros_rs_distance_batch(mpros_ctx *ctx, double rho, const double *a3, const double *b3, size_t n, double *out);
+
+/* ---- expansion (E1-E5) ---------------------------------------------------------------------------------- */
+/* HybridAstar::expandNode (hybrid_a_star.cpp:304-402) for n parents right after initialize(start, goal): the closed
+ * set holds only the start (g = 0) and goal (10000) seeds (start3 may be NULL: no seeds). Needs the goal map
+ * (mpros_map_update_goal). parents6: double[6n] {x, y, yaw, steer, direction, g}. P = 2 * steer_set_.size().
+ * prims: double[n*P*7] {x, y, yaw, steer, direction, collision(0/1), cell_in_map(0/1)} for every primitive in
+ * evaluation order (tree_); childs: double[n*P*10] {x, y, yaw, steer, direction, g, h, f, idx_i, idx_j} of the
+ * children inserted into the open list, in insertion order; nchild: int32[n]. */
+MPROS_API int mpros_expand_batch(mpros_ctx *ctx, const double *start3, const double *goal3, const double *parents6, size_t n,
+                                 double *prims, double *childs, int32_t *nchild);
+
+/* ---- planner ------------------------------------------------------------------------------------------------ */
+/* Per-query result of mpros_plan_batch: what HybridAstar::Plan() returns and why. */
+enum mpros_plan_status
+{
+    MPROS_PLAN_FOUND = 1,        /* Plan() == true ("Goal found")                                  */
+    MPROS_PLAN_LIMIT = 0,        /* "Iteration limit reached! Plan failed!"                        */
+    MPROS_PLAN_OPEN_EMPTY = -1,  /* "Open set empty! Plan failed!"                                 */
+    MPROS_PLAN_NOT_INIT = -2,    /* initialize() bailed out: start/goal in collision or outside    */
+    MPROS_PLAN_OVERFLOW = -3     /* internal node pool exhausted (never returned after the retries) */
+};
+/* For nq independent (start, goal) queries on the current map: NavMap::updateGoal + HybridAstar ctor/initialize +
+ * Plan() + the raw path_ of setPath (main_planner.cpp:225-229; hybrid_a_star.cpp:52-118, 682-811; getPath()).
+ * The per-query goal map is computed on demand on the device (values identical to generateGoalMap's).
+ * starts3/goals3: double[3nq]; status: int32[nq] (enum mpros_plan_status); cost: double[nq] = goal_node_->gvalue_
+ * (-1 when not found); path_len: int32[nq] = path_.size(); paths: double[nq*path_cap*5] {x, y, yaw, steer, direction}
+ * (first path_cap points; may be NULL with path_cap == 0); stats (optional): int64[4nq] {iterations, primitives
+ * evaluated (tree_.size()), RS shots, footPrintInCollision4 calls}. */
+MPROS_API int mpros_plan_batch(mpros_ctx *ctx, const double *starts3, const double *goals3, size_t nq, int32_t *status,
+                               double *cost, int32_t *path_len, double *paths, int path_cap, int64_t *stats);
+MPROS_API int mpros_plan_batch_dev(mpros_ctx *ctx, const double *d_starts3, const double *d_goals3, size_t nq,
+                                   int32_t *d_status, double *d_cost, int32_t *d_path_len, double *d_paths, int path_cap,
+                                   int64_t *d_stats);
 
 #ifdef __cplusplus
 }

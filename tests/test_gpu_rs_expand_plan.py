@@ -1,0 +1,217 @@
+"""GPU parity (through the C ABI) of the Reeds-Shepp generator, the OMPL-equivalent distance, node expansion and
+whole-query planning against the oracles (unmodified reference = `ref`, CPU restatement = `port`)."""
+import numpy as np
+import pytest
+
+from helpers import make_pair
+from oracle import portapi, refapi
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-4  # north_star tolerance for heuristic values and path cost
+TIGHT = 1e-9  # what FP64 libm-vs-libdevice differences actually allow
+
+
+def rs_cfg(ctx):
+    r = ctx.rs_default_config()
+    return [r.radius, r.steering_angle, r.step_size, r.pen_gear, r.pen_backward, r.pen_steer_change, r.pen_steer_angle]
+
+
+def random_rs_pairs(rng, n, reach=10.0):
+    s = np.zeros((n, 5))
+    s[:, 0] = rng.uniform(5, 15, n)
+    s[:, 1] = rng.uniform(5, 15, n)
+    s[:, 2] = rng.uniform(-np.pi, np.pi, n)
+    s[:, 3] = rng.choice([1.0, -1.0], n)
+    s[:, 4] = rng.choice([0.0, 0.35, -0.35, 0.175, -0.175], n)
+    ang = rng.uniform(-np.pi, np.pi, n)
+    d = rng.uniform(0.1, reach, n)
+    g = np.stack([s[:, 0] + d * np.cos(ang), s[:, 1] + d * np.sin(ang), rng.uniform(-np.pi, np.pi, n)], axis=1)
+    return s, g
+
+
+def test_rs_solve_matches_oracles(reflib, gpu_ctx_factory):
+    ctx = gpu_ctx_factory()
+    rm, params, m = make_pair(reflib, ctx, "reverse_parking", goal=(11.5, 2.1))
+    cfg = rs_cfg(ctx)
+    # the planner hands RSCurve (gear, backward, STEER_ANGLE, STEER_CHANGE) -> positional slots (hybrid_a_star.cpp:170)
+    assert cfg == [8.0, 0.35, 2.0, 10.0, 10.0, 0.5, 0.5]
+    rng = np.random.default_rng(3)
+    n = 20000
+    s, g = random_rs_pairs(rng, n)
+    out = ctx.rs_solve_batch(s, g, traj_cap=160)
+    plib = portapi.PortLib()
+    n_word_diff = 0
+    n_bitwise = 0
+    for k in range(n):
+        seg_p, cost_p, traj_p = portapi.rs_solve(plib, cfg, s[k], g[k])
+        if k < 2000:  # the reference itself on a subset (slower: multimap of vectors)
+            seg_r, cost_r, traj_r = refapi.ref_rs_solve(reflib, cfg, s[k], g[k])
+            assert np.array_equal(seg_r, seg_p) and cost_r == cost_p and np.array_equal(traj_r, traj_p)
+        ns = out["nseg"][k]
+        same_word = ns == len(seg_p) and np.array_equal(out["segs"][k, :ns, 1:], seg_p[:, 1:])
+        if not same_word:
+            # a different word may only win on a (near) tie of the penalised cost
+            n_word_diff += 1
+            assert abs(out["cost"][k] - cost_p) <= TIGHT * max(1.0, abs(cost_p))
+            continue
+        assert np.allclose(out["segs"][k, :ns, 0], seg_p[:, 0], rtol=0, atol=1e-11)
+        assert abs(out["cost"][k] - cost_p) <= 1e-12 * max(1.0, abs(cost_p))
+        assert out["npts"][k] == len(traj_p)
+        assert np.allclose(out["traj"][k, : len(traj_p)], traj_p, rtol=0, atol=1e-9)
+        n_bitwise += int(out["cost"][k] == cost_p and np.array_equal(out["traj"][k, : len(traj_p)], traj_p))
+    print("rs_solve: %d shots, %d bitwise identical, %d different word on cost tie" % (n, n_bitwise, n_word_diff))
+    assert n_word_diff <= n // 200
+    rm.close()
+
+
+def test_rs_distance_matches_port(gpu_ctx_factory, reflib):
+    ctx = gpu_ctx_factory()
+    rng = np.random.default_rng(5)
+    n = 100000
+    a = np.stack([rng.uniform(-30, 30, n), rng.uniform(-30, 30, n), rng.uniform(-np.pi, np.pi, n)], 1)
+    b = np.stack([rng.uniform(-30, 30, n), rng.uniform(-30, 30, n), rng.uniform(-np.pi, np.pi, n)], 1)
+    b[: n // 10, :2] = a[: n // 10, :2] + rng.uniform(-3, 3, (n // 10, 2))  # short manoeuvres
+    got = ctx.rs_distance_batch(8.0, a, b)
+    plib = portapi.PortLib()
+    want = np.array([portapi.rs_distance(plib, 8.0, a[k], b[k]) for k in range(n)])
+    rel = np.abs(got - want) / np.maximum(1.0, np.abs(want))
+    print("rs_distance: max rel err %.3g, bitwise equal %.4f" % (rel.max(), float((got == want).mean())))
+    assert rel.max() <= 1e-12
+    # and the reference wrapper (RSStateSpace over the OMPL stand-in) agrees with the port by construction
+    for k in range(200):
+        assert refapi.ref_rs_distance(reflib, 8.0, a[k], b[k]) == want[k]
+
+
+def test_rs_shot_verdicts(reflib, gpu_ctx_factory):
+    ctx = gpu_ctx_factory()
+    rm, params, m = make_pair(reflib, ctx, "parallel_parking3", goal=(10.7, 4.0))
+    rp = refapi.RefPlanner(rm)
+    cfg = rs_cfg(ctx)
+    rng = np.random.default_rng(7)
+    n = 4000
+    s, g = random_rs_pairs(rng, n)
+    s[:, 0] = rng.uniform(2, 18, n)
+    s[:, 1] = rng.uniform(2, 13, n)
+    g[:, 0], g[:, 1], g[:, 2] = 10.7, 4.0, 0.0
+    out = ctx.rs_solve_batch(s, g, traj_cap=160, shot=True)
+    plib = portapi.PortLib()
+    mism = 0
+    for k in range(n):
+        seg_p, cost_p, traj_p = portapi.rs_solve(plib, cfg, s[k], g[k])
+        want = int(rp.collision4(traj_p[:, :3]).any()) if len(traj_p) else 0
+        same_word = out["nseg"][k] == len(seg_p) and np.array_equal(out["segs"][k, : len(seg_p), 1:], seg_p[:, 1:])
+        if same_word:
+            mism += int(want != out["verdicts"][k])
+    print("rs_shot: free fraction %.3f, verdict mismatches %d" % (1 - out["verdicts"].mean(), mism))
+    assert 0.0 < out["verdicts"].mean() < 1.0
+    assert mism == 0
+    rp.close()
+    rm.close()
+
+
+@pytest.mark.parametrize("name,num_steer,start,goal", [
+    ("reverse_parking", None, [17.0, 8.0, 3.14], [11.5, 2.1, 1.57]),
+    ("parking4", 5, [-28.0, -1.5, 0.0], [10.0, -2.0, 1.57]),
+])
+def test_expand_matches_reference(reflib, gpu_ctx_factory, name, num_steer, start, goal):
+    ctx = gpu_ctx_factory()
+    rm, params, m = make_pair(reflib, ctx, name, num_steer=num_steer, goal=goal[:2])
+    ctx.upload_voronoi(rm.layer("voronoi"))  # isolate E1-E5 from the order-dependent Voronoi field
+    inf = rm.info()
+    rp = refapi.RefPlanner(rm)
+    P = ctx.n_primitives()
+    rng = np.random.default_rng(11)
+    # parents: collision-free poses
+    cand = np.stack([inf["ox"] + rng.uniform(-30, 30, 20000), inf["oy"] + rng.uniform(-5, 50, 20000), rng.uniform(-np.pi, np.pi, 20000)], 1)
+    if inf["oyaw"] == 0.0:
+        cand[:, 0] = rng.uniform(0, inf["W_orig"] * inf["res_orig"], 20000)
+        cand[:, 1] = rng.uniform(0, inf["H_orig"] * inf["res_orig"], 20000)
+    free = cand[rp.collision4(cand) == 0][:300]
+    assert len(free) >= 50
+    steer_set = [0.0, 0.35, -0.35, 0.175, -0.175] if num_steer == 5 else [0.0, 0.35, -0.35]
+    parents = np.zeros((len(free), 6))
+    parents[:, :3] = free
+    parents[:, 3] = rng.choice(steer_set, len(free))
+    parents[:, 4] = rng.choice([1.0, -1.0], len(free))
+    parents[:, 5] = rng.uniform(0, 50, len(free))
+    prims, childs, nchild = ctx.expand_batch(start, goal, parents)
+    for k in range(len(free)):
+        # the reference planner must be re-initialised per parent to get a fresh closed set
+        rp2 = refapi.RefPlanner(rm)
+        assert rp2.initialize(start, goal)
+        prim_r, child_r = rp2.expand(parents[k], P)
+        rp2.close()
+        assert np.allclose(prims[k, :, :5], prim_r[:, :5], rtol=0, atol=1e-12)
+        assert np.array_equal(prims[k, :, 5], prim_r[:, 5]), "collision verdicts of the primitives differ"
+        assert nchild[k] == len(child_r)
+        c = childs[k, : nchild[k]]
+        assert np.allclose(c[:, :5], child_r[:, :5], rtol=0, atol=1e-12)
+        assert np.array_equal(c[:, 8:], child_r[:, 8:])
+        assert np.allclose(c[:, 5:8], child_r[:, 5:8], rtol=1e-12, atol=0)  # g, h, f (tolerance budget: 1e-4)
+    rp.close()
+    rm.close()
+
+
+PLAN_CASES = [
+    # name, ds, num_steer, start, goal  (cases 0, 1, 5 and ARENA_part)
+    ("reverse_parking", 1, None, [17.0, 8.0, 3.14], [11.5, 2.1, 1.57]),
+    ("reverse_parking", 1, None, [3.0, 8.0, 0.0], [11.5, 2.1, 1.57]),
+    ("parallel_parking3", 1, None, [3.0, 8.5, 0.0], [10.7, 4.0, 0.0]),
+    ("parking4", 1, 5, [-28.0, -1.5, 0.0], [10.0, -2.0, 1.57]),
+    ("parking4", 1, 5, [-28.0, -1.5, 0.0], [8.0, -2.0, -1.57]),
+]
+
+
+@pytest.mark.parametrize("name,ds,num_steer,start,goal", PLAN_CASES)
+def test_plan_search_parity_with_reference_voronoi(reflib, gpu_ctx_factory, name, ds, num_steer, start, goal):
+    """(i) of SURVEY §9.4: the reference's Voronoi field injected -> isolates search parity. Expansion count, cost and
+    the raw path must match the unmodified reference."""
+    ctx = gpu_ctx_factory()
+    rm, params, m = make_pair(reflib, ctx, name, ds=ds, num_steer=num_steer, goal=goal[:2])
+    ctx.upload_voronoi(rm.layer("voronoi"))
+    r = refapi.ref_plan_query(rm, start, goal)
+    g = ctx.plan_batch([start], [goal], path_cap=512)
+    P = ctx.n_primitives()
+    print("%s: ref ok=%d g=%.9f prims=%d | gpu status=%d g=%.9f prims=%d iters=%d shots=%d" % (
+        name, r["plan_ok"], r["goal_g"], r["n_primitives"], g["status"][0], g["cost"][0], g["primitives"][0], g["iterations"][0], g["rs_shots"][0]))
+    assert (g["status"][0] == 1) == bool(r["plan_ok"])
+    assert g["primitives"][0] == int(r["n_primitives"]), "expansion count differs from the reference"
+    assert abs(g["cost"][0] - r["goal_g"]) <= TIGHT * abs(r["goal_g"])
+    assert g["path_len"][0] == len(r["path"])
+    assert np.allclose(g["paths"][0, : len(r["path"])], r["path"], rtol=0, atol=1e-8)
+    rm.close()
+
+
+@pytest.mark.parametrize("name,ds,num_steer,start,goal", PLAN_CASES)
+def test_plan_full_gpu_vs_reference(reflib, gpu_ctx_factory, name, ds, num_steer, start, goal):
+    """(ii) of SURVEY §9.4: everything GPU-generated (canonical Voronoi tie-breaks). Path collision-free for the
+    reference's own checker and cost no worse than the reference beyond 1e-4 relative."""
+    ctx = gpu_ctx_factory()
+    rm, params, m = make_pair(reflib, ctx, name, ds=ds, num_steer=num_steer, goal=goal[:2])
+    r = refapi.ref_plan_query(rm, start, goal)
+    g = ctx.plan_batch([start], [goal], path_cap=512)
+    assert (g["status"][0] == 1) == bool(r["plan_ok"])
+    rp = refapi.RefPlanner(rm)
+    path = g["paths"][0, : g["path_len"][0]]
+    assert not rp.collision4(path[:, :3]).any(), "returned path collides"
+    assert np.allclose(path[0, :3], start) and np.allclose(path[-1, :3], goal, atol=0.6)
+    rel = (g["cost"][0] - r["goal_g"]) / r["goal_g"]
+    print("%s: ref g=%.6f gpu g=%.6f rel %.3g; prims ref %d gpu %d" % (name, r["goal_g"], g["cost"][0], rel, r["n_primitives"], g["primitives"][0]))
+    assert rel <= REL
+    # and against the restatement, which shares the canonical Voronoi contract: search must be identical
+    plib = portapi.PortLib()
+    pm = portapi.PortMap(plib, params)
+    inf = rm.info()
+    pm.set_occupancy(m["occupancy"], inf["res_orig"], [inf["ox"], inf["oy"], inf["oyaw"]], exact_geometry=True)
+    pm.update_goal(goal[0], goal[1])
+    assert np.array_equal(pm.layer("voronoi"), ctx.layer("voronoi")), "GPU Voronoi field differs from the canonical restatement"
+    pp = portapi.PortPlanner(pm)
+    q = pp.plan(start, goal)
+    assert q["status"] == g["status"][0]
+    assert int(q["n_primitives"]) == g["primitives"][0] and int(q["iterations"]) == g["iterations"][0]
+    assert int(q["n_rs_shots"]) == g["rs_shots"][0] and int(q["n_collision"]) == g["collision_checks"][0]
+    assert abs(q["goal_g"] - g["cost"][0]) <= TIGHT * abs(q["goal_g"])
+    assert np.allclose(path, q["path"], rtol=0, atol=1e-8)
+    rp.close()
+    rm.close()
