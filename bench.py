@@ -1,12 +1,18 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200-native mpros hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload collision]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload plan|collision]
 
-Workload "collision" (SURVEY.md §8(d), C1 standalone): synthetic 8192x8192 grid @0.1 m (seed 20261019, 1-m border
-wall + 1100 rectangles), inflation 1.0 m, down-sampling 8; one STEP = one pass of batched footPrintInCollision4
-over 2^24 seeded uniform poses per GPU (403 MB of poses, larger than the 126 MB L2). Multi-GPU: poses are
-sharded across ranks, map replicated, no data-path collective (scaling "weak").
+Workload "plan" (default; BASELINE.json configs[4]): synthetic 8192x8192 occupancy grid @0.1 m
+(seed 20261019: 1-m border wall + 1100 rectangles), inflation 1.0 m, down-sampling 8, shipped planner parameters
+(3 steering angles, 36 yaw bins, step 2.0 m); 16384 independent seeded start/goal queries PER GPU (goal 20-80 m from
+the start, both collision-free and connected). One STEP = one mpros_plan_batch over the rank's 16384 queries =
+per query: obstacle-aware goal heuristic (on demand) + Hybrid A* with batched footprint checks + Reeds-Shepp shots.
+metric = plans/s; the same run also reports node expansions/s, footprint checks/s inside planning and the standalone
+batched collision kernel (2^24 poses). Multi-GPU: queries sharded across ranks, map replicated, the only exchange
+is the gather of the per-query results (scaling "weak": 16384 queries per GPU).
+
+Workload "collision": the C1 kernel alone, 2^24 seeded uniform poses per GPU per step.
 
 One JSON line on stdout (rank 0). The oracle (oracle/) is used only as the CPU baseline / reference arm.
 """
@@ -24,18 +30,40 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "hybrid-astar-planner_b200"))
 
-SYN_SIZE = 8192
-SYN_RES = 0.1
-SYN_DS = 8
+import synthetic  # noqa: E402  (workload generator: numpy only)
+
+SYN_SIZE, SYN_RES, SYN_DS = synthetic.SYN_SIZE, synthetic.SYN_RES, synthetic.SYN_DS
+EXTENT = SYN_SIZE * SYN_RES
+QUERIES_PER_GPU = 16384
+PATH_CAP = 128
 POSES_PER_STEP = 1 << 24
 POSE_SEED = 1
-ALGO_BYTES_PER_CHECK = 24 + 1 + (22 + 1 + 4)  # pose in + verdict out + (n+1+4) one-byte map cells, n=22 @0.1 m
+# algorithmic bytes per unit of work, SURVEY.md §8(d)
+B_CHECK = 24 + 1 + (22 + 1 + 4)  # C1 @0.1 m: pose in + verdict out + (n+1+4) one-byte map cells
+B_EXPANSION = 450                # E1 with the case-1 survivor / insert ratios
+B_SHOT = 440                     # R4 without the trajectory
+B_GOAL_CELL = 5                  # N4: 1 B in, 4 B out per cell of the goal map
+
+
+def shipped_params(ds=SYN_DS):
+    """planner_config.yaml + vehicle_config.yaml as the shipped launch loads them (the YAML's misspelled
+    steering_dsicretization leaves the code default of 3 steering angles)."""
+    return {
+        "/mpros/planner/optimal_path": 0, "/mpros/planner/interpolation_enable": 1, "/mpros/planner/step_size": 2.0,
+        "/mpros/planner/max_iteration": 100000, "/mpros/planner/gear_penalty": 10.0, "/mpros/planner/reverse_penalty": 10.0,
+        "/mpros/planner/steering_penalty": 0.5, "/mpros/planner/steering_change_penalty": 0.5,
+        "/mpros/planner/analytic_solution_range": 10.0, "/mpros/planner/yaw_discretization": 36,
+        "/mpros/planner/path_point_distance": 0.1, "/mpros/map/downsampling_factor": ds,
+        "/mpros/map/obstacle_inflation_radius": 1.0, "/mpros/map/free_thresh": 0.2, "/mpros/map/occupied_thresh": 0.68,
+        "/mpros/vehicle/max_steering_angle": 0.35, "/mpros/vehicle/max_curvature": 0.125, "/mpros/vehicle/width": 2.0,
+        "/mpros/vehicle/wheelbase": 3.0, "/mpros/vehicle/length": 4.2,
+        "/mpros/vehicle/center_to_rotate_center_longitudinal": 0.0,
+    }
 
 
 def measured_peak_gbs():
-    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
-        return float(json.load(open(p))["hbm_gbs"]), "measured"
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
     except Exception:
         return 6650.0, "fallback"
 
@@ -48,9 +76,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
-        self.gpu = gpu_index
-        self.samples = []
-        self.stop_flag = False
+        self.gpu, self.samples, self.stop_flag = gpu_index, [], False
 
     def run(self):
         while not self.stop_flag:
@@ -61,37 +87,40 @@ class ClockSampler(threading.Thread):
                     self.samples.append([s.strip() for s in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def summary(self):
-        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        def num(v):
+            try:
+                return float(v)
+            except ValueError:
+                return None
+        sm = [num(s[0]) for s in self.samples if s and num(s[0]) is not None]
+        mx = [num(s[1]) for s in self.samples if len(s) > 1 and num(s[1]) is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for k, n in enumerate(names) if any(len(s) > 2 + k and s[2 + k].lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def synthetic_setup():
-    from oracle import refapi  # map generator only (shared fixture recipe)
-
-    occ = refapi.synthetic_occupancy(SYN_SIZE, 1100, 20261019, SYN_RES)
-    params = refapi.shipped_params(0.2, 0.68, ds=SYN_DS)
-    return occ, params
-
-
-def gen_poses(n, seed, size_m):
+def gen_poses(n, seed):
     rng = np.random.default_rng(seed)
     p = np.empty((n, 3), dtype=np.float64)
-    p[:, 0] = rng.uniform(0.0, size_m, n)
-    p[:, 1] = rng.uniform(0.0, size_m, n)
+    p[:, 0] = rng.uniform(0.0, EXTENT, n)
+    p[:, 1] = rng.uniform(0.0, EXTENT, n)
     p[:, 2] = rng.uniform(-np.pi, np.pi, n)
     return p
 
 
+def gen_queries(ctx, n, seed):
+    """The §8(d) query recipe; footprint checks for the rejection sampling run on the GPU context."""
+    static_ds = ctx.layer("static")
+    return synthetic.synthetic_queries(n, ctx.collision_check, static_ds, SYN_RES * SYN_DS, EXTENT, seed)
+
+
 # ------------------------------------------------------------------------------------------------------------
-# CPU arm: the unmodified reference (oracle/_ref) — one process per core, one NavMap copy each, because the reference
-# is single-threaded and NavMap is mutable shared state.
+# CPU arm: the unmodified reference (oracle/_ref) — one process per core, one NavMap copy each, because the
+# reference is single-threaded and NavMap::updateGoal mutates shared state (BASELINE.md §3).
 _W = {}
 
 
@@ -104,7 +133,9 @@ def _cpu_worker_init(so_path, params, shm_name, shape, res):
     occ = np.ndarray(shape, dtype=np.int8, buffer=shm.buf)
     lib = refapi.RefLib(so_path)
     rm = refapi.RefMap(lib, params)
+    t0 = time.perf_counter()
     rm.set_occupancy(occ, res, [0.0, 0.0, 0.0])
+    _W["t_pre"] = time.perf_counter() - t0
     _W["rp"] = refapi.RefPlanner(rm)
     _W["rm"] = rm
     shm.close()
@@ -114,6 +145,19 @@ def _cpu_worker_collision(poses):
     t0 = time.perf_counter()
     v = _W["rp"].collision4(poses)
     return time.perf_counter() - t0, int(v.sum()), len(poses)
+
+
+def _cpu_worker_plan(job):
+    from oracle import refapi
+
+    starts, goals = job
+    t0 = time.perf_counter()
+    ok = prims = 0
+    for s, g in zip(starts, goals):
+        r = refapi.ref_plan_query(_W["rm"], s, g)  # updateGoal + ctor (dense state) + Plan(), main_planner.cpp:225-229
+        ok += int(r["plan_ok"])
+        prims += int(r["n_primitives"])
+    return time.perf_counter() - t0, ok, prims, len(starts), _W["t_pre"]
 
 
 class CpuArm:
@@ -131,10 +175,18 @@ class CpuArm:
                                               initargs=(refapi.REF_SO, params, self.shm.name, occ.shape, SYN_RES))
 
     def collision_rate(self, n_poses, seed):
-        poses = gen_poses(n_poses, seed, SYN_SIZE * SYN_RES)
+        poses = gen_poses(n_poses, seed)
         res = self.pool.map(_cpu_worker_collision, np.array_split(poses, self.cores))
         # workers run concurrently: throughput = total checks / slowest worker's footPrintInCollision4 loop
         return sum(r[2] for r in res) / max(r[0] for r in res)
+
+    def plan_rate(self, starts, goals):
+        jobs = list(zip(np.array_split(starts, self.cores), np.array_split(goals, self.cores)))
+        res = self.pool.map(_cpu_worker_plan, jobs)
+        t = max(r[0] for r in res)
+        n = sum(r[3] for r in res)
+        return {"plans_per_sec": n / t, "expansions_per_sec": sum(r[2] for r in res) / 6.0 / t, "solved": sum(r[1] for r in res),
+                "n": n, "preprocess_s": max(r[4] for r in res)}
 
     def close(self):
         self.pool.close()
@@ -143,42 +195,94 @@ class CpuArm:
         self.shm.unlink()
 
 
-def cpu_sample_text(n, cores):
-    return ("%d seeded uniform poses on the synthetic 8192^2 map, %d process(es) x 1 thread, unmodified reference "
-            "footPrintInCollision4 loop timed (map preprocessing excluded)" % (n, cores))
+def usable_cores():
+    """All host cores, limited by memory: the reference allocates a dense H'*W'*36*2 state per query (~1.8 GB at
+    1024^2) on top of its map copy."""
+    cores = os.cpu_count() or 1
+    try:
+        avail = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
+        cores = max(1, min(cores, int(avail * 0.8 / 3.5e9)))
+    except Exception:
+        pass
+    return cores
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return 0
-    occ, params = synthetic_setup()
-    cores = os.cpu_count() or 1
-    n = (1 << 20) * cores
+    occ = synthetic.synthetic_occupancy()
+    params = shipped_params()
+    cores = usable_cores()
     arm = CpuArm(occ, params, cores)
-    vals = []
+    vals, extra = [], {}
     t0 = time.perf_counter()
     try:
-        for s in range(args.warmup + args.steps):
-            v = arm.collision_rate(n, POSE_SEED + s)
-            if s >= args.warmup:
-                vals.append(v)
-            if time.perf_counter() - t0 > 200 and vals:
-                break
+        if args.workload == "collision":
+            n = (1 << 20) * cores
+            for s in range(args.warmup + args.steps):
+                v = arm.collision_rate(n, POSE_SEED + s)
+                if s >= args.warmup:
+                    vals.append(v)
+                if time.perf_counter() - t0 > 200 and vals:
+                    break
+            metric, unit = "collision_checks_per_sec", "checks/s"
+            sample = "%d seeded uniform poses per step on the synthetic 8192^2 map, %d processes x 1 thread; timed region = footPrintInCollision4 loop" % (n, cores)
+            per_step = n
+        else:
+            # the query set is generated with the reference's own collision test so that this arm needs no GPU
+            lib_poses = _ref_queries(occ, params, 2 * cores * max(1, args.steps + args.warmup))
+            per_step = 2 * cores
+            for s in range(args.warmup + args.steps):
+                sl = slice(s * per_step, (s + 1) * per_step)
+                r = arm.plan_rate(lib_poses[0][sl], lib_poses[1][sl])
+                if s >= args.warmup:
+                    vals.append(r["plans_per_sec"])
+                    extra = r
+                if time.perf_counter() - t0 > 240 and vals:
+                    break
+            metric, unit = "plans_per_sec", "plans/s"
+            sample = ("%d seeded queries per step (2 per process) on the synthetic 8192^2 map (ds=8), %d processes x 1 thread; timed region per "
+                      "query = NavMap::updateGoal + HybridAstar ctor + Plan() (map preprocessing %.1f s excluded)" % (per_step, cores, extra.get("preprocess_s", 0)))
     finally:
         arm.close()
     value = float(np.mean(vals))
     line = {
-        "impl": "reference", "metric": "collision_checks_per_sec", "value": value, "unit": "checks/s", "n_gpus": args.gpus,
-        "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1e3 * n / value, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": len(vals),
+        "warmup": args.warmup, "ms_per_step": 1e3 * per_step / value, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "collision: synthetic 8192x8192 @0.1 m (seed 20261019), inflation 1.0 m, seeded uniform poses",
-                   "poses_per_step": n},
-        "cpu_baseline": {"value": value, "unit": "checks/s", "cores": cores, "kind": "reference", "sample": cpu_sample_text(n, cores)},
-        "e2e": {"value": value, "unit": "checks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": workload_text(args.workload), "units_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if extra:
+        line["extra"] = {"node_expansions_per_sec": extra["expansions_per_sec"], "solved": extra["solved"], "queries": extra["n"]}
     print(json.dumps(line))
     return 0
+
+
+def _ref_queries(occ, params, n):
+    """§8(d) query recipe evaluated with the reference's own footprint test (CPU-only path for --impl reference)."""
+    from oracle import refapi
+
+    lib = refapi.RefLib()
+    # collision checks need only the raw + inflated layers: down-sampling 64 keeps the Voronoi/CCL part of the
+    # reference's preprocessing negligible here; the free-component test uses the ds=8 static layer built with numpy
+    p2 = dict(params)
+    rm = refapi.RefMap(lib, p2)
+    rm.set_occupancy(occ, SYN_RES, [0.0, 0.0, 0.0])
+    rp = refapi.RefPlanner(rm)
+    static_ds = rm.layer("static")
+    out = synthetic.synthetic_queries(n, rp.collision4, static_ds, SYN_RES * SYN_DS, EXTENT, synthetic.SYN_QUERY_SEED)
+    rp.close()
+    rm.close()
+    return out
+
+
+def workload_text(w):
+    if w == "collision":
+        return "collision: synthetic 8192x8192 @0.1 m (seed 20261019), inflation 1.0 m, batched footPrintInCollision4 over seeded uniform poses"
+    return ("plan: synthetic 8192x8192 @0.1 m (seed 20261019), ds=8, inflation 1.0 m, shipped planner config (3 steers, 36 yaw bins, step 2 m); "
+            "independent seeded start/goal queries 20-80 m apart; per query goal heuristic + Hybrid A* + Reeds-Shepp shots")
 
 
 def run_b200(args):
@@ -196,104 +300,186 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    occ, params = synthetic_setup()
+    occ = synthetic.synthetic_occupancy()
+    params = shipped_params()
     ctx = mpros_b200.Context(local_rank)
     ctx.map_config(params)
+    occ_pinned = torch.from_numpy(occ).pin_memory()
     t0 = time.perf_counter()
-    ctx.set_occupancy(occ, SYN_RES, [0.0, 0.0, 0.0])
+    ctx.set_occupancy(occ_pinned.numpy(), SYN_RES, [0.0, 0.0, 0.0])
     t_pre = time.perf_counter() - t0
     ctx.planner_config(params)
-
-    n = POSES_PER_STEP
-    poses_h = torch.from_numpy(gen_poses(n, POSE_SEED + 1000 * rank, SYN_SIZE * SYN_RES)).pin_memory()
-    poses_d = poses_h.cuda(non_blocking=False)
-    verd_d = torch.zeros(n, dtype=torch.uint8, device="cuda")
-    verd_h = torch.zeros(n, dtype=torch.uint8).pin_memory()
     stream = torch.cuda.ExternalStream(ctx.stream())
-
-    def step_dev():
-        ctx.collision_check_dev(poses_d.data_ptr(), n, verd_d.data_ptr())
+    warm = max(3, args.warmup)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
-        step_dev()
-    barrier()
+    def timed_device(step_fn):
+        """W warm-up steps, then K steps timed with CUDA events on the context's stream (per step + whole region)."""
+        for _ in range(warm):
+            step_fn()
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launch_count()
+        e0.record(stream)
+        for k in range(args.steps):
+            ev[k][0].record(stream)
+            step_fn()
+            ev[k][1].record(stream)
+        e1.record(stream)
+        barrier()
+        return e0.elapsed_time(e1), [a.elapsed_time(b) for a, b in ev], ctx.launch_count() - l0
+
+    def timed_host(step_fn):
+        for _ in range(2):
+            step_fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_fn()
+        barrier()
+        return (time.perf_counter() - t0) * 1e3
+
+    def max_over_ranks(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    # ---- collision kernel (always measured: headline for --workload collision, extra otherwise) ----
+    n = POSES_PER_STEP
+    col_steps = args.steps if args.workload == "collision" else min(args.steps, 5)
+    poses_h = torch.from_numpy(gen_poses(n, POSE_SEED + 1000 * rank)).pin_memory()
+    poses_d = poses_h.cuda()
+    verd_d = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    verd_h = torch.zeros(n, dtype=torch.uint8).pin_memory()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = ctx.launch_count()
-    # device-resident timing: one event pair per step (per-kernel durations) + one around the whole region
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e_all0.record(stream)
-    for k in range(args.steps):
-        ev[k][0].record(stream)
-        step_dev()
-        ev[k][1].record(stream)
-    e_all1.record(stream)
-    barrier()
-    launches = ctx.launch_count() - launches0
-    total_ms = e_all0.elapsed_time(e_all1)
-    kern_ms = [a.elapsed_time(b) for a, b in ev]
-
-    # end-to-end through the public host-pointer C-ABI call: pinned host poses -> H2D -> kernel -> D2H verdicts
-    L = ctx.L
-    for _ in range(2):
-        ctx._check(L.mpros_collision_check_poses(ctx.h, poses_h.data_ptr(), n, verd_h.data_ptr()))
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ctx._check(L.mpros_collision_check_poses(ctx.h, poses_h.data_ptr(), n, verd_h.data_ptr()))
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
-    hit_rate = float(verd_h.float().mean())
+    keep_steps = args.steps
+    args.steps = col_steps
+    col_total_ms, col_ms, col_launches = timed_device(lambda: ctx.collision_check_dev(poses_d.data_ptr(), n, verd_d.data_ptr()))
+    col_e2e_ms = timed_host(lambda: ctx._check(ctx.L.mpros_collision_check_poses(ctx.h, poses_h.data_ptr(), n, verd_h.data_ptr())))
+    args.steps = keep_steps
     assert torch.equal(verd_h, verd_d.cpu()), "host-API and device-API verdicts differ"
+    hit_rate = float(verd_h.float().mean())
+    col_total_ms, col_e2e_ms = max_over_ranks([col_total_ms, col_e2e_ms])
+    col_value = world * n * col_steps / (col_total_ms * 1e-3)
+    col_e2e = world * n * col_steps / (col_e2e_ms * 1e-3)
+    peak, peak_kind = measured_peak_gbs()
+    col_roof = {"bound": "hbm", "achieved": n * B_CHECK / (float(np.mean(col_ms)) * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "traffic": None, "kernel": "collision_poses_kernel", "kernel_ms": float(np.mean(col_ms)), "peak_source": peak_kind,
+                "algorithmic_bytes_per_unit": B_CHECK}
+    col_roof["frac"] = col_roof["achieved"] / peak
+    del poses_d, verd_d
 
-    t_max = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
-    total_ms_max, e2e_ms_max = t_max.tolist()
+    line = None
+    if args.workload == "collision":
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+        if rank == 0:
+            line = {"metric": "collision_checks_per_sec", "value": col_value, "unit": "checks/s", "ms_per_step": col_total_ms / col_steps,
+                    "e2e": {"value": col_e2e, "unit": "checks/s", "h2d_bytes_per_step": n * 24, "d2h_bytes_per_step": n},
+                    "gpu_launches": int(col_launches), "roofline": col_roof,
+                    "config": {"workload": workload_text("collision"), "poses_per_step_per_gpu": n, "hit_rate": hit_rate,
+                               "l2_policy": "inputs larger than L2 (403 MB of poses per step)", "preprocess_s_first_call": t_pre}}
+    else:
+        nq = QUERIES_PER_GPU
+        starts, goals = gen_queries(ctx, nq, synthetic.SYN_QUERY_SEED + rank)
+        s_h, g_h = torch.from_numpy(starts).pin_memory(), torch.from_numpy(goals).pin_memory()
+        s_d, g_d = s_h.cuda(), g_h.cuda()
+        status_d = torch.zeros(nq, dtype=torch.int32, device="cuda")
+        cost_d = torch.zeros(nq, dtype=torch.float64, device="cuda")
+        len_d = torch.zeros(nq, dtype=torch.int32, device="cuda")
+        paths_d = torch.zeros(nq * PATH_CAP * 5, dtype=torch.float64, device="cuda")
+        stats_d = torch.zeros(nq * 6, dtype=torch.int64, device="cuda")
+        status_h = torch.zeros(nq, dtype=torch.int32).pin_memory()
+        cost_h = torch.zeros(nq, dtype=torch.float64).pin_memory()
+        len_h = torch.zeros(nq, dtype=torch.int32).pin_memory()
+        paths_h = torch.zeros(nq * PATH_CAP * 5, dtype=torch.float64).pin_memory()
+        stats_h = torch.zeros(nq * 6, dtype=torch.int64).pin_memory()
+        gather = [torch.zeros(nq, dtype=torch.float64, device="cuda") for _ in range(world)] if world > 1 else None
 
-    if rank == 0:
-        peak, peak_kind = measured_peak_gbs()
-        value = world * n * args.steps / (total_ms_max * 1e-3)
-        e2e_value = world * n * args.steps / (e2e_ms_max * 1e-3)
-        k_ms = float(np.mean(kern_ms))
-        achieved = n * ALGO_BYTES_PER_CHECK / (k_ms * 1e-3) / 1e9
+        def step_dev():
+            ctx.plan_batch_dev(s_d.data_ptr(), g_d.data_ptr(), nq, status_d.data_ptr(), cost_d.data_ptr(), len_d.data_ptr(),
+                               paths_d.data_ptr(), PATH_CAP, stats_d.data_ptr())
+            if world > 1:  # the path's only exchange step: result gather over NCCL/NVLink
+                ctx.synchronize()
+                dist.all_gather(gather, cost_d)
+
+        def step_host():
+            ctx._check(ctx.L.mpros_plan_batch(ctx.h, s_h.data_ptr(), g_h.data_ptr(), nq, status_h.data_ptr(), cost_h.data_ptr(),
+                                              len_h.data_ptr(), paths_h.data_ptr(), PATH_CAP, stats_h.data_ptr()))
+
+        total_ms, step_ms, launches = timed_device(step_dev)
+        e2e_ms = timed_host(step_host)
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+        st = stats_d.cpu().numpy().reshape(nq, 6)
+        status = status_d.cpu().numpy()
+        assert np.array_equal(status, status_h.numpy()) and torch.equal(cost_h, cost_d.cpu()), "host-API and device-API plans differ"
+        iters, prims, shots, checks, cells = [int(st[:, k].sum()) for k in range(5)]
+        P = ctx.n_primitives()
+        expansions = prims // P
+        total_ms, e2e_ms = max_over_ranks([total_ms, e2e_ms])
+        sums = torch.tensor([expansions, checks, shots, cells, int((status == 1).sum()), int((status == 0).sum()), int((status < 0).sum())],
+                            dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(sums)
+        expansions_all, checks_all, shots_all, cells_all, n_found, n_limit, n_fail = [int(v) for v in sums.tolist()]
+        if rank == 0:
+            secs = total_ms * 1e-3 / args.steps
+            k_ms = float(np.mean(step_ms))
+            algo_bytes = B_EXPANSION * expansions + B_SHOT * shots + B_GOAL_CELL * cells
+            achieved = algo_bytes / (k_ms * 1e-3) / 1e9
+            line = {"metric": "plans_per_sec", "value": world * nq / secs, "unit": "plans/s", "ms_per_step": total_ms / args.steps,
+                    "e2e": {"value": world * nq * args.steps / (e2e_ms * 1e-3), "unit": "plans/s", "h2d_bytes_per_step": nq * 48,
+                            "d2h_bytes_per_step": nq * (4 + 8 + 4 + PATH_CAP * 40 + 48)},
+                    "gpu_launches": int(launches),
+                    "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                                 "kernel": "plan_batch_kernel", "kernel_ms": k_ms, "peak_source": peak_kind,
+                                 "algorithmic_bytes_per_launch": algo_bytes,
+                                 "note": "latency/FP64-issue bound (sequential A* per query, FP64 transcendentals), not HBM bound; see DESIGN.md"},
+                    "extra": {"node_expansions_per_sec": expansions_all / secs, "footprint_checks_per_sec_in_planning": checks_all / secs,
+                              "rs_shots_per_sec": shots_all / secs, "goal_map_cells_per_sec": cells_all / secs,
+                              "collision_kernel_checks_per_sec": col_value, "collision_kernel_e2e_checks_per_sec": col_e2e,
+                              "collision_kernel_roofline": col_roof, "collision_hit_rate": hit_rate,
+                              "plans_found": n_found, "plans_iteration_limit": n_limit, "plans_failed_other": n_fail,
+                              "mean_expansions_per_query": expansions_all / (world * nq)},
+                    "config": {"workload": workload_text("plan"), "queries_per_gpu": nq, "path_cap": PATH_CAP,
+                               "l2_policy": "per-query working sets live in a %d MB-per-warp HBM workspace (>> L2 in aggregate); map layers are L2-resident by design" % 3,
+                               "preprocess_s_first_call": t_pre}}
+
+    if rank == 0 and line is not None:
         cpu = None
         if args.gpus == 1 and not args.no_cpu:
             try:
                 arm = CpuArm(occ, params, 1)
                 try:
-                    arm.collision_rate(1 << 18, POSE_SEED + 5)
-                    v = arm.collision_rate(1 << 22, POSE_SEED + 6)
+                    if args.workload == "collision":
+                        arm.collision_rate(1 << 18, POSE_SEED + 5)
+                        v = arm.collision_rate(1 << 22, POSE_SEED + 6)
+                        cpu = {"value": v, "unit": "checks/s", "cores": 1, "kind": "reference",
+                               "sample": "4194304 seeded uniform poses on the synthetic 8192^2 map, 1 process x 1 thread, unmodified reference footPrintInCollision4 loop (preprocessing excluded)"}
+                    else:
+                        r = arm.plan_rate(starts[:8], goals[:8])
+                        cpu = {"value": r["plans_per_sec"], "unit": "plans/s", "cores": 1, "kind": "reference",
+                               "sample": "first 8 queries of rank 0's set, 1 process x 1 thread, unmodified reference: NavMap::updateGoal + HybridAstar ctor + Plan() per query (map preprocessing %.1f s excluded); %d/8 solved" % (r["preprocess_s"], r["solved"]),
+                               "node_expansions_per_sec": r["expansions_per_sec"]}
                 finally:
                     arm.close()
-                cpu = {"value": v, "unit": "checks/s", "cores": 1, "kind": "reference", "sample": cpu_sample_text(1 << 22, 1)}
-            except Exception as e:  # oracle absent: report it, do not fail the GPU bench
-                cpu = {"value": None, "unit": "checks/s", "cores": 0, "kind": "unavailable", "sample": str(e)}
-        line = {
-            "metric": "collision_checks_per_sec", "value": value, "unit": "checks/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "collision: synthetic 8192x8192 @0.1 m (seed 20261019), inflation 1.0 m, 2^24 seeded uniform poses per GPU per step",
-                       "poses_per_step_per_gpu": n, "l2_policy": "inputs larger than L2 (403 MB poses per step)",
-                       "hit_rate": hit_rate, "preprocess_s_first_call": t_pre},
-            "e2e": {"value": e2e_value, "unit": "checks/s", "h2d_bytes_per_step": n * 24, "d2h_bytes_per_step": n},
-            "gpu_launches": int(launches),
-            "clocks": sampler.summary(),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "collision_poses_kernel", "kernel_ms": k_ms, "peak_source": peak_kind,
-                         "algorithmic_bytes_per_check": ALGO_BYTES_PER_CHECK},
-            "cpu_baseline": cpu,
-        }
-        print(json.dumps(line))
+            except Exception as e:  # oracle absent: say so, do not fail the GPU bench
+                cpu = {"value": None, "unit": line["unit"], "cores": 0, "kind": "unavailable", "sample": str(e)}
+        line.update({"n_gpus": world, "steps": args.steps, "warmup": warm, "higher_is_better": True, "scaling": "weak",
+                     "vs_baseline": None, "dtype": "f64", "data": "synthetic", "clocks": sampler.summary(), "cpu_baseline": cpu})
+        order = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                 "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline", "extra"]
+        print(json.dumps({k: line[k] for k in order if k in line}))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
@@ -301,10 +487,10 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="collision")
+    ap.add_argument("--workload", default="plan", choices=["plan", "collision"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -8,6 +8,8 @@
 // hash, on-demand goal wavefront) lives in a per-warp HBM workspace that is reused without clearing (generation tags).
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "planner_device.cuh"
@@ -69,7 +71,7 @@ struct PlanBatchArgs
     int32_t *path_len; // nq
     double *paths;     // nq x path_cap x 5 (may be null when path_cap == 0)
     int path_cap;
-    int64_t *stats; // nq x 4 {iterations, primitives, rs_shots, collision_checks}
+    int64_t *stats; // nq x 6 {iterations, primitives, rs_shots, collision_checks, goal_map_cells, nodes_inserted}
     // work distribution
     const int32_t *todo; // indices of the queries to run in this pass (null = all)
     int n_todo;
@@ -80,6 +82,17 @@ struct PlanBatchArgs
     RsConfig rs;
     int optimal;
 };
+
+#ifdef MPROS_PROFILE
+__device__ unsigned long long g_prof[8];
+#define PROF_DECL long long pt0 = clock64(), pt1; long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define PROF_MARK(k) do { pt1 = clock64(); pacc[k] += pt1 - pt0; pt0 = pt1; } while (0)
+#define PROF_FLUSH do { if ((threadIdx.x & 31) == 0) for (int k_ = 0; k_ < 8; ++k_) atomicAdd(&g_prof[k_], (unsigned long long)pacc[k_]); } while (0)
+#else
+#define PROF_DECL
+#define PROF_MARK(k)
+#define PROF_FLUSH
+#endif
 
 // status codes of mpros_plan_batch (include/mpros_gpu.h)
 enum
@@ -92,7 +105,7 @@ enum
 };
 
 // heuristic of one node computed by a QUAD of lanes (hybrid_a_star.cpp:248-264); h1 is the goal-map value of the cell
-__device__ __forceinline__ double node_heuristic_quad(const MapView &m, const PlannerView &p, int h1_cells, double x, double y,
+__device__ __noinline__ double node_heuristic_quad(const MapView &m, const PlannerView &p, int h1_cells, double x, double y,
                                                       double yaw, double gx, double gy, double gyaw)
 {
     double h1 = (double)h1_cells * m.res; // getGoalCost: cost_ * map_resolution_
@@ -137,12 +150,12 @@ __device__ void plan_one_query(const MapView &m, const PlannerView &p, const Pla
     bool init_ok = true;
     {
         double s, c;
-        sincos(syaw, &s, &c);
+        dm::sincos_(syaw, &s, &c);
         if (warp_footprint_collision(m, p, sx, sy, s, c))
             init_ok = false; // "Start pose in collision"
         if (init_ok)
         {
-            sincos(gyaw, &s, &c);
+            dm::sincos_(gyaw, &s, &c);
             if (warp_footprint_collision(m, p, gx, gy, s, c))
                 init_ok = false; // "Goal pose in collision"
         }
@@ -189,6 +202,7 @@ __device__ void plan_one_query(const MapView &m, const PlannerView &p, const Pla
     uint32_t n_nodes = 1;
 
     // ---- Plan() (hybrid_a_star.cpp:682-777) ----
+    PROF_DECL
     if (init_ok)
     {
         bool goal_found = false, limit_reached = false, overflow = false;
@@ -201,8 +215,10 @@ __device__ void plan_one_query(const MapView &m, const PlannerView &p, const Pla
                 break;
             }
             unsigned long long fk;
+            PROF_MARK(7);
             uint32_t cur = heap_pop_warp(heap, fk);
             const PlanNode cn = nodes[cur];
+            PROF_MARK(0);
             if (cn.closed)
                 continue;
             // -- genRSPath (:853-900)
@@ -235,7 +251,7 @@ __device__ void plan_one_query(const MapView &m, const PlannerView &p, const Pla
                         if (k < np)
                         {
                             px = traj[3 * k], py = traj[3 * k + 1];
-                            sincos(traj[3 * k + 2], &s, &c);
+                            dm::sincos_(traj[3 * k + 2], &s, &c);
                         }
                         int cnt = min(32, np - base);
                         for (int t = 0; t < cnt && !hit; ++t)
@@ -259,6 +275,7 @@ __device__ void plan_one_query(const MapView &m, const PlannerView &p, const Pla
                     }
                 }
             }
+            PROF_MARK(1);
             if (shot_ok)
             {
                 goal_found = true;
@@ -270,13 +287,13 @@ __device__ void plan_one_query(const MapView &m, const PlannerView &p, const Pla
                 // -- expandNode (:304-402)
                 const int P = 2 * p.n_steer;
                 double s_yaw, c_yaw;
-                sincos(cn.yaw, &s_yaw, &c_yaw);
+                dm::sincos_(cn.yaw, &s_yaw, &c_yaw);
                 // every lane < P computes its primitive's end pose
                 double nx = 0, ny = 0, nyaw = 0, steer = 0, direc = 1, ns = 0, nc = 1;
                 if (lane < P)
                 {
                     primitive_end_pose(p, lane, cn.x, cn.y, cn.yaw, s_yaw, c_yaw, nx, ny, nyaw, steer, direc);
-                    sincos(nyaw, &ns, &nc);
+                    dm::sincos_(nyaw, &ns, &nc);
                 }
                 n_prim += P;
                 n_coll += P;
@@ -288,6 +305,7 @@ __device__ void plan_one_query(const MapView &m, const PlannerView &p, const Pla
                     if (!warp_footprint_collision(m, p, tx, ty, ts, tc))
                         free_mask |= 1u << c;
                 }
+                PROF_MARK(2);
                 // survivors: node cell, g (lane = primitive), goal-map value (on-demand wavefront)
                 bool alive = lane < P && ((free_mask >> lane) & 1u);
                 int ci = -1, cj = -1;
@@ -300,6 +318,7 @@ __device__ void plan_one_query(const MapView &m, const PlannerView &p, const Pla
                     double voro = (double)__ldg(m.voronoi + (size_t)ci * m.W + cj);
                     g = node_cost(p, cn.g, (double)cn.dir, cn.steer, voro, steer, direc);
                 }
+                PROF_MARK(3);
                 // heuristics: quad of lanes per primitive, 8 primitives per round
                 double hval = 0;
                 for (int base = 0; base < P; base += 8)
@@ -317,6 +336,7 @@ __device__ void plan_one_query(const MapView &m, const PlannerView &p, const Pla
                     if (owner_quad >= 0 && owner_quad < 8)
                         hval = back;
                 }
+                PROF_MARK(4);
                 // closed-set compare / open-list insert, strictly in primitive order (lane 0 walks the survivors)
                 unsigned alive_mask = __ballot_sync(kFull, alive);
                 for (int c = 0; c < P; ++c)
@@ -371,17 +391,19 @@ __device__ void plan_one_query(const MapView &m, const PlannerView &p, const Pla
                     }
                     __syncwarp();
                 }
+                PROF_MARK(5);
                 if (overflow)
                     break;
             }
             if (a.optimal)
             {
-                if (hypot(gx - cn.x, gy - cn.y) <= 1.0) // stop_radius (hybrid_a_star.h:345)
+                if (dm::hypot_(gx - cn.x, gy - cn.y) <= 1.0) // stop_radius (hybrid_a_star.h:345)
                     break;
             }
             ++iteration;
         }
         n_iter = iteration;
+        PROF_FLUSH;
         if (overflow)
             status = ST_OVERFLOW;
         else if (goal_found)
@@ -468,16 +490,21 @@ __device__ void plan_one_query(const MapView &m, const PlannerView &p, const Pla
         a.path_len[q] = out_len;
         if (a.stats)
         {
-            a.stats[4 * q + 0] = n_iter;
-            a.stats[4 * q + 1] = n_prim;
-            a.stats[4 * q + 2] = n_shots;
-            a.stats[4 * q + 3] = n_coll;
+            a.stats[6 * q + 0] = n_iter;
+            a.stats[6 * q + 1] = n_prim;
+            a.stats[6 * q + 2] = n_shots;
+            a.stats[6 * q + 3] = n_coll;
+            a.stats[6 * q + 4] = init_ok ? bfs.cells : 0;
+            a.stats[6 * q + 5] = n_nodes;
         }
     }
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(128) plan_batch_kernel(MapView m, PlannerView p, PlanBatchArgs a)
+#ifndef MPROS_PLAN_MIN_BLOCKS
+#define MPROS_PLAN_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(128, MPROS_PLAN_MIN_BLOCKS) plan_batch_kernel(MapView m, PlannerView p, PlanBatchArgs a)
 {
     const int lane = threadIdx.x & 31;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -549,7 +576,7 @@ __global__ void __launch_bounds__(128) rs_batch_kernel(MapView m, PlannerView p,
             for (int k = 0; k < stored && !hit; ++k)
             {
                 double s, c;
-                sincos(txyz[3 * k + 2], &s, &c);
+                dm::sincos_(txyz[3 * k + 2], &s, &c);
                 hit = warp_footprint_collision(m, p, txyz[3 * k], txyz[3 * k + 1], s, c);
             }
             if (lane == 0)
@@ -616,12 +643,12 @@ __global__ void __launch_bounds__(128) expand_batch_kernel(MapView m, PlannerVie
         const double *pr = a.parents6 + 6 * (size_t)q;
         const double cx = pr[0], cy = pr[1], cyaw = pr[2], psteer = pr[3], pdir = pr[4], pg = pr[5];
         double s_yaw, c_yaw;
-        sincos(cyaw, &s_yaw, &c_yaw);
+        dm::sincos_(cyaw, &s_yaw, &c_yaw);
         double nx = 0, ny = 0, nyaw = 0, steer = 0, direc = 1, ns = 0, nc = 1;
         if (lane < P)
         {
             primitive_end_pose(p, lane, cx, cy, cyaw, s_yaw, c_yaw, nx, ny, nyaw, steer, direc);
-            sincos(nyaw, &ns, &nc);
+            dm::sincos_(nyaw, &ns, &nc);
         }
         unsigned free_mask = 0;
         for (int c = 0; c < P; ++c)
@@ -994,7 +1021,9 @@ static int plan_pass(mpros_ctx *c, PlanBatchArgs &a, int pass, int node_cap, int
     MPROS_CUDA(cudaMemGetInfo(&free_b, &total_b));
     size_t budget = (free_b + S.ws_bytes) / 2;
     int per_block = 4;
-    int blocks = prop.multiProcessorCount * 4;
+    int resident = 0;
+    MPROS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, plan_batch_kernel, per_block * 32, 0));
+    int blocks = prop.multiProcessorCount * std::max(1, resident);
     blocks = std::min(blocks, (n_run + per_block - 1) / per_block);
     blocks = std::min<long long>(blocks, std::max<long long>(1, (long long)(budget / L.stride) / per_block));
     if (max_warps > 0)
@@ -1035,8 +1064,40 @@ static int plan_pass(mpros_ctx *c, PlanBatchArgs &a, int pass, int node_cap, int
     a.tag_base = S.tag_base;
     a.todo = d_todo;
     a.n_todo = n_run;
+    const bool dbg = std::getenv("MPROS_DEBUG") != nullptr;
+    cudaEvent_t e0, e1;
+    if (dbg)
+    {
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, c->stream);
+    }
     plan_batch_kernel<<<blocks, per_block * 32, 0, c->stream>>>(c->view(), c->pv, a);
     MPROS_LAUNCH_CHECK(c);
+    if (dbg)
+    {
+        cudaEventRecord(e1, c->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+#ifdef MPROS_PROFILE
+        {
+            unsigned long long h[8];
+            cudaMemcpyFromSymbol(h, g_prof, sizeof(h));
+            unsigned long long z[8] = {0};
+            cudaMemcpyToSymbol(g_prof, z, sizeof(z));
+            double tot = 0;
+            for (int k = 0; k < 8; ++k)
+                tot += (double)h[k];
+            std::fprintf(stderr, "[mpros] cycles%%: pop %.1f shot %.1f collision %.1f cell+bfs+g %.1f h2 %.1f insert %.1f loop %.1f (total %.3g warp-cycles)\n",
+                         100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot, 100 * h[4] / tot, 100 * h[5] / tot, 100 * h[7] / tot, tot);
+        }
+#endif
+        std::fprintf(stderr, "[mpros] plan pass %d: %d queries, node_cap %d, %d warps, %.1f MB/warp, %.3f ms\n", pass, n_run, node_cap,
+                     blocks * per_block, L.stride / 1048576.0, ms);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
     S.tag_base += (uint32_t)n_run + 1;
     return MPROS_OK;
 }
@@ -1061,7 +1122,7 @@ static int plan_batch_dev_impl(mpros_ctx *c, const double *d_starts, const doubl
     PlanScratch &S = g_plan_scratch[c->device & 15][0];
     // pass 1: every query with a small node pool; later passes: only the queries that overflowed, bigger pools
     const long long max_nodes = (long long)(c->pp.max_iteration + 2) * (2 * c->pv.n_steer) + 16;
-    long long caps[3] = {4096, 131072, max_nodes};
+    long long caps[3] = {16384, 131072, max_nodes};
     int rc = plan_pass(c, a, 0, (int)std::min<long long>(caps[0], max_nodes), nq, nullptr, 0);
     if (rc)
         return rc;
@@ -1141,7 +1202,7 @@ extern "C" int mpros_plan_batch(mpros_ctx *c, const double *starts3, const doubl
     MPROS_CUDA(cudaSetDevice(c->device));
     size_t pose_b = nq * 24, path_b = nq * (size_t)path_cap * 5 * 8;
     size_t total = 2 * align_up(pose_b, 256) + align_up(nq * 4, 256) * 2 + align_up(nq * 8, 256) + align_up(path_b, 256) +
-                   align_up(nq * 32, 256) + 1024;
+                   align_up(nq * 48, 256) + 1024;
     rc = ensure_stage(c, total);
     if (rc)
         return rc;
@@ -1156,7 +1217,7 @@ extern "C" int mpros_plan_batch(mpros_ctx *c, const double *starts3, const doubl
     int32_t *d_status = (int32_t *)take(nq * 4), *d_len = (int32_t *)take(nq * 4);
     double *d_cost = (double *)take(nq * 8);
     double *d_paths = path_cap ? (double *)take(path_b) : nullptr;
-    int64_t *d_stats = (int64_t *)take(nq * 32);
+    int64_t *d_stats = (int64_t *)take(nq * 48);
     cudaStream_t st = c->stream;
     MPROS_CUDA(cudaMemcpyAsync(d_s, starts3, pose_b, cudaMemcpyHostToDevice, st));
     MPROS_CUDA(cudaMemcpyAsync(d_g, goals3, pose_b, cudaMemcpyHostToDevice, st));
@@ -1169,7 +1230,7 @@ extern "C" int mpros_plan_batch(mpros_ctx *c, const double *starts3, const doubl
     if (path_cap)
         MPROS_CUDA(cudaMemcpyAsync(paths, d_paths, path_b, cudaMemcpyDeviceToHost, st));
     if (stats)
-        MPROS_CUDA(cudaMemcpyAsync(stats, d_stats, nq * 32, cudaMemcpyDeviceToHost, st));
+        MPROS_CUDA(cudaMemcpyAsync(stats, d_stats, nq * 48, cudaMemcpyDeviceToHost, st));
     MPROS_CUDA(cudaStreamSynchronize(st));
     return MPROS_OK;
 }

@@ -28,7 +28,7 @@ struct __align__(8) PlanNode
 
 // ---- warp-cooperative footPrintInCollision4 (hybrid_a_star.cpp:617-680) ---------------------------------------------
 // All lanes pass the same pose; probe k of the pose is evaluated by lane (k mod 32). Verdict is warp-uniform.
-__device__ __forceinline__ bool warp_footprint_collision(const MapView &m, const PlannerView &p, double px, double py, double s,
+__device__ __noinline__ bool warp_footprint_collision(const MapView &m, const PlannerView &p, double px, double py, double s,
                                                          double c)
 {
     const int lane = threadIdx.x & 31;
@@ -72,7 +72,7 @@ __device__ __forceinline__ bool heap_less(unsigned long long ka, uint32_t ia, un
     return ka < kb || (ka == kb && ia < ib);
 }
 // executed by lane 0 only; caller follows with __syncwarp()
-__device__ __forceinline__ void heap_push_lane0(OpenHeap &h, unsigned long long k, uint32_t id)
+__device__ __noinline__ void heap_push_lane0(OpenHeap &h, unsigned long long k, uint32_t id)
 {
     int pos = h.size;
     while (pos > 0)
@@ -90,7 +90,7 @@ __device__ __forceinline__ void heap_push_lane0(OpenHeap &h, unsigned long long 
     h.id[pos] = id;
 }
 // warp-cooperative pop; returns the id with the smallest (key, id); h.size must be > 0
-__device__ __forceinline__ uint32_t heap_pop_warp(OpenHeap &h, unsigned long long &out_key)
+__device__ __noinline__ uint32_t heap_pop_warp(OpenHeap &h, unsigned long long &out_key)
 {
     const int lane = threadIdx.x & 31;
     unsigned long long rk = h.key[0];
@@ -163,7 +163,7 @@ __device__ __forceinline__ uint32_t hash_index(unsigned long long idx)
     return (uint32_t)idx;
 }
 // single-lane find-or-insert-slot: returns slot; found says whether the key was present
-__device__ __forceinline__ uint32_t closed_find(const ClosedSet &t, unsigned long long idx, bool &found)
+__device__ __noinline__ uint32_t closed_find(const ClosedSet &t, unsigned long long idx, bool &found)
 {
     unsigned long long want = (t.tag << 34) | idx;
     uint32_t s = hash_index(idx) & t.mask;
@@ -196,9 +196,10 @@ struct GoalBfs
     int level;                // levels <= level are final
     int done;                 // frontier exhausted or level 999 reached
     int br0, br1, bw0, bw1;   // bbox (rows, words; map coordinates) of every visited cell so far
+    long long cells;          // cells discovered so far (statistics)
 };
 
-__device__ __forceinline__ void bfs_init_rows(const MapView &m, GoalBfs &b, int ra, int rb)
+__device__ __noinline__ void bfs_init_rows(const MapView &m, GoalBfs &b, int ra, int rb)
 {
     const int lane = threadIdx.x & 31;
     ra = max(ra, b.r0);
@@ -238,6 +239,7 @@ __device__ __forceinline__ void bfs_start(const MapView &m, GoalBfs &b, int gi, 
     b.wwords = w1 - b.w0 + 1;
     b.level = 0;
     b.done = 0;
+    b.cells = 1;
     b.br0 = b.br1 = gi;
     b.bw0 = b.bw1 = gj >> 5;
     bfs_init_rows(m, b, gi - 2, gi + 2);
@@ -251,7 +253,7 @@ __device__ __forceinline__ void bfs_start(const MapView &m, GoalBfs &b, int gi, 
 }
 
 // advance the wavefront by one level (warp-cooperative)
-__device__ __forceinline__ void bfs_step(const MapView &m, GoalBfs &b)
+__device__ __noinline__ void bfs_step(const MapView &m, GoalBfs &b)
 {
     const int lane = threadIdx.x & 31;
     const int level = b.level + 1;
@@ -270,6 +272,7 @@ __device__ __forceinline__ void bfs_step(const MapView &m, GoalBfs &b)
     uint32_t *fnext = (level & 1) ? b.f1 : b.f0;
     const int wpr = (m.W + 31) >> 5;
     int nr0 = 1 << 30, nr1 = -1, nw0 = 1 << 30, nw1 = -1;
+    int found = 0;
     for (int k = lane; k < total; k += 32)
     {
         int r = sr0 + k / nw, w = sw0 + k % nw;
@@ -292,6 +295,7 @@ __device__ __forceinline__ void bfs_step(const MapView &m, GoalBfs &b)
         if (nbits)
         {
             b.blocked[o] = bl | nbits;
+            found += __popc(nbits);
             nr0 = min(nr0, r), nr1 = max(nr1, r), nw0 = min(nw0, w), nw1 = max(nw1, w);
             uint16_t *drow = b.dist + ((size_t)lr * b.wwords + lw) * 32;
             while (nbits)
@@ -309,9 +313,11 @@ __device__ __forceinline__ void bfs_step(const MapView &m, GoalBfs &b)
         nr1 = max(nr1, __shfl_xor_sync(kFull, nr1, o));
         nw0 = min(nw0, __shfl_xor_sync(kFull, nw0, o));
         nw1 = max(nw1, __shfl_xor_sync(kFull, nw1, o));
+        found += __shfl_xor_sync(kFull, found, o);
     }
     __syncwarp();
     b.level = level;
+    b.cells += found;
     if (nr1 < 0)
         b.done = 1; // empty frontier
     else
@@ -396,7 +402,7 @@ __device__ __forceinline__ void primitive_end_pose(const PlannerView &p, int pri
         double steer_sign = steer / fabs(steer);
         double dyaw = p.step_size / radius;
         double sd, cd;
-        sincos(dyaw, &sd, &cd);
+        dm::sincos_(dyaw, &sd, &cd);
         dx = sd * radius * direc;
         dy = (1 - cd) * radius * steer_sign;
         nx = dx * c_yaw - dy * s_yaw + cx;

@@ -16,6 +16,22 @@ constexpr double kPi = 3.14159265358979323846;
 constexpr double kPi2 = 1.57079632679489661923; // M_PI_2
 constexpr unsigned kFull = 0xffffffffu;
 
+// Out-of-line wrappers of the FP64 math routines. The planner kernel calls each of them from dozens of sites; inlined
+// they blow the code up to ~290 KB and the kernel becomes instruction-fetch bound (ncu: stall_no_instruction dominant).
+// One shared copy each keeps the hot loop inside the instruction caches. Results are identical to the inlined calls.
+namespace dm
+{
+__device__ __noinline__ double atan2_(double y, double x) { return atan2(y, x); }
+__device__ __noinline__ double sqrt_(double x) { return sqrt(x); }
+__device__ __noinline__ double asin_(double x) { return asin(x); }
+__device__ __noinline__ double acos_(double x) { return acos(x); }
+__device__ __noinline__ double hypot_(double x, double y) { return hypot(x, y); }
+__device__ __noinline__ double sin_(double x) { return sin(x); }
+__device__ __noinline__ double cos_(double x) { return cos(x); }
+__device__ __noinline__ void sincos_(double x, double *s, double *c) { sincos(x, s, c); }
+__device__ __noinline__ double div_(double a, double b) { return a / b; }
+} // namespace dm
+
 struct RsConfig
 {
     double radius, steer_angle, step;
@@ -56,11 +72,11 @@ __device__ __noinline__ void rs_formula(int f, double x, double y, double phi, R
 {
     p.n = 0;
     double sphi, cphi;
-    sincos(phi, &sphi, &cphi);
+    dm::sincos_(phi, &sphi, &cphi);
     const bool typeA = (f == 0 || f == 2 || f == 3 || f == 4 || f == 7 || f == 9);
     double ax = typeA ? x - sphi : x + sphi;
     double ay = typeA ? y - 1 + cphi : y - 1 - cphi;
-    double dist = hypot(ax, ay), theta = atan2(ay, ax);
+    double dist = dm::hypot_(ax, ay), theta = dm::atan2_(ay, ax);
     const int L_ = 1, S_ = 0, R_ = -1, F_ = 1, B_ = -1;
     switch (f)
     {
@@ -73,8 +89,8 @@ __device__ __noinline__ void rs_formula(int f, double x, double y, double phi, R
     case 1:
         if (dist * dist >= 4)
         {
-            double u = sqrt(dist * dist - 4);
-            double t = rs_regular_rad(theta + atan2(2.0, u));
+            double u = dm::sqrt_(dist * dist - 4);
+            double t = rs_regular_rad(theta + dm::atan2_(2.0, u));
             double v = rs_regular_rad(t - phi);
             rs_push(p, t, L_, F_), rs_push(p, u, S_, F_), rs_push(p, v, R_, F_);
         }
@@ -82,7 +98,7 @@ __device__ __noinline__ void rs_formula(int f, double x, double y, double phi, R
     case 2:
         if (dist <= 4)
         {
-            double A = acos(dist / 4);
+            double A = dm::acos_(dist / 4);
             double u = rs_regular_rad(kPi - 2 * A);
             double t = rs_regular_rad(kPi2 + A + theta);
             double v = rs_regular_rad(phi - t - u);
@@ -92,9 +108,9 @@ __device__ __noinline__ void rs_formula(int f, double x, double y, double phi, R
     case 3:
         if (dist <= 4)
         {
-            double A = acos(dist / 4);
+            double A = dm::acos_(dist / 4);
             double u = rs_regular_rad(kPi - 2 * A);
-            double t = asin(theta + kPi2 + A); // sic, rs_curve.cpp:418
+            double t = dm::asin_(theta + kPi2 + A); // sic, rs_curve.cpp:418
             double v = rs_regular_rad(t + u - phi);
             rs_push(p, t, L_, F_), rs_push(p, u, R_, B_), rs_push(p, v, L_, B_);
         }
@@ -102,8 +118,8 @@ __device__ __noinline__ void rs_formula(int f, double x, double y, double phi, R
     case 4:
         if (dist <= 4)
         {
-            double u = acos(1 - dist * dist / 8);
-            double A = asin(2 * sin(u) / dist);
+            double u = dm::acos_(1 - dist * dist / 8);
+            double A = dm::asin_(2 * dm::sin_(u) / dist);
             double t = rs_regular_rad(theta + kPi2 - A);
             double v = rs_regular_rad(t - u - phi);
             rs_push(p, t, L_, F_), rs_push(p, u, R_, F_), rs_push(p, v, L_, B_);
@@ -115,14 +131,14 @@ __device__ __noinline__ void rs_formula(int f, double x, double y, double phi, R
             double A, t, u, v;
             if (dist <= 2)
             {
-                A = acos((dist + 2) / 4);
+                A = dm::acos_((dist + 2) / 4);
                 t = rs_regular_rad(theta + kPi2 + A);
                 u = rs_regular_rad(A);
                 v = rs_regular_rad(phi - t + 2 * u);
             }
             else
             {
-                A = acos((dist - 2) / 4);
+                A = dm::acos_((dist - 2) / 4);
                 t = rs_regular_rad(theta + kPi2 - A);
                 u = rs_regular_rad(kPi - A);
                 v = rs_regular_rad(phi - t + 2 * u);
@@ -135,8 +151,8 @@ __device__ __noinline__ void rs_formula(int f, double x, double y, double phi, R
         double u1 = (20 - dist * dist) / 16;
         if (dist <= 6 && u1 >= 0 && u1 <= 1)
         {
-            double u = acos(u1);
-            double A = asin(2 * sin(u) / dist);
+            double u = dm::acos_(u1);
+            double A = dm::asin_(2 * dm::sin_(u) / dist);
             double t = rs_regular_rad(theta + kPi2 + A);
             double v = rs_regular_rad(t - phi);
             rs_push(p, t, L_, F_), rs_push(p, u, R_, B_), rs_push(p, u, L_, B_), rs_push(p, v, R_, F_);
@@ -146,8 +162,8 @@ __device__ __noinline__ void rs_formula(int f, double x, double y, double phi, R
     case 7:
         if (dist >= 2)
         {
-            double u = sqrt(dist * dist - 4) - 2;
-            double A = atan2(2.0, u + 2);
+            double u = dm::sqrt_(dist * dist - 4) - 2;
+            double A = dm::atan2_(2.0, u + 2);
             double t = rs_regular_rad(theta + kPi2 + A);
             double v = rs_regular_rad(t - phi + kPi2);
             rs_push(p, t, L_, F_), rs_push(p, kPi2, R_, B_), rs_push(p, u, S_, B_), rs_push(p, v, L_, B_);
@@ -165,8 +181,8 @@ __device__ __noinline__ void rs_formula(int f, double x, double y, double phi, R
     case 9:
         if (dist >= 2)
         {
-            double u = sqrt(dist * dist - 4) - 2;
-            double A = atan2(u + 2, 2.0);
+            double u = dm::sqrt_(dist * dist - 4) - 2;
+            double A = dm::atan2_(u + 2, 2.0);
             double t = rs_regular_rad(theta + kPi2 - A);
             double v = rs_regular_rad(t - phi - kPi2);
             rs_push(p, t, L_, F_), rs_push(p, u, S_, F_), rs_push(p, kPi2, R_, F_), rs_push(p, v, L_, B_);
@@ -184,8 +200,8 @@ __device__ __noinline__ void rs_formula(int f, double x, double y, double phi, R
     case 11:
         if (dist >= 4)
         {
-            double u = sqrt(dist * dist - 4) - 4;
-            double A = atan2(2.0, u + 4);
+            double u = dm::sqrt_(dist * dist - 4) - 4;
+            double A = dm::atan2_(2.0, u + 4);
             double t = rs_regular_rad(theta + kPi2 + A);
             double v = rs_regular_rad(t - phi);
             rs_push(p, t, L_, F_), rs_push(p, kPi2, R_, B_), rs_push(p, u, S_, B_), rs_push(p, kPi2, L_, B_),
@@ -249,14 +265,14 @@ __device__ __forceinline__ double rs_path_length(const RsConfig &c, const RsPath
 // RSCurve::FindOptimalPath (rs_curve.cpp:111-163), one warp per shot. Candidate c = 4*f + j (f formula, j symmetry)
 // in the reference's evaluation order; multimap.begin() = smallest cost, first inserted among equals.
 // All lanes return the same best path / cost.
-__device__ __forceinline__ double rs_find_optimal_warp(const RsConfig &c, double sx, double sy, double sphi, int start_direc,
+__device__ __noinline__ double rs_find_optimal_warp(const RsConfig &c, double sx, double sy, double sphi, int start_direc,
                                                        double start_steer, double ex, double ey, double ephi, RsPath &best)
 {
     const int lane = threadIdx.x & 31;
     // NewGoalPoint (:51-58)
     double dx = ex - sx, dy = ey - sy;
     double cs, sn;
-    sincos(sphi, &sn, &cs);
+    dm::sincos_(sphi, &sn, &cs);
     double gx = (dx * cs + dy * sn) / c.radius;
     double gy = (-dx * sn + dy * cs) / c.radius;
     double gphi = ephi - sphi;
@@ -348,14 +364,14 @@ __device__ __noinline__ int rs_gen_traj(const RsConfig &c, double sx, double sy,
         {
             double dyaw = seg.len / num_pt;
             double sd, cd;
-            sincos(dyaw, &sd, &cd);
+            dm::sincos_(dyaw, &sd, &cd);
             double dx = sd * c.radius * direc;
             double dy = (1 - cd) * c.radius * (double)seg.steer;
 #pragma unroll 1
             for (int i = 0; i < num_pt; ++i)
             {
                 double sy_, cy_;
-                sincos(curr_yaw, &sy_, &cy_);
+                dm::sincos_(curr_yaw, &sy_, &cy_);
                 double nx = curr_x + (dx * cy_ - dy * sy_);
                 double ny = curr_y + (dx * sy_ + dy * cy_);
                 curr_x = nx;
@@ -375,7 +391,7 @@ __device__ __noinline__ int rs_gen_traj(const RsConfig &c, double sx, double sy,
         {
             double step = seg.len * c.radius / num_pt;
             double sy_, cy_;
-            sincos(curr_yaw, &sy_, &cy_);
+            dm::sincos_(curr_yaw, &sy_, &cy_);
 #pragma unroll 1
             for (int i = 0; i < num_pt; ++i)
             {
@@ -399,23 +415,31 @@ __device__ __noinline__ int rs_gen_traj(const RsConfig &c, double sx, double sy,
 // OMPL, see oracle/port/ompl_rs_distance.h); this mirrors it operation for operation.
 __device__ __forceinline__ double ompl_mod2pi(double x)
 {
-    double v = fmod(x, 2.0 * kPi);
+    // v = fmod(x, 2*pi), exact: identity below 2*pi; one exact subtraction (Sterbenz: 2pi <= |x| < 4pi) below 4*pi
+    const double twopi = 2.0 * kPi;
+    double ax = fabs(x), v;
+    if (ax < twopi)
+        v = x;
+    else if (ax < 2.0 * twopi)
+        v = x < 0 ? x + twopi : x - twopi;
+    else
+        v = fmod(x, twopi);
     if (v < -kPi)
-        v += 2.0 * kPi;
+        v += twopi;
     else if (v > kPi)
-        v -= 2.0 * kPi;
+        v -= twopi;
     return v;
 }
 constexpr double kOmplZero = 10.0 * DBL_EPSILON;
 
-__device__ __forceinline__ void ompl_tau_omega(double u, double v, double xi, double eta, double phi, double &tau, double &omega)
+__device__ __noinline__ void ompl_tau_omega(double u, double v, double xi, double eta, double phi, double &tau, double &omega)
 {
     double delta = ompl_mod2pi(u - v);
     double su, cu, sd, cd;
-    sincos(u, &su, &cu);
-    sincos(delta, &sd, &cd);
+    dm::sincos_(u, &su, &cu);
+    dm::sincos_(delta, &sd, &cd);
     double A = su - sd, B = cu - cd - 1.;
-    double t1 = atan2(eta * A - xi * B, xi * A + eta * B), t2 = 2. * (cd - cos(v) - cu) + 3;
+    double t1 = dm::atan2_(eta * A - xi * B, xi * A + eta * B), t2 = 2. * (cd - dm::cos_(v) - cu) + 3;
     tau = (t2 < 0) ? ompl_mod2pi(t1 + kPi) : ompl_mod2pi(t1);
     omega = ompl_mod2pi(tau - u + v - phi);
 }
@@ -430,15 +454,15 @@ __device__ __noinline__ void ompl_families(double x, double y, double phi, doubl
     m_ccsc = DBL_MAX;
     m_ccscc = DBL_MAX;
     double sphi, cphi;
-    sincos(phi, &sphi, &cphi);
+    dm::sincos_(phi, &sphi, &cphi);
     double t, u, v;
     // ---- arguments shared by several formulas
     const double xm = x - sphi, ym = y - 1. + cphi; // (xi, eta) of LpSpLp / LpRmL / LpRmSmLm
     const double xp = x + sphi, yp = y - 1. - cphi; // (xi, eta) of LpSpRp / CCCC / LpRmSmRm / LpRmSLmRp
     // LpSpLp (8.1)
     {
-        u = sqrt(xm * xm + ym * ym);
-        t = atan2(ym, xm);
+        u = dm::sqrt_(xm * xm + ym * ym);
+        t = dm::atan2_(ym, xm);
         if (t >= -kOmplZero)
         {
             v = ompl_mod2pi(phi - t);
@@ -448,12 +472,12 @@ __device__ __noinline__ void ompl_families(double x, double y, double phi, doubl
     }
     // LpSpRp (8.2)
     {
-        double u1 = sqrt(xp * xp + yp * yp), t1 = atan2(yp, xp);
+        double u1 = dm::sqrt_(xp * xp + yp * yp), t1 = dm::atan2_(yp, xp);
         u1 = u1 * u1;
         if (u1 >= 4.)
         {
-            u = sqrt(u1 - 4.);
-            double theta = atan2(2., u);
+            u = dm::sqrt_(u1 - 4.);
+            double theta = dm::atan2_(2., u);
             t = ompl_mod2pi(t1 + theta);
             v = ompl_mod2pi(t - phi);
             if (t >= -kOmplZero && v >= -kOmplZero)
@@ -465,10 +489,10 @@ __device__ __noinline__ void ompl_families(double x, double y, double phi, doubl
     for (int b = 0; b < 2; ++b)
     {
         double xi = b ? xb - sphi : xm, eta = b ? yb - 1. + cphi : ym;
-        double u1 = sqrt(xi * xi + eta * eta), theta = atan2(eta, xi);
+        double u1 = dm::sqrt_(xi * xi + eta * eta), theta = dm::atan2_(eta, xi);
         if (u1 <= 4.)
         {
-            u = -2. * asin(.25 * u1);
+            u = -2. * dm::asin_(.25 * u1);
             t = ompl_mod2pi(theta + .5 * u + kPi);
             v = ompl_mod2pi(phi - t + u);
             if (t >= -kOmplZero && u <= kOmplZero)
@@ -477,10 +501,10 @@ __device__ __noinline__ void ompl_families(double x, double y, double phi, doubl
     }
     // LpRupLumRm (8.7)
     {
-        double rho = .25 * (2. + sqrt(xp * xp + yp * yp));
+        double rho = .25 * (2. + dm::sqrt_(xp * xp + yp * yp));
         if (rho <= 1.)
         {
-            u = acos(rho);
+            u = dm::acos_(rho);
             ompl_tau_omega(u, -u, xp, yp, phi, t, v);
             if (t >= -kOmplZero && v <= kOmplZero)
                 m_plain = fmin(m_plain, fabs(t) + 2. * fabs(u) + fabs(v));
@@ -491,7 +515,7 @@ __device__ __noinline__ void ompl_families(double x, double y, double phi, doubl
         double rho = (20. - xp * xp - yp * yp) / 16.;
         if (rho >= 0 && rho <= 1)
         {
-            u = -acos(rho);
+            u = -dm::acos_(rho);
             if (u >= -.5 * kPi)
             {
                 ompl_tau_omega(u, u, xp, yp, phi, t, v);
@@ -505,18 +529,18 @@ __device__ __noinline__ void ompl_families(double x, double y, double phi, doubl
     for (int b = 0; b < 2; ++b)
     {
         double xi = b ? xb - sphi : xm, eta = b ? yb - 1. + cphi : ym;
-        double rho = sqrt(xi * xi + eta * eta), theta = atan2(eta, xi);
+        double rho = dm::sqrt_(xi * xi + eta * eta), theta = dm::atan2_(eta, xi);
         if (rho >= 2.)
         {
-            double r = sqrt(rho * rho - 4.);
+            double r = dm::sqrt_(rho * rho - 4.);
             u = 2. - r;
-            t = ompl_mod2pi(theta + atan2(r, -2.));
+            t = ompl_mod2pi(theta + dm::atan2_(r, -2.));
             v = ompl_mod2pi(phi - .5 * kPi - t);
             if (t >= -kOmplZero && u <= kOmplZero && v <= kOmplZero)
                 m_ccsc = fmin(m_ccsc, fabs(t) + fabs(u) + fabs(v));
         }
         double xi2 = b ? xb + sphi : xp, eta2 = b ? yb - 1. - cphi : yp;
-        double rho2 = sqrt(eta2 * eta2 + xi2 * xi2), theta2 = atan2(xi2, -eta2); // polar(-eta, xi)
+        double rho2 = dm::sqrt_(eta2 * eta2 + xi2 * xi2), theta2 = dm::atan2_(xi2, -eta2); // polar(-eta, xi)
         if (rho2 >= 2.)
         {
             t = theta2;
@@ -528,13 +552,13 @@ __device__ __noinline__ void ompl_families(double x, double y, double phi, doubl
     }
     // LpRmSLmRp (8.11)
     {
-        double rho = sqrt(xp * xp + yp * yp);
+        double rho = dm::sqrt_(xp * xp + yp * yp);
         if (rho >= 2.)
         {
-            u = 4. - sqrt(rho * rho - 4.);
+            u = 4. - dm::sqrt_(rho * rho - 4.);
             if (u <= kOmplZero)
             {
-                t = ompl_mod2pi(atan2((4. - u) * xp - 2. * yp, -2. * xp + (u - 4.) * yp));
+                t = ompl_mod2pi(dm::atan2_((4. - u) * xp - 2. * yp, -2. * xp + (u - 4.) * yp));
                 v = ompl_mod2pi(t - phi);
                 if (t >= -kOmplZero && v >= -kOmplZero)
                     m_ccscc = fmin(m_ccscc, fabs(t) + fabs(u) + fabs(v));
@@ -546,17 +570,17 @@ __device__ __noinline__ void ompl_families(double x, double y, double phi, doubl
 // Groups of 4 consecutive lanes cooperate on one (start -> goal) pair: lane (q = lane & 3) evaluates symmetry image q
 // of every base formula; the family minima are combined across the group with shuffles. All 4 lanes of the group get
 // the result. Inactive groups must still call this (full-warp shuffles) with any finite arguments.
-__device__ __forceinline__ double ompl_rs_distance_quad(double rho, double x1, double y1, double th1, double x2, double y2,
+__device__ __noinline__ double ompl_rs_distance_quad(double rho, double x1, double y1, double th1, double x2, double y2,
                                                         double th2)
 {
     const int q = threadIdx.x & 3;
     double dx = x2 - x1, dy = y2 - y1, dth = th2 - th1;
     double c, s;
-    sincos(th1, &s, &c);
+    dm::sincos_(th1, &s, &c);
     double x = (c * dx + s * dy) / rho, y = (-s * dx + c * dy) / rho;
     // backwards point of the un-flipped image; its images follow the same sign pattern
     double sphi, cphi;
-    sincos(dth, &sphi, &cphi);
+    dm::sincos_(dth, &sphi, &cphi);
     double xb = x * cphi + y * sphi, yb = x * sphi - y * cphi;
     const bool fx = (q == 1 || q == 3), fy = (q == 2 || q == 3), fp = (q == 1 || q == 2);
     double m_plain, m_ccsc, m_ccscc;

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmpros_b200.so")
+LIB_PATH = os.environ.get("MPROS_LIB", os.path.join(HERE, "libmpros_b200.so"))
 
 LAYERS = {
     "static_orig": (0, np.int8, True),
@@ -351,11 +351,12 @@ class Context:
         cost = np.zeros(nq)
         plen = np.zeros(nq, dtype=np.int32)
         paths = np.zeros((nq, path_cap, 5))
-        stats = np.zeros((nq, 4), dtype=np.int64)
+        stats = np.zeros((nq, 6), dtype=np.int64)
         self._check(self.L.mpros_plan_batch(self.h, s.ctypes.data, g.ctypes.data, nq, status.ctypes.data, cost.ctypes.data,
                                             plen.ctypes.data, paths.ctypes.data if path_cap else None, path_cap, stats.ctypes.data))
         return {"status": status, "cost": cost, "path_len": plen, "paths": paths, "iterations": stats[:, 0],
-                "primitives": stats[:, 1], "rs_shots": stats[:, 2], "collision_checks": stats[:, 3]}
+                "primitives": stats[:, 1], "rs_shots": stats[:, 2], "collision_checks": stats[:, 3],
+                "goal_map_cells": stats[:, 4], "nodes_inserted": stats[:, 5]}
 
     def plan_batch_dev(self, d_starts, d_goals, nq, d_status, d_cost, d_len, d_paths, path_cap, d_stats):
         self._check(self.L.mpros_plan_batch_dev(self.h, d_starts, d_goals, nq, d_status, d_cost, d_len, d_paths, path_cap, d_stats))

@@ -206,8 +206,8 @@ enum mpros_plan_status
  * The per-query goal map is computed on demand on the device (values identical to generateGoalMap's).
  * starts3/goals3: double[3nq]; status: int32[nq] (enum mpros_plan_status); cost: double[nq] = goal_node_->gvalue_
  * (-1 when not found); path_len: int32[nq] = path_.size(); paths: double[nq*path_cap*5] {x, y, yaw, steer, direction}
- * (first path_cap points; may be NULL with path_cap == 0); stats (optional): int64[4nq] {iterations, primitives
- * evaluated (tree_.size()), RS shots, footPrintInCollision4 calls}. */
+ * (first path_cap points; may be NULL with path_cap == 0); stats (optional): int64[6nq] {iterations, primitives
+ * evaluated (tree_.size()), RS shots, footPrintInCollision4 calls, goal-map cells computed, nodes inserted}. */
 MPROS_API int mpros_plan_batch(mpros_ctx *ctx, const double *starts3, const double *goals3, size_t nq, int32_t *status,
                                double *cost, int32_t *path_len, double *paths, int path_cap, int64_t *stats);
 MPROS_API int mpros_plan_batch_dev(mpros_ctx *ctx, const double *d_starts3, const double *d_goals3, size_t nq,

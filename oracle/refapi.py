@@ -74,28 +74,15 @@ def load_map(name):
 
 
 def synthetic_occupancy(size=8192, n_rect=1100, seed=20261019, res=0.1):
-    """Synthetic config of SURVEY.md §8(d): 1-m border wall + n_rect axis-aligned rectangles with sides
-    U[2,20] m and uniform centres, clipped; values {0,100}. (numpy Generator instead of mt19937_64 — the
-    map itself is the fixture, both arms consume the same array.)"""
-    rng = np.random.Generator(np.random.PCG64(seed))
-    occ = np.zeros((size, size), dtype=np.int8)
-    b = int(round(1.0 / res))
-    occ[:b, :] = 100
-    occ[-b:, :] = 100
-    occ[:, :b] = 100
-    occ[:, -b:] = 100
-    ext = size * res
-    cx = rng.uniform(0, ext, n_rect)
-    cy = rng.uniform(0, ext, n_rect)
-    sx = rng.uniform(2, 20, n_rect)
-    sy = rng.uniform(2, 20, n_rect)
-    for k in range(n_rect):
-        j0 = max(0, int((cx[k] - sx[k] / 2) / res))
-        j1 = min(size, int((cx[k] + sx[k] / 2) / res) + 1)
-        i0 = max(0, int((cy[k] - sy[k] / 2) / res))
-        i1 = min(size, int((cy[k] + sy[k] / 2) / res) + 1)
-        occ[i0:i1, j0:j1] = 100
-    return occ
+    """Synthetic map of SURVEY.md §8(d) — the generator lives with the workloads (input data, not oracle logic)."""
+    import sys
+
+    pkg = os.path.join(os.path.dirname(HERE), "hybrid-astar-planner_b200")
+    if pkg not in sys.path:
+        sys.path.insert(0, pkg)
+    import synthetic
+
+    return synthetic.synthetic_occupancy(size, n_rect, seed, res)
 
 
 def _dp(a):
