@@ -87,7 +87,7 @@ struct PlanBatchArgs
 __device__ unsigned long long g_prof[8];
 #define PROF_DECL long long pt0 = clock64(), pt1; long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define PROF_MARK(k) do { pt1 = clock64(); pacc[k] += pt1 - pt0; pt0 = pt1; } while (0)
-#define PROF_FLUSH do { if ((threadIdx.x & 31) == 0) for (int k_ = 0; k_ < 8; ++k_) atomicAdd(&g_prof[k_], (unsigned long long)pacc[k_]); } while (0)
+#define PROF_FLUSH do { if (threadIdx.x == 0) for (int k_ = 0; k_ < 8; ++k_) atomicAdd(&g_prof[k_], (unsigned long long)pacc[k_]); } while (0)
 #else
 #define PROF_DECL
 #define PROF_MARK(k)
@@ -106,424 +106,19 @@ enum
 
 // heuristic of one node computed by a QUAD of lanes (hybrid_a_star.cpp:248-264); h1 is the goal-map value of the cell
 __device__ __noinline__ double node_heuristic_quad(const MapView &m, const PlannerView &p, int h1_cells, double x, double y,
-                                                      double yaw, double gx, double gy, double gyaw)
+                                                   double yaw, double gx, double gy, double gyaw)
 {
     double h1 = (double)h1_cells * m.res; // getGoalCost: cost_ * map_resolution_
     double h2 = ompl_rs_distance_quad(p.min_r, x, y, yaw, gx, gy, gyaw);
     return fmax(h1, h2) * (1 + 1e-3);
 }
 
-__device__ void plan_one_query(const MapView &m, const PlannerView &p, const PlanBatchArgs &a, int q, char *ws, uint32_t tag)
+} // namespace mpros
+
+#include "plan_team.cuh"
+
+namespace mpros
 {
-    const int lane = threadIdx.x & 31;
-    const WarpWorkspaceLayout &L = a.L;
-    PlanNode *nodes = reinterpret_cast<PlanNode *>(ws + L.node_off);
-    OpenHeap heap;
-    heap.key = reinterpret_cast<unsigned long long *>(ws + L.hkey_off);
-    heap.id = reinterpret_cast<uint32_t *>(ws + L.hid_off);
-    heap.size = 0;
-    heap.cap = L.node_cap;
-    ClosedSet closed;
-    closed.key = reinterpret_cast<unsigned long long *>(ws + L.tkey_off);
-    closed.g = reinterpret_cast<double *>(ws + L.tg_off);
-    closed.node = reinterpret_cast<uint32_t *>(ws + L.tnode_off);
-    closed.mask = (uint32_t)L.table_slots - 1;
-    closed.tag = tag;
-    GoalBfs bfs;
-    bfs.blocked = reinterpret_cast<uint32_t *>(ws + L.blocked_off);
-    bfs.f0 = reinterpret_cast<uint32_t *>(ws + L.f0_off);
-    bfs.f1 = reinterpret_cast<uint32_t *>(ws + L.f1_off);
-    bfs.dist = reinterpret_cast<uint16_t *>(ws + L.dist_off);
-    bfs.row_tag = reinterpret_cast<uint32_t *>(ws + L.rowtag_off);
-    double *traj = reinterpret_cast<double *>(ws + L.traj_off); // kTrajCap x 3 xyz, then kTrajCap x 2 steer/dir
-
-    const double sx = a.starts[3 * q], sy = a.starts[3 * q + 1], syaw = a.starts[3 * q + 2];
-    const double gx = a.goals[3 * q], gy = a.goals[3 * q + 1], gyaw = a.goals[3 * q + 2];
-    long long n_iter = 0, n_prim = 0, n_shots = 0, n_coll = 0;
-    int status = ST_NOT_INIT;
-    double goal_g = -1.0;
-    uint32_t goal_parent = kNoNode;
-    int goal_traj_n = 0;
-    int out_len = 0;
-
-    // ---- initialize (hybrid_a_star.cpp:52-118) ----
-    bool init_ok = true;
-    {
-        double s, c;
-        dm::sincos_(syaw, &s, &c);
-        if (warp_footprint_collision(m, p, sx, sy, s, c))
-            init_ok = false; // "Start pose in collision"
-        if (init_ok)
-        {
-            dm::sincos_(gyaw, &s, &c);
-            if (warp_footprint_collision(m, p, gx, gy, s, c))
-                init_ok = false; // "Goal pose in collision"
-        }
-    }
-    int si = -1, sj = -1, gi = -1, gj = -1;
-    if (init_ok)
-    {
-        // node cells on the down-sampled grid; the goal map exists only if the goal lies inside the map (nav_map.cpp:297)
-        bool s_in = pos_to_index_ds(m, sx, sy, si, sj);
-        bool g_in = pos_to_index_ds(m, gx, gy, gi, gj);
-        if (!s_in || !g_in)
-            init_ok = false;
-    }
-    if (init_ok)
-    {
-        bfs_start(m, bfs, gi, gj, tag);
-        // start node: steer 0, direction 1, g = 0 (:83, :211-215)
-        int h1 = bfs_lookup_warp(m, bfs, lane == 0, si, sj);
-        h1 = __shfl_sync(kFull, h1, 0);
-        double h = node_heuristic_quad(m, p, h1, sx, sy, syaw, gx, gy, gyaw);
-        h = __shfl_sync(kFull, h, 0);
-        if (lane == 0)
-        {
-            PlanNode n;
-            n.x = sx, n.y = sy, n.yaw = syaw, n.steer = 0.0, n.g = 0.0, n.parent = kNoNode, n.dir = 1, n.closed = 0, n.pad = 0;
-            nodes[0] = n;
-            // cost_set_/node_set_ seeds (:107-112); the goal entry is written second and wins a shared cell
-            bool found;
-            unsigned long long sidx = cal_index(m, p, si, sj, yaw_to_idx(p, syaw), 1.0);
-            uint32_t s0 = closed_find(closed, sidx, found);
-            closed.key[s0] = (closed.tag << 34) | sidx;
-            closed.g[s0] = 0.0;
-            closed.node[s0] = 0;
-            unsigned long long gidx = cal_index(m, p, gi, gj, yaw_to_idx(p, gyaw), 1.0);
-            uint32_t s1 = closed_find(closed, gidx, found);
-            closed.key[s1] = (closed.tag << 34) | gidx;
-            closed.g[s1] = 10000.0;
-            closed.node[s1] = kGoalNode;
-            heap_push_lane0(heap, (unsigned long long)__double_as_longlong(0.0 + h), 0);
-        }
-        heap.size = 1;
-        __syncwarp();
-    }
-    uint32_t n_nodes = 1;
-
-    // ---- Plan() (hybrid_a_star.cpp:682-777) ----
-    PROF_DECL
-    if (init_ok)
-    {
-        bool goal_found = false, limit_reached = false, overflow = false;
-        int iteration = 0;
-        while (heap.size > 0)
-        {
-            if (iteration > p.max_iteration)
-            {
-                limit_reached = true;
-                break;
-            }
-            unsigned long long fk;
-            PROF_MARK(7);
-            uint32_t cur = heap_pop_warp(heap, fk);
-            const PlanNode cn = nodes[cur];
-            PROF_MARK(0);
-            if (cn.closed)
-                continue;
-            // -- genRSPath (:853-900)
-            bool shot_ok = false;
-            {
-                double ddx = cn.x - gx, ddy = cn.y - gy;
-                double goal_dist_sq = ddx * ddx + ddy * ddy;
-                if (goal_dist_sq < p.rs_range * p.rs_range)
-                {
-                    ++n_shots;
-                    RsPath best;
-                    double rs_cost = rs_find_optimal_warp(a.rs, cn.x, cn.y, cn.yaw, (int)cn.dir, cn.steer, gx, gy, gyaw, best);
-                    int np = 0;
-                    if (lane == 0)
-                        np = rs_gen_traj(a.rs, cn.x, cn.y, cn.yaw, best, traj, traj + 3 * kTrajCap, kTrajCap);
-                    np = __shfl_sync(kFull, np, 0);
-                    __syncwarp();
-                    bool hit = false;
-                    int checked = 0;
-                    if (np > kTrajCap)
-                    {
-                        hit = true; // cannot happen inside the shot range; treat as blocked rather than truncate
-                        checked = kTrajCap;
-                    }
-                    for (int base = 0; base < np && !hit; base += 32)
-                    {
-                        // lanes pre-compute sin/cos of their pose's yaw, then the poses are tested one by one
-                        int k = base + lane;
-                        double s = 0, c = 1, px = 0, py = 0;
-                        if (k < np)
-                        {
-                            px = traj[3 * k], py = traj[3 * k + 1];
-                            dm::sincos_(traj[3 * k + 2], &s, &c);
-                        }
-                        int cnt = min(32, np - base);
-                        for (int t = 0; t < cnt && !hit; ++t)
-                        {
-                            double tx = __shfl_sync(kFull, px, t), ty = __shfl_sync(kFull, py, t);
-                            double ts = __shfl_sync(kFull, s, t), tc = __shfl_sync(kFull, c, t);
-                            ++checked;
-                            hit = warp_footprint_collision(m, p, tx, ty, ts, tc);
-                        }
-                    }
-                    n_coll += checked;
-                    if (!hit)
-                    {
-                        if (goal_parent == kNoNode || goal_g > cn.g + rs_cost)
-                        {
-                            goal_parent = cur;
-                            goal_g = cn.g + rs_cost;
-                            goal_traj_n = np;
-                        }
-                        shot_ok = true;
-                    }
-                }
-            }
-            PROF_MARK(1);
-            if (shot_ok)
-            {
-                goal_found = true;
-                if (!a.optimal)
-                    break;
-            }
-            else
-            {
-                // -- expandNode (:304-402)
-                const int P = 2 * p.n_steer;
-                double s_yaw, c_yaw;
-                dm::sincos_(cn.yaw, &s_yaw, &c_yaw);
-                // every lane < P computes its primitive's end pose
-                double nx = 0, ny = 0, nyaw = 0, steer = 0, direc = 1, ns = 0, nc = 1;
-                if (lane < P)
-                {
-                    primitive_end_pose(p, lane, cn.x, cn.y, cn.yaw, s_yaw, c_yaw, nx, ny, nyaw, steer, direc);
-                    dm::sincos_(nyaw, &ns, &nc);
-                }
-                n_prim += P;
-                n_coll += P;
-                unsigned free_mask = 0;
-                for (int c = 0; c < P; ++c)
-                {
-                    double tx = __shfl_sync(kFull, nx, c), ty = __shfl_sync(kFull, ny, c);
-                    double ts = __shfl_sync(kFull, ns, c), tc = __shfl_sync(kFull, nc, c);
-                    if (!warp_footprint_collision(m, p, tx, ty, ts, tc))
-                        free_mask |= 1u << c;
-                }
-                PROF_MARK(2);
-                // survivors: node cell, g (lane = primitive), goal-map value (on-demand wavefront)
-                bool alive = lane < P && ((free_mask >> lane) & 1u);
-                int ci = -1, cj = -1;
-                if (alive && !pos_to_index_ds(m, nx, ny, ci, cj))
-                    alive = false; // the reference would index outside its arrays here (cannot pass the footprint test)
-                int h1 = bfs_lookup_warp(m, bfs, alive, ci, cj);
-                double g = 0;
-                if (alive)
-                {
-                    double voro = (double)__ldg(m.voronoi + (size_t)ci * m.W + cj);
-                    g = node_cost(p, cn.g, (double)cn.dir, cn.steer, voro, steer, direc);
-                }
-                PROF_MARK(3);
-                // heuristics: quad of lanes per primitive, 8 primitives per round
-                double hval = 0;
-                for (int base = 0; base < P; base += 8)
-                {
-                    int src = base + (lane >> 2);
-                    double qx = __shfl_sync(kFull, nx, src), qy = __shfl_sync(kFull, ny, src), qyaw = __shfl_sync(kFull, nyaw, src);
-                    int qh1 = __shfl_sync(kFull, h1, src);
-                    bool qalive = (__shfl_sync(kFull, (int)alive, src) != 0) && src < P;
-                    double hq = 0;
-                    if (__any_sync(kFull, qalive))
-                        hq = node_heuristic_quad(m, p, qh1, qalive ? qx : gx, qalive ? qy : gy, qalive ? qyaw : gyaw, gx, gy, gyaw);
-                    // hand the value back to the primitive's own lane
-                    int owner_quad = (lane - base);
-                    double back = __shfl_sync(kFull, hq, (owner_quad >= 0 && owner_quad < 8) ? owner_quad * 4 : 0);
-                    if (owner_quad >= 0 && owner_quad < 8)
-                        hval = back;
-                }
-                PROF_MARK(4);
-                // closed-set compare / open-list insert, strictly in primitive order (lane 0 walks the survivors)
-                unsigned alive_mask = __ballot_sync(kFull, alive);
-                for (int c = 0; c < P; ++c)
-                {
-                    if (!((alive_mask >> c) & 1u))
-                        continue;
-                    double tx = __shfl_sync(kFull, nx, c), ty = __shfl_sync(kFull, ny, c), tyaw = __shfl_sync(kFull, nyaw, c);
-                    double tsteer = __shfl_sync(kFull, steer, c), tdir = __shfl_sync(kFull, direc, c);
-                    double tg = __shfl_sync(kFull, g, c), th = __shfl_sync(kFull, hval, c);
-                    int ti = __shfl_sync(kFull, ci, c), tj = __shfl_sync(kFull, cj, c);
-                    int inserted = 0;
-                    if (lane == 0)
-                    {
-                        unsigned long long idx = cal_index(m, p, ti, tj, yaw_to_idx(p, tyaw), tdir);
-                        bool found;
-                        uint32_t slot = closed_find(closed, idx, found);
-                        double old_cost = found ? closed.g[slot] : __longlong_as_double(0x7ff0000000000000ll);
-                        if (old_cost > tg)
-                        {
-                            if (n_nodes >= (uint32_t)L.node_cap)
-                                inserted = -1;
-                            else
-                            {
-                                if (found)
-                                {
-                                    uint32_t old = closed.node[slot];
-                                    if (old < kGoalNode)
-                                        nodes[old].closed = 1;
-                                }
-                                closed.key[slot] = (closed.tag << 34) | idx;
-                                closed.g[slot] = tg;
-                                closed.node[slot] = n_nodes;
-                                PlanNode nn;
-                                nn.x = tx, nn.y = ty, nn.yaw = tyaw, nn.steer = tsteer, nn.g = tg, nn.parent = cur;
-                                nn.dir = (int8_t)(tdir > 0 ? 1 : -1), nn.closed = 0, nn.pad = 0;
-                                nodes[n_nodes] = nn;
-                                heap_push_lane0(heap, (unsigned long long)__double_as_longlong(tg + th), n_nodes);
-                                inserted = 1;
-                            }
-                        }
-                    }
-                    inserted = __shfl_sync(kFull, inserted, 0);
-                    if (inserted < 0)
-                    {
-                        overflow = true;
-                        break;
-                    }
-                    if (inserted)
-                    {
-                        heap.size++;
-                        n_nodes++;
-                    }
-                    __syncwarp();
-                }
-                PROF_MARK(5);
-                if (overflow)
-                    break;
-            }
-            if (a.optimal)
-            {
-                if (dm::hypot_(gx - cn.x, gy - cn.y) <= 1.0) // stop_radius (hybrid_a_star.h:345)
-                    break;
-            }
-            ++iteration;
-        }
-        n_iter = iteration;
-        PROF_FLUSH;
-        if (overflow)
-            status = ST_OVERFLOW;
-        else if (goal_found)
-            status = ST_FOUND;
-        else if (limit_reached)
-            status = ST_LIMIT;
-        else
-            status = ST_OPEN_EMPTY;
-    }
-
-    // ---- raw path_ of setPath (hybrid_a_star.cpp:779-811): start, expanded nodes, then the RS goal path ----
-    if (status == ST_FOUND)
-    {
-        // non-optimal mode stops at the first successful shot, so `traj` still holds goal_path_. In optimal mode the
-        // best shot may be older; re-generate it (deterministic) from the stored parent.
-        const PlanNode gp = nodes[goal_parent];
-        if (a.optimal)
-        {
-            RsPath best;
-            rs_find_optimal_warp(a.rs, gp.x, gp.y, gp.yaw, (int)gp.dir, gp.steer, gx, gy, gyaw, best);
-            if (lane == 0)
-                goal_traj_n = rs_gen_traj(a.rs, gp.x, gp.y, gp.yaw, best, traj, traj + 3 * kTrajCap, kTrajCap);
-            goal_traj_n = __shfl_sync(kFull, goal_traj_n, 0);
-            __syncwarp();
-        }
-        // chain length (nodes with a parent, walking up from goal's parent)
-        int chain = 0;
-        if (lane == 0)
-        {
-            uint32_t c = goal_parent;
-            while (nodes[c].parent != kNoNode)
-            {
-                ++chain;
-                c = nodes[c].parent;
-            }
-        }
-        chain = __shfl_sync(kFull, chain, 0);
-        out_len = 1 + chain + goal_traj_n;
-        if (a.paths && a.path_cap > 0)
-        {
-            double *dst = a.paths + (size_t)q * a.path_cap * 5;
-            if (lane == 0)
-            {
-                // start point: steer 0, direction of the first path point (:792-807)
-                double start_dir;
-                uint32_t c = goal_parent;
-                int pos = chain; // index of goal_parent's point in the output
-                double last_dir = 1.0;
-                while (nodes[c].parent != kNoNode)
-                {
-                    const PlanNode n = nodes[c];
-                    if (pos < a.path_cap)
-                    {
-                        double *o = dst + 5 * pos;
-                        o[0] = n.x, o[1] = n.y, o[2] = n.yaw, o[3] = n.steer, o[4] = (double)n.dir;
-                    }
-                    last_dir = (double)n.dir; // ends as the direction of the node next to the start
-                    --pos;
-                    c = n.parent;
-                }
-                if (chain > 1)
-                    start_dir = last_dir; // path_.back().back() before the start is pushed
-                else
-                    start_dir = goal_traj_n > 0 ? traj[3 * kTrajCap + 1] : 1.0; // goal_path_.front().back()
-                double *o = dst;
-                o[0] = sx, o[1] = sy, o[2] = syaw, o[3] = 0.0, o[4] = start_dir;
-            }
-            for (int k = lane; k < goal_traj_n; k += 32)
-            {
-                int pos = 1 + chain + k;
-                if (pos < a.path_cap)
-                {
-                    double *o = dst + 5 * pos;
-                    o[0] = traj[3 * k], o[1] = traj[3 * k + 1], o[2] = traj[3 * k + 2];
-                    o[3] = traj[3 * kTrajCap + 2 * k], o[4] = traj[3 * kTrajCap + 2 * k + 1];
-                }
-            }
-        }
-    }
-    if (lane == 0)
-    {
-        a.status[q] = status;
-        a.cost[q] = (status == ST_FOUND) ? goal_g : -1.0;
-        a.path_len[q] = out_len;
-        if (a.stats)
-        {
-            a.stats[6 * q + 0] = n_iter;
-            a.stats[6 * q + 1] = n_prim;
-            a.stats[6 * q + 2] = n_shots;
-            a.stats[6 * q + 3] = n_coll;
-            a.stats[6 * q + 4] = init_ok ? bfs.cells : 0;
-            a.stats[6 * q + 5] = n_nodes;
-        }
-    }
-    __syncwarp();
-}
-
-#ifndef MPROS_PLAN_MIN_BLOCKS
-#define MPROS_PLAN_MIN_BLOCKS 2
-#endif
-__global__ void __launch_bounds__(128, MPROS_PLAN_MIN_BLOCKS) plan_batch_kernel(MapView m, PlannerView p, PlanBatchArgs a)
-{
-    const int lane = threadIdx.x & 31;
-    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    char *ws = a.ws + (size_t)warp_global * a.L.stride;
-    uint32_t local_gen = 0;
-    const int total = a.todo ? a.n_todo : a.nq;
-    while (true)
-    {
-        unsigned int t = 0;
-        if (lane == 0)
-            t = atomicAdd(a.counter, 1u);
-        t = __shfl_sync(kFull, t, 0);
-        if (t >= (unsigned)total)
-            break;
-        int q = a.todo ? a.todo[t] : (int)t;
-        ++local_gen;
-        plan_one_query(m, p, a, q, ws, a.tag_base + local_gen);
-    }
-}
 
 // ---- standalone batches (R1-R4, E1-E5) ---------------------------------------------------------------------------------
 struct RsBatchArgs
@@ -999,6 +594,15 @@ extern "C" int mpros_expand_batch(mpros_ctx *c, const double *start3, const doub
 // ---- whole-query planner -------------------------------------------------------------------------------------------------
 namespace mpros
 {
+#ifndef MPROS_TEAM_WARPS
+#define MPROS_TEAM_WARPS 8
+#endif
+#ifndef MPROS_TEAM_MIN_BLOCKS
+#define MPROS_TEAM_MIN_BLOCKS 1
+#endif
+constexpr int kTeamWarps = MPROS_TEAM_WARPS;
+constexpr int kTeamMinBlocks = MPROS_TEAM_MIN_BLOCKS;
+
 struct PlanScratch
 {
     char *ws = nullptr;
@@ -1020,15 +624,15 @@ static int plan_pass(mpros_ctx *c, PlanBatchArgs &a, int pass, int node_cap, int
     size_t free_b = 0, total_b = 0;
     MPROS_CUDA(cudaMemGetInfo(&free_b, &total_b));
     size_t budget = (free_b + S.ws_bytes) / 2;
-    int per_block = 4;
     int resident = 0;
-    MPROS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, plan_batch_kernel, per_block * 32, 0));
+    MPROS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, plan_team_kernel<kTeamWarps, kTeamMinBlocks>, kTeamWarps * 32, 0));
+    // one team (CTA) per query; every resident team owns one workspace
     int blocks = prop.multiProcessorCount * std::max(1, resident);
-    blocks = std::min(blocks, (n_run + per_block - 1) / per_block);
-    blocks = std::min<long long>(blocks, std::max<long long>(1, (long long)(budget / L.stride) / per_block));
+    blocks = std::min(blocks, n_run);
+    blocks = (int)std::min<long long>(blocks, std::max<long long>(1, (long long)(budget / L.stride)));
     if (max_warps > 0)
-        blocks = std::min(blocks, std::max(1, max_warps / per_block));
-    size_t need = (size_t)blocks * per_block * L.stride;
+        blocks = std::min(blocks, std::max(1, max_warps));
+    size_t need = (size_t)blocks * L.stride;
     if (need > S.ws_bytes)
     {
         if (S.ws)
@@ -1072,7 +676,7 @@ static int plan_pass(mpros_ctx *c, PlanBatchArgs &a, int pass, int node_cap, int
         cudaEventCreate(&e1);
         cudaEventRecord(e0, c->stream);
     }
-    plan_batch_kernel<<<blocks, per_block * 32, 0, c->stream>>>(c->view(), c->pv, a);
+    plan_team_kernel<kTeamWarps, kTeamMinBlocks><<<blocks, kTeamWarps * 32, 0, c->stream>>>(c->view(), c->pv, a);
     MPROS_LAUNCH_CHECK(c);
     if (dbg)
     {
@@ -1089,12 +693,12 @@ static int plan_pass(mpros_ctx *c, PlanBatchArgs &a, int pass, int node_cap, int
             double tot = 0;
             for (int k = 0; k < 8; ++k)
                 tot += (double)h[k];
-            std::fprintf(stderr, "[mpros] cycles%%: pop %.1f shot %.1f collision %.1f cell+bfs+g %.1f h2 %.1f insert %.1f loop %.1f (total %.3g warp-cycles)\n",
-                         100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot, 100 * h[4] / tot, 100 * h[5] / tot, 100 * h[7] / tot, tot);
+            std::fprintf(stderr, "[mpros] cycles%%: pop %.1f shot %.1f children+collision %.1f survivors %.1f h1 %.1f h2 %.1f insert %.1f loop %.1f (total %.3g team-cycles)\n",
+                         100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot, 100 * h[6] / tot, 100 * h[4] / tot, 100 * h[5] / tot, 100 * h[7] / tot, tot);
         }
 #endif
-        std::fprintf(stderr, "[mpros] plan pass %d: %d queries, node_cap %d, %d warps, %.1f MB/warp, %.3f ms\n", pass, n_run, node_cap,
-                     blocks * per_block, L.stride / 1048576.0, ms);
+        std::fprintf(stderr, "[mpros] plan pass %d: %d queries, node_cap %d, %d teams x %d warps, %.1f MB/team, %.3f ms\n", pass, n_run,
+                     node_cap, blocks, kTeamWarps, L.stride / 1048576.0, ms);
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
     }

@@ -1,0 +1,872 @@
+// Whole-query planner, one CTA ("team" of NW warps) per query.
+//
+// Why a team and not a warp per query: A* is a dependent chain (pop -> expand -> insert), so the per-iteration LATENCY
+// sets both the tail of a batch (queries that run into the 100 000-iteration limit) and, with a fixed number of
+// resident queries, the throughput. The first version (one warp per query) was instruction-fetch bound: eight
+// independent warps per SM each walking ~170 KB of code (ncu: stall_no_instruction 4.2 per issue, issue active 16 %).
+// Here all warps of a CTA walk the SAME iteration in lock step (shared-memory hand-off, __syncthreads between phases):
+// the footprint tests of the primitives, the 11 base formulas of the OMPL distance, the 48 Reeds-Shepp candidates and
+// the wavefront rows are spread over the warps, the instruction stream is shared, and the sequential parts (heap,
+// closed set) run on warp 0.
+//
+// Reference semantics are unchanged: one popped node per step in std::multimap order, children in steer x direction
+// order, strict '>' prune, first successful shot ends the search (hybrid_a_star.cpp:682-777).
+#pragma once
+#include "planner_device.cuh"
+
+namespace mpros
+{
+
+struct TeamBfs
+{
+    uint32_t *blocked, *f0, *f1;
+    uint16_t *dist;
+    uint32_t *row_tag;
+    uint32_t tag;
+    int r0, w0, rows, wwords;
+    int gi, gj;
+    int level, done;
+    int br0, br1, bw0, bw1;
+    int ilo, ihi;                  // rows [ilo, ihi] (map coordinates) hold this query's bitmaps; others are stale
+    int nr0, nr1, nw0, nw1, found; // per-level reduction targets
+    long long cells;
+};
+
+template <int NW>
+struct TeamShared
+{
+    // query
+    double sx, sy, syaw, gx, gy, gyaw;
+    int si, sj, gi, gj;
+    int q, status, init_hit[2];
+    // search state
+    int heap_size, iteration, flag, need_shot, shot_ok, overflow, goal_found;
+    uint32_t n_nodes, cur_id, goal_parent;
+    double goal_g;
+    int goal_traj_n;
+    long long n_prim, n_shots, n_coll;
+    PlanNode cur;
+    double cur_s, cur_c;
+    // children of the current expansion (slot = primitive index)
+    int nslots;
+    double c_x[kMaxPrim], c_y[kMaxPrim], c_yaw[kMaxPrim], c_steer[kMaxPrim], c_dir[kMaxPrim], c_g[kMaxPrim], c_h[kMaxPrim];
+    int c_i[kMaxPrim], c_j[kMaxPrim], c_h1[kMaxPrim];
+    unsigned long long c_idx[kMaxPrim];
+    unsigned char c_alive[kMaxPrim], c_need[kMaxPrim];
+    int h_list[kMaxPrim], h_n, bfs_more;
+    unsigned long long hmin[kMaxPrim][3];
+    // Reeds-Shepp shot
+    double cand_cost[NW];
+    int cand_idx[NW];
+    RsPath cand_path[NW];
+    RsPath best;
+    double best_cost;
+    int traj_n, first_hit;
+    unsigned char traj_hit[kTrajCap];
+    double traj[kTrajCap * 5]; // kTrajCap x 3 {x, y, yaw}, then kTrajCap x 2 {steer, dir}
+    TeamBfs bfs;
+};
+
+// assignment of the 11 OMPL base formulas (rs_device.cuh: ompl_formula) to the warps of a team, heaviest first
+template <int NW>
+__device__ __forceinline__ int team_formula(int warp, int slot);
+template <>
+__device__ __forceinline__ int team_formula<8>(int warp, int slot)
+{
+    const signed char tab[8][2] = {{4, -1}, {5, -1}, {1, 10}, {6, 0}, {7, 8}, {2, 9}, {3, -1}, {-1, -1}};
+    return tab[warp][slot];
+}
+template <>
+__device__ __forceinline__ int team_formula<4>(int warp, int slot)
+{
+    const signed char tab[4][3] = {{4, 0, 8}, {5, 10, 9}, {1, 6, 2}, {7, 3, -1}};
+    return slot < 3 ? tab[warp][slot] : -1;
+}
+template <int NW>
+__device__ __forceinline__ int team_formula_slots() { return NW == 8 ? 2 : 3; }
+
+// ---- on-demand goal wavefront, team version (same semantics as planner_device.cuh: GoalBfs) -------------------------
+template <int NW>
+__device__ __forceinline__ void team_bfs_init_rows(const MapView &m, TeamBfs &b, int ra, int rb)
+{
+    // every thread sees the same b (shared). The initialised rows form one contiguous range [ilo, ihi] that only
+    // grows; rows outside it still hold a previous query's bits and are never read.
+    const int tid = threadIdx.x, NT = NW * 32;
+    ra = max(ra, b.r0);
+    rb = min(rb, b.r0 + b.rows - 1);
+    const int ilo = b.ilo, ihi = b.ihi;
+    if (ra >= ilo && rb <= ihi)
+        return;
+    const int wwords = b.wwords;
+    // new rows: [ra, ilo - 1] and [ihi + 1, rb] (the first call has ilo > ihi: everything is new)
+    const int lo_n = (ilo > ihi) ? (rb - ra + 1) : max(0, ilo - ra), hi_n = (ilo > ihi) ? 0 : max(0, rb - ihi);
+    for (int k = tid; k < (lo_n + hi_n) * wwords; k += NT)
+    {
+        int rr = k / wwords, w = k % wwords;
+        int r = rr < lo_n ? ra + rr : ihi + 1 + (rr - lo_n);
+        size_t o = (size_t)(r - b.r0) * wwords + w;
+        b.blocked[o] = __ldg(m.ds_bits + (size_t)r * m.pitch + b.w0 + w);
+        b.f0[o] = 0;
+        b.f1[o] = 0;
+    }
+    __syncthreads();
+    if (tid == 0)
+    {
+        b.ilo = (ilo > ihi) ? ra : min(ilo, ra);
+        b.ihi = (ilo > ihi) ? rb : max(ihi, rb);
+    }
+    __syncthreads();
+}
+
+template <int NW>
+__device__ __forceinline__ void team_bfs_start(const MapView &m, TeamBfs &b, int gi, int gj, uint32_t tag)
+{
+    const int tid = threadIdx.x;
+    if (tid == 0)
+    {
+        const int wpr = (m.W + 31) >> 5;
+        b.tag = tag;
+        b.gi = gi;
+        b.gj = gj;
+        b.r0 = max(0, gi - (kHugeInt - 1));
+        int r1 = min(m.H - 1, gi + (kHugeInt - 1));
+        b.w0 = max(0, gj - (kHugeInt - 1)) >> 5;
+        int w1 = min(wpr - 1, (gj + (kHugeInt - 1)) >> 5);
+        b.rows = r1 - b.r0 + 1;
+        b.wwords = w1 - b.w0 + 1;
+        b.level = 0;
+        b.done = 0;
+        b.cells = 1;
+        b.br0 = b.br1 = gi;
+        b.bw0 = b.bw1 = gj >> 5;
+        b.ilo = 1, b.ihi = 0; // nothing initialised yet
+    }
+    __syncthreads();
+    team_bfs_init_rows<NW>(m, b, gi - 2, gi + 2);
+    if (tid == 0)
+    {
+        size_t o = (size_t)(gi - b.r0) * b.wwords + ((gj >> 5) - b.w0);
+        b.f0[o] = 1u << (gj & 31);
+        b.blocked[o] |= 1u << (gj & 31);
+    }
+    __syncthreads();
+}
+
+template <int NW>
+__device__ __forceinline__ void team_bfs_step(const MapView &m, TeamBfs &b)
+{
+    const int tid = threadIdx.x, NT = NW * 32;
+    const int level = b.level + 1;
+    if (level >= kHugeInt)
+    {
+        __syncthreads();
+        if (tid == 0)
+            b.done = 1;
+        __syncthreads();
+        return;
+    }
+    const int wr1 = b.r0 + b.rows - 1, ww1 = b.w0 + b.wwords - 1;
+    const int sr0 = max(b.r0, b.br0 - 1), sr1 = min(wr1, b.br1 + 1);
+    const int sw0 = max(b.w0, b.bw0 - 1), sw1 = min(ww1, b.bw1 + 1);
+    team_bfs_init_rows<NW>(m, b, sr0 - 2, sr1 + 2);
+    if (tid == 0)
+    {
+        b.nr0 = 1 << 30, b.nr1 = -1, b.nw0 = 1 << 30, b.nw1 = -1, b.found = 0;
+    }
+    __syncthreads();
+    const int nw = sw1 - sw0 + 1;
+    const int total = (sr1 - sr0 + 1) * nw;
+    uint32_t *fprev = (level & 1) ? b.f0 : b.f1;
+    uint32_t *fnext = (level & 1) ? b.f1 : b.f0;
+    const int wpr = (m.W + 31) >> 5;
+    int nr0 = 1 << 30, nr1 = -1, nw0 = 1 << 30, nw1 = -1, found = 0;
+    const int rows = b.rows, wwords = b.wwords, r0 = b.r0, w0 = b.w0;
+    for (int k = tid; k < total; k += NT)
+    {
+        int r = sr0 + k / nw, w = sw0 + k % nw;
+        int lr = r - r0, lw = w - w0;
+        size_t o = (size_t)lr * wwords + lw;
+        uint32_t c = fprev[o];
+        uint32_t nb = (c << 1) | (c >> 1);
+        if (lw > 0)
+            nb |= fprev[o - 1] >> 31;
+        if (lw + 1 < wwords)
+            nb |= fprev[o + 1] << 31;
+        if (lr > 0)
+            nb |= fprev[o - wwords];
+        if (lr + 1 < rows)
+            nb |= fprev[o + wwords];
+        uint32_t valid = (w == wpr - 1 && (m.W & 31)) ? ((1u << (m.W & 31)) - 1u) : 0xffffffffu;
+        uint32_t bl = b.blocked[o];
+        uint32_t nbits = nb & ~bl & valid;
+        fnext[o] = nbits;
+        if (nbits)
+        {
+            b.blocked[o] = bl | nbits;
+            found += __popc(nbits);
+            nr0 = min(nr0, r), nr1 = max(nr1, r), nw0 = min(nw0, w), nw1 = max(nw1, w);
+            uint16_t *drow = b.dist + o * 32;
+            while (nbits)
+            {
+                int t = __ffs(nbits) - 1;
+                nbits &= nbits - 1;
+                drow[t] = (uint16_t)level;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        nr0 = min(nr0, __shfl_xor_sync(kFull, nr0, o));
+        nr1 = max(nr1, __shfl_xor_sync(kFull, nr1, o));
+        nw0 = min(nw0, __shfl_xor_sync(kFull, nw0, o));
+        nw1 = max(nw1, __shfl_xor_sync(kFull, nw1, o));
+        found += __shfl_xor_sync(kFull, found, o);
+    }
+    if ((tid & 31) == 0 && found)
+    {
+        atomicMin(&b.nr0, nr0);
+        atomicMax(&b.nr1, nr1);
+        atomicMin(&b.nw0, nw0);
+        atomicMax(&b.nw1, nw1);
+        atomicAdd(&b.found, found);
+    }
+    __syncthreads();
+    if (tid == 0)
+    {
+        b.level = level;
+        b.cells += b.found;
+        if (b.found == 0)
+            b.done = 1;
+        else
+        {
+            b.br0 = min(b.br0, b.nr0), b.br1 = max(b.br1, b.nr1), b.bw0 = min(b.bw0, b.nw0), b.bw1 = max(b.bw1, b.nw1);
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ int team_bfs_peek(const MapView &m, const TeamBfs &b, int i, int j)
+{
+    if (i == b.gi && j == b.gj)
+        return 0;
+    if (bit_at(m.ds_bits, m.pitch, i, j))
+        return kHugeInt;
+    int lr = i - b.r0, lw = (j >> 5) - b.w0;
+    if (lr < 0 || lr >= b.rows || lw < 0 || lw >= b.wwords)
+        return kHugeInt;
+    if (i >= b.ilo && i <= b.ihi)
+    {
+        size_t o = (size_t)lr * b.wwords + lw;
+        if ((b.blocked[o] >> (j & 31)) & 1u)
+            return b.dist[o * 32 + (j & 31)];
+    }
+    return b.done ? kHugeInt : -1;
+}
+
+// goal-map values for the slots flagged c_need (team-collective): advance the wavefront until all are final
+template <int NW>
+__device__ __forceinline__ void team_h1_lookup(const MapView &m, TeamShared<NW> &S)
+{
+    const int tid = threadIdx.x;
+    if (tid < S.nslots)
+        S.c_h1[tid] = -1;
+    __syncthreads();
+    while (true)
+    {
+        if (tid == 0)
+            S.bfs_more = 0;
+        __syncthreads();
+        if (tid < S.nslots && S.c_need[tid] && S.c_h1[tid] < 0)
+        {
+            int v = team_bfs_peek(m, S.bfs, S.c_i[tid], S.c_j[tid]);
+            S.c_h1[tid] = v;
+            if (v < 0)
+                S.bfs_more = 1;
+        }
+        __syncthreads();
+        if (!S.bfs_more)
+            break;
+        team_bfs_step<NW>(m, S.bfs);
+    }
+}
+
+// heuristics (hybrid_a_star.cpp:248-264) of the slots flagged c_need: h = max(h1 * res, RS distance) * 1.001
+template <int NW>
+__device__ __forceinline__ void team_heuristics(const MapView &m, const PlannerView &p, TeamShared<NW> &S)
+{
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0)
+    {
+        int n = 0;
+        for (int c = 0; c < S.nslots; ++c)
+            if (S.c_need[c])
+                S.h_list[n++] = c;
+        S.h_n = n;
+    }
+    if (tid < kMaxPrim * 3)
+        S.hmin[tid / 3][tid % 3] = (unsigned long long)__double_as_longlong(DBL_MAX);
+    __syncthreads();
+    const int hn = S.h_n;
+    for (int base = 0; base < hn; base += 8)
+    {
+        int e = base + (lane >> 2), q = lane & 3;
+        bool live = e < hn;
+        int c = live ? S.h_list[e] : 0;
+        double x, y, phi, xb, yb, sphi = 0, cphi = 1;
+        bool any_live = base < hn; // warp-uniform: at least lane 0's quad is live
+        if (any_live)
+        {
+            ompl_image(q, p.min_r, live ? S.c_x[c] : S.gx, live ? S.c_y[c] : S.gy, live ? S.c_yaw[c] : S.gyaw, S.gx, S.gy, S.gyaw, x, y,
+                       phi, xb, yb);
+            dm::sincos_(phi, &sphi, &cphi);
+#pragma unroll 1
+            for (int s = 0; s < team_formula_slots<NW>(); ++s)
+            {
+                int k = team_formula<NW>(warp, s);
+                if (k < 0)
+                    continue;
+                double L = ompl_formula(k, x, y, phi, xb, yb, sphi, cphi);
+                L = fmin(L, __shfl_xor_sync(kFull, L, 1));
+                L = fmin(L, __shfl_xor_sync(kFull, L, 2));
+                if (live && q == 0 && L < DBL_MAX)
+                    atomicMin(&S.hmin[c][ompl_formula_family(k)], (unsigned long long)__double_as_longlong(L));
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < hn)
+    {
+        int c = S.h_list[tid];
+        double h1 = (double)S.c_h1[c] * m.res; // getGoalCost: cost_ * map_resolution_
+        double h2 = ompl_combine(p.min_r, __longlong_as_double((long long)S.hmin[c][0]), __longlong_as_double((long long)S.hmin[c][1]),
+                                 __longlong_as_double((long long)S.hmin[c][2]));
+        S.c_h[c] = fmax(h1, h2) * (1 + 1e-3);
+    }
+    __syncthreads();
+}
+
+// Reeds-Shepp shot from (x, y, yaw, dir, steer) to the goal: FindOptimalPath + GenTraj into S.traj (team-collective).
+template <int NW>
+__device__ __forceinline__ void team_rs_solve(const RsConfig &rs, TeamShared<NW> &S, double x, double y, double yaw, int dir, double steer)
+{
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // NewGoalPoint (rs_curve.cpp:51-58)
+    double dx = S.gx - x, dy = S.gy - y;
+    double cs, sn;
+    dm::sincos_(yaw, &sn, &cs);
+    double gx = (dx * cs + dy * sn) / rs.radius;
+    double gy = (-dx * sn + dy * cs) / rs.radius;
+    double gphi = S.gyaw - yaw;
+    // candidate c = 4 f + j; warp w owns formulas w, w + NW, ...; lanes 4 g + j
+    const int groups = (12 + NW - 1) / NW;
+    double my_cost = 0;
+    int my_c = 1 << 20;
+    RsPath my;
+    my.n = 0;
+    {
+        int g = lane >> 2, j = lane & 3;
+        int f = warp + NW * g;
+        if (g < groups && f < 12)
+        {
+            double cx = (j == 1 || j == 3) ? -gx : gx;
+            double cy = (j == 2 || j == 3) ? -gy : gy;
+            double ph = (j == 1 || j == 2) ? -gphi : gphi;
+            rs_formula(f, cx, cy, ph, my);
+            if (j == 1 || j == 3)
+                rs_timeflip(my);
+            if (j == 2 || j == 3)
+                rs_reflect(my);
+            double len = rs_path_length(rs, my, dir, steer);
+            bool nan_seg = false;
+#pragma unroll
+            for (int k = 0; k < 5; ++k)
+                if (k < my.n && isnan(my.s[k].len))
+                    nan_seg = true;
+            if ((len != 0.0) && !nan_seg)
+            {
+                my_cost = len;
+                my_c = 4 * f + j;
+            }
+        }
+    }
+    double bc = my_cost;
+    int bi = my_c;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        double oc = __shfl_xor_sync(kFull, bc, o);
+        int oi = __shfl_xor_sync(kFull, bi, o);
+        bool take = (oi < (1 << 20)) && (bi >= (1 << 20) || oc < bc || (oc == bc && oi < bi));
+        if (take)
+        {
+            bc = oc;
+            bi = oi;
+        }
+    }
+    if (my_c == bi && bi < (1 << 20))
+    {
+        S.cand_cost[warp] = bc;
+        S.cand_idx[warp] = bi;
+        S.cand_path[warp] = my;
+    }
+    else if (lane == 0 && bi >= (1 << 20))
+        S.cand_idx[warp] = 1 << 20;
+    __syncthreads();
+    if (tid == 0)
+    {
+        int bw = -1;
+        for (int w = 0; w < NW; ++w)
+        {
+            if (S.cand_idx[w] >= (1 << 20))
+                continue;
+            if (bw < 0 || S.cand_cost[w] < S.cand_cost[bw] || (S.cand_cost[w] == S.cand_cost[bw] && S.cand_idx[w] < S.cand_idx[bw]))
+                bw = w;
+        }
+        S.best = S.cand_path[bw < 0 ? 0 : bw];
+        if (bw < 0)
+            S.best.n = 0;
+        S.best_cost = bw < 0 ? 0.0 : S.cand_cost[bw];
+        // GenTraj (rs_curve.cpp:165-222): sequential pose integration
+        S.traj_n = rs_gen_traj(rs, x, y, yaw, S.best, S.traj, S.traj + 3 * kTrajCap, kTrajCap);
+    }
+    __syncthreads();
+}
+
+template <int NW>
+__device__ void plan_team_query(const MapView &m, const PlannerView &p, const PlanBatchArgs &a, int q, char *ws, uint32_t tag,
+                                TeamShared<NW> &S)
+{
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const WarpWorkspaceLayout &L = a.L;
+    PlanNode *nodes = reinterpret_cast<PlanNode *>(ws + L.node_off);
+    OpenHeap heap;
+    heap.key = reinterpret_cast<unsigned long long *>(ws + L.hkey_off);
+    heap.id = reinterpret_cast<uint32_t *>(ws + L.hid_off);
+    heap.size = 0;
+    heap.cap = L.node_cap;
+    ClosedSet closed;
+    closed.key = reinterpret_cast<unsigned long long *>(ws + L.tkey_off);
+    closed.g = reinterpret_cast<double *>(ws + L.tg_off);
+    closed.node = reinterpret_cast<uint32_t *>(ws + L.tnode_off);
+    closed.mask = (uint32_t)L.table_slots - 1;
+    closed.tag = tag;
+
+    if (tid == 0)
+    {
+        S.sx = a.starts[3 * q], S.sy = a.starts[3 * q + 1], S.syaw = a.starts[3 * q + 2];
+        S.gx = a.goals[3 * q], S.gy = a.goals[3 * q + 1], S.gyaw = a.goals[3 * q + 2];
+        S.status = ST_NOT_INIT;
+        S.init_hit[0] = S.init_hit[1] = 0;
+        S.heap_size = 0, S.iteration = 0, S.overflow = 0, S.goal_found = 0;
+        S.n_nodes = 0, S.goal_parent = kNoNode, S.goal_g = -1.0, S.goal_traj_n = 0;
+        S.n_prim = S.n_shots = S.n_coll = 0;
+        S.bfs.blocked = reinterpret_cast<uint32_t *>(ws + L.blocked_off);
+        S.bfs.f0 = reinterpret_cast<uint32_t *>(ws + L.f0_off);
+        S.bfs.f1 = reinterpret_cast<uint32_t *>(ws + L.f1_off);
+        S.bfs.dist = reinterpret_cast<uint16_t *>(ws + L.dist_off);
+        S.bfs.row_tag = reinterpret_cast<uint32_t *>(ws + L.rowtag_off);
+        S.bfs.cells = 0;
+    }
+    __syncthreads();
+
+    // ---- initialize (hybrid_a_star.cpp:52-118): start / goal footprint tests on two warps ----
+    if (warp < 2)
+    {
+        double px = warp ? S.gx : S.sx, py = warp ? S.gy : S.sy, pyaw = warp ? S.gyaw : S.syaw;
+        double s, c;
+        dm::sincos_(pyaw, &s, &c);
+        bool hit = warp_footprint_collision(m, p, px, py, s, c);
+        if (lane == 0)
+            S.init_hit[warp] = hit;
+    }
+    __syncthreads();
+    bool init_ok = !S.init_hit[0] && !S.init_hit[1];
+    if (init_ok)
+    {
+        if (tid == 0)
+        {
+            bool s_in = pos_to_index_ds(m, S.sx, S.sy, S.si, S.sj);
+            bool g_in = pos_to_index_ds(m, S.gx, S.gy, S.gi, S.gj);
+            S.flag = (s_in && g_in) ? 1 : 0;
+        }
+        __syncthreads();
+        init_ok = S.flag != 0;
+    }
+    if (init_ok)
+    {
+        team_bfs_start<NW>(m, S.bfs, S.gi, S.gj, tag);
+        // start node: steer 0, direction 1, g = 0 (:83, :211-215); its heuristic through the generic slot machinery
+        if (tid == 0)
+        {
+            S.nslots = 1;
+            S.c_x[0] = S.sx, S.c_y[0] = S.sy, S.c_yaw[0] = S.syaw;
+            S.c_i[0] = S.si, S.c_j[0] = S.sj;
+            S.c_need[0] = 1;
+        }
+        __syncthreads();
+        team_h1_lookup<NW>(m, S);
+        team_heuristics<NW>(m, p, S);
+        if (tid == 0)
+        {
+            PlanNode n;
+            n.x = S.sx, n.y = S.sy, n.yaw = S.syaw, n.steer = 0.0, n.g = 0.0, n.parent = kNoNode, n.dir = 1, n.closed = 0, n.pad = 0;
+            nodes[0] = n;
+            bool found;
+            unsigned long long sidx = cal_index(m, p, S.si, S.sj, yaw_to_idx(p, S.syaw), 1.0);
+            uint32_t s0 = closed_find(closed, sidx, found);
+            closed.key[s0] = (closed.tag << 34) | sidx;
+            closed.g[s0] = 0.0;
+            closed.node[s0] = 0;
+            unsigned long long gidx = cal_index(m, p, S.gi, S.gj, yaw_to_idx(p, S.gyaw), 1.0);
+            uint32_t s1 = closed_find(closed, gidx, found);
+            closed.key[s1] = (closed.tag << 34) | gidx;
+            closed.g[s1] = 10000.0;
+            closed.node[s1] = kGoalNode;
+            heap_push_lane0(heap, (unsigned long long)__double_as_longlong(0.0 + S.c_h[0]), 0);
+            S.heap_size = 1;
+            S.n_nodes = 1;
+        }
+        __syncthreads();
+    }
+
+    // ---- Plan() (hybrid_a_star.cpp:682-777) ----
+    const int P = 2 * p.n_steer;
+    PROF_DECL
+    while (init_ok)
+    {
+        PROF_MARK(7);
+        // -- pop (warp 0): flag 0 continue, 1 iteration limit, 2 open set empty
+        if (warp == 0)
+        {
+            int flag = 0;
+            uint32_t cur = 0;
+            PlanNode cn;
+            if (S.iteration > p.max_iteration)
+                flag = 1;
+            else
+            {
+                heap.size = S.heap_size;
+                while (true)
+                {
+                    if (heap.size == 0)
+                    {
+                        flag = 2;
+                        break;
+                    }
+                    unsigned long long fk;
+                    cur = heap_pop_warp(heap, fk);
+                    cn = nodes[cur];
+                    if (!cn.closed)
+                        break;
+                }
+            }
+            if (lane == 0)
+            {
+                S.flag = flag;
+                S.heap_size = heap.size;
+                if (flag == 0)
+                {
+                    S.cur = cn;
+                    S.cur_id = cur;
+                    double ddx = cn.x - S.gx, ddy = cn.y - S.gy;
+                    S.need_shot = (ddx * ddx + ddy * ddy) < p.rs_range * p.rs_range;
+                    S.shot_ok = 0;
+                    dm::sincos_(cn.yaw, &S.cur_s, &S.cur_c);
+                }
+            }
+        }
+        __syncthreads();
+        PROF_MARK(0);
+        if (S.flag != 0)
+            break;
+        const PlanNode cn = S.cur;
+
+        // -- genRSPath (:853-900)
+        if (S.need_shot)
+        {
+            team_rs_solve<NW>(a.rs, S, cn.x, cn.y, cn.yaw, (int)cn.dir, cn.steer);
+            const int np = S.traj_n;
+            if (tid == 0)
+            {
+                S.n_shots++;
+                S.first_hit = np > kTrajCap ? 0 : -1; // longer than the buffer cannot happen inside the shot range
+            }
+            __syncthreads();
+            for (int base = 0; base < np && base < kTrajCap && S.first_hit < 0; base += NW)
+            {
+                int k = base + warp;
+                bool hit = false;
+                if (k < np)
+                {
+                    double s, c;
+                    dm::sincos_(S.traj[3 * k + 2], &s, &c);
+                    hit = warp_footprint_collision(m, p, S.traj[3 * k], S.traj[3 * k + 1], s, c);
+                }
+                if (lane == 0 && k < kTrajCap)
+                    S.traj_hit[k] = hit;
+                __syncthreads();
+                if (tid == 0)
+                {
+                    for (int t = base; t < min(np, base + NW); ++t)
+                        if (S.traj_hit[t])
+                        {
+                            S.first_hit = t;
+                            break;
+                        }
+                }
+                __syncthreads();
+            }
+            if (tid == 0)
+            {
+                S.n_coll += (S.first_hit >= 0) ? (S.first_hit + 1) : np;
+                if (S.first_hit < 0)
+                {
+                    if (S.goal_parent == kNoNode || S.goal_g > cn.g + S.best_cost)
+                    {
+                        S.goal_parent = S.cur_id;
+                        S.goal_g = cn.g + S.best_cost;
+                        S.goal_traj_n = np;
+                    }
+                    S.shot_ok = 1;
+                    S.goal_found = 1;
+                }
+            }
+            __syncthreads();
+        }
+        PROF_MARK(1);
+        if (S.shot_ok)
+        {
+            if (!a.optimal)
+                break;
+        }
+        else
+        {
+            // -- expandNode (:304-402): primitives' end poses + footprint tests, one warp per primitive
+            for (int c = warp; c < P; c += NW)
+            {
+                double nx = 0, ny = 0, nyaw = 0, steer = 0, direc = 1, ns = 0, nc = 1;
+                if (lane == 0)
+                {
+                    primitive_end_pose(p, c, cn.x, cn.y, cn.yaw, S.cur_s, S.cur_c, nx, ny, nyaw, steer, direc);
+                    dm::sincos_(nyaw, &ns, &nc);
+                }
+                nx = __shfl_sync(kFull, nx, 0), ny = __shfl_sync(kFull, ny, 0);
+                ns = __shfl_sync(kFull, ns, 0), nc = __shfl_sync(kFull, nc, 0);
+                bool hit = warp_footprint_collision(m, p, nx, ny, ns, nc);
+                if (lane == 0)
+                {
+                    S.c_x[c] = nx, S.c_y[c] = ny, S.c_yaw[c] = nyaw, S.c_steer[c] = steer, S.c_dir[c] = direc;
+                    S.c_alive[c] = hit ? 0 : 1;
+                }
+            }
+            if (tid == 0)
+            {
+                S.nslots = P;
+                S.n_prim += P;
+                S.n_coll += P;
+            }
+            __syncthreads();
+            PROF_MARK(2);
+            // survivors: node cell, g, closed-set probe (read only) -> which children need a heuristic at all
+            if (tid < P)
+            {
+                const int c = tid;
+                bool need = false;
+                if (S.c_alive[c])
+                {
+                    int ci, cj;
+                    if (pos_to_index_ds(m, S.c_x[c], S.c_y[c], ci, cj))
+                    {
+                        double voro = (double)__ldg(m.voronoi + (size_t)ci * m.W + cj);
+                        double g = node_cost(p, cn.g, (double)cn.dir, cn.steer, voro, S.c_steer[c], S.c_dir[c]);
+                        unsigned long long idx = cal_index(m, p, ci, cj, yaw_to_idx(p, S.c_yaw[c]), S.c_dir[c]);
+                        bool found;
+                        uint32_t slot = closed_find(closed, idx, found);
+                        double old_cost = found ? closed.g[slot] : __longlong_as_double(0x7ff0000000000000ll);
+                        need = old_cost > g; // an earlier sibling on the same index may still beat it; resolved at insert
+                        S.c_i[c] = ci, S.c_j[c] = cj, S.c_g[c] = g, S.c_idx[c] = idx;
+                    }
+                    else
+                        S.c_alive[c] = 0; // the reference would index outside its arrays (cannot pass the footprint test)
+                }
+                S.c_need[c] = need;
+            }
+            __syncthreads();
+            PROF_MARK(3);
+            team_h1_lookup<NW>(m, S);
+            PROF_MARK(6);
+            team_heuristics<NW>(m, p, S);
+            PROF_MARK(4);
+            // closed-set compare / open-list insert, strictly in primitive order (lane 0 of warp 0)
+            if (tid == 0)
+            {
+                heap.size = S.heap_size;
+                uint32_t n_nodes = S.n_nodes;
+                for (int c = 0; c < P; ++c)
+                {
+                    if (!S.c_need[c])
+                        continue;
+                    bool found;
+                    uint32_t slot = closed_find(closed, S.c_idx[c], found);
+                    double old_cost = found ? closed.g[slot] : __longlong_as_double(0x7ff0000000000000ll);
+                    double tg = S.c_g[c];
+                    if (!(old_cost > tg))
+                        continue;
+                    if (n_nodes >= (uint32_t)L.node_cap)
+                    {
+                        S.overflow = 1;
+                        break;
+                    }
+                    if (found)
+                    {
+                        uint32_t old = closed.node[slot];
+                        if (old < kGoalNode)
+                            nodes[old].closed = 1;
+                    }
+                    closed.key[slot] = (closed.tag << 34) | S.c_idx[c];
+                    closed.g[slot] = tg;
+                    closed.node[slot] = n_nodes;
+                    PlanNode nn;
+                    nn.x = S.c_x[c], nn.y = S.c_y[c], nn.yaw = S.c_yaw[c], nn.steer = S.c_steer[c], nn.g = tg, nn.parent = S.cur_id;
+                    nn.dir = (int8_t)(S.c_dir[c] > 0 ? 1 : -1), nn.closed = 0, nn.pad = 0;
+                    nodes[n_nodes] = nn;
+                    heap_push_lane0(heap, (unsigned long long)__double_as_longlong(tg + S.c_h[c]), n_nodes);
+                    heap.size++;
+                    n_nodes++;
+                }
+                S.heap_size = heap.size;
+                S.n_nodes = n_nodes;
+            }
+            __syncthreads();
+            PROF_MARK(5);
+            if (S.overflow)
+                break;
+        }
+        if (a.optimal)
+        {
+            if (dm::hypot_(S.gx - cn.x, S.gy - cn.y) <= 1.0) // stop_radius (hybrid_a_star.h:345)
+                break;
+        }
+        if (tid == 0)
+            S.iteration++;
+        __syncthreads();
+    }
+
+    PROF_FLUSH;
+    // ---- status + raw path_ of setPath (hybrid_a_star.cpp:779-811) ----
+    int status = ST_NOT_INIT;
+    if (init_ok)
+    {
+        if (S.overflow)
+            status = ST_OVERFLOW;
+        else if (S.goal_found)
+            status = ST_FOUND;
+        else if (S.flag == 1)
+            status = ST_LIMIT;
+        else
+            status = ST_OPEN_EMPTY;
+    }
+    int out_len = 0;
+    if (status == ST_FOUND)
+    {
+        const PlanNode gp = nodes[S.goal_parent];
+        if (a.optimal) // the best shot may be older than the last one: re-generate it (deterministic)
+        {
+            __syncthreads();
+            team_rs_solve<NW>(a.rs, S, gp.x, gp.y, gp.yaw, (int)gp.dir, gp.steer);
+            if (tid == 0)
+                S.goal_traj_n = S.traj_n;
+            __syncthreads();
+        }
+        if (tid == 0)
+        {
+            int chain = 0;
+            uint32_t c = S.goal_parent;
+            while (nodes[c].parent != kNoNode)
+            {
+                ++chain;
+                c = nodes[c].parent;
+            }
+            S.h_n = chain;
+            if (a.paths && a.path_cap > 0)
+            {
+                double *dst = a.paths + (size_t)q * a.path_cap * 5;
+                c = S.goal_parent;
+                int pos = chain;
+                double last_dir = 1.0;
+                while (nodes[c].parent != kNoNode)
+                {
+                    const PlanNode n = nodes[c];
+                    if (pos < a.path_cap)
+                    {
+                        double *o = dst + 5 * pos;
+                        o[0] = n.x, o[1] = n.y, o[2] = n.yaw, o[3] = n.steer, o[4] = (double)n.dir;
+                    }
+                    last_dir = (double)n.dir;
+                    --pos;
+                    c = n.parent;
+                }
+                double start_dir = chain > 1 ? last_dir : (S.goal_traj_n > 0 ? S.traj[3 * kTrajCap + 1] : 1.0);
+                dst[0] = S.sx, dst[1] = S.sy, dst[2] = S.syaw, dst[3] = 0.0, dst[4] = start_dir;
+            }
+        }
+        __syncthreads();
+        const int chain = S.h_n;
+        out_len = 1 + chain + S.goal_traj_n;
+        if (a.paths && a.path_cap > 0)
+        {
+            double *dst = a.paths + (size_t)q * a.path_cap * 5;
+            for (int k = tid; k < S.goal_traj_n && k < kTrajCap; k += NW * 32)
+            {
+                int pos = 1 + chain + k;
+                if (pos < a.path_cap)
+                {
+                    double *o = dst + 5 * pos;
+                    o[0] = S.traj[3 * k], o[1] = S.traj[3 * k + 1], o[2] = S.traj[3 * k + 2];
+                    o[3] = S.traj[3 * kTrajCap + 2 * k], o[4] = S.traj[3 * kTrajCap + 2 * k + 1];
+                }
+            }
+        }
+    }
+    if (tid == 0)
+    {
+        a.status[q] = status;
+        a.cost[q] = (status == ST_FOUND) ? S.goal_g : -1.0;
+        a.path_len[q] = out_len;
+        if (a.stats)
+        {
+            a.stats[6 * q + 0] = S.iteration;
+            a.stats[6 * q + 1] = S.n_prim;
+            a.stats[6 * q + 2] = S.n_shots;
+            a.stats[6 * q + 3] = S.n_coll;
+            a.stats[6 * q + 4] = S.bfs.cells;
+            a.stats[6 * q + 5] = S.n_nodes;
+        }
+    }
+    __syncthreads();
+}
+
+template <int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) plan_team_kernel(MapView m, PlannerView p, PlanBatchArgs a)
+{
+    __shared__ TeamShared<NW> S;
+    char *ws = a.ws + (size_t)blockIdx.x * a.L.stride;
+    uint32_t local_gen = 0;
+    const int total = a.todo ? a.n_todo : a.nq;
+    while (true)
+    {
+        __syncthreads();
+        if (threadIdx.x == 0)
+            S.q = (int)atomicAdd(a.counter, 1u);
+        __syncthreads();
+        const int t = S.q;
+        if (t >= total)
+            break;
+        int q = a.todo ? a.todo[t] : t;
+        ++local_gen;
+        plan_team_query<NW>(m, p, a, q, ws, a.tag_base + local_gen, S);
+    }
+}
+
+} // namespace mpros

@@ -567,6 +567,168 @@ __device__ __noinline__ void ompl_families(double x, double y, double phi, doubl
     }
 }
 
+// One base formula on one image, for the team planner where the 11 evaluations of ompl_families are spread over the
+// warps of a CTA. k is warp-uniform. Returns the candidate length (without the fixed quarter turns) or DBL_MAX.
+//   k: 0 LpSpLp  1 LpSpRp  2 LpRmL  3 LpRmL(backwards)  4 LpRupLumRm  5 LpRumLumRp      -> family 0 (plain)
+//      6 LpRmSmLm  7 LpRmSmLm(backwards)  8 LpRmSmRm  9 LpRmSmRm(backwards)            -> family 1 (CCSC)
+//      10 LpRmSLmRp                                                                   -> family 2 (CCSCC)
+// Operation for operation the same arithmetic as ompl_families.
+__device__ __forceinline__ int ompl_formula_family(int k) { return k < 6 ? 0 : (k < 10 ? 1 : 2); }
+__device__ __noinline__ double ompl_formula(int k, double x, double y, double phi, double xb, double yb, double sphi, double cphi)
+{
+    double t, u, v;
+    const double xm = x - sphi, ym = y - 1. + cphi;
+    const double xp = x + sphi, yp = y - 1. - cphi;
+    switch (k)
+    {
+    case 0:
+        u = dm::sqrt_(xm * xm + ym * ym);
+        t = dm::atan2_(ym, xm);
+        if (t >= -kOmplZero)
+        {
+            v = ompl_mod2pi(phi - t);
+            if (v >= -kOmplZero)
+                return fabs(t) + fabs(u) + fabs(v);
+        }
+        return DBL_MAX;
+    case 1:
+    {
+        double u1 = dm::sqrt_(xp * xp + yp * yp), t1 = dm::atan2_(yp, xp);
+        u1 = u1 * u1;
+        if (u1 >= 4.)
+        {
+            u = dm::sqrt_(u1 - 4.);
+            double theta = dm::atan2_(2., u);
+            t = ompl_mod2pi(t1 + theta);
+            v = ompl_mod2pi(t - phi);
+            if (t >= -kOmplZero && v >= -kOmplZero)
+                return fabs(t) + fabs(u) + fabs(v);
+        }
+        return DBL_MAX;
+    }
+    case 2:
+    case 3:
+    {
+        double xi = (k == 3) ? xb - sphi : xm, eta = (k == 3) ? yb - 1. + cphi : ym;
+        double u1 = dm::sqrt_(xi * xi + eta * eta), theta = dm::atan2_(eta, xi);
+        if (u1 <= 4.)
+        {
+            u = -2. * dm::asin_(.25 * u1);
+            t = ompl_mod2pi(theta + .5 * u + kPi);
+            v = ompl_mod2pi(phi - t + u);
+            if (t >= -kOmplZero && u <= kOmplZero)
+                return fabs(t) + fabs(u) + fabs(v);
+        }
+        return DBL_MAX;
+    }
+    case 4:
+    {
+        double rho = .25 * (2. + dm::sqrt_(xp * xp + yp * yp));
+        if (rho <= 1.)
+        {
+            u = dm::acos_(rho);
+            ompl_tau_omega(u, -u, xp, yp, phi, t, v);
+            if (t >= -kOmplZero && v <= kOmplZero)
+                return fabs(t) + 2. * fabs(u) + fabs(v);
+        }
+        return DBL_MAX;
+    }
+    case 5:
+    {
+        double rho = (20. - xp * xp - yp * yp) / 16.;
+        if (rho >= 0 && rho <= 1)
+        {
+            u = -dm::acos_(rho);
+            if (u >= -.5 * kPi)
+            {
+                ompl_tau_omega(u, u, xp, yp, phi, t, v);
+                if (t >= -kOmplZero && v >= -kOmplZero)
+                    return fabs(t) + 2. * fabs(u) + fabs(v);
+            }
+        }
+        return DBL_MAX;
+    }
+    case 6:
+    case 7:
+    {
+        double xi = (k == 7) ? xb - sphi : xm, eta = (k == 7) ? yb - 1. + cphi : ym;
+        double rho = dm::sqrt_(xi * xi + eta * eta), theta = dm::atan2_(eta, xi);
+        if (rho >= 2.)
+        {
+            double r = dm::sqrt_(rho * rho - 4.);
+            u = 2. - r;
+            t = ompl_mod2pi(theta + dm::atan2_(r, -2.));
+            v = ompl_mod2pi(phi - .5 * kPi - t);
+            if (t >= -kOmplZero && u <= kOmplZero && v <= kOmplZero)
+                return fabs(t) + fabs(u) + fabs(v);
+        }
+        return DBL_MAX;
+    }
+    case 8:
+    case 9:
+    {
+        double xi2 = (k == 9) ? xb + sphi : xp, eta2 = (k == 9) ? yb - 1. - cphi : yp;
+        double rho2 = dm::sqrt_(eta2 * eta2 + xi2 * xi2), theta2 = dm::atan2_(xi2, -eta2);
+        if (rho2 >= 2.)
+        {
+            t = theta2;
+            u = 2. - rho2;
+            v = ompl_mod2pi(t + .5 * kPi - phi);
+            if (t >= -kOmplZero && u <= kOmplZero && v <= kOmplZero)
+                return fabs(t) + fabs(u) + fabs(v);
+        }
+        return DBL_MAX;
+    }
+    default:
+    {
+        double rho = dm::sqrt_(xp * xp + yp * yp);
+        if (rho >= 2.)
+        {
+            u = 4. - dm::sqrt_(rho * rho - 4.);
+            if (u <= kOmplZero)
+            {
+                t = ompl_mod2pi(dm::atan2_((4. - u) * xp - 2. * yp, -2. * xp + (u - 4.) * yp));
+                v = ompl_mod2pi(t - phi);
+                if (t >= -kOmplZero && v >= -kOmplZero)
+                    return fabs(t) + fabs(u) + fabs(v);
+            }
+        }
+        return DBL_MAX;
+    }
+    }
+}
+
+// image q (0 id, 1 timeflip, 2 reflect, 3 both) of the normalised goal and of its backwards point
+__device__ __forceinline__ void ompl_image(int q, double rho, double x1, double y1, double th1, double x2, double y2, double th2, double &x,
+                                           double &y, double &phi, double &xb, double &yb)
+{
+    double dx = x2 - x1, dy = y2 - y1, dth = th2 - th1;
+    double c, s;
+    dm::sincos_(th1, &s, &c);
+    double nx = (c * dx + s * dy) / rho, ny = (-s * dx + c * dy) / rho;
+    double sphi, cphi;
+    dm::sincos_(dth, &sphi, &cphi);
+    double nxb = nx * cphi + ny * sphi, nyb = nx * sphi - ny * cphi;
+    const bool fx = (q == 1 || q == 3), fy = (q == 2 || q == 3), fp = (q == 1 || q == 2);
+    x = fx ? -nx : nx, y = fy ? -ny : ny, phi = fp ? -dth : dth, xb = fx ? -nxb : nxb, yb = fy ? -nyb : nyb;
+}
+// combine the three family minima exactly like the sequential CSC/CCC/CCCC, CCSC, CCSCC passes
+__device__ __forceinline__ double ompl_combine(double rho, double m_plain, double m_ccsc, double m_ccscc)
+{
+    double best = m_plain;
+    {
+        double l0 = best - .5 * kPi;
+        if (m_ccsc < l0)
+            best = m_ccsc + .5 * kPi;
+    }
+    {
+        double l0 = best - kPi;
+        if (m_ccscc < l0)
+            best = m_ccscc + kPi;
+    }
+    return rho * best;
+}
+
 // Groups of 4 consecutive lanes cooperate on one (start -> goal) pair: lane (q = lane & 3) evaluates symmetry image q
 // of every base formula; the family minima are combined across the group with shuffles. All 4 lanes of the group get
 // the result. Inactive groups must still call this (full-warp shuffles) with any finite arguments.
