@@ -215,6 +215,31 @@ extern "C" int mpros_planner_config(mpros_ctx *c, const mpros_planner_params *p)
     v.steer_set[v.n_steer++] = 0.0;
     v.step_size = p->step_size;
     v.arc_radius_num = p->wheelbase / 2 + off;
+    // motion primitives, hybrid_a_star.cpp:320-350 (steer outer loop, direction {+1, -1} inner loop)
+    for (int si = 0; si < v.n_steer; ++si)
+        for (int di = 0; di < 2; ++di)
+        {
+            const double steer = v.steer_set[si], direc = di ? -1.0 : 1.0;
+            double dx, dy, dyaw_signed;
+            if (steer == 0)
+            {
+                dx = direc * p->step_size;
+                dy = 0;
+                dyaw_signed = 0;
+            }
+            else
+            {
+                double radius = (p->wheelbase / 2 + off) / std::tan(std::abs(steer));
+                double steer_sign = steer / std::abs(steer);
+                double dyaw = p->step_size / radius;
+                dx = std::sin(dyaw) * radius * direc;
+                dy = (1 - std::cos(dyaw)) * radius * steer_sign;
+                dyaw_signed = dyaw * steer_sign * direc;
+            }
+            v.prim_dx[2 * si + di] = dx;
+            v.prim_dy[2 * si + di] = dy;
+            v.prim_dyaw[2 * si + di] = dyaw_signed;
+        }
     v.pen_gear = p->gear_penalty;
     v.pen_back = p->reverse_penalty;
     v.pen_steer = p->steering_penalty;

@@ -43,6 +43,9 @@ struct PlannerView
     int n_steer; // steer_set_.size()
     double steer_set[kMaxSteer];
     double step_size, arc_radius_num; // arc radius numerator: wheelbase/2 + offset (hybrid_a_star.cpp:339)
+    // per primitive (index 2 * steer_index + direction_index), evaluated ONCE on the host with the same libm the
+    // reference calls for every expansion (hybrid_a_star.cpp:325-348): displacement in the vehicle frame and yaw change
+    double prim_dx[2 * kMaxSteer], prim_dy[2 * kMaxSteer], prim_dyaw[2 * kMaxSteer];
     double pen_gear, pen_back, pen_steer, pen_steer_change;
     double min_r, max_steer, rs_range;
     int num_yaw;

@@ -19,7 +19,7 @@ namespace mpros
 
 struct WarpWorkspaceLayout
 {
-    size_t node_off, hkey_off, hid_off, tkey_off, tg_off, tnode_off, blocked_off, f0_off, f1_off, dist_off, rowtag_off, traj_off;
+    size_t node_off, hkey_off, hid_off, table_off, blocked_off, f0_off, f1_off, dist_off, rowtag_off, traj_off;
     size_t stride;
     int node_cap, table_slots, bfs_rows, bfs_wwords;
 };
@@ -47,9 +47,7 @@ static WarpWorkspaceLayout make_layout(int node_cap, int H, int W)
     L.node_off = take((size_t)node_cap * sizeof(PlanNode));
     L.hkey_off = take((size_t)node_cap * 8);
     L.hid_off = take((size_t)node_cap * 4);
-    L.tkey_off = take((size_t)slots * 8);
-    L.tg_off = take((size_t)slots * 8);
-    L.tnode_off = take((size_t)slots * 4);
+    L.table_off = take((size_t)slots * sizeof(ClosedSlot));
     size_t bw = (size_t)L.bfs_rows * L.bfs_wwords;
     L.blocked_off = take(bw * 4);
     L.f0_off = take(bw * 4);
@@ -598,7 +596,7 @@ namespace mpros
 #define MPROS_TEAM_WARPS 8
 #endif
 #ifndef MPROS_TEAM_MIN_BLOCKS
-#define MPROS_TEAM_MIN_BLOCKS 1
+#define MPROS_TEAM_MIN_BLOCKS 2
 #endif
 constexpr int kTeamWarps = MPROS_TEAM_WARPS;
 constexpr int kTeamMinBlocks = MPROS_TEAM_MIN_BLOCKS;
@@ -726,7 +724,19 @@ static int plan_batch_dev_impl(mpros_ctx *c, const double *d_starts, const doubl
     PlanScratch &S = g_plan_scratch[c->device & 15][0];
     // pass 1: every query with a small node pool; later passes: only the queries that overflowed, bigger pools
     const long long max_nodes = (long long)(c->pp.max_iteration + 2) * (2 * c->pv.n_steer) + 16;
+    // node pools: when every resident team can own a pool for the iteration limit (B200: 296 teams x ~100 MB) each query
+    // runs exactly once; otherwise small pools first and the queries that overflowed are re-run with bigger ones
     long long caps[3] = {16384, 131072, max_nodes};
+    {
+        size_t free_b = 0, total_b = 0;
+        MPROS_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        size_t have = free_b;
+        for (int k = 0; k < 3; ++k)
+            have += g_plan_scratch[c->device & 15][k].ws_bytes;
+        WarpWorkspaceLayout big = make_layout((int)max_nodes, c->H, c->W);
+        if (big.stride * (size_t)(2 * 148) < have / 2)
+            caps[0] = max_nodes;
+    }
     int rc = plan_pass(c, a, 0, (int)std::min<long long>(caps[0], max_nodes), nq, nullptr, 0);
     if (rc)
         return rc;

@@ -53,8 +53,12 @@ struct TeamShared
     int c_i[kMaxPrim], c_j[kMaxPrim], c_h1[kMaxPrim];
     unsigned long long c_idx[kMaxPrim];
     unsigned char c_alive[kMaxPrim], c_need[kMaxPrim];
-    int h_list[kMaxPrim], h_n, bfs_more;
+    int h_list[kMaxPrim], h_n, bfs_more, h_skip;
     unsigned long long hmin[kMaxPrim][3];
+    double img[8][4][7]; // per round: 8 children x 4 symmetry images x {x, y, phi, xb, yb, sin phi, cos phi}
+    // open list: top three levels of the 32-ary heap
+    unsigned long long heap_key[kHeapTop];
+    uint32_t heap_id[kHeapTop];
     // Reeds-Shepp shot
     double cand_cost[NW];
     int cand_idx[NW];
@@ -67,23 +71,26 @@ struct TeamShared
     TeamBfs bfs;
 };
 
-// assignment of the 11 OMPL base formulas (rs_device.cuh: ompl_formula) to the warps of a team, heaviest first
+// The 11 OMPL base formulas (rs_device.cuh: ompl_formula) are evaluated in two rounds. Round A: the two CSC formulas
+// (k = 0, 1) on warps 0 and 1; any valid candidate is an upper bound of the RS distance, so when rho * min(CSC) <= h1 for
+// every child the heuristic is max(h1, h2) = h1 exactly and round B is skipped. Round B: the other nine formulas spread
+// over the warps, heaviest (CCCC, with tauOmega) alone.
 template <int NW>
-__device__ __forceinline__ int team_formula(int warp, int slot);
+__device__ __forceinline__ int team_formula_b(int warp, int slot);
 template <>
-__device__ __forceinline__ int team_formula<8>(int warp, int slot)
+__device__ __forceinline__ int team_formula_b<8>(int warp, int slot)
 {
-    const signed char tab[8][2] = {{4, -1}, {5, -1}, {1, 10}, {6, 0}, {7, 8}, {2, 9}, {3, -1}, {-1, -1}};
+    const signed char tab[8][2] = {{4, -1}, {5, -1}, {6, -1}, {7, -1}, {2, -1}, {3, -1}, {8, 10}, {9, -1}};
     return tab[warp][slot];
 }
 template <>
-__device__ __forceinline__ int team_formula<4>(int warp, int slot)
+__device__ __forceinline__ int team_formula_b<4>(int warp, int slot)
 {
-    const signed char tab[4][3] = {{4, 0, 8}, {5, 10, 9}, {1, 6, 2}, {7, 3, -1}};
-    return slot < 3 ? tab[warp][slot] : -1;
+    const signed char tab[4][3] = {{4, 2, 8}, {5, 3, -1}, {6, 9, -1}, {7, 10, -1}};
+    return tab[warp][slot];
 }
 template <int NW>
-__device__ __forceinline__ int team_formula_slots() { return NW == 8 ? 2 : 3; }
+__device__ __forceinline__ int team_formula_b_slots() { return NW == 8 ? 2 : 3; }
 
 // ---- on-demand goal wavefront, team version (same semantics as planner_device.cuh: GoalBfs) -------------------------
 template <int NW>
@@ -310,31 +317,61 @@ __device__ __forceinline__ void team_heuristics(const MapView &m, const PlannerV
     const int hn = S.h_n;
     for (int base = 0; base < hn; base += 8)
     {
-        int e = base + (lane >> 2), q = lane & 3;
-        bool live = e < hn;
-        int c = live ? S.h_list[e] : 0;
-        double x, y, phi, xb, yb, sphi = 0, cphi = 1;
-        bool any_live = base < hn; // warp-uniform: at least lane 0's quad is live
-        if (any_live)
+        const int e = base + (lane >> 2), q = lane & 3;
+        const bool live = e < hn;
+        const int c = live ? S.h_list[e] : 0;
+        // symmetry images of the normalised goal, once per (child, image)
+        if (warp == 0 && live)
         {
-            ompl_image(q, p.min_r, live ? S.c_x[c] : S.gx, live ? S.c_y[c] : S.gy, live ? S.c_yaw[c] : S.gyaw, S.gx, S.gy, S.gyaw, x, y,
-                       phi, xb, yb);
+            double x, y, phi, xb, yb, sphi, cphi;
+            ompl_image(q, p.min_r, S.c_x[c], S.c_y[c], S.c_yaw[c], S.gx, S.gy, S.gyaw, x, y, phi, xb, yb);
             dm::sincos_(phi, &sphi, &cphi);
-#pragma unroll 1
-            for (int s = 0; s < team_formula_slots<NW>(); ++s)
+            double *o = S.img[lane >> 2][q];
+            o[0] = x, o[1] = y, o[2] = phi, o[3] = xb, o[4] = yb, o[5] = sphi, o[6] = cphi;
+        }
+        __syncthreads();
+        const double *im = S.img[lane >> 2][q];
+        // round A: CSC
+        if (warp < 2)
+        {
+            double L = live ? ompl_formula(warp, im[0], im[1], im[2], im[3], im[4], im[5], im[6]) : DBL_MAX;
+            L = fmin(L, __shfl_xor_sync(kFull, L, 1));
+            L = fmin(L, __shfl_xor_sync(kFull, L, 2));
+            if (live && q == 0 && L < DBL_MAX)
+                atomicMin(&S.hmin[c][0], (unsigned long long)__double_as_longlong(L));
+        }
+        __syncthreads();
+        if (tid == 0)
+        {
+            bool all = true;
+            for (int t = base; t < min(hn, base + 8); ++t)
             {
-                int k = team_formula<NW>(warp, s);
+                int cc = S.h_list[t];
+                double ub = p.min_r * __longlong_as_double((long long)S.hmin[cc][0]);
+                if (!(ub <= (double)S.c_h1[cc] * m.res))
+                    all = false;
+            }
+            S.h_skip = all;
+        }
+        __syncthreads();
+        // round B: CCC, CCCC, CCSC, CCSCC
+        if (!S.h_skip)
+        {
+#pragma unroll 1
+            for (int s = 0; s < team_formula_b_slots<NW>(); ++s)
+            {
+                int k = team_formula_b<NW>(warp, s);
                 if (k < 0)
                     continue;
-                double L = ompl_formula(k, x, y, phi, xb, yb, sphi, cphi);
+                double L = live ? ompl_formula(k, im[0], im[1], im[2], im[3], im[4], im[5], im[6]) : DBL_MAX;
                 L = fmin(L, __shfl_xor_sync(kFull, L, 1));
                 L = fmin(L, __shfl_xor_sync(kFull, L, 2));
                 if (live && q == 0 && L < DBL_MAX)
                     atomicMin(&S.hmin[c][ompl_formula_family(k)], (unsigned long long)__double_as_longlong(L));
             }
         }
+        __syncthreads();
     }
-    __syncthreads();
     if (tid < hn)
     {
         int c = S.h_list[tid];
@@ -443,12 +480,13 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
     OpenHeap heap;
     heap.key = reinterpret_cast<unsigned long long *>(ws + L.hkey_off);
     heap.id = reinterpret_cast<uint32_t *>(ws + L.hid_off);
+    heap.skey = S.heap_key;
+    heap.sid = S.heap_id;
+    heap.scap = kHeapTop;
     heap.size = 0;
     heap.cap = L.node_cap;
     ClosedSet closed;
-    closed.key = reinterpret_cast<unsigned long long *>(ws + L.tkey_off);
-    closed.g = reinterpret_cast<double *>(ws + L.tg_off);
-    closed.node = reinterpret_cast<uint32_t *>(ws + L.tnode_off);
+    closed.slot = reinterpret_cast<ClosedSlot *>(ws + L.table_off);
     closed.mask = (uint32_t)L.table_slots - 1;
     closed.tag = tag;
 
@@ -513,16 +551,14 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
             n.x = S.sx, n.y = S.sy, n.yaw = S.syaw, n.steer = 0.0, n.g = 0.0, n.parent = kNoNode, n.dir = 1, n.closed = 0, n.pad = 0;
             nodes[0] = n;
             bool found;
+            double og;
+            uint32_t on;
             unsigned long long sidx = cal_index(m, p, S.si, S.sj, yaw_to_idx(p, S.syaw), 1.0);
-            uint32_t s0 = closed_find(closed, sidx, found);
-            closed.key[s0] = (closed.tag << 34) | sidx;
-            closed.g[s0] = 0.0;
-            closed.node[s0] = 0;
+            uint32_t s0 = closed_find(closed, sidx, found, og, on);
+            closed_store(closed, s0, sidx, 0.0, 0);
             unsigned long long gidx = cal_index(m, p, S.gi, S.gj, yaw_to_idx(p, S.gyaw), 1.0);
-            uint32_t s1 = closed_find(closed, gidx, found);
-            closed.key[s1] = (closed.tag << 34) | gidx;
-            closed.g[s1] = 10000.0;
-            closed.node[s1] = kGoalNode;
+            uint32_t s1 = closed_find(closed, gidx, found, og, on);
+            closed_store(closed, s1, gidx, 10000.0, kGoalNode);
             heap_push_lane0(heap, (unsigned long long)__double_as_longlong(0.0 + S.c_h[0]), 0);
             S.heap_size = 1;
             S.n_nodes = 1;
@@ -682,8 +718,9 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                         double g = node_cost(p, cn.g, (double)cn.dir, cn.steer, voro, S.c_steer[c], S.c_dir[c]);
                         unsigned long long idx = cal_index(m, p, ci, cj, yaw_to_idx(p, S.c_yaw[c]), S.c_dir[c]);
                         bool found;
-                        uint32_t slot = closed_find(closed, idx, found);
-                        double old_cost = found ? closed.g[slot] : __longlong_as_double(0x7ff0000000000000ll);
+                        double old_cost;
+                        uint32_t old_node;
+                        closed_find(closed, idx, found, old_cost, old_node);
                         need = old_cost > g; // an earlier sibling on the same index may still beat it; resolved at insert
                         S.c_i[c] = ci, S.c_j[c] = cj, S.c_g[c] = g, S.c_idx[c] = idx;
                     }
@@ -708,8 +745,9 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                     if (!S.c_need[c])
                         continue;
                     bool found;
-                    uint32_t slot = closed_find(closed, S.c_idx[c], found);
-                    double old_cost = found ? closed.g[slot] : __longlong_as_double(0x7ff0000000000000ll);
+                    double old_cost;
+                    uint32_t old;
+                    uint32_t slot = closed_find(closed, S.c_idx[c], found, old_cost, old);
                     double tg = S.c_g[c];
                     if (!(old_cost > tg))
                         continue;
@@ -718,15 +756,9 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                         S.overflow = 1;
                         break;
                     }
-                    if (found)
-                    {
-                        uint32_t old = closed.node[slot];
-                        if (old < kGoalNode)
-                            nodes[old].closed = 1;
-                    }
-                    closed.key[slot] = (closed.tag << 34) | S.c_idx[c];
-                    closed.g[slot] = tg;
-                    closed.node[slot] = n_nodes;
+                    if (found && old < kGoalNode)
+                        nodes[old].closed = 1;
+                    closed_store(closed, slot, S.c_idx[c], tg, n_nodes);
                     PlanNode nn;
                     nn.x = S.c_x[c], nn.y = S.c_y[c], nn.yaw = S.c_yaw[c], nn.steer = S.c_steer[c], nn.g = tg, nn.parent = S.cur_id;
                     nn.dir = (int8_t)(S.c_dir[c] > 0 ? 1 : -1), nn.closed = 0, nn.pad = 0;

@@ -61,46 +61,63 @@ __device__ __noinline__ bool warp_footprint_collision(const MapView &m, const Pl
 // ---- open list --------------------------------------------------------------------------------------------------------
 // f >= 0 always, so the IEEE bit pattern orders like the value. Ties pop in insertion order (node ids grow with
 // insertion), which is what std::multimap::begin() + insert-at-upper-bound give the reference.
+constexpr int kHeapTop = 1 + 32 + 1024; // heap levels 0-2 live in shared memory
 struct OpenHeap
 {
-    unsigned long long *key;
+    unsigned long long *key; // global arrays (entries >= scap)
     uint32_t *id;
+    unsigned long long *skey; // shared-memory copy of the first scap entries (the hot top of the heap)
+    uint32_t *sid;
+    int scap;
     int size, cap;
 };
+__device__ __forceinline__ unsigned long long hk(const OpenHeap &h, int i) { return i < h.scap ? h.skey[i] : h.key[i]; }
+__device__ __forceinline__ uint32_t hi(const OpenHeap &h, int i) { return i < h.scap ? h.sid[i] : h.id[i]; }
+__device__ __forceinline__ void hset(const OpenHeap &h, int i, unsigned long long k, uint32_t id)
+{
+    if (i < h.scap)
+    {
+        h.skey[i] = k;
+        h.sid[i] = id;
+    }
+    else
+    {
+        h.key[i] = k;
+        h.id[i] = id;
+    }
+}
 __device__ __forceinline__ bool heap_less(unsigned long long ka, uint32_t ia, unsigned long long kb, uint32_t ib)
 {
     return ka < kb || (ka == kb && ia < ib);
 }
-// executed by lane 0 only; caller follows with __syncwarp()
+// executed by ONE thread; caller makes the writes visible (__syncwarp / __syncthreads) before the next pop
 __device__ __noinline__ void heap_push_lane0(OpenHeap &h, unsigned long long k, uint32_t id)
 {
     int pos = h.size;
     while (pos > 0)
     {
         int parent = (pos - 1) >> 5;
-        unsigned long long pk = h.key[parent];
-        uint32_t pi = h.id[parent];
+        unsigned long long pk = hk(h, parent);
+        uint32_t pi = hi(h, parent);
         if (!heap_less(k, id, pk, pi))
             break;
-        h.key[pos] = pk;
-        h.id[pos] = pi;
+        hset(h, pos, pk, pi);
         pos = parent;
     }
-    h.key[pos] = k;
-    h.id[pos] = id;
+    hset(h, pos, k, id);
 }
 // warp-cooperative pop; returns the id with the smallest (key, id); h.size must be > 0
 __device__ __noinline__ uint32_t heap_pop_warp(OpenHeap &h, unsigned long long &out_key)
 {
     const int lane = threadIdx.x & 31;
-    unsigned long long rk = h.key[0];
-    uint32_t ri = h.id[0];
+    unsigned long long rk = hk(h, 0);
+    uint32_t ri = hi(h, 0);
     out_key = rk;
     int n = --h.size;
     if (n == 0)
         return ri;
-    unsigned long long lk = h.key[n];
-    uint32_t li = h.id[n];
+    unsigned long long lk = hk(h, n);
+    uint32_t li = hi(h, n);
     int pos = 0;
     while (true)
     {
@@ -109,8 +126,8 @@ __device__ __noinline__ uint32_t heap_pop_warp(OpenHeap &h, unsigned long long &
         uint32_t ci = 0xffffffffu;
         if (child < n)
         {
-            ck = h.key[child];
-            ci = h.id[child];
+            ck = hk(h, child);
+            ci = hi(h, child);
         }
         int cpos = child;
 #pragma unroll
@@ -129,17 +146,11 @@ __device__ __noinline__ uint32_t heap_pop_warp(OpenHeap &h, unsigned long long &
         if ((pos << 5) + 1 >= n || !heap_less(ck, ci, lk, li))
             break;
         if (lane == 0)
-        {
-            h.key[pos] = ck;
-            h.id[pos] = ci;
-        }
+            hset(h, pos, ck, ci);
         pos = cpos;
     }
     if (lane == 0)
-    {
-        h.key[pos] = lk;
-        h.id[pos] = li;
-    }
+        hset(h, pos, lk, li);
     __syncwarp();
     return ri;
 }
@@ -147,11 +158,16 @@ __device__ __noinline__ uint32_t heap_pop_warp(OpenHeap &h, unsigned long long &
 // ---- closed set -------------------------------------------------------------------------------------------------------
 // cost_set_[index] / node_set_[index] (hybrid_a_star.cpp:103-112, 380-394) as a hash: slot = {tag<<34 | index, g, node}.
 // The tag (query generation) makes stale slots of earlier queries read as empty, so the table is never cleared.
+struct __align__(32) ClosedSlot
+{
+    unsigned long long key; // tag << 34 | index
+    double g;               // cost_set_[index]
+    uint32_t node;          // node_set_[index]
+    uint32_t pad[3];
+};
 struct ClosedSet
 {
-    unsigned long long *key;
-    double *g;
-    uint32_t *node;
+    ClosedSlot *slot;
     uint32_t mask; // slots - 1 (power of two)
     unsigned long long tag;
 };
@@ -162,26 +178,41 @@ __device__ __forceinline__ uint32_t hash_index(unsigned long long idx)
     idx ^= idx >> 32;
     return (uint32_t)idx;
 }
-// single-lane find-or-insert-slot: returns slot; found says whether the key was present
-__device__ __noinline__ uint32_t closed_find(const ClosedSet &t, unsigned long long idx, bool &found)
+// single-thread find-or-insert-slot: returns the slot index; found says whether the key was present, and then g / node
+// are the stored values (one 32-byte sector per probe)
+__device__ __noinline__ uint32_t closed_find(const ClosedSet &t, unsigned long long idx, bool &found, double &g, uint32_t &node)
 {
     unsigned long long want = (t.tag << 34) | idx;
     uint32_t s = hash_index(idx) & t.mask;
     while (true)
     {
-        unsigned long long k = t.key[s];
+        const uint4 raw = *reinterpret_cast<const uint4 *>(&t.slot[s]); // key + g
+        unsigned long long k = ((unsigned long long)raw.y << 32) | raw.x;
         if (k == want)
         {
             found = true;
+            g = __longlong_as_double((long long)(((unsigned long long)raw.w << 32) | raw.z));
+            node = t.slot[s].node;
             return s;
         }
         if ((k >> 34) != t.tag)
         {
             found = false;
+            g = __longlong_as_double(0x7ff0000000000000ll);
+            node = kNoNode;
             return s;
         }
         s = (s + 1) & t.mask;
     }
+}
+__device__ __forceinline__ void closed_store(const ClosedSet &t, uint32_t s, unsigned long long idx, double g, uint32_t node)
+{
+    ClosedSlot v;
+    v.key = (t.tag << 34) | idx;
+    v.g = g;
+    v.node = node;
+    v.pad[0] = v.pad[1] = v.pad[2] = 0;
+    t.slot[s] = v;
 }
 
 // ---- on-demand goal wavefront (N4 semantics, nav_map.cpp:279-349) -------------------------------------------------------
@@ -381,34 +412,18 @@ __device__ __forceinline__ unsigned long long cal_index(const MapView &m, const 
     return ((unsigned long long)((long long)i * m.W + j) * p.num_yaw + (unsigned long long)iyaw) * 2ull + idx_direc;
 }
 
-// One motion primitive (hybrid_a_star.cpp:320-350): prim = 2 * steer_index + direction_index
+// One motion primitive (hybrid_a_star.cpp:320-350): prim = 2 * steer_index + direction_index. The vehicle-frame
+// displacement and yaw change are per-primitive constants (PlannerView::prim_*); only the rotation into the map frame
+// depends on the node.
 __device__ __forceinline__ void primitive_end_pose(const PlannerView &p, int prim, double cx, double cy, double cyaw, double s_yaw,
                                                    double c_yaw, double &nx, double &ny, double &nyaw, double &steer, double &direc)
 {
     steer = p.steer_set[prim >> 1];
     direc = (prim & 1) ? -1.0 : 1.0;
-    double dx, dy;
-    if (steer == 0)
-    {
-        dx = direc * p.step_size;
-        dy = 0;
-        nx = dx * c_yaw - dy * s_yaw + cx;
-        ny = dx * s_yaw + dy * c_yaw + cy;
-        nyaw = cyaw;
-    }
-    else
-    {
-        double radius = p.arc_radius_num / tan(fabs(steer));
-        double steer_sign = steer / fabs(steer);
-        double dyaw = p.step_size / radius;
-        double sd, cd;
-        dm::sincos_(dyaw, &sd, &cd);
-        dx = sd * radius * direc;
-        dy = (1 - cd) * radius * steer_sign;
-        nx = dx * c_yaw - dy * s_yaw + cx;
-        ny = dx * s_yaw + dy * c_yaw + cy;
-        nyaw = regular_yaw(cyaw + dyaw * steer_sign * direc);
-    }
+    const double dx = p.prim_dx[prim], dy = p.prim_dy[prim];
+    nx = dx * c_yaw - dy * s_yaw + cx;
+    ny = dx * s_yaw + dy * c_yaw + cy;
+    nyaw = (steer == 0) ? cyaw : regular_yaw(cyaw + p.prim_dyaw[prim]);
 }
 
 // setNodeCost (hybrid_a_star.cpp:208-246)
