@@ -55,7 +55,7 @@ struct TeamShared
     unsigned char c_alive[kMaxPrim], c_need[kMaxPrim];
     int h_list[kMaxPrim], h_n, bfs_more, h_skip;
     unsigned long long hmin[kMaxPrim][3];
-    double img[8][4][7]; // per round: 8 children x 4 symmetry images x {x, y, phi, xb, yb, sin phi, cos phi}
+    double img[kMaxPrim][4][7]; // per child x symmetry image: {x, y, phi, xb, yb, sin phi, cos phi} of the normalised goal
     // open list: top three levels of the 32-ary heap
     unsigned long long heap_key[kHeapTop];
     uint32_t heap_id[kHeapTop];
@@ -276,9 +276,6 @@ template <int NW>
 __device__ __forceinline__ void team_h1_lookup(const MapView &m, TeamShared<NW> &S)
 {
     const int tid = threadIdx.x;
-    if (tid < S.nslots)
-        S.c_h1[tid] = -1;
-    __syncthreads();
     while (true)
     {
         if (tid == 0)
@@ -296,6 +293,17 @@ __device__ __forceinline__ void team_h1_lookup(const MapView &m, TeamShared<NW> 
             break;
         team_bfs_step<NW>(m, S.bfs);
     }
+}
+
+// symmetry image q of the normalised goal seen from child slot c (once per (child, image); consumed by team_heuristics)
+template <int NW>
+__device__ __forceinline__ void team_image(const PlannerView &p, TeamShared<NW> &S, int c, int q)
+{
+    double x, y, phi, xb, yb, sphi, cphi;
+    ompl_image(q, p.min_r, S.c_x[c], S.c_y[c], S.c_yaw[c], S.gx, S.gy, S.gyaw, x, y, phi, xb, yb);
+    dm::sincos_(phi, &sphi, &cphi);
+    double *o = S.img[c][q];
+    o[0] = x, o[1] = y, o[2] = phi, o[3] = xb, o[4] = yb, o[5] = sphi, o[6] = cphi;
 }
 
 // heuristics (hybrid_a_star.cpp:248-264) of the slots flagged c_need: h = max(h1 * res, RS distance) * 1.001
@@ -320,17 +328,7 @@ __device__ __forceinline__ void team_heuristics(const MapView &m, const PlannerV
         const int e = base + (lane >> 2), q = lane & 3;
         const bool live = e < hn;
         const int c = live ? S.h_list[e] : 0;
-        // symmetry images of the normalised goal, once per (child, image)
-        if (warp == 0 && live)
-        {
-            double x, y, phi, xb, yb, sphi, cphi;
-            ompl_image(q, p.min_r, S.c_x[c], S.c_y[c], S.c_yaw[c], S.gx, S.gy, S.gyaw, x, y, phi, xb, yb);
-            dm::sincos_(phi, &sphi, &cphi);
-            double *o = S.img[lane >> 2][q];
-            o[0] = x, o[1] = y, o[2] = phi, o[3] = xb, o[4] = yb, o[5] = sphi, o[6] = cphi;
-        }
-        __syncthreads();
-        const double *im = S.img[lane >> 2][q];
+        const double *im = S.img[c][q];
         // round A: CSC
         if (warp < 2)
         {
@@ -541,8 +539,11 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
             S.c_x[0] = S.sx, S.c_y[0] = S.sy, S.c_yaw[0] = S.syaw;
             S.c_i[0] = S.si, S.c_j[0] = S.sj;
             S.c_need[0] = 1;
+            S.c_h1[0] = -1;
         }
         __syncthreads();
+        if (tid < 4)
+            team_image<NW>(p, S, 0, tid);
         team_h1_lookup<NW>(m, S);
         team_heuristics<NW>(m, p, S);
         if (tid == 0)
@@ -591,8 +592,9 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                         break;
                     }
                     unsigned long long fk;
-                    cur = heap_pop_warp(heap, fk);
-                    cn = nodes[cur];
+                    cur = hi(heap, 0);
+                    cn = nodes[cur]; // in flight while the root is removed
+                    heap_pop_warp(heap, fk);
                     if (!cn.closed)
                         break;
                 }
@@ -704,11 +706,16 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
             }
             __syncthreads();
             PROF_MARK(2);
-            // survivors: node cell, g, closed-set probe (read only) -> which children need a heuristic at all
+            // survivors: node cell, g, closed-set probe (read only) -> which children need a heuristic at all. Warp 0: one
+            // lane per child (probe results stay in registers for the insert); warp 1: symmetry images of every alive child.
+            bool pr_found = false;
+            double pr_old_cost = 0;
+            uint32_t pr_old = kNoNode, pr_slot = 0xffffffffu - lane;
             if (tid < P)
             {
                 const int c = tid;
                 bool need = false;
+                int h1 = -1;
                 if (S.c_alive[c])
                 {
                     int ci, cj;
@@ -717,17 +724,23 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                         double voro = (double)__ldg(m.voronoi + (size_t)ci * m.W + cj);
                         double g = node_cost(p, cn.g, (double)cn.dir, cn.steer, voro, S.c_steer[c], S.c_dir[c]);
                         unsigned long long idx = cal_index(m, p, ci, cj, yaw_to_idx(p, S.c_yaw[c]), S.c_dir[c]);
-                        bool found;
-                        double old_cost;
-                        uint32_t old_node;
-                        closed_find(closed, idx, found, old_cost, old_node);
-                        need = old_cost > g; // an earlier sibling on the same index may still beat it; resolved at insert
+                        pr_slot = closed_find(closed, idx, pr_found, pr_old_cost, pr_old);
+                        need = pr_old_cost > g; // an earlier sibling on the same slot may still beat it; resolved at insert
                         S.c_i[c] = ci, S.c_j[c] = cj, S.c_g[c] = g, S.c_idx[c] = idx;
+                        if (need)
+                            h1 = team_bfs_peek(m, S.bfs, ci, cj);
                     }
                     else
                         S.c_alive[c] = 0; // the reference would index outside its arrays (cannot pass the footprint test)
                 }
                 S.c_need[c] = need;
+                S.c_h1[c] = h1;
+            }
+            else if (tid >= 32 && tid < 32 + 4 * P)
+            {
+                const int c = (tid - 32) >> 2, q = (tid - 32) & 3;
+                if (S.c_alive[c])
+                    team_image<NW>(p, S, c, q);
             }
             __syncthreads();
             PROF_MARK(3);
@@ -735,40 +748,98 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
             PROF_MARK(6);
             team_heuristics<NW>(m, p, S);
             PROF_MARK(4);
-            // closed-set compare / open-list insert, strictly in primitive order (lane 0 of warp 0)
-            if (tid == 0)
+            // closed-set compare / open-list insert in primitive order (warp 0). Common case: the children that need an
+            // insert touch distinct hash slots -> probes, slot / node stores and close-marks run one lane per child and
+            // only the heap pushes are serial. Children that collide on a slot (same index, or two new keys probing to the
+            // same empty slot) fall back to the strictly sequential walk.
+            if (warp == 0)
             {
                 heap.size = S.heap_size;
                 uint32_t n_nodes = S.n_nodes;
-                for (int c = 0; c < P; ++c)
+                const bool need = lane < P && S.c_need[lane];
+                const bool found = pr_found;
+                const double old_cost = pr_old_cost;
+                const uint32_t old = pr_old, slot = need ? pr_slot : 0xffffffffu - lane;
+                const unsigned same = __match_any_sync(kFull, slot);
+                const bool conflict = __any_sync(kFull, need && (same & (same - 1)) != 0);
+                if (!conflict)
                 {
-                    if (!S.c_need[c])
-                        continue;
-                    bool found;
-                    double old_cost;
-                    uint32_t old;
-                    uint32_t slot = closed_find(closed, S.c_idx[c], found, old_cost, old);
-                    double tg = S.c_g[c];
-                    if (!(old_cost > tg))
-                        continue;
-                    if (n_nodes >= (uint32_t)L.node_cap)
+                    const bool ins = need && old_cost > S.c_g[lane];
+                    const unsigned insmask = __ballot_sync(kFull, ins);
+                    const uint32_t id = n_nodes + __popc(insmask & ((1u << lane) - 1u));
+                    if (n_nodes + __popc(insmask) > (uint32_t)L.node_cap)
                     {
-                        S.overflow = 1;
-                        break;
+                        if (lane == 0)
+                            S.overflow = 1;
                     }
-                    if (found && old < kGoalNode)
-                        nodes[old].closed = 1;
-                    closed_store(closed, slot, S.c_idx[c], tg, n_nodes);
-                    PlanNode nn;
-                    nn.x = S.c_x[c], nn.y = S.c_y[c], nn.yaw = S.c_yaw[c], nn.steer = S.c_steer[c], nn.g = tg, nn.parent = S.cur_id;
-                    nn.dir = (int8_t)(S.c_dir[c] > 0 ? 1 : -1), nn.closed = 0, nn.pad = 0;
-                    nodes[n_nodes] = nn;
-                    heap_push_lane0(heap, (unsigned long long)__double_as_longlong(tg + S.c_h[c]), n_nodes);
-                    heap.size++;
-                    n_nodes++;
+                    else
+                    {
+                        if (ins)
+                        {
+                            if (found && old < kGoalNode)
+                                nodes[old].closed = 1;
+                            closed_store(closed, slot, S.c_idx[lane], S.c_g[lane], id);
+                            PlanNode nn;
+                            nn.x = S.c_x[lane], nn.y = S.c_y[lane], nn.yaw = S.c_yaw[lane], nn.steer = S.c_steer[lane], nn.g = S.c_g[lane];
+                            nn.parent = S.cur_id, nn.dir = (int8_t)(S.c_dir[lane] > 0 ? 1 : -1), nn.closed = 0, nn.pad = 0;
+                            nodes[id] = nn;
+                        }
+                        const unsigned long long fkey = ins ? (unsigned long long)__double_as_longlong(S.c_g[lane] + S.c_h[lane]) : 0ull;
+                        unsigned todo = insmask;
+                        while (todo)
+                        {
+                            const int b = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            const unsigned long long k = __shfl_sync(kFull, fkey, b);
+                            const uint32_t kid = __shfl_sync(kFull, id, b);
+                            if (lane == 0)
+                                heap_push_lane0(heap, k, kid);
+                            heap.size++;
+                            __syncwarp();
+                        }
+                        n_nodes += __popc(insmask);
+                    }
                 }
-                S.heap_size = heap.size;
-                S.n_nodes = n_nodes;
+                else if (lane == 0)
+                {
+                    for (int c = 0; c < P; ++c)
+                    {
+                        if (!S.c_need[c])
+                            continue;
+                        bool f2;
+                        double oc;
+                        uint32_t on;
+                        uint32_t sl = closed_find(closed, S.c_idx[c], f2, oc, on);
+                        double tg = S.c_g[c];
+                        if (!(oc > tg))
+                            continue;
+                        if (n_nodes >= (uint32_t)L.node_cap)
+                        {
+                            S.overflow = 1;
+                            break;
+                        }
+                        if (f2 && on < kGoalNode)
+                            nodes[on].closed = 1;
+                        closed_store(closed, sl, S.c_idx[c], tg, n_nodes);
+                        PlanNode nn;
+                        nn.x = S.c_x[c], nn.y = S.c_y[c], nn.yaw = S.c_yaw[c], nn.steer = S.c_steer[c], nn.g = tg, nn.parent = S.cur_id;
+                        nn.dir = (int8_t)(S.c_dir[c] > 0 ? 1 : -1), nn.closed = 0, nn.pad = 0;
+                        nodes[n_nodes] = nn;
+                        heap_push_lane0(heap, (unsigned long long)__double_as_longlong(tg + S.c_h[c]), n_nodes);
+                        heap.size++;
+                        n_nodes++;
+                    }
+                }
+                if (conflict)
+                {
+                    heap.size = __shfl_sync(kFull, heap.size, 0);
+                    n_nodes = __shfl_sync(kFull, n_nodes, 0);
+                }
+                if (lane == 0)
+                {
+                    S.heap_size = heap.size;
+                    S.n_nodes = n_nodes;
+                }
             }
             __syncthreads();
             PROF_MARK(5);
@@ -880,7 +951,8 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
 }
 
 template <int NW, int MINB>
-__global__ void __launch_bounds__(NW * 32, MINB) plan_team_kernel(MapView m, PlannerView p, PlanBatchArgs a)
+__global__ void __launch_bounds__(NW * 32, MINB) plan_team_kernel(const __grid_constant__ MapView m, const __grid_constant__ PlannerView p,
+                                                                   const __grid_constant__ PlanBatchArgs a)
 {
     __shared__ TeamShared<NW> S;
     char *ws = a.ws + (size_t)blockIdx.x * a.L.stride;

@@ -129,20 +129,22 @@ __device__ __noinline__ uint32_t heap_pop_warp(OpenHeap &h, unsigned long long &
             ck = hk(h, child);
             ci = hi(h, child);
         }
-        int cpos = child;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
+        // lexicographic arg-min over (key hi, key lo, id) with three warp reductions (redux.sync) instead of a
+        // 5-step shuffle butterfly on 128-bit tuples
         {
-            unsigned long long ok = __shfl_xor_sync(kFull, ck, o);
-            uint32_t oi = __shfl_xor_sync(kFull, ci, o);
-            int op = __shfl_xor_sync(kFull, cpos, o);
-            if (heap_less(ok, oi, ck, ci))
-            {
-                ck = ok;
-                ci = oi;
-                cpos = op;
-            }
+            const uint32_t khi = (uint32_t)(ck >> 32), klo = (uint32_t)ck;
+            const uint32_t m1 = __reduce_min_sync(kFull, khi);
+            const bool a1 = khi == m1;
+            const uint32_t m2 = __reduce_min_sync(kFull, a1 ? klo : 0xffffffffu);
+            const bool a2 = a1 && klo == m2;
+            const uint32_t m3 = __reduce_min_sync(kFull, a2 ? ci : 0xffffffffu);
+            const unsigned win = __ballot_sync(kFull, a2 && ci == m3);
+            ck = ((unsigned long long)m1 << 32) | m2;
+            ci = m3;
+            // no child at all: every lane holds the sentinel and lane 0 "wins"; the caller's bound check handles it
+            child = (pos << 5) + 1 + (__ffs(win) - 1);
         }
+        int cpos = child;
         if ((pos << 5) + 1 >= n || !heap_less(ck, ci, lk, li))
             break;
         if (lane == 0)

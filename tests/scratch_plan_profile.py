@@ -24,3 +24,10 @@ for cap in [4096, 16384, 65536, 131072]:
     print("queries needing >", cap, "nodes:", int((r["nodes_inserted"] >= cap).sum()))
 print("sum iterations", it.sum(), "excluding limit-hitters", it[r["status"] != 0].sum())
 print("goal cells mean", r["goal_map_cells"].mean(), "rs shots mean", r["rs_shots"].mean())
+# lone-team latency: only the queries that ran into the iteration limit
+hard = np.nonzero(r["status"] == 0)[0]
+if len(hard):
+    t0 = time.perf_counter()
+    r2 = ctx.plan_batch(s[hard], g[hard], path_cap=16)
+    dt = time.perf_counter() - t0
+    print("limit-hitters alone: %d queries, %.3f s -> %.2f us per iteration (lone team)" % (len(hard), dt, 1e6 * dt / r2["iterations"].max()))
