@@ -4,13 +4,19 @@
 // sets both the tail of a batch (queries that run into the 100 000-iteration limit) and, with a fixed number of
 // resident queries, the throughput. The first version (one warp per query) was instruction-fetch bound: eight
 // independent warps per SM each walking ~170 KB of code (ncu: stall_no_instruction 4.2 per issue, issue active 16 %).
-// Here all warps of a CTA walk the SAME iteration in lock step (shared-memory hand-off, __syncthreads between phases):
-// the footprint tests of the primitives, the 11 base formulas of the OMPL distance, the 48 Reeds-Shepp candidates and
-// the wavefront rows are spread over the warps, the instruction stream is shared, and the sequential parts (heap,
-// closed set) run on warp 0.
+// Here all warps of a CTA walk the SAME iteration, with roles:
+//   * compute warps 0..NW-3 : one warp per motion primitive (footprint test, one lane per probe), OMPL formulas, RS shot
+//   * closed-set warp NW-2  : one lane per child: node cell, g, closed-set probe (DRAM latency hidden behind the
+//                             footprint tests), symmetry images for the OMPL distance, later the inserts
+//   * heap warp NW-1        : owns the open list. It publishes the next node as soon as it is known and restores the
+//                             heap (sift-down of the removed root, sift-up of last iteration's inserts) IN THE BACKGROUND
+//                             while the other warps expand, so the heap's dependent DRAM accesses leave the critical path.
+// New children go to a small shared-memory insertion buffer; pop takes the minimum of (heap root, buffer), so a child
+// that is the next best node never touches the heap.
 //
-// Reference semantics are unchanged: one popped node per step in std::multimap order, children in steer x direction
-// order, strict '>' prune, first successful shot ends the search (hybrid_a_star.cpp:682-777).
+// Reference semantics are unchanged: one popped node per step in std::multimap order ((f, insertion id) total order),
+// children in steer x direction order, strict '>' prune, first successful shot ends the search
+// (hybrid_a_star.cpp:682-777).
 #pragma once
 #include "planner_device.cuh"
 
@@ -21,7 +27,6 @@ struct TeamBfs
 {
     uint32_t *blocked, *f0, *f1;
     uint16_t *dist;
-    uint32_t *row_tag;
     uint32_t tag;
     int r0, w0, rows, wwords;
     int gi, gj;
@@ -38,27 +43,30 @@ struct TeamShared
     // query
     double sx, sy, syaw, gx, gy, gyaw;
     int si, sj, gi, gj;
-    int q, status, init_hit[2];
+    int q, init_ok, init_hit[2];
     // search state
-    int heap_size, iteration, flag, need_shot, shot_ok, overflow, goal_found;
+    int iteration, flag, need_shot, shot_ok, overflow, goal_found, stop;
     uint32_t n_nodes, cur_id, goal_parent;
     double goal_g;
-    int goal_traj_n;
+    int goal_traj_n, chain;
     long long n_prim, n_shots, n_coll;
     PlanNode cur;
-    double cur_s, cur_c;
     // children of the current expansion (slot = primitive index)
     int nslots;
-    double c_x[kMaxPrim], c_y[kMaxPrim], c_yaw[kMaxPrim], c_steer[kMaxPrim], c_dir[kMaxPrim], c_g[kMaxPrim], c_h[kMaxPrim];
+    double c_x[kMaxPrim], c_y[kMaxPrim], c_yaw[kMaxPrim], c_s[kMaxPrim], c_c[kMaxPrim], c_steer[kMaxPrim], c_dir[kMaxPrim];
+    double c_g[kMaxPrim], c_h[kMaxPrim];
     int c_i[kMaxPrim], c_j[kMaxPrim], c_h1[kMaxPrim];
     unsigned long long c_idx[kMaxPrim];
-    unsigned char c_alive[kMaxPrim], c_need[kMaxPrim];
+    unsigned char c_alive[kMaxPrim], c_cand[kMaxPrim], c_need[kMaxPrim];
     int h_list[kMaxPrim], h_n, bfs_more, h_skip;
     unsigned long long hmin[kMaxPrim][3];
     double img[kMaxPrim][4][7]; // per child x symmetry image: {x, y, phi, xb, yb, sin phi, cos phi} of the normalised goal
-    // open list: top three levels of the 32-ary heap
+    // open list: top three levels of the 32-ary heap + the insertion buffers (double buffered by iteration parity)
     unsigned long long heap_key[kHeapTop];
     uint32_t heap_id[kHeapTop];
+    unsigned long long buf_key[2][kMaxPrim];
+    uint32_t buf_id[2][kMaxPrim];
+    int buf_n[2];
     // Reeds-Shepp shot
     double cand_cost[NW];
     int cand_idx[NW];
@@ -71,34 +79,41 @@ struct TeamShared
     TeamBfs bfs;
 };
 
+// barrier of the compute group (every warp except the heap warp)
+template <int NW>
+__device__ __forceinline__ void team_sync()
+{
+    asm volatile("bar.sync 1, %0;" ::"r"((NW - 1) * 32) : "memory");
+}
+
 // The 11 OMPL base formulas (rs_device.cuh: ompl_formula) are evaluated in two rounds. Round A: the two CSC formulas
 // (k = 0, 1) on warps 0 and 1; any valid candidate is an upper bound of the RS distance, so when rho * min(CSC) <= h1 for
 // every child the heuristic is max(h1, h2) = h1 exactly and round B is skipped. Round B: the other nine formulas spread
-// over the warps, heaviest (CCCC, with tauOmega) alone.
+// over the NW-1 compute-group warps, heaviest (CCCC, with tauOmega) alone.
 template <int NW>
 __device__ __forceinline__ int team_formula_b(int warp, int slot);
 template <>
 __device__ __forceinline__ int team_formula_b<8>(int warp, int slot)
 {
-    const signed char tab[8][2] = {{4, -1}, {5, -1}, {6, -1}, {7, -1}, {2, -1}, {3, -1}, {8, 10}, {9, -1}};
+    const signed char tab[7][2] = {{4, -1}, {5, -1}, {6, -1}, {7, -1}, {2, 8}, {3, 9}, {10, -1}};
     return tab[warp][slot];
 }
 template <>
 __device__ __forceinline__ int team_formula_b<4>(int warp, int slot)
 {
-    const signed char tab[4][3] = {{4, 2, 8}, {5, 3, -1}, {6, 9, -1}, {7, 10, -1}};
+    const signed char tab[3][3] = {{4, 6, 2}, {5, 7, 3}, {10, 8, 9}};
     return tab[warp][slot];
 }
 template <int NW>
 __device__ __forceinline__ int team_formula_b_slots() { return NW == 8 ? 2 : 3; }
 
-// ---- on-demand goal wavefront, team version (same semantics as planner_device.cuh: GoalBfs) -------------------------
+// ---- on-demand goal wavefront, compute-group version (same semantics as planner_device.cuh: GoalBfs) -----------------
 template <int NW>
 __device__ __forceinline__ void team_bfs_init_rows(const MapView &m, TeamBfs &b, int ra, int rb)
 {
-    // every thread sees the same b (shared). The initialised rows form one contiguous range [ilo, ihi] that only
-    // grows; rows outside it still hold a previous query's bits and are never read.
-    const int tid = threadIdx.x, NT = NW * 32;
+    // The initialised rows form one contiguous range [ilo, ihi] that only grows; rows outside it still hold a previous
+    // query's bits and are never read.
+    const int tid = threadIdx.x, CT = (NW - 1) * 32;
     ra = max(ra, b.r0);
     rb = min(rb, b.r0 + b.rows - 1);
     const int ilo = b.ilo, ihi = b.ihi;
@@ -107,7 +122,7 @@ __device__ __forceinline__ void team_bfs_init_rows(const MapView &m, TeamBfs &b,
     const int wwords = b.wwords;
     // new rows: [ra, ilo - 1] and [ihi + 1, rb] (the first call has ilo > ihi: everything is new)
     const int lo_n = (ilo > ihi) ? (rb - ra + 1) : max(0, ilo - ra), hi_n = (ilo > ihi) ? 0 : max(0, rb - ihi);
-    for (int k = tid; k < (lo_n + hi_n) * wwords; k += NT)
+    for (int k = tid; k < (lo_n + hi_n) * wwords; k += CT)
     {
         int rr = k / wwords, w = k % wwords;
         int r = rr < lo_n ? ra + rr : ihi + 1 + (rr - lo_n);
@@ -116,13 +131,13 @@ __device__ __forceinline__ void team_bfs_init_rows(const MapView &m, TeamBfs &b,
         b.f0[o] = 0;
         b.f1[o] = 0;
     }
-    __syncthreads();
+    team_sync<NW>();
     if (tid == 0)
     {
         b.ilo = (ilo > ihi) ? ra : min(ilo, ra);
         b.ihi = (ilo > ihi) ? rb : max(ihi, rb);
     }
-    __syncthreads();
+    team_sync<NW>();
 }
 
 template <int NW>
@@ -135,6 +150,7 @@ __device__ __forceinline__ void team_bfs_start(const MapView &m, TeamBfs &b, int
         b.tag = tag;
         b.gi = gi;
         b.gj = gj;
+        // only cells within 999 steps can ever hold a value < 1000
         b.r0 = max(0, gi - (kHugeInt - 1));
         int r1 = min(m.H - 1, gi + (kHugeInt - 1));
         b.w0 = max(0, gj - (kHugeInt - 1)) >> 5;
@@ -148,7 +164,7 @@ __device__ __forceinline__ void team_bfs_start(const MapView &m, TeamBfs &b, int
         b.bw0 = b.bw1 = gj >> 5;
         b.ilo = 1, b.ihi = 0; // nothing initialised yet
     }
-    __syncthreads();
+    team_sync<NW>();
     team_bfs_init_rows<NW>(m, b, gi - 2, gi + 2);
     if (tid == 0)
     {
@@ -156,20 +172,20 @@ __device__ __forceinline__ void team_bfs_start(const MapView &m, TeamBfs &b, int
         b.f0[o] = 1u << (gj & 31);
         b.blocked[o] |= 1u << (gj & 31);
     }
-    __syncthreads();
+    team_sync<NW>();
 }
 
 template <int NW>
 __device__ __forceinline__ void team_bfs_step(const MapView &m, TeamBfs &b)
 {
-    const int tid = threadIdx.x, NT = NW * 32;
+    const int tid = threadIdx.x, CT = (NW - 1) * 32;
     const int level = b.level + 1;
     if (level >= kHugeInt)
     {
-        __syncthreads();
+        team_sync<NW>();
         if (tid == 0)
             b.done = 1;
-        __syncthreads();
+        team_sync<NW>();
         return;
     }
     const int wr1 = b.r0 + b.rows - 1, ww1 = b.w0 + b.wwords - 1;
@@ -180,7 +196,7 @@ __device__ __forceinline__ void team_bfs_step(const MapView &m, TeamBfs &b)
     {
         b.nr0 = 1 << 30, b.nr1 = -1, b.nw0 = 1 << 30, b.nw1 = -1, b.found = 0;
     }
-    __syncthreads();
+    team_sync<NW>();
     const int nw = sw1 - sw0 + 1;
     const int total = (sr1 - sr0 + 1) * nw;
     uint32_t *fprev = (level & 1) ? b.f0 : b.f1;
@@ -188,7 +204,7 @@ __device__ __forceinline__ void team_bfs_step(const MapView &m, TeamBfs &b)
     const int wpr = (m.W + 31) >> 5;
     int nr0 = 1 << 30, nr1 = -1, nw0 = 1 << 30, nw1 = -1, found = 0;
     const int rows = b.rows, wwords = b.wwords, r0 = b.r0, w0 = b.w0;
-    for (int k = tid; k < total; k += NT)
+    for (int k = tid; k < total; k += CT)
     {
         int r = sr0 + k / nw, w = sw0 + k % nw;
         int lr = r - r0, lw = w - w0;
@@ -238,7 +254,7 @@ __device__ __forceinline__ void team_bfs_step(const MapView &m, TeamBfs &b)
         atomicMax(&b.nw1, nw1);
         atomicAdd(&b.found, found);
     }
-    __syncthreads();
+    team_sync<NW>();
     if (tid == 0)
     {
         b.level = level;
@@ -250,28 +266,29 @@ __device__ __forceinline__ void team_bfs_step(const MapView &m, TeamBfs &b)
             b.br0 = min(b.br0, b.nr0), b.br1 = max(b.br1, b.nr1), b.bw0 = min(b.bw0, b.nw0), b.bw1 = max(b.bw1, b.nw1);
         }
     }
-    __syncthreads();
+    team_sync<NW>();
 }
 
+// goal_cost_map_ value of cell (i, j); -1 while not final yet
 __device__ __forceinline__ int team_bfs_peek(const MapView &m, const TeamBfs &b, int i, int j)
 {
     if (i == b.gi && j == b.gj)
         return 0;
     if (bit_at(m.ds_bits, m.pitch, i, j))
-        return kHugeInt;
+        return kHugeInt; // occupied cells are never entered
     int lr = i - b.r0, lw = (j >> 5) - b.w0;
     if (lr < 0 || lr >= b.rows || lw < 0 || lw >= b.wwords)
-        return kHugeInt;
+        return kHugeInt; // further than 999 steps
     if (i >= b.ilo && i <= b.ihi)
     {
         size_t o = (size_t)lr * b.wwords + lw;
-        if ((b.blocked[o] >> (j & 31)) & 1u)
+        if ((b.blocked[o] >> (j & 31)) & 1u) // visited (not occupied, checked above)
             return b.dist[o * 32 + (j & 31)];
     }
     return b.done ? kHugeInt : -1;
 }
 
-// goal-map values for the slots flagged c_need (team-collective): advance the wavefront until all are final
+// goal-map values for the slots flagged c_need whose c_h1 is still unknown (< 0): advance the wavefront until final
 template <int NW>
 __device__ __forceinline__ void team_h1_lookup(const MapView &m, TeamShared<NW> &S)
 {
@@ -280,7 +297,7 @@ __device__ __forceinline__ void team_h1_lookup(const MapView &m, TeamShared<NW> 
     {
         if (tid == 0)
             S.bfs_more = 0;
-        __syncthreads();
+        team_sync<NW>();
         if (tid < S.nslots && S.c_need[tid] && S.c_h1[tid] < 0)
         {
             int v = team_bfs_peek(m, S.bfs, S.c_i[tid], S.c_j[tid]);
@@ -288,19 +305,19 @@ __device__ __forceinline__ void team_h1_lookup(const MapView &m, TeamShared<NW> 
             if (v < 0)
                 S.bfs_more = 1;
         }
-        __syncthreads();
+        team_sync<NW>();
         if (!S.bfs_more)
             break;
         team_bfs_step<NW>(m, S.bfs);
     }
 }
 
-// symmetry image q of the normalised goal seen from child slot c (once per (child, image); consumed by team_heuristics)
+// symmetry image q of the normalised goal seen from pose (x, y, yaw) into slot c (consumed by team_heuristics)
 template <int NW>
-__device__ __forceinline__ void team_image(const PlannerView &p, TeamShared<NW> &S, int c, int q)
+__device__ __forceinline__ void team_image(const PlannerView &p, TeamShared<NW> &S, int c, int q, double px, double py, double pyaw)
 {
     double x, y, phi, xb, yb, sphi, cphi;
-    ompl_image(q, p.min_r, S.c_x[c], S.c_y[c], S.c_yaw[c], S.gx, S.gy, S.gyaw, x, y, phi, xb, yb);
+    ompl_image(q, p.min_r, px, py, pyaw, S.gx, S.gy, S.gyaw, x, y, phi, xb, yb);
     dm::sincos_(phi, &sphi, &cphi);
     double *o = S.img[c][q];
     o[0] = x, o[1] = y, o[2] = phi, o[3] = xb, o[4] = yb, o[5] = sphi, o[6] = cphi;
@@ -321,7 +338,7 @@ __device__ __forceinline__ void team_heuristics(const MapView &m, const PlannerV
     }
     if (tid < kMaxPrim * 3)
         S.hmin[tid / 3][tid % 3] = (unsigned long long)__double_as_longlong(DBL_MAX);
-    __syncthreads();
+    team_sync<NW>();
     const int hn = S.h_n;
     for (int base = 0; base < hn; base += 8)
     {
@@ -338,7 +355,7 @@ __device__ __forceinline__ void team_heuristics(const MapView &m, const PlannerV
             if (live && q == 0 && L < DBL_MAX)
                 atomicMin(&S.hmin[c][0], (unsigned long long)__double_as_longlong(L));
         }
-        __syncthreads();
+        team_sync<NW>();
         if (tid == 0)
         {
             bool all = true;
@@ -351,7 +368,7 @@ __device__ __forceinline__ void team_heuristics(const MapView &m, const PlannerV
             }
             S.h_skip = all;
         }
-        __syncthreads();
+        team_sync<NW>();
         // round B: CCC, CCCC, CCSC, CCSCC
         if (!S.h_skip)
         {
@@ -368,7 +385,7 @@ __device__ __forceinline__ void team_heuristics(const MapView &m, const PlannerV
                     atomicMin(&S.hmin[c][ompl_formula_family(k)], (unsigned long long)__double_as_longlong(L));
             }
         }
-        __syncthreads();
+        team_sync<NW>();
     }
     if (tid < hn)
     {
@@ -378,14 +395,15 @@ __device__ __forceinline__ void team_heuristics(const MapView &m, const PlannerV
                                  __longlong_as_double((long long)S.hmin[c][2]));
         S.c_h[c] = fmax(h1, h2) * (1 + 1e-3);
     }
-    __syncthreads();
+    team_sync<NW>();
 }
 
-// Reeds-Shepp shot from (x, y, yaw, dir, steer) to the goal: FindOptimalPath + GenTraj into S.traj (team-collective).
+// Reeds-Shepp shot from (x, y, yaw, dir, steer) to the goal: FindOptimalPath + GenTraj into S.traj (compute group).
 template <int NW>
 __device__ __forceinline__ void team_rs_solve(const RsConfig &rs, TeamShared<NW> &S, double x, double y, double yaw, int dir, double steer)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int CW = NW - 1;
     // NewGoalPoint (rs_curve.cpp:51-58)
     double dx = S.gx - x, dy = S.gy - y;
     double cs, sn;
@@ -393,15 +411,15 @@ __device__ __forceinline__ void team_rs_solve(const RsConfig &rs, TeamShared<NW>
     double gx = (dx * cs + dy * sn) / rs.radius;
     double gy = (-dx * sn + dy * cs) / rs.radius;
     double gphi = S.gyaw - yaw;
-    // candidate c = 4 f + j; warp w owns formulas w, w + NW, ...; lanes 4 g + j
-    const int groups = (12 + NW - 1) / NW;
+    // candidate c = 4 f + j; warp w owns formulas w, w + CW, ...; lanes 4 g + j
+    const int groups = (12 + CW - 1) / CW;
     double my_cost = 0;
     int my_c = 1 << 20;
     RsPath my;
     my.n = 0;
     {
         int g = lane >> 2, j = lane & 3;
-        int f = warp + NW * g;
+        int f = warp + CW * g;
         if (g < groups && f < 12)
         {
             double cx = (j == 1 || j == 3) ? -gx : gx;
@@ -447,11 +465,11 @@ __device__ __forceinline__ void team_rs_solve(const RsConfig &rs, TeamShared<NW>
     }
     else if (lane == 0 && bi >= (1 << 20))
         S.cand_idx[warp] = 1 << 20;
-    __syncthreads();
+    team_sync<NW>();
     if (tid == 0)
     {
         int bw = -1;
-        for (int w = 0; w < NW; ++w)
+        for (int w = 0; w < CW; ++w)
         {
             if (S.cand_idx[w] >= (1 << 20))
                 continue;
@@ -465,7 +483,23 @@ __device__ __forceinline__ void team_rs_solve(const RsConfig &rs, TeamShared<NW>
         // GenTraj (rs_curve.cpp:165-222): sequential pose integration
         S.traj_n = rs_gen_traj(rs, x, y, yaw, S.best, S.traj, S.traj + 3 * kTrajCap, kTrajCap);
     }
-    __syncthreads();
+    team_sync<NW>();
+}
+
+// ---- heap warp --------------------------------------------------------------------------------------------------------
+// Arg-min over the heap root (lane 31) and the entries of an insertion buffer (lanes 0..n-1), lexicographic on
+// (key, id). Returns the winning lane, -1 when nothing is valid.
+__device__ __forceinline__ int open_argmin(unsigned long long key, uint32_t id, bool valid)
+{
+    if (!__any_sync(kFull, valid))
+        return -1;
+    const uint32_t khi = valid ? (uint32_t)(key >> 32) : 0xffffffffu, klo = (uint32_t)key;
+    const uint32_t m1 = __reduce_min_sync(kFull, khi);
+    const bool a1 = valid && khi == m1;
+    const uint32_t m2 = __reduce_min_sync(kFull, a1 ? klo : 0xffffffffu);
+    const bool a2 = a1 && klo == m2;
+    const uint32_t m3 = __reduce_min_sync(kFull, a2 ? id : 0xffffffffu);
+    return __ffs(__ballot_sync(kFull, a2 && id == m3)) - 1;
 }
 
 template <int NW>
@@ -473,6 +507,11 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                                 TeamShared<NW> &S)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int CW = NW - 1;       // warps of the compute group
+    constexpr int HEAP_W = NW - 1;   // heap warp
+    constexpr int CLOSED_W = NW - 2; // closed-set warp
+    constexpr int COL_W = NW - 2;    // warps 0..COL_W-1 run the footprint tests
+    const bool is_heap = warp == HEAP_W;
     const WarpWorkspaceLayout &L = a.L;
     PlanNode *nodes = reinterpret_cast<PlanNode *>(ws + L.node_off);
     OpenHeap heap;
@@ -492,117 +531,158 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
     {
         S.sx = a.starts[3 * q], S.sy = a.starts[3 * q + 1], S.syaw = a.starts[3 * q + 2];
         S.gx = a.goals[3 * q], S.gy = a.goals[3 * q + 1], S.gyaw = a.goals[3 * q + 2];
-        S.status = ST_NOT_INIT;
+        S.init_ok = 0;
         S.init_hit[0] = S.init_hit[1] = 0;
-        S.heap_size = 0, S.iteration = 0, S.overflow = 0, S.goal_found = 0;
-        S.n_nodes = 0, S.goal_parent = kNoNode, S.goal_g = -1.0, S.goal_traj_n = 0;
+        S.iteration = 0, S.overflow = 0, S.goal_found = 0, S.stop = 0, S.flag = 0, S.shot_ok = 0;
+        S.n_nodes = 0, S.goal_parent = kNoNode, S.goal_g = -1.0, S.goal_traj_n = 0, S.chain = 0;
         S.n_prim = S.n_shots = S.n_coll = 0;
+        S.buf_n[0] = S.buf_n[1] = 0;
         S.bfs.blocked = reinterpret_cast<uint32_t *>(ws + L.blocked_off);
         S.bfs.f0 = reinterpret_cast<uint32_t *>(ws + L.f0_off);
         S.bfs.f1 = reinterpret_cast<uint32_t *>(ws + L.f1_off);
         S.bfs.dist = reinterpret_cast<uint16_t *>(ws + L.dist_off);
-        S.bfs.row_tag = reinterpret_cast<uint32_t *>(ws + L.rowtag_off);
         S.bfs.cells = 0;
     }
     __syncthreads();
 
-    // ---- initialize (hybrid_a_star.cpp:52-118): start / goal footprint tests on two warps ----
-    if (warp < 2)
+    // ---- initialize (hybrid_a_star.cpp:52-118), compute group only; the heap warp waits at the barrier below ----
+    if (!is_heap)
     {
-        double px = warp ? S.gx : S.sx, py = warp ? S.gy : S.sy, pyaw = warp ? S.gyaw : S.syaw;
-        double s, c;
-        dm::sincos_(pyaw, &s, &c);
-        bool hit = warp_footprint_collision(m, p, px, py, s, c);
-        if (lane == 0)
-            S.init_hit[warp] = hit;
+        if (warp < 2)
+        {
+            double px = warp ? S.gx : S.sx, py = warp ? S.gy : S.sy, pyaw = warp ? S.gyaw : S.syaw;
+            double s, c;
+            dm::sincos_(pyaw, &s, &c);
+            bool hit = warp_footprint_collision(m, p, px, py, s, c);
+            if (lane == 0)
+                S.init_hit[warp] = hit;
+        }
+        team_sync<NW>();
+        if (tid == 0)
+        {
+            bool ok = !S.init_hit[0] && !S.init_hit[1]; // "Start pose in collision" / "Goal pose in collision"
+            if (ok)
+            {
+                bool s_in = pos_to_index_ds(m, S.sx, S.sy, S.si, S.sj);
+                bool g_in = pos_to_index_ds(m, S.gx, S.gy, S.gi, S.gj);
+                ok = s_in && g_in; // goal outside the map: no goal map (nav_map.cpp:297-302)
+            }
+            S.init_ok = ok;
+        }
+        team_sync<NW>();
+        if (S.init_ok)
+        {
+            team_bfs_start<NW>(m, S.bfs, S.gi, S.gj, tag);
+            // start node: steer 0, direction 1, g = 0 (:83, :211-215); its heuristic through the generic slot machinery
+            if (tid == 0)
+            {
+                S.nslots = 1;
+                S.c_i[0] = S.si, S.c_j[0] = S.sj;
+                S.c_need[0] = 1;
+                S.c_h1[0] = -1;
+            }
+            if (tid >= 32 && tid < 36)
+                team_image<NW>(p, S, 0, tid - 32, S.sx, S.sy, S.syaw);
+            team_sync<NW>();
+            team_h1_lookup<NW>(m, S);
+            team_heuristics<NW>(m, p, S);
+            if (tid == 0)
+            {
+                PlanNode n;
+                n.x = S.sx, n.y = S.sy, n.yaw = S.syaw, n.steer = 0.0, n.g = 0.0, n.parent = kNoNode, n.dir = 1, n.closed = 0, n.pad = 0;
+                dm::sincos_(S.syaw, &n.s, &n.c);
+                nodes[0] = n;
+                // cost_set_/node_set_ seeds (:107-112); the goal entry is written second and wins a shared cell
+                bool found;
+                double og;
+                uint32_t on;
+                unsigned long long sidx = cal_index(m, p, S.si, S.sj, yaw_to_idx(p, S.syaw), 1.0);
+                uint32_t s0 = closed_find(closed, sidx, found, og, on);
+                closed_store(closed, s0, sidx, 0.0, 0);
+                unsigned long long gidx = cal_index(m, p, S.gi, S.gj, yaw_to_idx(p, S.gyaw), 1.0);
+                uint32_t s1 = closed_find(closed, gidx, found, og, on);
+                closed_store(closed, s1, gidx, 10000.0, kGoalNode);
+                // the start node enters the open list through the insertion buffer of "iteration -1"
+                S.buf_key[1][0] = (unsigned long long)__double_as_longlong(0.0 + S.c_h[0]);
+                S.buf_id[1][0] = 0;
+                S.buf_n[1] = 1;
+                S.n_nodes = 1;
+            }
+        }
     }
     __syncthreads();
-    bool init_ok = !S.init_hit[0] && !S.init_hit[1];
-    if (init_ok)
-    {
-        if (tid == 0)
-        {
-            bool s_in = pos_to_index_ds(m, S.sx, S.sy, S.si, S.sj);
-            bool g_in = pos_to_index_ds(m, S.gx, S.gy, S.gi, S.gj);
-            S.flag = (s_in && g_in) ? 1 : 0;
-        }
-        __syncthreads();
-        init_ok = S.flag != 0;
-    }
-    if (init_ok)
-    {
-        team_bfs_start<NW>(m, S.bfs, S.gi, S.gj, tag);
-        // start node: steer 0, direction 1, g = 0 (:83, :211-215); its heuristic through the generic slot machinery
-        if (tid == 0)
-        {
-            S.nslots = 1;
-            S.c_x[0] = S.sx, S.c_y[0] = S.sy, S.c_yaw[0] = S.syaw;
-            S.c_i[0] = S.si, S.c_j[0] = S.sj;
-            S.c_need[0] = 1;
-            S.c_h1[0] = -1;
-        }
-        __syncthreads();
-        if (tid < 4)
-            team_image<NW>(p, S, 0, tid);
-        team_h1_lookup<NW>(m, S);
-        team_heuristics<NW>(m, p, S);
-        if (tid == 0)
-        {
-            PlanNode n;
-            n.x = S.sx, n.y = S.sy, n.yaw = S.syaw, n.steer = 0.0, n.g = 0.0, n.parent = kNoNode, n.dir = 1, n.closed = 0, n.pad = 0;
-            nodes[0] = n;
-            bool found;
-            double og;
-            uint32_t on;
-            unsigned long long sidx = cal_index(m, p, S.si, S.sj, yaw_to_idx(p, S.syaw), 1.0);
-            uint32_t s0 = closed_find(closed, sidx, found, og, on);
-            closed_store(closed, s0, sidx, 0.0, 0);
-            unsigned long long gidx = cal_index(m, p, S.gi, S.gj, yaw_to_idx(p, S.gyaw), 1.0);
-            uint32_t s1 = closed_find(closed, gidx, found, og, on);
-            closed_store(closed, s1, gidx, 10000.0, kGoalNode);
-            heap_push_lane0(heap, (unsigned long long)__double_as_longlong(0.0 + S.c_h[0]), 0);
-            S.heap_size = 1;
-            S.n_nodes = 1;
-        }
-        __syncthreads();
-    }
+    const bool init_ok = S.init_ok != 0;
 
     // ---- Plan() (hybrid_a_star.cpp:682-777) ----
     const int P = 2 * p.n_steer;
-    PROF_DECL
     while (init_ok)
     {
-        PROF_MARK(7);
-        // -- pop (warp 0): flag 0 continue, 1 iteration limit, 2 open set empty
-        if (warp == 0)
+        const int it = S.iteration;
+        const int par_prev = (it + 1) & 1, par_cur = it & 1; // insertion buffers: last iteration's / this iteration's
+        if (is_heap)
         {
+            // -- pop: minimum of (heap root, last iteration's inserts). flag 0 continue, 1 iteration limit, 2 open set empty
             int flag = 0;
             uint32_t cur = 0;
             PlanNode cn;
-            if (S.iteration > p.max_iteration)
+            bool root_taken = false;
+            int nbuf = S.buf_n[par_prev];
+            unsigned long long bkey = lane < nbuf ? S.buf_key[par_prev][lane] : 0ull;
+            uint32_t bid = lane < nbuf ? S.buf_id[par_prev][lane] : 0u;
+            bool bvalid = lane < nbuf;
+            if (it > p.max_iteration)
                 flag = 1;
             else
             {
-                heap.size = S.heap_size;
+                if (nbuf == 32)
+                {
+                    // lane 31 is needed for the heap root: flush the whole buffer first (only with 16 steering angles)
+                    for (int k = 0; k < 32; ++k)
+                    {
+                        if (lane == 0)
+                            heap_push_lane0(heap, S.buf_key[par_prev][k], S.buf_id[par_prev][k]);
+                        heap.size++;
+                        __syncwarp();
+                    }
+                    bvalid = false;
+                }
                 while (true)
                 {
-                    if (heap.size == 0)
+                    unsigned long long key = bkey;
+                    uint32_t id = bid;
+                    bool valid = bvalid;
+                    if (lane == 31 && heap.size > 0)
+                    {
+                        key = hk(heap, 0);
+                        id = hi(heap, 0);
+                        valid = true;
+                    }
+                    const int win = open_argmin(key, id, valid);
+                    if (win < 0)
                     {
                         flag = 2;
                         break;
                     }
-                    unsigned long long fk;
-                    cur = hi(heap, 0);
-                    cn = nodes[cur]; // in flight while the root is removed
-                    heap_pop_warp(heap, fk);
+                    cur = __shfl_sync(kFull, id, win);
+                    cn = nodes[cur];
+                    const bool from_heap = (win == 31) && heap.size > 0;
+                    if (!from_heap && lane == win)
+                        bvalid = false; // consumed straight from the buffer, never touches the heap
                     if (!cn.closed)
+                    {
+                        root_taken = from_heap;
                         break;
+                    }
+                    if (from_heap)
+                    {
+                        unsigned long long fk;
+                        heap_pop_warp(heap, fk); // closed node: drop it now and look again
+                    }
                 }
             }
             if (lane == 0)
             {
                 S.flag = flag;
-                S.heap_size = heap.size;
                 if (flag == 0)
                 {
                     S.cur = cn;
@@ -610,253 +690,269 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                     double ddx = cn.x - S.gx, ddy = cn.y - S.gy;
                     S.need_shot = (ddx * ddx + ddy * ddy) < p.rs_range * p.rs_range;
                     S.shot_ok = 0;
-                    dm::sincos_(cn.yaw, &S.cur_s, &S.cur_c);
                 }
             }
-        }
-        __syncthreads();
-        PROF_MARK(0);
-        if (S.flag != 0)
-            break;
-        const PlanNode cn = S.cur;
-
-        // -- genRSPath (:853-900)
-        if (S.need_shot)
-        {
-            team_rs_solve<NW>(a.rs, S, cn.x, cn.y, cn.yaw, (int)cn.dir, cn.steer);
-            const int np = S.traj_n;
-            if (tid == 0)
+            __syncthreads(); // (a) the popped node is public
+            if (flag == 0)
             {
-                S.n_shots++;
-                S.first_hit = np > kTrajCap ? 0 : -1; // longer than the buffer cannot happen inside the shot range
-            }
-            __syncthreads();
-            for (int base = 0; base < np && base < kTrajCap && S.first_hit < 0; base += NW)
-            {
-                int k = base + warp;
-                bool hit = false;
-                if (k < np)
+                // -- background: restore the heap while the other warps expand
+                if (root_taken)
                 {
-                    double s, c;
-                    dm::sincos_(S.traj[3 * k + 2], &s, &c);
-                    hit = warp_footprint_collision(m, p, S.traj[3 * k], S.traj[3 * k + 1], s, c);
+                    unsigned long long fk;
+                    heap_pop_warp(heap, fk);
                 }
-                if (lane == 0 && k < kTrajCap)
-                    S.traj_hit[k] = hit;
-                __syncthreads();
-                if (tid == 0)
+                unsigned todo = __ballot_sync(kFull, bvalid);
+                while (todo)
                 {
-                    for (int t = base; t < min(np, base + NW); ++t)
-                        if (S.traj_hit[t])
-                        {
-                            S.first_hit = t;
-                            break;
-                        }
-                }
-                __syncthreads();
-            }
-            if (tid == 0)
-            {
-                S.n_coll += (S.first_hit >= 0) ? (S.first_hit + 1) : np;
-                if (S.first_hit < 0)
-                {
-                    if (S.goal_parent == kNoNode || S.goal_g > cn.g + S.best_cost)
-                    {
-                        S.goal_parent = S.cur_id;
-                        S.goal_g = cn.g + S.best_cost;
-                        S.goal_traj_n = np;
-                    }
-                    S.shot_ok = 1;
-                    S.goal_found = 1;
+                    const int b = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const unsigned long long k = __shfl_sync(kFull, bkey, b);
+                    const uint32_t kid = __shfl_sync(kFull, bid, b);
+                    if (lane == 0)
+                        heap_push_lane0(heap, k, kid);
+                    heap.size++;
+                    __syncwarp();
                 }
             }
-            __syncthreads();
-        }
-        PROF_MARK(1);
-        if (S.shot_ok)
-        {
-            if (!a.optimal)
-                break;
         }
         else
         {
-            // -- expandNode (:304-402): primitives' end poses + footprint tests, one warp per primitive
-            for (int c = warp; c < P; c += NW)
+            __syncthreads(); // (a)
+        }
+        if (S.flag != 0)
+            break;
+        if (!is_heap)
+        {
+            const PlanNode cn = S.cur;
+            if (tid == 0)
+                S.buf_n[par_cur] = 0;
+            // -- genRSPath (:853-900)
+            if (S.need_shot)
             {
-                double nx = 0, ny = 0, nyaw = 0, steer = 0, direc = 1, ns = 0, nc = 1;
-                if (lane == 0)
+                team_rs_solve<NW>(a.rs, S, cn.x, cn.y, cn.yaw, (int)cn.dir, cn.steer);
+                const int np = S.traj_n;
+                if (tid == 0)
                 {
-                    primitive_end_pose(p, c, cn.x, cn.y, cn.yaw, S.cur_s, S.cur_c, nx, ny, nyaw, steer, direc);
-                    dm::sincos_(nyaw, &ns, &nc);
+                    S.n_shots++;
+                    S.first_hit = np > kTrajCap ? 0 : -1; // longer than the buffer cannot happen inside the shot range
                 }
-                nx = __shfl_sync(kFull, nx, 0), ny = __shfl_sync(kFull, ny, 0);
-                ns = __shfl_sync(kFull, ns, 0), nc = __shfl_sync(kFull, nc, 0);
-                bool hit = warp_footprint_collision(m, p, nx, ny, ns, nc);
-                if (lane == 0)
+                team_sync<NW>();
+                for (int base = 0; base < np && base < kTrajCap && S.first_hit < 0; base += CW)
                 {
-                    S.c_x[c] = nx, S.c_y[c] = ny, S.c_yaw[c] = nyaw, S.c_steer[c] = steer, S.c_dir[c] = direc;
-                    S.c_alive[c] = hit ? 0 : 1;
+                    int k = base + warp;
+                    bool hit = false;
+                    if (k < np)
+                    {
+                        double s, c;
+                        dm::sincos_(S.traj[3 * k + 2], &s, &c);
+                        hit = warp_footprint_collision(m, p, S.traj[3 * k], S.traj[3 * k + 1], s, c);
+                    }
+                    if (lane == 0 && k < kTrajCap)
+                        S.traj_hit[k] = hit;
+                    team_sync<NW>();
+                    if (tid == 0)
+                    {
+                        for (int t = base; t < min(np, base + CW); ++t)
+                            if (S.traj_hit[t])
+                            {
+                                S.first_hit = t;
+                                break;
+                            }
+                    }
+                    team_sync<NW>();
                 }
+                if (tid == 0)
+                {
+                    S.n_coll += (S.first_hit >= 0) ? (S.first_hit + 1) : np;
+                    if (S.first_hit < 0)
+                    {
+                        if (S.goal_parent == kNoNode || S.goal_g > cn.g + S.best_cost)
+                        {
+                            S.goal_parent = S.cur_id;
+                            S.goal_g = cn.g + S.best_cost;
+                            S.goal_traj_n = np;
+                        }
+                        S.shot_ok = 1;
+                        S.goal_found = 1;
+                    }
+                }
+                team_sync<NW>();
+            }
+            if (S.shot_ok)
+            {
+                if (!a.optimal && tid == 0)
+                    S.stop = 1; // first successful shot ends the search (:725-728)
+            }
+            else
+            {
+                // -- expandNode (:304-402)
+                // warps 0..COL_W-1: one primitive each: end pose + footprint test (one lane per probe);
+                // closed-set warp: one lane per child: node cell, g, closed-set probe, goal-map peek; then the symmetry images
+                bool pr_found = false;
+                double pr_old_cost = 0;
+                uint32_t pr_old = kNoNode, pr_slot = 0xffffffffu - lane;
+                if (warp < COL_W)
+                {
+                    for (int c = warp; c < P; c += COL_W)
+                    {
+                        double nx = 0, ny = 0, nyaw = 0, steer = 0, direc = 1, ns = 0, nc = 1;
+                        if (lane == 0)
+                        {
+                            primitive_end_pose(p, c, cn.x, cn.y, cn.yaw, cn.s, cn.c, nx, ny, nyaw, steer, direc);
+                            dm::sincos_(nyaw, &ns, &nc);
+                        }
+                        nx = __shfl_sync(kFull, nx, 0), ny = __shfl_sync(kFull, ny, 0);
+                        ns = __shfl_sync(kFull, ns, 0), nc = __shfl_sync(kFull, nc, 0);
+                        bool hit = warp_footprint_collision(m, p, nx, ny, ns, nc);
+                        if (lane == 0)
+                        {
+                            S.c_x[c] = nx, S.c_y[c] = ny, S.c_yaw[c] = nyaw, S.c_s[c] = ns, S.c_c[c] = nc;
+                            S.c_steer[c] = steer, S.c_dir[c] = direc;
+                            S.c_alive[c] = hit ? 0 : 1;
+                        }
+                    }
+                }
+                else if (warp == CLOSED_W)
+                {
+                    if (lane < P)
+                    {
+                        const int c = lane;
+                        double nx, ny, nyaw, steer, direc;
+                        primitive_end_pose(p, c, cn.x, cn.y, cn.yaw, cn.s, cn.c, nx, ny, nyaw, steer, direc);
+                        bool cand = false;
+                        int h1 = -1, ci = -1, cj = -1;
+                        if (pos_to_index_ds(m, nx, ny, ci, cj))
+                        {
+                            double voro = (double)__ldg(m.voronoi + (size_t)ci * m.W + cj);
+                            double g = node_cost(p, cn.g, (double)cn.dir, cn.steer, voro, steer, direc);
+                            unsigned long long idx = cal_index(m, p, ci, cj, yaw_to_idx(p, nyaw), direc);
+                            pr_slot = closed_find(closed, idx, pr_found, pr_old_cost, pr_old);
+                            cand = pr_old_cost > g; // an earlier sibling on the same slot may still beat it; resolved at insert
+                            S.c_g[c] = g, S.c_idx[c] = idx;
+                            if (cand)
+                                h1 = team_bfs_peek(m, S.bfs, ci, cj);
+                        }
+                        // a cell outside the map cannot pass the footprint test; the reference would index outside its arrays
+                        S.c_i[c] = ci, S.c_j[c] = cj;
+                        S.c_cand[c] = cand;
+                        S.c_h1[c] = h1;
+                    }
+                    for (int t = lane; t < 4 * P; t += 32)
+                    {
+                        const int c = t >> 2;
+                        double nx, ny, nyaw, steer, direc;
+                        primitive_end_pose(p, c, cn.x, cn.y, cn.yaw, cn.s, cn.c, nx, ny, nyaw, steer, direc);
+                        team_image<NW>(p, S, c, t & 3, nx, ny, nyaw);
+                    }
+                }
+                if (tid == 0)
+                {
+                    S.nslots = P;
+                    S.n_prim += P;
+                    S.n_coll += P;
+                }
+                team_sync<NW>();
+                if (tid < P)
+                    S.c_need[tid] = S.c_alive[tid] && S.c_cand[tid];
+                team_h1_lookup<NW>(m, S); // starts with a barrier
+                team_heuristics<NW>(m, p, S);
+                // closed-set compare / insert in primitive order (closed-set warp). Common case: the children that need an
+                // insert touch distinct hash slots -> slot / node stores and close-marks run one lane per child, the new open
+                // entries go to the insertion buffer. Children that collide on a slot (same index, or two new keys probing
+                // to the same empty slot) fall back to the strictly sequential walk.
+                if (warp == CLOSED_W)
+                {
+                    uint32_t n_nodes = S.n_nodes;
+                    const bool need = lane < P && S.c_need[lane];
+                    const uint32_t slot = need ? pr_slot : 0xffffffffu - lane;
+                    const unsigned same = __match_any_sync(kFull, slot);
+                    const bool conflict = __any_sync(kFull, need && (same & (same - 1)) != 0);
+                    if (!conflict)
+                    {
+                        const bool ins = need && pr_old_cost > S.c_g[lane];
+                        const unsigned insmask = __ballot_sync(kFull, ins);
+                        const int rank = __popc(insmask & ((1u << lane) - 1u));
+                        const uint32_t id = n_nodes + rank;
+                        if (n_nodes + __popc(insmask) > (uint32_t)L.node_cap)
+                        {
+                            if (lane == 0)
+                                S.overflow = 1;
+                        }
+                        else
+                        {
+                            if (ins)
+                            {
+                                if (pr_found && pr_old < kGoalNode)
+                                    nodes[pr_old].closed = 1;
+                                closed_store(closed, slot, S.c_idx[lane], S.c_g[lane], id);
+                                PlanNode nn;
+                                nn.x = S.c_x[lane], nn.y = S.c_y[lane], nn.yaw = S.c_yaw[lane], nn.steer = S.c_steer[lane], nn.g = S.c_g[lane];
+                                nn.s = S.c_s[lane], nn.c = S.c_c[lane];
+                                nn.parent = S.cur_id, nn.dir = (int8_t)(S.c_dir[lane] > 0 ? 1 : -1), nn.closed = 0, nn.pad = 0;
+                                nodes[id] = nn;
+                                S.buf_key[par_cur][rank] = (unsigned long long)__double_as_longlong(S.c_g[lane] + S.c_h[lane]);
+                                S.buf_id[par_cur][rank] = id;
+                            }
+                            if (lane == 0)
+                            {
+                                S.buf_n[par_cur] = __popc(insmask);
+                                S.n_nodes = n_nodes + __popc(insmask);
+                            }
+                        }
+                    }
+                    else if (lane == 0)
+                    {
+                        int nb = 0;
+                        for (int c = 0; c < P; ++c)
+                        {
+                            if (!S.c_need[c])
+                                continue;
+                            bool f2;
+                            double oc;
+                            uint32_t on;
+                            uint32_t sl = closed_find(closed, S.c_idx[c], f2, oc, on);
+                            double tg = S.c_g[c];
+                            if (!(oc > tg))
+                                continue;
+                            if (n_nodes >= (uint32_t)L.node_cap)
+                            {
+                                S.overflow = 1;
+                                break;
+                            }
+                            if (f2 && on < kGoalNode)
+                                nodes[on].closed = 1;
+                            closed_store(closed, sl, S.c_idx[c], tg, n_nodes);
+                            PlanNode nn;
+                            nn.x = S.c_x[c], nn.y = S.c_y[c], nn.yaw = S.c_yaw[c], nn.steer = S.c_steer[c], nn.g = tg, nn.parent = S.cur_id;
+                            nn.s = S.c_s[c], nn.c = S.c_c[c];
+                            nn.dir = (int8_t)(S.c_dir[c] > 0 ? 1 : -1), nn.closed = 0, nn.pad = 0;
+                            nodes[n_nodes] = nn;
+                            S.buf_key[par_cur][nb] = (unsigned long long)__double_as_longlong(tg + S.c_h[c]);
+                            S.buf_id[par_cur][nb] = n_nodes;
+                            ++nb;
+                            n_nodes++;
+                        }
+                        S.buf_n[par_cur] = nb;
+                        S.n_nodes = n_nodes;
+                    }
+                }
+                team_sync<NW>();
+                if (tid == 0 && S.overflow)
+                    S.stop = 1;
             }
             if (tid == 0)
             {
-                S.nslots = P;
-                S.n_prim += P;
-                S.n_coll += P;
+                if (a.optimal && dm::hypot_(S.gx - cn.x, S.gy - cn.y) <= 1.0) // stop_radius (hybrid_a_star.h:345)
+                    S.stop = 1;
+                if (!S.stop)
+                    S.iteration = it + 1; // every break of the reference's loop precedes ++iteration (:725-745)
             }
-            __syncthreads();
-            PROF_MARK(2);
-            // survivors: node cell, g, closed-set probe (read only) -> which children need a heuristic at all. Warp 0: one
-            // lane per child (probe results stay in registers for the insert); warp 1: symmetry images of every alive child.
-            bool pr_found = false;
-            double pr_old_cost = 0;
-            uint32_t pr_old = kNoNode, pr_slot = 0xffffffffu - lane;
-            if (tid < P)
-            {
-                const int c = tid;
-                bool need = false;
-                int h1 = -1;
-                if (S.c_alive[c])
-                {
-                    int ci, cj;
-                    if (pos_to_index_ds(m, S.c_x[c], S.c_y[c], ci, cj))
-                    {
-                        double voro = (double)__ldg(m.voronoi + (size_t)ci * m.W + cj);
-                        double g = node_cost(p, cn.g, (double)cn.dir, cn.steer, voro, S.c_steer[c], S.c_dir[c]);
-                        unsigned long long idx = cal_index(m, p, ci, cj, yaw_to_idx(p, S.c_yaw[c]), S.c_dir[c]);
-                        pr_slot = closed_find(closed, idx, pr_found, pr_old_cost, pr_old);
-                        need = pr_old_cost > g; // an earlier sibling on the same slot may still beat it; resolved at insert
-                        S.c_i[c] = ci, S.c_j[c] = cj, S.c_g[c] = g, S.c_idx[c] = idx;
-                        if (need)
-                            h1 = team_bfs_peek(m, S.bfs, ci, cj);
-                    }
-                    else
-                        S.c_alive[c] = 0; // the reference would index outside its arrays (cannot pass the footprint test)
-                }
-                S.c_need[c] = need;
-                S.c_h1[c] = h1;
-            }
-            else if (tid >= 32 && tid < 32 + 4 * P)
-            {
-                const int c = (tid - 32) >> 2, q = (tid - 32) & 3;
-                if (S.c_alive[c])
-                    team_image<NW>(p, S, c, q);
-            }
-            __syncthreads();
-            PROF_MARK(3);
-            team_h1_lookup<NW>(m, S);
-            PROF_MARK(6);
-            team_heuristics<NW>(m, p, S);
-            PROF_MARK(4);
-            // closed-set compare / open-list insert in primitive order (warp 0). Common case: the children that need an
-            // insert touch distinct hash slots -> probes, slot / node stores and close-marks run one lane per child and
-            // only the heap pushes are serial. Children that collide on a slot (same index, or two new keys probing to the
-            // same empty slot) fall back to the strictly sequential walk.
-            if (warp == 0)
-            {
-                heap.size = S.heap_size;
-                uint32_t n_nodes = S.n_nodes;
-                const bool need = lane < P && S.c_need[lane];
-                const bool found = pr_found;
-                const double old_cost = pr_old_cost;
-                const uint32_t old = pr_old, slot = need ? pr_slot : 0xffffffffu - lane;
-                const unsigned same = __match_any_sync(kFull, slot);
-                const bool conflict = __any_sync(kFull, need && (same & (same - 1)) != 0);
-                if (!conflict)
-                {
-                    const bool ins = need && old_cost > S.c_g[lane];
-                    const unsigned insmask = __ballot_sync(kFull, ins);
-                    const uint32_t id = n_nodes + __popc(insmask & ((1u << lane) - 1u));
-                    if (n_nodes + __popc(insmask) > (uint32_t)L.node_cap)
-                    {
-                        if (lane == 0)
-                            S.overflow = 1;
-                    }
-                    else
-                    {
-                        if (ins)
-                        {
-                            if (found && old < kGoalNode)
-                                nodes[old].closed = 1;
-                            closed_store(closed, slot, S.c_idx[lane], S.c_g[lane], id);
-                            PlanNode nn;
-                            nn.x = S.c_x[lane], nn.y = S.c_y[lane], nn.yaw = S.c_yaw[lane], nn.steer = S.c_steer[lane], nn.g = S.c_g[lane];
-                            nn.parent = S.cur_id, nn.dir = (int8_t)(S.c_dir[lane] > 0 ? 1 : -1), nn.closed = 0, nn.pad = 0;
-                            nodes[id] = nn;
-                        }
-                        const unsigned long long fkey = ins ? (unsigned long long)__double_as_longlong(S.c_g[lane] + S.c_h[lane]) : 0ull;
-                        unsigned todo = insmask;
-                        while (todo)
-                        {
-                            const int b = __ffs(todo) - 1;
-                            todo &= todo - 1;
-                            const unsigned long long k = __shfl_sync(kFull, fkey, b);
-                            const uint32_t kid = __shfl_sync(kFull, id, b);
-                            if (lane == 0)
-                                heap_push_lane0(heap, k, kid);
-                            heap.size++;
-                            __syncwarp();
-                        }
-                        n_nodes += __popc(insmask);
-                    }
-                }
-                else if (lane == 0)
-                {
-                    for (int c = 0; c < P; ++c)
-                    {
-                        if (!S.c_need[c])
-                            continue;
-                        bool f2;
-                        double oc;
-                        uint32_t on;
-                        uint32_t sl = closed_find(closed, S.c_idx[c], f2, oc, on);
-                        double tg = S.c_g[c];
-                        if (!(oc > tg))
-                            continue;
-                        if (n_nodes >= (uint32_t)L.node_cap)
-                        {
-                            S.overflow = 1;
-                            break;
-                        }
-                        if (f2 && on < kGoalNode)
-                            nodes[on].closed = 1;
-                        closed_store(closed, sl, S.c_idx[c], tg, n_nodes);
-                        PlanNode nn;
-                        nn.x = S.c_x[c], nn.y = S.c_y[c], nn.yaw = S.c_yaw[c], nn.steer = S.c_steer[c], nn.g = tg, nn.parent = S.cur_id;
-                        nn.dir = (int8_t)(S.c_dir[c] > 0 ? 1 : -1), nn.closed = 0, nn.pad = 0;
-                        nodes[n_nodes] = nn;
-                        heap_push_lane0(heap, (unsigned long long)__double_as_longlong(tg + S.c_h[c]), n_nodes);
-                        heap.size++;
-                        n_nodes++;
-                    }
-                }
-                if (conflict)
-                {
-                    heap.size = __shfl_sync(kFull, heap.size, 0);
-                    n_nodes = __shfl_sync(kFull, n_nodes, 0);
-                }
-                if (lane == 0)
-                {
-                    S.heap_size = heap.size;
-                    S.n_nodes = n_nodes;
-                }
-            }
-            __syncthreads();
-            PROF_MARK(5);
-            if (S.overflow)
-                break;
         }
-        if (a.optimal)
-        {
-            if (dm::hypot_(S.gx - cn.x, S.gy - cn.y) <= 1.0) // stop_radius (hybrid_a_star.h:345)
-                break;
-        }
-        if (tid == 0)
-            S.iteration++;
-        __syncthreads();
+        __syncthreads(); // (b) inserts are in the buffer, the heap is consistent again
+        if (S.stop)
+            break;
     }
 
-    PROF_FLUSH;
     // ---- status + raw path_ of setPath (hybrid_a_star.cpp:779-811) ----
     int status = ST_NOT_INIT;
     if (init_ok)
@@ -873,13 +969,15 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
     int out_len = 0;
     if (status == ST_FOUND)
     {
-        const PlanNode gp = nodes[S.goal_parent];
         if (a.optimal) // the best shot may be older than the last one: re-generate it (deterministic)
         {
-            __syncthreads();
-            team_rs_solve<NW>(a.rs, S, gp.x, gp.y, gp.yaw, (int)gp.dir, gp.steer);
-            if (tid == 0)
-                S.goal_traj_n = S.traj_n;
+            if (!is_heap)
+            {
+                const PlanNode gp = nodes[S.goal_parent];
+                team_rs_solve<NW>(a.rs, S, gp.x, gp.y, gp.yaw, (int)gp.dir, gp.steer);
+                if (tid == 0)
+                    S.goal_traj_n = S.traj_n;
+            }
             __syncthreads();
         }
         if (tid == 0)
@@ -891,7 +989,7 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                 ++chain;
                 c = nodes[c].parent;
             }
-            S.h_n = chain;
+            S.chain = chain;
             if (a.paths && a.path_cap > 0)
             {
                 double *dst = a.paths + (size_t)q * a.path_cap * 5;
@@ -906,16 +1004,17 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                         double *o = dst + 5 * pos;
                         o[0] = n.x, o[1] = n.y, o[2] = n.yaw, o[3] = n.steer, o[4] = (double)n.dir;
                     }
-                    last_dir = (double)n.dir;
+                    last_dir = (double)n.dir; // ends as the direction of the node next to the start
                     --pos;
                     c = n.parent;
                 }
+                // start point: steer 0, direction of the first path point (:792-807)
                 double start_dir = chain > 1 ? last_dir : (S.goal_traj_n > 0 ? S.traj[3 * kTrajCap + 1] : 1.0);
                 dst[0] = S.sx, dst[1] = S.sy, dst[2] = S.syaw, dst[3] = 0.0, dst[4] = start_dir;
             }
         }
         __syncthreads();
-        const int chain = S.h_n;
+        const int chain = S.chain;
         out_len = 1 + chain + S.goal_traj_n;
         if (a.paths && a.path_cap > 0)
         {

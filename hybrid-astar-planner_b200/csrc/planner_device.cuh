@@ -17,9 +17,10 @@ constexpr uint32_t kGoalNode = 0xfffffffeu;
 constexpr int kTrajCap = 256;
 constexpr int kMaxPrim = 2 * kMaxSteer;
 
-struct __align__(8) PlanNode
+struct __align__(16) PlanNode
 {
     double x, y, yaw, steer, g;
+    double s, c; // sin / cos of yaw (already computed for the footprint test when the node was a child)
     uint32_t parent;
     int8_t dir;
     uint8_t closed;
