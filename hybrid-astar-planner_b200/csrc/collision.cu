@@ -9,7 +9,7 @@
 namespace mpros
 {
 
-__global__ void __launch_bounds__(256) collision_poses_kernel(MapView m, PlannerView p, const double *__restrict__ xyyaw, size_t n,
+__global__ void __launch_bounds__(256, 4) collision_poses_kernel(const __grid_constant__ MapView m, const __grid_constant__ PlannerView p, const double *__restrict__ xyyaw, size_t n,
                                                               uint8_t *__restrict__ verdicts)
 {
     for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256) collision_poses_kernel(MapView m, Planner
 }
 
 // One warp per path: lanes stride over the poses, ballot gives the OR with an early exit per 32-pose round.
-__global__ void __launch_bounds__(256) collision_paths_kernel(MapView m, PlannerView p, const double *__restrict__ xyyaw,
+__global__ void __launch_bounds__(256) collision_paths_kernel(const __grid_constant__ MapView m, const __grid_constant__ PlannerView p, const double *__restrict__ xyyaw,
                                                               const int64_t *__restrict__ offsets, size_t n_paths,
                                                               uint8_t *__restrict__ verdicts)
 {

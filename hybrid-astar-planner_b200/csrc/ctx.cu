@@ -90,8 +90,8 @@ extern "C" int mpros_ctx_destroy(mpros_ctx *c)
         return MPROS_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    void *bufs[] = {c->raw_bits, c->infl_bits, c->ds_bits, c->goal, c->obs_dist, c->edge_dist,
-                    c->region, c->edge_bits, c->voronoi, c->scratch, c->stage};
+    void *bufs[] = {c->raw_bits, c->infl_bits, c->ds_bits, c->goal, c->obs_dist, c->edge_dist, c->region,
+                    c->edge_bits, c->voronoi, c->scratch, c->stage, c->raw_tw, c->infl_tw};
     for (void *b : bufs)
         if (b)
             cudaFree(b);
@@ -205,6 +205,12 @@ extern "C" int mpros_planner_config(mpros_ctx *c, const mpros_planner_params *p)
         set_error("mpros_planner_config: length - width must be positive");
         return MPROS_ERR_INVALID;
     }
+    v.inv_n_check = 1.0 / (double)v.n_check;
+    v.fx_extent = v.n_check <= 512 ? std::fabs(L) + std::fabs(Wd) + std::fabs(off) : INFINITY;
+    // corners lie within |W| (> sqrt(2) * W / 2) of an axis end point
+    v.fx_slack = (int)std::ceil(std::fabs(Wd) / c->res0) + 2;
+    if (!(v.fx_slack < kTwMargin - 2) || !(Wd > 0) || !(L > 0))
+        v.fx_extent = INFINITY;
     // steer_set_ (hybrid_a_star.cpp:176-184)
     v.n_steer = 0;
     for (int i = 1; i <= num_pos_steer; ++i)

@@ -54,11 +54,10 @@ __device__ __forceinline__ bool pos_to_index_ds(const MapView &m, double x, doub
 //       i = 0..n, tested in the INFLATED map;
 //  (ii) the 4 rectangle corners x*c - y*s + px, x*s + y*c + py tested in the RAW map.
 // The verdict is an OR, so evaluation order / early exit do not change it.
-__device__ __forceinline__ bool footprint_in_collision4(const MapView &m, const PlannerView &p, double px, double py,
-                                                        double yaw)
+//
+// Reference arithmetic, probe by probe (FP64, two IEEE divisions per probe): the exact path, used as the fallback.
+static __device__ __noinline__ bool footprint_in_collision4_exact(const MapView &m, const PlannerView &p, double px, double py, double s, double c)
 {
-    double s, c;
-    sincos(yaw, &s, &c);
     // Eigen 2x2 * 2x2: a(i,0)*b(0,j) + a(i,1)*b(1,j) with b(1,j) == 0 -> the second term is a signed zero
     double x0 = c * p.longi_x0 + px, y0 = s * p.longi_x0 + py;
     double x1 = c * p.longi_x1 + px, y1 = s * p.longi_x1 + py;
@@ -70,7 +69,7 @@ __device__ __forceinline__ bool footprint_in_collision4(const MapView &m, const 
         if (point_hits_orig(m, m.infl_bits, ox * kk + x0, oy * kk + y0))
             return true;
     }
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < 4; ++k)
     {
         double cx = p.corner_x[k], cy = p.corner_y[k];
@@ -78,6 +77,92 @@ __device__ __forceinline__ bool footprint_in_collision4(const MapView &m, const 
             return true;
     }
     return false;
+}
+
+// Fast path. Only trunc(q) and the comparisons of q with -1 and the map size are ever used of a probe's grid
+// coordinates q = (rotated offset) / res. In real arithmetic q is LINEAR along the axis line, so the probes are walked in
+// 32.32 fixed point: Q(k) = Q(0) + k * dQ, cell = high word, no FP64 and no division per probe (~18 integer
+// instructions instead of ~80 FP64 ones). The reference's rounded q and this Q differ by at most
+//   128 * 2^-53 * (|x| + |y| + |origin| + footprint) / res  (FP64 roundings on both sides)  +  (n_check + 1) * 2^-32
+// cells, i.e. < 2^-24 + 2^-23 under the two preconditions checked below (pose within 2^22 cells of the origin,
+// n_check <= 512). If ANY probe's fractional part lies within kFxEps = 2^-22 of a cell edge the whole pose is decided by
+// the exact path (probability ~3e-5 per pose); everywhere else both values have the same trunc() and the same in-map
+// verdict. Verdicts stay bit-exact.
+//
+// The probes read the PADDED TILE-WORD copies of the two collision layers (MapView::raw_tw / infl_tw, built by
+// build_tilewords_kernel): a margin of kTwMargin cells around the map reads "occupied" (outside the map = collision,
+// nav_map.cpp:259-277) except the ring at index -1, which repeats cell 0 (truncation toward zero: q in (-1, 0) is cell 0).
+// So the loop needs no bounds test and no clamp. A 32-bit word holds 4 rows x 8 columns, a 32-byte sector 4 x 64 cells.
+constexpr uint32_t kFxEps = 1u << 10; // 2^-22 cell in units of 2^-32
+
+__device__ __forceinline__ uint32_t tw_probe(const uint32_t *__restrict__ tw, int pitch, long long qj, long long qi)
+{
+    const int hj = (int)(qj >> 32), hi = (int)(qi >> 32);
+    const uint32_t w = __ldg(tw + ((hi >> 2) * pitch + (hj >> 3)));
+    return w >> ((((unsigned)hi << 3) & 24u) | ((unsigned)hj & 7u));
+}
+// distance of the fractional parts from the nearest cell edge (wraps: 0 at an edge), running minimum
+__device__ __forceinline__ uint32_t tw_edge(uint32_t acc, long long qj, long long qi)
+{
+    return min(acc, min((uint32_t)qj + kFxEps, (uint32_t)qi + kFxEps));
+}
+
+__device__ __forceinline__ bool footprint_in_collision4_sc(const MapView &m, const PlannerView &p, double px, double py, double s, double c)
+{
+    const double x0 = c * p.longi_x0 + px, y0 = s * p.longi_x0 + py;
+    const double x1 = c * p.longi_x1 + px, y1 = s * p.longi_x1 + py;
+    // far away, a NaN anywhere in the pose (x0 / y0 carry px, py, sin and cos) or a footprint the fast path cannot take
+    if (!(fabs(x0) + fabs(y0) < m.fx_span - p.fx_extent))
+        return footprint_in_collision4_exact(m, p, px, py, s, c);
+    const double kTwo32 = 4294967296.0;
+    const double sc = m.inv_res0 * kTwo32;
+    const double jc = m.ocos * sc, js = m.osin * sc; // grid-j row of the scaled rotation; grid-i row is (-js, jc)
+    const double off = (double)kTwMargin * kTwo32;   // padded coordinates
+    const double ax0 = x0 - m.ox, ay0 = y0 - m.oy, ax1 = x1 - m.ox, ay1 = y1 - m.oy;
+    const double fj0 = ax0 * jc + ay0 * js + off, fi0 = ay0 * jc - ax0 * js + off;
+    const double fj1 = ax1 * jc + ay1 * js + off, fi1 = ay1 * jc - ax1 * js + off;
+    long long qj = __double2ll_rd(fj0), qi = __double2ll_rd(fi0);
+    // both axis end points at least fx_slack cells inside the padded array: then every probe and corner is inside it
+    {
+        const long long ej = __double2ll_rd(fj1), ei = __double2ll_rd(fi1);
+        const unsigned lim_j = (unsigned)(m.W0 + 2 * kTwMargin - 2 * p.fx_slack), lim_i = (unsigned)(m.H0 + 2 * kTwMargin - 2 * p.fx_slack);
+        const bool in = ((unsigned)((int)(qj >> 32) - p.fx_slack) < lim_j) & ((unsigned)((int)(ej >> 32) - p.fx_slack) < lim_j) &
+                        ((unsigned)((int)(qi >> 32) - p.fx_slack) < lim_i) & ((unsigned)((int)(ei >> 32) - p.fx_slack) < lim_i);
+        if (!in)
+            return footprint_in_collision4_exact(m, p, px, py, s, c);
+    }
+    const long long dj = __double2ll_rn((fj1 - fj0) * p.inv_n_check), di = __double2ll_rn((fi1 - fi0) * p.inv_n_check);
+    uint32_t any = 0, edge = 0xffffffffu;
+    const int n = p.n_check;
+#pragma unroll 4
+    for (int k = 0; k <= n; ++k)
+    {
+        any |= tw_probe(m.infl_tw, m.tw_pitch, qj, qi);
+        edge = tw_edge(edge, qj, qi);
+        qj += dj;
+        qi += di;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+        const double cx = p.corner_x[k], cy = p.corner_y[k];
+        const double X = cx * c - cy * s + px, Y = cx * s + cy * c + py; // as the reference computes them
+        const double ax = X - m.ox, ay = Y - m.oy;
+        const long long cj = __double2ll_rd(ax * jc + ay * js + off), ci = __double2ll_rd(ay * jc - ax * js + off);
+        any |= tw_probe(m.raw_tw, m.tw_pitch, cj, ci);
+        edge = tw_edge(edge, cj, ci);
+    }
+    if (edge < 2 * kFxEps) // some probe too close to a cell edge to trust the fixed-point walk
+        return footprint_in_collision4_exact(m, p, px, py, s, c);
+    return (any & 1u) != 0;
+}
+
+__device__ __forceinline__ bool footprint_in_collision4(const MapView &m, const PlannerView &p, double px, double py,
+                                                        double yaw)
+{
+    double s, c;
+    sincos(yaw, &s, &c);
+    return footprint_in_collision4_sc(m, p, px, py, s, c);
 }
 
 } // namespace mpros

@@ -260,6 +260,49 @@ __global__ void point_lookup_kernel(const uint32_t *__restrict__ bits, int H, in
     }
 }
 
+// Padded tile-word copy of a bit-packed collision layer for the fixed-point footprint walk (layout: MapView::raw_tw).
+// Outside the map reads 1 (collision) except index -1, which repeats cell 0 (truncation toward zero).
+__global__ void __launch_bounds__(256) build_tilewords_kernel(const uint32_t *__restrict__ bits, int H, int W, int pitch,
+                                                              uint32_t *__restrict__ tw, int tw_pitch, int tw_rows)
+{
+    const size_t total = (size_t)tw_pitch * tw_rows;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x)
+    {
+        const int wi = (int)(t / tw_pitch), wj = (int)(t % tw_pitch);
+        const int j0 = wj * 8 - kTwMargin; // multiple of 8
+        uint32_t v = 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+        {
+            int i = wi * 4 + r - kTwMargin;
+            if (i == -1)
+                i = 0;
+            uint32_t row = 0xffu;
+            if (i >= 0 && i < H)
+            {
+                if (j0 >= 0 && j0 + 8 <= W)
+                    row = (bits[(size_t)i * pitch + (j0 >> 5)] >> (j0 & 31)) & 0xffu;
+                else
+                {
+                    row = 0;
+                    for (int cc = 0; cc < 8; ++cc)
+                    {
+                        int j = j0 + cc;
+                        if (j == -1)
+                            j = 0;
+                        uint32_t b = 1;
+                        if (j >= 0 && j < W)
+                            b = (bits[(size_t)i * pitch + (j >> 5)] >> (j & 31)) & 1u;
+                        row |= b << cc;
+                    }
+                }
+            }
+            v |= row << (8 * r);
+        }
+        tw[t] = v;
+    }
+}
+
 static int grid_for(size_t work_items, int block = 256)
 {
     size_t g = (work_items + block - 1) / block;
@@ -282,6 +325,22 @@ static int realloc_layers(Ctx *c)
         MPROS_CUDA(cudaMalloc(&c->infl_bits, words0 * 4));
         // raw_bits is re-created by the caller (it needs the old content for relinearisation)
         c->cap0_words = words0;
+    }
+    {
+        c->tw_pitch = (c->W0 + 2 * kTwMargin + 7) / 8;
+        const int tw_rows = (c->H0 + 2 * kTwMargin + 3) / 4;
+        size_t tw_words = (size_t)c->tw_pitch * tw_rows;
+        if (tw_words > c->cap_tw)
+        {
+            if (c->raw_tw)
+                MPROS_CUDA(cudaFree(c->raw_tw));
+            if (c->infl_tw)
+                MPROS_CUDA(cudaFree(c->infl_tw));
+            c->raw_tw = c->infl_tw = nullptr;
+            MPROS_CUDA(cudaMalloc(&c->raw_tw, tw_words * 4));
+            MPROS_CUDA(cudaMalloc(&c->infl_tw, tw_words * 4));
+            c->cap_tw = tw_words;
+        }
     }
     if (words > c->cap_words)
     {
@@ -450,6 +509,15 @@ static int set_occupancy_impl(Ctx *c, const int8_t *d_data, int width, int heigh
             }
             MPROS_LAUNCH_CHECK(c);
         }
+    }
+    // padded tile-word copies of the two collision layers
+    {
+        const int tw_rows = (c->H0 + 2 * kTwMargin + 3) / 4;
+        const size_t tw_words = (size_t)c->tw_pitch * tw_rows;
+        build_tilewords_kernel<<<grid_for(tw_words), 256, 0, st>>>(c->raw_bits, c->H0, c->W0, c->pitch0, c->raw_tw, c->tw_pitch, tw_rows);
+        MPROS_LAUNCH_CHECK(c);
+        build_tilewords_kernel<<<grid_for(tw_words), 256, 0, st>>>(c->infl_bits, c->H0, c->W0, c->pitch0, c->infl_tw, c->tw_pitch, tw_rows);
+        MPROS_LAUNCH_CHECK(c);
     }
     // the reference sets get_map_ at the very end but the sub-steps below only need the geometry
     c->get_map = true;

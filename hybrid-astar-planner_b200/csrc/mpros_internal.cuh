@@ -1,6 +1,7 @@
 // Internal definitions shared by the CUDA translation units of libmpros_b200.so (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cmath>
 #include <stdint.h>
 #include <string>
 #include <vector>
@@ -11,6 +12,7 @@ namespace mpros
 {
 
 constexpr int kHugeInt = 1000; // HUGE_INT, mpros_navigation_map/node.h:4
+constexpr int kTwMargin = 256;  // cells of "outside the map" padding around the tile-word collision layers
 
 // ---- HBM layout of one map (all device pointers) -------------------------------------------------------
 // Occupancy layers are BIT-PACKED: bit (j & 31) of word [i * pitch + (j >> 5)] is cell (i, j); bits past
@@ -23,12 +25,19 @@ struct MapView
     const uint32_t *raw_bits;  // static_map_orig_      [H0 x pitch0]
     const uint32_t *infl_bits; // inflate_map_orig_     [H0 x pitch0]
     const uint32_t *ds_bits;   // static_map_           [H  x pitch ]
+    // the two collision layers again as padded TILE WORDS for the fixed-point footprint walk (map_device.cuh): cell
+    // (i, j) is bit ((pi & 3) << 3) | (pj & 7) of word [(pi >> 2) * tw_pitch + (pj >> 3)], (pi, pj) = (i, j) + kTwMargin
+    const uint32_t *raw_tw, *infl_tw;
+    int tw_pitch;
     const float *voronoi;      // voronoi_value_map_    [H*W]
     const uint16_t *goal;      // goal_cost_map_ as u16 [H*W] (single-goal context map)
     int H0, W0, pitch0;
     int H, W, pitch;
     double ox, oy, osin, ocos; // map_origin_x_/y_/sin_/cos_
     double res0, res;          // map_resolution_orig_, map_resolution_
+    // fixed-point fast path of the footprint test (map_device.cuh: footprint_in_collision4): RN(1 / res0) and the
+    // largest |x| + |y| of a pose for which the error bound of that path holds (2^22 cells minus the origin offset)
+    double inv_res0, fx_span;
 };
 
 // ---- per-planner constants (HybridAstar::config / setFootprint, hybrid_a_star.cpp:120-206) -----------
@@ -39,6 +48,10 @@ struct PlannerView
     double longi_x0, longi_x1;
     double corner_x[4], corner_y[4];
     int n_check; // num_checking_step = ceil((L - W) / res_orig), hybrid_a_star.cpp:633
+    // fixed-point fast path: 1 / n_check and the footprint's reach (subtracted from MapView::fx_span); fx_extent is
+    // +inf when the path may not be used (n_check > 512)
+    double inv_n_check, fx_extent;
+    int fx_slack; // cells an axis end point must keep from the border of the padded layers (covers the corners)
     // expansion
     int n_steer; // steer_set_.size()
     double steer_set[kMaxSteer];
@@ -72,6 +85,9 @@ struct Ctx
 
     // device buffers
     uint32_t *raw_bits = nullptr, *infl_bits = nullptr, *ds_bits = nullptr;
+    uint32_t *raw_tw = nullptr, *infl_tw = nullptr; // derived from raw_bits / infl_bits (build_tilewords_kernel)
+    int tw_pitch = 0;
+    size_t cap_tw = 0;
     uint16_t *goal = nullptr, *obs_dist = nullptr, *edge_dist = nullptr;
     int32_t *region = nullptr;
     uint32_t *edge_bits = nullptr;
@@ -91,6 +107,9 @@ struct Ctx
         v.raw_bits = raw_bits;
         v.infl_bits = infl_bits;
         v.ds_bits = ds_bits;
+        v.raw_tw = raw_tw;
+        v.infl_tw = infl_tw;
+        v.tw_pitch = tw_pitch;
         v.voronoi = voronoi;
         v.goal = goal;
         v.H0 = H0;
@@ -105,6 +124,10 @@ struct Ctx
         v.ocos = ocos;
         v.res0 = res0;
         v.res = res;
+        v.inv_res0 = 1.0 / res0;
+        v.fx_span = 4194304.0 * res0 - (std::fabs(ox) + std::fabs(oy));
+        if ((unsigned long long)(H0 + 2 * kTwMargin) * (unsigned long long)(W0 + 2 * kTwMargin) >= (1ull << 36)) // 32-bit word index
+            v.fx_span = -1.0;
         return v;
     }
 };

@@ -81,15 +81,42 @@ struct PlanBatchArgs
     int optimal;
 };
 
+// Phase profile of the team planner (developer build only: make PROFILE=1). Cycle counts are taken by thread 0 of the
+// compute group and lane 0 of the heap warp and summed over all queries.
 #ifdef MPROS_PROFILE
-__device__ unsigned long long g_prof[8];
-#define PROF_DECL long long pt0 = clock64(), pt1; long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#define PROF_MARK(k) do { pt1 = clock64(); pacc[k] += pt1 - pt0; pt0 = pt1; } while (0)
-#define PROF_FLUSH do { if (threadIdx.x == 0) for (int k_ = 0; k_ < 8; ++k_) atomicAdd(&g_prof[k_], (unsigned long long)pacc[k_]); } while (0)
+__device__ unsigned long long g_prof[24];
+struct Prof
+{
+    long long t0;
+    unsigned long long *acc; // 24 accumulators in shared memory (TeamShared::prof); each slot has ONE writing thread
+    static __device__ __forceinline__ long long now()
+    {
+        long long t;
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+        return t;
+    }
+    __device__ __forceinline__ void start(unsigned long long *a)
+    {
+        acc = a;
+        t0 = now();
+    }
+    __device__ __forceinline__ void restart() { t0 = now(); }
+    __device__ __forceinline__ void mark(int k)
+    {
+        long long t1 = now();
+        acc[k] += (unsigned long long)(t1 - t0);
+        t0 = t1;
+    }
+    __device__ __forceinline__ void count(int k) { acc[k] += 1; }
+};
 #else
-#define PROF_DECL
-#define PROF_MARK(k)
-#define PROF_FLUSH
+struct Prof
+{
+    __device__ __forceinline__ void start(unsigned long long *) {}
+    __device__ __forceinline__ void restart() {}
+    __device__ __forceinline__ void mark(int) {}
+    __device__ __forceinline__ void count(int) {}
+};
 #endif
 
 // status codes of mpros_plan_batch (include/mpros_gpu.h)
@@ -135,7 +162,7 @@ struct RsBatchArgs
     RsConfig rs;
 };
 
-__global__ void __launch_bounds__(128) rs_batch_kernel(MapView m, PlannerView p, RsBatchArgs a)
+__global__ void __launch_bounds__(128) rs_batch_kernel(const __grid_constant__ MapView m, const __grid_constant__ PlannerView p, RsBatchArgs a)
 {
     const int lane = threadIdx.x & 31;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -225,7 +252,7 @@ struct ExpandArgs
     int have_seeds;
 };
 
-__global__ void __launch_bounds__(128) expand_batch_kernel(MapView m, PlannerView p, ExpandArgs a)
+__global__ void __launch_bounds__(128) expand_batch_kernel(const __grid_constant__ MapView m, const __grid_constant__ PlannerView p, ExpandArgs a)
 {
     const int lane = threadIdx.x & 31;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -684,15 +711,20 @@ static int plan_pass(mpros_ctx *c, PlanBatchArgs &a, int pass, int node_cap, int
         cudaEventElapsedTime(&ms, e0, e1);
 #ifdef MPROS_PROFILE
         {
-            unsigned long long h[8];
+            unsigned long long h[24];
             cudaMemcpyFromSymbol(h, g_prof, sizeof(h));
-            unsigned long long z[8] = {0};
+            unsigned long long z[24] = {0};
             cudaMemcpyToSymbol(g_prof, z, sizeof(z));
-            double tot = 0;
-            for (int k = 0; k < 8; ++k)
-                tot += (double)h[k];
-            std::fprintf(stderr, "[mpros] cycles%%: pop %.1f shot %.1f children+collision %.1f survivors %.1f h1 %.1f h2 %.1f insert %.1f loop %.1f (total %.3g team-cycles)\n",
-                         100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot, 100 * h[6] / tot, 100 * h[4] / tot, 100 * h[5] / tot, 100 * h[7] / tot, tot);
+            const char *names[12] = {"wait_pop", "shot", "expand", "h1_peek", "bfs_steps", "h2_roundA", "h2_roundB", "h2_tail", "insert", "wait_heap",
+                                     "heap_pop", "heap_restore"};
+            double its = (double)h[12];
+            std::fprintf(stderr, "[mpros] profile: %.0f iterations, %.3f bfs steps/it, %.3f roundB/it, %.4f shots/it; cycles per iteration:\n", its,
+                         h[13] / its, h[14] / its, h[15] / its);
+            for (int k = 0; k < 12; ++k)
+                std::fprintf(stderr, "[mpros]   %-12s %9.1f\n", names[k], h[k] / its);
+            const char *names2[8] = {"col:pose+sincos", "col:footprint", "closed:probe+peek", "closed:images", "", "", "", ""};
+            for (int k = 16; k < 20; ++k)
+                std::fprintf(stderr, "[mpros]   %-18s %9.1f\n", names2[k - 16], h[k] / its);
         }
 #endif
         std::fprintf(stderr, "[mpros] plan pass %d: %d queries, node_cap %d, %d teams x %d warps, %.1f MB/team, %.3f ms\n", pass, n_run,

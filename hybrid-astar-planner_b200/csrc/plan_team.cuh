@@ -77,6 +77,9 @@ struct TeamShared
     unsigned char traj_hit[kTrajCap];
     double traj[kTrajCap * 5]; // kTrajCap x 3 {x, y, yaw}, then kTrajCap x 2 {steer, dir}
     TeamBfs bfs;
+#ifdef MPROS_PROFILE
+    unsigned long long prof[24];
+#endif
 };
 
 // barrier of the compute group (every warp except the heap warp)
@@ -290,7 +293,7 @@ __device__ __forceinline__ int team_bfs_peek(const MapView &m, const TeamBfs &b,
 
 // goal-map values for the slots flagged c_need whose c_h1 is still unknown (< 0): advance the wavefront until final
 template <int NW>
-__device__ __forceinline__ void team_h1_lookup(const MapView &m, TeamShared<NW> &S)
+__device__ __forceinline__ void team_h1_lookup(const MapView &m, TeamShared<NW> &S, Prof &pf)
 {
     const int tid = threadIdx.x;
     while (true)
@@ -308,8 +311,12 @@ __device__ __forceinline__ void team_h1_lookup(const MapView &m, TeamShared<NW> 
         team_sync<NW>();
         if (!S.bfs_more)
             break;
+        if (threadIdx.x == 0) pf.mark(3);
         team_bfs_step<NW>(m, S.bfs);
+        if (threadIdx.x == 0) pf.mark(4);
+        if (threadIdx.x == 0) pf.count(13);
     }
+    if (threadIdx.x == 0) pf.mark(3);
 }
 
 // symmetry image q of the normalised goal seen from pose (x, y, yaw) into slot c (consumed by team_heuristics)
@@ -325,7 +332,7 @@ __device__ __forceinline__ void team_image(const PlannerView &p, TeamShared<NW> 
 
 // heuristics (hybrid_a_star.cpp:248-264) of the slots flagged c_need: h = max(h1 * res, RS distance) * 1.001
 template <int NW>
-__device__ __forceinline__ void team_heuristics(const MapView &m, const PlannerView &p, TeamShared<NW> &S)
+__device__ __forceinline__ void team_heuristics(const MapView &m, const PlannerView &p, TeamShared<NW> &S, Prof &pf)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0)
@@ -369,9 +376,11 @@ __device__ __forceinline__ void team_heuristics(const MapView &m, const PlannerV
             S.h_skip = all;
         }
         team_sync<NW>();
+        if (threadIdx.x == 0) pf.mark(5);
         // round B: CCC, CCCC, CCSC, CCSCC
         if (!S.h_skip)
         {
+            if (threadIdx.x == 0) pf.count(14);
 #pragma unroll 1
             for (int s = 0; s < team_formula_b_slots<NW>(); ++s)
             {
@@ -386,6 +395,7 @@ __device__ __forceinline__ void team_heuristics(const MapView &m, const PlannerV
             }
         }
         team_sync<NW>();
+        if (threadIdx.x == 0) pf.mark(6);
     }
     if (tid < hn)
     {
@@ -396,6 +406,7 @@ __device__ __forceinline__ void team_heuristics(const MapView &m, const PlannerV
         S.c_h[c] = fmax(h1, h2) * (1 + 1e-3);
     }
     team_sync<NW>();
+    if (threadIdx.x == 0) pf.mark(7);
 }
 
 // Reeds-Shepp shot from (x, y, yaw, dir, steer) to the goal: FindOptimalPath + GenTraj into S.traj (compute group).
@@ -526,6 +537,15 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
     closed.slot = reinterpret_cast<ClosedSlot *>(ws + L.table_off);
     closed.mask = (uint32_t)L.table_slots - 1;
     closed.tag = tag;
+    Prof pf; // phase profile (developer build): thread 0, lane 0 of the heap warp and lane 0 of the closed-set warp write
+#ifdef MPROS_PROFILE
+    if (tid < 24)
+        S.prof[tid] = 0;
+    __syncthreads();
+    const bool pf_on = tid == 0 || (lane == 0 && (warp == HEAP_W || warp == CLOSED_W));
+    pf.start(S.prof);
+    (void)pf_on;
+#endif
 
     if (tid == 0)
     {
@@ -584,8 +604,8 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
             if (tid >= 32 && tid < 36)
                 team_image<NW>(p, S, 0, tid - 32, S.sx, S.sy, S.syaw);
             team_sync<NW>();
-            team_h1_lookup<NW>(m, S);
-            team_heuristics<NW>(m, p, S);
+            team_h1_lookup<NW>(m, S, pf);
+            team_heuristics<NW>(m, p, S, pf);
             if (tid == 0)
             {
                 PlanNode n;
@@ -612,6 +632,7 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
     }
     __syncthreads();
     const bool init_ok = S.init_ok != 0;
+    pf.restart();
 
     // ---- Plan() (hybrid_a_star.cpp:682-777) ----
     const int P = 2 * p.n_steer;
@@ -680,6 +701,7 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                     }
                 }
             }
+            if (is_heap && lane == 0) pf.mark(10);
             if (lane == 0)
             {
                 S.flag = flag;
@@ -714,10 +736,13 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                     __syncwarp();
                 }
             }
+            if (is_heap && lane == 0) pf.mark(11);
         }
         else
         {
             __syncthreads(); // (a)
+            if (tid == 0) pf.mark(0);
+            if (tid == 0) pf.count(12);
         }
         if (S.flag != 0)
             break;
@@ -777,7 +802,10 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                     }
                 }
                 team_sync<NW>();
+                if (tid == 0) pf.count(15);
             }
+            if (tid == 0) pf.mark(1);
+            pf.restart();
             if (S.shot_ok)
             {
                 if (!a.optimal && tid == 0)
@@ -803,7 +831,9 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                         }
                         nx = __shfl_sync(kFull, nx, 0), ny = __shfl_sync(kFull, ny, 0);
                         ns = __shfl_sync(kFull, ns, 0), nc = __shfl_sync(kFull, nc, 0);
+                        if (tid == 0) pf.mark(16);
                         bool hit = warp_footprint_collision(m, p, nx, ny, ns, nc);
+                        if (tid == 0) pf.mark(17);
                         if (lane == 0)
                         {
                             S.c_x[c] = nx, S.c_y[c] = ny, S.c_yaw[c] = nyaw, S.c_s[c] = ns, S.c_c[c] = nc;
@@ -814,6 +844,7 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                 }
                 else if (warp == CLOSED_W)
                 {
+                    pf.restart();
                     if (lane < P)
                     {
                         const int c = lane;
@@ -837,6 +868,8 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                         S.c_cand[c] = cand;
                         S.c_h1[c] = h1;
                     }
+                    __syncwarp();
+                    if (warp == CLOSED_W && lane == 0) pf.mark(18);
                     for (int t = lane; t < 4 * P; t += 32)
                     {
                         const int c = t >> 2;
@@ -844,6 +877,8 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                         primitive_end_pose(p, c, cn.x, cn.y, cn.yaw, cn.s, cn.c, nx, ny, nyaw, steer, direc);
                         team_image<NW>(p, S, c, t & 3, nx, ny, nyaw);
                     }
+                    __syncwarp();
+                    if (warp == CLOSED_W && lane == 0) pf.mark(19);
                 }
                 if (tid == 0)
                 {
@@ -854,8 +889,9 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                 team_sync<NW>();
                 if (tid < P)
                     S.c_need[tid] = S.c_alive[tid] && S.c_cand[tid];
-                team_h1_lookup<NW>(m, S); // starts with a barrier
-                team_heuristics<NW>(m, p, S);
+                if (tid == 0) pf.mark(2);
+                team_h1_lookup<NW>(m, S, pf); // starts with a barrier
+                team_heuristics<NW>(m, p, S, pf);
                 // closed-set compare / insert in primitive order (closed-set warp). Common case: the children that need an
                 // insert touch distinct hash slots -> slot / node stores and close-marks run one lane per child, the new open
                 // entries go to the insertion buffer. Children that collide on a slot (same index, or two new keys probing
@@ -937,6 +973,7 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                     }
                 }
                 team_sync<NW>();
+                if (tid == 0) pf.mark(8);
                 if (tid == 0 && S.overflow)
                     S.stop = 1;
             }
@@ -949,9 +986,20 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
             }
         }
         __syncthreads(); // (b) inserts are in the buffer, the heap is consistent again
+        if (!is_heap)
+        {
+            if (tid == 0) pf.mark(9);
+        }
+        else
+            pf.restart();
         if (S.stop)
             break;
     }
+#ifdef MPROS_PROFILE
+    __syncthreads();
+    if (tid < 24 && S.prof[tid])
+        atomicAdd(&g_prof[tid], S.prof[tid]);
+#endif
 
     // ---- status + raw path_ of setPath (hybrid_a_star.cpp:779-811) ----
     int status = ST_NOT_INIT;

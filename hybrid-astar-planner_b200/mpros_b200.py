@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("MPROS_LIB", os.path.join(HERE, "libmpros_b200.so"))
+LIB_PATH = os.environ.get("MPROS_LIB", os.path.join(HERE, "libmpros_b200.so"))  # MPROS_LIB: developer builds (phase profile)
 
 LAYERS = {
     "static_orig": (0, np.int8, True),

@@ -17,6 +17,8 @@ for rep in range(2):
     r = ctx.plan_batch(s, g, path_cap=128)
     print("plan_batch wall %.3f s" % (time.perf_counter() - t0))
 it = r["iterations"]
+if os.environ.get("MPROS_SAVE"):
+    np.savez_compressed(os.environ["MPROS_SAVE"], starts=s, goals=g, **{k: v for k, v in r.items() if isinstance(v, np.ndarray) and v.ndim == 1})
 print("status counts", {int(k): int((r["status"] == k).sum()) for k in np.unique(r["status"])})
 print("iterations: mean %.1f median %.1f p90 %.0f p99 %.0f max %d" % (it.mean(), np.median(it), np.percentile(it, 90), np.percentile(it, 99), it.max()))
 print("nodes inserted: mean %.1f p90 %.0f p99 %.0f max %d" % (r["nodes_inserted"].mean(), np.percentile(r["nodes_inserted"], 90), np.percentile(r["nodes_inserted"], 99), r["nodes_inserted"].max()))

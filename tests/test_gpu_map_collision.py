@@ -81,6 +81,10 @@ def test_collision_verdicts_bit_exact(reflib, gpu_ctx_factory, name, ds, goal):
     poses[:k, 0] = np.round(poses[:k, 0] / m["resolution"]) * m["resolution"]
     poses[:k, 1] = np.round(poses[:k, 1] / m["resolution"]) * m["resolution"]
     poses[: k // 2, 2] = rng.choice([0.0, np.pi / 2, -np.pi / 2, np.pi, 1.57, 3.14], k // 2)
+    # far-away, non-finite and huge-yaw poses (the fixed-point fast path must hand these to the exact path)
+    odd = np.array([[1e7, 1e7, 0.1], [4.2e5, 0.0, 0.0], [-4.2e5, 3.0, 1.0], [np.nan, 1.0, 0.0], [1.0, np.inf, 0.0], [5.0, 5.0, np.nan],
+                    [5.0, 5.0, np.inf], [1e300, -1e300, 2.0], [5.0, 5.0, 1e10], [-1e-320, 5.0, 0.0], [2.0 ** 22 * m["resolution"], 1.0, 0.3]])
+    poses[-len(odd):] = odd
     want = rp.collision4(poses)
     got = ctx.collision_check(poses)
     assert 0.02 < want.mean() < 0.999
