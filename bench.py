@@ -440,7 +440,7 @@ def run_b200(args):
                             "d2h_bytes_per_step": nq * (4 + 8 + 4 + PATH_CAP * 40 + 48)},
                     "gpu_launches": int(launches),
                     "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                                 "kernel": "plan_batch_kernel", "kernel_ms": k_ms, "peak_source": peak_kind,
+                                 "kernel": "plan_team_kernel", "kernel_ms": k_ms, "peak_source": peak_kind,
                                  "algorithmic_bytes_per_launch": algo_bytes,
                                  "note": "latency/FP64-issue bound (sequential A* per query, FP64 transcendentals), not HBM bound; see DESIGN.md"},
                     "extra": {"node_expansions_per_sec": expansions_all / secs, "footprint_checks_per_sec_in_planning": checks_all / secs,
@@ -450,7 +450,7 @@ def run_b200(args):
                               "plans_found": n_found, "plans_iteration_limit": n_limit, "plans_failed_other": n_fail,
                               "mean_expansions_per_query": expansions_all / (world * nq)},
                     "config": {"workload": workload_text("plan"), "queries_per_gpu": nq, "path_cap": PATH_CAP,
-                               "l2_policy": "per-query working sets live in a %d MB-per-warp HBM workspace (>> L2 in aggregate); map layers are L2-resident by design" % 3,
+                               "l2_policy": "per-query working sets (node pool, open list, closed set, goal wavefront) live in a ~110 MB-per-team HBM workspace, 296 teams (>> L2 in aggregate); map layers are L2-resident by design",
                                "preprocess_s_first_call": t_pre}}
 
     if rank == 0 and line is not None:

@@ -165,6 +165,36 @@ __global__ void __launch_bounds__(256) downsample_kernel(const uint32_t *__restr
     }
 }
 
+// Fast path of N2 when ds is a power of two <= 32 that divides both map dimensions (then none of the off-by-one quirks
+// above can trigger): one thread per OUTPUT word = ds input rows x ds input words; groups of ds bits are OR-folded in
+// the word and their representatives gathered. Reads every input word exactly once, coalesced.
+__global__ void __launch_bounds__(256) downsample_pow2_kernel(const uint32_t *__restrict__ raw, int pitch0, uint32_t *__restrict__ out,
+                                                              int H, int W, int pitch, int ds, int log2ds)
+{
+    const int words_per_row = (W + 31) >> 5;
+    const size_t total_words = (size_t)H * words_per_row;
+    const int per = 32 >> log2ds; // output bits produced by one input word
+    for (size_t wd = (size_t)blockIdx.x * blockDim.x + threadIdx.x; wd < total_words; wd += (size_t)gridDim.x * blockDim.x)
+    {
+        const int i = (int)(wd / words_per_row), w = (int)(wd % words_per_row);
+        const int in_words = min(ds, (W - (w << 5) + per - 1) / per); // input words that carry cells of this output word
+        uint32_t word = 0;
+        for (int q = 0; q < in_words; ++q)
+        {
+            uint32_t v = 0;
+            for (int a = 0; a < ds; ++a)
+                v |= __ldg(raw + (size_t)(i * ds + a) * pitch0 + (size_t)w * ds + q);
+            for (int sh = 1; sh < ds; sh <<= 1) // bit 0 of every group of ds bits = OR of the group
+                v |= v >> sh;
+            uint32_t g = 0;
+            for (int t = 0; t < per; ++t)
+                g |= ((v >> (t << log2ds)) & 1u) << t;
+            word |= g << (q * per);
+        }
+        out[(size_t)i * pitch + w] = word;
+    }
+}
+
 // ---- N3: NavMap::inflateObstacle (nav_map.cpp:164-214) ----------------------------------------------------
 // Binary dilation by SE = {(di,dj): (|di|-1/2)^2 + (|dj|-1/2)^2 <= r^2}, clipped to the map. The SE is
 // monotone in |di| and |dj|, so SE = union over column offsets s of the vertical run |di| <= a(|s|).
@@ -176,13 +206,14 @@ __constant__ int16_t c_ext_tab[kMaxInflRadius + 1];
 
 template <int K, bool SMALL> // K = words of halo on each side; SMALL: smax <= 31, all shifts stay within +-1 word
 __global__ void __launch_bounds__(256) inflate_kernel(const uint32_t *__restrict__ raw, uint32_t *__restrict__ out, int H,
-                                                      int W, int pitch, int smax)
+                                                      int W, int pitch, int smax, int row0, int nrows)
 {
+    // output rows [row0, row0 + nrows) (a row band when the map is tiled across GPUs); input rows are clipped to the map
     const int words_per_row = (W + 31) >> 5;
-    const size_t total = (size_t)H * words_per_row;
+    const size_t total = (size_t)nrows * words_per_row;
     for (size_t wd = (size_t)blockIdx.x * blockDim.x + threadIdx.x; wd < total; wd += (size_t)gridDim.x * blockDim.x)
     {
-        int i = (int)(wd / words_per_row), w = (int)(wd % words_per_row);
+        int i = row0 + (int)(wd / words_per_row), w = (int)(wd % words_per_row);
         uint32_t V[2 * K + 2]; // V[k] = OR over current rows of word w - K + k; one spare so V[q+1] is always valid
 #pragma unroll
         for (int k = 0; k < 2 * K + 2; ++k)
@@ -370,8 +401,10 @@ static int realloc_layers(Ctx *c)
     return MPROS_OK;
 }
 
-static int set_occupancy_impl(Ctx *c, const int8_t *d_data, int width, int height, double resolution, double ox, double oy,
-                              double oyaw)
+// ---- NavMap::setOccupancyMap in stages, so that a row band can be processed per GPU (mpros_map_band_*) -------------
+// stage 0: geometry + allocation (nav_map.cpp:54-112). Returns whether an earlier map's cells must be merged (the
+// reference only overwrites cells that are definitely occupied or definitely free, :114-131).
+static int map_begin(Ctx *c, int width, int height, double resolution, double ox, double oy, double oyaw, int *have_old_out)
 {
     cudaStream_t st = c->stream;
     const bool first = !c->get_map;
@@ -415,29 +448,115 @@ static int set_occupancy_impl(Ctx *c, const int8_t *d_data, int width, int heigh
     }
     else
         have_old = 1;
+    // padding words/bits must stay zero: clear the layer when there is no old state to merge
+    if (!have_old)
+        MPROS_CUDA(cudaMemsetAsync(c->raw_bits, 0, (size_t)c->H0 * c->pitch0 * 4, st));
+    *have_old_out = have_old;
+    return MPROS_OK;
+}
 
-    // N1 (exact integer form of the double comparisons against free_thres_)
+// stage 1 (N1) for rows [row0, row0 + nrows): d_rows points at the first of these rows
+static int map_threshold_rows(Ctx *c, const int8_t *d_rows, int row0, int nrows, int have_old)
+{
+    cudaStream_t st = c->stream;
+    const int width = c->W0;
+    // exact integer form of the double comparisons against free_thres_
     const double t = c->mp.free_thresh;
     double occ_min_d = std::floor(t) + 1.0, free_max_d = std::ceil(t) - 1.0;
     int occ_min = occ_min_d > 200 ? 200 : (occ_min_d < -200 ? -200 : (int)occ_min_d);
     int free_max = free_max_d > 200 ? 200 : (free_max_d < -200 ? -200 : (int)free_max_d);
-    // padding words/bits must stay zero: clear the layer when there is no old state to merge
-    if (!have_old)
-        MPROS_CUDA(cudaMemsetAsync(c->raw_bits, 0, (size_t)c->H0 * c->pitch0 * 4, st));
-    if ((width % 32) == 0 && (reinterpret_cast<uintptr_t>(d_data) % 16) == 0)
+    uint32_t *bits = c->raw_bits + (size_t)row0 * c->pitch0;
+    if ((width % 32) == 0 && (reinterpret_cast<uintptr_t>(d_rows) % 16) == 0)
     {
-        size_t words = (size_t)height * (width >> 5);
-        threshold_pack_vec_kernel<<<grid_for(words), 256, 0, st>>>(d_data, c->raw_bits, height, width, c->pitch0, occ_min,
-                                                                      free_max, have_old);
+        size_t words = (size_t)nrows * (width >> 5);
+        threshold_pack_vec_kernel<<<grid_for(words), 256, 0, st>>>(d_rows, bits, nrows, width, c->pitch0, occ_min, free_max, have_old);
     }
     else
     {
-        size_t words = (size_t)height * ((width + 31) / 32);
-        threshold_pack_kernel<<<grid_for(words * 32), 256, 0, st>>>(d_data, c->raw_bits, height, width, c->pitch0, occ_min,
-                                                                  free_max, have_old);
+        size_t words = (size_t)nrows * ((width + 31) / 32);
+        threshold_pack_kernel<<<grid_for(words * 32), 256, 0, st>>>(d_rows, bits, nrows, width, c->pitch0, occ_min, free_max, have_old);
     }
     MPROS_LAUNCH_CHECK(c);
+    return MPROS_OK;
+}
 
+// stage 2a (N3 set-up): structuring-element table exactly as the reference evaluates it (quarter-integers, exact in
+// double). smax = widest column offset of the SE (-1: empty SE, radius 0 inflates nothing); *radius_px = rows of halo.
+static int map_inflate_prepare(Ctx *c, int *smax_out, int *radius_px)
+{
+    int r = (int)std::ceil(c->mp.obstacle_inflation_radius / c->res0);
+    if (r < 0)
+        r = 0;
+    if (r > kMaxInflRadius)
+    {
+        set_error("obstacle_inflation_radius / resolution exceeds 255 pixels (unsupported)");
+        return MPROS_ERR_INVALID;
+    }
+    double r_sq = r * r;
+    int16_t tab[kMaxInflRadius + 1];
+    int smax = -1;
+    for (int s = 0; s <= kMaxInflRadius; ++s)
+    {
+        tab[s] = -1;
+        if (s > r)
+            continue;
+        double j_dist = std::abs(s) - 0.5;
+        for (int a = 0; a <= r; ++a)
+        {
+            double i_dist = std::abs(a) - 0.5;
+            if (i_dist * i_dist + j_dist * j_dist <= r_sq)
+                tab[s] = (int16_t)a;
+        }
+        if (tab[s] >= 0)
+            smax = s;
+    }
+    MPROS_CUDA(cudaMemcpyToSymbolAsync(c_ext_tab, tab, sizeof(tab), 0, cudaMemcpyHostToDevice, c->stream));
+    *smax_out = smax;
+    if (radius_px)
+        *radius_px = r;
+    return MPROS_OK;
+}
+
+// stage 2b (N3) for output rows [row0, row0 + nrows); reads raw rows up to the SE radius beyond the band
+static int map_inflate_rows(Ctx *c, int smax, int row0, int nrows)
+{
+    cudaStream_t st = c->stream;
+    MPROS_CUDA(cudaMemsetAsync(c->infl_bits + (size_t)row0 * c->pitch0, 0, (size_t)nrows * c->pitch0 * 4, st));
+    if (smax < 0 || nrows <= 0)
+        return MPROS_OK;
+    size_t words = (size_t)nrows * ((c->W0 + 31) / 32);
+    int K = (smax + 31) / 32;
+    if (K < 1)
+        K = 1;
+    int g = grid_for(words);
+    switch (K)
+    {
+    case 1:
+        if (smax <= 31)
+            inflate_kernel<1, true><<<g, 256, 0, st>>>(c->raw_bits, c->infl_bits, c->H0, c->W0, c->pitch0, smax, row0, nrows);
+        else
+            inflate_kernel<1, false><<<g, 256, 0, st>>>(c->raw_bits, c->infl_bits, c->H0, c->W0, c->pitch0, smax, row0, nrows);
+        break;
+    case 2:
+        inflate_kernel<2, false><<<g, 256, 0, st>>>(c->raw_bits, c->infl_bits, c->H0, c->W0, c->pitch0, smax, row0, nrows);
+        break;
+    case 3:
+    case 4:
+        inflate_kernel<4, false><<<g, 256, 0, st>>>(c->raw_bits, c->infl_bits, c->H0, c->W0, c->pitch0, smax, row0, nrows);
+        break;
+    default:
+        inflate_kernel<8, false><<<g, 256, 0, st>>>(c->raw_bits, c->infl_bits, c->H0, c->W0, c->pitch0, smax, row0, nrows);
+        break;
+    }
+    MPROS_LAUNCH_CHECK(c);
+    return MPROS_OK;
+}
+
+// stage 3: everything that needs the complete original-resolution layers: N2, the padded tile-word copies, N4 (if a goal is
+// set), N5-N9
+static int map_finish(Ctx *c)
+{
+    cudaStream_t st = c->stream;
     // N2
     const int ds = c->mp.downsampling_factor;
     if (ds == 1)
@@ -446,69 +565,18 @@ static int set_occupancy_impl(Ctx *c, const int8_t *d_data, int width, int heigh
     {
         MPROS_CUDA(cudaMemsetAsync(c->ds_bits, 0, (size_t)c->H * c->pitch * 4, st));
         size_t words = (size_t)c->H * ((c->W + 31) / 32);
-        downsample_kernel<<<grid_for(words * 32), 256, 0, st>>>(c->raw_bits, c->H0, c->W0, c->pitch0, c->ds_bits, c->H, c->W,
-                                                              c->pitch, ds);
+        const bool pow2 = ds <= 32 && (ds & (ds - 1)) == 0 && c->H0 % ds == 0 && c->W0 % ds == 0;
+        if (pow2)
+        {
+            int log2ds = 0;
+            while ((1 << log2ds) < ds)
+                ++log2ds;
+            downsample_pow2_kernel<<<grid_for(words), 256, 0, st>>>(c->raw_bits, c->pitch0, c->ds_bits, c->H, c->W, c->pitch, ds, log2ds);
+        }
+        else
+            downsample_kernel<<<grid_for(words * 32), 256, 0, st>>>(c->raw_bits, c->H0, c->W0, c->pitch0, c->ds_bits, c->H, c->W,
+                                                                  c->pitch, ds);
         MPROS_LAUNCH_CHECK(c);
-    }
-
-    // N3: structuring-element table exactly as the reference evaluates it (quarter-integers, exact in double)
-    {
-        int r = (int)std::ceil(c->mp.obstacle_inflation_radius / c->res0);
-        if (r < 0)
-            r = 0;
-        if (r > kMaxInflRadius)
-        {
-            set_error("obstacle_inflation_radius / resolution exceeds 255 pixels (unsupported)");
-            return MPROS_ERR_INVALID;
-        }
-        double r_sq = r * r;
-        int16_t tab[kMaxInflRadius + 1];
-        int smax = -1;
-        for (int s = 0; s <= kMaxInflRadius; ++s)
-        {
-            tab[s] = -1;
-            if (s > r)
-                continue;
-            double j_dist = std::abs(s) - 0.5;
-            for (int a = 0; a <= r; ++a)
-            {
-                double i_dist = std::abs(a) - 0.5;
-                if (i_dist * i_dist + j_dist * j_dist <= r_sq)
-                    tab[s] = (int16_t)a;
-            }
-            if (tab[s] >= 0)
-                smax = s;
-        }
-        MPROS_CUDA(cudaMemcpyToSymbolAsync(c_ext_tab, tab, sizeof(tab), 0, cudaMemcpyHostToDevice, st));
-        MPROS_CUDA(cudaMemsetAsync(c->infl_bits, 0, (size_t)c->H0 * c->pitch0 * 4, st));
-        if (smax >= 0)
-        {
-            size_t words = (size_t)c->H0 * ((c->W0 + 31) / 32);
-            int K = (smax + 31) / 32;
-            if (K < 1)
-                K = 1;
-            int g = grid_for(words);
-            switch (K)
-            {
-            case 1:
-                if (smax <= 31)
-                    inflate_kernel<1, true><<<g, 256, 0, st>>>(c->raw_bits, c->infl_bits, c->H0, c->W0, c->pitch0, smax);
-                else
-                    inflate_kernel<1, false><<<g, 256, 0, st>>>(c->raw_bits, c->infl_bits, c->H0, c->W0, c->pitch0, smax);
-                break;
-            case 2:
-                inflate_kernel<2, false><<<g, 256, 0, st>>>(c->raw_bits, c->infl_bits, c->H0, c->W0, c->pitch0, smax);
-                break;
-            case 3:
-            case 4:
-                inflate_kernel<4, false><<<g, 256, 0, st>>>(c->raw_bits, c->infl_bits, c->H0, c->W0, c->pitch0, smax);
-                break;
-            default:
-                inflate_kernel<8, false><<<g, 256, 0, st>>>(c->raw_bits, c->infl_bits, c->H0, c->W0, c->pitch0, smax);
-                break;
-            }
-            MPROS_LAUNCH_CHECK(c);
-        }
     }
     // padded tile-word copies of the two collision layers
     {
@@ -521,6 +589,7 @@ static int set_occupancy_impl(Ctx *c, const int8_t *d_data, int width, int heigh
     }
     // the reference sets get_map_ at the very end but the sub-steps below only need the geometry
     c->get_map = true;
+    c->band_open = false;
     if (c->planner_configured)
     {
         int rc = mpros_planner_config(static_cast<mpros_ctx *>(c), &c->pp); // n_check depends on the resolution
@@ -539,6 +608,25 @@ static int set_occupancy_impl(Ctx *c, const int8_t *d_data, int width, int heigh
         return rc;
     MPROS_CUDA(cudaStreamSynchronize(st));
     return MPROS_OK;
+}
+
+static int set_occupancy_impl(Ctx *c, const int8_t *d_data, int width, int height, double resolution, double ox, double oy,
+                              double oyaw)
+{
+    int have_old = 0, smax = -1;
+    int rc = map_begin(c, width, height, resolution, ox, oy, oyaw, &have_old);
+    if (rc)
+        return rc;
+    rc = map_threshold_rows(c, d_data, 0, height, have_old);
+    if (rc)
+        return rc;
+    rc = map_inflate_prepare(c, &smax, nullptr);
+    if (rc)
+        return rc;
+    rc = map_inflate_rows(c, smax, 0, height);
+    if (rc)
+        return rc;
+    return map_finish(c);
 }
 
 } // namespace mpros
@@ -572,6 +660,120 @@ extern "C" int mpros_map_set_occupancy(mpros_ctx *c, const int8_t *data, int wid
         return rc;
     MPROS_CUDA(cudaMemcpyAsync(c->stage, data, bytes, cudaMemcpyHostToDevice, c->stream));
     return set_occupancy_impl(c, static_cast<const int8_t *>(c->stage), width, height, resolution, ox, oy, oyaw);
+}
+
+// ---- row-band tiling of the original-resolution stages across GPUs (include/mpros_gpu.h: mpros_map_band_*) ----------
+static int band_args_ok(mpros_ctx *c, const char *who, int row0, int nrows)
+{
+    if (!c)
+    {
+        set_error(std::string(who) + ": NULL context");
+        return MPROS_ERR_INVALID;
+    }
+    if (!c->band_open)
+    {
+        set_error(std::string(who) + ": call mpros_map_band_begin first");
+        return MPROS_ERR_INVALID;
+    }
+    if (row0 < 0 || nrows < 0 || row0 + nrows > c->H0)
+    {
+        set_error(std::string(who) + ": row range outside the map");
+        return MPROS_ERR_INVALID;
+    }
+    return MPROS_OK;
+}
+
+extern "C" int mpros_map_band_begin(mpros_ctx *c, int width, int height, double resolution, double origin_x, double origin_y,
+                                    double origin_yaw, int *halo_rows)
+{
+    if (!c || width <= 0 || height <= 0 || !(resolution > 0))
+    {
+        set_error("mpros_map_band_begin: invalid argument");
+        return MPROS_ERR_INVALID;
+    }
+    MPROS_CUDA(cudaSetDevice(c->device));
+    int have_old = 0;
+    int rc = map_begin(c, width, height, resolution, origin_x, origin_y, origin_yaw, &have_old);
+    if (rc)
+        return rc;
+    c->band_have_old = have_old;
+    int r = 0;
+    rc = map_inflate_prepare(c, &c->band_smax, &r);
+    if (rc)
+        return rc;
+    if (halo_rows)
+        *halo_rows = r;
+    c->band_open = true;
+    return MPROS_OK;
+}
+
+extern "C" int mpros_map_band_threshold(mpros_ctx *c, const int8_t *rows, int row0, int nrows)
+{
+    int rc = band_args_ok(c, "mpros_map_band_threshold", row0, nrows);
+    if (rc)
+        return rc;
+    if (nrows == 0)
+        return MPROS_OK;
+    if (!rows)
+    {
+        set_error("mpros_map_band_threshold: NULL data");
+        return MPROS_ERR_INVALID;
+    }
+    MPROS_CUDA(cudaSetDevice(c->device));
+    size_t bytes = (size_t)nrows * c->W0;
+    rc = ensure_stage(c, bytes);
+    if (rc)
+        return rc;
+    MPROS_CUDA(cudaMemcpyAsync(c->stage, rows, bytes, cudaMemcpyHostToDevice, c->stream));
+    return map_threshold_rows(c, static_cast<const int8_t *>(c->stage), row0, nrows, c->band_have_old);
+}
+
+extern "C" int mpros_map_band_threshold_dev(mpros_ctx *c, const int8_t *d_rows, int row0, int nrows)
+{
+    int rc = band_args_ok(c, "mpros_map_band_threshold_dev", row0, nrows);
+    if (rc)
+        return rc;
+    if (nrows == 0)
+        return MPROS_OK;
+    if (!d_rows)
+    {
+        set_error("mpros_map_band_threshold_dev: NULL data");
+        return MPROS_ERR_INVALID;
+    }
+    MPROS_CUDA(cudaSetDevice(c->device));
+    return map_threshold_rows(c, d_rows, row0, nrows, c->band_have_old);
+}
+
+extern "C" int mpros_map_band_layer_ptr(mpros_ctx *c, int layer, void **d_ptr, size_t *row_pitch_bytes)
+{
+    if (!c || !d_ptr || !row_pitch_bytes || !c->band_open || (layer != MPROS_LAYER_STATIC_ORIG && layer != MPROS_LAYER_INFLATE_ORIG))
+    {
+        set_error("mpros_map_band_layer_ptr: needs an open band session and MPROS_LAYER_STATIC_ORIG / _INFLATE_ORIG");
+        return MPROS_ERR_INVALID;
+    }
+    *d_ptr = layer == MPROS_LAYER_STATIC_ORIG ? (void *)c->raw_bits : (void *)c->infl_bits;
+    *row_pitch_bytes = (size_t)c->pitch0 * 4;
+    return MPROS_OK;
+}
+
+extern "C" int mpros_map_band_inflate(mpros_ctx *c, int row0, int nrows)
+{
+    int rc = band_args_ok(c, "mpros_map_band_inflate", row0, nrows);
+    if (rc)
+        return rc;
+    MPROS_CUDA(cudaSetDevice(c->device));
+    return map_inflate_rows(c, c->band_smax, row0, nrows);
+}
+
+extern "C" int mpros_map_band_finish(mpros_ctx *c)
+{
+    if (!c || !c->band_open)
+    {
+        set_error("mpros_map_band_finish: no open band session");
+        return MPROS_ERR_INVALID;
+    }
+    MPROS_CUDA(cudaSetDevice(c->device));
+    return map_finish(c);
 }
 
 extern "C" int mpros_map_get_info(mpros_ctx *c, mpros_map_info *o)

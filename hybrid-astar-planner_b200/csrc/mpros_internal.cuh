@@ -78,6 +78,9 @@ struct Ctx
 
     // NavMap public state
     bool get_map = false, get_goal = false;
+    // row-band session (mpros_map_band_begin .. mpros_map_band_finish)
+    bool band_open = false;
+    int band_have_old = 0, band_smax = -1;
     int H0 = 0, W0 = 0, pitch0 = 0, H = 0, W = 0, pitch = 0;
     double res0 = 0, res = 0, ox = 0, oy = 0, oyaw = 0, osin = 0, ocos = 1;
     double goal_x = 0, goal_y = 0;

@@ -722,8 +722,8 @@ static int plan_pass(mpros_ctx *c, PlanBatchArgs &a, int pass, int node_cap, int
                          h[13] / its, h[14] / its, h[15] / its);
             for (int k = 0; k < 12; ++k)
                 std::fprintf(stderr, "[mpros]   %-12s %9.1f\n", names[k], h[k] / its);
-            const char *names2[8] = {"col:pose+sincos", "col:footprint", "closed:probe+peek", "closed:images", "", "", "", ""};
-            for (int k = 16; k < 20; ++k)
+            const char *names2[8] = {"col:pose+sincos", "col:footprint", "closed:A loads", "closed:B-D", "closed:insert", "", "", ""};
+            for (int k = 16; k < 21; ++k)
                 std::fprintf(stderr, "[mpros]   %-18s %9.1f\n", names2[k - 16], h[k] / its);
         }
 #endif

@@ -60,6 +60,10 @@ struct TeamShared
     unsigned char c_alive[kMaxPrim], c_cand[kMaxPrim], c_need[kMaxPrim];
     int h_list[kMaxPrim], h_n, bfs_more, h_skip;
     unsigned long long hmin[kMaxPrim][3];
+    double k_x[kMaxPrim], k_y[kMaxPrim], k_yaw[kMaxPrim]; // closed-set warp's own copy of the child poses
+    double sc[2][kMaxPrim][2];                            // {sin, cos} of the child yaw / of goal yaw - child yaw
+    double hf[11][kMaxPrim];                              // OMPL base formula k on child c (min over the 4 images)
+    int h_skipg[(kMaxPrim + 7) / 8];                      // group of 8 entries settled by the CSC round alone
     double img[kMaxPrim][4][7]; // per child x symmetry image: {x, y, phi, xb, yb, sin phi, cos phi} of the normalised goal
     // open list: top three levels of the 32-ary heap + the insertion buffers (double buffered by iteration parity)
     unsigned long long heap_key[kHeapTop];
@@ -144,7 +148,7 @@ __device__ __forceinline__ void team_bfs_init_rows(const MapView &m, TeamBfs &b,
 }
 
 template <int NW>
-__device__ __forceinline__ void team_bfs_start(const MapView &m, TeamBfs &b, int gi, int gj, uint32_t tag)
+__device__ __noinline__ void team_bfs_start(const MapView &m, TeamBfs &b, int gi, int gj, uint32_t tag)
 {
     const int tid = threadIdx.x;
     if (tid == 0)
@@ -293,7 +297,7 @@ __device__ __forceinline__ int team_bfs_peek(const MapView &m, const TeamBfs &b,
 
 // goal-map values for the slots flagged c_need whose c_h1 is still unknown (< 0): advance the wavefront until final
 template <int NW>
-__device__ __forceinline__ void team_h1_lookup(const MapView &m, TeamShared<NW> &S, Prof &pf)
+__device__ __noinline__ void team_h1_lookup(const MapView &m, TeamShared<NW> &S, Prof &pf)
 {
     const int tid = threadIdx.x;
     while (true)
@@ -332,7 +336,7 @@ __device__ __forceinline__ void team_image(const PlannerView &p, TeamShared<NW> 
 
 // heuristics (hybrid_a_star.cpp:248-264) of the slots flagged c_need: h = max(h1 * res, RS distance) * 1.001
 template <int NW>
-__device__ __forceinline__ void team_heuristics(const MapView &m, const PlannerView &p, TeamShared<NW> &S, Prof &pf)
+__device__ __noinline__ void team_heuristics(const MapView &m, const PlannerView &p, TeamShared<NW> &S, Prof &pf)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0)
@@ -411,7 +415,7 @@ __device__ __forceinline__ void team_heuristics(const MapView &m, const PlannerV
 
 // Reeds-Shepp shot from (x, y, yaw, dir, steer) to the goal: FindOptimalPath + GenTraj into S.traj (compute group).
 template <int NW>
-__device__ __forceinline__ void team_rs_solve(const RsConfig &rs, TeamShared<NW> &S, double x, double y, double yaw, int dir, double steer)
+__device__ __noinline__ void team_rs_solve(const RsConfig &rs, TeamShared<NW> &S, double x, double y, double yaw, int dir, double steer)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int CW = NW - 1;
@@ -497,6 +501,105 @@ __device__ __forceinline__ void team_rs_solve(const RsConfig &rs, TeamShared<NW>
     team_sync<NW>();
 }
 
+// genRSPath (hybrid_a_star.cpp:853-900) from the popped node S.cur: Reeds-Shepp solve, sampled trajectory, footprint tests.
+// Out of line: shots are rare (a few per query) and their ~15 KB of code must not sit inside the hot loop.
+template <int NW>
+__device__ __noinline__ void team_shot(const MapView &m, const PlannerView &p, const PlanBatchArgs &a, TeamShared<NW> &S, Prof &pf)
+{
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int CW = NW - 1;
+    const PlanNode cn = S.cur;
+    team_rs_solve<NW>(a.rs, S, cn.x, cn.y, cn.yaw, (int)cn.dir, cn.steer);
+    const int np = S.traj_n;
+    if (tid == 0)
+    {
+        S.n_shots++;
+        S.first_hit = np > kTrajCap ? 0 : -1; // longer than the buffer cannot happen inside the shot range
+    }
+    team_sync<NW>();
+    for (int base = 0; base < np && base < kTrajCap && S.first_hit < 0; base += CW)
+    {
+        int k = base + warp;
+        bool hit = false;
+        if (k < np)
+        {
+            double s, c;
+            dm::sincos_(S.traj[3 * k + 2], &s, &c);
+            hit = warp_footprint_collision(m, p, S.traj[3 * k], S.traj[3 * k + 1], s, c);
+        }
+        if (lane == 0 && k < kTrajCap)
+            S.traj_hit[k] = hit;
+        team_sync<NW>();
+        if (tid == 0)
+        {
+            for (int t = base; t < min(np, base + CW); ++t)
+                if (S.traj_hit[t])
+                {
+                    S.first_hit = t;
+                    break;
+                }
+        }
+        team_sync<NW>();
+    }
+    if (tid == 0)
+    {
+        S.n_coll += (S.first_hit >= 0) ? (S.first_hit + 1) : np;
+        if (S.first_hit < 0)
+        {
+            if (S.goal_parent == kNoNode || S.goal_g > cn.g + S.best_cost)
+            {
+                S.goal_parent = S.cur_id;
+                S.goal_g = cn.g + S.best_cost;
+                S.goal_traj_n = np;
+            }
+            S.shot_ok = 1;
+            S.goal_found = 1;
+        }
+    }
+    team_sync<NW>();
+    if (tid == 0) pf.count(15);
+}
+
+// Insert of the children one by one in primitive order (one thread): the fallback when two children of one expansion
+// touch the same closed-set slot (same index, or two new keys probing to the same empty slot). Rare, out of line.
+template <int NW>
+__device__ __noinline__ void team_insert_sequential(PlanNode *nodes, const ClosedSet &closed, TeamShared<NW> &S, int P, int par_cur, int node_cap)
+{
+    uint32_t n_nodes = S.n_nodes;
+    int nb = 0;
+    for (int c = 0; c < P; ++c)
+    {
+        if (!S.c_need[c])
+            continue;
+        bool f2;
+        double oc;
+        uint32_t on;
+        uint32_t sl = closed_find(closed, S.c_idx[c], f2, oc, on);
+        double tg = S.c_g[c];
+        if (!(oc > tg))
+            continue;
+        if (n_nodes >= (uint32_t)node_cap)
+        {
+            S.overflow = 1;
+            break;
+        }
+        if (f2 && on < kGoalNode)
+            nodes[on].closed = 1;
+        closed_store(closed, sl, S.c_idx[c], tg, n_nodes);
+        PlanNode nn;
+        nn.x = S.c_x[c], nn.y = S.c_y[c], nn.yaw = S.c_yaw[c], nn.steer = S.c_steer[c], nn.g = tg, nn.parent = S.cur_id;
+        nn.s = S.c_s[c], nn.c = S.c_c[c];
+        nn.dir = (int8_t)(S.c_dir[c] > 0 ? 1 : -1), nn.closed = 0, nn.pad = 0;
+        nodes[n_nodes] = nn;
+        S.buf_key[par_cur][nb] = (unsigned long long)__double_as_longlong(tg + S.c_h[c]);
+        S.buf_id[par_cur][nb] = n_nodes;
+        ++nb;
+        n_nodes++;
+    }
+    S.buf_n[par_cur] = nb;
+    S.n_nodes = n_nodes;
+}
+
 // ---- heap warp --------------------------------------------------------------------------------------------------------
 // Arg-min over the heap root (lane 31) and the entries of an insertion buffer (lanes 0..n-1), lexicographic on
 // (key, id). Returns the winning lane, -1 when nothing is valid.
@@ -518,7 +621,7 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                                 TeamShared<NW> &S)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int CW = NW - 1;       // warps of the compute group
+
     constexpr int HEAP_W = NW - 1;   // heap warp
     constexpr int CLOSED_W = NW - 2; // closed-set warp
     constexpr int COL_W = NW - 2;    // warps 0..COL_W-1 run the footprint tests
@@ -625,6 +728,7 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                 // the start node enters the open list through the insertion buffer of "iteration -1"
                 S.buf_key[1][0] = (unsigned long long)__double_as_longlong(0.0 + S.c_h[0]);
                 S.buf_id[1][0] = 0;
+
                 S.buf_n[1] = 1;
                 S.n_nodes = 1;
             }
@@ -753,57 +857,7 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                 S.buf_n[par_cur] = 0;
             // -- genRSPath (:853-900)
             if (S.need_shot)
-            {
-                team_rs_solve<NW>(a.rs, S, cn.x, cn.y, cn.yaw, (int)cn.dir, cn.steer);
-                const int np = S.traj_n;
-                if (tid == 0)
-                {
-                    S.n_shots++;
-                    S.first_hit = np > kTrajCap ? 0 : -1; // longer than the buffer cannot happen inside the shot range
-                }
-                team_sync<NW>();
-                for (int base = 0; base < np && base < kTrajCap && S.first_hit < 0; base += CW)
-                {
-                    int k = base + warp;
-                    bool hit = false;
-                    if (k < np)
-                    {
-                        double s, c;
-                        dm::sincos_(S.traj[3 * k + 2], &s, &c);
-                        hit = warp_footprint_collision(m, p, S.traj[3 * k], S.traj[3 * k + 1], s, c);
-                    }
-                    if (lane == 0 && k < kTrajCap)
-                        S.traj_hit[k] = hit;
-                    team_sync<NW>();
-                    if (tid == 0)
-                    {
-                        for (int t = base; t < min(np, base + CW); ++t)
-                            if (S.traj_hit[t])
-                            {
-                                S.first_hit = t;
-                                break;
-                            }
-                    }
-                    team_sync<NW>();
-                }
-                if (tid == 0)
-                {
-                    S.n_coll += (S.first_hit >= 0) ? (S.first_hit + 1) : np;
-                    if (S.first_hit < 0)
-                    {
-                        if (S.goal_parent == kNoNode || S.goal_g > cn.g + S.best_cost)
-                        {
-                            S.goal_parent = S.cur_id;
-                            S.goal_g = cn.g + S.best_cost;
-                            S.goal_traj_n = np;
-                        }
-                        S.shot_ok = 1;
-                        S.goal_found = 1;
-                    }
-                }
-                team_sync<NW>();
-                if (tid == 0) pf.count(15);
-            }
+                team_shot<NW>(m, p, a, S, pf);
             if (tid == 0) pf.mark(1);
             pf.restart();
             if (S.shot_ok)
@@ -813,9 +867,10 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
             }
             else
             {
-                // -- expandNode (:304-402)
-                // warps 0..COL_W-1: one primitive each: end pose + footprint test (one lane per probe);
-                // closed-set warp: one lane per child: node cell, g, closed-set probe, goal-map peek; then the symmetry images
+                // -- expandNode (:304-402). Three barriers of the compute group: children, CSC round, (other formulas).
+                //   warps 0..COL_W-1 : one primitive each: end pose, sin/cos, footprint test (one lane per probe)
+                //   closed-set warp  : one lane per child: node cell, closed-set slot, Voronoi cost and goal-map value with ALL
+                //                      global loads issued together, the symmetry images computed while they are in flight
                 bool pr_found = false;
                 double pr_old_cost = 0;
                 uint32_t pr_old = kNoNode, pr_slot = 0xffffffffu - lane;
@@ -845,61 +900,212 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                 else if (warp == CLOSED_W)
                 {
                     pf.restart();
+                    // phase A (lane = child): cell, key, and every global load the child needs, issued back to back
+                    double k_steer = 0, k_direc = 1;
+                    int ci = -1, cj = -1;
+                    bool inmap = false, isgoal = false, inwin = false;
+                    unsigned long long idx = 0;
+                    uint32_t hs = 0, first_node = kNoNode, dsw = 0, blk = 0;
+                    uint4 first = make_uint4(0, 0, 0, 0);
+                    float voro_f = 0.f;
+                    uint16_t dv = 0;
                     if (lane < P)
                     {
-                        const int c = lane;
-                        double nx, ny, nyaw, steer, direc;
-                        primitive_end_pose(p, c, cn.x, cn.y, cn.yaw, cn.s, cn.c, nx, ny, nyaw, steer, direc);
-                        bool cand = false;
-                        int h1 = -1, ci = -1, cj = -1;
-                        if (pos_to_index_ds(m, nx, ny, ci, cj))
+                        double nx, ny, nyaw;
+                        primitive_end_pose(p, lane, cn.x, cn.y, cn.yaw, cn.s, cn.c, nx, ny, nyaw, k_steer, k_direc);
+                        S.k_x[lane] = nx, S.k_y[lane] = ny, S.k_yaw[lane] = nyaw;
+                        inmap = pos_to_index_ds(m, nx, ny, ci, cj);
+                        if (inmap)
                         {
-                            double voro = (double)__ldg(m.voronoi + (size_t)ci * m.W + cj);
-                            double g = node_cost(p, cn.g, (double)cn.dir, cn.steer, voro, steer, direc);
-                            unsigned long long idx = cal_index(m, p, ci, cj, yaw_to_idx(p, nyaw), direc);
-                            pr_slot = closed_find(closed, idx, pr_found, pr_old_cost, pr_old);
-                            cand = pr_old_cost > g; // an earlier sibling on the same slot may still beat it; resolved at insert
-                            S.c_g[c] = g, S.c_idx[c] = idx;
-                            if (cand)
-                                h1 = team_bfs_peek(m, S.bfs, ci, cj);
+                            voro_f = __ldg(m.voronoi + (size_t)ci * m.W + cj);
+                            idx = cal_index(m, p, ci, cj, yaw_to_idx(p, nyaw), k_direc);
+                            hs = hash_index(idx) & closed.mask;
+                            first = *reinterpret_cast<const uint4 *>(&closed.slot[hs]);
+                            first_node = closed.slot[hs].node;
+                            // goal-map value (team_bfs_peek) with its three loads hoisted
+                            const TeamBfs &b = S.bfs;
+                            isgoal = (ci == b.gi && cj == b.gj);
+                            dsw = __ldg(m.ds_bits + (size_t)ci * m.pitch + (cj >> 5));
+                            const int lr = ci - b.r0, lw = (cj >> 5) - b.w0;
+                            inwin = !(lr < 0 || lr >= b.rows || lw < 0 || lw >= b.wwords);
+                            if (inwin && ci >= b.ilo && ci <= b.ihi)
+                            {
+                                const size_t o = (size_t)lr * b.wwords + lw;
+                                blk = b.blocked[o];
+                                dv = b.dist[o * 32 + (cj & 31)];
+                            }
                         }
-                        // a cell outside the map cannot pass the footprint test; the reference would index outside its arrays
-                        S.c_i[c] = ci, S.c_j[c] = cj;
-                        S.c_cand[c] = cand;
-                        S.c_h1[c] = h1;
                     }
                     __syncwarp();
                     if (warp == CLOSED_W && lane == 0) pf.mark(18);
-                    for (int t = lane; t < 4 * P; t += 32)
+                    // phase B: sin/cos of the child yaw (t < P) and of goal yaw - child yaw (t >= P)
+                    for (int t = lane; t < 2 * P; t += 32)
                     {
-                        const int c = t >> 2;
-                        double nx, ny, nyaw, steer, direc;
-                        primitive_end_pose(p, c, cn.x, cn.y, cn.yaw, cn.s, cn.c, nx, ny, nyaw, steer, direc);
-                        team_image<NW>(p, S, c, t & 3, nx, ny, nyaw);
+                        const int c = t < P ? t : t - P, which = t < P ? 0 : 1;
+                        const double ang = which ? S.gyaw - S.k_yaw[c] : S.k_yaw[c];
+                        double sn, cs;
+                        dm::sincos_(ang, &sn, &cs);
+                        S.sc[which][c][0] = sn, S.sc[which][c][1] = cs;
                     }
                     __syncwarp();
+                    // phase C: the four symmetry images of the normalised goal per child (ompl_image; sin(-x) = -sin(x) and
+                    // cos(-x) = cos(x) hold bit for bit, so the image's own sin/cos phi follow from those of dth)
+                    for (int t = lane; t < 4 * P; t += 32)
+                    {
+                        const int c = t >> 2, q = t & 3;
+                        const double dx = S.gx - S.k_x[c], dy = S.gy - S.k_y[c], dth = S.gyaw - S.k_yaw[c];
+                        const double sn = S.sc[0][c][0], cs = S.sc[0][c][1];
+                        const double inx = dm::div_(cs * dx + sn * dy, p.min_r), iny = dm::div_(-sn * dx + cs * dy, p.min_r);
+                        const double sphi = S.sc[1][c][0], cphi = S.sc[1][c][1];
+                        const double nxb = inx * cphi + iny * sphi, nyb = inx * sphi - iny * cphi;
+                        const bool fx = (q == 1 || q == 3), fy = (q == 2 || q == 3), fp = (q == 1 || q == 2);
+                        double *o = S.img[c][q];
+                        o[0] = fx ? -inx : inx, o[1] = fy ? -iny : iny, o[2] = fp ? -dth : dth, o[3] = fx ? -nxb : nxb, o[4] = fy ? -nyb : nyb;
+                        o[5] = fp ? -sphi : sphi, o[6] = cphi;
+                    }
+                    // phase D (lane = child): consume the loads: g, closed-set compare, goal-map value
+                    bool cand = false;
+                    int h1 = -1;
+                    if (inmap)
+                    {
+                        const double g = node_cost(p, cn.g, (double)cn.dir, cn.steer, (double)voro_f, k_steer, k_direc);
+                        const unsigned long long want = (closed.tag << 34) | idx;
+                        const unsigned long long k0 = ((unsigned long long)first.y << 32) | first.x;
+                        if (k0 == want)
+                        {
+                            pr_found = true;
+                            pr_old_cost = __longlong_as_double((long long)(((unsigned long long)first.w << 32) | first.z));
+                            pr_old = first_node;
+                            pr_slot = hs;
+                        }
+                        else if ((k0 >> 34) != closed.tag)
+                        {
+                            pr_found = false;
+                            pr_old_cost = __longlong_as_double(0x7ff0000000000000ll);
+                            pr_old = kNoNode;
+                            pr_slot = hs;
+                        }
+                        else // first slot taken by another key: keep probing (rare at this load factor)
+                            pr_slot = closed_find(closed, idx, pr_found, pr_old_cost, pr_old);
+                        cand = pr_old_cost > g; // an earlier sibling on the same slot may still beat it; resolved at insert
+                        S.c_g[lane] = g, S.c_idx[lane] = idx;
+                        if (cand)
+                        {
+                            if (isgoal)
+                                h1 = 0;
+                            else if ((dsw >> (cj & 31)) & 1u)
+                                h1 = kHugeInt; // occupied cells are never entered
+                            else if (!inwin)
+                                h1 = kHugeInt; // further than 999 steps
+                            else if ((blk >> (cj & 31)) & 1u)
+                                h1 = dv; // visited (blk is 0 for rows that are not initialised yet)
+                            else
+                                h1 = S.bfs.done ? kHugeInt : -1;
+                        }
+                    }
+                    if (lane < P)
+                    {
+                        // a cell outside the map cannot pass the footprint test; the reference would index outside its arrays
+                        S.c_i[lane] = ci, S.c_j[lane] = cj;
+                        S.c_cand[lane] = cand;
+                        S.c_h1[lane] = h1;
+                    }
+                    if (lane == 0)
+                    {
+                        S.nslots = P;
+                        S.n_prim += P;
+                        S.n_coll += P;
+                    }
                     if (warp == CLOSED_W && lane == 0) pf.mark(19);
                 }
-                if (tid == 0)
-                {
-                    S.nslots = P;
-                    S.n_prim += P;
-                    S.n_coll += P;
-                }
-                team_sync<NW>();
-                if (tid < P)
-                    S.c_need[tid] = S.c_alive[tid] && S.c_cand[tid];
+                team_sync<NW>(); // (1) children public
                 if (tid == 0) pf.mark(2);
-                team_h1_lookup<NW>(m, S, pf); // starts with a barrier
-                team_heuristics<NW>(m, p, S, pf);
+                // every warp derives the set of children that need a heuristic (alive, and cheaper than the closed set's entry)
+                bool need = lane < P && S.c_alive[lane] && S.c_cand[lane];
+                if (__any_sync(kFull, need && S.c_h1[lane] < 0))
+                {
+                    // some goal-map value is not final yet: advance the wavefront (rare; barriers inside)
+                    if (tid < P)
+                        S.c_need[tid] = need;
+                    team_h1_lookup<NW>(m, S, pf);
+                }
+                if (tid == 0) pf.mark(3);
+                const unsigned needmask = __ballot_sync(kFull, need);
+                const int hn = __popc(needmask);
+                // heuristics (hybrid_a_star.cpp:248-264): h = max(h1 * res, RS distance) * 1.001; lanes = (entry, image)
+                for (int base = 0; base < hn; base += 8)
+                {
+                    const int e = base + (lane >> 2), q = lane & 3;
+                    const bool live = e < hn;
+                    const int c = live ? (int)__fns(needmask, 0, e + 1) : 0;
+                    const double *im = S.img[c][q];
+                    // round A: the two CSC formulas. Any valid candidate is an upper bound of the RS distance.
+                    if (warp < 2)
+                    {
+                        double Lf = live ? ompl_formula(warp, im[0], im[1], im[2], im[3], im[4], im[5], im[6]) : DBL_MAX;
+                        Lf = fmin(Lf, __shfl_xor_sync(kFull, Lf, 1));
+                        Lf = fmin(Lf, __shfl_xor_sync(kFull, Lf, 2));
+                        if (live && q == 0)
+                            S.hf[warp][c] = Lf;
+                    }
+                    team_sync<NW>(); // (2)
+                    if (tid == 0) pf.mark(5);
+                    // when rho * min(CSC) <= h1 for every entry of the group the other nine formulas cannot change max(h1, h2)
+                    bool ok = true;
+                    if (lane < 8 && base + lane < hn)
+                    {
+                        const int ce = (int)__fns(needmask, 0, base + lane + 1);
+                        const double ub = p.min_r * fmin(S.hf[0][ce], S.hf[1][ce]);
+                        ok = ub <= (double)S.c_h1[ce] * m.res;
+                    }
+                    const bool skip = __all_sync(kFull, ok);
+                    if (warp == CLOSED_W && lane == 0)
+                        S.h_skipg[base >> 3] = skip;
+                    if (!skip)
+                    {
+                        if (tid == 0) pf.count(14);
+#pragma unroll 1
+                        for (int sl = 0; sl < team_formula_b_slots<NW>(); ++sl)
+                        {
+                            const int k = team_formula_b<NW>(warp, sl);
+                            if (k < 0)
+                                continue;
+                            double Lf = live ? ompl_formula(k, im[0], im[1], im[2], im[3], im[4], im[5], im[6]) : DBL_MAX;
+                            Lf = fmin(Lf, __shfl_xor_sync(kFull, Lf, 1));
+                            Lf = fmin(Lf, __shfl_xor_sync(kFull, Lf, 2));
+                            if (live && q == 0)
+                                S.hf[k][c] = Lf;
+                        }
+                        team_sync<NW>(); // (3)
+                    }
+                    if (tid == 0) pf.mark(6);
+                }
                 // closed-set compare / insert in primitive order (closed-set warp). Common case: the children that need an
                 // insert touch distinct hash slots -> slot / node stores and close-marks run one lane per child, the new open
                 // entries go to the insertion buffer. Children that collide on a slot (same index, or two new keys probing
                 // to the same empty slot) fall back to the strictly sequential walk.
                 if (warp == CLOSED_W)
                 {
+                    __syncwarp();
+                    pf.restart();
+                    if (need)
+                    {
+                        const int c = lane, e = __popc(needmask & ((1u << lane) - 1u));
+                        double plain = fmin(S.hf[0][c], S.hf[1][c]), ccsc = DBL_MAX, ccscc = DBL_MAX;
+                        if (!S.h_skipg[e >> 3])
+                        {
+                            plain = fmin(fmin(plain, fmin(S.hf[2][c], S.hf[3][c])), fmin(S.hf[4][c], S.hf[5][c]));
+                            ccsc = fmin(fmin(S.hf[6][c], S.hf[7][c]), fmin(S.hf[8][c], S.hf[9][c]));
+                            ccscc = S.hf[10][c];
+                        }
+                        const double h1v = (double)S.c_h1[c] * m.res; // getGoalCost: cost_ * map_resolution_
+                        S.c_h[c] = fmax(h1v, ompl_combine(p.min_r, plain, ccsc, ccscc)) * (1 + 1e-3);
+                        S.c_need[c] = 1;
+                    }
+                    else if (lane < P)
+                        S.c_need[lane] = 0;
+                    __syncwarp();
                     uint32_t n_nodes = S.n_nodes;
-                    const bool need = lane < P && S.c_need[lane];
                     const uint32_t slot = need ? pr_slot : 0xffffffffu - lane;
                     const unsigned same = __match_any_sync(kFull, slot);
                     const bool conflict = __any_sync(kFull, need && (same & (same - 1)) != 0);
@@ -937,52 +1143,27 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                         }
                     }
                     else if (lane == 0)
+                        team_insert_sequential<NW>(nodes, closed, S, P, par_cur, L.node_cap);
+                    __syncwarp();
+                    if (lane == 0)
                     {
-                        int nb = 0;
-                        for (int c = 0; c < P; ++c)
-                        {
-                            if (!S.c_need[c])
-                                continue;
-                            bool f2;
-                            double oc;
-                            uint32_t on;
-                            uint32_t sl = closed_find(closed, S.c_idx[c], f2, oc, on);
-                            double tg = S.c_g[c];
-                            if (!(oc > tg))
-                                continue;
-                            if (n_nodes >= (uint32_t)L.node_cap)
-                            {
-                                S.overflow = 1;
-                                break;
-                            }
-                            if (f2 && on < kGoalNode)
-                                nodes[on].closed = 1;
-                            closed_store(closed, sl, S.c_idx[c], tg, n_nodes);
-                            PlanNode nn;
-                            nn.x = S.c_x[c], nn.y = S.c_y[c], nn.yaw = S.c_yaw[c], nn.steer = S.c_steer[c], nn.g = tg, nn.parent = S.cur_id;
-                            nn.s = S.c_s[c], nn.c = S.c_c[c];
-                            nn.dir = (int8_t)(S.c_dir[c] > 0 ? 1 : -1), nn.closed = 0, nn.pad = 0;
-                            nodes[n_nodes] = nn;
-                            S.buf_key[par_cur][nb] = (unsigned long long)__double_as_longlong(tg + S.c_h[c]);
-                            S.buf_id[par_cur][nb] = n_nodes;
-                            ++nb;
-                            n_nodes++;
-                        }
-                        S.buf_n[par_cur] = nb;
-                        S.n_nodes = n_nodes;
+                        if (S.overflow)
+                            S.stop = 1;
+                        if (a.optimal && dm::hypot_(S.gx - cn.x, S.gy - cn.y) <= 1.0) // stop_radius (hybrid_a_star.h:345)
+                            S.stop = 1;
+                        if (!S.stop)
+                            S.iteration = it + 1; // every break of the reference's loop precedes ++iteration (:725-745)
                     }
+                    if (warp == CLOSED_W && lane == 0) pf.mark(20);
                 }
-                team_sync<NW>();
                 if (tid == 0) pf.mark(8);
-                if (tid == 0 && S.overflow)
-                    S.stop = 1;
             }
-            if (tid == 0)
+            if (S.shot_ok && tid == 0)
             {
                 if (a.optimal && dm::hypot_(S.gx - cn.x, S.gy - cn.y) <= 1.0) // stop_radius (hybrid_a_star.h:345)
                     S.stop = 1;
                 if (!S.stop)
-                    S.iteration = it + 1; // every break of the reference's loop precedes ++iteration (:725-745)
+                    S.iteration = it + 1;
             }
         }
         __syncthreads(); // (b) inserts are in the buffer, the heap is consistent again

@@ -29,15 +29,61 @@ struct __align__(16) PlanNode
 
 // ---- warp-cooperative footPrintInCollision4 (hybrid_a_star.cpp:617-680) ---------------------------------------------
 // All lanes pass the same pose; probe k of the pose is evaluated by lane (k mod 32). Verdict is warp-uniform.
+// Fast path: the fixed-point walk of map_device.cuh (Q(k) = Q(0) + k * dQ over the padded tile-word layers) with the same
+// preconditions and the same error bound; if the pose is out of its range or ANY probe lies within kFxEps of a cell edge
+// the reference arithmetic below decides.
 __device__ __noinline__ bool warp_footprint_collision(const MapView &m, const PlannerView &p, double px, double py, double s,
                                                          double c)
 {
     const int lane = threadIdx.x & 31;
     double x0 = c * p.longi_x0 + px, y0 = s * p.longi_x0 + py;
     double x1 = c * p.longi_x1 + px, y1 = s * p.longi_x1 + py;
+    const int total = p.n_check + 1 + 4;
+    if (fabs(x0) + fabs(y0) < m.fx_span - p.fx_extent)
+    {
+        const double kTwo32 = 4294967296.0;
+        const double sc = m.inv_res0 * kTwo32;
+        const double jc = m.ocos * sc, js = m.osin * sc;
+        const double off = (double)kTwMargin * kTwo32;
+        const double ax0 = x0 - m.ox, ay0 = y0 - m.oy, ax1 = x1 - m.ox, ay1 = y1 - m.oy;
+        const double fj0 = ax0 * jc + ay0 * js + off, fi0 = ay0 * jc - ax0 * js + off;
+        const double fj1 = ax1 * jc + ay1 * js + off, fi1 = ay1 * jc - ax1 * js + off;
+        const long long qj0 = __double2ll_rd(fj0), qi0 = __double2ll_rd(fi0);
+        const long long ej = __double2ll_rd(fj1), ei = __double2ll_rd(fi1);
+        const unsigned lim_j = (unsigned)(m.W0 + 2 * kTwMargin - 2 * p.fx_slack), lim_i = (unsigned)(m.H0 + 2 * kTwMargin - 2 * p.fx_slack);
+        const bool in = ((unsigned)((int)(qj0 >> 32) - p.fx_slack) < lim_j) & ((unsigned)((int)(ej >> 32) - p.fx_slack) < lim_j) &
+                        ((unsigned)((int)(qi0 >> 32) - p.fx_slack) < lim_i) & ((unsigned)((int)(ei >> 32) - p.fx_slack) < lim_i);
+        if (in)
+        {
+            const long long dj = __double2ll_rn((fj1 - fj0) * p.inv_n_check), di = __double2ll_rn((fi1 - fi0) * p.inv_n_check);
+            uint32_t any = 0, edge = 0xffffffffu;
+            for (int base = 0; base < total; base += 32)
+            {
+                const int k = base + lane;
+                if (k <= p.n_check)
+                {
+                    // the sequential walk adds dQ k times; k * dQ is the same integer
+                    const long long qj = qj0 + (long long)k * dj, qi = qi0 + (long long)k * di;
+                    any |= tw_probe(m.infl_tw, m.tw_pitch, qj, qi);
+                    edge = tw_edge(edge, qj, qi);
+                }
+                else if (k < total)
+                {
+                    const int q = k - p.n_check - 1;
+                    const double cx = p.corner_x[q], cy = p.corner_y[q];
+                    const double X = cx * c - cy * s + px, Y = cx * s + cy * c + py;
+                    const double ax = X - m.ox, ay = Y - m.oy;
+                    const long long cj = __double2ll_rd(ax * jc + ay * js + off), ci = __double2ll_rd(ay * jc - ax * js + off);
+                    any |= tw_probe(m.raw_tw, m.tw_pitch, cj, ci);
+                    edge = tw_edge(edge, cj, ci);
+                }
+            }
+            if (!__any_sync(kFull, edge < 2 * kFxEps))
+                return __any_sync(kFull, (any & 1u) != 0);
+        }
+    }
     double n = (double)p.n_check;
     double ox = (x1 - x0) / n, oy = (y1 - y0) / n;
-    const int total = p.n_check + 1 + 4;
     for (int base = 0; base < total; base += 32)
     {
         int k = base + lane;

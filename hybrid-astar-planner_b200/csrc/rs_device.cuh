@@ -30,6 +30,7 @@ __device__ __noinline__ double sin_(double x) { return sin(x); }
 __device__ __noinline__ double cos_(double x) { return cos(x); }
 __device__ __noinline__ void sincos_(double x, double *s, double *c) { sincos(x, s, c); }
 __device__ __noinline__ double div_(double a, double b) { return a / b; }
+__device__ __noinline__ double fmod_(double a, double b) { return fmod(a, b); }
 } // namespace dm
 
 struct RsConfig
@@ -423,7 +424,7 @@ __device__ __forceinline__ double ompl_mod2pi(double x)
     else if (ax < 2.0 * twopi)
         v = x < 0 ? x + twopi : x - twopi;
     else
-        v = fmod(x, twopi);
+        v = dm::fmod_(x, twopi); // rare (|x| >= 4 pi); out of line: inlined it was 30 KB of cold code inside the hot paths
     if (v < -kPi)
         v += twopi;
     else if (v > kPi)

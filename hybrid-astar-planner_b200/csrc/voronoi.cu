@@ -261,31 +261,68 @@ __global__ void __launch_bounds__(256) dt_row_kernel(const uint32_t *__restrict_
     }
 }
 
-// Column pass: one thread per column, forward then backward sweep of key = min(key, neighbour + 1).
-// Loads do not depend on the recurrence, so the unrolled loop keeps several rows in flight.
-__global__ void __launch_bounds__(128) dt_col_kernel(unsigned long long *__restrict__ key, int H, int W)
+// Column pass: key[i] = min over i' of key[i'] + |i - i'| (in the packed key, distance in the high word) = the classic
+// forward / backward sweep pair. A sweep is a prefix minimum in disguise:
+//   fwd[i] = min_{i' <= i} key[i'] + (i - i')  =  prefixmin_i( key[i'] + (H - i') ) - (H - i),
+// so a column is cut into 32 chunks that are scanned in parallel: per chunk aggregate -> exclusive prefix over the 32
+// aggregates in shared memory -> sweep of the chunk seeded with it. Block = 32 columns x 32 chunks; a warp reads 32
+// consecutive keys of one row (256 B). The old one-thread-per-column sweep (1024 dependent steps, 8 CTAs) took 613 us
+// per call at 1024^2 and was 72 % of the whole map preprocessing.
+__global__ void __launch_bounds__(1024) dt_col_kernel(unsigned long long *__restrict__ key, int H, int W)
 {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= W)
-        return;
-    unsigned long long cur = kInfKey;
-#pragma unroll 8
-    for (int i = 0; i < H; ++i)
+    __shared__ unsigned long long agg[32][33];
+    const int x = threadIdx.x, y = threadIdx.y;
+    const int j = blockIdx.x * 32 + x;
+    const int R = (H + 31) / 32;
+    const int i0 = min(H, y * R), i1 = min(H, i0 + R);
+    const bool live = j < W;
+    // forward: aggregate of key[i] + (H - i)
+    unsigned long long a = ~0ull;
+    if (live)
+        for (int i = i0; i < i1; ++i)
+        {
+            unsigned long long v = key[(size_t)i * W + j] + (unsigned long long)(H - i) * kOne;
+            a = v < a ? v : a;
+        }
+    agg[y][x] = a;
+    __syncthreads();
+    unsigned long long run = ~0ull;
+    for (int c = 0; c < y; ++c)
     {
-        unsigned long long v = key[(size_t)i * W + j];
-        cur += kOne;
-        cur = v < cur ? v : cur;
-        key[(size_t)i * W + j] = cur;
+        unsigned long long v = agg[c][x];
+        run = v < run ? v : run;
     }
-    cur = kInfKey;
-#pragma unroll 8
-    for (int i = H - 1; i >= 0; --i)
+    __syncthreads();
+    // forward sweep of the chunk (in place) + aggregate of fwd[i] + i for the backward pass
+    a = ~0ull;
+    if (live)
+        for (int i = i0; i < i1; ++i)
+        {
+            const unsigned long long off = (unsigned long long)(H - i) * kOne;
+            unsigned long long v = key[(size_t)i * W + j] + off;
+            run = v < run ? v : run;
+            const unsigned long long f = run - off;
+            key[(size_t)i * W + j] = f;
+            const unsigned long long b = f + (unsigned long long)i * kOne;
+            a = b < a ? b : a;
+        }
+    agg[y][x] = a;
+    __syncthreads();
+    run = ~0ull;
+    for (int c = y + 1; c < 32; ++c)
     {
-        unsigned long long v = key[(size_t)i * W + j];
-        cur += kOne;
-        cur = v < cur ? v : cur;
-        key[(size_t)i * W + j] = cur;
+        unsigned long long v = agg[c][x];
+        run = v < run ? v : run;
     }
+    // backward sweep: out[i] = min_{i' >= i} fwd[i'] + (i' - i)
+    if (live)
+        for (int i = i1 - 1; i >= i0; --i)
+        {
+            const unsigned long long off = (unsigned long long)i * kOne;
+            unsigned long long v = key[(size_t)i * W + j] + off;
+            run = v < run ? v : run;
+            key[(size_t)i * W + j] = run - off;
+        }
 }
 
 // N6 epilogue: cap (>= 1000 stays 1000 / region -1), keep obstacle cells' own labels
@@ -459,7 +496,7 @@ int map_build_voronoi(Ctx *c)
     // N6
     dt_row_kernel<<<grid_for(cells), 256, 0, st>>>(c->ds_bits, H, W, pitch, c->region, key);
     MPROS_LAUNCH_CHECK(c);
-    dt_col_kernel<<<cdiv(W, 128), 128, 0, st>>>(key, H, W);
+    dt_col_kernel<<<cdiv(W, 32), dim3(32, 32), 0, st>>>(key, H, W);
     MPROS_LAUNCH_CHECK(c);
     obs_finish_kernel<<<grid_for(cells), 256, 0, st>>>(key, cells, c->obs_dist, c->region);
     MPROS_LAUNCH_CHECK(c);
@@ -473,7 +510,7 @@ int map_build_voronoi(Ctx *c)
     // N8
     dt_row_kernel<<<grid_for(cells), 256, 0, st>>>(c->edge_bits, H, W, pitch, nullptr, key);
     MPROS_LAUNCH_CHECK(c);
-    dt_col_kernel<<<cdiv(W, 128), 128, 0, st>>>(key, H, W);
+    dt_col_kernel<<<cdiv(W, 32), dim3(32, 32), 0, st>>>(key, H, W);
     MPROS_LAUNCH_CHECK(c);
     edge_finish_kernel<<<grid_for(cells), 256, 0, st>>>(key, cells, c->edge_dist);
     MPROS_LAUNCH_CHECK(c);

@@ -129,6 +129,12 @@ def load_library(path=LIB_PATH):
     L.mpros_map_set_occupancy.argtypes = [vp, vp, i, i, d, d, d, d]
     L.mpros_map_set_occupancy_dev.argtypes = [vp, vp, i, i, d, d, d, d]
     L.mpros_map_update_goal.argtypes = [vp, d, d]
+    L.mpros_map_band_begin.argtypes = [vp, i, i, d, d, d, d, C.POINTER(C.c_int)]
+    L.mpros_map_band_threshold.argtypes = [vp, vp, i, i]
+    L.mpros_map_band_threshold_dev.argtypes = [vp, vp, i, i]
+    L.mpros_map_band_layer_ptr.argtypes = [vp, i, C.POINTER(vp), C.POINTER(sz)]
+    L.mpros_map_band_inflate.argtypes = [vp, i, i]
+    L.mpros_map_band_finish.argtypes = [vp]
     L.mpros_map_get_info.argtypes = [vp, C.POINTER(MapInfo)]
     L.mpros_map_download.argtypes = [vp, i, vp, sz]
     L.mpros_map_upload.argtypes = [vp, i, vp, sz]
@@ -203,6 +209,7 @@ class Context:
         h = C.c_void_p()
         self._check(self.L.mpros_ctx_create(device, C.byref(h)))
         self.h = h
+        self.device = device
 
     def _check(self, rc):
         if rc != 0:
@@ -245,6 +252,40 @@ class Context:
     def set_occupancy_dev(self, dptr, W, H, resolution, origin):
         res = float(np.float32(resolution))
         self._check(self.L.mpros_map_set_occupancy_dev(self.h, dptr, W, H, res, origin[0], origin[1], origin[2]))
+
+    # ---- NavMap::setOccupancyMap tiled by row bands (one context per GPU; sharding.set_occupancy_banded drives it) ----
+    def band_begin(self, W, H, resolution, origin):
+        """Geometry + allocation; returns the halo (rows of the raw layer a band needs from each neighbour for N3)."""
+        halo = C.c_int(0)
+        res = float(np.float32(resolution))
+        self._check(self.L.mpros_map_band_begin(self.h, W, H, res, origin[0], origin[1], origin[2], C.byref(halo)))
+        return halo.value
+
+    def band_threshold(self, rows, row0):
+        rows = np.ascontiguousarray(rows, dtype=np.int8)
+        self._check(self.L.mpros_map_band_threshold(self.h, rows.ctypes.data, row0, rows.shape[0]))
+
+    def band_rows(self, layer, row0, nrows):
+        """Rows [row0, row0 + nrows) of the bit-packed static_orig / inflate_orig layer as a torch int32 CUDA tensor
+        [nrows, pitch_words] that ALIASES the layer's device memory (for the halo exchange / all-gather)."""
+        import torch
+
+        ptr, pitch = C.c_void_p(0), C.c_size_t(0)
+        self._check(self.L.mpros_map_band_layer_ptr(self.h, LAYERS[layer][0], C.byref(ptr), C.byref(pitch)))
+        words = pitch.value // 4
+
+        class _Alias:  # CUDA array interface: lets torch wrap memory owned by the context
+            __cuda_array_interface__ = {"shape": (nrows, words), "typestr": "<i4", "data": (ptr.value + row0 * pitch.value, False),
+                                        "version": 3, "strides": None}
+
+        self.synchronize()  # the tensor is used on torch's stream
+        return torch.as_tensor(_Alias(), device="cuda:%d" % self.device)
+
+    def band_inflate(self, row0, nrows):
+        self._check(self.L.mpros_map_band_inflate(self.h, row0, nrows))
+
+    def band_finish(self):
+        self._check(self.L.mpros_map_band_finish(self.h))
 
     def update_goal(self, gx, gy):
         self._check(self.L.mpros_map_update_goal(self.h, gx, gy))

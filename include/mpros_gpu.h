@@ -128,6 +128,29 @@ MPROS_API int mpros_map_set_occupancy(mpros_ctx *ctx, const int8_t *data, int wi
 /* Same, data already resident in HBM. */
 MPROS_API int mpros_map_set_occupancy_dev(mpros_ctx *ctx, const int8_t *d_data, int width, int height, double resolution,
                                 double origin_x, double origin_y, double origin_yaw);
+/* ---- the same, tiled by ROW BANDS across the GPUs of one box (very large maps) ----------------------
+ * NavMap::setOccupancyMap's original-resolution stages split per band; every rank (one context per GPU) calls the same
+ * sequence and the caller moves the bit-packed rows between ranks (NCCL over NVLink; hybrid-astar-planner_b200/sharding.py:
+ * set_occupancy_banded):
+ *   1. mpros_map_band_begin      geometry + allocation (nav_map.cpp:54-112); *halo_rows = the structuring element's
+ *                                radius in pixels = rows of static_map_orig_ a band needs from each neighbour for N3
+ *   2. mpros_map_band_threshold  N1 (nav_map.cpp:114-131) for the rank's rows [row0, row0 + nrows)
+ *   3. halo exchange             rows [row0 - halo, row0) and [row0 + nrows, row0 + nrows + halo) of MPROS_LAYER_STATIC_ORIG
+ *                                from the neighbouring ranks into the SAME rows of this rank's layer (mpros_map_band_layer_ptr)
+ *   4. mpros_map_band_inflate    N3 (inflateObstacle, nav_map.cpp:164-214) for the rank's rows
+ *   5. all-gather                every rank's rows of both layers into every rank's layers
+ *   6. mpros_map_band_finish     N2, N4 (if a goal is set), N5-N9 on the complete layers (at the down-sampled resolution)
+ * The result is bit-identical to mpros_map_set_occupancy on one GPU. Layers are bit-packed: bit (j & 31) of 32-bit word
+ * [i * row_pitch_bytes / 4 + (j >> 5)]. */
+MPROS_API int mpros_map_band_begin(mpros_ctx *ctx, int width, int height, double resolution, double origin_x, double origin_y,
+                                   double origin_yaw, int *halo_rows);
+/* rows: host int8[nrows * width], the rank's rows of the occupancy grid. */
+MPROS_API int mpros_map_band_threshold(mpros_ctx *ctx, const int8_t *rows, int row0, int nrows);
+MPROS_API int mpros_map_band_threshold_dev(mpros_ctx *ctx, const int8_t *d_rows, int row0, int nrows);
+/* Device pointer and row pitch of MPROS_LAYER_STATIC_ORIG / MPROS_LAYER_INFLATE_ORIG in their bit-packed form. */
+MPROS_API int mpros_map_band_layer_ptr(mpros_ctx *ctx, int layer, void **d_ptr, size_t *row_pitch_bytes);
+MPROS_API int mpros_map_band_inflate(mpros_ctx *ctx, int row0, int nrows);
+MPROS_API int mpros_map_band_finish(mpros_ctx *ctx);
 /* NavMap::updateGoal -> generateGoalMap (nav_map.h:204-210, nav_map.cpp:279-349). Goal outside the map
  * clears get_goal (nav_map.cpp:297-302) and returns MPROS_OK. */
 MPROS_API int mpros_map_update_goal(mpros_ctx *ctx, double goal_x, double goal_y);

@@ -77,6 +77,17 @@ def main():
         )
         vals, cnt = np.unique(occ, return_counts=True)
         print(name, occ.shape, meta["resolution"], meta["origin"], dict(zip(vals.tolist(), cnt.tolist())))
+    # case 3 stand-in: Arena2036.pgm is missing from the reference, so ARENA_part's image is read with
+    # Arena2036.yaml's geometry and thresholds (res 0.04, origin 0, occupied 0.99, free 0.6); the tests scale it x4
+    # (nearest neighbour) to 2000 x 2000
+    meta = read_yaml(os.path.join(REF_MAPS, "Arena2036.yaml"))
+    img = read_pgm(os.path.join(REF_MAPS, "ARENA_part.pgm"))
+    occ = to_occupancy(img, meta)
+    np.savez_compressed(os.path.join(OUT, "arena_standin.npz"), occupancy=occ, resolution=np.float64(meta["resolution"]),
+                        origin=np.array(meta["origin"], dtype=np.float64), occupied_thresh=np.float64(meta["occupied_thresh"]),
+                        free_thresh=np.float64(meta["free_thresh"]))
+    vals, cnt = np.unique(occ, return_counts=True)
+    print("arena_standin", occ.shape, meta["resolution"], meta["origin"], dict(zip(vals.tolist(), cnt.tolist())))
 
 
 if __name__ == "__main__":

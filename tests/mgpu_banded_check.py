@@ -1,0 +1,77 @@
+"""Multi-GPU check (run under torchrun, one rank per GPU): NavMap::setOccupancyMap tiled by row bands across the ranks
+(sharding.set_occupancy_banded: N1 + halo exchange + N3 per band, all-gather, replicated finish) must give layers that are
+bit-identical to the single-GPU mpros_map_set_occupancy, and the sharded planner must return the single-GPU results.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tests/mgpu_banded_check.py
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "hybrid-astar-planner_b200"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    import bench
+    import mpros_b200
+    import sharding
+    import synthetic
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    size = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+    occ = synthetic.synthetic_occupancy()[:size, :size].copy()
+    occ[-10:, :] = 100  # close the cropped map with a wall again
+    occ[:, -10:] = 100
+    H, W = occ.shape
+    params = bench.shipped_params()
+    single = mpros_b200.Context(local)
+    single.map_config(params)
+    t0 = time.perf_counter()
+    single.set_occupancy(occ, synthetic.SYN_RES, [0.0, 0.0, 0.0])
+    t_single = time.perf_counter() - t0
+    banded = mpros_b200.Context(local)
+    banded.map_config(params)
+    lo, hi = sharding.band_rows(H, rank, world)
+    for rep in range(2):
+        dist.barrier()
+        t0 = time.perf_counter()
+        sharding.set_occupancy_banded(banded, occ[lo:hi], H, W, synthetic.SYN_RES, [0.0, 0.0, 0.0], dist=dist)
+        t_banded = time.perf_counter() - t0
+    bad = 0
+    for layer in ["static_orig", "inflate_orig", "static", "obs_dist", "region", "isedge", "edge_dist", "voronoi"]:
+        a, b = single.layer(layer), banded.layer(layer)
+        if not np.array_equal(a, b):
+            bad += 1
+            print("rank %d: layer %s differs in %d cells" % (rank, layer, int((a != b).sum())), flush=True)
+    # queries sharded across the ranks on the banded map vs all of them on the single-GPU map
+    single.planner_config(params)
+    banded.planner_config(params)
+    starts, goals = synthetic.synthetic_queries(64, single.collision_check, single.layer("static"), synthetic.SYN_RES * synthetic.SYN_DS,
+                                                size * synthetic.SYN_RES, synthetic.SYN_QUERY_SEED)
+    ref = single.plan_batch(starts, goals, path_cap=64)
+    got = sharding.plan_batch_sharded(banded, starts, goals, 64, dist=dist, device="cuda")
+    if not (np.array_equal(ref["status"], got["status"]) and np.array_equal(ref["cost"], got["cost"]) and
+            np.array_equal(ref["iterations"], got["iterations"])):
+        bad += 1
+        print("rank %d: sharded plans differ from the single-GPU plans" % rank, flush=True)
+    t = torch.tensor([bad], device="cuda")
+    dist.all_reduce(t)
+    if rank == 0:
+        print("mgpu_banded_check: world %d, map %dx%d, halo exchange + all-gather; single %.1f ms, banded %.1f ms; %s" % (
+            world, H, W, 1e3 * t_single, 1e3 * t_banded, "OK" if int(t.item()) == 0 else "MISMATCH"), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0 if int(t.item()) == 0 else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -7,6 +7,8 @@ import mpros_b200, synthetic, bench
 os.environ["MPROS_DEBUG"] = "1"
 ctx = mpros_b200.Context(0)
 params = bench.shipped_params()
+if os.environ.get("MPROS_MAXIT"):
+    params["/mpros/planner/max_iteration"] = int(os.environ["MPROS_MAXIT"])
 ctx.map_config(params)
 ctx.set_occupancy(synthetic.synthetic_occupancy(), synthetic.SYN_RES, [0, 0, 0])
 ctx.planner_config(params)
