@@ -263,12 +263,29 @@ bool HybridAstar::Plan()
 
 std::vector<PathPoint> HybridAstar::getNewPath()
 {
+    // new_path_ as setPath builds it (hybrid_a_star.cpp:814-838): path length, cusps, curvature and, with
+    // interpolation_enable, the collision-checked Bezier up-sampling of upsampleAndPopulatePath
     std::vector<PathPoint> out;
+    if (path_.empty())
+        return out;
+    std::vector<double> raw;
+    raw.reserve(path_.size() * 5);
     for (auto &p : path_)
+        raw.insert(raw.end(), p.begin(), p.begin() + 5);
+    int64_t offs[2] = {0, (int64_t)path_.size()}, out_offs[2] = {0, 0};
+    std::vector<double> buf((size_t)8 * 64 * path_.size());
+    int rc = mpros_path_postprocess_batch(map_->ctx(), raw.data(), offs, 1, buf.data(), buf.size() / 8, out_offs);
+    if (rc == MPROS_ERR_CAPACITY)
     {
-        PathPoint pt(p[0], p[1], p[2]);
-        pt.steering_ = p[3];
-        pt.direc_ = p[4];
+        buf.resize((size_t)8 * out_offs[1]);
+        rc = mpros_path_postprocess_batch(map_->ctx(), raw.data(), offs, 1, buf.data(), buf.size() / 8, out_offs);
+    }
+    check(rc, "mpros_path_postprocess_batch");
+    for (int64_t k = 0; k < out_offs[1]; ++k)
+    {
+        const double *o = buf.data() + 8 * k;
+        PathPoint pt(o[0], o[1], o[2]);
+        pt.curv_ = o[3], pt.direc_ = o[4], pt.steering_ = o[5], pt.is_cusp_ = o[6] != 0.0, pt.dist_ = o[7];
         out.push_back(pt);
     }
     return out;

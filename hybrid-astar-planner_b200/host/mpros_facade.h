@@ -73,6 +73,8 @@ struct PathPoint
     double getY() const { return y_; }
     double getYaw() const { return yaw_; }
     double x_ = 0, y_ = 0, yaw_ = 0, curv_ = 0, direc_ = 1, steering_ = 0;
+    bool is_cusp_ = false;
+    double dist_ = 0; // distance from start to this point
 };
 
 class NavMap
@@ -228,7 +230,7 @@ public:
     void reset();                                                                                        // :32-50
     bool Plan();                                                                                         // :682-777
     std::vector<std::vector<double>> getPath() { return path_; } // {x, y, yaw, steer, direction}
-    std::vector<PathPoint> getNewPath();                          // raw path as PathPoints (no Bezier up-sampling yet)
+    std::vector<PathPoint> getNewPath();                          // hybrid_a_star.cpp:848-851: setPath's up-sampled path (:814-838)
     bool pathInCollision(const std::vector<std::vector<double>> &path); // :404-416
     bool pathInCollision(const std::vector<PathPoint> &path);           // :418-430
     bool footPrintInCollision4(const double &x, const double &y, const double &yaw); // :617-680

@@ -176,6 +176,11 @@ int main(int argc, char **argv)
                     map.map_height_, map.map_width_);
         for (size_t k = 0; k < path.size(); ++k)
             std::printf("%s[%.17g, %.17g, %.17g, %.17g, %.17g]", k ? ", " : "", path[k][0], path[k][1], path[k][2], path[k][3], path[k][4]);
+        std::printf("], \"new_path\": [");
+        std::vector<PathPoint> np = ok ? planner.getNewPath() : std::vector<PathPoint>();
+        for (size_t k = 0; k < np.size(); ++k)
+            std::printf("%s[%.17g, %.17g, %.17g, %.17g, %.17g, %.17g, %d, %.17g]", k ? ", " : "", np[k].x_, np[k].y_, np[k].yaw_, np[k].curv_, np[k].direc_,
+                        np[k].steering_, np[k].is_cusp_ ? 1 : 0, np[k].dist_);
         std::printf("]}\n");
         return 0;
     }

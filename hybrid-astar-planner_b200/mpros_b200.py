@@ -148,6 +148,7 @@ def load_library(path=LIB_PATH):
     L.mpros_rs_distance_batch.argtypes = [vp, d, vp, vp, sz, vp]
     L.mpros_expand_batch.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp]
     L.mpros_plan_batch.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, i, vp]
+    L.mpros_path_postprocess_batch.argtypes = [vp, vp, vp, sz, vp, sz, vp]
     L.mpros_plan_batch_dev.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, i, vp]
     _lib = L
     return L
@@ -401,6 +402,25 @@ class Context:
 
     def plan_batch_dev(self, d_starts, d_goals, nq, d_status, d_cost, d_len, d_paths, path_cap, d_stats):
         self._check(self.L.mpros_plan_batch_dev(self.h, d_starts, d_goals, nq, d_status, d_cost, d_len, d_paths, path_cap, d_stats))
+
+    def path_postprocess(self, paths):
+        """getNewPath() for a list of raw paths (each [n_k, 5] {x, y, yaw, steer, direction}): list of [m_k, 8] arrays
+        {x, y, yaw, curv, direc, steering, is_cusp, dist} (setPath's post-processing incl. Bezier up-sampling)."""
+        paths = [np.ascontiguousarray(p, dtype=np.float64).reshape(-1, 5) for p in paths]
+        offs = np.zeros(len(paths) + 1, dtype=np.int64)
+        offs[1:] = np.cumsum([len(p) for p in paths])
+        flat = np.concatenate(paths) if paths else np.zeros((0, 5))
+        out_offs = np.zeros(len(paths) + 1, dtype=np.int64)
+        cap = 64 * max(1, int(offs[-1]))
+        while True:
+            out = np.zeros((cap, 8), dtype=np.float64)
+            rc = self.L.mpros_path_postprocess_batch(self.h, flat.ctypes.data, offs.ctypes.data, len(paths), out.ctypes.data, cap, out_offs.ctypes.data)
+            if rc == 3 and out_offs[-1] > cap:  # MPROS_ERR_CAPACITY: sizes are known now
+                cap = int(out_offs[-1])
+                continue
+            self._check(rc)
+            break
+        return [out[out_offs[k]:out_offs[k + 1]].copy() for k in range(len(paths))]
 
     # ---- plumbing ----
     def stream(self):

@@ -237,6 +237,20 @@ MPROS_API int mpros_plan_batch_dev(mpros_ctx *ctx, const double *d_starts3, cons
                                    int32_t *d_status, double *d_cost, int32_t *d_path_len, double *d_paths, int path_cap,
                                    int64_t *d_stats);
 
+
+/* ---- path post-processing -------------------------------------------------------------------- */
+/* What HybridAstar::setPath does to the raw path_ before getNewPath() returns it (hybrid_a_star.cpp:814-838):
+ * updatePathLength, setCusp, updateCurvatureNew (planner_utils.h:35-61, 251-309) and, when interpolation_enable is set,
+ * upsampleAndPopulatePath (hybrid_a_star.cpp:902-1112: collision-checked cubic Bezier arcs) followed by
+ * updateCurvatureNew + updatePathLength again. For a batch of raw paths: path q owns points [offsets[q], offsets[q+1])
+ * of paths5 = double[5 * offsets[n_paths]] {x, y, yaw, steer, direction} (getPath()'s rows, e.g. mpros_plan_batch's).
+ * out8: double[8 * out_cap_points] {x, y, yaw, curv_, direc_, steering_, is_cusp_, dist_} = the PathPoints of
+ * getNewPath(), concatenated in path order; out_offsets: int64[n_paths + 1]. When out_cap_points is too small the call
+ * returns MPROS_ERR_CAPACITY with out_offsets holding the required sizes. All candidate arcs of one segment of every path
+ * are footprint-tested in ONE launch of the batched pathInCollision kernel. */
+MPROS_API int mpros_path_postprocess_batch(mpros_ctx *ctx, const double *paths5, const int64_t *offsets, size_t n_paths, double *out8,
+                                           size_t out_cap_points, int64_t *out_offsets);
+
 #ifdef __cplusplus
 }
 #endif

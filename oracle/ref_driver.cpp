@@ -296,6 +296,67 @@ extern "C"
         return ok;
     }
 
+    // setPath's PathPoint post-processing (hybrid_a_star.cpp:814-838) applied to a given raw path_ {x,y,yaw,steer,dir}:
+    // updatePathLength / setCusp / updateCurvatureNew, then (interpolation_enable) upsampleAndPopulatePath +
+    // updateCurvatureNew + updatePathLength — the reference's own functions, called in the reference's order on a planner
+    // constructed for the path's end poses. newpath_out: cap x 8 {x, y, yaw, curv, direc, steering, is_cusp, dist} = what
+    // getNewPath() returns. Returns new_path_.size().
+    int ref_upsample_path(void *map, const double *path5, int n, double *newpath_out, int cap)
+    {
+        NavMap *m = static_cast<NavMap *>(map);
+        std::vector<double> s(path5, path5 + 3), g(path5 + 5 * (n - 1), path5 + 5 * (n - 1) + 3);
+        HybridAstar planner(s, g, *m, g_vis, g_nh);
+        std::vector<PathPoint> &np_ = planner.new_path_;
+        np_.clear();
+        for (int i = 0; i < n; ++i)
+        {
+            PathPoint pp(path5[5 * i], path5[5 * i + 1], path5[5 * i + 2]);
+            pp.steering_ = path5[5 * i + 3];
+            pp.direc_ = path5[5 * i + 4];
+            np_.push_back(pp);
+        }
+        mpros_utils::updatePathLength(np_);
+        mpros_utils::setCusp(np_);
+        mpros_utils::updateCurvatureNew(np_);
+        if (planner.inter_enable_)
+        {
+            planner.upsampleAndPopulatePath(np_);
+            mpros_utils::updateCurvatureNew(np_);
+            mpros_utils::updatePathLength(np_);
+        }
+        int k = 0;
+        for (; k < (int)np_.size() && k < cap; ++k)
+        {
+            const PathPoint &q = np_[k];
+            double *o = newpath_out + 8 * k;
+            o[0] = q.getX(), o[1] = q.getY(), o[2] = q.getYaw(), o[3] = q.curv_, o[4] = q.direc_, o[5] = q.steering_;
+            o[6] = q.is_cusp_ ? 1.0 : 0.0, o[7] = q.dist_;
+        }
+        return (int)np_.size();
+    }
+
+    // getNewPath() of a whole query (main_planner.cpp:225-233): Plan() then the up-sampled path. Returns its size (0 when
+    // the plan failed).
+    int ref_plan_newpath(void *map, const double *start3, const double *goal3, int do_update_goal, double *newpath_out, int cap)
+    {
+        NavMap *m = static_cast<NavMap *>(map);
+        std::vector<double> s(start3, start3 + 3), g(goal3, goal3 + 3);
+        if (do_update_goal)
+            m->updateGoal(g[0], g[1]);
+        HybridAstar planner(s, g, *m, g_vis, g_nh);
+        if (!planner.Plan())
+            return 0;
+        std::vector<PathPoint> np_ = planner.getNewPath();
+        for (int k = 0; k < (int)np_.size() && k < cap; ++k)
+        {
+            const PathPoint &q = np_[k];
+            double *o = newpath_out + 8 * k;
+            o[0] = q.getX(), o[1] = q.getY(), o[2] = q.getYaw(), o[3] = q.curv_, o[4] = q.direc_, o[5] = q.steering_;
+            o[6] = q.is_cusp_ ? 1.0 : 0.0, o[7] = q.dist_;
+        }
+        return (int)np_.size();
+    }
+
     // ---- RS::RSCurve ------------------------------------------------------------------------------
     // cfg: {radius, max_steer, step, pen_gear, pen_back, pen_a3, pen_a4} with pen_a3/pen_a4 passed in the
     // POSITIONS the planner uses (hybrid_a_star.cpp:170: setPenalty(gear, back, STEER_ANGLE, STEER_CHANGE)).

@@ -220,6 +220,27 @@ def ref_plan_query(rmap, start, goal, update_goal=True, path_cap=4096):
     return d
 
 
+def ref_upsample_path(rmap, path5, cap=8192):
+    """setPath's post-processing (hybrid_a_star.cpp:814-838) of a raw path -> getNewPath() rows
+    {x, y, yaw, curv, direc, steering, is_cusp, dist}."""
+    p = np.ascontiguousarray(path5, dtype=np.float64)
+    out = np.zeros((cap, 8), dtype=np.float64)
+    rmap.lib.L.ref_upsample_path.restype = C.c_int
+    n = rmap.lib.L.ref_upsample_path(C.c_void_p(rmap.h), C.c_void_p(p.ctypes.data), C.c_int(len(p)), C.c_void_p(out.ctypes.data), C.c_int(cap))
+    assert n <= cap
+    return out[:n].copy()
+
+
+def ref_plan_newpath(rmap, start, goal, update_goal=True, cap=8192):
+    s = np.array(start, dtype=np.float64)
+    g = np.array(goal, dtype=np.float64)
+    out = np.zeros((cap, 8), dtype=np.float64)
+    rmap.lib.L.ref_plan_newpath.restype = C.c_int
+    n = rmap.lib.L.ref_plan_newpath(C.c_void_p(rmap.h), C.c_void_p(s.ctypes.data), C.c_void_p(g.ctypes.data), C.c_int(int(update_goal)),
+                                    C.c_void_p(out.ctypes.data), C.c_int(cap))
+    return out[: min(n, cap)].copy()
+
+
 def ref_rs_solve(lib, cfg7, start5, goal3, traj_cap=256):
     cfg = np.array(cfg7, dtype=np.float64)
     s = np.array(start5, dtype=np.float64)

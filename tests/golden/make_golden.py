@@ -79,6 +79,8 @@ def main():
         r = refapi.ref_plan_query(rm, start, goal)
         plans["stats_%d" % ci] = np.array([r["plan_ok"], r["goal_g"], r["n_primitives"], r["num_nodes"], r["path_len"]])
         plans["path_%d" % ci] = r["path"]
+        # getNewPath(): setPath's post-processing of that raw path incl. Bezier up-sampling (hybrid_a_star.cpp:814-838)
+        plans["newpath_%d" % ci] = refapi.ref_upsample_path(rm, r["path"])
         P = 2 * (2 * ((num_steer or 3) // 2) + 1)
         parents = gi.expansion_parents(rm, refapi.RefPlanner(rm), num_steer)
         prims = np.zeros((len(parents), P, 7))

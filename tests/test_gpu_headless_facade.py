@@ -54,3 +54,8 @@ def test_headless_driver_matches_golden_plan(tmp_path, ci):
     if ci in (0, 1, 3):  # these cases do not touch a tie-broken Voronoi cell: identical search
         assert r["n_primitives"] == int(prims_ref)
         assert np.allclose(path, z["path_%d" % ci], rtol=0, atol=1e-8)
+        # HybridAstar::getNewPath(): the up-sampled path of setPath (hybrid_a_star.cpp:814-838)
+        newp = np.array(r["new_path"])
+        want = z["newpath_%d" % ci]
+        assert newp.shape == want.shape
+        assert np.allclose(newp, want, rtol=0, atol=1e-7)
