@@ -334,6 +334,58 @@ __global__ void __launch_bounds__(256) build_tilewords_kernel(const uint32_t *__
     }
 }
 
+// ---- NavMap::vecToMsg (nav_map.cpp:654-693): a layer as the int8 payload of a nav_msgs/OccupancyGrid ------------------
+// data[i] = floor(float(layer[i]) * 100 / maxval), maxval = min(100, max(layer)), stored into int8 the way the x86 build of
+// the reference does (float -> int32 truncation, low byte): goal-map values above 127 wrap. A 0/1 layer becomes 0/100.
+__global__ void __launch_bounds__(256) msg_bits_kernel(const uint32_t *__restrict__ bits, int H, int W, int pitch, int8_t *__restrict__ out)
+{
+    size_t total = (size_t)H * W;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x)
+    {
+        int i = (int)(k / W), j = (int)(k % W);
+        out[k] = ((bits[(size_t)i * pitch + (j >> 5)] >> (j & 31)) & 1u) ? (int8_t)100 : (int8_t)0;
+    }
+}
+__global__ void __launch_bounds__(256) msg_max_u16_kernel(const uint16_t *__restrict__ in, size_t n, int *__restrict__ maxv)
+{
+    int m = 0;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+        m = max(m, (int)in[k]);
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0)
+        atomicMax(maxv, m);
+}
+__global__ void __launch_bounds__(256) msg_max_f32_kernel(const float *__restrict__ in, size_t n, int *__restrict__ maxv)
+{
+    // the Voronoi field is non-negative, so the IEEE bit patterns order like the values
+    int m = 0;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+        m = max(m, __float_as_int(fmaxf(in[k], 0.f)));
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0)
+        atomicMax(maxv, m);
+}
+__device__ __forceinline__ int8_t msg_store(float f)
+{
+    // x86 cvttss2si: NaN / out of range -> INT_MIN (low byte 0); then the low byte is kept
+    int v = (f != f || f >= 2147483648.f || f < -2147483648.f) ? (int)0x80000000 : (int)f;
+    return (int8_t)(v & 0xff);
+}
+__global__ void __launch_bounds__(256) msg_scale_u16_kernel(const uint16_t *__restrict__ in, size_t n, const int *__restrict__ maxv,
+                                                            int8_t *__restrict__ out)
+{
+    const int maxval = min(100, *maxv);
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+        out[k] = msg_store(floorf(__fdiv_rn(__fmul_rn((float)in[k], 100.f), (float)maxval)));
+}
+__global__ void __launch_bounds__(256) msg_scale_f32_kernel(const float *__restrict__ in, size_t n, const int *__restrict__ maxv,
+                                                            int8_t *__restrict__ out)
+{
+    const float maxval = fminf(100.f, __int_as_float(*maxv));
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+        out[k] = msg_store(floorf(__fdiv_rn(__fmul_rn(in[k], 100.f), maxval)));
+}
+
 static int grid_for(size_t work_items, int block = 256)
 {
     size_t g = (work_items + block - 1) / block;
@@ -886,6 +938,68 @@ extern "C" int mpros_map_download(mpros_ctx *c, int layer, void *dst, size_t dst
         return MPROS_ERR_CAPACITY;
     }
     MPROS_CUDA(cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, st));
+    MPROS_CUDA(cudaStreamSynchronize(st));
+    return MPROS_OK;
+}
+
+extern "C" int mpros_map_layer_msg(mpros_ctx *c, int layer, int8_t *dst, size_t dst_bytes, size_t *n_out)
+{
+    if (!c || !n_out)
+    {
+        set_error("mpros_map_layer_msg: NULL argument");
+        return MPROS_ERR_INVALID;
+    }
+    *n_out = 0;
+    const bool bit_layer = layer == MPROS_LAYER_STATIC || layer == MPROS_LAYER_STATIC_ORIG || layer == MPROS_LAYER_INFLATE_ORIG;
+    if (!bit_layer && layer != MPROS_LAYER_GOAL && layer != MPROS_LAYER_VORONOI)
+    {
+        set_error("mpros_map_layer_msg: the reference publishes only the static, goal, Voronoi, static_orig and inflate_orig layers");
+        return MPROS_ERR_INVALID;
+    }
+    // vecToMsg returns an empty message while there is no map / no such layer yet (nav_map.cpp:659-662)
+    if (!c->get_map || (layer == MPROS_LAYER_GOAL && !c->get_goal))
+        return MPROS_OK;
+    const bool orig = layer == MPROS_LAYER_STATIC_ORIG || layer == MPROS_LAYER_INFLATE_ORIG;
+    const size_t n = orig ? (size_t)c->H0 * c->W0 : (size_t)c->H * c->W;
+    *n_out = n;
+    if (!dst)
+        return MPROS_OK; // size query
+    if (dst_bytes < n)
+    {
+        set_error("mpros_map_layer_msg: destination buffer too small");
+        return MPROS_ERR_CAPACITY;
+    }
+    MPROS_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    int rc = ensure_scratch(c, n + 256);
+    if (rc)
+        return rc;
+    int8_t *out = static_cast<int8_t *>(c->scratch);
+    int *maxv = reinterpret_cast<int *>(static_cast<char *>(c->scratch) + ((n + 255) / 256) * 256);
+    if (bit_layer)
+    {
+        const uint32_t *bits = layer == MPROS_LAYER_STATIC_ORIG ? c->raw_bits : layer == MPROS_LAYER_INFLATE_ORIG ? c->infl_bits : c->ds_bits;
+        msg_bits_kernel<<<grid_for(n), 256, 0, st>>>(bits, orig ? c->H0 : c->H, orig ? c->W0 : c->W, orig ? c->pitch0 : c->pitch, out);
+        MPROS_LAUNCH_CHECK(c);
+    }
+    else
+    {
+        MPROS_CUDA(cudaMemsetAsync(maxv, 0, 4, st));
+        if (layer == MPROS_LAYER_GOAL)
+        {
+            msg_max_u16_kernel<<<grid_for(n), 256, 0, st>>>(c->goal, n, maxv);
+            MPROS_LAUNCH_CHECK(c);
+            msg_scale_u16_kernel<<<grid_for(n), 256, 0, st>>>(c->goal, n, maxv, out);
+        }
+        else
+        {
+            msg_max_f32_kernel<<<grid_for(n), 256, 0, st>>>(c->voronoi, n, maxv);
+            MPROS_LAUNCH_CHECK(c);
+            msg_scale_f32_kernel<<<grid_for(n), 256, 0, st>>>(c->voronoi, n, maxv, out);
+        }
+        MPROS_LAUNCH_CHECK(c);
+    }
+    MPROS_CUDA(cudaMemcpyAsync(dst, out, n, cudaMemcpyDeviceToHost, st));
     MPROS_CUDA(cudaStreamSynchronize(st));
     return MPROS_OK;
 }

@@ -1058,7 +1058,11 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                         const double ub = p.min_r * fmin(S.hf[0][ce], S.hf[1][ce]);
                         ok = ub <= (double)S.c_h1[ce] * m.res;
                     }
+#ifdef MPROS_EXPERIMENT_SKIP_B // instruction-cache experiment (wrong heuristics): never run the nine non-CSC formulas
+                    const bool skip = true || __all_sync(kFull, ok);
+#else
                     const bool skip = __all_sync(kFull, ok);
+#endif
                     if (warp == CLOSED_W && lane == 0)
                         S.h_skipg[base >> 3] = skip;
                     if (!skip)

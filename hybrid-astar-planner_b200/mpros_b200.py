@@ -138,6 +138,7 @@ def load_library(path=LIB_PATH):
     L.mpros_map_get_info.argtypes = [vp, C.POINTER(MapInfo)]
     L.mpros_map_download.argtypes = [vp, i, vp, sz]
     L.mpros_map_upload.argtypes = [vp, i, vp, sz]
+    L.mpros_map_layer_msg.argtypes = [vp, i, vp, sz, C.POINTER(sz)]
     L.mpros_map_point_in_collision.argtypes = [vp, i, vp, sz, vp]
     L.mpros_collision_check_poses.argtypes = [vp, vp, sz, vp]
     L.mpros_collision_check_poses_dev.argtypes = [vp, vp, sz, vp]
@@ -302,6 +303,15 @@ class Context:
         shape = (inf["map_height_orig"], inf["map_width_orig"]) if orig else (inf["map_height"], inf["map_width"])
         out = np.zeros(shape, dtype=dt)
         self._check(self.L.mpros_map_download(self.h, lid, out.ctypes.data, out.nbytes))
+        return out
+
+    def layer_msg(self, name):
+        """NavMap::get*MapMsg (nav_map.cpp:654-716): the int8 data of the published OccupancyGrid for one layer (flat)."""
+        n = C.c_size_t(0)
+        self._check(self.L.mpros_map_layer_msg(self.h, LAYERS[name][0], None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.int8)
+        if n.value:
+            self._check(self.L.mpros_map_layer_msg(self.h, LAYERS[name][0], out.ctypes.data, out.nbytes, C.byref(n)))
         return out
 
     def upload_voronoi(self, v):

@@ -158,6 +158,13 @@ MPROS_API int mpros_map_get_info(mpros_ctx *ctx, mpros_map_info *out);
 /* getGoalMap / getVoronoiMap / the private layers (nav_map.h:261-273): copies one layer to host memory in the
  * reference's element type (see enum mpros_layer). dst_bytes must be >= the layer size. */
 MPROS_API int mpros_map_download(mpros_ctx *ctx, int layer, void *dst, size_t dst_bytes);
+/* NavMap::getStaticMapMsg / getGoalMapMsg / getVoroMapMsg / getStaticOrigMapMsg / getInflationOrigMapMsg -> vecToMsg
+ * (nav_map.cpp:654-716): the int8 `data` of the nav_msgs/OccupancyGrid the node publishes for one layer,
+ * floor(float(v) * 100 / min(100, max)) with the reference's int8 wrap-around (goal-map values above 127).
+ * layer: MPROS_LAYER_STATIC, _GOAL, _VORONOI, _STATIC_ORIG or _INFLATE_ORIG. *n_out = msg.data.size() (0 while the layer
+ * does not exist, like the reference's empty message); dst == NULL only queries the size. Geometry of the message:
+ * mpros_map_get_info (height/width/resolution of the original or the down-sampled grid, origin). */
+MPROS_API int mpros_map_layer_msg(mpros_ctx *ctx, int layer, int8_t *dst, size_t dst_bytes, size_t *n_out);
 /* Overwrite the Voronoi-field layer (float[H*W], host) with caller-provided values, e.g. a field computed elsewhere.
  * Only MPROS_LAYER_VORONOI can be uploaded; the next mpros_map_set_occupancy recomputes it. */
 MPROS_API int mpros_map_upload(mpros_ctx *ctx, int layer, const void *src, size_t src_bytes);

@@ -148,6 +148,39 @@ extern "C"
         }
         return n;
     }
+    // The map-layer messages the node publishes (nav_map.cpp:654-716: getStaticMapMsg / getGoalMapMsg / getVoroMapMsg /
+    // getStaticOrigMapMsg / getInflationOrigMapMsg -> vecToMsg): layer ids as ref_map_layer (1, 3, 8, 0, 2).
+    // dst: int8[msg.data.size()]; meta3: {height, width, resolution}. Returns msg.data.size().
+    long ref_map_layer_msg(void *h, int layer, int8_t *dst, double *meta3)
+    {
+        NavMap *m = static_cast<NavMap *>(h);
+        nav_msgs::OccupancyGrid msg;
+        switch (layer)
+        {
+        case 1:
+            msg = m->getStaticMapMsg();
+            break;
+        case 3:
+            msg = m->getGoalMapMsg();
+            break;
+        case 8:
+            msg = m->getVoroMapMsg();
+            break;
+        case 0:
+            msg = m->getStaticOrigMapMsg();
+            break;
+        case 2:
+            msg = m->getInflationOrigMapMsg();
+            break;
+        default:
+            return -1;
+        }
+        if (meta3)
+            meta3[0] = msg.info.height, meta3[1] = msg.info.width, meta3[2] = msg.info.resolution;
+        if (dst)
+            std::memcpy(dst, msg.data.data(), msg.data.size());
+        return (long)msg.data.size();
+    }
     // NavMap point lookups (nav_map.cpp:249-277), layer: 0 = downsampled, 1 = orig, 2 = inflated orig
     int ref_map_point_in_collision(void *h, int layer, int i, int j)
     {

@@ -170,6 +170,20 @@ class RefMap:
         return out.reshape(shape) if n == shape[0] * shape[1] else out
 
 
+def ref_layer_msg(rmap, name):
+    """msg.data (int8, flat) and (height, width, resolution) of NavMap::get*MapMsg (nav_map.cpp:654-716) for the layer
+    'static', 'goal', 'voronoi', 'static_orig' or 'inflate_orig'."""
+    lid = LAYERS[name][0]
+    meta = np.zeros(3, dtype=np.float64)
+    L = rmap.lib.L
+    L.ref_map_layer_msg.restype = C.c_long
+    n = L.ref_map_layer_msg(C.c_void_p(rmap.h), C.c_int(lid), None, C.c_void_p(meta.ctypes.data))
+    out = np.zeros(max(n, 0), dtype=np.int8)
+    if n > 0:
+        L.ref_map_layer_msg(C.c_void_p(rmap.h), C.c_int(lid), C.c_void_p(out.ctypes.data), C.c_void_p(meta.ctypes.data))
+    return out, (int(meta[0]), int(meta[1]), float(meta[2]))
+
+
 class RefPlanner:
     """Configured planner bound to a RefMap (uses the parameter store as set when created)."""
 
