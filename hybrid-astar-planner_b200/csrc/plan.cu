@@ -649,10 +649,19 @@ static int plan_pass(mpros_ctx *c, PlanBatchArgs &a, int pass, int node_cap, int
     size_t free_b = 0, total_b = 0;
     MPROS_CUDA(cudaMemGetInfo(&free_b, &total_b));
     size_t budget = (free_b + S.ws_bytes) / 2;
+    // team = one CTA (default) or a cluster of two CTAs on the two SMs of a TPC (MPROS_PLAN_MODE=cluster; plan_team.cuh).
+    // Measured on the 16 384-query synthetic batch: CTA teams 1.57 s (296 teams, 6.8-7.5 us per iteration alone, ~11 us with
+    // two teams per SM), CTA pairs 2.24 s (148 teams, 8.2-8.6 us per iteration alone AND loaded: no interference between
+    // co-resident teams any more, but the two cluster barriers cost ~4 k cycles per iteration). Results are identical.
+    const char *mode_env = std::getenv("MPROS_PLAN_MODE");
+    const bool cluster = mode_env && std::strcmp(mode_env, "cluster") == 0;
     int resident = 0;
-    MPROS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, plan_team_kernel<kTeamWarps, kTeamMinBlocks>, kTeamWarps * 32, 0));
-    // one team (CTA) per query; every resident team owns one workspace
-    int blocks = prop.multiProcessorCount * std::max(1, resident);
+    if (cluster)
+        MPROS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, plan_cluster_kernel<kTeamWarps, kTeamMinBlocks>, kTeamWarps * 32, 0));
+    else
+        MPROS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, plan_team_kernel<kTeamWarps, kTeamMinBlocks>, kTeamWarps * 32, 0));
+    // one team per query at a time; every resident team owns one workspace
+    int blocks = (cluster ? prop.multiProcessorCount / 2 : prop.multiProcessorCount) * std::max(1, resident);
     blocks = std::min(blocks, n_run);
     blocks = (int)std::min<long long>(blocks, std::max<long long>(1, (long long)(budget / L.stride)));
     if (max_warps > 0)
@@ -701,7 +710,10 @@ static int plan_pass(mpros_ctx *c, PlanBatchArgs &a, int pass, int node_cap, int
         cudaEventCreate(&e1);
         cudaEventRecord(e0, c->stream);
     }
-    plan_team_kernel<kTeamWarps, kTeamMinBlocks><<<blocks, kTeamWarps * 32, 0, c->stream>>>(c->view(), c->pv, a);
+    if (cluster)
+        plan_cluster_kernel<kTeamWarps, kTeamMinBlocks><<<2 * blocks, kTeamWarps * 32, 0, c->stream>>>(c->view(), c->pv, a);
+    else
+        plan_team_kernel<kTeamWarps, kTeamMinBlocks><<<blocks, kTeamWarps * 32, 0, c->stream>>>(c->view(), c->pv, a);
     MPROS_LAUNCH_CHECK(c);
     if (dbg)
     {
@@ -727,8 +739,8 @@ static int plan_pass(mpros_ctx *c, PlanBatchArgs &a, int pass, int node_cap, int
                 std::fprintf(stderr, "[mpros]   %-18s %9.1f\n", names2[k - 16], h[k] / its);
         }
 #endif
-        std::fprintf(stderr, "[mpros] plan pass %d: %d queries, node_cap %d, %d teams x %d warps, %.1f MB/team, %.3f ms\n", pass, n_run,
-                     node_cap, blocks, kTeamWarps, L.stride / 1048576.0, ms);
+        std::fprintf(stderr, "[mpros] plan pass %d: %d queries, node_cap %d, %d teams (%s) x %d warps, %.1f MB/team, %.3f ms\n", pass, n_run,
+                     node_cap, blocks, cluster ? "CTA pairs" : "CTAs", kTeamWarps, L.stride / 1048576.0, ms);
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
     }

@@ -71,6 +71,11 @@ struct TeamShared
     unsigned long long buf_key[2][kMaxPrim];
     uint32_t buf_id[2][kMaxPrim];
     int buf_n[2];
+    PlanNode buf_node[2][kMaxPrim];  // node records of the buffered children: the pop never waits for global memory
+    PlanNode root_node;              // node record of the heap root, fetched in the background once the heap is restored
+    uint32_t root_node_id;
+    uint32_t closed_marks[kMaxPrim]; // nodes marked CLOSE by this iteration's inserts (newer than root_node)
+    int n_marks;
     // Reeds-Shepp shot
     double cand_cost[NW];
     int cand_idx[NW];
@@ -566,7 +571,7 @@ template <int NW>
 __device__ __noinline__ void team_insert_sequential(PlanNode *nodes, const ClosedSet &closed, TeamShared<NW> &S, int P, int par_cur, int node_cap)
 {
     uint32_t n_nodes = S.n_nodes;
-    int nb = 0;
+    int nb = 0, nm = 0;
     for (int c = 0; c < P; ++c)
     {
         if (!S.c_need[c])
@@ -584,13 +589,20 @@ __device__ __noinline__ void team_insert_sequential(PlanNode *nodes, const Close
             break;
         }
         if (f2 && on < kGoalNode)
+        {
             nodes[on].closed = 1;
+            S.closed_marks[nm++] = on;
+            for (int b2 = 0; b2 < nb; ++b2) // a sibling inserted a moment ago
+                if (S.buf_id[par_cur][b2] == on)
+                    S.buf_node[par_cur][b2].closed = 1;
+        }
         closed_store(closed, sl, S.c_idx[c], tg, n_nodes);
         PlanNode nn;
         nn.x = S.c_x[c], nn.y = S.c_y[c], nn.yaw = S.c_yaw[c], nn.steer = S.c_steer[c], nn.g = tg, nn.parent = S.cur_id;
         nn.s = S.c_s[c], nn.c = S.c_c[c];
         nn.dir = (int8_t)(S.c_dir[c] > 0 ? 1 : -1), nn.closed = 0, nn.pad = 0;
         nodes[n_nodes] = nn;
+        S.buf_node[par_cur][nb] = nn;
         S.buf_key[par_cur][nb] = (unsigned long long)__double_as_longlong(tg + S.c_h[c]);
         S.buf_id[par_cur][nb] = n_nodes;
         ++nb;
@@ -598,6 +610,169 @@ __device__ __noinline__ void team_insert_sequential(PlanNode *nodes, const Close
     }
     S.buf_n[par_cur] = nb;
     S.n_nodes = n_nodes;
+    S.n_marks = nm;
+}
+
+// ---- heuristics rounds (hybrid_a_star.cpp:248-264), shared by the single-CTA team and the heuristic CTA of a cluster -----
+// h = max(h1 * res, RS distance) * 1.001 for the children flagged in needmask. Lanes = (child, symmetry image): child
+// c = base + (lane >> 2), image q = lane & 3. Round A: the two CSC formulas on warps 0 and 1; any valid candidate is an
+// upper bound of the RS distance, so when rho * min(CSC) <= h1 for every needed child of the group of 8 the other nine
+// formulas cannot change max(h1, h2) and round B is skipped. Round B: formulas 2..10 spread over warps 0..NW-2.
+struct HeurView
+{
+    double (*img)[4][7];      // [child][image]{x, y, phi, xb, yb, sin phi, cos phi}
+    int *h1;                  // goal-map value per child
+    double (*hf)[kMaxPrim];   // [formula][child] minimum over the four images
+    int *skipg;               // per group of 8 children: settled by round A alone
+};
+template <int NW, bool CTA_WIDE>
+__device__ __forceinline__ void heur_sync()
+{
+    if (CTA_WIDE)
+        __syncthreads();
+    else
+        team_sync<NW>();
+}
+template <int NW, bool CTA_WIDE>
+__device__ __forceinline__ void heur_rounds(const MapView &m, const PlannerView &p, const HeurView &V, unsigned needmask, int P, int writer_warp,
+                                            Prof &pf)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int base = 0; base < P; base += 8)
+    {
+        if (((needmask >> base) & 0xffu) == 0)
+            continue;
+        const int c = base + (lane >> 2), q = lane & 3;
+        const bool live = c < P && ((needmask >> c) & 1u);
+        const double *im = V.img[live ? c : 0][q];
+        if (warp < 2)
+        {
+            double Lf = live ? ompl_formula(warp, im[0], im[1], im[2], im[3], im[4], im[5], im[6]) : DBL_MAX;
+            Lf = fmin(Lf, __shfl_xor_sync(kFull, Lf, 1));
+            Lf = fmin(Lf, __shfl_xor_sync(kFull, Lf, 2));
+            if (live && q == 0)
+                V.hf[warp][c] = Lf;
+        }
+        heur_sync<NW, CTA_WIDE>(); // (2)
+        if (threadIdx.x == 0) pf.mark(5);
+        bool ok = true;
+        {
+            const int ce = base + lane;
+            if (lane < 8 && ce < P && ((needmask >> ce) & 1u))
+            {
+                const double ub = p.min_r * fmin(V.hf[0][ce], V.hf[1][ce]);
+                ok = ub <= (double)V.h1[ce] * m.res;
+            }
+        }
+#ifdef MPROS_EXPERIMENT_SKIP_B // instruction-cache experiment (wrong heuristics): never run the nine non-CSC formulas
+        const bool skip = true || __all_sync(kFull, ok);
+#else
+        const bool skip = __all_sync(kFull, ok);
+#endif
+        if (warp == writer_warp && lane == 0)
+            V.skipg[base >> 3] = skip;
+        if (!skip)
+        {
+            if (threadIdx.x == 0) pf.count(14);
+            if (warp < NW - 1)
+            {
+#pragma unroll 1
+                for (int sl = 0; sl < team_formula_b_slots<NW>(); ++sl)
+                {
+                    const int k = team_formula_b<NW>(warp, sl);
+                    if (k < 0)
+                        continue;
+                    double Lf = live ? ompl_formula(k, im[0], im[1], im[2], im[3], im[4], im[5], im[6]) : DBL_MAX;
+                    Lf = fmin(Lf, __shfl_xor_sync(kFull, Lf, 1));
+                    Lf = fmin(Lf, __shfl_xor_sync(kFull, Lf, 2));
+                    if (live && q == 0)
+                        V.hf[k][c] = Lf;
+                }
+            }
+            heur_sync<NW, CTA_WIDE>(); // (3)
+        }
+        if (threadIdx.x == 0) pf.mark(6);
+    }
+}
+// one child's heuristic from the per-formula minima (same combination as the sequential CSC/CCC/CCCC, CCSC, CCSCC passes)
+__device__ __forceinline__ double heur_combine(const MapView &m, const PlannerView &p, const HeurView &V, int c)
+{
+    double plain = fmin(V.hf[0][c], V.hf[1][c]), ccsc = DBL_MAX, ccscc = DBL_MAX;
+    if (!V.skipg[c >> 3])
+    {
+        plain = fmin(fmin(plain, fmin(V.hf[2][c], V.hf[3][c])), fmin(V.hf[4][c], V.hf[5][c]));
+        ccsc = fmin(fmin(V.hf[6][c], V.hf[7][c]), fmin(V.hf[8][c], V.hf[9][c]));
+        ccscc = V.hf[10][c];
+    }
+    const double h1v = (double)V.h1[c] * m.res; // getGoalCost: cost_ * map_resolution_
+    return fmax(h1v, ompl_combine(p.min_r, plain, ccsc, ccscc)) * (1 + 1e-3);
+}
+
+// ---- cluster mode: a team is a CLUSTER of two CTAs on the two SMs of a TPC ------------------------------------------------
+// Why: the planner is bound by instruction-cache misses (ncu: sm__icc hit rate 66-72 %, SM time = misses x ~38 cycles): one
+// A* iteration walks ~45-54 KB of code (search + eleven FP64 Reeds-Shepp formulas with their libdevice routines) against a
+// ~32 KB per-SM instruction cache, so every line is fetched again every iteration. CTA rank 0 ("search": open list,
+// expansion, footprint tests, closed set, inserts) and CTA rank 1 ("heuristic": the OMPL-equivalent RS distance) each run
+// HALF of that code, and the hardware places rank 0 on the even and rank 1 on the odd SM of a TPC (measured: no SM ever gets
+// both ranks), so each SM's instruction working set fits its cache. The children's symmetry images travel to the heuristic
+// CTA through distributed shared memory (the search CTA's closed-set warp writes them straight into the peer's shared
+// memory), the heuristics come back the same way; two cluster barriers (arrive.release / wait.acquire) per iteration order
+// the exchange.
+struct HeurShared
+{
+    double img[kMaxPrim][4][7];
+    double hf[11][kMaxPrim];
+    int h1[kMaxPrim];
+    int skipg[(kMaxPrim + 7) / 8];
+    unsigned needmask;
+    int P;
+    int cmd; // 0: work, 1: exit
+#ifdef MPROS_PROFILE
+    unsigned long long prof[24];
+#endif
+};
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+template <typename T>
+__device__ __forceinline__ T *cluster_peer(T *local, unsigned rank)
+{
+    // generic address of the same shared-memory object in CTA `rank` of the cluster
+    unsigned long long out;
+    asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"((unsigned long long)local), "r"(rank));
+    return reinterpret_cast<T *>(out);
+}
+
+// the heuristic CTA (cluster rank 1): serve one request per iteration of the search CTA until told to exit
+template <int NW>
+__device__ void heur_cta_loop(const MapView &m, const PlannerView &p, HeurShared &H, double *peer_c_h)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Prof pf;
+#ifdef MPROS_PROFILE
+    pf.start(H.prof); // marks of the shared heuristics code land here and are not reported
+#endif
+    HeurView V{H.img, H.h1, H.hf, H.skipg};
+    while (true)
+    {
+        cluster_arrive(); // X: the search CTA has written images, h1, needmask
+        cluster_wait();
+        if (H.cmd != 0)
+            break;
+        const unsigned needmask = H.needmask;
+        const int P = H.P;
+        if (needmask)
+        {
+            heur_rounds<NW, true>(m, p, V, needmask, P, 0, pf);
+            if (warp == 0)
+            {
+                __syncwarp();
+                if (lane < P && ((needmask >> lane) & 1u))
+                    peer_c_h[lane] = heur_combine(m, p, V, lane);
+            }
+        }
+        cluster_arrive(); // Y: heuristics are in the search CTA's shared memory
+        cluster_wait();
+    }
 }
 
 // ---- heap warp --------------------------------------------------------------------------------------------------------
@@ -616,9 +791,9 @@ __device__ __forceinline__ int open_argmin(unsigned long long key, uint32_t id, 
     return __ffs(__ballot_sync(kFull, a2 && id == m3)) - 1;
 }
 
-template <int NW>
+template <int NW, bool CL>
 __device__ void plan_team_query(const MapView &m, const PlannerView &p, const PlanBatchArgs &a, int q, char *ws, uint32_t tag,
-                                TeamShared<NW> &S)
+                                TeamShared<NW> &S, HeurShared *Hpeer)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -660,6 +835,8 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
         S.n_nodes = 0, S.goal_parent = kNoNode, S.goal_g = -1.0, S.goal_traj_n = 0, S.chain = 0;
         S.n_prim = S.n_shots = S.n_coll = 0;
         S.buf_n[0] = S.buf_n[1] = 0;
+        S.root_node_id = kNoNode;
+        S.n_marks = 0;
         S.bfs.blocked = reinterpret_cast<uint32_t *>(ws + L.blocked_off);
         S.bfs.f0 = reinterpret_cast<uint32_t *>(ws + L.f0_off);
         S.bfs.f1 = reinterpret_cast<uint32_t *>(ws + L.f1_off);
@@ -728,7 +905,7 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                 // the start node enters the open list through the insertion buffer of "iteration -1"
                 S.buf_key[1][0] = (unsigned long long)__double_as_longlong(0.0 + S.c_h[0]);
                 S.buf_id[1][0] = 0;
-
+                S.buf_node[1][0] = n;
                 S.buf_n[1] = 1;
                 S.n_nodes = 1;
             }
@@ -789,8 +966,18 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                         break;
                     }
                     cur = __shfl_sync(kFull, id, win);
-                    cn = nodes[cur];
                     const bool from_heap = (win == 31) && heap.size > 0;
+                    if (!from_heap)
+                        cn = S.buf_node[par_prev][win]; // a child of the last expansion: still in shared memory
+                    else if (S.root_node_id == cur)
+                    {
+                        cn = S.root_node; // fetched in the background; CLOSE marks newer than the fetch are in closed_marks
+                        const bool marked = lane < S.n_marks && S.closed_marks[lane] == cur;
+                        if (__any_sync(kFull, marked))
+                            cn.closed = 1;
+                    }
+                    else
+                        cn = nodes[cur];
                     if (!from_heap && lane == win)
                         bvalid = false; // consumed straight from the buffer, never touches the heap
                     if (!cn.closed)
@@ -808,6 +995,7 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
             if (is_heap && lane == 0) pf.mark(10);
             if (lane == 0)
             {
+                S.n_marks = 0;
                 S.flag = flag;
                 if (flag == 0)
                 {
@@ -819,6 +1007,8 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                 }
             }
             __syncthreads(); // (a) the popped node is public
+            if (CL && flag == 0)
+                cluster_arrive(); // X of this iteration: the heap warp contributes nothing to the request, so it arrives at once
             if (flag == 0)
             {
                 // -- background: restore the heap while the other warps expand
@@ -839,8 +1029,36 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                     heap.size++;
                     __syncwarp();
                 }
+                // still in the background: drop roots that are already CLOSE (stale entries of nodes that were re-inserted
+                // with a smaller g; each costs a full sift-down) and fetch the surviving root's node record, so that the next
+                // pop is an arg-min over shared memory
+                while (heap.size > 0)
+                {
+                    const uint32_t rid = hi(heap, 0);
+                    if (lane < 4)
+                        reinterpret_cast<uint4 *>(&S.root_node)[lane] = reinterpret_cast<const uint4 *>(&nodes[rid])[lane];
+                    __syncwarp();
+                    if (!S.root_node.closed)
+                    {
+                        if (lane == 0)
+                            S.root_node_id = rid;
+                        break;
+                    }
+                    unsigned long long fk;
+                    heap_pop_warp(heap, fk);
+                }
+                if (heap.size == 0 && lane == 0)
+                    S.root_node_id = kNoNode;
+                __syncwarp();
             }
             if (is_heap && lane == 0) pf.mark(11);
+            if (CL && flag == 0)
+            {
+                // the cluster barriers count every thread of both CTAs: X (request, arrived above) and Y (heuristics)
+                cluster_wait();
+                cluster_arrive();
+                cluster_wait();
+            }
         }
         else
         {
@@ -864,6 +1082,19 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
             {
                 if (!a.optimal && tid == 0)
                     S.stop = 1; // first successful shot ends the search (:725-728)
+                if (CL)
+                {
+                    // no expansion in this iteration: an empty request keeps the two CTAs in step
+                    if (tid == 0)
+                    {
+                        Hpeer->needmask = 0;
+                        Hpeer->cmd = 0;
+                    }
+                    cluster_arrive();
+                    cluster_wait();
+                    cluster_arrive();
+                    cluster_wait();
+                }
             }
             else
             {
@@ -959,7 +1190,7 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                         const double sphi = S.sc[1][c][0], cphi = S.sc[1][c][1];
                         const double nxb = inx * cphi + iny * sphi, nyb = inx * sphi - iny * cphi;
                         const bool fx = (q == 1 || q == 3), fy = (q == 2 || q == 3), fp = (q == 1 || q == 2);
-                        double *o = S.img[c][q];
+                        double *o = CL ? Hpeer->img[c][q] : S.img[c][q]; // cluster mode: straight into the heuristic CTA's shared memory
                         o[0] = fx ? -inx : inx, o[1] = fy ? -iny : iny, o[2] = fp ? -dth : dth, o[3] = fx ? -nxb : nxb, o[4] = fy ? -nyb : nyb;
                         o[5] = fp ? -sphi : sphi, o[6] = cphi;
                     }
@@ -1031,58 +1262,32 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                 }
                 if (tid == 0) pf.mark(3);
                 const unsigned needmask = __ballot_sync(kFull, need);
-                const int hn = __popc(needmask);
-                // heuristics (hybrid_a_star.cpp:248-264): h = max(h1 * res, RS distance) * 1.001; lanes = (entry, image)
-                for (int base = 0; base < hn; base += 8)
+                if (CL)
                 {
-                    const int e = base + (lane >> 2), q = lane & 3;
-                    const bool live = e < hn;
-                    const int c = live ? (int)__fns(needmask, 0, e + 1) : 0;
-                    const double *im = S.img[c][q];
-                    // round A: the two CSC formulas. Any valid candidate is an upper bound of the RS distance.
-                    if (warp < 2)
+                    // hand the request to the heuristic CTA (rank 1): goal-map values and the set of children; the images are
+                    // already there. X: request complete; Y: S.c_h holds the heuristics.
+                    if (warp == 0)
                     {
-                        double Lf = live ? ompl_formula(warp, im[0], im[1], im[2], im[3], im[4], im[5], im[6]) : DBL_MAX;
-                        Lf = fmin(Lf, __shfl_xor_sync(kFull, Lf, 1));
-                        Lf = fmin(Lf, __shfl_xor_sync(kFull, Lf, 2));
-                        if (live && q == 0)
-                            S.hf[warp][c] = Lf;
-                    }
-                    team_sync<NW>(); // (2)
-                    if (tid == 0) pf.mark(5);
-                    // when rho * min(CSC) <= h1 for every entry of the group the other nine formulas cannot change max(h1, h2)
-                    bool ok = true;
-                    if (lane < 8 && base + lane < hn)
-                    {
-                        const int ce = (int)__fns(needmask, 0, base + lane + 1);
-                        const double ub = p.min_r * fmin(S.hf[0][ce], S.hf[1][ce]);
-                        ok = ub <= (double)S.c_h1[ce] * m.res;
-                    }
-#ifdef MPROS_EXPERIMENT_SKIP_B // instruction-cache experiment (wrong heuristics): never run the nine non-CSC formulas
-                    const bool skip = true || __all_sync(kFull, ok);
-#else
-                    const bool skip = __all_sync(kFull, ok);
-#endif
-                    if (warp == CLOSED_W && lane == 0)
-                        S.h_skipg[base >> 3] = skip;
-                    if (!skip)
-                    {
-                        if (tid == 0) pf.count(14);
-#pragma unroll 1
-                        for (int sl = 0; sl < team_formula_b_slots<NW>(); ++sl)
+                        if (lane < P)
+                            Hpeer->h1[lane] = S.c_h1[lane];
+                        if (lane == 0)
                         {
-                            const int k = team_formula_b<NW>(warp, sl);
-                            if (k < 0)
-                                continue;
-                            double Lf = live ? ompl_formula(k, im[0], im[1], im[2], im[3], im[4], im[5], im[6]) : DBL_MAX;
-                            Lf = fmin(Lf, __shfl_xor_sync(kFull, Lf, 1));
-                            Lf = fmin(Lf, __shfl_xor_sync(kFull, Lf, 2));
-                            if (live && q == 0)
-                                S.hf[k][c] = Lf;
+                            Hpeer->needmask = needmask;
+                            Hpeer->P = P;
+                            Hpeer->cmd = 0;
                         }
-                        team_sync<NW>(); // (3)
                     }
+                    cluster_arrive();
+                    cluster_wait();
+                    if (tid == 0) pf.mark(5);
+                    cluster_arrive();
+                    cluster_wait();
                     if (tid == 0) pf.mark(6);
+                }
+                else
+                {
+                    HeurView V{S.img, S.c_h1, S.hf, S.h_skipg};
+                    heur_rounds<NW, false>(m, p, V, needmask, P, CLOSED_W, pf);
                 }
                 // closed-set compare / insert in primitive order (closed-set warp). Common case: the children that need an
                 // insert touch distinct hash slots -> slot / node stores and close-marks run one lane per child, the new open
@@ -1094,17 +1299,12 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                     pf.restart();
                     if (need)
                     {
-                        const int c = lane, e = __popc(needmask & ((1u << lane) - 1u));
-                        double plain = fmin(S.hf[0][c], S.hf[1][c]), ccsc = DBL_MAX, ccscc = DBL_MAX;
-                        if (!S.h_skipg[e >> 3])
+                        if (!CL)
                         {
-                            plain = fmin(fmin(plain, fmin(S.hf[2][c], S.hf[3][c])), fmin(S.hf[4][c], S.hf[5][c]));
-                            ccsc = fmin(fmin(S.hf[6][c], S.hf[7][c]), fmin(S.hf[8][c], S.hf[9][c]));
-                            ccscc = S.hf[10][c];
+                            HeurView V{S.img, S.c_h1, S.hf, S.h_skipg};
+                            S.c_h[lane] = heur_combine(m, p, V, lane);
                         }
-                        const double h1v = (double)S.c_h1[c] * m.res; // getGoalCost: cost_ * map_resolution_
-                        S.c_h[c] = fmax(h1v, ompl_combine(p.min_r, plain, ccsc, ccscc)) * (1 + 1e-3);
-                        S.c_need[c] = 1;
+                        S.c_need[lane] = 1;
                     }
                     else if (lane < P)
                         S.c_need[lane] = 0;
@@ -1126,9 +1326,15 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                         }
                         else
                         {
+                            const bool mk = ins && pr_found && pr_old < kGoalNode;
+                            const unsigned mkmask = __ballot_sync(kFull, mk);
+                            if (mk)
+                                S.closed_marks[__popc(mkmask & ((1u << lane) - 1u))] = pr_old;
+                            if (lane == 0)
+                                S.n_marks = __popc(mkmask);
                             if (ins)
                             {
-                                if (pr_found && pr_old < kGoalNode)
+                                if (mk)
                                     nodes[pr_old].closed = 1;
                                 closed_store(closed, slot, S.c_idx[lane], S.c_g[lane], id);
                                 PlanNode nn;
@@ -1136,6 +1342,7 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                                 nn.s = S.c_s[lane], nn.c = S.c_c[lane];
                                 nn.parent = S.cur_id, nn.dir = (int8_t)(S.c_dir[lane] > 0 ? 1 : -1), nn.closed = 0, nn.pad = 0;
                                 nodes[id] = nn;
+                                S.buf_node[par_cur][rank] = nn;
                                 S.buf_key[par_cur][rank] = (unsigned long long)__double_as_longlong(S.c_g[lane] + S.c_h[lane]);
                                 S.buf_id[par_cur][rank] = id;
                             }
@@ -1301,8 +1508,55 @@ __global__ void __launch_bounds__(NW * 32, MINB) plan_team_kernel(const __grid_c
             break;
         int q = a.todo ? a.todo[t] : t;
         ++local_gen;
-        plan_team_query<NW>(m, p, a, q, ws, a.tag_base + local_gen, S);
+        plan_team_query<NW, false>(m, p, a, q, ws, a.tag_base + local_gen, S, nullptr);
     }
+}
+
+// Cluster mode (see "cluster mode" above): CTA pair per team, blockIdx.x >> 1 = team, cluster rank = role.
+template <int NW, int MINB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NW * 32, MINB)
+    plan_cluster_kernel(const __grid_constant__ MapView m, const __grid_constant__ PlannerView p, const __grid_constant__ PlanBatchArgs a)
+{
+    // the search CTA uses S, the heuristic CTA uses H: same storage (each CTA of the pair has its own shared memory)
+    __shared__ union ClusterShared
+    {
+        TeamShared<NW> S;
+        HeurShared H;
+    } U;
+    TeamShared<NW> &S = U.S;
+    HeurShared &H = U.H;
+    unsigned rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    // both CTAs must be running before either touches the other's shared memory
+    cluster_arrive();
+    cluster_wait();
+    if (rank == 1)
+    {
+        heur_cta_loop<NW>(m, p, H, cluster_peer(&S.c_h[0], 0));
+        return;
+    }
+    HeurShared *Hpeer = cluster_peer(&H, 1);
+    char *ws = a.ws + (size_t)(blockIdx.x >> 1) * a.L.stride;
+    uint32_t local_gen = 0;
+    const int total = a.todo ? a.n_todo : a.nq;
+    while (true)
+    {
+        __syncthreads();
+        if (threadIdx.x == 0)
+            S.q = (int)atomicAdd(a.counter, 1u);
+        __syncthreads();
+        const int t = S.q;
+        if (t >= total)
+            break;
+        int q = a.todo ? a.todo[t] : t;
+        ++local_gen;
+        plan_team_query<NW, true>(m, p, a, q, ws, a.tag_base + local_gen, S, Hpeer);
+    }
+    // release the heuristic CTA: the last X of this cluster carries the exit command
+    if (threadIdx.x == 0)
+        Hpeer->cmd = 1;
+    cluster_arrive();
+    cluster_wait();
 }
 
 } // namespace mpros
