@@ -61,6 +61,15 @@ def shipped_params(ds=SYN_DS):
     }
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes (read + write) per launch of `kernel` from the committed ncu capture of this very command
+    (profiles/r01_traffic.json, written from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`); None if absent."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     try:
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
@@ -371,7 +380,7 @@ def run_b200(args):
     col_e2e = world * n * col_steps / (col_e2e_ms * 1e-3)
     peak, peak_kind = measured_peak_gbs()
     col_roof = {"bound": "hbm", "achieved": n * B_CHECK / (float(np.mean(col_ms)) * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "traffic": None, "kernel": "collision_poses_kernel", "kernel_ms": float(np.mean(col_ms)), "peak_source": peak_kind,
+                "traffic": ncu_traffic("collision_poses_kernel"), "kernel": "collision_poses_kernel", "kernel_ms": float(np.mean(col_ms)), "peak_source": peak_kind,
                 "algorithmic_bytes_per_unit": B_CHECK}
     col_roof["frac"] = col_roof["achieved"] / peak
     del poses_d, verd_d
@@ -439,7 +448,7 @@ def run_b200(args):
                     "e2e": {"value": world * nq * args.steps / (e2e_ms * 1e-3), "unit": "plans/s", "h2d_bytes_per_step": nq * 48,
                             "d2h_bytes_per_step": nq * (4 + 8 + 4 + PATH_CAP * 40 + 48)},
                     "gpu_launches": int(launches),
-                    "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("plan_team_kernel"),
                                  "kernel": "plan_team_kernel", "kernel_ms": k_ms, "peak_source": peak_kind,
                                  "algorithmic_bytes_per_launch": algo_bytes,
                                  "note": "latency/FP64-issue bound (sequential A* per query, FP64 transcendentals), not HBM bound; see DESIGN.md"},

@@ -730,12 +730,12 @@ static int plan_pass(mpros_ctx *c, PlanBatchArgs &a, int pass, int node_cap, int
             const char *names[12] = {"wait_pop", "shot", "expand", "h1_peek", "bfs_steps", "h2_roundA", "h2_roundB", "h2_tail", "insert", "wait_heap",
                                      "heap_pop", "heap_restore"};
             double its = (double)h[12];
-            std::fprintf(stderr, "[mpros] profile: %.0f iterations, %.3f bfs steps/it, %.3f roundB/it, %.4f shots/it; cycles per iteration:\n", its,
+            std::fprintf(stderr, "[mpros] profile: %.0f iterations, %.3f (bfs steps + stale roots dropped)/it, %.3f (roundB + sequential heap pushes)/it, %.4f shots/it; cycles per iteration:\n", its,
                          h[13] / its, h[14] / its, h[15] / its);
             for (int k = 0; k < 12; ++k)
                 std::fprintf(stderr, "[mpros]   %-12s %9.1f\n", names[k], h[k] / its);
-            const char *names2[8] = {"col:pose+sincos", "col:footprint", "closed:A loads", "closed:B-D", "closed:insert", "", "", ""};
-            for (int k = 16; k < 21; ++k)
+            const char *names2[8] = {"col:pose+sincos", "col:footprint", "closed:A loads", "closed:B-D", "closed:insert", "heap:remove root", "heap:pushes", "heap:(rest=elim+fetch in heap_restore)"};
+            for (int k = 16; k < 23; ++k)
                 std::fprintf(stderr, "[mpros]   %-18s %9.1f\n", names2[k - 16], h[k] / its);
         }
 #endif

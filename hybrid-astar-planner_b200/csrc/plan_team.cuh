@@ -955,8 +955,8 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                     bool valid = bvalid;
                     if (lane == 31 && heap.size > 0)
                     {
-                        key = hk(heap, 0);
-                        id = hi(heap, 0);
+                        key = S.heap_key[0]; // the heap top lives in shared memory
+                        id = S.heap_id[0];
                         valid = true;
                     }
                     const int win = open_argmin(key, id, valid);
@@ -1017,7 +1017,29 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                     unsigned long long fk;
                     heap_pop_warp(heap, fk);
                 }
+                if (is_heap && lane == 0) pf.mark(21);
                 unsigned todo = __ballot_sync(kFull, bvalid);
+                if (todo)
+                {
+                    // common case: none of the new entries beats its parent (children mostly cost more than what is already
+                    // open), so all of them are appended at once; one parent read per lane instead of a chain per entry
+                    const int rank = __popc(todo & ((1u << lane) - 1u));
+                    const int pos = heap.size + rank;
+                    bool up = false;
+                    if (bvalid && pos > 0)
+                    {
+                        const int parent = (pos - 1) >> 5;
+                        up = parent >= heap.size ? true : heap_less(bkey, bid, hk(heap, parent), hi(heap, parent));
+                    }
+                    if (!__any_sync(kFull, up) && heap.size > 0)
+                    {
+                        if (bvalid)
+                            hset(heap, pos, bkey, bid);
+                        heap.size += __popc(todo);
+                        todo = 0;
+                        __syncwarp();
+                    }
+                }
                 while (todo)
                 {
                     const int b = __ffs(todo) - 1;
@@ -1028,13 +1050,15 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                         heap_push_lane0(heap, k, kid);
                     heap.size++;
                     __syncwarp();
+                    if (is_heap && lane == 0) pf.count(14);
                 }
+                if (is_heap && lane == 0) pf.mark(22);
                 // still in the background: drop roots that are already CLOSE (stale entries of nodes that were re-inserted
                 // with a smaller g; each costs a full sift-down) and fetch the surviving root's node record, so that the next
                 // pop is an arg-min over shared memory
                 while (heap.size > 0)
                 {
-                    const uint32_t rid = hi(heap, 0);
+                    const uint32_t rid = S.heap_id[0];
                     if (lane < 4)
                         reinterpret_cast<uint4 *>(&S.root_node)[lane] = reinterpret_cast<const uint4 *>(&nodes[rid])[lane];
                     __syncwarp();
@@ -1046,6 +1070,7 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                     }
                     unsigned long long fk;
                     heap_pop_warp(heap, fk);
+                    if (is_heap && lane == 0) pf.count(13);
                 }
                 if (heap.size == 0 && lane == 0)
                     S.root_node_id = kNoNode;
@@ -1107,26 +1132,35 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                 uint32_t pr_old = kNoNode, pr_slot = 0xffffffffu - lane;
                 if (warp < COL_W)
                 {
+                    // (i) end pose and both sin/cos pairs of every child of this warp: lane 0 the child yaw (footprint test,
+                    // node record), lane 1 goal yaw - child yaw (symmetry images) - one call, two lanes
                     for (int c = warp; c < P; c += COL_W)
                     {
-                        double nx = 0, ny = 0, nyaw = 0, steer = 0, direc = 1, ns = 0, nc = 1;
-                        if (lane == 0)
+                        if (lane < 2)
                         {
+                            double nx, ny, nyaw, steer, direc, sn, cs;
                             primitive_end_pose(p, c, cn.x, cn.y, cn.yaw, cn.s, cn.c, nx, ny, nyaw, steer, direc);
-                            dm::sincos_(nyaw, &ns, &nc);
-                        }
-                        nx = __shfl_sync(kFull, nx, 0), ny = __shfl_sync(kFull, ny, 0);
-                        ns = __shfl_sync(kFull, ns, 0), nc = __shfl_sync(kFull, nc, 0);
-                        if (tid == 0) pf.mark(16);
-                        bool hit = warp_footprint_collision(m, p, nx, ny, ns, nc);
-                        if (tid == 0) pf.mark(17);
-                        if (lane == 0)
-                        {
-                            S.c_x[c] = nx, S.c_y[c] = ny, S.c_yaw[c] = nyaw, S.c_s[c] = ns, S.c_c[c] = nc;
-                            S.c_steer[c] = steer, S.c_dir[c] = direc;
-                            S.c_alive[c] = hit ? 0 : 1;
+                            dm::sincos_(lane ? S.gyaw - nyaw : nyaw, &sn, &cs);
+                            S.sc[lane][c][0] = sn, S.sc[lane][c][1] = cs;
+                            if (lane == 0)
+                            {
+                                S.c_x[c] = nx, S.c_y[c] = ny, S.c_yaw[c] = nyaw, S.c_s[c] = sn, S.c_c[c] = cs;
+                                S.c_steer[c] = steer, S.c_dir[c] = direc;
+                            }
                         }
                     }
+                    __syncwarp();
+                    // the closed-set warp builds the images from these as soon as all footprint warps have arrived
+                    asm volatile("bar.arrive 2, %0;" ::"r"((COL_W + 1) * 32) : "memory");
+                    if (tid == 0) pf.mark(16);
+                    // (ii) footprint tests, one lane per probe
+                    for (int c = warp; c < P; c += COL_W)
+                    {
+                        const bool hit = warp_footprint_collision(m, p, S.c_x[c], S.c_y[c], S.c_s[c], S.c_c[c]);
+                        if (lane == 0)
+                            S.c_alive[c] = hit ? 0 : 1;
+                    }
+                    if (tid == 0) pf.mark(17);
                 }
                 else if (warp == CLOSED_W)
                 {
@@ -1169,16 +1203,8 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                     }
                     __syncwarp();
                     if (warp == CLOSED_W && lane == 0) pf.mark(18);
-                    // phase B: sin/cos of the child yaw (t < P) and of goal yaw - child yaw (t >= P)
-                    for (int t = lane; t < 2 * P; t += 32)
-                    {
-                        const int c = t < P ? t : t - P, which = t < P ? 0 : 1;
-                        const double ang = which ? S.gyaw - S.k_yaw[c] : S.k_yaw[c];
-                        double sn, cs;
-                        dm::sincos_(ang, &sn, &cs);
-                        S.sc[which][c][0] = sn, S.sc[which][c][1] = cs;
-                    }
-                    __syncwarp();
+                    // phase B: the sin/cos pairs come from the footprint warps (child yaw and goal yaw - child yaw)
+                    asm volatile("bar.sync 2, %0;" ::"r"((COL_W + 1) * 32) : "memory");
                     // phase C: the four symmetry images of the normalised goal per child (ompl_image; sin(-x) = -sin(x) and
                     // cos(-x) = cos(x) hold bit for bit, so the image's own sin/cos phi follow from those of dth)
                     for (int t = lane; t < 4 * P; t += 32)

@@ -414,7 +414,7 @@ __device__ __noinline__ int rs_gen_traj(const RsConfig &c, double sx, double sy,
 // ---- OMPL-equivalent Reeds-Shepp distance ---------------------------------------------------
 // The oracle's stand-in for ompl::base::ReedsSheppStateSpace::distance is the specification (parity unpinned vs real
 // OMPL, see oracle/port/ompl_rs_distance.h); this mirrors it operation for operation.
-__device__ __forceinline__ double ompl_mod2pi(double x)
+__device__ __noinline__ double ompl_mod2pi(double x) // out of line: ~25 call sites in the hot formulas (3 KB of instruction-cache footprint inlined)
 {
     // v = fmod(x, 2*pi), exact: identity below 2*pi; one exact subtraction (Sterbenz: 2pi <= |x| < 4pi) below 4*pi
     const double twopi = 2.0 * kPi;
