@@ -9,7 +9,10 @@
 namespace mpros
 {
 
-__global__ void __launch_bounds__(256, 4) collision_poses_kernel(const __grid_constant__ MapView m, const __grid_constant__ PlannerView p, const double *__restrict__ xyyaw, size_t n,
+#ifndef MPROS_C1_MINB
+#define MPROS_C1_MINB 4
+#endif
+__global__ void __launch_bounds__(256, MPROS_C1_MINB) collision_poses_kernel(const __grid_constant__ MapView m, const __grid_constant__ PlannerView p, const double *__restrict__ xyyaw, size_t n,
                                                               uint8_t *__restrict__ verdicts)
 {
     for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)

@@ -98,7 +98,12 @@ constexpr uint32_t kFxEps = 1u << 10; // 2^-22 cell in units of 2^-32
 __device__ __forceinline__ uint32_t tw_probe(const uint32_t *__restrict__ tw, int pitch, long long qj, long long qi)
 {
     const int hj = (int)(qj >> 32), hi = (int)(qi >> 32);
+#if MPROS_TW_BLOCK16
+    // 16 x 16-cell blocks: the eight words of a block (4 word rows x 2 word columns) share one 32-byte sector
+    const uint32_t w = __ldg(tw + (((((hi >> 4) * pitch + (hj >> 4)) << 3) | ((hi >> 1) & 6)) | ((hj >> 3) & 1)));
+#else
     const uint32_t w = __ldg(tw + ((hi >> 2) * pitch + (hj >> 3)));
+#endif
     return w >> ((((unsigned)hi << 3) & 24u) | ((unsigned)hj & 7u));
 }
 // distance of the fractional parts from the nearest cell edge (wraps: 0 at an edge), running minimum
@@ -134,7 +139,11 @@ __device__ __forceinline__ bool footprint_in_collision4_sc(const MapView &m, con
     const long long dj = __double2ll_rn((fj1 - fj0) * p.inv_n_check), di = __double2ll_rn((fi1 - fi0) * p.inv_n_check);
     uint32_t any = 0, edge = 0xffffffffu;
     const int n = p.n_check;
-#pragma unroll 4
+#ifndef MPROS_C1_UNROLL
+#define MPROS_C1_UNROLL 4
+#endif
+    constexpr int kUnroll = MPROS_C1_UNROLL; // independent probe loads in flight per thread
+#pragma unroll kUnroll
     for (int k = 0; k <= n; ++k)
     {
         any |= tw_probe(m.infl_tw, m.tw_pitch, qj, qi);

@@ -299,7 +299,13 @@ __global__ void __launch_bounds__(256) build_tilewords_kernel(const uint32_t *__
     const size_t total = (size_t)tw_pitch * tw_rows;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x)
     {
+#if MPROS_TW_BLOCK16
+        const size_t blk = t >> 3;
+        const int sub = (int)(t & 7);
+        const int wi = (int)(blk / tw_pitch) * 4 + (sub >> 1), wj = (int)(blk % tw_pitch) * 2 + (sub & 1);
+#else
         const int wi = (int)(t / tw_pitch), wj = (int)(t % tw_pitch);
+#endif
         const int j0 = wj * 8 - kTwMargin; // multiple of 8
         uint32_t v = 0;
 #pragma unroll
@@ -410,8 +416,13 @@ static int realloc_layers(Ctx *c)
         c->cap0_words = words0;
     }
     {
+#if MPROS_TW_BLOCK16
+        c->tw_pitch = (c->W0 + 2 * kTwMargin + 15) / 16;                 // blocks per block row
+        const int tw_rows = ((c->H0 + 2 * kTwMargin + 15) / 16) * 8;      // so that tw_pitch * tw_rows = words
+#else
         c->tw_pitch = (c->W0 + 2 * kTwMargin + 7) / 8;
         const int tw_rows = (c->H0 + 2 * kTwMargin + 3) / 4;
+#endif
         size_t tw_words = (size_t)c->tw_pitch * tw_rows;
         if (tw_words > c->cap_tw)
         {
@@ -632,7 +643,11 @@ static int map_finish(Ctx *c)
     }
     // padded tile-word copies of the two collision layers
     {
+#if MPROS_TW_BLOCK16
+        const int tw_rows = ((c->H0 + 2 * kTwMargin + 15) / 16) * 8;
+#else
         const int tw_rows = (c->H0 + 2 * kTwMargin + 3) / 4;
+#endif
         const size_t tw_words = (size_t)c->tw_pitch * tw_rows;
         build_tilewords_kernel<<<grid_for(tw_words), 256, 0, st>>>(c->raw_bits, c->H0, c->W0, c->pitch0, c->raw_tw, c->tw_pitch, tw_rows);
         MPROS_LAUNCH_CHECK(c);

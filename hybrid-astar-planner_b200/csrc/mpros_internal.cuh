@@ -12,6 +12,10 @@ namespace mpros
 {
 
 constexpr int kHugeInt = 1000; // HUGE_INT, mpros_navigation_map/node.h:4
+// probe layout: words of a 16 x 16-cell block share a sector (1) or plain row-major tile words (0); 1 measured +5 %
+#ifndef MPROS_TW_BLOCK16
+#define MPROS_TW_BLOCK16 1
+#endif
 constexpr int kTwMargin = 256;  // cells of "outside the map" padding around the tile-word collision layers
 
 // ---- HBM layout of one map (all device pointers) -------------------------------------------------------
@@ -26,7 +30,9 @@ struct MapView
     const uint32_t *infl_bits; // inflate_map_orig_     [H0 x pitch0]
     const uint32_t *ds_bits;   // static_map_           [H  x pitch ]
     // the two collision layers again as padded TILE WORDS for the fixed-point footprint walk (map_device.cuh): cell
-    // (i, j) is bit ((pi & 3) << 3) | (pj & 7) of word [(pi >> 2) * tw_pitch + (pj >> 3)], (pi, pj) = (i, j) + kTwMargin
+    // (i, j) is bit ((pi & 3) << 3) | (pj & 7) of a 32-bit word holding 4 rows x 8 columns, (pi, pj) = (i, j) + kTwMargin;
+    // the eight words of a 16 x 16-cell block (4 word rows x 2 word columns) are contiguous = one 32-byte sector:
+    // word index (((pi >> 4) * tw_pitch + (pj >> 4)) << 3) | ((pi >> 1) & 6) | ((pj >> 3) & 1), tw_pitch = blocks per row
     const uint32_t *raw_tw, *infl_tw;
     int tw_pitch;
     const float *voronoi;      // voronoi_value_map_    [H*W]

@@ -153,7 +153,11 @@ __device__ __noinline__ void heap_push_lane0(OpenHeap &h, unsigned long long k, 
     }
     hset(h, pos, k, id);
 }
-// warp-cooperative pop; returns the id with the smallest (key, id); h.size must be > 0
+// warp-cooperative pop; returns the id with the smallest (key, id); h.size must be > 0.
+// Bottom-up variant: the hole left by the root walks down along the smallest children to a leaf WITHOUT looking at the
+// element that will fill it (the heap's last entry, almost always larger than everything on the way), so that entry's load
+// overlaps the whole descent instead of heading the dependent chain; it is then placed by a (rarely needed) sift-up.
+// Any valid heap gives the same pop order: the order is fixed by the (key, id) total order alone.
 __device__ __noinline__ uint32_t heap_pop_warp(OpenHeap &h, unsigned long long &out_key)
 {
     const int lane = threadIdx.x & 31;
@@ -163,10 +167,10 @@ __device__ __noinline__ uint32_t heap_pop_warp(OpenHeap &h, unsigned long long &
     int n = --h.size;
     if (n == 0)
         return ri;
-    unsigned long long lk = hk(h, n);
+    unsigned long long lk = hk(h, n); // in flight during the descent
     uint32_t li = hi(h, n);
     int pos = 0;
-    while (true)
+    while ((pos << 5) + 1 < n)
     {
         int child = (pos << 5) + 1 + lane;
         unsigned long long ck = ~0ull;
@@ -176,30 +180,34 @@ __device__ __noinline__ uint32_t heap_pop_warp(OpenHeap &h, unsigned long long &
             ck = hk(h, child);
             ci = hi(h, child);
         }
-        // lexicographic arg-min over (key hi, key lo, id) with three warp reductions (redux.sync) instead of a
-        // 5-step shuffle butterfly on 128-bit tuples
-        {
-            const uint32_t khi = (uint32_t)(ck >> 32), klo = (uint32_t)ck;
-            const uint32_t m1 = __reduce_min_sync(kFull, khi);
-            const bool a1 = khi == m1;
-            const uint32_t m2 = __reduce_min_sync(kFull, a1 ? klo : 0xffffffffu);
-            const bool a2 = a1 && klo == m2;
-            const uint32_t m3 = __reduce_min_sync(kFull, a2 ? ci : 0xffffffffu);
-            const unsigned win = __ballot_sync(kFull, a2 && ci == m3);
-            ck = ((unsigned long long)m1 << 32) | m2;
-            ci = m3;
-            // no child at all: every lane holds the sentinel and lane 0 "wins"; the caller's bound check handles it
-            child = (pos << 5) + 1 + (__ffs(win) - 1);
-        }
-        int cpos = child;
-        if ((pos << 5) + 1 >= n || !heap_less(ck, ci, lk, li))
-            break;
+        // lexicographic arg-min over (key hi, key lo, id) with three warp reductions (redux.sync)
+        const uint32_t khi = (uint32_t)(ck >> 32), klo = (uint32_t)ck;
+        const uint32_t m1 = __reduce_min_sync(kFull, khi);
+        const bool a1 = khi == m1;
+        const uint32_t m2 = __reduce_min_sync(kFull, a1 ? klo : 0xffffffffu);
+        const bool a2 = a1 && klo == m2;
+        const uint32_t m3 = __reduce_min_sync(kFull, a2 ? ci : 0xffffffffu);
+        const unsigned win = __ballot_sync(kFull, a2 && ci == m3);
         if (lane == 0)
-            hset(h, pos, ck, ci);
-        pos = cpos;
+            hset(h, pos, ((unsigned long long)m1 << 32) | m2, m3);
+        pos = (pos << 5) + 1 + (__ffs(win) - 1);
     }
+    // place the last entry: sift it up from the hole (lane 0; the parents on the way were written above, so make them visible)
+    __syncwarp();
     if (lane == 0)
+    {
+        while (pos > 0)
+        {
+            const int parent = (pos - 1) >> 5;
+            const unsigned long long pk = hk(h, parent);
+            const uint32_t pi = hi(h, parent);
+            if (!heap_less(lk, li, pk, pi))
+                break;
+            hset(h, pos, pk, pi);
+            pos = parent;
+        }
         hset(h, pos, lk, li);
+    }
     __syncwarp();
     return ri;
 }
