@@ -245,7 +245,27 @@ extern "C" int mpros_planner_config(mpros_ctx *c, const mpros_planner_params *p)
             v.prim_dx[2 * si + di] = dx;
             v.prim_dy[2 * si + di] = dy;
             v.prim_dyaw[2 * si + di] = dyaw_signed;
+            // one leaf of the search-tree visualisation (hybrid_a_star.cpp:1133-1153)
+            if (steer == 0)
+            {
+                dx = direc * p->path_point_distance;
+                dy = 0;
+                dyaw_signed = 0;
+            }
+            else
+            {
+                double radius = (p->wheelbase / 2 + off) / std::tan(std::abs(steer));
+                double steer_sign = steer / std::abs(steer);
+                double dyaw = p->path_point_distance / radius;
+                dx = std::sin(dyaw) * radius * direc;
+                dy = (1 - std::cos(dyaw)) * radius * steer_sign;
+                dyaw_signed = dyaw * steer_sign * direc;
+            }
+            v.leaf_dx[2 * si + di] = dx;
+            v.leaf_dy[2 * si + di] = dy;
+            v.leaf_dyaw[2 * si + di] = dyaw_signed;
         }
+    v.leaf_num = (int)std::ceil(p->step_size / p->path_point_distance);
     v.pen_gear = p->gear_penalty;
     v.pen_back = p->reverse_penalty;
     v.pen_steer = p->steering_penalty;

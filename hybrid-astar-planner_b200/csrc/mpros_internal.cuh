@@ -65,6 +65,9 @@ struct PlannerView
     // per primitive (index 2 * steer_index + direction_index), evaluated ONCE on the host with the same libm the
     // reference calls for every expansion (hybrid_a_star.cpp:325-348): displacement in the vehicle frame and yaw change
     double prim_dx[2 * kMaxSteer], prim_dy[2 * kMaxSteer], prim_dyaw[2 * kMaxSteer];
+    // the same for one leaf of getSearchTree (hybrid_a_star.cpp:1114-1164): path_granularity_ instead of step_size_
+    double leaf_dx[2 * kMaxSteer], leaf_dy[2 * kMaxSteer], leaf_dyaw[2 * kMaxSteer];
+    int leaf_num; // ceil(step_size_ / path_granularity_)
     double pen_gear, pen_back, pen_steer, pen_steer_change;
     double min_r, max_steer, rs_range;
     int num_yaw;

@@ -79,6 +79,10 @@ struct PlanBatchArgs
     WarpWorkspaceLayout L;
     RsConfig rs;
     int optimal;
+    // optional expansion trace (mpros_plan_search_tree, single query): pose of every expanded node in expansion order
+    double *trace;         // trace_cap x 3 {x, y, yaw}
+    long long trace_cap;
+    long long *trace_n;    // number of expansions (may exceed trace_cap: then the trace is truncated)
 };
 
 // Phase profile of the team planner (developer build only: make PROFILE=1). Cycle counts are taken by thread 0 of the
@@ -750,10 +754,14 @@ static int plan_pass(mpros_ctx *c, PlanBatchArgs &a, int pass, int node_cap, int
 } // namespace mpros
 
 static int plan_batch_dev_impl(mpros_ctx *c, const double *d_starts, const double *d_goals, int nq, int32_t *d_status, double *d_cost,
-                               int32_t *d_path_len, double *d_paths, int path_cap, int64_t *d_stats)
+                               int32_t *d_path_len, double *d_paths, int path_cap, int64_t *d_stats, double *d_trace = nullptr,
+                               long long trace_cap = 0, long long *d_trace_n = nullptr)
 {
     PlanBatchArgs a;
     std::memset(&a, 0, sizeof(a));
+    a.trace = d_trace;
+    a.trace_cap = trace_cap;
+    a.trace_n = d_trace_n;
     a.starts = d_starts;
     a.goals = d_goals;
     a.nq = nq;
@@ -813,6 +821,124 @@ static int plan_batch_dev_impl(mpros_ctx *c, const double *d_starts, const doubl
         if (cap >= max_nodes)
             break;
     }
+    return MPROS_OK;
+}
+
+namespace mpros
+{
+// HybridAstar::getSearchTree (hybrid_a_star.cpp:1114-1164): every tree_ entry (expanded node x primitive) becomes
+// leaf_num short segments {next_x, next_y, curr_x, curr_y}. One thread per entry; the per-primitive leaf displacement is a
+// host-computed constant (PlannerView::leaf_*), the rotation into the map frame runs here.
+__global__ void __launch_bounds__(256) search_tree_kernel(const __grid_constant__ PlannerView p, const double *__restrict__ trace,
+                                                          long long n_exp, double *__restrict__ tree4)
+{
+    const int P = 2 * p.n_steer;
+    const long long total = n_exp * P;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x)
+    {
+        const long long k = e / P;
+        const int c = (int)(e % P);
+        double x = trace[3 * k], y = trace[3 * k + 1], yaw = trace[3 * k + 2];
+        const double dx = p.leaf_dx[c], dy = p.leaf_dy[c], dyaw = p.leaf_dyaw[c];
+        const bool straight = p.steer_set[c >> 1] == 0;
+        double *o = tree4 + (size_t)e * p.leaf_num * 4;
+        for (int i = 0; i < p.leaf_num; ++i)
+        {
+            double sn, cs;
+            sincos(yaw, &sn, &cs);
+            const double nx = dx * cs - dy * sn + x, ny = dx * sn + dy * cs + y;
+            o[4 * i] = nx, o[4 * i + 1] = ny, o[4 * i + 2] = x, o[4 * i + 3] = y;
+            x = nx, y = ny;
+            if (!straight)
+                yaw = regular_yaw(yaw + dyaw);
+        }
+    }
+}
+} // namespace mpros
+
+extern "C" int mpros_plan_search_tree(mpros_ctx *c, const double *start3, const double *goal3, int32_t *status, double *cost, double *tree4,
+                                      size_t cap_segments, size_t *n_segments)
+{
+    int rc = check_planner_ready(c, "mpros_plan_search_tree");
+    if (rc)
+        return rc;
+    if (!start3 || !goal3 || !status || !cost || !n_segments)
+    {
+        set_error("mpros_plan_search_tree: NULL argument");
+        return MPROS_ERR_INVALID;
+    }
+    MPROS_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int P = 2 * c->pv.n_steer, leaf = c->pv.leaf_num;
+    const long long max_exp = (long long)c->pp.max_iteration + 2;
+    // device scratch: poses, results, trace
+    double *d_sg = nullptr, *d_cost = nullptr, *d_trace = nullptr;
+    int32_t *d_status = nullptr, *d_len = nullptr;
+    long long *d_n = nullptr;
+    const size_t trace_bytes = (size_t)max_exp * 24;
+    MPROS_CUDA(cudaMalloc(&d_sg, 48 + 8 + 8 + 8 + 8));
+    MPROS_CUDA(cudaMalloc(&d_trace, trace_bytes));
+    d_cost = d_sg + 6;
+    d_status = reinterpret_cast<int32_t *>(d_sg + 7);
+    d_len = d_status + 1;
+    d_n = reinterpret_cast<long long *>(d_sg + 8);
+    auto cleanup = [&]() {
+        cudaFree(d_sg);
+        cudaFree(d_trace);
+    };
+    double sg[6] = {start3[0], start3[1], start3[2], goal3[0], goal3[1], goal3[2]};
+    cudaMemcpyAsync(d_sg, sg, sizeof(sg), cudaMemcpyHostToDevice, st);
+    cudaMemsetAsync(d_n, 0, 8, st);
+    rc = plan_batch_dev_impl(c, d_sg, d_sg + 3, 1, d_status, d_cost, d_len, nullptr, 0, nullptr, d_trace, max_exp, d_n);
+    if (rc)
+    {
+        cleanup();
+        return rc;
+    }
+    long long n_exp = 0;
+    cudaMemcpyAsync(&n_exp, d_n, 8, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(status, d_status, 4, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(cost, d_cost, 8, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess)
+    {
+        cleanup();
+        return cuda_fail(cudaGetLastError(), "mpros_plan_search_tree", __FILE__, __LINE__);
+    }
+    if (n_exp > max_exp)
+        n_exp = max_exp;
+    const size_t n_seg = (size_t)n_exp * P * leaf;
+    *n_segments = n_seg;
+    if (!tree4 || n_seg > cap_segments)
+    {
+        cleanup();
+        if (!tree4 && cap_segments == 0)
+            return MPROS_OK; // size query
+        set_error("mpros_plan_search_tree: output buffer too small (*n_segments holds the required size)");
+        return MPROS_ERR_CAPACITY;
+    }
+    if (n_seg)
+    {
+        double *d_tree = nullptr;
+        if (cudaMalloc(&d_tree, n_seg * 32) != cudaSuccess)
+        {
+            cleanup();
+            return cuda_fail(cudaGetLastError(), "cudaMalloc(search tree)", __FILE__, __LINE__);
+        }
+        size_t blocks = ((size_t)n_exp * P + 255) / 256;
+        if (blocks > 148 * 8)
+            blocks = 148 * 8;
+        search_tree_kernel<<<(unsigned)blocks, 256, 0, st>>>(c->pv, d_trace, n_exp, d_tree);
+        c->launches++;
+        cudaMemcpyAsync(tree4, d_tree, n_seg * 32, cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        cudaFree(d_tree);
+        if (e != cudaSuccess)
+        {
+            cleanup();
+            return cuda_fail(e, "search_tree_kernel", __FILE__, __LINE__);
+        }
+    }
+    cleanup();
     return MPROS_OK;
 }
 

@@ -1269,6 +1269,14 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                     }
                     if (lane == 0)
                     {
+                        if (a.trace)
+                        {
+                            // tree_ of the reference (hybrid_a_star.cpp:352) holds P entries per expansion, all with this parent
+                            const long long k = S.n_prim / P;
+                            if (k < a.trace_cap)
+                                a.trace[3 * k] = cn.x, a.trace[3 * k + 1] = cn.y, a.trace[3 * k + 2] = cn.yaw;
+                            *a.trace_n = k + 1;
+                        }
                         S.nslots = P;
                         S.n_prim += P;
                         S.n_coll += P;

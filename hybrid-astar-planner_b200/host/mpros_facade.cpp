@@ -261,6 +261,21 @@ bool HybridAstar::Plan()
     return true;
 }
 
+std::vector<std::array<double, 4>> HybridAstar::getSearchTree()
+{
+    std::vector<std::array<double, 4>> tree;
+    if (!initialized_)
+        return tree;
+    int32_t status = 0;
+    double cost = -1;
+    size_t n = 0;
+    check(mpros_plan_search_tree(map_->ctx(), start_.data(), goal_.data(), &status, &cost, nullptr, 0, &n), "mpros_plan_search_tree");
+    tree.resize(n);
+    if (n)
+        check(mpros_plan_search_tree(map_->ctx(), start_.data(), goal_.data(), &status, &cost, &tree[0][0], n, &n), "mpros_plan_search_tree");
+    return tree;
+}
+
 std::vector<PathPoint> HybridAstar::getNewPath()
 {
     // new_path_ as setPath builds it (hybrid_a_star.cpp:814-838): path length, cusps, curvature and, with

@@ -12,6 +12,7 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <array>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -230,6 +231,9 @@ public:
     void reset();                                                                                        // :32-50
     bool Plan();                                                                                         // :682-777
     std::vector<std::vector<double>> getPath() { return path_; } // {x, y, yaw, steer, direction}
+    // hybrid_a_star.cpp:1114-1164: leaf segments {next_x, next_y, curr_x, curr_y} of every evaluated primitive (re-plans
+    // the query on the device with the expansion trace switched on)
+    std::vector<std::array<double, 4>> getSearchTree();
     std::vector<PathPoint> getNewPath();                          // hybrid_a_star.cpp:848-851: setPath's up-sampled path (:814-838)
     bool pathInCollision(const std::vector<std::vector<double>> &path); // :404-416
     bool pathInCollision(const std::vector<PathPoint> &path);           // :418-430

@@ -150,6 +150,7 @@ def load_library(path=LIB_PATH):
     L.mpros_expand_batch.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp]
     L.mpros_plan_batch.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, i, vp]
     L.mpros_path_postprocess_batch.argtypes = [vp, vp, vp, sz, vp, sz, vp]
+    L.mpros_plan_search_tree.argtypes = [vp, vp, vp, vp, vp, vp, sz, C.POINTER(sz)]
     L.mpros_plan_batch_dev.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, i, vp]
     _lib = L
     return L
@@ -412,6 +413,18 @@ class Context:
 
     def plan_batch_dev(self, d_starts, d_goals, nq, d_status, d_cost, d_len, d_paths, path_cap, d_stats):
         self._check(self.L.mpros_plan_batch_dev(self.h, d_starts, d_goals, nq, d_status, d_cost, d_len, d_paths, path_cap, d_stats))
+
+    def plan_search_tree(self, start, goal):
+        """HybridAstar::getSearchTree for one query: (status, cost, [n, 4] {next_x, next_y, curr_x, curr_y})."""
+        s = np.ascontiguousarray(start, dtype=np.float64)
+        g = np.ascontiguousarray(goal, dtype=np.float64)
+        status, cost, n = C.c_int32(0), C.c_double(0), C.c_size_t(0)
+        self._check(self.L.mpros_plan_search_tree(self.h, s.ctypes.data, g.ctypes.data, C.byref(status), C.byref(cost), None, 0, C.byref(n)))
+        tree = np.zeros((n.value, 4), dtype=np.float64)
+        if n.value:
+            self._check(self.L.mpros_plan_search_tree(self.h, s.ctypes.data, g.ctypes.data, C.byref(status), C.byref(cost), tree.ctypes.data,
+                                                      n.value, C.byref(n)))
+        return status.value, cost.value, tree
 
     def path_postprocess(self, paths):
         """getNewPath() for a list of raw paths (each [n_k, 5] {x, y, yaw, steer, direction}): list of [m_k, 8] arrays

@@ -244,6 +244,14 @@ MPROS_API int mpros_plan_batch_dev(mpros_ctx *ctx, const double *d_starts3, cons
                                    int32_t *d_status, double *d_cost, int32_t *d_path_len, double *d_paths, int path_cap,
                                    int64_t *d_stats);
 
+/* HybridAstar::getSearchTree (hybrid_a_star.cpp:1114-1164) of ONE query: plans (start, goal) exactly like
+ * mpros_plan_batch with nq = 1 while recording tree_ (the pose of every expanded node; hybrid_a_star.cpp:352 stores it once
+ * per primitive) and turns every (expanded node, primitive) into ceil(step_size / path_point_distance) leaf segments
+ * {next_x, next_y, curr_x, curr_y} (the reference's Eigen::Vector4d), in the reference's order. tree4: double[4 *
+ * cap_segments]; *n_segments = number of segments; tree4 == NULL with cap_segments == 0 only queries the size (the plan is
+ * run); MPROS_ERR_CAPACITY when the buffer is too small. */
+MPROS_API int mpros_plan_search_tree(mpros_ctx *ctx, const double *start3, const double *goal3, int32_t *status, double *cost,
+                                     double *tree4, size_t cap_segments, size_t *n_segments);
 
 /* ---- path post-processing -------------------------------------------------------------------- */
 /* What HybridAstar::setPath does to the raw path_ before getNewPath() returns it (hybrid_a_star.cpp:814-838):

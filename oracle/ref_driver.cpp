@@ -390,6 +390,23 @@ extern "C"
         return (int)np_.size();
     }
 
+    // getSearchTree() of a whole query (main_planner.cpp:260): Plan() then the visualisation tree. out4: cap x 4
+    // {next_x, next_y, curr_x, curr_y}; returns the number of segments.
+    long ref_plan_search_tree(void *map, const double *start3, const double *goal3, int do_update_goal, double *out4, long cap)
+    {
+        NavMap *m = static_cast<NavMap *>(map);
+        std::vector<double> s(start3, start3 + 3), g(goal3, goal3 + 3);
+        if (do_update_goal)
+            m->updateGoal(g[0], g[1]);
+        HybridAstar planner(s, g, *m, g_vis, g_nh);
+        planner.Plan();
+        std::vector<Eigen::Vector4d> tree = planner.getSearchTree();
+        for (long k = 0; k < (long)tree.size() && k < cap; ++k)
+            for (int c = 0; c < 4; ++c)
+                out4[4 * k + c] = tree[k](c);
+        return (long)tree.size();
+    }
+
     // ---- RS::RSCurve ------------------------------------------------------------------------------
     // cfg: {radius, max_steer, step, pen_gear, pen_back, pen_a3, pen_a4} with pen_a3/pen_a4 passed in the
     // POSITIONS the planner uses (hybrid_a_star.cpp:170: setPenalty(gear, back, STEER_ANGLE, STEER_CHANGE)).

@@ -255,6 +255,19 @@ def ref_plan_newpath(rmap, start, goal, update_goal=True, cap=8192):
     return out[: min(n, cap)].copy()
 
 
+def ref_plan_search_tree(rmap, start, goal, update_goal=True, cap=1 << 22):
+    """Plan() + getSearchTree() (hybrid_a_star.cpp:1114-1164): [n, 4] {next_x, next_y, curr_x, curr_y}."""
+    s = np.array(start, dtype=np.float64)
+    g = np.array(goal, dtype=np.float64)
+    out = np.zeros((cap, 4), dtype=np.float64)
+    L = rmap.lib.L
+    L.ref_plan_search_tree.restype = C.c_long
+    n = L.ref_plan_search_tree(C.c_void_p(rmap.h), C.c_void_p(s.ctypes.data), C.c_void_p(g.ctypes.data), C.c_int(int(update_goal)),
+                               C.c_void_p(out.ctypes.data), C.c_long(cap))
+    assert n <= cap
+    return out[:n].copy()
+
+
 def ref_rs_solve(lib, cfg7, start5, goal3, traj_cap=256):
     cfg = np.array(cfg7, dtype=np.float64)
     s = np.array(start5, dtype=np.float64)

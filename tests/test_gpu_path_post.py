@@ -75,3 +75,21 @@ def test_degenerate_inputs(gpu_ctx_factory, reflib):
     one = ctx.path_postprocess([np.array([[3.0, 8.0, 0.0, 0.0, 1.0]])])
     assert one[0].shape == (1, 8)
     rm.close()
+
+
+@pytest.mark.parametrize("ci", [0, 3])
+def test_search_tree_matches_reference(reflib, gpu_ctx_factory, ci):
+    """HybridAstar::getSearchTree (hybrid_a_star.cpp:1114-1164) through mpros_plan_search_tree: the same expansions in the
+    same order, every (expanded node, primitive) as ceil(step / granularity) leaf segments."""
+    name, ds, num_steer, start, goal = gi.PLAN_CASES[ci]
+    ctx = gpu_ctx_factory()
+    rm, params, m = make_pair(reflib, ctx, name, ds=ds, num_steer=num_steer, goal=goal[:2])
+    ctx.upload_voronoi(rm.layer("voronoi"))
+    want = refapi.ref_plan_search_tree(rm, start, goal)
+    status, cost, got = ctx.plan_search_tree(start, goal)
+    r = refapi.ref_plan_query(rm, start, goal)
+    print("%s: %d segments (%d primitives x %d leaves)" % (name, len(got), int(r["n_primitives"]), len(got) // max(1, int(r["n_primitives"]))))
+    assert status == 1 and abs(cost - r["goal_g"]) <= 1e-9 * r["goal_g"]
+    assert got.shape == want.shape and len(got) == int(r["n_primitives"]) * 20
+    assert np.allclose(got, want, rtol=0, atol=1e-9)
+    rm.close()
