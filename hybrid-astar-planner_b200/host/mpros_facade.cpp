@@ -314,6 +314,18 @@ bool HybridAstar::footPrintInCollision4(const double &x, const double &y, const 
     return v != 0;
 }
 
+static bool footprint_method(mpros_ctx *ctx, int method, double x, double y, double yaw)
+{
+    double pose[3] = {x, y, yaw};
+    uint8_t v = 1;
+    if (mpros_collision_check_poses_method(ctx, method, pose, 1, &v) != MPROS_OK)
+        throw MprosFailure(std::string("mpros_collision_check_poses_method: ") + mpros_last_error_string());
+    return v != 0;
+}
+bool HybridAstar::footPrintInCollision(const double &x, const double &y, const double &yaw) { return footprint_method(map_->ctx(), 1, x, y, yaw); }
+bool HybridAstar::footPrintInCollision2(const double &x, const double &y, const double &yaw) { return footprint_method(map_->ctx(), 2, x, y, yaw); }
+bool HybridAstar::footPrintInCollision3(const double &x, const double &y, const double &yaw) { return footprint_method(map_->ctx(), 3, x, y, yaw); }
+
 bool HybridAstar::pathInCollision(const std::vector<std::vector<double>> &path)
 {
     if (path.empty())

@@ -238,6 +238,10 @@ public:
     bool pathInCollision(const std::vector<std::vector<double>> &path); // :404-416
     bool pathInCollision(const std::vector<PathPoint> &path);           // :418-430
     bool footPrintInCollision4(const double &x, const double &y, const double &yaw); // :617-680
+    // hybrid_a_star.cpp:432-615: the three methods no caller of the reference uses (mpros_collision_check_poses_method)
+    bool footPrintInCollision(const double &x, const double &y, const double &yaw);
+    bool footPrintInCollision2(const double &x, const double &y, const double &yaw);
+    bool footPrintInCollision3(const double &x, const double &y, const double &yaw);
     int calIndex(const int &idx_i, const int &idx_j, const int &idx_yaw, const double &direc); // :281-290
     int yawToIdx(const double &yaw);                                                          // :292-302
     void regularYaw(double &yaw);                                                             // :266-279

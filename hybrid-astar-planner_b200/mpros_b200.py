@@ -143,6 +143,7 @@ def load_library(path=LIB_PATH):
     L.mpros_collision_check_poses.argtypes = [vp, vp, sz, vp]
     L.mpros_collision_check_poses_dev.argtypes = [vp, vp, sz, vp]
     L.mpros_collision_check_paths.argtypes = [vp, vp, vp, sz, vp]
+    L.mpros_collision_check_poses_method.argtypes = [vp, i, vp, sz, vp]
     L.mpros_rs_default_config.argtypes = [vp, C.POINTER(RsParams)]
     L.mpros_rs_solve_batch.argtypes = [vp, C.POINTER(RsParams), vp, vp, sz, vp, vp, vp, vp, i, vp]
     L.mpros_rs_shot_batch.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, i, vp, vp]
@@ -425,6 +426,13 @@ class Context:
             self._check(self.L.mpros_plan_search_tree(self.h, s.ctypes.data, g.ctypes.data, C.byref(status), C.byref(cost), tree.ctypes.data,
                                                       n.value, C.byref(n)))
         return status.value, cost.value, tree
+
+    def collision_check_method(self, method, poses):
+        """footPrintInCollision (1), footPrintInCollision2 (2), footPrintInCollision3 (3) or footPrintInCollision4 (4)."""
+        poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 3)
+        out = np.zeros(len(poses), dtype=np.uint8)
+        self._check(self.L.mpros_collision_check_poses_method(self.h, method, poses.ctypes.data, len(poses), out.ctypes.data))
+        return out
 
     def path_postprocess(self, paths):
         """getNewPath() for a list of raw paths (each [n_k, 5] {x, y, yaw, steer, direction}): list of [m_k, 8] arrays

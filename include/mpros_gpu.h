@@ -182,6 +182,13 @@ MPROS_API int mpros_collision_check_poses_dev(mpros_ctx *ctx, const double *d_xy
 MPROS_API int mpros_collision_check_paths(mpros_ctx *ctx, const double *xyyaw, const int64_t *offsets, size_t n_paths,
                                 uint8_t *verdicts);
 
+/* The other footprint tests of the public HybridAstar interface (no caller in the reference):
+ * method 1 footPrintInCollision (hybrid_a_star.cpp:432-483, Bresenham lines between the corner cells, raw map),
+ * method 2 footPrintInCollision2 (:485-575, winding-angle sum of the obstacle cells in the circumscribed square),
+ * method 3 footPrintInCollision3 (:577-615, rasterised footprint kernel per yaw bin, mpros_utils/footprint.h),
+ * method 4 = mpros_collision_check_poses. Same arguments as mpros_collision_check_poses. */
+MPROS_API int mpros_collision_check_poses_method(mpros_ctx *ctx, int method, const double *xyyaw, size_t n, uint8_t *verdicts);
+
 /* ---- Reeds-Shepp (R1-R5) ----------------------------------------------------------------------------- */
 /* RS::RSCurve configuration: SetRadius / setSteeringAngle / setStepSize / setPenalty (rs_curve.h:58-100).
  * The four penalties are in RSCurve::setPenalty's DECLARED order (gear, backward, steer_change, steer_angle);

@@ -213,6 +213,17 @@ extern "C"
         return now_s() - t0;
     }
 
+    // footPrintInCollision (1), footPrintInCollision2 (2), footPrintInCollision3 (3): the unused methods of the interface
+    void ref_planner_collision_method(void *h, int method, const double *xyyaw, long n, uint8_t *out)
+    {
+        HybridAstar *p = static_cast<HybridAstar *>(h);
+        for (long k = 0; k < n; ++k)
+        {
+            const double x = xyyaw[3 * k], y = xyyaw[3 * k + 1], yaw = xyyaw[3 * k + 2];
+            out[k] = method == 1 ? p->footPrintInCollision(x, y, yaw) : method == 2 ? p->footPrintInCollision2(x, y, yaw) : p->footPrintInCollision3(x, y, yaw);
+        }
+    }
+
     // initialize() for a query; returns initialized_ (0 when start/goal collide or no goal map)
     int ref_planner_initialize(void *h, void *map, const double *start3, const double *goal3)
     {

@@ -203,6 +203,13 @@ class RefPlanner:
         self.t_collision = self.lib.L.ref_planner_collision4(self.h, poses.ctypes.data, len(poses), out.ctypes.data)
         return out
 
+    def collision_method(self, method, poses):
+        poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 3)
+        out = np.zeros(len(poses), dtype=np.uint8)
+        self.lib.L.ref_planner_collision_method(C.c_void_p(self.h), C.c_int(method), C.c_void_p(poses.ctypes.data), C.c_long(len(poses)),
+                                                C.c_void_p(out.ctypes.data))
+        return out
+
     def initialize(self, start, goal):
         s = np.array(start, dtype=np.float64)
         g = np.array(goal, dtype=np.float64)
