@@ -326,8 +326,9 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_device(step_fn):
-        """W warm-up steps, then K steps timed with CUDA events on the context's stream (per step + whole region)."""
+    def timed_device(step_fn, join=None):
+        """W warm-up steps, then K steps timed with CUDA events on the context's stream (per step + whole region).
+        join(): makes the context's stream wait for the other streams the steps ran on (plan lanes)."""
         for _ in range(warm):
             step_fn()
         barrier()
@@ -339,17 +340,23 @@ def run_b200(args):
             ev[k][0].record(stream)
             step_fn()
             ev[k][1].record(stream)
+        if join:
+            join()
         e1.record(stream)
         barrier()
         return e0.elapsed_time(e1), [a.elapsed_time(b) for a, b in ev], ctx.launch_count() - l0
 
-    def timed_host(step_fn):
+    def timed_host(step_fn, finish=None):
         for _ in range(2):
             step_fn()
+        if finish:
+            finish()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             step_fn()
+        if finish:
+            finish()
         barrier()
         return (time.perf_counter() - t0) * 1e3
 
@@ -400,31 +407,79 @@ def run_b200(args):
         starts, goals = gen_queries(ctx, nq, synthetic.SYN_QUERY_SEED + rank)
         s_h, g_h = torch.from_numpy(starts).pin_memory(), torch.from_numpy(goals).pin_memory()
         s_d, g_d = s_h.cuda(), g_h.cuda()
-        status_d = torch.zeros(nq, dtype=torch.int32, device="cuda")
-        cost_d = torch.zeros(nq, dtype=torch.float64, device="cuda")
-        len_d = torch.zeros(nq, dtype=torch.int32, device="cuda")
-        paths_d = torch.zeros(nq * PATH_CAP * 5, dtype=torch.float64, device="cuda")
-        stats_d = torch.zeros(nq * 6, dtype=torch.int64, device="cuda")
-        status_h = torch.zeros(nq, dtype=torch.int32).pin_memory()
-        cost_h = torch.zeros(nq, dtype=torch.float64).pin_memory()
-        len_h = torch.zeros(nq, dtype=torch.int32).pin_memory()
-        paths_h = torch.zeros(nq * PATH_CAP * 5, dtype=torch.float64).pin_memory()
-        stats_h = torch.zeros(nq * 6, dtype=torch.int64).pin_memory()
-        gather = [torch.zeros(nq, dtype=torch.float64, device="cuda") for _ in range(world)] if world > 1 else None
+        # Batches in flight: step k runs on lane k % LANES (own stream + planner workspaces, include/mpros_gpu.h), so the
+        # iteration-limit tail of one batch (a few queries, each a dependent chain of 100 001 expansions) overlaps the next
+        # batch. Every step still plans all nq queries and writes all results; --lanes 1 gives one batch at a time.
+        LANES = max(1, min(args.lanes, mpros_b200.PLAN_LANES))
+
+        def dev_bufs():
+            return {"status": torch.zeros(nq, dtype=torch.int32, device="cuda"), "cost": torch.zeros(nq, dtype=torch.float64, device="cuda"),
+                    "len": torch.zeros(nq, dtype=torch.int32, device="cuda"),
+                    "paths": torch.zeros(nq * PATH_CAP * 5, dtype=torch.float64, device="cuda"),
+                    "stats": torch.zeros(nq * 6, dtype=torch.int64, device="cuda")}
+
+        def host_bufs():
+            return {"status": torch.zeros(nq, dtype=torch.int32).pin_memory(), "cost": torch.zeros(nq, dtype=torch.float64).pin_memory(),
+                    "len": torch.zeros(nq, dtype=torch.int32).pin_memory(),
+                    "paths": torch.zeros(nq * PATH_CAP * 5, dtype=torch.float64).pin_memory(),
+                    "stats": torch.zeros(nq * 6, dtype=torch.int64).pin_memory()}
+
+        dbuf = [dev_bufs() for _ in range(LANES)]
+        hbuf = [host_bufs() for _ in range(LANES)]
+        status_d, cost_d, stats_d = dbuf[0]["status"], dbuf[0]["cost"], dbuf[0]["stats"]
+        status_h, cost_h = hbuf[0]["status"], hbuf[0]["cost"]
+        gather = [[torch.zeros(nq, dtype=torch.float64, device="cuda") for _ in range(world)] for _ in range(LANES)] if world > 1 else None
+        lane_ext = {}
+        counter = {"dev": 0, "host": 0}
+
+        def lane_stream(lane):
+            if lane not in lane_ext:
+                lane_ext[lane] = torch.cuda.ExternalStream(ctx.plan_lane_stream(lane))
+            return lane_ext[lane]
 
         def step_dev():
-            ctx.plan_batch_dev(s_d.data_ptr(), g_d.data_ptr(), nq, status_d.data_ptr(), cost_d.data_ptr(), len_d.data_ptr(),
-                               paths_d.data_ptr(), PATH_CAP, stats_d.data_ptr())
-            if world > 1:  # the path's only exchange step: result gather over NCCL/NVLink
-                ctx.synchronize()
-                dist.all_gather(gather, cost_d)
+            lane = counter["dev"] % LANES
+            counter["dev"] += 1
+            b = dbuf[lane]
+            ctx.plan_batch_submit_dev(lane, s_d.data_ptr(), g_d.data_ptr(), nq, b["status"].data_ptr(), b["cost"].data_ptr(),
+                                      b["len"].data_ptr(), b["paths"].data_ptr(), PATH_CAP, b["stats"].data_ptr())
+            if world > 1:  # the path's only exchange step: result gather over NCCL/NVLink, ordered behind the lane's batch
+                cur = torch.cuda.current_stream()
+                cur.wait_stream(lane_stream(lane))
+                dist.all_gather(gather[lane], b["cost"])
+                lane_stream(lane).wait_stream(cur)  # the lane's next batch overwrites b["cost"]
 
         def step_host():
-            ctx._check(ctx.L.mpros_plan_batch(ctx.h, s_h.data_ptr(), g_h.data_ptr(), nq, status_h.data_ptr(), cost_h.data_ptr(),
-                                              len_h.data_ptr(), paths_h.data_ptr(), PATH_CAP, stats_h.data_ptr()))
+            lane = counter["host"] % LANES
+            counter["host"] += 1
+            b = hbuf[lane]
+            ctx.plan_batch_wait(lane)  # the lane's previous results have been consumed
+            ctx.plan_batch_submit(lane, s_h.data_ptr(), g_h.data_ptr(), nq, b["status"].data_ptr(), b["cost"].data_ptr(),
+                                  b["len"].data_ptr(), b["paths"].data_ptr(), PATH_CAP, b["stats"].data_ptr())
 
-        total_ms, step_ms, launches = timed_device(step_dev)
-        e2e_ms = timed_host(step_host)
+        def join_lanes():
+            """everything issued on the lanes precedes what follows on the context's stream (where the events are)"""
+            for lane in range(1, LANES):
+                if ctx.plan_lane_stream(lane):
+                    stream.wait_stream(lane_stream(lane))
+            if world > 1:
+                stream.wait_stream(torch.cuda.current_stream())  # the result gathers
+
+        total_ms, step_ms, launches = timed_device(step_dev, join_lanes)
+        e2e_ms = timed_host(step_host, lambda: ctx.plan_batch_wait(-1))
+        # one batch alone (no overlap): its latency and the planner kernel's own duration
+        lone = []
+        for _ in range(2):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            a0.record(stream)
+            b = dbuf[0]
+            ctx.plan_batch_submit_dev(0, s_d.data_ptr(), g_d.data_ptr(), nq, b["status"].data_ptr(), b["cost"].data_ptr(),
+                                      b["len"].data_ptr(), b["paths"].data_ptr(), PATH_CAP, b["stats"].data_ptr())
+            a1.record(stream)
+            barrier()
+            lone.append(a0.elapsed_time(a1))
+        lone_ms = float(min(lone))
         sampler.stop_flag = True
         sampler.join(timeout=2)
         st = stats_d.cpu().numpy().reshape(nq, 6)
@@ -441,7 +496,9 @@ def run_b200(args):
         expansions_all, checks_all, shots_all, cells_all, n_found, n_limit, n_fail = [int(v) for v in sums.tolist()]
         if rank == 0:
             secs = total_ms * 1e-3 / args.steps
-            k_ms = float(np.mean(step_ms))
+            # launches overlap when LANES > 1: the kernel's share of the timed region is region / launches (CUDA events on the
+            # context's stream around the whole region); one launch alone takes lone_ms
+            k_ms = float(np.mean(step_ms)) if LANES == 1 else total_ms / args.steps
             algo_bytes = B_EXPANSION * expansions + B_SHOT * shots + B_GOAL_CELL * cells
             achieved = algo_bytes / (k_ms * 1e-3) / 1e9
             line = {"metric": "plans_per_sec", "value": world * nq / secs, "unit": "plans/s", "ms_per_step": total_ms / args.steps,
@@ -449,7 +506,7 @@ def run_b200(args):
                             "d2h_bytes_per_step": nq * (4 + 8 + 4 + PATH_CAP * 40 + 48)},
                     "gpu_launches": int(launches),
                     "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("plan_team_kernel"),
-                                 "kernel": "plan_team_kernel", "kernel_ms": k_ms, "peak_source": peak_kind,
+                                 "kernel": "plan_team_kernel", "kernel_ms": k_ms, "kernel_ms_alone": lone_ms, "peak_source": peak_kind,
                                  "algorithmic_bytes_per_launch": algo_bytes,
                                  "note": "latency/FP64-issue bound (sequential A* per query, FP64 transcendentals), not HBM bound; see DESIGN.md"},
                     "extra": {"node_expansions_per_sec": expansions_all / secs, "footprint_checks_per_sec_in_planning": checks_all / secs,
@@ -458,7 +515,8 @@ def run_b200(args):
                               "collision_kernel_roofline": col_roof, "collision_hit_rate": hit_rate,
                               "plans_found": n_found, "plans_iteration_limit": n_limit, "plans_failed_other": n_fail,
                               "mean_expansions_per_query": expansions_all / (world * nq)},
-                    "config": {"workload": workload_text("plan"), "queries_per_gpu": nq, "path_cap": PATH_CAP,
+                    "config": {"workload": workload_text("plan"), "queries_per_gpu": nq, "path_cap": PATH_CAP, "batches_in_flight": LANES,
+                               "single_batch_ms": lone_ms,
                                "l2_policy": "per-query working sets (node pool, open list, closed set, goal wavefront) live in a ~110 MB-per-team HBM workspace, 296 teams (>> L2 in aggregate); map layers are L2-resident by design",
                                "preprocess_s_first_call": t_pre}}
 
@@ -500,6 +558,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="plan", choices=["plan", "collision"])
+    ap.add_argument("--lanes", type=int, default=3, help="plan workload: query batches in flight (1 = one batch at a time)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -90,6 +90,15 @@ extern "C" int mpros_ctx_destroy(mpros_ctx *c)
         return MPROS_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    for (int l = 1; l < MPROS_PLAN_LANES; ++l)
+        if (c->lane_stream[l])
+        {
+            cudaStreamSynchronize(c->lane_stream[l]);
+            cudaStreamDestroy(c->lane_stream[l]);
+            cudaEventDestroy(c->lane_event[l]);
+            if (c->lane_stage[l])
+                cudaFree(c->lane_stage[l]);
+        }
     void *bufs[] = {c->raw_bits, c->infl_bits, c->ds_bits, c->goal, c->obs_dist, c->edge_dist, c->region,
                     c->edge_bits, c->voronoi, c->scratch, c->stage, c->raw_tw, c->infl_tw};
     for (void *b : bufs)

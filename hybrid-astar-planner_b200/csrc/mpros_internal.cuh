@@ -110,6 +110,11 @@ struct Ctx
     size_t scratch_bytes = 0;
     void *stage = nullptr; // device staging for host-pointer entry points
     size_t stage_bytes = 0;
+    // plan lanes 1 .. MPROS_PLAN_LANES-1 (batches in flight beside the context's own stream, plan.cu); created on first use
+    cudaStream_t lane_stream[MPROS_PLAN_LANES] = {};
+    cudaEvent_t lane_event[MPROS_PLAN_LANES] = {};
+    void *lane_stage[MPROS_PLAN_LANES] = {};
+    size_t lane_stage_bytes[MPROS_PLAN_LANES] = {};
 
     PlannerView pv;
 

@@ -641,11 +641,12 @@ struct PlanScratch
     size_t todo_cap = 0;
     uint32_t tag_base = 0;
 };
-static PlanScratch g_plan_scratch[16][3]; // per device, per pass (node-pool size class)
+static PlanScratch g_plan_scratch[16][MPROS_PLAN_LANES][3]; // per device, per lane (batches in flight), per pass (node-pool size class)
 
-static int plan_pass(mpros_ctx *c, PlanBatchArgs &a, int pass, int node_cap, int n_run, const int32_t *d_todo, int max_warps)
+static int plan_pass(mpros_ctx *c, int lane, cudaStream_t stream, PlanBatchArgs &a, int pass, int node_cap, int n_run, const int32_t *d_todo,
+                     int max_warps)
 {
-    PlanScratch &S = g_plan_scratch[c->device & 15][pass];
+    PlanScratch &S = g_plan_scratch[c->device & 15][lane][pass];
     WarpWorkspaceLayout L = make_layout(node_cap, c->H, c->W);
     // resident warps: 4 per CTA, a multiple of the SM count; bounded by the workspace budget
     cudaDeviceProp prop;
@@ -678,7 +679,7 @@ static int plan_pass(mpros_ctx *c, PlanBatchArgs &a, int pass, int node_cap, int
         S.ws = nullptr;
         S.ws_bytes = 0;
         MPROS_CUDA(cudaMalloc(&S.ws, need));
-        MPROS_CUDA(cudaMemsetAsync(S.ws, 0, need, c->stream));
+        MPROS_CUDA(cudaMemsetAsync(S.ws, 0, need, stream));
         S.ws_bytes = need;
         S.tag_base = 0;
     }
@@ -687,19 +688,19 @@ static int plan_pass(mpros_ctx *c, PlanBatchArgs &a, int pass, int node_cap, int
     // generation tags must stay below 2^30 and unique per (warp, query); every warp handles < n_run queries
     if ((unsigned long long)S.tag_base + (unsigned long long)n_run + 2ull >= (1ull << 30))
     {
-        MPROS_CUDA(cudaMemsetAsync(S.ws, 0, S.ws_bytes, c->stream));
+        MPROS_CUDA(cudaMemsetAsync(S.ws, 0, S.ws_bytes, stream));
         S.tag_base = 0;
     }
     // a different layout re-interprets the same bytes: stale tags could alias, so clear when the layout changes
-    static WarpWorkspaceLayout last_layout[16][3];
-    WarpWorkspaceLayout &prev = last_layout[c->device & 15][pass];
+    static WarpWorkspaceLayout last_layout[16][MPROS_PLAN_LANES][3];
+    WarpWorkspaceLayout &prev = last_layout[c->device & 15][lane][pass];
     if (std::memcmp(&prev, &L, sizeof(L)) != 0)
     {
-        MPROS_CUDA(cudaMemsetAsync(S.ws, 0, S.ws_bytes, c->stream));
+        MPROS_CUDA(cudaMemsetAsync(S.ws, 0, S.ws_bytes, stream));
         S.tag_base = 0;
         prev = L;
     }
-    MPROS_CUDA(cudaMemsetAsync(S.counter, 0, 4, c->stream));
+    MPROS_CUDA(cudaMemsetAsync(S.counter, 0, 4, stream));
     a.L = L;
     a.ws = S.ws;
     a.counter = S.counter;
@@ -712,16 +713,16 @@ static int plan_pass(mpros_ctx *c, PlanBatchArgs &a, int pass, int node_cap, int
     {
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
-        cudaEventRecord(e0, c->stream);
+        cudaEventRecord(e0, stream);
     }
     if (cluster)
-        plan_cluster_kernel<kTeamWarps, kTeamMinBlocks><<<2 * blocks, kTeamWarps * 32, 0, c->stream>>>(c->view(), c->pv, a);
+        plan_cluster_kernel<kTeamWarps, kTeamMinBlocks><<<2 * blocks, kTeamWarps * 32, 0, stream>>>(c->view(), c->pv, a);
     else
-        plan_team_kernel<kTeamWarps, kTeamMinBlocks><<<blocks, kTeamWarps * 32, 0, c->stream>>>(c->view(), c->pv, a);
+        plan_team_kernel<kTeamWarps, kTeamMinBlocks><<<blocks, kTeamWarps * 32, 0, stream>>>(c->view(), c->pv, a);
     MPROS_LAUNCH_CHECK(c);
     if (dbg)
     {
-        cudaEventRecord(e1, c->stream);
+        cudaEventRecord(e1, stream);
         cudaEventSynchronize(e1);
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
@@ -753,9 +754,9 @@ static int plan_pass(mpros_ctx *c, PlanBatchArgs &a, int pass, int node_cap, int
 }
 } // namespace mpros
 
-static int plan_batch_dev_impl(mpros_ctx *c, const double *d_starts, const double *d_goals, int nq, int32_t *d_status, double *d_cost,
-                               int32_t *d_path_len, double *d_paths, int path_cap, int64_t *d_stats, double *d_trace = nullptr,
-                               long long trace_cap = 0, long long *d_trace_n = nullptr)
+static int plan_batch_dev_impl(mpros_ctx *c, int lane, cudaStream_t stream, const double *d_starts, const double *d_goals, int nq,
+                               int32_t *d_status, double *d_cost, int32_t *d_path_len, double *d_paths, int path_cap, int64_t *d_stats,
+                               double *d_trace = nullptr, long long trace_cap = 0, long long *d_trace_n = nullptr)
 {
     PlanBatchArgs a;
     std::memset(&a, 0, sizeof(a));
@@ -773,7 +774,7 @@ static int plan_batch_dev_impl(mpros_ctx *c, const double *d_starts, const doubl
     a.stats = d_stats;
     a.rs = rs_config_from_planner(c);
     a.optimal = c->pp.optimal_path;
-    PlanScratch &S = g_plan_scratch[c->device & 15][0];
+    PlanScratch &S = g_plan_scratch[c->device & 15][lane][0];
     // pass 1: every query with a small node pool; later passes: only the queries that overflowed, bigger pools
     const long long max_nodes = (long long)(c->pp.max_iteration + 2) * (2 * c->pv.n_steer) + 16;
     // node pools: when every resident team can own a pool for the iteration limit (B200: 296 teams x ~100 MB) each query
@@ -784,12 +785,13 @@ static int plan_batch_dev_impl(mpros_ctx *c, const double *d_starts, const doubl
         MPROS_CUDA(cudaMemGetInfo(&free_b, &total_b));
         size_t have = free_b;
         for (int k = 0; k < 3; ++k)
-            have += g_plan_scratch[c->device & 15][k].ws_bytes;
+            have += g_plan_scratch[c->device & 15][lane][k].ws_bytes;
         WarpWorkspaceLayout big = make_layout((int)max_nodes, c->H, c->W);
-        if (big.stride * (size_t)(2 * 148) < have / 2)
+        // lane 0 keeps half of the memory free for the caller; the extra lanes (pipelined batches) may use what is left
+        if (big.stride * (size_t)(kTeamMinBlocks * 148) < (lane == 0 ? have / 2 : have - have / 8))
             caps[0] = max_nodes;
     }
-    int rc = plan_pass(c, a, 0, (int)std::min<long long>(caps[0], max_nodes), nq, nullptr, 0);
+    int rc = plan_pass(c, lane, stream, a, 0, (int)std::min<long long>(caps[0], max_nodes), nq, nullptr, 0);
     if (rc)
         return rc;
     if (caps[0] >= max_nodes)
@@ -797,8 +799,8 @@ static int plan_batch_dev_impl(mpros_ctx *c, const double *d_starts, const doubl
     std::vector<int32_t> h_status(nq);
     for (int pass = 1; pass < 3; ++pass)
     {
-        MPROS_CUDA(cudaMemcpyAsync(h_status.data(), d_status, (size_t)nq * 4, cudaMemcpyDeviceToHost, c->stream));
-        MPROS_CUDA(cudaStreamSynchronize(c->stream));
+        MPROS_CUDA(cudaMemcpyAsync(h_status.data(), d_status, (size_t)nq * 4, cudaMemcpyDeviceToHost, stream));
+        MPROS_CUDA(cudaStreamSynchronize(stream));
         std::vector<int32_t> todo;
         for (int q = 0; q < nq; ++q)
             if (h_status[q] == ST_OVERFLOW)
@@ -813,9 +815,10 @@ static int plan_batch_dev_impl(mpros_ctx *c, const double *d_starts, const doubl
             MPROS_CUDA(cudaMalloc(&S.todo, todo.size() * 4 + 1024));
             S.todo_cap = todo.size() + 256;
         }
-        MPROS_CUDA(cudaMemcpyAsync(S.todo, todo.data(), todo.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        MPROS_CUDA(cudaMemcpyAsync(S.todo, todo.data(), todo.size() * 4, cudaMemcpyHostToDevice, stream));
+        // `todo` is pageable: the copy above has been staged before the call returns, the vector may go away
         long long cap = std::min(caps[pass], max_nodes);
-        rc = plan_pass(c, a, pass, (int)cap, (int)todo.size(), S.todo, 0);
+        rc = plan_pass(c, lane, stream, a, pass, (int)cap, (int)todo.size(), S.todo, 0);
         if (rc)
             return rc;
         if (cap >= max_nodes)
@@ -889,7 +892,7 @@ extern "C" int mpros_plan_search_tree(mpros_ctx *c, const double *start3, const 
     double sg[6] = {start3[0], start3[1], start3[2], goal3[0], goal3[1], goal3[2]};
     cudaMemcpyAsync(d_sg, sg, sizeof(sg), cudaMemcpyHostToDevice, st);
     cudaMemsetAsync(d_n, 0, 8, st);
-    rc = plan_batch_dev_impl(c, d_sg, d_sg + 3, 1, d_status, d_cost, d_len, nullptr, 0, nullptr, d_trace, max_exp, d_n);
+    rc = plan_batch_dev_impl(c, 0, st, d_sg, d_sg + 3, 1, d_status, d_cost, d_len, nullptr, 0, nullptr, d_trace, max_exp, d_n);
     if (rc)
     {
         cleanup();
@@ -942,55 +945,140 @@ extern "C" int mpros_plan_search_tree(mpros_ctx *c, const double *start3, const 
     return MPROS_OK;
 }
 
+namespace mpros
+{
+// Lanes: up to MPROS_PLAN_LANES query batches in flight per context. Lane 0 is the context's own stream; the others get a
+// stream, a staging area and planner workspaces of their own on first use, so the few long queries at the end of one batch
+// (the iteration-limit tail: a dependent chain of up to max_iteration expansions) overlap the next batch instead of
+// leaving the SMs idle. The map layers are shared and read-only while batches are in flight.
+static int lane_stream(mpros_ctx *c, int lane, cudaStream_t *out)
+{
+    if (lane < 0 || lane >= MPROS_PLAN_LANES)
+    {
+        set_error("plan lane out of range (0 .. MPROS_PLAN_LANES-1)");
+        return MPROS_ERR_INVALID;
+    }
+    if (lane == 0)
+    {
+        *out = c->stream;
+        return MPROS_OK;
+    }
+    if (!c->lane_stream[lane])
+    {
+        MPROS_CUDA(cudaStreamCreateWithFlags(&c->lane_stream[lane], cudaStreamNonBlocking));
+        MPROS_CUDA(cudaEventCreateWithFlags(&c->lane_event[lane], cudaEventDisableTiming));
+    }
+    // everything issued on the context's stream so far (map layers, planner configuration) precedes the batch
+    MPROS_CUDA(cudaEventRecord(c->lane_event[lane], c->stream));
+    MPROS_CUDA(cudaStreamWaitEvent(c->lane_stream[lane], c->lane_event[lane], 0));
+    *out = c->lane_stream[lane];
+    return MPROS_OK;
+}
+
+static int check_plan_args(mpros_ctx *c, const char *who, const void *s, const void *g, size_t nq, const void *status, const void *cost,
+                           const void *len, const void *paths, int path_cap)
+{
+    if (!s || !g || !status || !cost || !len || path_cap < 0 || (path_cap > 0 && !paths) || nq > (size_t)(1 << 28))
+    {
+        set_error(std::string(who) + ": NULL / invalid argument");
+        return MPROS_ERR_INVALID;
+    }
+    if ((unsigned long long)c->H * c->W * c->pv.num_yaw * 2ull >= (1ull << 34))
+    {
+        set_error("mpros_plan_batch: H*W*yaw*2 exceeds the closed-set key range (2^34)");
+        return MPROS_ERR_INVALID;
+    }
+    return MPROS_OK;
+}
+} // namespace mpros
+
+extern "C" void *mpros_plan_lane_stream(mpros_ctx *c, int lane)
+{
+    if (!c || lane < 0 || lane >= MPROS_PLAN_LANES)
+        return nullptr;
+    return lane == 0 ? (void *)c->stream : (void *)c->lane_stream[lane];
+}
+
+extern "C" int mpros_plan_batch_wait(mpros_ctx *c, int lane)
+{
+    if (!c || lane >= MPROS_PLAN_LANES)
+    {
+        set_error("mpros_plan_batch_wait: invalid argument");
+        return MPROS_ERR_INVALID;
+    }
+    MPROS_CUDA(cudaSetDevice(c->device));
+    for (int l = 0; l < MPROS_PLAN_LANES; ++l)
+    {
+        if (lane >= 0 && l != lane)
+            continue;
+        cudaStream_t st = l == 0 ? c->stream : c->lane_stream[l];
+        if (l == 0 || st)
+            MPROS_CUDA(cudaStreamSynchronize(st));
+    }
+    return MPROS_OK;
+}
+
+extern "C" int mpros_plan_batch_submit_dev(mpros_ctx *c, int lane, const double *d_starts3, const double *d_goals3, size_t nq,
+                                           int32_t *d_status, double *d_cost, int32_t *d_path_len, double *d_paths, int path_cap,
+                                           int64_t *d_stats)
+{
+    int rc = check_planner_ready(c, "mpros_plan_batch_submit_dev");
+    if (rc)
+        return rc;
+    if (nq == 0)
+        return MPROS_OK;
+    rc = check_plan_args(c, "mpros_plan_batch_submit_dev", d_starts3, d_goals3, nq, d_status, d_cost, d_path_len, d_paths, path_cap);
+    if (rc)
+        return rc;
+    MPROS_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st;
+    rc = lane_stream(c, lane, &st);
+    if (rc)
+        return rc;
+    return plan_batch_dev_impl(c, lane, st, d_starts3, d_goals3, (int)nq, d_status, d_cost, d_path_len, d_paths, path_cap, d_stats);
+}
+
 extern "C" int mpros_plan_batch_dev(mpros_ctx *c, const double *d_starts3, const double *d_goals3, size_t nq, int32_t *d_status,
                                     double *d_cost, int32_t *d_path_len, double *d_paths, int path_cap, int64_t *d_stats)
 {
-    int rc = check_planner_ready(c, "mpros_plan_batch_dev");
-    if (rc)
-        return rc;
-    if (nq == 0)
-        return MPROS_OK;
-    if (!d_starts3 || !d_goals3 || !d_status || !d_cost || !d_path_len || path_cap < 0 || (path_cap > 0 && !d_paths) ||
-        nq > (size_t)(1 << 28))
-    {
-        set_error("mpros_plan_batch_dev: NULL / invalid argument");
-        return MPROS_ERR_INVALID;
-    }
-    if ((unsigned long long)c->H * c->W * c->pv.num_yaw * 2ull >= (1ull << 34))
-    {
-        set_error("mpros_plan_batch: H*W*yaw*2 exceeds the closed-set key range (2^34)");
-        return MPROS_ERR_INVALID;
-    }
-    MPROS_CUDA(cudaSetDevice(c->device));
-    return plan_batch_dev_impl(c, d_starts3, d_goals3, (int)nq, d_status, d_cost, d_path_len, d_paths, path_cap, d_stats);
+    return mpros_plan_batch_submit_dev(c, 0, d_starts3, d_goals3, nq, d_status, d_cost, d_path_len, d_paths, path_cap, d_stats);
 }
 
-extern "C" int mpros_plan_batch(mpros_ctx *c, const double *starts3, const double *goals3, size_t nq, int32_t *status, double *cost,
-                                int32_t *path_len, double *paths, int path_cap, int64_t *stats)
+extern "C" int mpros_plan_batch_submit(mpros_ctx *c, int lane, const double *starts3, const double *goals3, size_t nq, int32_t *status,
+                                       double *cost, int32_t *path_len, double *paths, int path_cap, int64_t *stats)
 {
-    int rc = check_planner_ready(c, "mpros_plan_batch");
+    int rc = check_planner_ready(c, "mpros_plan_batch_submit");
     if (rc)
         return rc;
     if (nq == 0)
         return MPROS_OK;
-    if (!starts3 || !goals3 || !status || !cost || !path_len || path_cap < 0 || (path_cap > 0 && !paths) || nq > (size_t)(1 << 28))
-    {
-        set_error("mpros_plan_batch: NULL / invalid argument");
-        return MPROS_ERR_INVALID;
-    }
-    if ((unsigned long long)c->H * c->W * c->pv.num_yaw * 2ull >= (1ull << 34))
-    {
-        set_error("mpros_plan_batch: H*W*yaw*2 exceeds the closed-set key range (2^34)");
-        return MPROS_ERR_INVALID;
-    }
+    rc = check_plan_args(c, "mpros_plan_batch_submit", starts3, goals3, nq, status, cost, path_len, paths, path_cap);
+    if (rc)
+        return rc;
     MPROS_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st;
+    rc = lane_stream(c, lane, &st);
+    if (rc)
+        return rc;
     size_t pose_b = nq * 24, path_b = nq * (size_t)path_cap * 5 * 8;
     size_t total = 2 * align_up(pose_b, 256) + align_up(nq * 4, 256) * 2 + align_up(nq * 8, 256) + align_up(path_b, 256) +
                    align_up(nq * 48, 256) + 1024;
-    rc = ensure_stage(c, total);
+    if (lane == 0)
+        rc = ensure_stage(c, total);
+    else if (total > c->lane_stage_bytes[lane])
+    {
+        // the lane's previous batch may still read its staging area
+        MPROS_CUDA(cudaStreamSynchronize(st));
+        if (c->lane_stage[lane])
+            MPROS_CUDA(cudaFree(c->lane_stage[lane]));
+        c->lane_stage[lane] = nullptr;
+        c->lane_stage_bytes[lane] = 0;
+        MPROS_CUDA(cudaMalloc(&c->lane_stage[lane], total));
+        c->lane_stage_bytes[lane] = total;
+    }
     if (rc)
         return rc;
-    char *base = static_cast<char *>(c->stage);
+    char *base = static_cast<char *>(lane == 0 ? c->stage : c->lane_stage[lane]);
     size_t o = 0;
     auto take = [&](size_t bytes) {
         char *p = base + o;
@@ -1002,10 +1090,9 @@ extern "C" int mpros_plan_batch(mpros_ctx *c, const double *starts3, const doubl
     double *d_cost = (double *)take(nq * 8);
     double *d_paths = path_cap ? (double *)take(path_b) : nullptr;
     int64_t *d_stats = (int64_t *)take(nq * 48);
-    cudaStream_t st = c->stream;
     MPROS_CUDA(cudaMemcpyAsync(d_s, starts3, pose_b, cudaMemcpyHostToDevice, st));
     MPROS_CUDA(cudaMemcpyAsync(d_g, goals3, pose_b, cudaMemcpyHostToDevice, st));
-    rc = plan_batch_dev_impl(c, d_s, d_g, (int)nq, d_status, d_cost, d_len, d_paths, path_cap, d_stats);
+    rc = plan_batch_dev_impl(c, lane, st, d_s, d_g, (int)nq, d_status, d_cost, d_len, d_paths, path_cap, d_stats);
     if (rc)
         return rc;
     MPROS_CUDA(cudaMemcpyAsync(status, d_status, nq * 4, cudaMemcpyDeviceToHost, st));
@@ -1015,6 +1102,14 @@ extern "C" int mpros_plan_batch(mpros_ctx *c, const double *starts3, const doubl
         MPROS_CUDA(cudaMemcpyAsync(paths, d_paths, path_b, cudaMemcpyDeviceToHost, st));
     if (stats)
         MPROS_CUDA(cudaMemcpyAsync(stats, d_stats, nq * 48, cudaMemcpyDeviceToHost, st));
-    MPROS_CUDA(cudaStreamSynchronize(st));
     return MPROS_OK;
+}
+
+extern "C" int mpros_plan_batch(mpros_ctx *c, const double *starts3, const double *goals3, size_t nq, int32_t *status, double *cost,
+                                int32_t *path_len, double *paths, int path_cap, int64_t *stats)
+{
+    int rc = mpros_plan_batch_submit(c, 0, starts3, goals3, nq, status, cost, path_len, paths, path_cap, stats);
+    if (rc || nq == 0)
+        return rc;
+    return mpros_plan_batch_wait(c, 0);
 }

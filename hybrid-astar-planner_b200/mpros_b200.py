@@ -153,8 +153,16 @@ def load_library(path=LIB_PATH):
     L.mpros_path_postprocess_batch.argtypes = [vp, vp, vp, sz, vp, sz, vp]
     L.mpros_plan_search_tree.argtypes = [vp, vp, vp, vp, vp, vp, sz, C.POINTER(sz)]
     L.mpros_plan_batch_dev.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, i, vp]
+    L.mpros_plan_batch_submit.argtypes = [vp, i, vp, vp, sz, vp, vp, vp, vp, i, vp]
+    L.mpros_plan_batch_submit_dev.argtypes = [vp, i, vp, vp, sz, vp, vp, vp, vp, i, vp]
+    L.mpros_plan_batch_wait.argtypes = [vp, i]
+    L.mpros_plan_lane_stream.restype = vp
+    L.mpros_plan_lane_stream.argtypes = [vp, i]
     _lib = L
     return L
+
+
+PLAN_LANES = 4  # MPROS_PLAN_LANES
 
 
 def exported_symbols():
@@ -414,6 +422,21 @@ class Context:
 
     def plan_batch_dev(self, d_starts, d_goals, nq, d_status, d_cost, d_len, d_paths, path_cap, d_stats):
         self._check(self.L.mpros_plan_batch_dev(self.h, d_starts, d_goals, nq, d_status, d_cost, d_len, d_paths, path_cap, d_stats))
+
+    # batches in flight: lane = 0 .. PLAN_LANES-1, raw pointers (device for *_dev, page-locked host otherwise)
+    def plan_batch_submit_dev(self, lane, d_starts, d_goals, nq, d_status, d_cost, d_len, d_paths, path_cap, d_stats):
+        self._check(self.L.mpros_plan_batch_submit_dev(self.h, lane, d_starts, d_goals, nq, d_status, d_cost, d_len, d_paths, path_cap,
+                                                       d_stats))
+
+    def plan_batch_submit(self, lane, h_starts, h_goals, nq, h_status, h_cost, h_len, h_paths, path_cap, h_stats):
+        self._check(self.L.mpros_plan_batch_submit(self.h, lane, h_starts, h_goals, nq, h_status, h_cost, h_len, h_paths, path_cap,
+                                                   h_stats))
+
+    def plan_batch_wait(self, lane=-1):
+        self._check(self.L.mpros_plan_batch_wait(self.h, lane))
+
+    def plan_lane_stream(self, lane):
+        return self.L.mpros_plan_lane_stream(self.h, lane)
 
     def plan_search_tree(self, start, goal):
         """HybridAstar::getSearchTree for one query: (status, cost, [n, 4] {next_x, next_y, curr_x, curr_y})."""

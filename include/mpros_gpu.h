@@ -251,6 +251,27 @@ MPROS_API int mpros_plan_batch_dev(mpros_ctx *ctx, const double *d_starts3, cons
                                    int32_t *d_status, double *d_cost, int32_t *d_path_len, double *d_paths, int path_cap,
                                    int64_t *d_stats);
 
+/* Batches in flight ("lanes"). The reference plans one query at a time in the ROS spin thread (main_planner.cpp:225-229,
+ * planner_ros.cpp:44-51); a caller that streams query batches (a planning service) keeps up to MPROS_PLAN_LANES of them in
+ * flight: mpros_plan_batch_submit[_dev] enqueues the batch on the lane's own stream (lane 0 = the context's stream) with
+ * the lane's own planner workspaces and returns; mpros_plan_batch_wait(ctx, lane) blocks until that lane's batch and its
+ * result copies are complete (lane < 0: all lanes). The iteration-limit tail of one batch - a handful of queries, each a
+ * dependent chain of up to max_iteration expansions - then overlaps the next batch. Results are identical to
+ * mpros_plan_batch (which is submit on lane 0 + wait). Host buffers of mpros_plan_batch_submit must stay valid until the
+ * wait and should be page-locked (pageable buffers make the copies synchronous). The map layers are shared by all lanes:
+ * do not call mpros_map_set_occupancy / mpros_map_upload / mpros_planner_config while a batch is in flight. A lane takes
+ * one batch at a time (submitting to a busy lane queues behind it on the lane's stream). */
+#define MPROS_PLAN_LANES 4
+MPROS_API int mpros_plan_batch_submit(mpros_ctx *ctx, int lane, const double *starts3, const double *goals3, size_t nq,
+                                      int32_t *status, double *cost, int32_t *path_len, double *paths, int path_cap,
+                                      int64_t *stats);
+MPROS_API int mpros_plan_batch_submit_dev(mpros_ctx *ctx, int lane, const double *d_starts3, const double *d_goals3, size_t nq,
+                                          int32_t *d_status, double *d_cost, int32_t *d_path_len, double *d_paths,
+                                          int path_cap, int64_t *d_stats);
+MPROS_API int mpros_plan_batch_wait(mpros_ctx *ctx, int lane);
+/* cudaStream_t of a lane (NULL before its first submit), e.g. to record events or order other device work behind a batch */
+MPROS_API void *mpros_plan_lane_stream(mpros_ctx *ctx, int lane);
+
 /* HybridAstar::getSearchTree (hybrid_a_star.cpp:1114-1164) of ONE query: plans (start, goal) exactly like
  * mpros_plan_batch with nq = 1 while recording tree_ (the pose of every expanded node; hybrid_a_star.cpp:352 stores it once
  * per primitive) and turns every (expanded node, primitive) into ceil(step_size / path_point_distance) leaf segments

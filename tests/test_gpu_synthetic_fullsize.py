@@ -117,3 +117,58 @@ def test_full_batch_properties(syn):
     assert (a["cost"][ok] >= d - 1e-9).all()
     poses = np.concatenate([a["paths"][q, : a["path_len"][q], :3] for q in ok[:4096]])
     assert not ctx.collision_check(poses).any(), "a returned path collides"
+
+
+def test_batches_in_flight_match_the_synchronous_call(syn):
+    """mpros_plan_batch_submit[_dev] / mpros_plan_batch_wait: several batches in flight on their own lanes (streams +
+    workspaces) give exactly the per-query results of mpros_plan_batch, in any interleaving."""
+    import torch
+
+    import mpros_b200
+
+    ctx, params, occ, starts, goals = syn
+    n = 2048
+    cap = 64
+    ref = [ctx.plan_batch(starts[k * n:(k + 1) * n], goals[k * n:(k + 1) * n], path_cap=cap) for k in range(4)]
+    lanes = [0, 1, 2, 3][: mpros_b200.PLAN_LANES]
+
+    def bufs(pin):
+        mk = (lambda *a, **k: torch.zeros(*a, **k).pin_memory()) if pin else (lambda *a, **k: torch.zeros(*a, device="cuda", **k))
+        return {"status": mk(n, dtype=torch.int32), "cost": mk(n, dtype=torch.float64), "len": mk(n, dtype=torch.int32),
+                "paths": mk(n * cap * 5, dtype=torch.float64), "stats": mk(n * 6, dtype=torch.int64)}
+
+    # host buffers (page-locked): all lanes submitted before the first wait
+    hb = [bufs(True) for _ in lanes]
+    hs = [torch.from_numpy(starts[k * n:(k + 1) * n].copy()).pin_memory() for k in range(len(lanes))]
+    hg = [torch.from_numpy(goals[k * n:(k + 1) * n].copy()).pin_memory() for k in range(len(lanes))]
+    for k, lane in enumerate(lanes):
+        b = hb[k]
+        ctx.plan_batch_submit(lane, hs[k].data_ptr(), hg[k].data_ptr(), n, b["status"].data_ptr(), b["cost"].data_ptr(),
+                              b["len"].data_ptr(), b["paths"].data_ptr(), cap, b["stats"].data_ptr())
+    ctx.plan_batch_wait(-1)
+    for k in range(len(lanes)):
+        b, r = hb[k], ref[k]
+        assert np.array_equal(b["status"].numpy(), r["status"]) and np.array_equal(b["cost"].numpy(), r["cost"]), "lane %d" % k
+        assert np.array_equal(b["len"].numpy(), r["path_len"])
+        got = b["paths"].numpy().reshape(n, cap, 5)
+        valid = np.arange(cap)[None, :] < np.minimum(r["path_len"], cap)[:, None]  # rows past path_len are not written
+        assert np.array_equal(got[valid], r["paths"][valid])
+        assert np.array_equal(b["stats"].numpy().reshape(n, 6)[:, 0], r["iterations"])
+    # device buffers, two rounds per lane (the second queues behind the first on the lane's stream), waited per lane
+    ds = [t.cuda() for t in hs]
+    dg = [t.cuda() for t in hg]
+    db = [bufs(False) for _ in lanes]
+    torch.cuda.synchronize()
+    for rnd in range(2):
+        for k, lane in enumerate(lanes):
+            b = db[k]
+            ctx.plan_batch_submit_dev(lane, ds[k].data_ptr(), dg[k].data_ptr(), n, b["status"].data_ptr(), b["cost"].data_ptr(),
+                                      b["len"].data_ptr(), b["paths"].data_ptr(), cap, b["stats"].data_ptr())
+    for k, lane in reversed(list(enumerate(lanes))):
+        ctx.plan_batch_wait(lane)
+        b, r = db[k], ref[k]
+        assert np.array_equal(b["status"].cpu().numpy(), r["status"]) and np.array_equal(b["cost"].cpu().numpy(), r["cost"])
+        assert np.array_equal(b["stats"].cpu().numpy().reshape(n, 6)[:, 0], r["iterations"])
+    assert ctx.plan_lane_stream(1) and ctx.plan_lane_stream(0) == ctx.stream()
+    with pytest.raises(Exception):
+        ctx.plan_batch_wait(mpros_b200.PLAN_LANES)
