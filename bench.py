@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200-native mpros hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload plan|collision]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload plan|collision|expand|preprocess]
 
 Workload "plan" (default; BASELINE.json configs[4]): synthetic 8192x8192 occupancy grid @0.1 m
 (seed 20261019: 1-m border wall + 1100 rectangles), inflation 1.0 m, down-sampling 8, shipped planner parameters
@@ -42,6 +42,7 @@ POSE_SEED = 1
 B_CHECK = 24 + 1 + (22 + 1 + 4)  # C1 @0.1 m: pose in + verdict out + (n+1+4) one-byte map cells
 B_EXPANSION = 450                # E1 with the case-1 survivor / insert ratios
 B_SHOT = 440                     # R4 without the trajectory
+EXPANSIONS_PER_STEP = 1 << 20
 B_GOAL_CELL = 5                  # N4: 1 B in, 4 B out per cell of the goal map
 
 
@@ -156,6 +157,12 @@ def _cpu_worker_collision(poses):
     return time.perf_counter() - t0, int(v.sum()), len(poses)
 
 
+def _cpu_worker_pre(goal):
+    t0 = time.perf_counter()
+    _W["rm"].update_goal(goal[0], goal[1])
+    return _W["t_pre"], time.perf_counter() - t0
+
+
 def _cpu_worker_plan(job):
     from oracle import refapi
 
@@ -196,6 +203,10 @@ class CpuArm:
         n = sum(r[3] for r in res)
         return {"plans_per_sec": n / t, "expansions_per_sec": sum(r[2] for r in res) / 6.0 / t, "solved": sum(r[1] for r in res),
                 "n": n, "preprocess_s": max(r[4] for r in res)}
+
+    def preprocess_time(self, gx, gy):
+        res = self.pool.map(_cpu_worker_pre, [(gx, gy)] * self.cores)
+        return max(r[0] for r in res), max(r[1] for r in res)
 
     def close(self):
         self.pool.close()
@@ -245,11 +256,11 @@ def run_reference(args):
                 sl = slice(s * per_step, (s + 1) * per_step)
                 r = arm.plan_rate(lib_poses[0][sl], lib_poses[1][sl])
                 if s >= args.warmup:
-                    vals.append(r["plans_per_sec"])
+                    vals.append(r["expansions_per_sec"] if args.workload == "expand" else r["plans_per_sec"])
                     extra = r
                 if time.perf_counter() - t0 > 240 and vals:
                     break
-            metric, unit = "plans_per_sec", "plans/s"
+            metric, unit = ("node_expansions_per_sec", "expansions/s") if args.workload == "expand" else ("plans_per_sec", "plans/s")
             sample = ("%d seeded queries per step (2 per process) on the synthetic 8192^2 map (ds=8), %d processes x 1 thread; timed region per "
                       "query = NavMap::updateGoal + HybridAstar ctor + Plan() (map preprocessing %.1f s excluded)" % (per_step, cores, extra.get("preprocess_s", 0)))
     finally:
@@ -257,7 +268,7 @@ def run_reference(args):
     value = float(np.mean(vals))
     line = {
         "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": len(vals),
-        "warmup": args.warmup, "ms_per_step": 1e3 * per_step / value, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": (1e3 * per_step / extra["plans_per_sec"]) if args.workload == "expand" else 1e3 * per_step / value, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_text(args.workload), "units_per_step": per_step},
         "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "reference", "sample": sample},
@@ -290,6 +301,13 @@ def _ref_queries(occ, params, n):
 def workload_text(w):
     if w == "collision":
         return "collision: synthetic 8192x8192 @0.1 m (seed 20261019), inflation 1.0 m, batched footPrintInCollision4 over seeded uniform poses"
+    if w == "preprocess":
+        return ("preprocess: synthetic 8192x8192 @0.1 m (seed 20261019), ds=8, inflation 1.0 m; NavMap::setOccupancyMap (threshold, inflation, "
+                "down-sampling, obstacle labelling, L1 distance maps, Voronoi field) + NavMap::updateGoal (holonomic goal map) per step")
+    if w == "expand":
+        return ("expand: synthetic 8192x8192 @0.1 m (seed 20261019), ds=8, inflation 1.0 m, shipped planner config; batched "
+                "HybridAstar::expandNode (6 primitives, footprint test, node cost, goal-map + Reeds-Shepp heuristic, closed-set prune) over "
+                "seeded collision-free parent poses of one query")
     return ("plan: synthetic 8192x8192 @0.1 m (seed 20261019), ds=8, inflation 1.0 m, shipped planner config (3 steers, 36 yaw bins, step 2 m); "
             "independent seeded start/goal queries 20-80 m apart; per query goal heuristic + Hybrid A* + Reeds-Shepp shots")
 
@@ -402,6 +420,119 @@ def run_b200(args):
                     "gpu_launches": int(col_launches), "roofline": col_roof,
                     "config": {"workload": workload_text("collision"), "poses_per_step_per_gpu": n, "hit_rate": hit_rate,
                                "l2_policy": "inputs larger than L2 (403 MB of poses per step)", "preprocess_s_first_call": t_pre}}
+    elif args.workload == "preprocess":
+        # N1-N9 + N4: every map layer from the int8 occupancy grid, then the goal map of one goal
+        H0, W0 = occ.shape
+        occ_d = occ_pinned.cuda()
+        info = ctx.info()
+        cells0, cells = H0 * W0, int(info["map_height"]) * int(info["map_width"])
+        gx, gy = EXTENT * 0.5 + 3.3, EXTENT * 0.5 - 1.7
+        vor_h = torch.zeros(cells, dtype=torch.float32).pin_memory()
+        goal_h = torch.zeros(cells, dtype=torch.int32).pin_memory()
+
+        def step_dev():
+            ctx.set_occupancy_dev(occ_d.data_ptr(), W0, H0, SYN_RES, [0.0, 0.0, 0.0])
+            ctx.update_goal(gx, gy)
+
+        def step_host():
+            ctx._check(ctx.L.mpros_map_set_occupancy(ctx.h, occ_pinned.data_ptr(), W0, H0, SYN_RES, 0.0, 0.0, 0.0))
+            ctx.update_goal(gx, gy)
+            ctx._check(ctx.L.mpros_map_download(ctx.h, mpros_b200.LAYERS["voronoi"][0], vor_h.data_ptr(), vor_h.numel() * 4))
+            ctx._check(ctx.L.mpros_map_download(ctx.h, mpros_b200.LAYERS["goal"][0], goal_h.data_ptr(), goal_h.numel() * 4))
+
+        total_ms, step_ms, launches = timed_device(step_dev)
+        e2e_ms = timed_host(step_host)
+        # split of one step: the map layers (N1-N3, N5-N9) and the goal map (N4)
+        split = []
+        for _ in range(5):
+            ea, eb, ec = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ea.record(stream)
+            ctx.set_occupancy_dev(occ_d.data_ptr(), W0, H0, SYN_RES, [0.0, 0.0, 0.0])
+            eb.record(stream)
+            ctx.update_goal(gx, gy)
+            ec.record(stream)
+            torch.cuda.synchronize()
+            split.append((ea.elapsed_time(eb), eb.elapsed_time(ec)))
+        occ_ms, goal_ms = [float(np.median(v)) for v in zip(*split)]
+        goal_layer = ctx.layer("goal")
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+        total_ms, e2e_ms = max_over_ranks([total_ms, e2e_ms])
+        if rank == 0:
+            k_ms = float(np.mean(step_ms))
+            ds = SYN_DS
+            algo = cells0 * (2 + (1 + 1.0 / (ds * ds)) + 2) + cells * (18 + 2 * B_GOAL_CELL)
+            achieved = algo / (k_ms * 1e-3) / 1e9
+            line = {"metric": "map_cells_per_sec", "value": world * cells0 * args.steps / (total_ms * 1e-3), "unit": "cells/s",
+                    "ms_per_step": total_ms / args.steps,
+                    "e2e": {"value": world * cells0 * args.steps / (e2e_ms * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": cells0,
+                            "d2h_bytes_per_step": cells * 8},
+                    "gpu_launches": int(launches),
+                    "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                                 "kernel": "whole step (%d launches: N1 threshold_pack_vec, N3 inflate, N2 downsample, tile words, N5 ccl_*, N6/N8 dt_row/dt_col, N7 edge, N9 voronoi_cost, N4 goal_bfs_cluster x2)" % (launches // max(1, args.steps)),
+                                 "kernel_ms": k_ms, "peak_source": peak_kind, "algorithmic_bytes_per_launch": algo,
+                                 "note": "per original cell N1 2 B + N2 1+1/ds^2 B + N3 2 B, per down-sampled cell N5-N9 18 B + N4 2 x 5 B (SURVEY 8d; setOccupancyMap regenerates the goal map once a goal is known, nav_map.cpp:150-156, updateGoal does it again); the step is a chain of ~40 short kernels on a 1024^2 grid plus <= 999 wavefront levels, launch/sync latency bound rather than HBM bound"},
+                    "extra": {"set_occupancy_ms": occ_ms, "update_goal_ms": goal_ms,
+                              "goal_map_levels": int(goal_layer[goal_layer < 1000].max()), "goal_map_cells_reached": int((goal_layer < 1000).sum()),
+                              "collision_kernel_checks_per_sec": col_value},
+                    "config": {"workload": workload_text("preprocess"), "cells_per_step_per_gpu": cells0, "downsampled_cells": cells,
+                               "l2_policy": "64 MiB int8 grid read once per step; the bit-packed layers (8 MiB each) stay in L2 by design",
+                               "preprocess_s_first_call": t_pre}}
+    elif args.workload == "expand":
+        # E1-E5: the frontier-parallel expansion kernel on a node batch of ONE query (goal fixed, goal map resident)
+        ne = EXPANSIONS_PER_STEP
+        P = ctx.n_primitives()
+        rng = np.random.default_rng(POSE_SEED + 77 + rank)
+        cand = gen_poses(3 * ne, POSE_SEED + 50 + 1000 * rank)
+        cand = cand[ctx.collision_check(cand) == 0][:ne]
+        assert len(cand) == ne
+        goal = np.array([EXTENT * 0.5 + 3.3, EXTENT * 0.5 - 1.7, 0.6])
+        while ctx.collision_check(goal[None, :])[0]:
+            goal[:2] += 0.9
+        ctx.update_goal(goal[0], goal[1])
+        steer = params["/mpros/vehicle/max_steering_angle"] * rng.integers(-1, 2, ne)
+        par = np.concatenate([cand, steer[:, None], rng.choice([-1.0, 1.0], ne)[:, None], rng.uniform(0, 100, ne)[:, None]], axis=1)
+        par_h = torch.from_numpy(np.ascontiguousarray(par)).pin_memory()
+        par_d = par_h.cuda()
+        pr_d = torch.zeros(ne * P * 7, dtype=torch.float64, device="cuda")
+        ch_d = torch.zeros(ne * P * 10, dtype=torch.float64, device="cuda")
+        nc_d = torch.zeros(ne, dtype=torch.int32, device="cuda")
+        pr_h = torch.zeros(ne * P * 7, dtype=torch.float64).pin_memory()
+        ch_h = torch.zeros(ne * P * 10, dtype=torch.float64).pin_memory()
+        nc_h = torch.zeros(ne, dtype=torch.int32).pin_memory()
+        g_c = goal.ctypes.data
+
+        def step_dev():
+            ctx._check(ctx.L.mpros_expand_batch_dev(ctx.h, None, g_c, par_d.data_ptr(), ne, pr_d.data_ptr(), ch_d.data_ptr(), nc_d.data_ptr()))
+
+        def step_host():
+            ctx._check(ctx.L.mpros_expand_batch(ctx.h, None, g_c, par_h.data_ptr(), ne, pr_h.data_ptr(), ch_h.data_ptr(), nc_h.data_ptr()))
+
+        total_ms, step_ms, launches = timed_device(step_dev)
+        e2e_ms = timed_host(step_host)
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+        assert torch.equal(nc_h, nc_d.cpu()) and torch.equal(ch_h, ch_d.cpu()), "host-API and device-API expansions differ"
+        total_ms, e2e_ms = max_over_ranks([total_ms, e2e_ms])
+        if rank == 0:
+            k_ms = float(np.mean(step_ms))
+            achieved = ne * B_EXPANSION / (k_ms * 1e-3) / 1e9
+            survivors = float((pr_h.view(ne, P, 7)[:, :, 5] == 0).float().mean())
+            line = {"metric": "node_expansions_per_sec", "value": world * ne * args.steps / (total_ms * 1e-3), "unit": "expansions/s",
+                    "ms_per_step": total_ms / args.steps,
+                    "e2e": {"value": world * ne * args.steps / (e2e_ms * 1e-3), "unit": "expansions/s", "h2d_bytes_per_step": ne * 48,
+                            "d2h_bytes_per_step": ne * (P * 17 * 8 + 4)},
+                    "gpu_launches": int(launches),
+                    "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                                 "traffic": ncu_traffic("expand_batch_kernel"), "kernel": "expand_batch_kernel", "kernel_ms": k_ms,
+                                 "peak_source": peak_kind, "algorithmic_bytes_per_unit": B_EXPANSION,
+                                 "note": "the kernel also writes the reference-format records (P x 7 + P x 10 doubles = 816 B per expansion), above the 450 B algorithmic figure"},
+                    "extra": {"primitives_per_sec": world * ne * P * args.steps / (total_ms * 1e-3), "primitive_survival_rate": survivors,
+                              "children_inserted_per_expansion": float(nc_h.float().mean()),
+                              "collision_kernel_checks_per_sec": col_value, "collision_kernel_roofline": col_roof},
+                    "config": {"workload": workload_text("expand"), "expansions_per_step_per_gpu": ne, "primitives_per_expansion": P,
+                               "l2_policy": "inputs + outputs larger than L2 (50 MB of parents in, 860 MB of records out per step)",
+                               "preprocess_s_first_call": t_pre}}
     else:
         nq = QUERIES_PER_GPU
         starts, goals = gen_queries(ctx, nq, synthetic.SYN_QUERY_SEED + rank)
@@ -531,6 +662,15 @@ def run_b200(args):
                         v = arm.collision_rate(1 << 22, POSE_SEED + 6)
                         cpu = {"value": v, "unit": "checks/s", "cores": 1, "kind": "reference",
                                "sample": "4194304 seeded uniform poses on the synthetic 8192^2 map, 1 process x 1 thread, unmodified reference footPrintInCollision4 loop (preprocessing excluded)"}
+                    elif args.workload == "preprocess":
+                        r = arm.preprocess_time(EXTENT * 0.5 + 3.3, EXTENT * 0.5 - 1.7)
+                        cpu = {"value": occ.size / (r[0] + r[1]), "unit": "cells/s", "cores": 1, "kind": "reference",
+                               "sample": "one pass: unmodified reference NavMap::setOccupancyMap (%.2f s) + updateGoal (%.2f s) on the same 8192^2 map, 1 process x 1 thread" % r}
+                    elif args.workload == "expand":
+                        qs, qg = gen_queries(ctx, 8, synthetic.SYN_QUERY_SEED)
+                        r = arm.plan_rate(qs, qg)
+                        cpu = {"value": r["expansions_per_sec"], "unit": "expansions/s", "cores": 1, "kind": "reference",
+                               "sample": "expandNode calls inside the unmodified reference's Plan() on 8 seeded queries of the plan workload, 1 process x 1 thread (primitives evaluated / 6 / time of updateGoal + ctor + Plan())"}
                     else:
                         r = arm.plan_rate(starts[:8], goals[:8])
                         cpu = {"value": r["plans_per_sec"], "unit": "plans/s", "cores": 1, "kind": "reference",
@@ -557,7 +697,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="plan", choices=["plan", "collision"])
+    ap.add_argument("--workload", default="plan", choices=["plan", "collision", "expand", "preprocess"])
     ap.add_argument("--lanes", type=int, default=3, help="plan workload: query batches in flight (1 = one batch at a time)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

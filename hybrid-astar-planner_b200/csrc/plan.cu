@@ -545,22 +545,23 @@ extern "C" int mpros_rs_distance_batch(mpros_ctx *c, double rho, const double *a
     return MPROS_OK;
 }
 
-extern "C" int mpros_expand_batch(mpros_ctx *c, const double *start3, const double *goal3, const double *parents6, size_t n,
-                                  double *prims, double *childs, int32_t *nchild)
+// expandNode for n parents of one query; device buffers, asynchronous on the context's stream
+static int expand_launch(mpros_ctx *c, const char *who, const double *start3, const double *goal3, const double *d_parents6, size_t n,
+                         double *d_prims, double *d_childs, int32_t *d_nchild)
 {
-    int rc = check_planner_ready(c, "mpros_expand_batch");
+    int rc = check_planner_ready(c, who);
     if (rc)
         return rc;
     if (!c->get_goal)
     {
-        set_error("mpros_expand_batch: no goal map (mpros_map_update_goal first)"); // hybrid_a_star.cpp:96-100
+        set_error(std::string(who) + ": no goal map (mpros_map_update_goal first)"); // hybrid_a_star.cpp:96-100
         return MPROS_ERR_INVALID;
     }
     if (n == 0)
         return MPROS_OK;
-    if (!goal3 || !parents6 || !prims || !childs || !nchild || n > (size_t)INT32_MAX)
+    if (!goal3 || !d_parents6 || !d_prims || !d_childs || !d_nchild || n > (size_t)INT32_MAX)
     {
-        set_error("mpros_expand_batch: NULL / invalid argument");
+        set_error(std::string(who) + ": NULL / invalid argument");
         return MPROS_ERR_INVALID;
     }
     MPROS_CUDA(cudaSetDevice(c->device));
@@ -594,6 +595,40 @@ extern "C" int mpros_expand_batch(mpros_ctx *c, const double *start3, const doub
                 a.start_idx = ~0ull; // the goal seed overwrites a shared cell
         }
     }
+    cudaStream_t st = c->stream;
+    MPROS_CUDA(cudaMemsetAsync(d_childs, 0, n * P * 10 * 8, st));
+    a.parents6 = d_parents6;
+    a.prims = d_prims;
+    a.childs = d_childs;
+    a.nchild = d_nchild;
+    // one warp per parent, 4 warps per CTA; grid = a multiple of the 148 SMs (16 resident CTAs each), grid-stride beyond
+    int blocks = (int)std::min<size_t>((n + 3) / 4, (size_t)148 * 16);
+    expand_batch_kernel<<<blocks, 128, 0, st>>>(c->view(), c->pv, a);
+    MPROS_LAUNCH_CHECK(c);
+    return MPROS_OK;
+}
+
+extern "C" int mpros_expand_batch_dev(mpros_ctx *c, const double *start3, const double *goal3, const double *d_parents6, size_t n,
+                                      double *d_prims, double *d_childs, int32_t *d_nchild)
+{
+    return expand_launch(c, "mpros_expand_batch_dev", start3, goal3, d_parents6, n, d_prims, d_childs, d_nchild);
+}
+
+extern "C" int mpros_expand_batch(mpros_ctx *c, const double *start3, const double *goal3, const double *parents6, size_t n,
+                                  double *prims, double *childs, int32_t *nchild)
+{
+    int rc = check_planner_ready(c, "mpros_expand_batch");
+    if (rc)
+        return rc;
+    if (n == 0)
+        return MPROS_OK;
+    if (!goal3 || !parents6 || !prims || !childs || !nchild || n > (size_t)INT32_MAX)
+    {
+        set_error("mpros_expand_batch: NULL / invalid argument");
+        return MPROS_ERR_INVALID;
+    }
+    MPROS_CUDA(cudaSetDevice(c->device));
+    const int P = 2 * c->pv.n_steer;
     size_t in_b = n * 6 * 8, pr_b = n * P * 7 * 8, ch_b = n * P * 10 * 8;
     rc = ensure_stage(c, in_b + pr_b + ch_b + n * 4 + 2048);
     if (rc)
@@ -605,14 +640,9 @@ extern "C" int mpros_expand_batch(mpros_ctx *c, const double *start3, const doub
     int32_t *d_nc = (int32_t *)((char *)d_ch + align_up(ch_b, 256));
     cudaStream_t st = c->stream;
     MPROS_CUDA(cudaMemcpyAsync(d_in, parents6, in_b, cudaMemcpyHostToDevice, st));
-    MPROS_CUDA(cudaMemsetAsync(d_ch, 0, ch_b, st));
-    a.parents6 = d_in;
-    a.prims = d_pr;
-    a.childs = d_ch;
-    a.nchild = d_nc;
-    int blocks = (int)std::min<size_t>((n + 3) / 4, (size_t)148 * 8);
-    expand_batch_kernel<<<blocks, 128, 0, st>>>(c->view(), c->pv, a);
-    MPROS_LAUNCH_CHECK(c);
+    rc = expand_launch(c, "mpros_expand_batch", start3, goal3, d_in, n, d_pr, d_ch, d_nc);
+    if (rc)
+        return rc;
     MPROS_CUDA(cudaMemcpyAsync(prims, d_pr, pr_b, cudaMemcpyDeviceToHost, st));
     MPROS_CUDA(cudaMemcpyAsync(childs, d_ch, ch_b, cudaMemcpyDeviceToHost, st));
     MPROS_CUDA(cudaMemcpyAsync(nchild, d_nc, n * 4, cudaMemcpyDeviceToHost, st));

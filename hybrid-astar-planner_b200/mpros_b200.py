@@ -149,6 +149,7 @@ def load_library(path=LIB_PATH):
     L.mpros_rs_shot_batch.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, i, vp, vp]
     L.mpros_rs_distance_batch.argtypes = [vp, d, vp, vp, sz, vp]
     L.mpros_expand_batch.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp]
+    L.mpros_expand_batch_dev.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp]
     L.mpros_plan_batch.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, i, vp]
     L.mpros_path_postprocess_batch.argtypes = [vp, vp, vp, sz, vp, sz, vp]
     L.mpros_plan_search_tree.argtypes = [vp, vp, vp, vp, vp, vp, sz, C.POINTER(sz)]

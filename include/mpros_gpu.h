@@ -227,6 +227,9 @@ MPROS_API int mpros_rs_distance_batch(mpros_ctx *ctx, double rho, const double *
  * children inserted into the open list, in insertion order; nchild: int32[n]. */
 MPROS_API int mpros_expand_batch(mpros_ctx *ctx, const double *start3, const double *goal3, const double *parents6, size_t n,
                                  double *prims, double *childs, int32_t *nchild);
+/* Same with the batch in device memory (start3/goal3 stay host pointers); asynchronous on the context's stream. */
+MPROS_API int mpros_expand_batch_dev(mpros_ctx *ctx, const double *start3, const double *goal3, const double *d_parents6, size_t n,
+                                     double *d_prims, double *d_childs, int32_t *d_nchild);
 
 /* ---- planner ------------------------------------------------------------------------------------------------ */
 /* Per-query result of mpros_plan_batch: what HybridAstar::Plan() returns and why. */

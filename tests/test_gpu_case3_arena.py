@@ -62,3 +62,36 @@ def test_case3_plan_search_parity(arena, start, goal, solved):
         assert np.allclose(g["paths"][0, : len(r["path"])], r["path"], rtol=0, atol=1e-8)
     else:
         assert g["status"][0] == 0 and g["iterations"][0] == 100001
+
+
+def test_case3_goal_map_full_resolution(gpu_ctx_factory):
+    """N4 on the 2000 x 2000 grid at ds = 1 (the largest window the cluster kernel takes: 1999 rows x 63 words, 189 KB of
+    shared memory per CTA) against the CPU restatement (bit-identical to the reference, tests/test_oracle_port.py); the
+    cooperative grid kernel must agree too."""
+    import os
+
+    from oracle import portapi
+
+    part = refapi.load_map("arena_standin")
+    occ = np.ascontiguousarray(np.repeat(np.repeat(part["occupancy"], 4, axis=0), 4, axis=1))
+    params = refapi.shipped_params(part["free_thresh"], part["occupied_thresh"], ds=1)
+    pm = portapi.PortMap(portapi.PortLib(), params)
+    pm.set_occupancy(occ, 0.04, [0.0, 0.0, 0.0])
+    ctx = gpu_ctx_factory()
+    ctx.map_config(params)
+    ctx.set_occupancy(occ, 0.04, [0.0, 0.0, 0.0])
+    try:
+        for gx, gy in [(40.0, 40.0), (5.0, 5.0), (70.0, 21.0), (79.5, 0.5)]:
+            pm.update_goal(gx, gy)
+            want = pm.layer("goal")
+            os.environ.pop("MPROS_GOAL_MODE", None)
+            ctx.update_goal(gx, gy)
+            a = ctx.layer("goal")
+            os.environ["MPROS_GOAL_MODE"] = "grid"
+            ctx.update_goal(gx, gy)
+            b = ctx.layer("goal")
+            assert np.array_equal(a, want), "cluster kernel, goal (%.1f, %.1f): %d mismatches" % (gx, gy, int((a != want).sum()))
+            assert np.array_equal(b, want), "grid kernel, goal (%.1f, %.1f)" % (gx, gy)
+    finally:
+        os.environ.pop("MPROS_GOAL_MODE", None)
+        pm.close()

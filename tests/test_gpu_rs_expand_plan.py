@@ -254,3 +254,36 @@ def test_cluster_mode_gives_identical_plans(reflib, gpu_ctx_factory, monkeypatch
         assert np.array_equal(a[key], b[key]), key
     rp.close()
     rm.close()
+
+
+def test_expand_batch_device_buffers_match_host_buffers(gpu_ctx_factory):
+    """mpros_expand_batch_dev (batch resident in device memory, asynchronous) == mpros_expand_batch."""
+    import torch
+
+    import bench
+    import synthetic
+
+    ctx = gpu_ctx_factory()
+    params = bench.shipped_params()
+    ctx.map_config(params)
+    ctx.set_occupancy(synthetic.synthetic_occupancy(size=2048, n_rect=70), synthetic.SYN_RES, [0.0, 0.0, 0.0])
+    ctx.planner_config(params)
+    rng = np.random.default_rng(5)
+    poses = np.stack([rng.uniform(0, 204.8, 6000), rng.uniform(0, 204.8, 6000), rng.uniform(-np.pi, np.pi, 6000)], axis=1)
+    poses = poses[ctx.collision_check(poses) == 0][:2000]
+    goal = poses[0].copy()
+    ctx.update_goal(goal[0], goal[1])
+    n, P = len(poses), ctx.n_primitives()
+    par = np.concatenate([poses, 0.35 * rng.integers(-1, 2, n)[:, None], rng.choice([-1.0, 1.0], n)[:, None], rng.uniform(0, 50, n)[:, None]], axis=1)
+    prims, childs, nchild = ctx.expand_batch(poses[1], goal, par)
+    par_d = torch.from_numpy(np.ascontiguousarray(par)).cuda()
+    pr_d = torch.zeros(n * P * 7, dtype=torch.float64, device="cuda")
+    ch_d = torch.full((n * P * 10,), 7.0, dtype=torch.float64, device="cuda")
+    nc_d = torch.zeros(n, dtype=torch.int32, device="cuda")
+    s3 = np.ascontiguousarray(poses[1])
+    ctx._check(ctx.L.mpros_expand_batch_dev(ctx.h, s3.ctypes.data, goal.ctypes.data, par_d.data_ptr(), n, pr_d.data_ptr(), ch_d.data_ptr(),
+                                            nc_d.data_ptr()))
+    ctx.synchronize()
+    assert np.array_equal(nc_d.cpu().numpy(), nchild) and nchild.sum() > n
+    assert np.array_equal(pr_d.cpu().numpy().reshape(n, P, 7), prims)
+    assert np.array_equal(ch_d.cpu().numpy().reshape(n, P, 10), childs)

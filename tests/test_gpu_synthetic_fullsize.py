@@ -172,3 +172,27 @@ def test_batches_in_flight_match_the_synchronous_call(syn):
     assert ctx.plan_lane_stream(1) and ctx.plan_lane_stream(0) == ctx.stream()
     with pytest.raises(Exception):
         ctx.plan_batch_wait(mpros_b200.PLAN_LANES)
+
+
+def test_goal_map_cluster_and_grid_kernels_agree(syn, port):
+    """N4 at 1024 x 1024: the cluster/DSMEM wavefront (default) and the cooperative grid kernel (MPROS_GOAL_MODE=grid) both
+    reproduce generateGoalMap bit for bit, for goals in the middle, in a corner (window clipped) and on an obstacle."""
+    ctx = syn[0]
+    static = ctx.layer("static")
+    occ_cells = np.argwhere(static != 0)
+    goals = [(409.6 + 3.3, 409.6 - 1.7), (1.3, 1.2), (817.9, 818.1), (12.0, 700.0),
+             ((occ_cells[len(occ_cells) // 2][1] + 0.5) * 0.8, (occ_cells[len(occ_cells) // 2][0] + 0.5) * 0.8)]
+    try:
+        for gx, gy in goals:
+            port.update_goal(gx, gy)
+            want = port.layer("goal")
+            os.environ.pop("MPROS_GOAL_MODE", None)
+            ctx.update_goal(gx, gy)
+            a = ctx.layer("goal")
+            os.environ["MPROS_GOAL_MODE"] = "grid"
+            ctx.update_goal(gx, gy)
+            b = ctx.layer("goal")
+            assert np.array_equal(a, want), "cluster kernel, goal (%.1f, %.1f): %d mismatches" % (gx, gy, int((a != want).sum()))
+            assert np.array_equal(b, want), "grid kernel, goal (%.1f, %.1f)" % (gx, gy)
+    finally:
+        os.environ.pop("MPROS_GOAL_MODE", None)
