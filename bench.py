@@ -559,7 +559,11 @@ def run_b200(args):
         hbuf = [host_bufs() for _ in range(LANES)]
         status_d, cost_d, stats_d = dbuf[0]["status"], dbuf[0]["cost"], dbuf[0]["stats"]
         status_h, cost_h = hbuf[0]["status"], hbuf[0]["cost"]
-        gather = [[torch.zeros(nq, dtype=torch.float64, device="cuda") for _ in range(world)] for _ in range(LANES)] if world > 1 else None
+        # result gather (world > 1): per-step cost buffers in a ring, so that a lane's next batch never waits for a gather
+        RING = 8
+        cost_ring = [torch.zeros(nq, dtype=torch.float64, device="cuda") for _ in range(RING)] if world > 1 else None
+        gather = [[torch.zeros(nq, dtype=torch.float64, device="cuda") for _ in range(world)] for _ in range(RING)] if world > 1 else None
+        gathered = [None] * RING
         lane_ext = {}
         counter = {"dev": 0, "host": 0}
 
@@ -569,16 +573,26 @@ def run_b200(args):
             return lane_ext[lane]
 
         def step_dev():
-            lane = counter["dev"] % LANES
+            k = counter["dev"]
+            lane = k % LANES
             counter["dev"] += 1
             b = dbuf[lane]
-            ctx.plan_batch_submit_dev(lane, s_d.data_ptr(), g_d.data_ptr(), nq, b["status"].data_ptr(), b["cost"].data_ptr(),
+            cost_k = b["cost"]
+            if world > 1:
+                j = k % RING
+                cost_k = cost_ring[j]
+                if gathered[j] is not None and ctx.plan_lane_stream(lane):
+                    lane_stream(lane).wait_event(gathered[j])  # the gather of step k - RING has read this buffer
+            ctx.plan_batch_submit_dev(lane, s_d.data_ptr(), g_d.data_ptr(), nq, b["status"].data_ptr(), cost_k.data_ptr(),
                                       b["len"].data_ptr(), b["paths"].data_ptr(), PATH_CAP, b["stats"].data_ptr())
             if world > 1:  # the path's only exchange step: result gather over NCCL/NVLink, ordered behind the lane's batch
                 cur = torch.cuda.current_stream()
                 cur.wait_stream(lane_stream(lane))
-                dist.all_gather(gather[lane], b["cost"])
-                lane_stream(lane).wait_stream(cur)  # the lane's next batch overwrites b["cost"]
+                dist.all_gather(gather[j], cost_k)
+                gathered[j] = torch.cuda.Event()
+                gathered[j].record(cur)
+                if lane == 0:
+                    b["cost"].copy_(cost_k, non_blocking=True)  # lane 0's buffers are the ones checked after the run
 
         def step_host():
             lane = counter["host"] % LANES

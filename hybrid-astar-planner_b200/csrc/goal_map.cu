@@ -110,15 +110,24 @@ __global__ void __launch_bounds__(256) goal_bfs_kernel(const uint32_t *__restric
 }
 
 // Cluster form of the same wavefront for windows that fit the shared memory of one thread-block cluster (every BASELINE
-// config: 1024^2 needs 48 KB per CTA, the 2000^2 Arena stand-in at ds = 1 189 KB). Only cells within 999 steps of the goal
+// config: 1024^2 needs 55 KB per CTA, the 2000^2 Arena stand-in at ds = 1 205 KB). Only cells within 999 steps of the goal
 // can ever hold a value < 1000, so the wavefront lives in the WINDOW rows [gi-999, gi+999] x words [(gj-999)>>5, (gj+999)>>5].
-// The window is cut into 8 row bands, one per CTA of the cluster; `blocked` and both frontier buffers of a band stay in
-// that CTA's shared memory for all levels, the row above / below a band is read from the neighbour CTA through
-// distributed shared memory, and ONE hardware cluster barrier per level replaces the grid-wide software barrier of the
-// cooperative kernel (~1 us instead of ~10 us per level; <= 999 levels). Distances go straight to global memory when a
-// cell is discovered. Termination: every CTA posts "found something" into a slot of every CTA before the barrier.
+//  * The window is cut into 8 row bands, one per CTA of the cluster; `blocked` and both frontier buffers of a band stay in
+//    that CTA's shared memory for all levels. Distances go straight to global memory when a cell is discovered.
+//  * Every band carries K halo rows above and below (copies of the neighbour CTAs' rows, read through distributed shared
+//    memory). Row e of level L+1 depends on rows e-1, e, e+1 of level L, so after an exchange the CTA can run K levels on
+//    its own: at sub-level j the halo is exact except its outer j rows, the band itself stays exact. The cluster meets
+//    only every K levels (two hardware cluster barriers + the halo copy); in between a __syncthreads() separates levels.
+//  * A lane moves 128 cells (uint4) of a row per step, over the bounding box of the L1 ball of the current level: the level
+//    time is the instruction stream of the 8 SMs, and the vector form runs a quarter of the instructions of a word per lane. (A variant with per-row
+//    masks of non-zero frontier words touched fewer words but ran more instructions per warp and level and was slower:
+//    3.75 ms against 2.45 ms for the plain form with one cluster barrier per level; the level time is the dependent
+//    instruction chain of one warp, not the number of words.)
+// Termination: at every exchange each CTA posts "found something since the last one" into a slot of every CTA.
 constexpr int kGoalCluster = 8;
 constexpr int kGoalThreads = 1024;
+constexpr int kGoalMaxHalo = 8;
+constexpr size_t kGoalMaxSmem = 220 * 1024;
 
 __global__ void fill_u16_kernel(uint16_t *__restrict__ p, size_t n, uint16_t v)
 {
@@ -131,119 +140,155 @@ __global__ void fill_u16_kernel(uint16_t *__restrict__ p, size_t n, uint16_t v)
         p[n - 1] = v;
 }
 
+// words per row in shared memory: a multiple of 4 so that a lane moves 128 cells (uint4) at a time
+__host__ __device__ inline int goal_row_stride(int nw) { return (nw + 3) & ~3; }
+
 __global__ void __cluster_dims__(kGoalCluster, 1, 1) __launch_bounds__(kGoalThreads, 1)
     goal_bfs_cluster_kernel(const uint32_t *__restrict__ occ, int H, int W, int pitch, int gi, int gj, uint16_t *__restrict__ dist, int r0,
-                            int rows, int w0, int nw, int band)
+                            int rows, int w0, int nw, int band, int K)
 {
-    extern __shared__ uint32_t gsm[];
+    extern __shared__ __align__(16) uint32_t gsm[];
     __shared__ int slots[2][kGoalCluster];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int tid = threadIdx.x;
     const int wpr = (W + 31) >> 5;
-    const int band_words = band * nw;
-    uint32_t *blocked = gsm, *fa = gsm + band_words, *fb = fa + band_words;
-    const int row_first = rank * band;                               // window row of local row 0
-    const int my_rows = max(0, min(band, rows - row_first));         // the last bands may be short or empty
-    const bool have_up = rank > 0 && my_rows > 0;                    // CTA rank-1 always holds `band` rows when this one has any
-    const bool have_down = rank + 1 < kGoalCluster && row_first + band < rows;
-    const uint32_t *up_a = have_up ? cluster.map_shared_rank(fa, rank - 1) + (size_t)(band - 1) * nw : nullptr;
-    const uint32_t *up_b = have_up ? cluster.map_shared_rank(fb, rank - 1) + (size_t)(band - 1) * nw : nullptr;
-    const uint32_t *dn_a = have_down ? cluster.map_shared_rank(fa, rank + 1) : nullptr;
-    const uint32_t *dn_b = have_down ? cluster.map_shared_rank(fb, rank + 1) : nullptr;
+    const int ext = band + 2 * K;       // rows held by this CTA: K halo + band + K halo
+    const int nws = goal_row_stride(nw); // row stride in words
+    const int G = nws >> 2;             // uint4 groups per row
+    const int ext_words = ext * nws;
+    uint32_t *blocked = gsm, *fa = gsm + ext_words, *fb = fa + ext_words;
+    const int row_first = rank * band;  // window row of the band's first row; ext row e <-> window row row_first - K + e
+    const int my_rows = max(0, min(band, rows - row_first));
 
-    for (int k = tid; k < band_words; k += kGoalThreads)
+    // prologue: rows outside the window, padding words and the bits beyond the last column are blocked for good, so the
+    // level loop needs no validity masks
+    const uint32_t last_valid = (W & 31) ? ((1u << (W & 31)) - 1u) : 0xffffffffu;
+    for (int idx = tid; idx < ext_words; idx += kGoalThreads)
     {
-        const int li = k / nw, w = k - li * nw;
-        blocked[k] = li < my_rows ? occ[(size_t)(r0 + row_first + li) * pitch + (w0 + w)] : 0xffffffffu;
-        fa[k] = 0;
-        fb[k] = 0;
+        const int e = idx / nws, w = idx - e * nws;
+        const int gr = row_first - K + e;
+        uint32_t b = 0xffffffffu;
+        if (gr >= 0 && gr < rows && w < nw)
+        {
+            b = occ[(size_t)(r0 + gr) * pitch + (w0 + w)];
+            if (w0 + w == wpr - 1)
+                b |= ~last_valid;
+        }
+        blocked[idx] = b;
+        fa[idx] = 0;
+        fb[idx] = 0;
     }
     if (tid < 2 * kGoalCluster)
         (&slots[0][0])[tid] = 0;
     __syncthreads();
     {
-        const int gl = gi - r0 - row_first; // goal row, local
-        if (tid == 0 && gl >= 0 && gl < my_rows)
+        const int ge = gi - r0 - row_first + K; // goal row in ext coordinates (it may lie in a halo)
+        if (tid == 0 && ge >= 0 && ge < ext)
         {
-            const int k = gl * nw + ((gj >> 5) - w0);
-            fa[k] = 1u << (gj & 31);
-            blocked[k] |= 1u << (gj & 31);
-            dist[(size_t)gi * W + gj] = 0; // goal cell is 0 even if occupied (nav_map.cpp:304)
+            const int gw = (gj >> 5) - w0;
+            fa[ge * nws + gw] = 1u << (gj & 31);
+            blocked[ge * nws + gw] |= 1u << (gj & 31);
+            if (ge >= K && ge < K + my_rows)
+                dist[(size_t)gi * W + gj] = 0; // goal cell is 0 even if occupied (nav_map.cpp:304)
         }
     }
     cluster.sync();
 
-    const uint32_t last_valid = (W & 31) ? ((1u << (W & 31)) - 1u) : 0xffffffffu;
-    int found = 0; // since the last termination test
+    uint32_t *const up_base = rank > 0 ? cluster.map_shared_rank(gsm, rank - 1) : nullptr;
+    uint32_t *const dn_base = rank + 1 < kGoalCluster ? cluster.map_shared_rank(gsm, rank + 1) : nullptr;
+    int found = 0; // in the band, since the last exchange
     for (int level = 1; level < kHugeInt; ++level)
     {
         const bool odd = level & 1; // odd levels read fa, write fb
         const uint32_t *fprev = odd ? fa : fb;
         uint32_t *fnext = odd ? fb : fa;
-        const uint32_t *up = odd ? up_a : up_b, *dn = odd ? dn_a : dn_b;
-        // the L1 ball of radius `level`, in window / local coordinates
-        const int lo = max(max(0, gi - level - r0), row_first) - row_first;
-        const int hi = min(min(rows - 1, gi + level - r0), row_first + my_rows - 1) - row_first;
-        const int wl = max(0, (max(0, gj - level) >> 5) - w0), wh = min(nw - 1, ((gj + level) >> 5) - w0);
-        const int nwa = wh - wl + 1;
-        const int total = (hi >= lo && nwa > 0) ? (hi - lo + 1) * nwa : 0;
-        for (int k = tid; k < total; k += kGoalThreads)
-        {
-            const int li = lo + k / nwa, w = wl + k % nwa;
-            const int idx = li * nw + w;
-            const uint32_t c = fprev[idx];
-            uint32_t nb = (c << 1) | (c >> 1);
-            if (w > 0)
-                nb |= fprev[idx - 1] >> 31;
-            if (w + 1 < nw)
-                nb |= fprev[idx + 1] << 31;
-            if (li > 0)
-                nb |= fprev[idx - nw];
-            else if (up)
-                nb |= up[w];
-            if (li + 1 < my_rows)
-                nb |= fprev[idx + nw];
-            else if (dn)
-                nb |= dn[w];
-            const uint32_t valid = (w0 + w == wpr - 1) ? last_valid : 0xffffffffu;
-            const uint32_t fresh = nb & ~blocked[idx] & valid;
-            fnext[idx] = fresh;
-            if (fresh)
+        // the L1 ball of radius `level`: rows in ext coordinates, uint4 groups in window coordinates. Every group inside it
+        // is rewritten at every level (the ball only grows), so the buffer written two levels ago holds nothing stale.
+        const int lo = max(0, gi - level - r0 - row_first + K), hi = min(ext - 1, gi + level - r0 - row_first + K);
+        const int gl = max(0, (max(0, gj - level) >> 5) - w0) >> 2, gh = min(nw - 1, ((gj + level) >> 5) - w0) >> 2;
+        // lanes per row: the power of two that covers the groups in range; the other lanes take further rows
+        const int ga = gh - gl + 1;
+        const int lpr_log = ga <= 1 ? 0 : 32 - __clz(ga - 1);
+        const int rows_per_pass = kGoalThreads >> lpr_log;
+        const int g = gl + (tid & ((1 << lpr_log) - 1));
+        if (g <= gh)
+            for (int e = lo + (tid >> lpr_log); e <= hi; e += rows_per_pass)
             {
-                blocked[idx] |= fresh;
-                found = 1;
-                uint16_t *drow = dist + (size_t)(r0 + row_first + li) * W + ((size_t)(w0 + w) << 5);
-                uint32_t b = fresh;
-                while (b)
+                const int idx = e * nws + 4 * g;
+                const uint4 c = *reinterpret_cast<const uint4 *>(fprev + idx);
+                uint4 u = make_uint4(0, 0, 0, 0), d = make_uint4(0, 0, 0, 0);
+                if (e > 0)
+                    u = *reinterpret_cast<const uint4 *>(fprev + idx - nws);
+                if (e + 1 < ext)
+                    d = *reinterpret_cast<const uint4 *>(fprev + idx + nws);
+                const uint32_t lw = g > 0 ? fprev[idx - 1] : 0u, rw = g + 1 < G ? fprev[idx + 4] : 0u;
+                const uint4 bl = *reinterpret_cast<const uint4 *>(blocked + idx);
+                uint4 fr;
+                fr.x = ((c.x << 1) | (c.x >> 1) | (lw >> 31) | (c.y << 31) | u.x | d.x) & ~bl.x;
+                fr.y = ((c.y << 1) | (c.y >> 1) | (c.x >> 31) | (c.z << 31) | u.y | d.y) & ~bl.y;
+                fr.z = ((c.z << 1) | (c.z >> 1) | (c.y >> 31) | (c.w << 31) | u.z | d.z) & ~bl.z;
+                fr.w = ((c.w << 1) | (c.w >> 1) | (c.z >> 31) | (rw << 31) | u.w | d.w) & ~bl.w;
+                *reinterpret_cast<uint4 *>(fnext + idx) = fr;
+                if (fr.x | fr.y | fr.z | fr.w)
                 {
-                    const int t = __ffs(b) - 1;
-                    b &= b - 1;
-                    drow[t] = (uint16_t)level;
+                    *reinterpret_cast<uint4 *>(blocked + idx) = make_uint4(bl.x | fr.x, bl.y | fr.y, bl.z | fr.z, bl.w | fr.w);
+                    if (e >= K && e < K + my_rows)
+                    {
+                        found = 1;
+                        uint16_t *drow = dist + (size_t)(r0 + row_first - K + e) * W + ((size_t)(w0 + 4 * g) << 5);
+                        const uint32_t fw[4] = {fr.x, fr.y, fr.z, fr.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                        {
+                            uint32_t b = fw[q];
+                            while (b)
+                            {
+                                const int t = __ffs(b) - 1;
+                                b &= b - 1;
+                                drow[32 * q + t] = (uint16_t)level;
+                            }
+                        }
+                    }
+                }
+            }
+        if (level % K != 0)
+        {
+            __syncthreads();
+            continue;
+        }
+        // ---- exchange: termination vote, then the K halo rows on each side from the neighbours' bands
+        const int par = (level / K) & 1;
+        const int any = __syncthreads_or(found);
+        found = 0;
+        if (tid < kGoalCluster)
+            *cluster.map_shared_rank(&slots[par][rank], tid) = any;
+        cluster.sync(); // every band is final for this level, the votes are visible
+        int tot = 0;
+#pragma unroll
+        for (int t = 0; t < kGoalCluster; ++t)
+            tot |= slots[par][t];
+        if (!tot)
+            break; // uniform across the cluster: no band found anything in the last K levels, the frontier is exhausted
+        {
+            const size_t f_off = (size_t)(fnext - gsm); // this level's output = next level's input
+            if (up_base) // my ext rows [0, K) <- rows [band, band + K) of rank - 1 (the last K rows of its band)
+                for (int idx = tid; idx < K * nws; idx += kGoalThreads)
+                {
+                    blocked[idx] = up_base[band * nws + idx];
+                    fnext[idx] = up_base[f_off + band * nws + idx];
+                }
+            if (dn_base) // my ext rows [K + band, K + band + K) <- rows [K, 2K) of rank + 1 (the first K rows of its band)
+            {
+                const int dst = (K + band) * nws;
+                for (int idx = tid; idx < K * nws; idx += kGoalThreads)
+                {
+                    blocked[dst + idx] = dn_base[K * nws + idx];
+                    fnext[dst + idx] = dn_base[f_off + K * nws + idx];
                 }
             }
         }
-        // termination is tested every 4th level only (an exhausted frontier produces nothing, the extra levels are empty):
-        // three of four levels cost one cluster barrier and nothing else
-        const bool check = (level & 3) == 0;
-        const int par = (level >> 2) & 1;
-        if (check)
-        {
-            const int any = __syncthreads_or(found);
-            found = 0;
-            if (tid < kGoalCluster)
-                *cluster.map_shared_rank(&slots[par][rank], tid) = any;
-        }
-        cluster.sync();
-        if (check)
-        {
-            int tot = 0;
-#pragma unroll
-            for (int t = 0; t < kGoalCluster; ++t)
-                tot |= slots[par][t];
-            if (!tot)
-                break; // uniform across the cluster: frontier exhausted
-        }
+        cluster.sync(); // halos copied before any band changes again
     }
     cluster.sync(); // nobody leaves while a neighbour may still read its shared memory
 }
@@ -268,21 +313,26 @@ int map_build_goal(Ctx *c)
         const int w0 = std::max(0, gj - (kHugeInt - 1)) >> 5, w1 = std::min(wpr - 1, (gj + (kHugeInt - 1)) >> 5);
         const int rows = r1 - r0 + 1, nw = w1 - w0 + 1;
         const int band = (rows + kGoalCluster - 1) / kGoalCluster;
-        const size_t smem = (size_t)3 * band * nw * sizeof(uint32_t);
+        // halo depth: as deep as the shared memory allows, never deeper than a band (a halo is a copy of the neighbour's band rows)
+        int halo = std::min(kGoalMaxHalo, band);
+        auto smem_for = [&](int k) { return (size_t)3 * (band + 2 * k) * goal_row_stride(nw) * sizeof(uint32_t); };
+        while (halo > 1 && smem_for(halo) > kGoalMaxSmem)
+            halo >>= 1;
+        const size_t smem = smem_for(halo);
         const char *mode = std::getenv("MPROS_GOAL_MODE"); // "grid": force the cooperative kernel (tests compare the two)
-        if (smem <= 200 * 1024 && !(mode && std::strcmp(mode, "grid") == 0))
+        if (smem <= kGoalMaxSmem && !(mode && std::strcmp(mode, "grid") == 0))
         {
             static bool attr_set[16] = {};
             if (!attr_set[c->device & 15])
             {
-                MPROS_CUDA(cudaFuncSetAttribute(goal_bfs_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                MPROS_CUDA(cudaFuncSetAttribute(goal_bfs_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGoalMaxSmem));
                 attr_set[c->device & 15] = true;
             }
             const size_t cells = (size_t)c->H * c->W;
             fill_u16_kernel<<<148 * 4, 256, 0, c->stream>>>(c->goal, cells, (uint16_t)kHugeInt);
             MPROS_LAUNCH_CHECK(c);
             goal_bfs_cluster_kernel<<<kGoalCluster, kGoalThreads, smem, c->stream>>>(c->ds_bits, c->H, c->W, c->pitch, gi, gj, c->goal, r0, rows,
-                                                                                 w0, nw, band);
+                                                                                 w0, nw, band, halo);
             MPROS_LAUNCH_CHECK(c);
             return MPROS_OK;
         }

@@ -3,6 +3,7 @@ import numpy as np
 import pytest
 
 from helpers import make_pair, random_poses
+from oracle import refapi
 
 pytestmark = pytest.mark.gpu
 
@@ -96,3 +97,28 @@ def test_collision_verdicts_bit_exact(reflib, gpu_ctx_factory, name, ds, goal):
     assert np.array_equal(want_paths, got_paths)
     rp.close()
     rm.close()
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (3, 70), (6, 40), (9, 33), (17, 100), (70, 3), (130, 257), (300, 2100)])
+def test_goal_map_small_and_odd_shapes(gpu_ctx_factory, shape):
+    """N4 on grids whose row bands are shorter than the halo depth of the cluster wavefront (or empty), with a ragged last
+    word, and on a grid wider than one 64-word mask (cooperative kernel); against the CPU restatement."""
+    from oracle import portapi
+
+    H, W = shape
+    rng = np.random.default_rng(H * 1000 + W)
+    occ = np.where(rng.random((H, W)) < 0.25, 100, 0).astype(np.int8)
+    params = refapi.shipped_params(0.2, 0.68, ds=1)
+    pm = portapi.PortMap(portapi.PortLib(), params)
+    pm.set_occupancy(occ, 0.1, [0.0, 0.0, 0.0])
+    ctx = gpu_ctx_factory()
+    ctx.map_config(params)
+    ctx.set_occupancy(occ, 0.1, [0.0, 0.0, 0.0])
+    for _ in range(4):
+        gi, gj = int(rng.integers(0, H)), int(rng.integers(0, W))
+        gx, gy = (gj + 0.5) * 0.1, (gi + 0.5) * 0.1
+        pm.update_goal(gx, gy)
+        ctx.update_goal(gx, gy)
+        a, b = pm.layer("goal"), ctx.layer("goal")
+        assert np.array_equal(a, b), "goal (%d, %d): %d mismatches" % (gi, gj, int((a != b).sum()))
+    pm.close()
