@@ -4,6 +4,9 @@
 // 32-byte sectors of the bit-packed layers, which are L2-resident (8 MiB per 8192^2 layer). The kernel is bound
 // by FP64 issue (two IEEE divisions per probe) and L2 sector throughput, not by HBM; the algorithmic HBM traffic
 // is the 24 B pose read + 1 B verdict write.
+#include <cstdlib>
+#include <cstring>
+
 #include "map_device.cuh"
 
 namespace mpros
@@ -19,6 +22,92 @@ __global__ void __launch_bounds__(256, MPROS_C1_MINB) collision_poses_kernel(con
     {
         double x = __ldg(xyyaw + 3 * k), y = __ldg(xyyaw + 3 * k + 1), yaw = __ldg(xyyaw + 3 * k + 2);
         verdicts[k] = footprint_in_collision4(m, p, x, y, yaw) ? 1 : 0;
+    }
+}
+
+// Two-phase form of the same batch (default). Most uniformly distributed poses are decided by the cell of the pose alone:
+//   * SURELY FREE: no cell any probe can fall into is occupied or outside the map (one bit of Ctx::unsafe_tw, built by
+//     map_build_unsafe from both collision layers and the footprint) -> false;
+//   * SURE HIT: the axis line's middle probe (k = n_check / 2, when n_check is even and the axis symmetric) is the pose
+//     itself up to ~1e-12 cells of rounding, so if the pose lies at least 2^-22 cells away from every cell edge and its
+//     cell is occupied in the inflated layer the reference's probe hits it too -> true.
+// Neither needs sin/cos or the probe walk. Phase 1 classifies kC1PosesPerThread poses per thread and compacts the
+// undecided ones into shared memory; phase 2 runs the exact footprint test (fixed-point walk with its own exact
+// fallback) on the dense list, so the warps of phase 2 are full although only ~30 % of the poses reach it.
+constexpr int kC1PosesPerThread = 4;
+__global__ void __launch_bounds__(256, MPROS_C1_MINB) collision_poses_2phase_kernel(const __grid_constant__ MapView m, const __grid_constant__ PlannerView p,
+                                                                                      const uint32_t *__restrict__ unsafe_tw, int center_probe,
+                                                                                      const double *__restrict__ xyyaw, size_t n,
+                                                                                      uint8_t *__restrict__ verdicts)
+{
+    constexpr int kChunk = 256 * kC1PosesPerThread;
+    __shared__ uint16_t list[kChunk];
+    __shared__ int count;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const double kTwo32 = 4294967296.0;
+    const double sc = m.inv_res0 * kTwo32;
+    const double jc = m.ocos * sc, js = m.osin * sc;
+    const double off = (double)kTwMargin * kTwo32;
+    const double span = m.fx_span - p.fx_extent;
+    const unsigned lim_j = (unsigned)(m.W0 + 2 * kTwMargin - 2 * p.fx_slack), lim_i = (unsigned)(m.H0 + 2 * kTwMargin - 2 * p.fx_slack);
+    const size_t n_chunks = (n + kChunk - 1) / kChunk;
+    for (size_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x)
+    {
+        const size_t base = chunk * kChunk;
+        if (tid == 0)
+            count = 0;
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kC1PosesPerThread; ++r)
+        {
+            const int kl = r * 256 + tid;
+            const size_t k = base + kl;
+            bool undecided = false;
+            if (k < n)
+            {
+                const double x = __ldg(xyyaw + 3 * k), y = __ldg(xyyaw + 3 * k + 1), yaw = __ldg(xyyaw + 3 * k + 2);
+                undecided = true;
+                // same preconditions as the fixed-point walk (pose within the error bound's range, finite) + a finite yaw
+                if (fabs(x) + fabs(y) < span && fabs(yaw) <= 1.7976931348623157e308)
+                {
+                    const double ax = x - m.ox, ay = y - m.oy;
+                    const long long qj = __double2ll_rd(ax * jc + ay * js + off), qi = __double2ll_rd(ay * jc - ax * js + off);
+                    const bool in = ((unsigned)((int)(qj >> 32) - p.fx_slack) < lim_j) & ((unsigned)((int)(qi >> 32) - p.fx_slack) < lim_i);
+                    if (in)
+                    {
+                        const uint32_t us = tw_probe(unsafe_tw, m.tw_pitch, qj, qi), hit = tw_probe(m.infl_tw, m.tw_pitch, qj, qi);
+                        if (!(us & 1u))
+                        {
+                            verdicts[k] = 0;
+                            undecided = false;
+                        }
+                        else if (center_probe && (hit & 1u) && tw_edge(0xffffffffu, qj, qi) >= 2 * kFxEps)
+                        {
+                            verdicts[k] = 1;
+                            undecided = false;
+                        }
+                    }
+                }
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, undecided);
+            if (mask)
+            {
+                int slot = 0;
+                if (lane == __ffs(mask) - 1)
+                    slot = atomicAdd(&count, __popc(mask));
+                slot = __shfl_sync(0xffffffffu, slot, __ffs(mask) - 1);
+                if (undecided)
+                    list[slot + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)kl;
+            }
+        }
+        __syncthreads();
+        const int cnt = count;
+        for (int t = tid; t < cnt; t += 256)
+        {
+            const size_t k = base + list[t];
+            verdicts[k] = footprint_in_collision4(m, p, __ldg(xyyaw + 3 * k), __ldg(xyyaw + 3 * k + 1), __ldg(xyyaw + 3 * k + 2)) ? 1 : 0;
+        }
+        __syncthreads();
     }
 }
 
@@ -69,7 +158,22 @@ static int launch_poses(Ctx *c, const double *d_xyyaw, size_t n, uint8_t *d_verd
     size_t cap = 148 * 32;
     if (blocks > cap)
         blocks = cap;
-    collision_poses_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(c->view(), c->pv, d_xyyaw, n, d_verdicts);
+    // MPROS_C1_MODE=walk: every pose through the probe walk (the single-phase kernel), for A/B measurements and tests
+    const char *mode = std::getenv("MPROS_C1_MODE");
+    if (mode && std::strcmp(mode, "walk") == 0)
+    {
+        collision_poses_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(c->view(), c->pv, d_xyyaw, n, d_verdicts);
+        MPROS_LAUNCH_CHECK(c);
+        return MPROS_OK;
+    }
+    int rc = map_build_unsafe(c);
+    if (rc)
+        return rc;
+    size_t chunks = (n + 256 * kC1PosesPerThread - 1) / (256 * kC1PosesPerThread);
+    if (chunks > cap)
+        chunks = cap;
+    collision_poses_2phase_kernel<<<(unsigned)chunks, 256, 0, c->stream>>>(c->view(), c->pv, c->unsafe_tw, c->unsafe_center_probe, d_xyyaw, n,
+                                                                         d_verdicts);
     MPROS_LAUNCH_CHECK(c);
     return MPROS_OK;
 }

@@ -100,7 +100,7 @@ extern "C" int mpros_ctx_destroy(mpros_ctx *c)
                 cudaFree(c->lane_stage[l]);
         }
     void *bufs[] = {c->raw_bits, c->infl_bits, c->ds_bits, c->goal, c->obs_dist, c->edge_dist, c->region,
-                    c->edge_bits, c->voronoi, c->scratch, c->stage, c->raw_tw, c->infl_tw};
+                    c->edge_bits, c->voronoi, c->scratch, c->stage, c->raw_tw, c->infl_tw, c->unsafe_tw};
     for (void *b : bufs)
         if (b)
             cudaFree(b);
@@ -192,6 +192,7 @@ extern "C" int mpros_planner_config(mpros_ctx *c, const mpros_planner_params *p)
         return MPROS_ERR_INVALID;
     }
     c->pp = *p;
+    c->unsafe_valid = false; // depends on the footprint
     PlannerView &v = c->pv;
     const double L = p->length, Wd = p->width, off = p->steer_offset;
     // footprint_m_ corners, clockwise (hybrid_a_star.cpp:193-196)

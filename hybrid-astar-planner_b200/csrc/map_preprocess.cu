@@ -654,6 +654,7 @@ static int map_finish(Ctx *c)
         build_tilewords_kernel<<<grid_for(tw_words), 256, 0, st>>>(c->infl_bits, c->H0, c->W0, c->pitch0, c->infl_tw, c->tw_pitch, tw_rows);
         MPROS_LAUNCH_CHECK(c);
     }
+    c->unsafe_valid = false; // derived from the two layers just rebuilt
     // the reference sets get_map_ at the very end but the sub-steps below only need the geometry
     c->get_map = true;
     c->band_open = false;
@@ -674,6 +675,123 @@ static int map_finish(Ctx *c)
     if (rc)
         return rc;
     MPROS_CUDA(cudaStreamSynchronize(st));
+    return MPROS_OK;
+}
+
+// ---- pre-classification layer of the batched footprint test (collision.cu) ---------------------------------------------
+// A pose is SURELY FREE when every cell any probe of footPrintInCollision4 can fall into is free and inside the map: the
+// axis probes lie within max|footprint_longi_| of the pose, the four corners within the half diagonal. unsafe(i, j) = 1 unless
+// all cells of the inflated layer within Chebyshev distance r_axis and all cells of the raw layer within r_corner of (i, j)
+// are free, and (i, j) is at least r_corner cells inside the map. Square (Chebyshev) neighbourhoods contain the discs, the
+// radii carry two extra cells for the truncation of the pose and of the probes: conservative, never wrong. Binary
+// dilation of the bit-packed layers: a row pass (funnel shifts) and a column pass.
+__global__ void __launch_bounds__(256) dilate_rows_kernel(const uint32_t *__restrict__ in, int H, int pitch, int R, uint32_t *__restrict__ out)
+{
+    const size_t total = (size_t)H * pitch;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x)
+    {
+        const int w = (int)(t % pitch);
+        const uint32_t *row = in + (t - w);
+        auto word = [&](int k) -> uint32_t { return (k >= 0 && k < pitch) ? row[k] : 0u; };
+        uint32_t acc = 0;
+        // shift by s cells toward higher columns: result word w = (in[w - q] << r) | (in[w - q - 1] >> (32 - r)), s = 32 q + r
+        const int Q = (R + 31) >> 5;
+        for (int q = -Q - 1; q <= Q; ++q)
+        {
+            const uint32_t hi = word(w - q), lo = word(w - q - 1);
+            if ((hi | lo) == 0)
+                continue;
+            const int s0 = max(-R, 32 * q), s1 = min(R, 32 * q + 31);
+            for (int sft = s0; sft <= s1; ++sft)
+                acc |= __funnelshift_l(lo, hi, sft - 32 * q); // (hi << r) | (lo >> (32 - r)), r in 0..31
+        }
+        out[t] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) unsafe_cols_kernel(const uint32_t *__restrict__ rows_axis, int r_axis, const uint32_t *__restrict__ rows_corner,
+                                                          int r_corner, int H, int W, int pitch, uint32_t *__restrict__ out)
+{
+    const size_t total = (size_t)H * pitch;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x)
+    {
+        const int i = (int)(t / pitch), w = (int)(t % pitch);
+        uint32_t acc = 0;
+        for (int d = max(0, i - r_axis); d <= min(H - 1, i + r_axis); ++d)
+            acc |= rows_axis[(size_t)d * pitch + w];
+        for (int d = max(0, i - r_corner); d <= min(H - 1, i + r_corner); ++d)
+            acc |= rows_corner[(size_t)d * pitch + w];
+        // at least r_corner cells inside the map on every side
+        uint32_t interior = 0;
+        if (i >= r_corner && i < H - r_corner)
+        {
+            const int j0 = w * 32;
+            const int a = max(r_corner - j0, 0), b = min(W - r_corner - j0, 32); // bits [a, b) are interior columns
+            if (b > a)
+                interior = (b - a >= 32) ? 0xffffffffu : (((1u << (b - a)) - 1u) << a);
+        }
+        const int nbits = W - w * 32; // padding bits and words of the bit-packed layers stay zero
+        const uint32_t valid = nbits >= 32 ? 0xffffffffu : (nbits > 0 ? ((1u << nbits) - 1u) : 0u);
+        out[t] = (acc | ~interior) & valid;
+    }
+}
+
+int map_build_unsafe(Ctx *c)
+{
+    if (c->unsafe_valid)
+        return MPROS_OK;
+    if (!c->get_map || !c->planner_configured)
+    {
+        set_error("map_build_unsafe: needs a map and a planner configuration");
+        return MPROS_ERR_INVALID;
+    }
+    const PlannerView &v = c->pv;
+    double reach_axis = std::fmax(std::fabs(v.longi_x0), std::fabs(v.longi_x1)), reach_corner = 0;
+    for (int k = 0; k < 4; ++k)
+        reach_corner = std::fmax(reach_corner, std::hypot(v.corner_x[k], v.corner_y[k]));
+    const double ra = std::ceil(reach_axis / c->res0) + 2, rc_ = std::ceil(reach_corner / c->res0) + 2;
+    cudaStream_t st = c->stream;
+    const size_t words0 = (size_t)c->H0 * c->pitch0;
+#if MPROS_TW_BLOCK16
+    const int tw_rows = ((c->H0 + 2 * kTwMargin + 15) / 16) * 8;
+#else
+    const int tw_rows = (c->H0 + 2 * kTwMargin + 3) / 4;
+#endif
+    const size_t tw_words = (size_t)c->tw_pitch * tw_rows;
+    if (tw_words > c->cap_unsafe_tw)
+    {
+        if (c->unsafe_tw)
+            MPROS_CUDA(cudaFree(c->unsafe_tw));
+        c->unsafe_tw = nullptr;
+        c->cap_unsafe_tw = 0;
+        MPROS_CUDA(cudaMalloc(&c->unsafe_tw, tw_words * 4));
+        c->cap_unsafe_tw = tw_words;
+    }
+    int rc = ensure_scratch(c, words0 * 4 * 3 + 1024);
+    if (rc)
+        return rc;
+    uint32_t *rows_axis = static_cast<uint32_t *>(c->scratch), *rows_corner = rows_axis + words0, *unsafe_bits = rows_corner + words0;
+    if (!(ra < 4096) || !(rc_ < 4096) || ra >= c->H0 || rc_ >= c->W0)
+    {
+        // degenerate footprint / tiny map: nothing is surely free
+        MPROS_CUDA(cudaMemsetAsync(c->unsafe_tw, 0xff, tw_words * 4, st));
+    }
+    else
+    {
+        const int r_axis = (int)ra, r_corner = (int)rc_;
+        dilate_rows_kernel<<<grid_for(words0), 256, 0, st>>>(c->infl_bits, c->H0, c->pitch0, r_axis, rows_axis);
+        MPROS_LAUNCH_CHECK(c);
+        dilate_rows_kernel<<<grid_for(words0), 256, 0, st>>>(c->raw_bits, c->H0, c->pitch0, r_corner, rows_corner);
+        MPROS_LAUNCH_CHECK(c);
+        unsafe_cols_kernel<<<grid_for(words0), 256, 0, st>>>(rows_axis, r_axis, rows_corner, r_corner, c->H0, c->W0, c->pitch0, unsafe_bits);
+        MPROS_LAUNCH_CHECK(c);
+        build_tilewords_kernel<<<grid_for(tw_words), 256, 0, st>>>(unsafe_bits, c->H0, c->W0, c->pitch0, c->unsafe_tw, c->tw_pitch, tw_rows);
+        MPROS_LAUNCH_CHECK(c);
+    }
+    // the axis line has a probe exactly at the pose when n_check is even and the axis is symmetric about it
+    // (footprint_longi_ = +-(L - W) / 2, hybrid_a_star.cpp:198-199, with center_to_rotate_center_longitudinal = 0)
+    c->unsafe_center_probe = (v.n_check % 2 == 0 && v.longi_x0 == -v.longi_x1 && std::isfinite(v.fx_extent)) ? 1 : 0;
+    c->unsafe_valid = true;
     return MPROS_OK;
 }
 

@@ -100,6 +100,12 @@ struct Ctx
     uint32_t *raw_tw = nullptr, *infl_tw = nullptr; // derived from raw_bits / infl_bits (build_tilewords_kernel)
     int tw_pitch = 0;
     size_t cap_tw = 0;
+    // "not surely free" layer of the batched footprint test (collision.cu), same tile-word layout; built on demand from the
+    // two collision layers and the planner's footprint (map_build_unsafe), invalidated when either changes
+    uint32_t *unsafe_tw = nullptr;
+    size_t cap_unsafe_tw = 0;
+    bool unsafe_valid = false;
+    int unsafe_center_probe = 0; // the axis line has a probe exactly at the pose (n_check even, symmetric axis)
     uint16_t *goal = nullptr, *obs_dist = nullptr, *edge_dist = nullptr;
     int32_t *region = nullptr;
     uint32_t *edge_bits = nullptr;
@@ -177,6 +183,7 @@ inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 // stage entry points implemented in the other translation units
 int map_build_voronoi(Ctx *c);          // N5-N9, voronoi.cu
 int map_build_goal(Ctx *c);             // N4, goal_map.cu
+int map_build_unsafe(Ctx *c);           // pre-classification layer of the batched footprint test, map_preprocess.cu
 
 } // namespace mpros
 

@@ -62,10 +62,21 @@ def test_collision_verdicts_bit_exact_4m_poses(syn, port):
     poses = bench.gen_poses(1 << 22, 7)
     k = len(poses) // 4
     poses[:k, :2] = np.round(poses[:k, :2] / 0.1) * 0.1
+    # cell centres, cell edges (where the two-phase kernel must hand over to the exact path) and non-finite poses
+    poses[k:k + 1000, :2] = (np.floor(poses[k:k + 1000, :2] / 0.1) + 0.5) * 0.1
+    poses[k + 1000:k + 1008, 2] = [np.nan, np.inf, -np.inf, 1e300, -1e300, 0.0, np.pi, -np.pi]
+    poses[k + 1008:k + 1012, 0] = [np.nan, np.inf, -1e300, 1e12]
     want = portapi.PortPlanner(port).collision4(poses)
     got = ctx.collision_check(poses)
     assert 0.2 < want.mean() < 0.4
     assert np.array_equal(want, got), "%d verdict mismatches of %d" % (int((want != got).sum()), len(poses))
+    # the single-phase kernel (every pose through the probe walk) gives the same verdicts
+    os.environ["MPROS_C1_MODE"] = "walk"
+    try:
+        walk = ctx.collision_check(poses)
+    finally:
+        os.environ.pop("MPROS_C1_MODE", None)
+    assert np.array_equal(want, walk)
 
 
 def test_sampled_plans_equal_restatement(syn, port):
