@@ -404,8 +404,9 @@ def run_b200(args):
     col_value = world * n * col_steps / (col_total_ms * 1e-3)
     col_e2e = world * n * col_steps / (col_e2e_ms * 1e-3)
     peak, peak_kind = measured_peak_gbs()
+    col_kernel = "collision_poses_kernel" if os.environ.get("MPROS_C1_MODE") == "walk" else "collision_poses_2phase_kernel"
     col_roof = {"bound": "hbm", "achieved": n * B_CHECK / (float(np.mean(col_ms)) * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "traffic": ncu_traffic("collision_poses_kernel"), "kernel": "collision_poses_kernel", "kernel_ms": float(np.mean(col_ms)), "peak_source": peak_kind,
+                "traffic": ncu_traffic(col_kernel), "kernel": col_kernel, "kernel_ms": float(np.mean(col_ms)), "peak_source": peak_kind,
                 "algorithmic_bytes_per_unit": B_CHECK}
     col_roof["frac"] = col_roof["achieved"] / peak
     del poses_d, verd_d

@@ -31,19 +31,22 @@ __global__ void __launch_bounds__(256, MPROS_C1_MINB) collision_poses_kernel(con
 //   * SURE HIT: the axis line's middle probe (k = n_check / 2, when n_check is even and the axis symmetric) is the pose
 //     itself up to ~1e-12 cells of rounding, so if the pose lies at least 2^-22 cells away from every cell edge and its
 //     cell is occupied in the inflated layer the reference's probe hits it too -> true.
-// Neither needs sin/cos or the probe walk. Phase 1 classifies kC1PosesPerThread poses per thread and compacts the
-// undecided ones into shared memory; phase 2 runs the exact footprint test (fixed-point walk with its own exact
-// fallback) on the dense list, so the warps of phase 2 are full although only ~30 % of the poses reach it.
-constexpr int kC1PosesPerThread = 4;
+// Neither needs sin/cos or the probe walk. Everything is warp-local (no block barrier, no atomics): a warp classifies
+// 32 x kC1PosesPerLane poses (all pose loads, then all probe loads in flight together), appends the undecided ones to its
+// own ring in shared memory, and runs the exact footprint test (fixed-point walk with its own exact fallback) on FULL
+// rounds of 32 entries; what is left (< 32) waits for the next chunk. Only ~30 % of uniform poses reach the walk and the
+// warps that run it are full.
+constexpr int kC1PosesPerLane = 4;
+constexpr int kC1Ring = 256; // entries per warp ring (power of two, > 31 + 32 * kC1PosesPerLane)
 __global__ void __launch_bounds__(256, MPROS_C1_MINB) collision_poses_2phase_kernel(const __grid_constant__ MapView m, const __grid_constant__ PlannerView p,
                                                                                       const uint32_t *__restrict__ unsafe_tw, int center_probe,
                                                                                       const double *__restrict__ xyyaw, size_t n,
                                                                                       uint8_t *__restrict__ verdicts)
 {
-    constexpr int kChunk = 256 * kC1PosesPerThread;
-    __shared__ uint16_t list[kChunk];
-    __shared__ int count;
-    const int tid = threadIdx.x, lane = tid & 31;
+    constexpr int kChunk = 32 * kC1PosesPerLane;
+    __shared__ uint32_t ring_all[8][kC1Ring];
+    const int lane = threadIdx.x & 31;
+    uint32_t *ring = ring_all[threadIdx.x >> 5];
     const double kTwo32 = 4294967296.0;
     const double sc = m.inv_res0 * kTwo32;
     const double jc = m.ocos * sc, js = m.osin * sc;
@@ -51,63 +54,73 @@ __global__ void __launch_bounds__(256, MPROS_C1_MINB) collision_poses_2phase_ker
     const double span = m.fx_span - p.fx_extent;
     const unsigned lim_j = (unsigned)(m.W0 + 2 * kTwMargin - 2 * p.fx_slack), lim_i = (unsigned)(m.H0 + 2 * kTwMargin - 2 * p.fx_slack);
     const size_t n_chunks = (n + kChunk - 1) / kChunk;
-    for (size_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x)
+    const size_t warp_global = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    unsigned head = 0, tail = 0; // warp-uniform ring positions
+    for (size_t chunk = warp_global; chunk < n_chunks; chunk += n_warps)
     {
         const size_t base = chunk * kChunk;
-        if (tid == 0)
-            count = 0;
-        __syncthreads();
+        double x[kC1PosesPerLane], y[kC1PosesPerLane], yaw[kC1PosesPerLane];
 #pragma unroll
-        for (int r = 0; r < kC1PosesPerThread; ++r)
+        for (int r = 0; r < kC1PosesPerLane; ++r)
         {
-            const int kl = r * 256 + tid;
-            const size_t k = base + kl;
-            bool undecided = false;
-            if (k < n)
+            const size_t k = base + r * 32 + lane;
+            const bool have = k < n;
+            x[r] = have ? __ldg(xyyaw + 3 * k) : 0.0;
+            y[r] = have ? __ldg(xyyaw + 3 * k + 1) : 0.0;
+            yaw[r] = have ? __ldg(xyyaw + 3 * k + 2) : 0.0;
+        }
+        uint32_t us[kC1PosesPerLane], hit[kC1PosesPerLane];
+        bool pre[kC1PosesPerLane], centred[kC1PosesPerLane];
+#pragma unroll
+        for (int r = 0; r < kC1PosesPerLane; ++r)
+        {
+            // same preconditions as the fixed-point walk (pose within the error bound's range, finite) + a finite yaw
+            pre[r] = fabs(x[r]) + fabs(y[r]) < span && fabs(yaw[r]) <= 1.7976931348623157e308;
+            const double ax = x[r] - m.ox, ay = y[r] - m.oy;
+            long long qj = __double2ll_rd(ax * jc + ay * js + off), qi = __double2ll_rd(ay * jc - ax * js + off);
+            pre[r] = pre[r] && (((unsigned)((int)(qj >> 32) - p.fx_slack) < lim_j) & ((unsigned)((int)(qi >> 32) - p.fx_slack) < lim_i));
+            if (!pre[r])
+                qj = qi = (long long)kTwMargin << 32; // any valid address; the result is not used
+            us[r] = tw_probe(unsafe_tw, m.tw_pitch, qj, qi);
+            hit[r] = tw_probe(m.infl_tw, m.tw_pitch, qj, qi);
+            centred[r] = tw_edge(0xffffffffu, qj, qi) >= 2 * kFxEps;
+        }
+#pragma unroll
+        for (int r = 0; r < kC1PosesPerLane; ++r)
+        {
+            const size_t k = base + r * 32 + lane;
+            bool undecided = k < n;
+            if (undecided && pre[r])
             {
-                const double x = __ldg(xyyaw + 3 * k), y = __ldg(xyyaw + 3 * k + 1), yaw = __ldg(xyyaw + 3 * k + 2);
-                undecided = true;
-                // same preconditions as the fixed-point walk (pose within the error bound's range, finite) + a finite yaw
-                if (fabs(x) + fabs(y) < span && fabs(yaw) <= 1.7976931348623157e308)
+                if (!(us[r] & 1u))
                 {
-                    const double ax = x - m.ox, ay = y - m.oy;
-                    const long long qj = __double2ll_rd(ax * jc + ay * js + off), qi = __double2ll_rd(ay * jc - ax * js + off);
-                    const bool in = ((unsigned)((int)(qj >> 32) - p.fx_slack) < lim_j) & ((unsigned)((int)(qi >> 32) - p.fx_slack) < lim_i);
-                    if (in)
-                    {
-                        const uint32_t us = tw_probe(unsafe_tw, m.tw_pitch, qj, qi), hit = tw_probe(m.infl_tw, m.tw_pitch, qj, qi);
-                        if (!(us & 1u))
-                        {
-                            verdicts[k] = 0;
-                            undecided = false;
-                        }
-                        else if (center_probe && (hit & 1u) && tw_edge(0xffffffffu, qj, qi) >= 2 * kFxEps)
-                        {
-                            verdicts[k] = 1;
-                            undecided = false;
-                        }
-                    }
+                    verdicts[k] = 0;
+                    undecided = false;
+                }
+                else if (center_probe && (hit[r] & 1u) && centred[r])
+                {
+                    verdicts[k] = 1;
+                    undecided = false;
                 }
             }
             const unsigned mask = __ballot_sync(0xffffffffu, undecided);
-            if (mask)
-            {
-                int slot = 0;
-                if (lane == __ffs(mask) - 1)
-                    slot = atomicAdd(&count, __popc(mask));
-                slot = __shfl_sync(0xffffffffu, slot, __ffs(mask) - 1);
-                if (undecided)
-                    list[slot + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)kl;
-            }
+            if (undecided)
+                ring[(tail + __popc(mask & ((1u << lane) - 1u))) & (kC1Ring - 1)] = (uint32_t)k;
+            tail += __popc(mask);
         }
-        __syncthreads();
-        const int cnt = count;
-        for (int t = tid; t < cnt; t += 256)
+        __syncwarp();
+        while (tail - head >= 32)
         {
-            const size_t k = base + list[t];
+            const size_t k = ring[(head + lane) & (kC1Ring - 1)];
             verdicts[k] = footprint_in_collision4(m, p, __ldg(xyyaw + 3 * k), __ldg(xyyaw + 3 * k + 1), __ldg(xyyaw + 3 * k + 2)) ? 1 : 0;
+            head += 32;
         }
-        __syncthreads();
+        __syncwarp();
+    }
+    if (lane < tail - head)
+    {
+        const size_t k = ring[(head + lane) & (kC1Ring - 1)];
+        verdicts[k] = footprint_in_collision4(m, p, __ldg(xyyaw + 3 * k), __ldg(xyyaw + 3 * k + 1), __ldg(xyyaw + 3 * k + 2)) ? 1 : 0;
     }
 }
 
@@ -169,9 +182,16 @@ static int launch_poses(Ctx *c, const double *d_xyyaw, size_t n, uint8_t *d_verd
     int rc = map_build_unsafe(c);
     if (rc)
         return rc;
-    size_t chunks = (n + 256 * kC1PosesPerThread - 1) / (256 * kC1PosesPerThread);
-    if (chunks > cap)
-        chunks = cap;
+    size_t chunks = (n + 256 * kC1PosesPerLane - 1) / (256 * kC1PosesPerLane); // CTAs of 8 warps, one warp chunk each at least
+    // persistent: one wave of resident CTAs, so that a warp sees many chunks and its last, partly filled round is rare
+    if (chunks > (size_t)148 * MPROS_C1_MINB)
+        chunks = (size_t)148 * MPROS_C1_MINB;
+    if (n >= (1ull << 32)) // ring entries are 32-bit pose indices
+    {
+        collision_poses_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(c->view(), c->pv, d_xyyaw, n, d_verdicts);
+        MPROS_LAUNCH_CHECK(c);
+        return MPROS_OK;
+    }
     collision_poses_2phase_kernel<<<(unsigned)chunks, 256, 0, c->stream>>>(c->view(), c->pv, c->unsafe_tw, c->unsafe_center_probe, d_xyyaw, n,
                                                                          d_verdicts);
     MPROS_LAUNCH_CHECK(c);
