@@ -683,7 +683,7 @@ static int map_finish(Ctx *c)
 // axis probes lie within max|footprint_longi_| of the pose, the four corners within the half diagonal. unsafe(i, j) = 1 unless
 // all cells of the inflated layer within Chebyshev distance r_axis and all cells of the raw layer within r_corner of (i, j)
 // are free, and (i, j) is at least r_corner cells inside the map. Square (Chebyshev) neighbourhoods contain the discs, the
-// radii carry two extra cells for the truncation of the pose and of the probes: conservative, never wrong. Binary
+// radii carry one extra cell for the truncation of the pose and of the probes: conservative, never wrong. Binary
 // dilation of the bit-packed layers: a row pass (funnel shifts) and a column pass.
 __global__ void __launch_bounds__(256) dilate_rows_kernel(const uint32_t *__restrict__ in, int H, int pitch, int R, uint32_t *__restrict__ out)
 {
@@ -749,7 +749,9 @@ int map_build_unsafe(Ctx *c)
     double reach_axis = std::fmax(std::fabs(v.longi_x0), std::fabs(v.longi_x1)), reach_corner = 0;
     for (int k = 0; k < 4; ++k)
         reach_corner = std::fmax(reach_corner, std::hypot(v.corner_x[k], v.corner_y[k]));
-    const double ra = std::ceil(reach_axis / c->res0) + 2, rc_ = std::ceil(reach_corner / c->res0) + 2;
+    // A probe at distance d cells from the pose lies at most floor(frac + d) <= floor(d) + 1 cells from the pose's cell in each
+    // axis (frac < 1 is the pose's offset inside its cell); 1e-6 cells cover every rounding on either side.
+    const double ra = std::floor(reach_axis / c->res0 + 1e-6) + 1, rc_ = std::floor(reach_corner / c->res0 + 1e-6) + 1;
     cudaStream_t st = c->stream;
     const size_t words0 = (size_t)c->H0 * c->pitch0;
 #if MPROS_TW_BLOCK16
