@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200-native mpros hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload plan|collision|expand|preprocess]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload plan|collision|expand|preprocess|rs]
 
 Workload "plan" (default; BASELINE.json configs[4]): synthetic 8192x8192 occupancy grid @0.1 m
 (seed 20261019: 1-m border wall + 1100 rectangles), inflation 1.0 m, down-sampling 8, shipped planner parameters
@@ -30,6 +30,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "hybrid-astar-planner_b200"))
 
+import ctypes
+
+C_DOUBLE = ctypes.c_double
 import synthetic  # noqa: E402  (workload generator: numpy only)
 
 SYN_SIZE, SYN_RES, SYN_DS = synthetic.SYN_SIZE, synthetic.SYN_RES, synthetic.SYN_DS
@@ -43,6 +46,7 @@ B_CHECK = 24 + 1 + (22 + 1 + 4)  # C1 @0.1 m: pose in + verdict out + (n+1+4) on
 B_EXPANSION = 450                # E1 with the case-1 survivor / insert ratios
 B_SHOT = 440                     # R4 without the trajectory
 EXPANSIONS_PER_STEP = 1 << 20
+RS_SHOTS_PER_STEP = 1 << 20
 B_GOAL_CELL = 5                  # N4: 1 B in, 4 B out per cell of the goal map
 
 
@@ -157,6 +161,25 @@ def _cpu_worker_collision(poses):
     return time.perf_counter() - t0, int(v.sum()), len(poses)
 
 
+def _cpu_worker_rs(job):
+    from oracle import refapi
+
+    st5, g3, cfg = job  # cfg: radius, steering angle, step, penalties as HybridAstar::config hands them to RSCurve
+    rp, lib = _W["rp"], _W["rp"].lib
+    t0 = time.perf_counter()
+    for s, g in zip(st5, g3):
+        seg, cost, traj = refapi.ref_rs_solve(lib, cfg, s, g)
+        if len(traj):
+            rp.collision4(traj[:, :3])
+    dt = time.perf_counter() - t0
+    z = np.zeros(3)
+    t0 = time.perf_counter()
+    for _ in range(2000):
+        lib.L.ref_rs_distance(C_DOUBLE(8.0), z.ctypes.data, z.ctypes.data)
+    overhead = (time.perf_counter() - t0) / 2000 * 2  # two library calls per shot
+    return dt, len(st5), overhead
+
+
 def _cpu_worker_pre(goal):
     t0 = time.perf_counter()
     _W["rm"].update_goal(goal[0], goal[1])
@@ -203,6 +226,10 @@ class CpuArm:
         n = sum(r[3] for r in res)
         return {"plans_per_sec": n / t, "expansions_per_sec": sum(r[2] for r in res) / 6.0 / t, "solved": sum(r[1] for r in res),
                 "n": n, "preprocess_s": max(r[4] for r in res)}
+
+    def rs_rate(self, st5, g3, cfg):
+        res = self.pool.map(_cpu_worker_rs, [(a, b, cfg) for a, b in zip(np.array_split(st5, self.cores), np.array_split(g3, self.cores))])
+        return sum(r[1] for r in res) / max(r[0] for r in res), max(r[2] for r in res)
 
     def preprocess_time(self, gx, gy):
         res = self.pool.map(_cpu_worker_pre, [(gx, gy)] * self.cores)
@@ -301,6 +328,10 @@ def _ref_queries(occ, params, n):
 def workload_text(w):
     if w == "collision":
         return "collision: synthetic 8192x8192 @0.1 m (seed 20261019), inflation 1.0 m, batched footPrintInCollision4 over seeded uniform poses"
+    if w == "rs":
+        return ("rs: synthetic 8192x8192 @0.1 m (seed 20261019), inflation 1.0 m, shipped planner config (rho 8 m, step 2 m); batched "
+                "HybridAstar::genRSPath shots: RSCurve::FindOptimalPath (48 candidate words) + GetTraj + pathInCollision of the sampled "
+                "path, over seeded collision-free start poses and goals within the 10 m analytic range")
     if w == "preprocess":
         return ("preprocess: synthetic 8192x8192 @0.1 m (seed 20261019), ds=8, inflation 1.0 m; NavMap::setOccupancyMap (threshold, inflation, "
                 "down-sampling, obstacle labelling, L1 distance maps, Voronoi field) + NavMap::updateGoal (holonomic goal map) per step")
@@ -421,6 +452,58 @@ def run_b200(args):
                     "gpu_launches": int(col_launches), "roofline": col_roof,
                     "config": {"workload": workload_text("collision"), "poses_per_step_per_gpu": n, "hit_rate": hit_rate,
                                "l2_policy": "inputs larger than L2 (403 MB of poses per step)", "preprocess_s_first_call": t_pre}}
+    elif args.workload == "rs":
+        # R1-R4: batched Reeds-Shepp word evaluation + sampled-path collision
+        ns = RS_SHOTS_PER_STEP
+        rng = np.random.default_rng(POSE_SEED + 99 + rank)
+        cand = gen_poses(3 * ns, POSE_SEED + 60 + 1000 * rank)
+        cand = cand[ctx.collision_check(cand) == 0][:ns]
+        assert len(cand) == ns
+        st5 = np.concatenate([cand, rng.choice([-1.0, 1.0], ns)[:, None],
+                              (params["/mpros/vehicle/max_steering_angle"] * rng.integers(-1, 2, ns))[:, None]], axis=1)
+        dd, aa = rng.uniform(0.5, 10.0, ns), rng.uniform(-np.pi, np.pi, ns)
+        g3 = np.stack([cand[:, 0] + dd * np.cos(aa), cand[:, 1] + dd * np.sin(aa), rng.uniform(-np.pi, np.pi, ns)], axis=1)
+        s_h, g_h = torch.from_numpy(np.ascontiguousarray(st5)).pin_memory(), torch.from_numpy(np.ascontiguousarray(g3)).pin_memory()
+        s_d, g_d = s_h.cuda(), g_h.cuda()
+        mk_d = lambda shape, dt: torch.zeros(shape, dtype=dt, device="cuda")
+        mk_h = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()
+        seg_d, nseg_d, cost_d, npts_d, ver_d = mk_d(ns * 15, torch.float64), mk_d(ns, torch.int32), mk_d(ns, torch.float64), mk_d(ns, torch.int32), mk_d(ns, torch.uint8)
+        seg_h, nseg_h, cost_h, npts_h, ver_h = mk_h(ns * 15, torch.float64), mk_h(ns, torch.int32), mk_h(ns, torch.float64), mk_h(ns, torch.int32), mk_h(ns, torch.uint8)
+
+        def step_dev():
+            ctx._check(ctx.L.mpros_rs_shot_batch_dev(ctx.h, s_d.data_ptr(), g_d.data_ptr(), ns, seg_d.data_ptr(), nseg_d.data_ptr(), cost_d.data_ptr(),
+                                                     npts_d.data_ptr(), ver_d.data_ptr()))
+
+        def step_host():
+            ctx._check(ctx.L.mpros_rs_shot_batch(ctx.h, s_h.data_ptr(), g_h.data_ptr(), ns, seg_h.data_ptr(), nseg_h.data_ptr(), cost_h.data_ptr(),
+                                                 None, 0, npts_h.data_ptr(), ver_h.data_ptr()))
+
+        total_ms, step_ms, launches = timed_device(step_dev)
+        e2e_ms = timed_host(step_host)
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+        assert torch.equal(ver_h, ver_d.cpu()) and torch.equal(cost_h, cost_d.cpu()), "host-API and device-API shots differ"
+        total_ms, e2e_ms = max_over_ranks([total_ms, e2e_ms])
+        if rank == 0:
+            k_ms = float(np.mean(step_ms))
+            mean_pts = float(npts_h.float().mean())
+            n_probe = B_CHECK - 25
+            algo_unit = 64 + 16 + mean_pts * (n_probe + 5 - 4)  # 64 B in + 16 B out + n_pts x (n + 5) B probes (n = 22)
+            achieved = ns * algo_unit / (k_ms * 1e-3) / 1e9
+            line = {"metric": "rs_shots_per_sec", "value": world * ns * args.steps / (total_ms * 1e-3), "unit": "shots/s",
+                    "ms_per_step": total_ms / args.steps,
+                    "e2e": {"value": world * ns * args.steps / (e2e_ms * 1e-3), "unit": "shots/s", "h2d_bytes_per_step": ns * 64,
+                            "d2h_bytes_per_step": ns * (120 + 4 + 8 + 4 + 1)},
+                    "gpu_launches": int(launches),
+                    "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                                 "traffic": ncu_traffic("rs_batch_kernel"), "kernel": "rs_batch_kernel", "kernel_ms": k_ms, "peak_source": peak_kind,
+                                 "algorithmic_bytes_per_unit": algo_unit,
+                                 "note": "FP64-issue bound (48 Reeds-Shepp candidate words with sin/cos/atan2/acos per shot, sequential trajectory integration), not HBM bound"},
+                    "extra": {"mean_trajectory_poses": mean_pts, "shots_in_collision": float(ver_h.float().mean()),
+                              "trajectory_poses_checked_per_sec": world * ns * mean_pts * args.steps / (total_ms * 1e-3),
+                              "collision_kernel_checks_per_sec": col_value},
+                    "config": {"workload": workload_text("rs"), "shots_per_step_per_gpu": ns,
+                               "l2_policy": "inputs + outputs 207 MB per step (larger than L2)", "preprocess_s_first_call": t_pre}}
     elif args.workload == "preprocess":
         # N1-N9 + N4: every map layer from the int8 occupancy grid, then the goal map of one goal
         H0, W0 = occ.shape
@@ -677,6 +760,12 @@ def run_b200(args):
                         v = arm.collision_rate(1 << 22, POSE_SEED + 6)
                         cpu = {"value": v, "unit": "checks/s", "cores": 1, "kind": "reference",
                                "sample": "4194304 seeded uniform poses on the synthetic 8192^2 map, 1 process x 1 thread, unmodified reference footPrintInCollision4 loop (preprocessing excluded)"}
+                    elif args.workload == "rs":
+                        rc = ctx.rs_default_config()
+                        v = arm.rs_rate(st5[:20000], g3[:20000], [rc.radius, rc.steering_angle, rc.step_size, rc.pen_gear, rc.pen_backward,
+                                                                    rc.pen_steer_change, rc.pen_steer_angle])
+                        cpu = {"value": v[0], "unit": "shots/s", "cores": 1, "kind": "reference",
+                               "sample": "the first 20000 shots of the step, 1 process x 1 thread, unmodified reference RSCurve::SetStart/SetEnd/FindOptimalPath/GetTraj + pathInCollision of the trajectory, one ctypes call per shot (call overhead measured on an empty call: %.1f us of %.1f us per shot)" % (v[1] * 1e6, 1e6 / v[0])}
                     elif args.workload == "preprocess":
                         r = arm.preprocess_time(EXTENT * 0.5 + 3.3, EXTENT * 0.5 - 1.7)
                         cpu = {"value": occ.size / (r[0] + r[1]), "unit": "cells/s", "cores": 1, "kind": "reference",
@@ -712,7 +801,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="plan", choices=["plan", "collision", "expand", "preprocess"])
+    ap.add_argument("--workload", default="plan", choices=["plan", "collision", "expand", "preprocess", "rs"])
     ap.add_argument("--lanes", type=int, default=3, help="plan workload: query batches in flight (1 = one batch at a time)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -147,6 +147,7 @@ def load_library(path=LIB_PATH):
     L.mpros_rs_default_config.argtypes = [vp, C.POINTER(RsParams)]
     L.mpros_rs_solve_batch.argtypes = [vp, C.POINTER(RsParams), vp, vp, sz, vp, vp, vp, vp, i, vp]
     L.mpros_rs_shot_batch.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, i, vp, vp]
+    L.mpros_rs_shot_batch_dev.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, vp]
     L.mpros_rs_distance_batch.argtypes = [vp, d, vp, vp, sz, vp]
     L.mpros_expand_batch.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp]
     L.mpros_expand_batch_dev.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp]

@@ -215,6 +215,9 @@ MPROS_API int mpros_rs_solve_batch(mpros_ctx *ctx, const mpros_rs_params *rs, co
  * verdicts: uint8[n], 1 = pathInCollision(rs_path). */
 MPROS_API int mpros_rs_shot_batch(mpros_ctx *ctx, const double *starts5, const double *goals3, size_t n, double *segs,
                                   int32_t *nseg, double *cost, double *traj, int traj_cap, int32_t *npts, uint8_t *verdicts);
+/* The same shot with every buffer in device memory (no trajectory output); asynchronous on the context's stream. */
+MPROS_API int mpros_rs_shot_batch_dev(mpros_ctx *ctx, const double *d_starts5, const double *d_goals3, size_t n, double *d_segs,
+                                      int32_t *d_nseg, double *d_cost, int32_t *d_npts, uint8_t *d_verdicts);
 /* RSStateSpace(rho).setStart/setEnd/getCost (rs_statespace.h:37-54): OMPL-equivalent Reeds-Shepp distance. */
 MPROS_API int mpros_rs_distance_batch(mpros_ctx *ctx, double rho, const double *a3, const double *b3, size_t n, double *out);
 

@@ -287,3 +287,37 @@ def test_expand_batch_device_buffers_match_host_buffers(gpu_ctx_factory):
     assert np.array_equal(nc_d.cpu().numpy(), nchild) and nchild.sum() > n
     assert np.array_equal(pr_d.cpu().numpy().reshape(n, P, 7), prims)
     assert np.array_equal(ch_d.cpu().numpy().reshape(n, P, 10), childs)
+
+
+def test_rs_shot_batch_device_buffers_match_host_buffers(gpu_ctx_factory):
+    """mpros_rs_shot_batch_dev (device buffers, asynchronous, no trajectory) == mpros_rs_shot_batch."""
+    import torch
+
+    import bench
+    import synthetic
+
+    ctx = gpu_ctx_factory()
+    params = bench.shipped_params()
+    ctx.map_config(params)
+    ctx.set_occupancy(synthetic.synthetic_occupancy(size=2048, n_rect=70), synthetic.SYN_RES, [0.0, 0.0, 0.0])
+    ctx.planner_config(params)
+    rng = np.random.default_rng(9)
+    poses = np.stack([rng.uniform(0, 204.8, 9000), rng.uniform(0, 204.8, 9000), rng.uniform(-np.pi, np.pi, 9000)], axis=1)
+    poses = poses[ctx.collision_check(poses) == 0][:3000]
+    n = len(poses)
+    s5 = np.concatenate([poses, rng.choice([-1.0, 1.0], n)[:, None], 0.35 * rng.integers(-1, 2, n)[:, None]], axis=1)
+    d, a = rng.uniform(0.5, 10, n), rng.uniform(-np.pi, np.pi, n)
+    g3 = np.stack([poses[:, 0] + d * np.cos(a), poses[:, 1] + d * np.sin(a), rng.uniform(-np.pi, np.pi, n)], axis=1)
+    want = ctx.rs_solve_batch(s5, g3, traj_cap=0, shot=True)
+    s_d, g_d = torch.from_numpy(np.ascontiguousarray(s5)).cuda(), torch.from_numpy(np.ascontiguousarray(g3)).cuda()
+    seg = torch.zeros(n * 15, dtype=torch.float64, device="cuda")
+    nseg = torch.zeros(n, dtype=torch.int32, device="cuda")
+    cost = torch.zeros(n, dtype=torch.float64, device="cuda")
+    npts = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ver = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    ctx._check(ctx.L.mpros_rs_shot_batch_dev(ctx.h, s_d.data_ptr(), g_d.data_ptr(), n, seg.data_ptr(), nseg.data_ptr(), cost.data_ptr(),
+                                             npts.data_ptr(), ver.data_ptr()))
+    ctx.synchronize()
+    assert np.array_equal(ver.cpu().numpy(), want["verdicts"]) and 0.05 < want["verdicts"].mean() < 0.95
+    assert np.array_equal(cost.cpu().numpy(), want["cost"]) and np.array_equal(npts.cpu().numpy(), want["npts"])
+    assert np.array_equal(nseg.cpu().numpy(), want["nseg"])
