@@ -166,6 +166,31 @@ __device__ __forceinline__ bool footprint_in_collision4_sc(const MapView &m, con
     return (any & 1u) != 0;
 }
 
+// Pre-classification of a pose by its own cell (collision.cu explains the two rules; Ctx::unsafe_tw is built by
+// map_build_unsafe): 0 = surely free, 1 = sure hit, 2 = undecided (run the footprint test). yaw is only tested for
+// finiteness. unsafe_tw == nullptr classifies nothing.
+__device__ __forceinline__ int footprint_preclass(const MapView &m, const PlannerView &p, const uint32_t *__restrict__ unsafe_tw, int center_probe,
+                                                  double px, double py, double yaw)
+{
+    if (!unsafe_tw || !(fabs(px) + fabs(py) < m.fx_span - p.fx_extent) || !(fabs(yaw) <= 1.7976931348623157e308))
+        return 2;
+    const double kTwo32 = 4294967296.0;
+    const double sc = m.inv_res0 * kTwo32;
+    const double jc = m.ocos * sc, js = m.osin * sc;
+    const double off = (double)kTwMargin * kTwo32;
+    const double ax = px - m.ox, ay = py - m.oy;
+    const long long qj = __double2ll_rd(ax * jc + ay * js + off), qi = __double2ll_rd(ay * jc - ax * js + off);
+    const unsigned lim_j = (unsigned)(m.W0 + 2 * kTwMargin - 2 * p.fx_slack), lim_i = (unsigned)(m.H0 + 2 * kTwMargin - 2 * p.fx_slack);
+    if (!(((unsigned)((int)(qj >> 32) - p.fx_slack) < lim_j) & ((unsigned)((int)(qi >> 32) - p.fx_slack) < lim_i)))
+        return 2;
+    const uint32_t us = tw_probe(unsafe_tw, m.tw_pitch, qj, qi), hit = tw_probe(m.infl_tw, m.tw_pitch, qj, qi);
+    if (!(us & 1u))
+        return 0;
+    if (center_probe && (hit & 1u) && tw_edge(0xffffffffu, qj, qi) >= 2 * kFxEps)
+        return 1;
+    return 2;
+}
+
 __device__ __forceinline__ bool footprint_in_collision4(const MapView &m, const PlannerView &p, double px, double py,
                                                         double yaw)
 {

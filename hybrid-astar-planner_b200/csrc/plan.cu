@@ -257,6 +257,8 @@ struct ExpandArgs
     unsigned long long start_idx, goal_idx;
     double start_g;
     int have_seeds;
+    const uint32_t *unsafe_tw; // pre-classification layer of the footprint test (may be NULL)
+    int center_probe;
 };
 
 #ifndef MPROS_EXPAND_MINB
@@ -280,9 +282,15 @@ __global__ void __launch_bounds__(128, MPROS_EXPAND_MINB) expand_batch_kernel(co
             primitive_end_pose(p, lane, cx, cy, cyaw, s_yaw, c_yaw, nx, ny, nyaw, steer, direc);
             dm::sincos_(nyaw, &ns, &nc);
         }
-        unsigned free_mask = 0;
-        for (int c = 0; c < P; ++c)
+        // most end poses are decided by their own cell (surely free / sure hit, map_device.cuh: footprint_preclass), one lane
+        // per child; only the undecided ones get the warp-wide probe walk
+        const int cls = lane < P ? footprint_preclass(m, p, a.unsafe_tw, a.center_probe, nx, ny, nyaw) : 0;
+        unsigned free_mask = __ballot_sync(kFull, lane < P && cls == 0);
+        unsigned walk_mask = __ballot_sync(kFull, lane < P && cls == 2);
+        while (walk_mask)
         {
+            const int c = __ffs(walk_mask) - 1;
+            walk_mask &= walk_mask - 1;
             double tx = __shfl_sync(kFull, nx, c), ty = __shfl_sync(kFull, ny, c);
             double ts = __shfl_sync(kFull, ns, c), tc = __shfl_sync(kFull, nc, c);
             if (!warp_footprint_collision(m, p, tx, ty, ts, tc))
@@ -650,6 +658,11 @@ static int expand_launch(mpros_ctx *c, const char *who, const double *start3, co
         }
     }
     cudaStream_t st = c->stream;
+    rc = map_build_unsafe(c);
+    if (rc)
+        return rc;
+    a.unsafe_tw = c->unsafe_tw;
+    a.center_probe = c->unsafe_center_probe;
     MPROS_CUDA(cudaMemsetAsync(d_childs, 0, n * P * 10 * 8, st));
     a.parents6 = d_parents6;
     a.prims = d_prims;
