@@ -771,8 +771,8 @@ def run_b200(args):
                         cpu = {"value": occ.size / (r[0] + r[1]), "unit": "cells/s", "cores": 1, "kind": "reference",
                                "sample": "one pass: unmodified reference NavMap::setOccupancyMap (%.2f s) + updateGoal (%.2f s) on the same 8192^2 map, 1 process x 1 thread" % r}
                     elif args.workload == "expand":
-                        qs, qg = gen_queries(ctx, 8, synthetic.SYN_QUERY_SEED)
-                        r = arm.plan_rate(qs, qg)
+                        qs, qg = gen_queries(ctx, QUERIES_PER_GPU, synthetic.SYN_QUERY_SEED)  # the plan workload's first 8 queries
+                        r = arm.plan_rate(qs[:8], qg[:8])
                         cpu = {"value": r["expansions_per_sec"], "unit": "expansions/s", "cores": 1, "kind": "reference",
                                "sample": "expandNode calls inside the unmodified reference's Plan() on 8 seeded queries of the plan workload, 1 process x 1 thread (primitives evaluated / 6 / time of updateGoal + ctor + Plan())"}
                     else:

@@ -164,6 +164,8 @@ struct RsBatchArgs
     int traj_cap;
     char *ws;          // per-warp scratch: kTrajCap x 5 doubles
     RsConfig rs;
+    const uint32_t *unsafe_tw = nullptr; // pre-classification layer of the footprint test (may be NULL)
+    int center_probe = 0;
 };
 
 #ifndef MPROS_RS_MINB
@@ -182,11 +184,7 @@ __global__ void __launch_bounds__(128, MPROS_RS_MINB) rs_batch_kernel(const __gr
         double cost = rs_find_optimal_warp(a.rs, s5[0], s5[1], s5[2], (int)s5[3], s5[4], g3[0], g3[1], g3[2], best);
         double *txyz = scratch, *tsd = scratch + 3 * kTrajCap;
         int cap = kTrajCap;
-        int np = 0;
-        if (lane == 0)
-            np = rs_gen_traj(a.rs, s5[0], s5[1], s5[2], best, txyz, tsd, cap);
-        np = __shfl_sync(kFull, np, 0);
-        __syncwarp();
+        const int np = rs_gen_traj_warp(a.rs, s5[0], s5[1], s5[2], best, txyz, tsd, cap);
         int stored = min(np, cap);
         if (a.traj)
         {
@@ -200,11 +198,31 @@ __global__ void __launch_bounds__(128, MPROS_RS_MINB) rs_batch_kernel(const __gr
         if (a.verdicts)
         {
             bool hit = np > cap; // longer than the scratch: report blocked rather than judge a truncated path
-            for (int k = 0; k < stored && !hit; ++k)
+            // pathInCollision is an OR over the poses: one lane per pose decides it by the pose's own cell where that is
+            // possible (map_device.cuh: footprint_preclass), the undecided poses get their sin/cos in parallel and the
+            // warp-wide probe walk one after the other
+            for (int k0 = 0; k0 < stored && !hit; k0 += 32)
             {
-                double s, c;
-                dm::sincos_(txyz[3 * k + 2], &s, &c);
-                hit = warp_footprint_collision(m, p, txyz[3 * k], txyz[3 * k + 1], s, c);
+                const int k = k0 + lane;
+                int cls = 0;
+                if (k < stored)
+                    cls = footprint_preclass(m, p, a.unsafe_tw, a.center_probe, txyz[3 * k], txyz[3 * k + 1], txyz[3 * k + 2]);
+                if (__any_sync(kFull, cls == 1))
+                {
+                    hit = true;
+                    break;
+                }
+                unsigned walk = __ballot_sync(kFull, cls == 2);
+                double s = 0, c = 1;
+                if (cls == 2)
+                    dm::sincos_(txyz[3 * k + 2], &s, &c);
+                while (walk && !hit)
+                {
+                    const int j = __ffs(walk) - 1;
+                    walk &= walk - 1;
+                    const double ts = __shfl_sync(kFull, s, j), tc = __shfl_sync(kFull, c, j);
+                    hit = warp_footprint_collision(m, p, txyz[3 * (k0 + j)], txyz[3 * (k0 + j) + 1], ts, tc);
+                }
             }
             if (lane == 0)
                 a.verdicts[q] = hit ? 1 : 0;
@@ -506,6 +524,14 @@ static int rs_batch_impl(mpros_ctx *c, const mpros_rs_params *rp, const double *
     a.verdicts = with_collision ? d_ver : nullptr;
     a.traj_cap = traj_cap;
     a.ws = d_ws;
+    if (with_collision)
+    {
+        rc = map_build_unsafe(c);
+        if (rc)
+            return rc;
+        a.unsafe_tw = c->unsafe_tw;
+        a.center_probe = c->unsafe_center_probe;
+    }
     rs_batch_kernel<<<blocks, block, 0, st>>>(c->view(), c->pv, a);
     MPROS_LAUNCH_CHECK(c);
     MPROS_CUDA(cudaMemcpyAsync(segs, d_seg, seg_bytes, cudaMemcpyDeviceToHost, st));
@@ -558,6 +584,9 @@ extern "C" int mpros_rs_shot_batch_dev(mpros_ctx *c, const double *d_starts5, co
     const int block = 128, warps_per_block = block / 32;
     int blocks = (int)std::min<size_t>((n + warps_per_block - 1) / warps_per_block, (size_t)148 * 8);
     const size_t ws_bytes = (size_t)blocks * warps_per_block * kTrajCap * 5 * 8;
+    rc = map_build_unsafe(c); // before the scratch is handed out: the builder uses it for its temporaries
+    if (rc)
+        return rc;
     rc = ensure_scratch(c, ws_bytes + 256);
     if (rc)
         return rc;
@@ -571,6 +600,8 @@ extern "C" int mpros_rs_shot_batch_dev(mpros_ctx *c, const double *d_starts5, co
     a.npts = d_npts;
     a.verdicts = d_verdicts;
     a.traj_cap = 0;
+    a.unsafe_tw = c->unsafe_tw;
+    a.center_probe = c->unsafe_center_probe;
     a.ws = static_cast<char *>(c->scratch);
     rs_batch_kernel<<<blocks, block, 0, c->stream>>>(c->view(), c->pv, a);
     MPROS_LAUNCH_CHECK(c);

@@ -411,6 +411,110 @@ __device__ __noinline__ int rs_gen_traj(const RsConfig &c, double sx, double sy,
     return n;
 }
 
+// RSCurve::GenTraj by a whole warp, the same operations in the same order as rs_gen_traj (all lanes hold the same path and
+// start pose; all 32 lanes must call it). GenTraj carries three chains from pose to pose: the yaw (one add + wrap per pose:
+// cheap, run by every lane redundantly), sin/cos of the yaw a pose starts from (expensive, independent once the yaws are
+// known: ONE lane per pose) and the position (x += increment: sequential floating-point adds, replayed in order over
+// warp shuffles). Paths with more than 32 poses (rare inside the 10 m analytic range) take the one-lane routine.
+__device__ __noinline__ int rs_gen_traj_warp(const RsConfig &c, double sx, double sy, double syaw, const RsPath &path, double *out_xyz,
+                                             double *out_sd, int cap)
+{
+    const int lane = threadIdx.x & 31;
+    const double curve_min_num = 3;
+    // per segment: number of poses, and the constants of its pose step (lane k < path.n evaluates segment k)
+    int my_num = 0;
+    double my_a = 0, my_b = 0, my_dyaw = 0; // arc: dx, dy, yaw step; straight: step * direc, unused, 0
+    if (lane < path.n)
+    {
+        const RsSeg seg = path.s[lane];
+        my_num = (int)fmax(ceil(seg.len * c.radius / c.step), curve_min_num);
+        const double direc = (double)seg.dir;
+        if (seg.steer != 0)
+        {
+            const double dyaw = seg.len / my_num;
+            double sd, cd;
+            dm::sincos_(dyaw, &sd, &cd);
+            my_a = sd * c.radius * direc;
+            my_b = (1 - cd) * c.radius * (double)seg.steer;
+            my_dyaw = dyaw * direc * (double)seg.steer;
+        }
+        else
+            my_a = seg.len * c.radius / my_num;
+    }
+    int total = 0;
+    for (int k = 0; k < path.n; ++k)
+        total += __shfl_sync(kFull, my_num, k);
+    if (total > 32)
+    {
+        int n = 0;
+        if (lane == 0)
+            n = rs_gen_traj(c, sx, sy, syaw, path, out_xyz, out_sd, cap);
+        n = __shfl_sync(kFull, n, 0);
+        __syncwarp();
+        return n;
+    }
+    // yaw chain: lane n keeps the yaw pose n starts from, the yaw it ends with and its segment
+    double yaw_from = syaw, yaw_to = syaw, curr_yaw = syaw;
+    int my_seg = 0;
+    {
+        int n = 0;
+        for (int k = 0; k < path.n; ++k)
+        {
+            const int num_pt = __shfl_sync(kFull, my_num, k);
+            const double dyaw = __shfl_sync(kFull, my_dyaw, k);
+            const bool arc = path.s[k].steer != 0;
+            for (int i = 0; i < num_pt; ++i, ++n)
+            {
+                const double before = curr_yaw;
+                if (arc)
+                {
+                    curr_yaw += dyaw;
+                    curr_yaw = rs_regular_rad(curr_yaw);
+                }
+                if (lane == n)
+                    yaw_from = before, yaw_to = curr_yaw, my_seg = k;
+            }
+        }
+    }
+    // position increments, one lane per pose
+    const bool live = lane < total;
+    const RsSeg seg = path.s[live ? my_seg : 0];
+    const double a = __shfl_sync(kFull, my_a, my_seg), b = __shfl_sync(kFull, my_b, my_seg);
+    double inc_x = 0, inc_y = 0;
+    {
+        double sy_, cy_;
+        dm::sincos_(yaw_from, &sy_, &cy_);
+        if (seg.steer != 0)
+        {
+            inc_x = a * cy_ - b * sy_;
+            inc_y = a * sy_ + b * cy_;
+        }
+        else
+        {
+            const double direc = (double)seg.dir;
+            inc_x = a * cy_ * direc;
+            inc_y = a * sy_ * direc;
+        }
+    }
+    // positions: the reference's running sums, in order
+    double cx = sx, cy = sy, my_x = sx, my_y = sy;
+    for (int n = 0; n < total; ++n)
+    {
+        cx = cx + __shfl_sync(kFull, inc_x, n);
+        cy = cy + __shfl_sync(kFull, inc_y, n);
+        if (lane == n)
+            my_x = cx, my_y = cy;
+    }
+    if (live && lane < cap)
+    {
+        out_xyz[3 * lane] = my_x, out_xyz[3 * lane + 1] = my_y, out_xyz[3 * lane + 2] = yaw_to;
+        if (out_sd)
+            out_sd[2 * lane] = (double)seg.steer * c.steer_angle, out_sd[2 * lane + 1] = (double)seg.dir;
+    }
+    __syncwarp();
+    return total;
+}
+
 // ---- OMPL-equivalent Reeds-Shepp distance ---------------------------------------------------
 // The oracle's stand-in for ompl::base::ReedsSheppStateSpace::distance is the specification (parity unpinned vs real
 // OMPL, see oracle/port/ompl_rs_distance.h); this mirrors it operation for operation.
