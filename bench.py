@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200-native mpros hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload plan|collision|expand|preprocess|rs]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload plan|collision|expand|preprocess|rs|arena]
 
 Workload "plan" (default; BASELINE.json configs[4]): synthetic 8192x8192 occupancy grid @0.1 m
 (seed 20261019: 1-m border wall + 1100 rectangles), inflation 1.0 m, down-sampling 8, shipped planner parameters
@@ -47,6 +47,8 @@ B_EXPANSION = 450                # E1 with the case-1 survivor / insert ratios
 B_SHOT = 440                     # R4 without the trajectory
 EXPANSIONS_PER_STEP = 1 << 20
 RS_SHOTS_PER_STEP = 1 << 20
+ARENA_QUERIES = 2048
+ARENA_CPU_QUERIES = 4
 B_GOAL_CELL = 5                  # N4: 1 B in, 4 B out per cell of the goal map
 
 
@@ -117,11 +119,11 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def gen_poses(n, seed):
+def gen_poses(n, seed, extent=EXTENT):
     rng = np.random.default_rng(seed)
     p = np.empty((n, 3), dtype=np.float64)
-    p[:, 0] = rng.uniform(0.0, EXTENT, n)
-    p[:, 1] = rng.uniform(0.0, EXTENT, n)
+    p[:, 0] = rng.uniform(0.0, extent, n)
+    p[:, 1] = rng.uniform(0.0, extent, n)
     p[:, 2] = rng.uniform(-np.pi, np.pi, n)
     return p
 
@@ -200,7 +202,7 @@ def _cpu_worker_plan(job):
 
 
 class CpuArm:
-    def __init__(self, occ, params, cores):
+    def __init__(self, occ, params, cores, res=None):
         from multiprocessing import get_context, shared_memory
 
         from oracle import refapi
@@ -211,10 +213,10 @@ class CpuArm:
         self.shm = shared_memory.SharedMemory(create=True, size=occ.nbytes)
         np.ndarray(occ.shape, dtype=np.int8, buffer=self.shm.buf)[:] = occ
         self.pool = get_context("spawn").Pool(cores, initializer=_cpu_worker_init,
-                                              initargs=(refapi.REF_SO, params, self.shm.name, occ.shape, SYN_RES))
+                                              initargs=(refapi.REF_SO, params, self.shm.name, occ.shape, SYN_RES if res is None else res))
 
-    def collision_rate(self, n_poses, seed):
-        poses = gen_poses(n_poses, seed)
+    def collision_rate(self, n_poses, seed, extent=None):
+        poses = gen_poses(n_poses, seed) if extent is None else gen_poses(n_poses, seed, extent)
         res = self.pool.map(_cpu_worker_collision, np.array_split(poses, self.cores))
         # workers run concurrently: throughput = total checks / slowest worker's footPrintInCollision4 loop
         return sum(r[2] for r in res) / max(r[0] for r in res)
@@ -795,18 +797,177 @@ def run_b200(args):
     return 0
 
 
+def run_arena(args):
+    """BASELINE.json configs[2], "case 3 Arena whole map" (the case the north star's 50x target names): the 2000 x 2000 @0.04 m
+    stand-in of SURVEY.md 8(d) (Arena2036's pgm is missing from the reference: ARENA_part's image read with Arena2036.yaml's
+    thresholds, nearest-neighbour x4; committed input fixture tests/golden/maps/arena_standin.npz), down-sampling 4. One line:
+    plans/s (headline), footprint checks/s and map preprocessing on this map, each beside the unmodified reference."""
+    import torch
+
+    import mpros_b200
+
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise RuntimeError("--workload arena is a single-GPU workload")
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
+    z = np.load(os.path.join(ROOT, "tests", "golden", "maps", "arena_standin.npz"))
+    occ = np.ascontiguousarray(np.repeat(np.repeat(z["occupancy"], 4, axis=0), 4, axis=1))
+    res, ds = 0.04, 4
+    extent = occ.shape[0] * res
+    params = shipped_params(ds)
+    params["/mpros/map/free_thresh"], params["/mpros/map/occupied_thresh"] = float(z["free_thresh"]), float(z["occupied_thresh"])
+    ctx = mpros_b200.Context(0)
+    ctx.map_config(params)
+    occ_pinned = torch.from_numpy(occ).pin_memory()
+    ctx.set_occupancy(occ_pinned.numpy(), res, [0.0, 0.0, 0.0])
+    ctx.planner_config(params)
+    stream = torch.cuda.ExternalStream(ctx.stream())
+    warm, K = max(3, args.warmup), args.steps
+    sampler = ClockSampler(0)
+    sampler.start()
+
+    def timed(fn, steps, join=None):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launch_count()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        if join:
+            join()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), ctx.launch_count() - l0
+
+    # map preprocessing (host buffer -> all layers), median of 5
+    t_pre = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        ctx.set_occupancy(occ_pinned.numpy(), res, [0.0, 0.0, 0.0])
+        t_pre.append(time.perf_counter() - t0)
+    t_pre = float(np.median(t_pre))
+    # footprint checks: 2^24 uniform poses, n_check = 55 probes at this resolution -> 24 + 1 + 60 = 85 B per check
+    n = POSES_PER_STEP
+    poses_d = torch.from_numpy(gen_poses(n, POSE_SEED, extent)).cuda()
+    verd_d = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    col_ms, _ = timed(lambda: ctx.collision_check_dev(poses_d.data_ptr(), n, verd_d.data_ptr()), 10)
+    col_rate = n * 10 / (col_ms * 1e-3)
+    hit_rate = float(verd_d.float().mean())
+    del poses_d, verd_d
+    # plans: seeded independent queries 20-80 m apart (the synthetic recipe on this map), batches in flight as in run_b200
+    nq = ARENA_QUERIES
+    static_ds = ctx.layer("static")
+    starts, goals = synthetic.synthetic_queries(nq, ctx.collision_check, static_ds, res * ds, extent, synthetic.SYN_QUERY_SEED)
+    s_h, g_h = torch.from_numpy(starts).pin_memory(), torch.from_numpy(goals).pin_memory()
+    s_d, g_d = s_h.cuda(), g_h.cuda()
+    LANES = max(1, min(args.lanes, mpros_b200.PLAN_LANES))
+    mk = lambda pin: {k: (torch.zeros(sz, dtype=dt).pin_memory() if pin else torch.zeros(sz, dtype=dt, device="cuda"))
+                      for k, sz, dt in (("status", nq, torch.int32), ("cost", nq, torch.float64), ("len", nq, torch.int32),
+                                        ("paths", nq * PATH_CAP * 5, torch.float64), ("stats", nq * 6, torch.int64))}
+    dbuf, hbuf = [mk(False) for _ in range(LANES)], [mk(True) for _ in range(LANES)]
+    cnt = {"d": 0, "h": 0}
+
+    def step_dev():
+        lane = cnt["d"] % LANES
+        cnt["d"] += 1
+        b = dbuf[lane]
+        ctx.plan_batch_submit_dev(lane, s_d.data_ptr(), g_d.data_ptr(), nq, b["status"].data_ptr(), b["cost"].data_ptr(), b["len"].data_ptr(),
+                                  b["paths"].data_ptr(), PATH_CAP, b["stats"].data_ptr())
+
+    def join():
+        for lane in range(1, LANES):
+            if ctx.plan_lane_stream(lane):
+                stream.wait_stream(torch.cuda.ExternalStream(ctx.plan_lane_stream(lane)))
+
+    plan_ms, launches = timed(step_dev, K, join)
+
+    def step_host():
+        lane = cnt["h"] % LANES
+        cnt["h"] += 1
+        b = hbuf[lane]
+        ctx.plan_batch_wait(lane)
+        ctx.plan_batch_submit(lane, s_h.data_ptr(), g_h.data_ptr(), nq, b["status"].data_ptr(), b["cost"].data_ptr(), b["len"].data_ptr(),
+                              b["paths"].data_ptr(), PATH_CAP, b["stats"].data_ptr())
+
+    for _ in range(2):
+        step_host()
+    ctx.plan_batch_wait(-1)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step_host()
+    ctx.plan_batch_wait(-1)
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    st = dbuf[0]["stats"].cpu().numpy().reshape(nq, 6)
+    status = dbuf[0]["status"].cpu().numpy()
+    assert np.array_equal(status, hbuf[0]["status"].numpy()), "host-API and device-API plans differ"
+    P = ctx.n_primitives()
+    expansions, shots, cells = int(st[:, 1].sum()) // P, int(st[:, 2].sum()), int(st[:, 4].sum())
+    secs = plan_ms * 1e-3 / K
+    peak, peak_kind = measured_peak_gbs()
+    algo = B_EXPANSION * expansions + B_SHOT * shots + B_GOAL_CELL * cells
+    line = {"metric": "plans_per_sec", "value": nq / secs, "unit": "plans/s", "n_gpus": 1, "steps": K, "warmup": warm, "ms_per_step": plan_ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "arena: case 3 'Arena whole map' stand-in, 2000x2000 @0.04 m (ARENA_part x4 with Arena2036.yaml's thresholds), ds=4, inflation 1.0 m, "
+                                   "shipped planner config; seeded independent start/goal queries 20-80 m apart; per query goal heuristic + Hybrid A* + Reeds-Shepp shots",
+                       "queries_per_gpu": nq, "path_cap": PATH_CAP, "batches_in_flight": LANES,
+                       "l2_policy": "per-query working sets in per-team HBM workspaces (>> L2 in aggregate); map layers L2-resident by design"},
+            "e2e": {"value": nq * K / e2e_s, "unit": "plans/s", "h2d_bytes_per_step": nq * 48, "d2h_bytes_per_step": nq * (4 + 8 + 4 + PATH_CAP * 40 + 48)},
+            "gpu_launches": int(launches), "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "achieved": algo / secs / 1e9, "peak": peak, "unit": "GB/s", "frac": algo / secs / 1e9 / peak, "traffic": None,
+                         "kernel": "plan_team_kernel", "kernel_ms": plan_ms / K, "peak_source": peak_kind, "algorithmic_bytes_per_launch": algo,
+                         "note": "latency/FP64-issue bound (sequential A* per query), not HBM bound; see DESIGN.md"},
+            "extra": {"node_expansions_per_sec": expansions / secs, "plans_found": int((status == 1).sum()), "plans_iteration_limit": int((status == 0).sum()),
+                      "plans_failed_other": int((status < 0).sum()), "mean_expansions_per_query": expansions / nq,
+                      "collision_checks_per_sec": col_rate, "collision_hit_rate": hit_rate,
+                      "collision_roofline_frac": col_rate * (24 + 1 + ctx_n_check(ctx) + 1 + 4) / 1e9 / peak,
+                      "preprocess_s_host_buffer": t_pre}}
+    cpu = None
+    if not args.no_cpu:
+        try:
+            arm = CpuArm(occ, params, 1, res)
+            try:
+                arm.collision_rate(1 << 16, POSE_SEED + 5, extent)
+                cv = arm.collision_rate(1 << 20, POSE_SEED + 6, extent)
+                r = arm.plan_rate(starts[:ARENA_CPU_QUERIES], goals[:ARENA_CPU_QUERIES])
+                cpu = {"value": r["plans_per_sec"], "unit": "plans/s", "cores": 1, "kind": "reference",
+                       "sample": "first %d queries of the step, 1 process x 1 thread, unmodified reference: NavMap::updateGoal + HybridAstar ctor + Plan() per query; %d/%d solved; "
+                                 "map preprocessing (setOccupancyMap) %.2f s; footPrintInCollision4 on 1048576 uniform poses" % (ARENA_CPU_QUERIES, r["solved"], ARENA_CPU_QUERIES, r["preprocess_s"]),
+                       "collision_checks_per_sec": cv, "preprocess_s": r["preprocess_s"], "node_expansions_per_sec": r["expansions_per_sec"]}
+            finally:
+                arm.close()
+        except Exception as e:
+            cpu = {"value": None, "unit": "plans/s", "cores": 0, "kind": "unavailable", "sample": str(e)}
+    line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    return 0
+
+
+def ctx_n_check(ctx):
+    """num_checking_step of the configured planner = ceil((L - W) / map_resolution_orig_) (hybrid_a_star.cpp:632-633)."""
+    import math
+
+    inf = ctx.info()
+    return int(math.ceil((4.2 - 2.0) / inf["map_resolution_orig"]))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="plan", choices=["plan", "collision", "expand", "preprocess", "rs"])
+    ap.add_argument("--workload", default="plan", choices=["plan", "collision", "expand", "preprocess", "rs", "arena"])
     ap.add_argument("--lanes", type=int, default=3, help="plan workload: query batches in flight (1 = one batch at a time)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "arena":
+        return run_arena(args)
     return run_b200(args)
 
 
