@@ -961,7 +961,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="plan", choices=["plan", "collision", "expand", "preprocess", "rs", "arena"])
-    ap.add_argument("--lanes", type=int, default=3, help="plan workload: query batches in flight (1 = one batch at a time)")
+    ap.add_argument("--lanes", type=int, default=4, help="plan workload: query batches in flight (1 = one batch at a time)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

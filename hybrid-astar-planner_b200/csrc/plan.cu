@@ -776,29 +776,39 @@ static int plan_pass(mpros_ctx *c, int lane, cudaStream_t stream, PlanBatchArgs 
 {
     PlanScratch &S = g_plan_scratch[c->device & 15][lane][pass];
     WarpWorkspaceLayout L = make_layout(node_cap, c->H, c->W);
-    // resident warps: 4 per CTA, a multiple of the SM count; bounded by the workspace budget
-    cudaDeviceProp prop;
-    MPROS_CUDA(cudaGetDeviceProperties(&prop, c->device));
-    size_t free_b = 0, total_b = 0;
-    MPROS_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    size_t budget = (free_b + S.ws_bytes) / 2;
+    // resident teams: a multiple of the SM count; bounded by the workspace budget. Device queries are cached per device:
+    // a batch submission should cost the host microseconds (cudaGetDeviceProperties alone takes milliseconds).
+    static int sm_count[16] = {}, resident_cta[16] = {}, resident_pair[16] = {};
+    if (!sm_count[c->device & 15])
+        MPROS_CUDA(cudaDeviceGetAttribute(&sm_count[c->device & 15], cudaDevAttrMultiProcessorCount, c->device));
+    const int n_sm = sm_count[c->device & 15];
     // team = one CTA (default) or a cluster of two CTAs on the two SMs of a TPC (MPROS_PLAN_MODE=cluster; plan_team.cuh).
     // Measured on the 16 384-query synthetic batch: CTA teams 1.57 s (296 teams, 6.8-7.5 us per iteration alone, ~11 us with
     // two teams per SM), CTA pairs 2.24 s (148 teams, 8.2-8.6 us per iteration alone AND loaded: no interference between
     // co-resident teams any more, but the two cluster barriers cost ~4 k cycles per iteration). Results are identical.
     const char *mode_env = std::getenv("MPROS_PLAN_MODE");
     const bool cluster = mode_env && std::strcmp(mode_env, "cluster") == 0;
-    int resident = 0;
-    if (cluster)
-        MPROS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, plan_cluster_kernel<kTeamWarps, kTeamMinBlocks>, kTeamWarps * 32, 0));
-    else
-        MPROS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, plan_team_kernel<kTeamWarps, kTeamMinBlocks>, kTeamWarps * 32, 0));
+    int &resident = cluster ? resident_pair[c->device & 15] : resident_cta[c->device & 15];
+    if (!resident)
+    {
+        if (cluster)
+            MPROS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, plan_cluster_kernel<kTeamWarps, kTeamMinBlocks>, kTeamWarps * 32, 0));
+        else
+            MPROS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, plan_team_kernel<kTeamWarps, kTeamMinBlocks>, kTeamWarps * 32, 0));
+        resident = std::max(1, resident);
+    }
     // one team per query at a time; every resident team owns one workspace
-    int blocks = (cluster ? prop.multiProcessorCount / 2 : prop.multiProcessorCount) * std::max(1, resident);
+    int blocks = (cluster ? n_sm / 2 : n_sm) * resident;
     blocks = std::min(blocks, n_run);
-    blocks = (int)std::min<long long>(blocks, std::max<long long>(1, (long long)(budget / L.stride)));
     if (max_warps > 0)
         blocks = std::min(blocks, std::max(1, max_warps));
+    if ((size_t)blocks * L.stride > S.ws_bytes) // what the lane already owns does not cover it: ask the device
+    {
+        size_t free_b = 0, total_b = 0;
+        MPROS_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const size_t budget = (free_b + S.ws_bytes) / 2;
+        blocks = (int)std::min<long long>(blocks, std::max<long long>(1, (long long)(budget / L.stride)));
+    }
     size_t need = (size_t)blocks * L.stride;
     if (need > S.ws_bytes)
     {
@@ -909,15 +919,21 @@ static int plan_batch_dev_impl(mpros_ctx *c, int lane, cudaStream_t stream, cons
     // runs exactly once; otherwise small pools first and the queries that overflowed are re-run with bigger ones
     long long caps[3] = {16384, 131072, max_nodes};
     {
-        size_t free_b = 0, total_b = 0;
-        MPROS_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        size_t have = free_b;
-        for (int k = 0; k < 3; ++k)
-            have += g_plan_scratch[c->device & 15][lane][k].ws_bytes;
         WarpWorkspaceLayout big = make_layout((int)max_nodes, c->H, c->W);
-        // lane 0 keeps half of the memory free for the caller; the extra lanes (pipelined batches) may use what is left
-        if (big.stride * (size_t)(kTeamMinBlocks * 148) < (lane == 0 ? have / 2 : have - have / 8))
+        const size_t full = big.stride * (size_t)(kTeamMinBlocks * 148);
+        if (S.ws_bytes >= full) // the lane already owns full-size pools
             caps[0] = max_nodes;
+        else
+        {
+            size_t free_b = 0, total_b = 0;
+            MPROS_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            size_t have = free_b;
+            for (int k = 0; k < 3; ++k)
+                have += g_plan_scratch[c->device & 15][lane][k].ws_bytes;
+            // lane 0 keeps half of the memory free for the caller; the extra lanes (pipelined batches) may use what is left
+            if (full < (lane == 0 ? have / 2 : have - have / 8))
+                caps[0] = max_nodes;
+        }
     }
     int rc = plan_pass(c, lane, stream, a, 0, (int)std::min<long long>(caps[0], max_nodes), nq, nullptr, 0);
     if (rc)
