@@ -2,7 +2,9 @@
  * mpros_gpu.h — C ABI of the B200-native (sm_100a) data-parallel core of the mpros Hybrid A* planner.
  *
  * This is the drop-in boundary: plain pointers and sizes, opaque context handle, int status returns,
- * caller-owned buffers, one CUDA stream per context, a context is not thread-safe. There is NO CPU
+ * caller-owned buffers, one CUDA stream per context (plus one per extra plan lane), a context is not
+ * thread-safe. The planner's per-query workspaces belong to the (device, lane) pair and are shared by the
+ * contexts of a process: one mpros_plan_batch* call at a time per device and lane. There is NO CPU
  * fallback behind any entry point: without a CUDA device every call fails with MPROS_ERR_CUDA.
  *
  * Each entry point names the reference interface it replaces (file:line in Runningchauncey/Hybrid-Astar-Planner).
