@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256, MPROS_C1_MINB) collision_poses_2phase_ker
 // One warp per path: lanes stride over the poses, ballot gives the OR with an early exit per 32-pose round.
 __global__ void __launch_bounds__(256) collision_paths_kernel(const __grid_constant__ MapView m, const __grid_constant__ PlannerView p, const double *__restrict__ xyyaw,
                                                               const int64_t *__restrict__ offsets, size_t n_paths,
-                                                              uint8_t *__restrict__ verdicts)
+                                                              uint8_t *__restrict__ verdicts, const uint32_t *__restrict__ unsafe_tw, int center_probe)
 {
     const int lane = threadIdx.x & 31;
     size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -141,7 +141,12 @@ __global__ void __launch_bounds__(256) collision_paths_kernel(const __grid_const
             int64_t k = k0 + lane;
             bool h = false;
             if (k < e)
-                h = footprint_in_collision4(m, p, xyyaw[3 * k], xyyaw[3 * k + 1], xyyaw[3 * k + 2]);
+            {
+                // decided by the pose's own cell where possible (footprint_preclass), the probe walk otherwise
+                const double x = xyyaw[3 * k], y = xyyaw[3 * k + 1], yaw = xyyaw[3 * k + 2];
+                const int cls = footprint_preclass(m, p, unsafe_tw, center_probe, x, y, yaw);
+                h = cls == 1 || (cls == 2 && footprint_in_collision4(m, p, x, y, yaw));
+            }
             hit = __any_sync(0xffffffffu, h);
         }
         if (lane == 0)
@@ -280,7 +285,10 @@ extern "C" int mpros_collision_check_paths(mpros_ctx *c, const double *xyyaw, co
     size_t blocks = (n_paths * 32 + 255) / 256;
     if (blocks > 148 * 32)
         blocks = 148 * 32;
-    collision_paths_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(c->view(), c->pv, d_in, d_off, n_paths, d_out);
+    rc = map_build_unsafe(c);
+    if (rc)
+        return rc;
+    collision_paths_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(c->view(), c->pv, d_in, d_off, n_paths, d_out, c->unsafe_tw, c->unsafe_center_probe);
     MPROS_LAUNCH_CHECK(c);
     MPROS_CUDA(cudaMemcpyAsync(verdicts, d_out, n_paths, cudaMemcpyDeviceToHost, c->stream));
     MPROS_CUDA(cudaStreamSynchronize(c->stream));
