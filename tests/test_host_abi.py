@@ -60,3 +60,25 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"(from|import)\s+oracle|#include\s+\"[^\"]*oracle|libmpros_oracle|libmpros_ref", txt), os.path.join(dirpath, f)
+
+
+def test_plan_lanes_constant_matches_header():
+    import re
+
+    hdr = open(os.path.join(ROOT, "include", "mpros_gpu.h")).read()
+    m = re.search(r"#define\s+MPROS_PLAN_LANES\s+(\d+)", hdr)
+    assert m and int(m.group(1)) == mpros_b200.PLAN_LANES
+
+
+def test_bench_workloads_are_documented():
+    """Every --workload of bench.py appears in its usage line and in DESIGN.md's measurement section."""
+    import re
+
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    choices = re.search(r'"--workload", default="plan", choices=\[([^\]]*)\]', src).group(1)
+    names = re.findall(r'"(\w+)"', choices)
+    assert set(names) >= {"plan", "collision", "expand", "preprocess", "rs", "arena"}
+    design = open(os.path.join(ROOT, "DESIGN.md")).read()
+    for w in names:
+        if w != "plan":
+            assert "--workload %s" % w in design, w
