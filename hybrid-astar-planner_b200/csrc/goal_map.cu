@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(256) goal_bfs_kernel(const uint32_t *__restric
 //    3.75 ms against 2.45 ms for the plain form with one cluster barrier per level; the level time is the dependent
 //    instruction chain of one warp, not the number of words.)
 // Termination: at every exchange each CTA posts "found something since the last one" into a slot of every CTA.
-constexpr int kGoalCluster = 8;
+constexpr int kGoalCluster = 8;     // portable cluster size
+constexpr int kGoalClusterMax = 16; // non-portable size, used when the device can co-schedule it (one GPC)
 constexpr int kGoalThreads = 1024;
 constexpr int kGoalMaxHalo = 8;
 constexpr size_t kGoalMaxSmem = 220 * 1024;
@@ -143,14 +144,15 @@ __global__ void fill_u16_kernel(uint16_t *__restrict__ p, size_t n, uint16_t v)
 // words per row in shared memory: a multiple of 4 so that a lane moves 128 cells (uint4) at a time
 __host__ __device__ inline int goal_row_stride(int nw) { return (nw + 3) & ~3; }
 
-__global__ void __cluster_dims__(kGoalCluster, 1, 1) __launch_bounds__(kGoalThreads, 1)
+__global__ void __launch_bounds__(kGoalThreads, 1)
     goal_bfs_cluster_kernel(const uint32_t *__restrict__ occ, int H, int W, int pitch, int gi, int gj, uint16_t *__restrict__ dist, int r0,
                             int rows, int w0, int nw, int band, int K)
 {
     extern __shared__ __align__(16) uint32_t gsm[];
-    __shared__ int slots[2][kGoalCluster];
+    __shared__ int slots[2][kGoalClusterMax];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
+    const int csize = (int)cluster.num_blocks(); // 8 or 16 CTAs (launch attribute)
     const int tid = threadIdx.x;
     const int wpr = (W + 31) >> 5;
     const int ext = band + 2 * K;       // rows held by this CTA: K halo + band + K halo
@@ -179,7 +181,7 @@ __global__ void __cluster_dims__(kGoalCluster, 1, 1) __launch_bounds__(kGoalThre
         fa[idx] = 0;
         fb[idx] = 0;
     }
-    if (tid < 2 * kGoalCluster)
+    if (tid < 2 * kGoalClusterMax)
         (&slots[0][0])[tid] = 0;
     __syncthreads();
     {
@@ -196,7 +198,7 @@ __global__ void __cluster_dims__(kGoalCluster, 1, 1) __launch_bounds__(kGoalThre
     cluster.sync();
 
     uint32_t *const up_base = rank > 0 ? cluster.map_shared_rank(gsm, rank - 1) : nullptr;
-    uint32_t *const dn_base = rank + 1 < kGoalCluster ? cluster.map_shared_rank(gsm, rank + 1) : nullptr;
+    uint32_t *const dn_base = rank + 1 < csize ? cluster.map_shared_rank(gsm, rank + 1) : nullptr;
     int found = 0; // in the band, since the last exchange
     for (int level = 1; level < kHugeInt; ++level)
     {
@@ -261,12 +263,11 @@ __global__ void __cluster_dims__(kGoalCluster, 1, 1) __launch_bounds__(kGoalThre
         const int par = (level / K) & 1;
         const int any = __syncthreads_or(found);
         found = 0;
-        if (tid < kGoalCluster)
+        if (tid < csize)
             *cluster.map_shared_rank(&slots[par][rank], tid) = any;
         cluster.sync(); // every band is final for this level, the votes are visible
         int tot = 0;
-#pragma unroll
-        for (int t = 0; t < kGoalCluster; ++t)
+        for (int t = 0; t < csize; ++t)
             tot |= slots[par][t];
         if (!tot)
             break; // uniform across the cluster: no band found anything in the last K levels, the frontier is exhausted
@@ -312,28 +313,66 @@ int map_build_goal(Ctx *c)
         const int r0 = std::max(0, gi - (kHugeInt - 1)), r1 = std::min(c->H - 1, gi + (kHugeInt - 1));
         const int w0 = std::max(0, gj - (kHugeInt - 1)) >> 5, w1 = std::min(wpr - 1, (gj + (kHugeInt - 1)) >> 5);
         const int rows = r1 - r0 + 1, nw = w1 - w0 + 1;
-        const int band = (rows + kGoalCluster - 1) / kGoalCluster;
-        // halo depth: as deep as the shared memory allows, never deeper than a band (a halo is a copy of the neighbour's band rows)
-        int halo = std::min(kGoalMaxHalo, band);
-        auto smem_for = [&](int k) { return (size_t)3 * (band + 2 * k) * goal_row_stride(nw) * sizeof(uint32_t); };
-        while (halo > 1 && smem_for(halo) > kGoalMaxSmem)
-            halo >>= 1;
-        const size_t smem = smem_for(halo);
-        const char *mode = std::getenv("MPROS_GOAL_MODE"); // "grid": force the cooperative kernel (tests compare the two)
-        if (smem <= kGoalMaxSmem && !(mode && std::strcmp(mode, "grid") == 0))
+        const char *mode = std::getenv("MPROS_GOAL_MODE"); // "grid": the cooperative kernel; "cluster8": the portable cluster size
+        const bool force_grid = mode && std::strcmp(mode, "grid") == 0;
+        static int attr_set[16] = {}; // 0 = not yet, 1 = 8 CTAs only, 2 = 16 CTAs available
+        if (!force_grid && !attr_set[c->device & 15])
         {
-            static bool attr_set[16] = {};
-            if (!attr_set[c->device & 15])
+            MPROS_CUDA(cudaFuncSetAttribute(goal_bfs_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGoalMaxSmem));
+            attr_set[c->device & 15] = 1;
+            if (cudaFuncSetAttribute(goal_bfs_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess)
             {
-                MPROS_CUDA(cudaFuncSetAttribute(goal_bfs_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGoalMaxSmem));
-                attr_set[c->device & 15] = true;
+                cudaLaunchConfig_t probe = {};
+                probe.gridDim = dim3(kGoalClusterMax);
+                probe.blockDim = dim3(kGoalThreads);
+                probe.dynamicSmemBytes = 64 * 1024;
+                cudaLaunchAttribute pa[1];
+                pa[0].id = cudaLaunchAttributeClusterDimension;
+                pa[0].val.clusterDim.x = kGoalClusterMax;
+                pa[0].val.clusterDim.y = 1;
+                pa[0].val.clusterDim.z = 1;
+                probe.attrs = pa;
+                probe.numAttrs = 1;
+                int n_clusters = 0;
+                if (cudaOccupancyMaxActiveClusters(&n_clusters, goal_bfs_cluster_kernel, &probe) == cudaSuccess && n_clusters >= 1)
+                    attr_set[c->device & 15] = 2;
             }
+            (void)cudaGetLastError();
+        }
+        int csize = (attr_set[c->device & 15] == 2 && !(mode && std::strcmp(mode, "cluster8") == 0)) ? kGoalClusterMax : kGoalCluster;
+        auto plan_for = [&](int cs, int &band_o, int &halo_o) {
+            band_o = (rows + cs - 1) / cs;
+            // halo depth: as deep as the shared memory allows, never deeper than a band (a halo is a copy of the neighbour's band rows)
+            halo_o = std::min(kGoalMaxHalo, band_o);
+            auto smem_for = [&](int k) { return (size_t)3 * (band_o + 2 * k) * goal_row_stride(nw) * sizeof(uint32_t); };
+            while (halo_o > 1 && smem_for(halo_o) > kGoalMaxSmem)
+                halo_o >>= 1;
+            return smem_for(halo_o);
+        };
+        int band = 0, halo = 0;
+        size_t smem = plan_for(csize, band, halo);
+        if (!force_grid && smem <= kGoalMaxSmem)
+        {
             const size_t cells = (size_t)c->H * c->W;
             fill_u16_kernel<<<148 * 4, 256, 0, c->stream>>>(c->goal, cells, (uint16_t)kHugeInt);
             MPROS_LAUNCH_CHECK(c);
-            goal_bfs_cluster_kernel<<<kGoalCluster, kGoalThreads, smem, c->stream>>>(c->ds_bits, c->H, c->W, c->pitch, gi, gj, c->goal, r0, rows,
-                                                                                 w0, nw, band, halo);
-            MPROS_LAUNCH_CHECK(c);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(csize);
+            cfg.blockDim = dim3(kGoalThreads);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = c->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = csize;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            const uint32_t *occ = c->ds_bits;
+            uint16_t *dist = c->goal;
+            int H = c->H, W = c->W, pitch = c->pitch;
+            MPROS_CUDA(cudaLaunchKernelEx(&cfg, goal_bfs_cluster_kernel, occ, H, W, pitch, gi, gj, dist, r0, rows, w0, nw, band, halo));
+            c->launches++;
             return MPROS_OK;
         }
     }
