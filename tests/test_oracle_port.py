@@ -143,3 +143,52 @@ def test_port_matches_live_reference(plib):
         assert np.array_equal(rm.layer(layer), pm.layer(layer)), layer
     poses = gi.collision_poses(inf, n=20000, seed=4)
     assert np.array_equal(refapi.RefPlanner(rm).collision4(poses), portapi.PortPlanner(pm, params).collision4(poses))
+
+
+def test_footprint_preclassification_rules_hold_for_the_reference_arithmetic():
+    """The two rules behind the GPU's two-phase footprint test (collision.cu, map_device.cuh: footprint_preclass), checked on
+    the CPU against the restatement of footPrintInCollision4 (itself bit-identical to the reference):
+      surely free: no inflated cell within Chebyshev distance floor(reach_axis/res)+1 and no raw cell within
+                   floor(reach_corner/res)+1 of the pose's cell, that far inside the map  =>  verdict 0;
+      sure hit:    n_check even, symmetric axis, the pose's own cell occupied in the inflated layer and the pose at least
+                   2^-22 cells away from every cell edge  =>  verdict 1."""
+    import sys
+
+    from scipy import ndimage
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hybrid-astar-planner_b200"))
+    import synthetic
+
+    res = 0.1
+    occ = synthetic.synthetic_occupancy(size=2048, n_rect=70)
+    params = refapi.shipped_params(0.2, 0.68, ds=8)
+    pm = portapi.PortMap(portapi.PortLib(), params)
+    pm.set_occupancy(occ, res, [0.0, 0.0, 0.0])
+    raw, infl = pm.layer("static_orig") != 0, pm.layer("inflate_orig") != 0
+    L, W = 4.2, 2.0
+    r_axis = int(np.floor((L - W) / 2 / res + 1e-6) + 1)
+    r_corner = int(np.floor(np.hypot(L / 2, W / 2) / res + 1e-6) + 1)
+    assert (r_axis, r_corner) == (12, 24) and int(np.ceil((L - W) / res)) % 2 == 0
+    unsafe = ndimage.maximum_filter(infl, size=2 * r_axis + 1) | ndimage.maximum_filter(raw, size=2 * r_corner + 1)
+    unsafe[:r_corner, :] = unsafe[-r_corner:, :] = True
+    unsafe[:, :r_corner] = unsafe[:, -r_corner:] = True
+    rng = np.random.default_rng(17)
+    n = 1 << 20
+    ext = occ.shape[0] * res
+    poses = np.stack([rng.uniform(0, ext, n), rng.uniform(0, ext, n), rng.uniform(-np.pi, np.pi, n)], axis=1)
+    k = n // 4
+    poses[:k, :2] = np.round(poses[:k, :2] / res) * res                      # on cell edges: neither rule may fire wrongly
+    poses[k:2 * k, :2] = (np.floor(poses[k:2 * k, :2] / res) + 0.5) * res    # cell centres
+    want = portapi.PortPlanner(pm).collision4(poses)
+    q = poses[:, :2] / res
+    cell = np.floor(q).astype(np.int64)
+    inside = (cell >= 0).all(1) & (cell < occ.shape[0]).all(1)
+    cj, ci = np.clip(cell[:, 0], 0, occ.shape[1] - 1), np.clip(cell[:, 1], 0, occ.shape[0] - 1)
+    frac = q - np.floor(q)
+    centred = (np.minimum(frac, 1 - frac) >= 2.0 ** -22).all(1)
+    free = inside & ~unsafe[ci, cj]
+    hit = inside & unsafe[ci, cj] & infl[ci, cj] & centred
+    assert free.mean() > 0.3 and hit.mean() > 0.1
+    assert not want[free].any(), "%d 'surely free' poses collide for the reference" % int(want[free].sum())
+    assert want[hit].all(), "%d 'sure hit' poses are free for the reference" % int((want[hit] == 0).sum())
+    pm.close()
