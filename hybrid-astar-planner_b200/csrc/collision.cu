@@ -171,14 +171,13 @@ static int check_ready(Ctx *c, const char *who)
 
 static int launch_poses(Ctx *c, const double *d_xyyaw, size_t n, uint8_t *d_verdicts)
 {
-    // grid = multiple of the 148 SMs, 8 resident CTAs of 256 threads each; grid-stride covers the rest
+    // grid = multiple of the SM count, 8 resident CTAs of 256 threads each; grid-stride covers the rest
     size_t blocks = (n + 255) / 256;
-    size_t cap = 148 * 32;
+    size_t cap = (size_t)c->n_sm * 32;
     if (blocks > cap)
         blocks = cap;
     // MPROS_C1_MODE=walk: every pose through the probe walk (the single-phase kernel), for A/B measurements and tests
-    const char *mode = std::getenv("MPROS_C1_MODE");
-    if (mode && std::strcmp(mode, "walk") == 0)
+    if (c->opt.c1_walk)
     {
         collision_poses_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(c->view(), c->pv, d_xyyaw, n, d_verdicts);
         MPROS_LAUNCH_CHECK(c);
@@ -189,8 +188,8 @@ static int launch_poses(Ctx *c, const double *d_xyyaw, size_t n, uint8_t *d_verd
         return rc;
     size_t chunks = (n + 256 * kC1PosesPerLane - 1) / (256 * kC1PosesPerLane); // CTAs of 8 warps, one warp chunk each at least
     // persistent: one wave of resident CTAs, so that a warp sees many chunks and its last, partly filled round is rare
-    if (chunks > (size_t)148 * MPROS_C1_MINB)
-        chunks = (size_t)148 * MPROS_C1_MINB;
+    if (chunks > (size_t)c->n_sm * MPROS_C1_MINB)
+        chunks = (size_t)c->n_sm * MPROS_C1_MINB;
     if (n >= (1ull << 32)) // ring entries are 32-bit pose indices
     {
         collision_poses_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(c->view(), c->pv, d_xyyaw, n, d_verdicts);
@@ -283,8 +282,8 @@ extern "C" int mpros_collision_check_paths(mpros_ctx *c, const double *xyyaw, co
         MPROS_CUDA(cudaMemcpyAsync(d_in, xyyaw, pose_bytes, cudaMemcpyHostToDevice, c->stream));
     MPROS_CUDA(cudaMemcpyAsync(d_off, offsets, off_bytes, cudaMemcpyHostToDevice, c->stream));
     size_t blocks = (n_paths * 32 + 255) / 256;
-    if (blocks > 148 * 32)
-        blocks = 148 * 32;
+    if (blocks > (size_t)c->n_sm * 32)
+        blocks = (size_t)c->n_sm * 32;
     rc = map_build_unsafe(c);
     if (rc)
         return rc;

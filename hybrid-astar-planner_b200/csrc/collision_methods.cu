@@ -363,8 +363,8 @@ extern "C" int mpros_collision_check_poses_method(mpros_ctx *c, int method, cons
             a.fx[k] = fx[k], a.fy[k] = fy[k];
     }
     size_t blocks = (n * 32 + 255) / 256;
-    if (blocks > 148 * 16)
-        blocks = 148 * 16;
+    if (blocks > (size_t)c->n_sm * 16)
+        blocks = (size_t)c->n_sm * 16;
     if (method == 1)
         collision_method1_kernel<<<(unsigned)blocks, 256, 0, st>>>(c->view(), c->pv, a);
     else if (method == 2)

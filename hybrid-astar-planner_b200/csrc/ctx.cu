@@ -1,6 +1,7 @@
 // Context lifetime, error reporting and configuration (NavMap::config, HybridAstar::config/setFootprint).
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -35,6 +36,51 @@ static int grow(void **p, size_t *cap, size_t bytes)
 }
 int ensure_scratch(Ctx *c, size_t bytes) { return grow(&c->scratch, &c->scratch_bytes, bytes); }
 int ensure_stage(Ctx *c, size_t bytes) { return grow(&c->stage, &c->stage_bytes, bytes); }
+
+// one switch of Options; value == nullptr or "" restores the default
+static bool apply_option(Options &o, const char *key, const char *value)
+{
+    const std::string k = key ? key : "", v = value ? value : "";
+    if (k == "c1_mode")
+    {
+        if (v != "" && v != "2phase" && v != "walk")
+            return false;
+        o.c1_walk = v == "walk";
+    }
+    else if (k == "goal_mode")
+    {
+        if (v != "" && v != "cluster" && v != "cluster8" && v != "grid")
+            return false;
+        o.goal_mode = v == "grid" ? 2 : v == "cluster8" ? 1 : 0;
+    }
+    else if (k == "plan_mode")
+    {
+        if (v != "" && v != "team" && v != "cluster")
+            return false;
+        o.plan_cluster = v == "cluster";
+    }
+    else if (k == "debug")
+        o.debug = !(v == "" || v == "0");
+    else
+        return false;
+    return true;
+}
+
+static void free_plan_scratch(Ctx *c)
+{
+    for (int l = 0; l < MPROS_PLAN_LANES; ++l)
+        for (int k = 0; k < kPlanPasses; ++k)
+        {
+            PlanScratch &S = c->plan_scratch[l][k];
+            if (S.ws)
+                cudaFree(S.ws);
+            if (S.counter)
+                cudaFree(S.counter);
+            if (S.todo)
+                cudaFree(S.todo);
+            S = PlanScratch();
+        }
+}
 } // namespace mpros
 
 using namespace mpros;
@@ -71,6 +117,17 @@ extern "C" int mpros_ctx_create(int device, mpros_ctx **out)
         return MPROS_ERR_INVALID;
     }
     c->device = device;
+    cudaError_t ae = cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device);
+    if (ae != cudaSuccess || c->n_sm < 1)
+    {
+        delete c;
+        return cuda_fail(ae == cudaSuccess ? cudaErrorInvalidDevice : ae, "cudaDevAttrMultiProcessorCount", __FILE__, __LINE__);
+    }
+    // the MPROS_* environment is read here and nowhere else; unknown values keep the default
+    apply_option(c->opt, "c1_mode", std::getenv("MPROS_C1_MODE"));
+    apply_option(c->opt, "goal_mode", std::getenv("MPROS_GOAL_MODE"));
+    apply_option(c->opt, "plan_mode", std::getenv("MPROS_PLAN_MODE"));
+    apply_option(c->opt, "debug", std::getenv("MPROS_DEBUG"));
     mpros_map_params_default(&c->mp);
     mpros_planner_params_default(&c->pp);
     std::memset(&c->pv, 0, sizeof(c->pv));
@@ -99,6 +156,7 @@ extern "C" int mpros_ctx_destroy(mpros_ctx *c)
             if (c->lane_stage[l])
                 cudaFree(c->lane_stage[l]);
         }
+    free_plan_scratch(c); // node pools, open lists, closed sets of every lane (tens of GB at full size)
     void *bufs[] = {c->raw_bits, c->infl_bits, c->ds_bits, c->goal, c->obs_dist, c->edge_dist, c->region,
                     c->edge_bits, c->voronoi, c->scratch, c->stage, c->raw_tw, c->infl_tw, c->unsafe_tw};
     for (void *b : bufs)
@@ -106,6 +164,37 @@ extern "C" int mpros_ctx_destroy(mpros_ctx *c)
             cudaFree(b);
     cudaStreamDestroy(c->stream);
     delete c;
+    return MPROS_OK;
+}
+
+extern "C" int mpros_ctx_set_option(mpros_ctx *c, const char *key, const char *value)
+{
+    if (!c || !key)
+    {
+        set_error("mpros_ctx_set_option: NULL argument");
+        return MPROS_ERR_INVALID;
+    }
+    if (!apply_option(c->opt, key, value))
+    {
+        set_error(std::string("mpros_ctx_set_option: unknown option or value: ") + key + "=" + (value ? value : ""));
+        return MPROS_ERR_INVALID;
+    }
+    return MPROS_OK;
+}
+
+extern "C" int mpros_plan_release_workspaces(mpros_ctx *c)
+{
+    if (!c)
+    {
+        set_error("mpros_plan_release_workspaces: NULL context");
+        return MPROS_ERR_INVALID;
+    }
+    MPROS_CUDA(cudaSetDevice(c->device));
+    MPROS_CUDA(cudaStreamSynchronize(c->stream));
+    for (int l = 1; l < MPROS_PLAN_LANES; ++l)
+        if (c->lane_stream[l])
+            MPROS_CUDA(cudaStreamSynchronize(c->lane_stream[l]));
+    free_plan_scratch(c);
     return MPROS_OK;
 }
 
@@ -191,9 +280,26 @@ extern "C" int mpros_planner_config(mpros_ctx *c, const mpros_planner_params *p)
         set_error("mpros_planner_config: steering_discretization / yaw_discretization out of range");
         return MPROS_ERR_INVALID;
     }
-    c->pp = *p;
-    c->unsafe_valid = false; // depends on the footprint
-    PlannerView &v = c->pv;
+    // Everything is validated and built in a local PlannerView; the context is only touched on success, so a failed call
+    // leaves the previous configuration (or "not configured") intact.
+    auto finite_pos = [](double v) { return std::isfinite(v) && v > 0; };
+    if (!finite_pos(p->step_size) || !finite_pos(p->path_point_distance) || !finite_pos(p->max_curvature) ||
+        !finite_pos(p->max_steering_angle) || !finite_pos(p->length) || !finite_pos(p->width) || !std::isfinite(p->wheelbase) ||
+        !std::isfinite(p->steer_offset) || !std::isfinite(p->analytic_solution_range) || p->max_iteration < 0 ||
+        !std::isfinite(p->gear_penalty) || !std::isfinite(p->reverse_penalty) || !std::isfinite(p->steering_penalty) ||
+        !std::isfinite(p->steering_change_penalty))
+    {
+        set_error("mpros_planner_config: step_size, path_point_distance, max_curvature, max_steering_angle, length and width must "
+                  "be finite and positive, the other parameters finite");
+        return MPROS_ERR_INVALID;
+    }
+    if (!(p->step_size / p->path_point_distance < 1e6))
+    {
+        set_error("mpros_planner_config: step_size / path_point_distance too large");
+        return MPROS_ERR_INVALID;
+    }
+    PlannerView v;
+    std::memset(&v, 0, sizeof(v));
     const double L = p->length, Wd = p->width, off = p->steer_offset;
     // footprint_m_ corners, clockwise (hybrid_a_star.cpp:193-196)
     v.corner_x[0] = L / 2 + off;
@@ -209,12 +315,13 @@ extern "C" int mpros_planner_config(mpros_ctx *c, const mpros_planner_params *p)
     v.longi_x1 = -L / 2 + off + 1.0 / 2 * Wd;
     // num_checking_step (hybrid_a_star.cpp:632-633)
     double footprint_len = L - Wd;
-    v.n_check = (int)std::ceil(footprint_len / c->res0);
-    if (v.n_check < 1)
+    const double n_check_d = std::ceil(footprint_len / c->res0);
+    if (!(n_check_d >= 1) || !(n_check_d < 1e8))
     {
-        set_error("mpros_planner_config: length - width must be positive");
+        set_error("mpros_planner_config: length - width must be positive (num_checking_step >= 1)");
         return MPROS_ERR_INVALID;
     }
+    v.n_check = (int)n_check_d;
     v.inv_n_check = 1.0 / (double)v.n_check;
     v.fx_extent = v.n_check <= 512 ? std::fabs(L) + std::fabs(Wd) + std::fabs(off) : INFINITY;
     // corners lie within |W| (> sqrt(2) * W / 2) of an axis end point
@@ -286,6 +393,10 @@ extern "C" int mpros_planner_config(mpros_ctx *c, const mpros_planner_params *p)
     v.num_yaw = p->yaw_discretization;
     v.yaw_resol = 2 * M_PI / p->yaw_discretization;
     v.max_iteration = p->max_iteration;
+    // commit
+    c->pp = *p;
+    c->pv = v;
+    c->unsafe_valid = false; // depends on the footprint
     c->planner_configured = true;
     return MPROS_OK;
 }

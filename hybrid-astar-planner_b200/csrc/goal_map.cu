@@ -313,8 +313,7 @@ int map_build_goal(Ctx *c)
         const int r0 = std::max(0, gi - (kHugeInt - 1)), r1 = std::min(c->H - 1, gi + (kHugeInt - 1));
         const int w0 = std::max(0, gj - (kHugeInt - 1)) >> 5, w1 = std::min(wpr - 1, (gj + (kHugeInt - 1)) >> 5);
         const int rows = r1 - r0 + 1, nw = w1 - w0 + 1;
-        const char *mode = std::getenv("MPROS_GOAL_MODE"); // "grid": the cooperative kernel; "cluster8": the portable cluster size
-        const bool force_grid = mode && std::strcmp(mode, "grid") == 0;
+        const bool force_grid = c->opt.goal_mode == 2; // "grid": the cooperative kernel; 1 = "cluster8": the portable cluster size
         static int attr_set[16] = {}; // 0 = not yet, 1 = 8 CTAs only, 2 = 16 CTAs available
         if (!force_grid && !attr_set[c->device & 15])
         {
@@ -339,7 +338,7 @@ int map_build_goal(Ctx *c)
             }
             (void)cudaGetLastError();
         }
-        int csize = (attr_set[c->device & 15] == 2 && !(mode && std::strcmp(mode, "cluster8") == 0)) ? kGoalClusterMax : kGoalCluster;
+        int csize = (attr_set[c->device & 15] == 2 && c->opt.goal_mode != 1) ? kGoalClusterMax : kGoalCluster;
         auto plan_for = [&](int cs, int &band_o, int &halo_o) {
             band_o = (rows + cs - 1) / cs;
             // halo depth: as deep as the shared memory allows, never deeper than a band (a halo is a copy of the neighbour's band rows)
@@ -354,7 +353,7 @@ int map_build_goal(Ctx *c)
         if (!force_grid && smem <= kGoalMaxSmem)
         {
             const size_t cells = (size_t)c->H * c->W;
-            fill_u16_kernel<<<148 * 4, 256, 0, c->stream>>>(c->goal, cells, (uint16_t)kHugeInt);
+            fill_u16_kernel<<<c->n_sm * 4, 256, 0, c->stream>>>(c->goal, cells, (uint16_t)kHugeInt);
             MPROS_LAUNCH_CHECK(c);
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(csize);
@@ -387,13 +386,11 @@ int map_build_goal(Ctx *c)
 
     int per_sm = 0;
     MPROS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, goal_bfs_kernel, 256, 0));
-    cudaDeviceProp prop;
-    MPROS_CUDA(cudaGetDeviceProperties(&prop, c->device));
     if (per_sm < 1)
         per_sm = 1;
     if (per_sm > 4)
         per_sm = 4; // the per-level work is small; fewer CTAs make grid.sync cheaper
-    int grid = prop.multiProcessorCount * per_sm;
+    int grid = c->n_sm * per_sm;
     const uint32_t *occ = c->ds_bits;
     int H = c->H, W = c->W, pitch = c->pitch;
     uint16_t *dist = c->goal;

@@ -392,17 +392,6 @@ __global__ void __launch_bounds__(256) msg_scale_f32_kernel(const float *__restr
         out[k] = msg_store(floorf(__fdiv_rn(__fmul_rn(in[k], 100.f), maxval)));
 }
 
-static int grid_for(size_t work_items, int block = 256)
-{
-    size_t g = (work_items + block - 1) / block;
-    const size_t cap = 148 * 16; // multiples of the SM count; grid-stride loops cover the rest
-    if (g > cap)
-        g = cap;
-    if (g < 1)
-        g = 1;
-    return (int)g;
-}
-
 static int realloc_layers(Ctx *c)
 {
     size_t words0 = (size_t)c->H0 * c->pitch0, words = (size_t)c->H * c->pitch, cells = (size_t)c->H * c->W;
@@ -499,7 +488,7 @@ static int map_begin(Ctx *c, int width, int height, double resolution, double ox
         MPROS_CUDA(cudaMalloc(&nb, (size_t)c->H0 * c->pitch0 * 4));
         if (geom_change && old_bits)
         {
-            relinearize_kernel<<<grid_for((size_t)c->H0 * c->pitch0), 256, 0, st>>>(old_bits, oldH, oldW, old_pitch, nb, c->H0,
+            relinearize_kernel<<<grid_for(c, (size_t)c->H0 * c->pitch0), 256, 0, st>>>(old_bits, oldH, oldW, old_pitch, nb, c->H0,
                                                                                   c->W0, c->pitch0);
             MPROS_LAUNCH_CHECK(c);
             MPROS_CUDA(cudaStreamSynchronize(st));
@@ -532,12 +521,12 @@ static int map_threshold_rows(Ctx *c, const int8_t *d_rows, int row0, int nrows,
     if ((width % 32) == 0 && (reinterpret_cast<uintptr_t>(d_rows) % 16) == 0)
     {
         size_t words = (size_t)nrows * (width >> 5);
-        threshold_pack_vec_kernel<<<grid_for(words), 256, 0, st>>>(d_rows, bits, nrows, width, c->pitch0, occ_min, free_max, have_old);
+        threshold_pack_vec_kernel<<<grid_for(c, words), 256, 0, st>>>(d_rows, bits, nrows, width, c->pitch0, occ_min, free_max, have_old);
     }
     else
     {
         size_t words = (size_t)nrows * ((width + 31) / 32);
-        threshold_pack_kernel<<<grid_for(words * 32), 256, 0, st>>>(d_rows, bits, nrows, width, c->pitch0, occ_min, free_max, have_old);
+        threshold_pack_kernel<<<grid_for(c, words * 32), 256, 0, st>>>(d_rows, bits, nrows, width, c->pitch0, occ_min, free_max, have_old);
     }
     MPROS_LAUNCH_CHECK(c);
     return MPROS_OK;
@@ -591,7 +580,7 @@ static int map_inflate_rows(Ctx *c, int smax, int row0, int nrows)
     int K = (smax + 31) / 32;
     if (K < 1)
         K = 1;
-    int g = grid_for(words);
+    int g = grid_for(c, words);
     switch (K)
     {
     case 1:
@@ -634,10 +623,10 @@ static int map_finish(Ctx *c)
             int log2ds = 0;
             while ((1 << log2ds) < ds)
                 ++log2ds;
-            downsample_pow2_kernel<<<grid_for(words), 256, 0, st>>>(c->raw_bits, c->pitch0, c->ds_bits, c->H, c->W, c->pitch, ds, log2ds);
+            downsample_pow2_kernel<<<grid_for(c, words), 256, 0, st>>>(c->raw_bits, c->pitch0, c->ds_bits, c->H, c->W, c->pitch, ds, log2ds);
         }
         else
-            downsample_kernel<<<grid_for(words * 32), 256, 0, st>>>(c->raw_bits, c->H0, c->W0, c->pitch0, c->ds_bits, c->H, c->W,
+            downsample_kernel<<<grid_for(c, words * 32), 256, 0, st>>>(c->raw_bits, c->H0, c->W0, c->pitch0, c->ds_bits, c->H, c->W,
                                                                   c->pitch, ds);
         MPROS_LAUNCH_CHECK(c);
     }
@@ -649,9 +638,9 @@ static int map_finish(Ctx *c)
         const int tw_rows = (c->H0 + 2 * kTwMargin + 3) / 4;
 #endif
         const size_t tw_words = (size_t)c->tw_pitch * tw_rows;
-        build_tilewords_kernel<<<grid_for(tw_words), 256, 0, st>>>(c->raw_bits, c->H0, c->W0, c->pitch0, c->raw_tw, c->tw_pitch, tw_rows);
+        build_tilewords_kernel<<<grid_for(c, tw_words), 256, 0, st>>>(c->raw_bits, c->H0, c->W0, c->pitch0, c->raw_tw, c->tw_pitch, tw_rows);
         MPROS_LAUNCH_CHECK(c);
-        build_tilewords_kernel<<<grid_for(tw_words), 256, 0, st>>>(c->infl_bits, c->H0, c->W0, c->pitch0, c->infl_tw, c->tw_pitch, tw_rows);
+        build_tilewords_kernel<<<grid_for(c, tw_words), 256, 0, st>>>(c->infl_bits, c->H0, c->W0, c->pitch0, c->infl_tw, c->tw_pitch, tw_rows);
         MPROS_LAUNCH_CHECK(c);
     }
     c->unsafe_valid = false; // derived from the two layers just rebuilt
@@ -660,9 +649,13 @@ static int map_finish(Ctx *c)
     c->band_open = false;
     if (c->planner_configured)
     {
-        int rc = mpros_planner_config(static_cast<mpros_ctx *>(c), &c->pp); // n_check depends on the resolution
+        const mpros_planner_params keep = c->pp;
+        int rc = mpros_planner_config(static_cast<mpros_ctx *>(c), &keep); // n_check depends on the resolution
         if (rc)
+        {
+            c->planner_configured = false; // the old footprint constants do not fit the new resolution
             return rc;
+        }
     }
     // nav_map.cpp:150-156
     if (c->get_goal)
@@ -781,13 +774,13 @@ int map_build_unsafe(Ctx *c)
     else
     {
         const int r_axis = (int)ra, r_corner = (int)rc_;
-        dilate_rows_kernel<<<grid_for(words0), 256, 0, st>>>(c->infl_bits, c->H0, c->pitch0, r_axis, rows_axis);
+        dilate_rows_kernel<<<grid_for(c, words0), 256, 0, st>>>(c->infl_bits, c->H0, c->pitch0, r_axis, rows_axis);
         MPROS_LAUNCH_CHECK(c);
-        dilate_rows_kernel<<<grid_for(words0), 256, 0, st>>>(c->raw_bits, c->H0, c->pitch0, r_corner, rows_corner);
+        dilate_rows_kernel<<<grid_for(c, words0), 256, 0, st>>>(c->raw_bits, c->H0, c->pitch0, r_corner, rows_corner);
         MPROS_LAUNCH_CHECK(c);
-        unsafe_cols_kernel<<<grid_for(words0), 256, 0, st>>>(rows_axis, r_axis, rows_corner, r_corner, c->H0, c->W0, c->pitch0, unsafe_bits);
+        unsafe_cols_kernel<<<grid_for(c, words0), 256, 0, st>>>(rows_axis, r_axis, rows_corner, r_corner, c->H0, c->W0, c->pitch0, unsafe_bits);
         MPROS_LAUNCH_CHECK(c);
-        build_tilewords_kernel<<<grid_for(tw_words), 256, 0, st>>>(unsafe_bits, c->H0, c->W0, c->pitch0, c->unsafe_tw, c->tw_pitch, tw_rows);
+        build_tilewords_kernel<<<grid_for(c, tw_words), 256, 0, st>>>(unsafe_bits, c->H0, c->W0, c->pitch0, c->unsafe_tw, c->tw_pitch, tw_rows);
         MPROS_LAUNCH_CHECK(c);
     }
     // the axis line has a probe exactly at the pose when n_check is even and the axis is symmetric about it
@@ -1028,7 +1021,7 @@ extern "C" int mpros_map_download(mpros_ctx *c, int layer, void *dst, size_t dst
                                : layer == MPROS_LAYER_INFLATE_ORIG ? c->infl_bits
                                : layer == MPROS_LAYER_STATIC ? c->ds_bits
                                                              : c->edge_bits;
-        unpack_bits_kernel<<<grid_for(need), 256, 0, st>>>(bits, orig ? c->H0 : c->H, orig ? c->W0 : c->W,
+        unpack_bits_kernel<<<grid_for(c, need), 256, 0, st>>>(bits, orig ? c->H0 : c->H, orig ? c->W0 : c->W,
                                                           orig ? c->pitch0 : c->pitch, static_cast<int8_t *>(c->scratch));
         MPROS_LAUNCH_CHECK(c);
         src = c->scratch;
@@ -1050,7 +1043,7 @@ extern "C" int mpros_map_download(mpros_ctx *c, int layer, void *dst, size_t dst
         if (rc)
             return rc;
         const uint16_t *in = layer == MPROS_LAYER_GOAL ? c->goal : layer == MPROS_LAYER_OBS_DIST ? c->obs_dist : c->edge_dist;
-        widen_u16_kernel<<<grid_for(cells), 256, 0, st>>>(in, cells, static_cast<int32_t *>(c->scratch));
+        widen_u16_kernel<<<grid_for(c, cells), 256, 0, st>>>(in, cells, static_cast<int32_t *>(c->scratch));
         MPROS_LAUNCH_CHECK(c);
         src = c->scratch;
         break;
@@ -1114,7 +1107,7 @@ extern "C" int mpros_map_layer_msg(mpros_ctx *c, int layer, int8_t *dst, size_t 
     if (bit_layer)
     {
         const uint32_t *bits = layer == MPROS_LAYER_STATIC_ORIG ? c->raw_bits : layer == MPROS_LAYER_INFLATE_ORIG ? c->infl_bits : c->ds_bits;
-        msg_bits_kernel<<<grid_for(n), 256, 0, st>>>(bits, orig ? c->H0 : c->H, orig ? c->W0 : c->W, orig ? c->pitch0 : c->pitch, out);
+        msg_bits_kernel<<<grid_for(c, n), 256, 0, st>>>(bits, orig ? c->H0 : c->H, orig ? c->W0 : c->W, orig ? c->pitch0 : c->pitch, out);
         MPROS_LAUNCH_CHECK(c);
     }
     else
@@ -1122,15 +1115,15 @@ extern "C" int mpros_map_layer_msg(mpros_ctx *c, int layer, int8_t *dst, size_t 
         MPROS_CUDA(cudaMemsetAsync(maxv, 0, 4, st));
         if (layer == MPROS_LAYER_GOAL)
         {
-            msg_max_u16_kernel<<<grid_for(n), 256, 0, st>>>(c->goal, n, maxv);
+            msg_max_u16_kernel<<<grid_for(c, n), 256, 0, st>>>(c->goal, n, maxv);
             MPROS_LAUNCH_CHECK(c);
-            msg_scale_u16_kernel<<<grid_for(n), 256, 0, st>>>(c->goal, n, maxv, out);
+            msg_scale_u16_kernel<<<grid_for(c, n), 256, 0, st>>>(c->goal, n, maxv, out);
         }
         else
         {
-            msg_max_f32_kernel<<<grid_for(n), 256, 0, st>>>(c->voronoi, n, maxv);
+            msg_max_f32_kernel<<<grid_for(c, n), 256, 0, st>>>(c->voronoi, n, maxv);
             MPROS_LAUNCH_CHECK(c);
-            msg_scale_f32_kernel<<<grid_for(n), 256, 0, st>>>(c->voronoi, n, maxv, out);
+            msg_scale_f32_kernel<<<grid_for(c, n), 256, 0, st>>>(c->voronoi, n, maxv, out);
         }
         MPROS_LAUNCH_CHECK(c);
     }
@@ -1198,7 +1191,7 @@ extern "C" int mpros_map_point_in_collision(mpros_ctx *c, int layer, const int32
     int32_t *d_ij = static_cast<int32_t *>(c->stage);
     uint8_t *d_out = reinterpret_cast<uint8_t *>(c->stage) + in_bytes;
     MPROS_CUDA(cudaMemcpyAsync(d_ij, ij, in_bytes, cudaMemcpyHostToDevice, c->stream));
-    point_lookup_kernel<<<grid_for(n), 256, 0, c->stream>>>(bits, H, W, pitch, d_ij, n, d_out);
+    point_lookup_kernel<<<grid_for(c, n), 256, 0, c->stream>>>(bits, H, W, pitch, d_ij, n, d_out);
     MPROS_LAUNCH_CHECK(c);
     MPROS_CUDA(cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, c->stream));
     MPROS_CUDA(cudaStreamSynchronize(c->stream));

@@ -75,11 +75,39 @@ struct PlannerView
     int max_iteration;
 };
 
+// Per-query planner workspaces of one (lane, pass): node pools, open lists, closed sets and goal-wavefront windows of every
+// resident team (plan.cu). Owned by the context, freed by mpros_ctx_destroy / mpros_plan_release_workspaces.
+struct PlanScratch
+{
+    char *ws = nullptr;
+    size_t ws_bytes = 0;
+    unsigned int *counter = nullptr;
+    int32_t *todo = nullptr;
+    size_t todo_cap = 0;
+    uint32_t tag_base = 0;
+    unsigned char last_layout[128] = {}; // WarpWorkspaceLayout the bytes were last interpreted with (stale tags could alias)
+};
+constexpr int kPlanPasses = 3; // node-pool size classes
+
+// Developer / tuning switches. Defaults come from the MPROS_* environment, read ONCE in mpros_ctx_create;
+// mpros_ctx_set_option changes them per context afterwards.
+struct Options
+{
+    bool c1_walk = false;      // MPROS_C1_MODE=walk: single-phase footprint kernel
+    int goal_mode = 0;         // MPROS_GOAL_MODE: 0 cluster (16 CTAs when granted), 1 "cluster8", 2 "grid"
+    bool plan_cluster = false; // MPROS_PLAN_MODE=cluster: a team is a CTA pair
+    bool debug = false;        // MPROS_DEBUG: per-pass timing (and the phase profile of the -DMPROS_PROFILE build) on stderr
+};
+
 struct Ctx
 {
     int device = 0;
+    int n_sm = 0; // cudaDevAttrMultiProcessorCount, queried once in mpros_ctx_create; every grid is a multiple of it
     cudaStream_t stream = nullptr;
     uint64_t launches = 0;
+    Options opt;
+    PlanScratch plan_scratch[MPROS_PLAN_LANES][kPlanPasses];
+    int plan_resident[2] = {0, 0}; // resident planner CTAs per SM: [0] CTA teams, [1] CTA-pair teams (occupancy query, cached)
 
     mpros_map_params mp;
     mpros_planner_params pp;
@@ -179,6 +207,15 @@ int ensure_stage(Ctx *c, size_t bytes);
 
 inline int pitch_words(int width) { return ((width + 31) / 32 + 3) & ~3; }
 inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+// grid of a grid-stride kernel: enough CTAs for the work, capped at 16 resident CTAs on every SM of the device
+inline int grid_for(const Ctx *c, size_t work_items, int block = 256)
+{
+    size_t g = (work_items + block - 1) / block;
+    const size_t cap = (size_t)(c->n_sm > 0 ? c->n_sm : 1) * 16;
+    if (g > cap)
+        g = cap;
+    return g < 1 ? 1 : (int)g;
+}
 
 // stage entry points implemented in the other translation units
 int map_build_voronoi(Ctx *c);          // N5-N9, voronoi.cu

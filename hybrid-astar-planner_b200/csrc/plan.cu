@@ -482,7 +482,7 @@ static int rs_batch_impl(mpros_ctx *c, const mpros_rs_params *rp, const double *
     else
         a.rs = rs_config_from_planner(c);
     const int block = 128, warps_per_block = block / 32;
-    int blocks = (int)std::min<size_t>((n + warps_per_block - 1) / warps_per_block, (size_t)148 * 8);
+    int blocks = (int)std::min<size_t>((n + warps_per_block - 1) / warps_per_block, (size_t)c->n_sm * 8);
     size_t nwarps = (size_t)blocks * warps_per_block;
     size_t in_bytes = n * 8 * 8, seg_bytes = n * 15 * 8, traj_bytes = n * (size_t)traj_cap * 5 * 8;
     size_t ws_bytes = nwarps * kTrajCap * 5 * 8;
@@ -582,7 +582,7 @@ extern "C" int mpros_rs_shot_batch_dev(mpros_ctx *c, const double *d_starts5, co
     RsBatchArgs a;
     a.rs = rs_config_from_planner(c);
     const int block = 128, warps_per_block = block / 32;
-    int blocks = (int)std::min<size_t>((n + warps_per_block - 1) / warps_per_block, (size_t)148 * 8);
+    int blocks = (int)std::min<size_t>((n + warps_per_block - 1) / warps_per_block, (size_t)c->n_sm * 8);
     const size_t ws_bytes = (size_t)blocks * warps_per_block * kTrajCap * 5 * 8;
     rc = map_build_unsafe(c); // before the scratch is handed out: the builder uses it for its temporaries
     if (rc)
@@ -630,7 +630,7 @@ extern "C" int mpros_rs_distance_batch(mpros_ctx *c, double rho, const double *a
     cudaStream_t st = c->stream;
     MPROS_CUDA(cudaMemcpyAsync(d_a, a3, n * 24, cudaMemcpyHostToDevice, st));
     MPROS_CUDA(cudaMemcpyAsync(d_b, b3, n * 24, cudaMemcpyHostToDevice, st));
-    int blocks = (int)std::min<size_t>((n * 4 + 127) / 128, (size_t)148 * 16);
+    int blocks = (int)std::min<size_t>((n * 4 + 127) / 128, (size_t)c->n_sm * 16);
     rs_distance_kernel<<<blocks, 128, 0, st>>>(rho, d_a, d_b, (int)n, d_o);
     MPROS_LAUNCH_CHECK(c);
     MPROS_CUDA(cudaMemcpyAsync(out, d_o, n * 8, cudaMemcpyDeviceToHost, st));
@@ -699,8 +699,8 @@ static int expand_launch(mpros_ctx *c, const char *who, const double *start3, co
     a.prims = d_prims;
     a.childs = d_childs;
     a.nchild = d_nchild;
-    // one warp per parent, 4 warps per CTA; grid = a multiple of the 148 SMs (16 resident CTAs each), grid-stride beyond
-    int blocks = (int)std::min<size_t>((n + 3) / 4, (size_t)148 * 16);
+    // one warp per parent, 4 warps per CTA; grid = a multiple of the SM count (16 resident CTAs each), grid-stride beyond
+    int blocks = (int)std::min<size_t>((n + 3) / 4, (size_t)c->n_sm * 16);
     expand_batch_kernel<<<blocks, 128, 0, st>>>(c->view(), c->pv, a);
     MPROS_LAUNCH_CHECK(c);
     return MPROS_OK;
@@ -760,35 +760,22 @@ namespace mpros
 constexpr int kTeamWarps = MPROS_TEAM_WARPS;
 constexpr int kTeamMinBlocks = MPROS_TEAM_MIN_BLOCKS;
 
-struct PlanScratch
-{
-    char *ws = nullptr;
-    size_t ws_bytes = 0;
-    unsigned int *counter = nullptr;
-    int32_t *todo = nullptr;
-    size_t todo_cap = 0;
-    uint32_t tag_base = 0;
-};
-static PlanScratch g_plan_scratch[16][MPROS_PLAN_LANES][3]; // per device, per lane (batches in flight), per pass (node-pool size class)
+static_assert(sizeof(WarpWorkspaceLayout) <= sizeof(PlanScratch::last_layout), "PlanScratch::last_layout too small");
 
 static int plan_pass(mpros_ctx *c, int lane, cudaStream_t stream, PlanBatchArgs &a, int pass, int node_cap, int n_run, const int32_t *d_todo,
                      int max_warps)
 {
-    PlanScratch &S = g_plan_scratch[c->device & 15][lane][pass];
+    PlanScratch &S = c->plan_scratch[lane][pass]; // owned by the context: two contexts never share workspaces
     WarpWorkspaceLayout L = make_layout(node_cap, c->H, c->W);
-    // resident teams: a multiple of the SM count; bounded by the workspace budget. Device queries are cached per device:
-    // a batch submission should cost the host microseconds (cudaGetDeviceProperties alone takes milliseconds).
-    static int sm_count[16] = {}, resident_cta[16] = {}, resident_pair[16] = {};
-    if (!sm_count[c->device & 15])
-        MPROS_CUDA(cudaDeviceGetAttribute(&sm_count[c->device & 15], cudaDevAttrMultiProcessorCount, c->device));
-    const int n_sm = sm_count[c->device & 15];
+    // resident teams: a multiple of the SM count; bounded by the workspace budget. Device queries are cached in the
+    // context: a batch submission should cost the host microseconds (cudaGetDeviceProperties alone takes milliseconds).
+    const int n_sm = c->n_sm;
     // team = one CTA (default) or a cluster of two CTAs on the two SMs of a TPC (MPROS_PLAN_MODE=cluster; plan_team.cuh).
     // Measured on the 16 384-query synthetic batch: CTA teams 1.57 s (296 teams, 6.8-7.5 us per iteration alone, ~11 us with
     // two teams per SM), CTA pairs 2.24 s (148 teams, 8.2-8.6 us per iteration alone AND loaded: no interference between
     // co-resident teams any more, but the two cluster barriers cost ~4 k cycles per iteration). Results are identical.
-    const char *mode_env = std::getenv("MPROS_PLAN_MODE");
-    const bool cluster = mode_env && std::strcmp(mode_env, "cluster") == 0;
-    int &resident = cluster ? resident_pair[c->device & 15] : resident_cta[c->device & 15];
+    const bool cluster = c->opt.plan_cluster;
+    int &resident = c->plan_resident[cluster ? 1 : 0];
     if (!resident)
     {
         if (cluster)
@@ -830,13 +817,11 @@ static int plan_pass(mpros_ctx *c, int lane, cudaStream_t stream, PlanBatchArgs 
         S.tag_base = 0;
     }
     // a different layout re-interprets the same bytes: stale tags could alias, so clear when the layout changes
-    static WarpWorkspaceLayout last_layout[16][MPROS_PLAN_LANES][3];
-    WarpWorkspaceLayout &prev = last_layout[c->device & 15][lane][pass];
-    if (std::memcmp(&prev, &L, sizeof(L)) != 0)
+    if (std::memcmp(S.last_layout, &L, sizeof(L)) != 0)
     {
         MPROS_CUDA(cudaMemsetAsync(S.ws, 0, S.ws_bytes, stream));
         S.tag_base = 0;
-        prev = L;
+        std::memcpy(S.last_layout, &L, sizeof(L));
     }
     MPROS_CUDA(cudaMemsetAsync(S.counter, 0, 4, stream));
     a.L = L;
@@ -845,7 +830,7 @@ static int plan_pass(mpros_ctx *c, int lane, cudaStream_t stream, PlanBatchArgs 
     a.tag_base = S.tag_base;
     a.todo = d_todo;
     a.n_todo = n_run;
-    const bool dbg = std::getenv("MPROS_DEBUG") != nullptr;
+    const bool dbg = c->opt.debug;
     cudaEvent_t e0, e1;
     if (dbg)
     {
@@ -912,7 +897,7 @@ static int plan_batch_dev_impl(mpros_ctx *c, int lane, cudaStream_t stream, cons
     a.stats = d_stats;
     a.rs = rs_config_from_planner(c);
     a.optimal = c->pp.optimal_path;
-    PlanScratch &S = g_plan_scratch[c->device & 15][lane][0];
+    PlanScratch &S = c->plan_scratch[lane][0];
     // pass 1: every query with a small node pool; later passes: only the queries that overflowed, bigger pools
     const long long max_nodes = (long long)(c->pp.max_iteration + 2) * (2 * c->pv.n_steer) + 16;
     // node pools: when every resident team can own a pool for the iteration limit (B200: 296 teams x ~100 MB) each query
@@ -920,7 +905,7 @@ static int plan_batch_dev_impl(mpros_ctx *c, int lane, cudaStream_t stream, cons
     long long caps[3] = {16384, 131072, max_nodes};
     {
         WarpWorkspaceLayout big = make_layout((int)max_nodes, c->H, c->W);
-        const size_t full = big.stride * (size_t)(kTeamMinBlocks * 148);
+        const size_t full = big.stride * (size_t)(kTeamMinBlocks * c->n_sm);
         if (S.ws_bytes >= full) // the lane already owns full-size pools
             caps[0] = max_nodes;
         else
@@ -928,8 +913,8 @@ static int plan_batch_dev_impl(mpros_ctx *c, int lane, cudaStream_t stream, cons
             size_t free_b = 0, total_b = 0;
             MPROS_CUDA(cudaMemGetInfo(&free_b, &total_b));
             size_t have = free_b;
-            for (int k = 0; k < 3; ++k)
-                have += g_plan_scratch[c->device & 15][lane][k].ws_bytes;
+            for (int k = 0; k < kPlanPasses; ++k)
+                have += c->plan_scratch[lane][k].ws_bytes;
             // lane 0 keeps half of the memory free for the caller; the extra lanes (pipelined batches) may use what is left
             if (full < (lane == 0 ? have / 2 : have - have / 8))
                 caps[0] = max_nodes;
@@ -1072,8 +1057,8 @@ extern "C" int mpros_plan_search_tree(mpros_ctx *c, const double *start3, const 
             return cuda_fail(cudaGetLastError(), "cudaMalloc(search tree)", __FILE__, __LINE__);
         }
         size_t blocks = ((size_t)n_exp * P + 255) / 256;
-        if (blocks > 148 * 8)
-            blocks = 148 * 8;
+        if (blocks > (size_t)c->n_sm * 8)
+            blocks = (size_t)c->n_sm * 8;
         search_tree_kernel<<<(unsigned)blocks, 256, 0, st>>>(c->pv, d_trace, n_exp, d_tree);
         c->launches++;
         cudaMemcpyAsync(tree4, d_tree, n_seg * 32, cudaMemcpyDeviceToHost, st);

@@ -917,6 +917,7 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
 
     // ---- Plan() (hybrid_a_star.cpp:682-777) ----
     const int P = 2 * p.n_steer;
+    int bg_dropped = 0; // heap warp: stale roots removed ahead of time in the previous iteration's background phase
     while (init_ok)
     {
         const int it = S.iteration;
@@ -933,7 +934,11 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
             uint32_t bid = lane < nbuf ? S.buf_id[par_prev][lane] : 0u;
             bool bvalid = lane < nbuf;
             if (it > p.max_iteration)
-                flag = 1;
+            {
+                // the reference tests `while (!open_map_.empty())` BEFORE the limit (hybrid_a_star.cpp:702-709), and its
+                // multimap still holds the CLOSE entries this warp dropped from the root in the last background phase
+                flag = (heap.size > 0 || nbuf > 0 || bg_dropped > 0) ? 1 : 2;
+            }
             else
             {
                 if (nbuf == 32)
@@ -1056,6 +1061,7 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                 // still in the background: drop roots that are already CLOSE (stale entries of nodes that were re-inserted
                 // with a smaller g; each costs a full sift-down) and fetch the surviving root's node record, so that the next
                 // pop is an arg-min over shared memory
+                bg_dropped = 0;
                 while (heap.size > 0)
                 {
                     const uint32_t rid = S.heap_id[0];
@@ -1070,6 +1076,7 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                     }
                     unsigned long long fk;
                     heap_pop_warp(heap, fk);
+                    ++bg_dropped;
                     if (is_heap && lane == 0) pf.count(13);
                 }
                 if (heap.size == 0 && lane == 0)

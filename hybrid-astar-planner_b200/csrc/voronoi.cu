@@ -453,16 +453,6 @@ __global__ void __launch_bounds__(256) voronoi_cost_kernel(const uint32_t *__res
     }
 }
 
-static int grid_for(size_t items, int block = 256)
-{
-    size_t g = (items + block - 1) / block;
-    if (g > 148 * 16)
-        g = 148 * 16;
-    if (g < 1)
-        g = 1;
-    return (int)g;
-}
-
 int map_build_voronoi(Ctx *c)
 {
     cudaStream_t st = c->stream;
@@ -481,42 +471,42 @@ int map_build_voronoi(Ctx *c)
     int *d_nreg = tile_count + n_tiles;
 
     // N5
-    ccl_init_kernel<<<grid_for(cells), 256, 0, st>>>(c->ds_bits, H, W, pitch, parent);
+    ccl_init_kernel<<<grid_for(c, cells), 256, 0, st>>>(c->ds_bits, H, W, pitch, parent);
     MPROS_LAUNCH_CHECK(c);
-    ccl_merge_kernel<<<grid_for(cells), 256, 0, st>>>(c->ds_bits, H, W, pitch, parent);
+    ccl_merge_kernel<<<grid_for(c, cells), 256, 0, st>>>(c->ds_bits, H, W, pitch, parent);
     MPROS_LAUNCH_CHECK(c);
     ccl_flatten_rank_kernel<<<n_tiles, 1024, 0, st>>>(parent, cells, local_rank, tile_count);
     MPROS_LAUNCH_CHECK(c);
     scan_tiles_kernel<<<1, 1024, 0, st>>>(tile_count, n_tiles, d_nreg);
     MPROS_LAUNCH_CHECK(c);
-    ccl_region_kernel<<<grid_for(cells), 256, 0, st>>>(parent, cells, local_rank, tile_count, c->region);
+    ccl_region_kernel<<<grid_for(c, cells), 256, 0, st>>>(parent, cells, local_rank, tile_count, c->region);
     MPROS_LAUNCH_CHECK(c);
     MPROS_CUDA(cudaMemcpyAsync(&c->num_regions, d_nreg, sizeof(int), cudaMemcpyDeviceToHost, st));
 
     // N6
-    dt_row_kernel<<<grid_for(cells), 256, 0, st>>>(c->ds_bits, H, W, pitch, c->region, key);
+    dt_row_kernel<<<grid_for(c, cells), 256, 0, st>>>(c->ds_bits, H, W, pitch, c->region, key);
     MPROS_LAUNCH_CHECK(c);
     dt_col_kernel<<<cdiv(W, 32), dim3(32, 32), 0, st>>>(key, H, W);
     MPROS_LAUNCH_CHECK(c);
-    obs_finish_kernel<<<grid_for(cells), 256, 0, st>>>(key, cells, c->obs_dist, c->region);
+    obs_finish_kernel<<<grid_for(c, cells), 256, 0, st>>>(key, cells, c->obs_dist, c->region);
     MPROS_LAUNCH_CHECK(c);
 
     // N7
     size_t words = (size_t)H * ((W + 31) / 32);
     MPROS_CUDA(cudaMemsetAsync(c->edge_bits, 0, (size_t)H * pitch * 4, st));
-    edge_kernel<<<grid_for(words * 32), 256, 0, st>>>(c->ds_bits, c->obs_dist, c->region, H, W, pitch, c->edge_bits);
+    edge_kernel<<<grid_for(c, words * 32), 256, 0, st>>>(c->ds_bits, c->obs_dist, c->region, H, W, pitch, c->edge_bits);
     MPROS_LAUNCH_CHECK(c);
 
     // N8
-    dt_row_kernel<<<grid_for(cells), 256, 0, st>>>(c->edge_bits, H, W, pitch, nullptr, key);
+    dt_row_kernel<<<grid_for(c, cells), 256, 0, st>>>(c->edge_bits, H, W, pitch, nullptr, key);
     MPROS_LAUNCH_CHECK(c);
     dt_col_kernel<<<cdiv(W, 32), dim3(32, 32), 0, st>>>(key, H, W);
     MPROS_LAUNCH_CHECK(c);
-    edge_finish_kernel<<<grid_for(cells), 256, 0, st>>>(key, cells, c->edge_dist);
+    edge_finish_kernel<<<grid_for(c, cells), 256, 0, st>>>(key, cells, c->edge_dist);
     MPROS_LAUNCH_CHECK(c);
 
     // N9
-    voronoi_cost_kernel<<<grid_for(cells), 256, 0, st>>>(c->ds_bits, c->edge_bits, c->obs_dist, c->edge_dist, H, W, pitch,
+    voronoi_cost_kernel<<<grid_for(c, cells), 256, 0, st>>>(c->ds_bits, c->edge_bits, c->obs_dist, c->edge_dist, H, W, pitch,
                                                         c->mp.voro_fallout_rate, c->mp.voro_max_region, c->voronoi);
     MPROS_LAUNCH_CHECK(c);
     return MPROS_OK;

@@ -244,12 +244,21 @@ bool HybridAstar::Plan()
 {
     if (!initialized_)
         return false; // "Planner not properly initialized!"
-    const int cap = 4096;
+    int cap = 4096;
     std::vector<double> paths((size_t)cap * 5);
     int32_t status = 0, len = 0;
     int64_t st[6] = {0, 0, 0, 0, 0, 0};
     double cost = -1;
     check(mpros_plan_batch(map_->ctx(), start_.data(), goal_.data(), 1, &status, &cost, &len, paths.data(), cap, st), "mpros_plan_batch");
+    if (status == MPROS_PLAN_FOUND && len > cap)
+    {
+        // path_ never comes back truncated: the search is deterministic, run it again with room for the whole path
+        cap = len;
+        paths.assign((size_t)cap * 5, 0.0);
+        check(mpros_plan_batch(map_->ctx(), start_.data(), goal_.data(), 1, &status, &cost, &len, paths.data(), cap, st), "mpros_plan_batch");
+        if (len > cap)
+            throw std::runtime_error("mpros_b200::HybridAstar::Plan: path longer than the buffer after the re-run");
+    }
     for (int k = 0; k < 6; ++k)
         stats_[k] = st[k];
     goal_cost_ = cost;

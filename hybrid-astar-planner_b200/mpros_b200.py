@@ -160,6 +160,8 @@ def load_library(path=LIB_PATH):
     L.mpros_plan_batch_wait.argtypes = [vp, i]
     L.mpros_plan_lane_stream.restype = vp
     L.mpros_plan_lane_stream.argtypes = [vp, i]
+    L.mpros_ctx_set_option.argtypes = [vp, C.c_char_p, C.c_char_p]
+    L.mpros_plan_release_workspaces.argtypes = [vp]
     _lib = L
     return L
 
@@ -228,6 +230,13 @@ class Context:
     def _check(self, rc):
         if rc != 0:
             raise MprosError("mpros error %d: %s" % (rc, self.L.mpros_last_error_string().decode()))
+
+    def set_option(self, key, value=None):
+        """mpros_ctx_set_option: "c1_mode", "goal_mode", "plan_mode", "debug" (value None = default)."""
+        self._check(self.L.mpros_ctx_set_option(self.h, key.encode(), None if value is None else str(value).encode()))
+
+    def release_workspaces(self):
+        self._check(self.L.mpros_plan_release_workspaces(self.h))
 
     def close(self):
         if getattr(self, "h", None):
@@ -407,7 +416,9 @@ class Context:
         return prims, childs, nchild
 
     # ---- planner ----
-    def plan_batch(self, starts3, goals3, path_cap=256):
+    def plan_batch(self, starts3, goals3, path_cap=256, truncate_ok=False):
+        """mpros_plan_batch. A path longer than path_cap is an error (the C entry stores only the first path_cap points
+        and reports the full length in path_len) unless truncate_ok is set or no paths are asked for (path_cap == 0)."""
         s = np.ascontiguousarray(starts3, dtype=np.float64).reshape(-1, 3)
         g = np.ascontiguousarray(goals3, dtype=np.float64).reshape(-1, 3)
         nq = len(s)
@@ -418,6 +429,9 @@ class Context:
         stats = np.zeros((nq, 6), dtype=np.int64)
         self._check(self.L.mpros_plan_batch(self.h, s.ctypes.data, g.ctypes.data, nq, status.ctypes.data, cost.ctypes.data,
                                             plen.ctypes.data, paths.ctypes.data if path_cap else None, path_cap, stats.ctypes.data))
+        if path_cap and not truncate_ok and nq and int(plen.max()) > path_cap:
+            raise MprosError("plan_batch: a path has %d points, path_cap is %d (MPROS_ERR_CAPACITY); re-run with a larger path_cap"
+                             % (int(plen.max()), path_cap))
         return {"status": status, "cost": cost, "path_len": plen, "paths": paths, "iterations": stats[:, 0],
                 "primitives": stats[:, 1], "rs_shots": stats[:, 2], "collision_checks": stats[:, 3],
                 "goal_map_cells": stats[:, 4], "nodes_inserted": stats[:, 5]}

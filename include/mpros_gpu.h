@@ -3,8 +3,9 @@
  *
  * This is the drop-in boundary: plain pointers and sizes, opaque context handle, int status returns,
  * caller-owned buffers, one CUDA stream per context (plus one per extra plan lane), a context is not
- * thread-safe. The planner's per-query workspaces belong to the (device, lane) pair and are shared by the
- * contexts of a process: one mpros_plan_batch* call at a time per device and lane. There is NO CPU
+ * thread-safe. Everything a context allocates (map layers, staging areas, the planner's per-query workspaces of
+ * every lane) belongs to that context and is freed by mpros_ctx_destroy; two contexts on one device share
+ * nothing and may run concurrently from two host threads. There is NO CPU
  * fallback behind any entry point: without a CUDA device every call fails with MPROS_ERR_CUDA.
  *
  * Each entry point names the reference interface it replaces (file:line in Runningchauncey/Hybrid-Astar-Planner).
@@ -110,6 +111,15 @@ MPROS_API void *mpros_ctx_stream(mpros_ctx *ctx);
 MPROS_API int mpros_ctx_synchronize(mpros_ctx *ctx);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 MPROS_API uint64_t mpros_ctx_launch_count(mpros_ctx *ctx);
+
+/* Developer / tuning switches of one context. The MPROS_* environment variables give the defaults and are read ONCE, in
+ * mpros_ctx_create; this call changes a switch afterwards (value NULL or "" = default). Keys and values:
+ *   "c1_mode"   "2phase" (default) | "walk"               footprint kernel: pre-classified two-phase form / plain probe walk
+ *   "goal_mode" "cluster" (default) | "cluster8" | "grid"  N4 wavefront: 16-CTA cluster when granted / 8-CTA cluster / cooperative grid
+ *   "plan_mode" "team" (default) | "cluster"               planner team = one CTA / a CTA pair on the two SMs of a TPC
+ *   "debug"     "0" (default) | "1"                        per-pass timing on stderr
+ * Results never depend on these switches (tests/ hold every mode to the same outputs). No reference counterpart. */
+MPROS_API int mpros_ctx_set_option(mpros_ctx *ctx, const char *key, const char *value);
 
 /* ---- configuration ------------------------------------------------------------------------------- */
 MPROS_API void mpros_map_params_default(mpros_map_params *p);         /* nav_map.cpp:27-34 defaults       */
@@ -277,6 +287,10 @@ MPROS_API int mpros_plan_batch_submit_dev(mpros_ctx *ctx, int lane, const double
                                           int32_t *d_status, double *d_cost, int32_t *d_path_len, double *d_paths,
                                           int path_cap, int64_t *d_stats);
 MPROS_API int mpros_plan_batch_wait(mpros_ctx *ctx, int lane);
+/* Frees the planner workspaces of every lane of this context (node pools, open lists, closed sets, goal-wavefront windows:
+ * up to ~33 GB per lane at the 100 000-iteration limit on a B200) after waiting for the batches in flight. They are owned by
+ * the context, re-created by the next mpros_plan_batch* call and freed by mpros_ctx_destroy. */
+MPROS_API int mpros_plan_release_workspaces(mpros_ctx *ctx);
 /* cudaStream_t of a lane (NULL before its first submit), e.g. to record events or order other device work behind a batch */
 MPROS_API void *mpros_plan_lane_stream(mpros_ctx *ctx, int lane);
 

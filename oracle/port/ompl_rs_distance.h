@@ -8,7 +8,7 @@
 //
 // PARITY UNPINNED: OMPL is absent from /root/reference and from this image, the reference holds no
 // test vector for it. The only available pin is a cross-check against the reference's own RS::RSCurve
-// with zero penalties (tests/test_oracle_rs.py).
+// with zero penalties (tests/test_oracle_port.py (test_ompl_standin_*)).
 #pragma once
 #include <cfloat>
 #include <cmath>

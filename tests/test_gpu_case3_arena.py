@@ -84,14 +84,14 @@ def test_case3_goal_map_full_resolution(gpu_ctx_factory):
         for gx, gy in [(40.0, 40.0), (5.0, 5.0), (70.0, 21.0), (79.5, 0.5)]:
             pm.update_goal(gx, gy)
             want = pm.layer("goal")
-            os.environ.pop("MPROS_GOAL_MODE", None)
+            ctx.set_option("goal_mode", "cluster")
             ctx.update_goal(gx, gy)
             a = ctx.layer("goal")
-            os.environ["MPROS_GOAL_MODE"] = "grid"
+            ctx.set_option("goal_mode", "grid")
             ctx.update_goal(gx, gy)
             b = ctx.layer("goal")
             assert np.array_equal(a, want), "cluster kernel, goal (%.1f, %.1f): %d mismatches" % (gx, gy, int((a != want).sum()))
             assert np.array_equal(b, want), "grid kernel, goal (%.1f, %.1f)" % (gx, gy)
     finally:
-        os.environ.pop("MPROS_GOAL_MODE", None)
+        ctx.set_option("goal_mode", None)
         pm.close()

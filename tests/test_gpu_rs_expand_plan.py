@@ -231,7 +231,7 @@ def test_plan_full_gpu_vs_reference(reflib, gpu_ctx_factory, name, ds, num_steer
 
 
 def test_cluster_mode_gives_identical_plans(reflib, gpu_ctx_factory, monkeypatch):
-    """MPROS_PLAN_MODE=cluster: a team is a pair of CTAs on the two SMs of a TPC (search CTA + heuristic CTA exchanging the
+    """plan_mode=cluster (mpros_ctx_set_option): a team is a pair of CTAs on the two SMs of a TPC (search CTA + heuristic CTA exchanging the
     children's symmetry images and heuristics through distributed shared memory). Same searches, bit for bit."""
     ctx = gpu_ctx_factory()
     rm, params, m = make_pair(reflib, ctx, "parking4", num_steer=5, goal=(10.0, -2.0))
@@ -244,11 +244,11 @@ def test_cluster_mode_gives_identical_plans(reflib, gpu_ctx_factory, monkeypatch
     cand = np.stack([inf["ox"] + u * c - v * s, inf["oy"] + u * s + v * c, rng.uniform(-np.pi, np.pi, 6000)], 1)
     free = cand[rp.collision4(cand) == 0]
     starts, goals = free[:200], free[200:400]
-    monkeypatch.delenv("MPROS_PLAN_MODE", raising=False)
+    ctx.set_option("plan_mode", "team")
     a = ctx.plan_batch(starts, goals, path_cap=256)
-    monkeypatch.setenv("MPROS_PLAN_MODE", "cluster")
+    ctx.set_option("plan_mode", "cluster")
     b = ctx.plan_batch(starts, goals, path_cap=256)
-    monkeypatch.delenv("MPROS_PLAN_MODE", raising=False)
+    ctx.set_option("plan_mode", None)
     assert (a["status"] == 1).sum() > 50
     for key in ["status", "cost", "path_len", "iterations", "primitives", "rs_shots", "paths"]:
         assert np.array_equal(a[key], b[key]), key

@@ -71,11 +71,11 @@ def test_collision_verdicts_bit_exact_4m_poses(syn, port):
     assert 0.2 < want.mean() < 0.4
     assert np.array_equal(want, got), "%d verdict mismatches of %d" % (int((want != got).sum()), len(poses))
     # the single-phase kernel (every pose through the probe walk) gives the same verdicts
-    os.environ["MPROS_C1_MODE"] = "walk"
+    ctx.set_option("c1_mode", "walk")
     try:
         walk = ctx.collision_check(poses)
     finally:
-        os.environ.pop("MPROS_C1_MODE", None)
+        ctx.set_option("c1_mode", None)
     assert np.array_equal(want, walk)
 
 
@@ -186,7 +186,7 @@ def test_batches_in_flight_match_the_synchronous_call(syn):
 
 
 def test_goal_map_cluster_and_grid_kernels_agree(syn, port):
-    """N4 at 1024 x 1024: the cluster/DSMEM wavefront (default) and the cooperative grid kernel (MPROS_GOAL_MODE=grid) both
+    """N4 at 1024 x 1024: the cluster/DSMEM wavefront (default) and the cooperative grid kernel (goal_mode=grid) both
     reproduce generateGoalMap bit for bit, for goals in the middle, in a corner (window clipped) and on an obstacle."""
     ctx = syn[0]
     static = ctx.layer("static")
@@ -197,13 +197,13 @@ def test_goal_map_cluster_and_grid_kernels_agree(syn, port):
         for gx, gy in goals:
             port.update_goal(gx, gy)
             want = port.layer("goal")
-            os.environ.pop("MPROS_GOAL_MODE", None)
+            ctx.set_option("goal_mode", "cluster")
             ctx.update_goal(gx, gy)
             a = ctx.layer("goal")
-            os.environ["MPROS_GOAL_MODE"] = "grid"
+            ctx.set_option("goal_mode", "grid")
             ctx.update_goal(gx, gy)
             b = ctx.layer("goal")
             assert np.array_equal(a, want), "cluster kernel, goal (%.1f, %.1f): %d mismatches" % (gx, gy, int((a != want).sum()))
             assert np.array_equal(b, want), "grid kernel, goal (%.1f, %.1f)" % (gx, gy)
     finally:
-        os.environ.pop("MPROS_GOAL_MODE", None)
+        ctx.set_option("goal_mode", None)
