@@ -262,6 +262,25 @@ __global__ void __launch_bounds__(128) rs_distance_kernel(double rho, const doub
     }
 }
 
+// RS::PathFunction::path1..12 (rs_curve.cpp:353-599) for n normalised goals: one thread per goal
+__global__ void __launch_bounds__(128) rs_word_kernel(int word, const double *__restrict__ xyphi, int n, double *__restrict__ segs,
+                                                      int32_t *__restrict__ nseg)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+    {
+        RsPath p;
+        rs_formula(word, xyphi[3 * k], xyphi[3 * k + 1], xyphi[3 * k + 2], p);
+        nseg[k] = p.n;
+        for (int t = 0; t < 5; ++t)
+        {
+            const bool have = t < p.n;
+            segs[15 * k + 3 * t] = have ? p.s[t].len : 0.0;
+            segs[15 * k + 3 * t + 1] = have ? (double)p.s[t].steer : 0.0;
+            segs[15 * k + 3 * t + 2] = have ? (double)p.s[t].dir : 0.0;
+        }
+    }
+}
+
 // E1-E5 for a batch of parents against the context's goal map (mpros_map_update_goal) with a FRESH closed set per
 // parent (only the start/goal seeds), i.e. what HybridAstar::expandNode does right after initialize().
 struct ExpandArgs
@@ -634,6 +653,34 @@ extern "C" int mpros_rs_distance_batch(mpros_ctx *c, double rho, const double *a
     rs_distance_kernel<<<blocks, 128, 0, st>>>(rho, d_a, d_b, (int)n, d_o);
     MPROS_LAUNCH_CHECK(c);
     MPROS_CUDA(cudaMemcpyAsync(out, d_o, n * 8, cudaMemcpyDeviceToHost, st));
+    MPROS_CUDA(cudaStreamSynchronize(st));
+    return MPROS_OK;
+}
+
+extern "C" int mpros_rs_word_batch(mpros_ctx *c, int word, const double *xyphi, size_t n, double *segs, int32_t *nseg)
+{
+    if (!c || word < 1 || word > 12 || (n && (!xyphi || !segs || !nseg)) || n > (size_t)INT32_MAX)
+    {
+        set_error("mpros_rs_word_batch: NULL / invalid argument (word is 1..12)");
+        return MPROS_ERR_INVALID;
+    }
+    if (n == 0)
+        return MPROS_OK;
+    MPROS_CUDA(cudaSetDevice(c->device));
+    const size_t in_b = align_up(n * 24, 256), seg_b = align_up(n * 120, 256);
+    int rc = ensure_stage(c, in_b + seg_b + n * 4 + 256);
+    if (rc)
+        return rc;
+    char *base = static_cast<char *>(c->stage);
+    double *d_in = (double *)base, *d_seg = (double *)(base + in_b);
+    int32_t *d_n = (int32_t *)(base + in_b + seg_b);
+    cudaStream_t st = c->stream;
+    MPROS_CUDA(cudaMemcpyAsync(d_in, xyphi, n * 24, cudaMemcpyHostToDevice, st));
+    int blocks = (int)std::min<size_t>((n + 127) / 128, (size_t)c->n_sm * 16);
+    rs_word_kernel<<<blocks, 128, 0, st>>>(word - 1, d_in, (int)n, d_seg, d_n);
+    MPROS_LAUNCH_CHECK(c);
+    MPROS_CUDA(cudaMemcpyAsync(segs, d_seg, n * 120, cudaMemcpyDeviceToHost, st));
+    MPROS_CUDA(cudaMemcpyAsync(nseg, d_n, n * 4, cudaMemcpyDeviceToHost, st));
     MPROS_CUDA(cudaStreamSynchronize(st));
     return MPROS_OK;
 }

@@ -30,7 +30,18 @@ NavMap::NavMap(int device)
     check(mpros_ctx_create(device, &ctx_), "mpros_ctx_create");
     mpros_map_params_default(&params_);
 }
+NavMap::NavMap(ParamServer &nh, int device) : NavMap(device)
+{
+#ifdef MPROS_FACADE_ROS
+    nh_ = nh;
+    map_sub = nh.subscribe("map", 1, &NavMap::getOccupancyMap, this); // nav_map.cpp:18
+#else
+    (void)nh;
+#endif
+}
 NavMap::~NavMap() { mpros_ctx_destroy(ctx_); }
+
+void NavMap::getOccupancyMap(const OccupancyGrid::ConstPtr &map_msg) { setOccupancyMap(*map_msg); }
 
 void NavMap::config(const ParamServer &nh)
 {
@@ -58,16 +69,64 @@ void NavMap::refresh()
     x_max_ = i.x_max, x_min_ = i.x_min, y_max_ = i.y_max, y_min_ = i.y_min;
 }
 
-void NavMap::setOccupancyMap(const OccupancyGridLite &og)
+void NavMap::setOccupancyMap(const OccupancyGrid &og)
 {
-    if (og.stamp_nsec == 0) // "is initial map" -> ignored (nav_map.cpp:48-52)
+    if (grid_stamp_nsec(og) == 0) // "is initial map" -> ignored (nav_map.cpp:48-52)
         return;
-    double yaw = yaw_from_quaternion(og.origin_qx, og.origin_qy, og.origin_qz, og.origin_qw);
-    check(mpros_map_set_occupancy(ctx_, og.data.data(), (int)og.width, (int)og.height, (double)og.resolution, og.origin_x, og.origin_y, yaw),
-          "mpros_map_set_occupancy");
+#ifdef MPROS_FACADE_ROS
+    const double qx = og.info.origin.orientation.x, qy = og.info.origin.orientation.y, qz = og.info.origin.orientation.z,
+                 qw = og.info.origin.orientation.w;
+    const int width = (int)og.info.width, height = (int)og.info.height;
+    const double res = (double)og.info.resolution, ox = og.info.origin.position.x, oy = og.info.origin.position.y;
+#else
+    const double qx = og.origin_qx, qy = og.origin_qy, qz = og.origin_qz, qw = og.origin_qw;
+    const int width = (int)og.width, height = (int)og.height;
+    const double res = (double)og.resolution, ox = og.origin_x, oy = og.origin_y;
+#endif
+    const double yaw = yaw_from_quaternion(qx, qy, qz, qw);
+    check(mpros_map_set_occupancy(ctx_, og.data.data(), width, height, res, ox, oy, yaw), "mpros_map_set_occupancy");
+    origin_q_[0] = qx, origin_q_[1] = qy, origin_q_[2] = qz, origin_q_[3] = qw;
     goal_cache_ok_ = voro_cache_ok_ = false;
     refresh();
 }
+
+// vecToMsg (nav_map.cpp:654-691): the scaled int8 data come from the device, the geometry from the public members
+OccupancyGrid NavMap::layerMsg(int layer, bool is_original)
+{
+    OccupancyGrid msg;
+    size_t n = 0;
+    if (get_map_)
+        check(mpros_map_layer_msg(ctx_, layer, nullptr, 0, &n), "mpros_map_layer_msg");
+#ifdef MPROS_FACADE_ROS
+    msg.header.frame_id = "map";
+    if (!get_map_ || n == 0)
+        return msg;
+    msg.info.height = is_original ? map_height_orig_ : map_height_;
+    msg.info.width = is_original ? map_width_orig_ : map_width_;
+    msg.info.resolution = is_original ? map_resolution_orig_ : map_resolution_;
+    msg.info.origin.position.x = map_origin_x_;
+    msg.info.origin.position.y = map_origin_y_;
+    msg.info.origin.orientation.x = origin_q_[0], msg.info.origin.orientation.y = origin_q_[1];
+    msg.info.origin.orientation.z = origin_q_[2], msg.info.origin.orientation.w = origin_q_[3];
+#else
+    msg.frame_id = "map";
+    if (!get_map_ || n == 0)
+        return msg;
+    msg.height = is_original ? map_height_orig_ : map_height_;
+    msg.width = is_original ? map_width_orig_ : map_width_;
+    msg.resolution = (float)(is_original ? map_resolution_orig_ : map_resolution_);
+    msg.origin_x = map_origin_x_, msg.origin_y = map_origin_y_;
+    msg.origin_qx = origin_q_[0], msg.origin_qy = origin_q_[1], msg.origin_qz = origin_q_[2], msg.origin_qw = origin_q_[3];
+#endif
+    msg.data.resize(n);
+    check(mpros_map_layer_msg(ctx_, layer, msg.data.data(), n, &n), "mpros_map_layer_msg");
+    return msg;
+}
+OccupancyGrid NavMap::getStaticMapMsg() { return layerMsg(MPROS_LAYER_STATIC, false); }
+OccupancyGrid NavMap::getGoalMapMsg() { return layerMsg(MPROS_LAYER_GOAL, false); }
+OccupancyGrid NavMap::getVoroMapMsg() { return layerMsg(MPROS_LAYER_VORONOI, false); }
+OccupancyGrid NavMap::getStaticOrigMapMsg() { return layerMsg(MPROS_LAYER_STATIC_ORIG, true); }
+OccupancyGrid NavMap::getInflationOrigMapMsg() { return layerMsg(MPROS_LAYER_INFLATE_ORIG, true); }
 
 void NavMap::updateGoal(const double &x, const double &y)
 {
@@ -171,6 +230,24 @@ std::vector<PathPoint> RSCurve::getTrajectory()
     }
     return out;
 }
+namespace PathFunction
+{
+static thread_local mpros_ctx *g_ctx = nullptr;
+void bind(mpros_ctx *ctx) { g_ctx = ctx; }
+Path word(int k, const Point &pt)
+{
+    if (!g_ctx)
+        throw MprosFailure("RS::PathFunction: no context bound (RS::PathFunction::bind)");
+    const double in[3] = {pt.x, pt.y, pt.phi};
+    double segs[15];
+    int32_t n = 0;
+    check(mpros_rs_word_batch(g_ctx, k, in, 1, segs, &n), "mpros_rs_word_batch");
+    Path out;
+    for (int t = 0; t < n; ++t)
+        out.push_back(PathSeg{segs[3 * t], (Steer)(int)segs[3 * t + 1], (Direc)(int)segs[3 * t + 2]});
+    return out;
+}
+} // namespace PathFunction
 } // namespace RS
 
 // ---- HybridAstar ------------------------------------------------------------------------------------------------------
@@ -179,6 +256,37 @@ HybridAstar::HybridAstar(const std::vector<double> &start_pt, const std::vector<
 {
     config(nh);
     initialize(start_pt, goal_pt, map);
+}
+HybridAstar::HybridAstar(const std::vector<double> &start_pt, const std::vector<double> &goal_pt, NavMap &map, Visualizer &vis,
+                         const ParamServer &nh)
+    : map_(&map), vis_(&vis)
+{
+    config(nh);
+    initialize(start_pt, goal_pt, map);
+}
+
+void HybridAstar::setFootprint()
+{
+    // footprint_m_, footprint_longi_ and num_checking_step are derived from the vehicle parameters and map_resolution_orig_
+    // inside mpros_planner_config; calling it again re-derives them for the current map
+    if (!map_)
+        throw MprosFailure("HybridAstar::setFootprint: no map bound");
+    check(mpros_planner_config(map_->ctx(), &pp_), "mpros_planner_config");
+}
+
+bool HybridAstar::genRSPath(const double &x, const double &y, const double &yaw, int direction, double steer)
+{
+    if (!configured_ || goal_.size() < 3)
+        return false;
+    const double dx = x - goal_[0], dy = y - goal_[1];
+    if (!(dx * dx + dy * dy < pp_.analytic_solution_range * pp_.analytic_solution_range)) // hybrid_a_star.cpp:869
+        return false;
+    const double s5[5] = {x, y, yaw, (double)direction, steer};
+    double segs[15], cost = 0;
+    int32_t nseg = 0, npts = 0;
+    uint8_t hit = 1;
+    check(mpros_rs_shot_batch(map_->ctx(), s5, goal_.data(), 1, segs, &nseg, &cost, nullptr, 0, &npts, &hit), "mpros_rs_shot_batch");
+    return hit == 0;
 }
 
 void HybridAstar::config(const ParamServer &nh)
@@ -203,11 +311,11 @@ void HybridAstar::config(const ParamServer &nh)
     nh.param<double>(p + "path_point_distance", pp_.path_point_distance, 0.2);
     nh.param<int>(p + "steering_discretization", pp_.steering_discretization, 3);
     nh.param<int>(p + "max_iteration", pp_.max_iteration, 10000);
-    int optimal = 0, inter = 1;
-    nh.param<int>(p + "optimal_path", optimal, 0);
-    nh.param<int>(p + "interpolation_enable", inter, 1);
-    pp_.optimal_path = optimal;
-    pp_.interpolation_enable = inter;
+    bool optimal = false, inter = true; // bool parameters in the reference (hybrid_a_star.cpp:158-161)
+    nh.param<bool>(p + "optimal_path", optimal, false);
+    nh.param<bool>(p + "interpolation_enable", inter, true);
+    pp_.optimal_path = optimal ? 1 : 0;
+    pp_.interpolation_enable = inter ? 1 : 0;
     yaw_resol_ = 2 * M_PI / pp_.yaw_discretization;
     if (!map_)
         throw MprosFailure("HybridAstar::config: no map bound (setFootprint reads map_->map_resolution_orig_)");
@@ -270,18 +378,20 @@ bool HybridAstar::Plan()
     return true;
 }
 
-std::vector<std::array<double, 4>> HybridAstar::getSearchTree()
+std::vector<TreeSegment> HybridAstar::getSearchTree()
 {
-    std::vector<std::array<double, 4>> tree;
+    std::vector<TreeSegment> tree;
     if (!initialized_)
         return tree;
     int32_t status = 0;
     double cost = -1;
     size_t n = 0;
     check(mpros_plan_search_tree(map_->ctx(), start_.data(), goal_.data(), &status, &cost, nullptr, 0, &n), "mpros_plan_search_tree");
+    static_assert(sizeof(TreeSegment) == 4 * sizeof(double), "a search-tree segment is four packed doubles");
     tree.resize(n);
     if (n)
-        check(mpros_plan_search_tree(map_->ctx(), start_.data(), goal_.data(), &status, &cost, &tree[0][0], n, &n), "mpros_plan_search_tree");
+        check(mpros_plan_search_tree(map_->ctx(), start_.data(), goal_.data(), &status, &cost, reinterpret_cast<double *>(tree.data()), n, &n),
+              "mpros_plan_search_tree");
     return tree;
 }
 

@@ -6,27 +6,56 @@
 // so the mpros_planner node can swap the library in. Every method that computes forwards to the
 // CUDA library; there is no CPU implementation here.
 //
-// ROS is absent in this build environment, so the two ROS types the interfaces touch are mirrored by small PODs
-// (OccupancyGridLite for nav_msgs::OccupancyGrid, ParamServer for ros::NodeHandle::param). With -DMPROS_FACADE_ROS the
-// real types are used instead (INTEGRATION.md shows the three-line adapter).
+// Two build modes:
+//   * default (headless): ROS is absent in this build environment, so the ROS types the interfaces touch are mirrored by small
+//     PODs (OccupancyGridLite for nav_msgs::OccupancyGrid, ParamServer for ros::NodeHandle::param, a PathPoint with the
+//     reference's member names, std::array<double, 4> for Eigen::Vector4d, an empty Visualizer);
+//   * -DMPROS_FACADE_ROS (inside the catkin workspace): the REAL types are used - ros::NodeHandle, nav_msgs::OccupancyGrid,
+//     the reference's own mpros_utils/pathpoint.h PathPoint and mpros_utils/visualizer.h Visualizer, Eigen::Vector4d - and
+//     host/compat/{mpros_navigation_map/nav_map.h, mpros_algorithm/hybrid_a_star.h, mpros_rs_path/rs_curve.h} pull the classes
+//     into the global namespace, so main_planner.cpp compiles unchanged (tests/test_facade_compile.py compiles the node's
+//     main() against it).
 #pragma once
 #include <cmath>
 #include <cstdint>
 #include <array>
 #include <map>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
 #include "mpros_gpu.h"
 
+#ifdef MPROS_FACADE_ROS
+#include <Eigen/Core>
+
+#include "nav_msgs/OccupancyGrid.h"
+#include "ros/ros.h"
+#include "mpros_utils/pathpoint.h" // the reference's own boundary record
+class NavMap;                      // mpros_utils/visualizer.h names NavMap in publishCostmap (the compat headers alias it)
+#ifndef MPROS_FACADE_NO_VISUALIZER
+#include "mpros_utils/visualizer.h"
+#endif
+#endif
+
 namespace mpros_b200
 {
 
-// nav_msgs::OccupancyGrid, the fields NavMap::setOccupancyMap reads (nav_map.cpp:42-131)
+#ifdef MPROS_FACADE_ROS
+typedef ros::NodeHandle ParamServer;
+typedef nav_msgs::OccupancyGrid OccupancyGrid;
+typedef ::PathPoint PathPoint;
+typedef Eigen::Vector4d TreeSegment; // {next_x, next_y, curr_x, curr_y}, hybrid_a_star.cpp:1114-1164
+typedef ::Visualizer Visualizer;
+inline uint64_t grid_stamp_nsec(const OccupancyGrid &og) { return og.header.stamp.toNSec(); }
+#else
+// nav_msgs::OccupancyGrid, the fields NavMap::setOccupancyMap reads (nav_map.cpp:42-131) and vecToMsg writes (:654-691)
 struct OccupancyGridLite
 {
+    typedef std::shared_ptr<const OccupancyGridLite> ConstPtr;
     uint64_t stamp_nsec = 1; // header.stamp; 0 = "initial map", ignored (nav_map.cpp:48-52)
+    std::string frame_id;    // header.frame_id ("map" in every message NavMap builds)
     uint32_t width = 0, height = 0;
     float resolution = 0; // float32 in the message
     double origin_x = 0, origin_y = 0;
@@ -39,6 +68,8 @@ struct OccupancyGridLite
         origin_qw = std::cos(yaw * 0.5);
     }
 };
+typedef OccupancyGridLite OccupancyGrid;
+inline uint64_t grid_stamp_nsec(const OccupancyGrid &og) { return og.stamp_nsec; }
 
 // ros::NodeHandle::param<T>(key, var, default) over a flat key -> double store
 class ParamServer
@@ -65,29 +96,41 @@ private:
     bool ok_ = true;
 };
 
-// mpros_utils/pathpoint.h:7-35 (the boundary record of getNewPath / pathInCollision)
+// mpros_utils/pathpoint.h:7-35 (the boundary record of getNewPath / pathInCollision), same member names
 struct PathPoint
 {
     PathPoint() {}
-    PathPoint(double x, double y, double yaw) : x_(x), y_(y), yaw_(yaw) {}
-    double getX() const { return x_; }
-    double getY() const { return y_; }
+    PathPoint(const double &x, const double &y, const double &yaw) : yaw_(yaw) { point_[0] = x, point_[1] = y; }
+    double getX() const { return point_[0]; }
+    double getY() const { return point_[1]; }
     double getYaw() const { return yaw_; }
-    double x_ = 0, y_ = 0, yaw_ = 0, curv_ = 0, direc_ = 1, steering_ = 0;
+    std::array<double, 2> point_ = {{0, 0}};
+    double yaw_ = 0, curv_ = 0, vel_ = 0, accel_ = 0, jerk_ = 0;
+    double direc_ = 1, steering_ = 0;
+    bool fixed_ = false;
     bool is_cusp_ = false;
     double dist_ = 0; // distance from start to this point
+    double time_ = 0;
 };
+typedef std::array<double, 4> TreeSegment; // Eigen::Vector4d {next_x, next_y, curr_x, curr_y}
+struct Visualizer // mpros_utils/visualizer.h: only a reference is taken (hybrid_a_star.cpp:11-20, 66-68)
+{
+};
+#endif
 
 class NavMap
 {
 public:
-    NavMap(int device = 0);
+    NavMap(int device = 0); // nav_map.cpp:10-12 (plus the CUDA device the layers live on)
+    // nav_map.cpp:14-19: keeps the handle and, with the real ros::NodeHandle, subscribes getOccupancyMap to "map"
+    explicit NavMap(ParamServer &nh, int device = 0);
     ~NavMap();
     NavMap(const NavMap &) = delete;
     NavMap &operator=(const NavMap &) = delete;
 
-    void config(const ParamServer &nh);                     // nav_map.cpp:25-35
-    void setOccupancyMap(const OccupancyGridLite &og);      // nav_map.cpp:42-162
+    void config(const ParamServer &nh);                            // nav_map.cpp:25-35
+    void getOccupancyMap(const OccupancyGrid::ConstPtr &map_msg);  // nav_map.cpp:37-40 (the "map" subscriber callback)
+    void setOccupancyMap(const OccupancyGrid &og);                 // nav_map.cpp:42-162
     void updateGoal(const double &x, const double &y);      // nav_map.h:204-210
     bool pointInCollision(const int &i, const int &j);      // nav_map.cpp:249-257
     bool pointInCollisionOrig(const int &i, const int &j);  // nav_map.cpp:259-267
@@ -135,6 +178,13 @@ public:
     std::vector<int8_t> getStaticMap() const;
     std::vector<int8_t> getStaticOrigMap() const;
     std::vector<int8_t> getInflationOrigMap() const;
+    // nav_map.cpp:693-716 -> vecToMsg (:654-691): the messages main_planner.cpp:216-220 publishes; data scaled on the device
+    // (mpros_map_layer_msg), header.frame_id "map", geometry of the original or the down-sampled grid, origin orientation
+    OccupancyGrid getStaticMapMsg();
+    OccupancyGrid getGoalMapMsg();
+    OccupancyGrid getVoroMapMsg();
+    OccupancyGrid getStaticOrigMapMsg();
+    OccupancyGrid getInflationOrigMapMsg();
 
     mpros_ctx *ctx() const { return ctx_; }
 
@@ -152,7 +202,13 @@ private:
     void refresh();
     template <typename T>
     std::vector<T> download(int layer, size_t n) const;
+    OccupancyGrid layerMsg(int layer, bool is_original);
     mpros_ctx *ctx_ = nullptr;
+    double origin_q_[4] = {0, 0, 0, 1}; // map_origin_q_ (x, y, z, w) as the last occupancy grid carried it
+#ifdef MPROS_FACADE_ROS
+    ros::NodeHandle nh_;
+    ros::Subscriber map_sub;
+#endif
     mpros_map_params params_;
     // host mirrors for the single-cell getters
     std::vector<int> goal_cache_;
@@ -179,6 +235,11 @@ struct PathSeg
     double GetLength() const { return value; }
     Steer GetSteer() const { return steer; }
     Direc GetDirec() const { return direc; }
+    // rs_curve_basic.h:94-96
+    std::string GetManuever() const
+    {
+        return "Steer: " + std::to_string(GetSteer()) + "; Direction: " + std::to_string(GetDirec()) + "; Value: " + std::to_string(GetLength());
+    }
 };
 typedef std::vector<PathSeg> Path;
 
@@ -209,6 +270,13 @@ public:
     std::vector<std::vector<double>> GetTraj();        // rs_curve.cpp:280-284 {x, y, yaw, steer*steer_angle, direc}
     std::vector<PathPoint> getTrajectory();
     Path getOptimalPath() const { return optimal_path_; }
+    std::string GetManuever(const Path &path) // rs_curve.cpp:286-294
+    {
+        std::string manuever;
+        for (auto &seg : path)
+            manuever += seg.GetManuever() + "\n";
+        return manuever;
+    }
 
 private:
     mpros_ctx *ctx_;
@@ -218,13 +286,33 @@ private:
     Path optimal_path_;
     std::vector<std::vector<double>> traj_;
 };
+// RS::PathFunction::path1..12 (rs_curve.h:248-334, rs_curve.cpp:353-599) evaluated on the device (mpros_rs_word_batch).
+// The reference's free functions take only the point; here the context travels in a thread-local set by bind().
+namespace PathFunction
+{
+void bind(mpros_ctx *ctx);
+Path word(int k, const Point &pt); // k = 1..12
+inline Path path1(const Point &pt) { return word(1, pt); }
+inline Path path2(const Point &pt) { return word(2, pt); }
+inline Path path3(const Point &pt) { return word(3, pt); }
+inline Path path4(const Point &pt) { return word(4, pt); }
+inline Path path5(const Point &pt) { return word(5, pt); }
+inline Path path6(const Point &pt) { return word(6, pt); }
+inline Path path7(const Point &pt) { return word(7, pt); }
+inline Path path8(const Point &pt) { return word(8, pt); }
+inline Path path9(const Point &pt) { return word(9, pt); }
+inline Path path10(const Point &pt) { return word(10, pt); }
+inline Path path11(const Point &pt) { return word(11, pt); }
+inline Path path12(const Point &pt) { return word(12, pt); }
+} // namespace PathFunction
 } // namespace RS
 
 class HybridAstar
 {
 public:
     HybridAstar() = default;
-    // compact constructor: config, then initialize (hybrid_a_star.cpp:11-20)
+    // compact constructor: config, then initialize (hybrid_a_star.cpp:11-20); the Visualizer is only kept, as in the reference
+    HybridAstar(const std::vector<double> &start_pt, const std::vector<double> &goal_pt, NavMap &map, Visualizer &vis, const ParamServer &nh);
     HybridAstar(const std::vector<double> &start_pt, const std::vector<double> &goal_pt, NavMap &map, const ParamServer &nh);
     void config(const ParamServer &nh);                                                                  // :120-188
     void initialize(const std::vector<double> &start_pt, const std::vector<double> &goal_pt, NavMap &map); // :52-118
@@ -233,7 +321,7 @@ public:
     std::vector<std::vector<double>> getPath() { return path_; } // {x, y, yaw, steer, direction}
     // hybrid_a_star.cpp:1114-1164: leaf segments {next_x, next_y, curr_x, curr_y} of every evaluated primitive (re-plans
     // the query on the device with the expansion trace switched on)
-    std::vector<std::array<double, 4>> getSearchTree();
+    std::vector<TreeSegment> getSearchTree();
     std::vector<PathPoint> getNewPath();                          // hybrid_a_star.cpp:848-851: setPath's up-sampled path (:814-838)
     bool pathInCollision(const std::vector<std::vector<double>> &path); // :404-416
     bool pathInCollision(const std::vector<PathPoint> &path);           // :418-430
@@ -242,6 +330,10 @@ public:
     bool footPrintInCollision(const double &x, const double &y, const double &yaw);
     bool footPrintInCollision2(const double &x, const double &y, const double &yaw);
     bool footPrintInCollision3(const double &x, const double &y, const double &yaw);
+    void setFootprint(); // :190-206: footprint_m_ / footprint_longi_ from the configured vehicle (part of mpros_planner_config)
+    // :853-900 for a free-standing pose: Reeds-Shepp shot to the goal if it lies within analytic_solution_range; true = a
+    // collision-free path exists (the planner's own shots run inside Plan() on the device)
+    bool genRSPath(const double &x, const double &y, const double &yaw, int direction = 1, double steer = 0.0);
     int calIndex(const int &idx_i, const int &idx_j, const int &idx_yaw, const double &direc); // :281-290
     int yawToIdx(const double &yaw);                                                          // :292-302
     void regularYaw(double &yaw);                                                             // :266-279
@@ -254,6 +346,7 @@ public:
 
 private:
     NavMap *map_ = nullptr;
+    Visualizer *vis_ = nullptr;
     mpros_planner_params pp_;
     bool configured_ = false, initialized_ = false;
     std::vector<double> start_, goal_;

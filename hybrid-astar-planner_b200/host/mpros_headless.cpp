@@ -162,11 +162,20 @@ int main(int argc, char **argv)
         }
         std::vector<double> start = {atof(argv[2]), atof(argv[3]), atof(argv[4])}, goal = {atof(argv[5]), atof(argv[6]), atof(argv[7])};
 
-        NavMap map;
+        // main_planner.cpp:179-229: NavMap(nh) + config, the "map" callback, the five published layers, updateGoal, the
+        // five-argument planner constructor, Plan()
+        NavMap map(nh);
+        Visualizer vis;
         map.config(nh);
-        map.setOccupancyMap(og);
+        map.getOccupancyMap(std::make_shared<const OccupancyGridLite>(og));
         map.updateGoal(goal[0], goal[1]);
-        HybridAstar planner(start, goal, map, nh);
+        struct NamedMsg
+        {
+            const char *name;
+            OccupancyGridLite msg;
+        } msgs[5] = {{"static", map.getStaticMapMsg()}, {"voronoi", map.getVoroMapMsg()}, {"static_orig", map.getStaticOrigMapMsg()},
+                     {"inflate_orig", map.getInflationOrigMapMsg()}, {"goal", map.getGoalMapMsg()}};
+        HybridAstar planner(start, goal, map, vis, nh);
         bool ok = planner.Plan();
         std::vector<std::vector<double>> path = planner.getPath();
         bool collides = ok ? planner.pathInCollision(path) : false;
@@ -179,9 +188,23 @@ int main(int argc, char **argv)
         std::printf("], \"new_path\": [");
         std::vector<PathPoint> np = ok ? planner.getNewPath() : std::vector<PathPoint>();
         for (size_t k = 0; k < np.size(); ++k)
-            std::printf("%s[%.17g, %.17g, %.17g, %.17g, %.17g, %.17g, %d, %.17g]", k ? ", " : "", np[k].x_, np[k].y_, np[k].yaw_, np[k].curv_, np[k].direc_,
+            std::printf("%s[%.17g, %.17g, %.17g, %.17g, %.17g, %.17g, %d, %.17g]", k ? ", " : "", np[k].getX(), np[k].getY(), np[k].getYaw(), np[k].curv_, np[k].direc_,
                         np[k].steering_, np[k].is_cusp_ ? 1 : 0, np[k].dist_);
-        std::printf("]}\n");
+        std::printf("], \"msgs\": {");
+        for (int k = 0; k < 5; ++k)
+        {
+            // FNV-1a-64 of msg.data, with the geometry vecToMsg writes (nav_map.cpp:654-691)
+            unsigned long long hsh = 1469598103934665603ull;
+            for (int8_t v : msgs[k].msg.data)
+                hsh = (hsh ^ (unsigned char)v) * 1099511628211ull;
+            std::printf("%s\"%s\": {\"frame_id\": \"%s\", \"height\": %u, \"width\": %u, \"resolution\": %.9g, \"origin\": [%.17g, %.17g], \"n\": %zu, "
+                        "\"fnv\": \"%016llx\"}",
+                        k ? ", " : "", msgs[k].name, msgs[k].msg.frame_id.c_str(), msgs[k].msg.height, msgs[k].msg.width, (double)msgs[k].msg.resolution,
+                        msgs[k].msg.origin_x, msgs[k].msg.origin_y, msgs[k].msg.data.size(), hsh);
+        }
+        // main_planner.cpp:259: the searched tree handed to the visualiser; :243 pathInCollision on the PathPoint path
+        std::printf("}, \"search_tree_segments\": %zu, \"new_path_in_collision\": %d, \"rs_shot_from_start\": %d}\n", planner.getSearchTree().size(),
+                    (ok && planner.pathInCollision(np)) ? 1 : 0, planner.genRSPath(start[0], start[1], start[2]) ? 1 : 0);
         return 0;
     }
     catch (const std::exception &e)

@@ -230,6 +230,10 @@ MPROS_API int mpros_rs_shot_batch(mpros_ctx *ctx, const double *starts5, const d
 /* The same shot with every buffer in device memory (no trajectory output); asynchronous on the context's stream. */
 MPROS_API int mpros_rs_shot_batch_dev(mpros_ctx *ctx, const double *d_starts5, const double *d_goals3, size_t n, double *d_segs,
                                       int32_t *d_nseg, double *d_cost, int32_t *d_npts, uint8_t *d_verdicts);
+/* RS::PathFunction::path1 .. path12 (rs_curve.h:248-334, rs_curve.cpp:353-599): the closed-form word `word` (1..12) for n
+ * goals already normalised into the start frame and divided by the radius. xyphi: double[3n]; segs: double[15n] = 5 x
+ * {|value|, steer, direction} as the PathSeg constructor stores them (rs_curve_basic.h:84-88), zero-filled beyond nseg[k]. */
+MPROS_API int mpros_rs_word_batch(mpros_ctx *ctx, int word, const double *xyphi, size_t n, double *segs, int32_t *nseg);
 /* RSStateSpace(rho).setStart/setEnd/getCost (rs_statespace.h:37-54): OMPL-equivalent Reeds-Shepp distance. */
 MPROS_API int mpros_rs_distance_batch(mpros_ctx *ctx, double rho, const double *a3, const double *b3, size_t n, double *out);
 

@@ -7,6 +7,7 @@
 //
 // What it wraps (reference file:line):
 //   NavMap::config / setOccupancyMap / updateGoal          nav_map.cpp:25-35, 42-162, nav_map.h:204-210
+//   NavMap::pointInCollision{,Orig,INFLOrig}               nav_map.cpp:249-277
 //   HybridAstar ctor / config / initialize / Plan          hybrid_a_star.cpp:11-20, 52-188, 682-777
 //   HybridAstar::footPrintInCollision4 / expandNode        hybrid_a_star.cpp:617-680, 304-402
 //   RS::RSCurve::FindOptimalPath / GetTraj / GetLength     rs_curve.cpp:111-163, 280-284, 275-278
@@ -90,6 +91,16 @@ extern "C"
         out_d[4] = m->map_origin_yaw_;
         out_d[5] = m->map_origin_sin_;
         out_d[6] = m->map_origin_cos_;
+    }
+    // batch of cells through NavMap::pointInCollision (mpros_layer 1) / pointInCollisionOrig (0) / pointInCollisionINFLOrig (2), nav_map.cpp:249-277
+    void ref_map_points_in_collision(void *h, int layer, const int *ij, long n, uint8_t *out)
+    {
+        NavMap *m = static_cast<NavMap *>(h);
+        for (long k = 0; k < n; ++k)
+        {
+            const int i = ij[2 * k], j = ij[2 * k + 1];
+            out[k] = layer == 1 ? m->pointInCollision(i, j) : layer == 0 ? m->pointInCollisionOrig(i, j) : m->pointInCollisionINFLOrig(i, j);
+        }
     }
     // layer ids: 0 static_map_orig_ (i8, orig) 1 static_map_ (i8) 2 inflate_map_orig_ (i8, orig)
     // 3 goal_cost_map_ (i32) 4 obs_dist_ (i32) 5 region_ (i32) 6 isedge_ (u8) 7 edge_dist_ (i32)
@@ -333,6 +344,9 @@ extern "C"
         stats_out[9] = t3 - t2;
         stats_out[10] = planner.time_rs_shot_.count();
         stats_out[11] = planner.time_colli_.count();
+        // why Plan() returned (hybrid_a_star.cpp:756-776), in enum mpros_plan_status codes: 1 goal found, 0 iteration limit
+        // (the loop broke with entries left in open_map_), -1 open set empty, -2 planner not initialised
+        stats_out[12] = !planner.initialized_ ? -2.0 : ok ? 1.0 : planner.open_map_.empty() ? -1.0 : 0.0;
         int n = (int)path.size() < path_cap ? (int)path.size() : path_cap;
         for (int k = 0; k < n; ++k)
             for (int c = 0; c < 5; ++c)
@@ -449,6 +463,27 @@ extern "C"
             for (int c = 0; c < 5; ++c)
                 traj_out[5 * k + c] = traj[k][c];
         return (int)traj.size();
+    }
+
+    // RS::PathFunction::path1..12 (rs_curve.cpp:353-599) on n normalised goals {x, y, phi}: seg_out n x 5 x 3 {len, steer, dir}
+    void ref_rs_word(int word, const double *xyphi, long n, double *seg_out, int *nseg)
+    {
+        typedef RS::Path (*Fn)(const RS::Point &);
+        static const Fn fns[12] = {RS::PathFunction::path1, RS::PathFunction::path2, RS::PathFunction::path3, RS::PathFunction::path4,
+                                   RS::PathFunction::path5, RS::PathFunction::path6, RS::PathFunction::path7, RS::PathFunction::path8,
+                                   RS::PathFunction::path9, RS::PathFunction::path10, RS::PathFunction::path11, RS::PathFunction::path12};
+        for (long k = 0; k < n; ++k)
+        {
+            RS::Path path = fns[word - 1](RS::Point(xyphi[3 * k], xyphi[3 * k + 1], xyphi[3 * k + 2]));
+            nseg[k] = (int)path.size();
+            for (int t = 0; t < 5; ++t)
+            {
+                const bool have = t < (int)path.size();
+                seg_out[15 * k + 3 * t + 0] = have ? path[t].GetLength() : 0.0;
+                seg_out[15 * k + 3 * t + 1] = have ? (double)path[t].GetSteer() : 0.0;
+                seg_out[15 * k + 3 * t + 2] = have ? (double)path[t].GetDirec() : 0.0;
+            }
+        }
     }
 
     // RSStateSpace(rho).getCost() — OMPL stand-in, PARITY UNPINNED (oracle/port/ompl_rs_distance.h)

@@ -107,6 +107,7 @@ class RefLib:
         L.ref_map_layer.restype = C.c_long
         L.ref_map_layer.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.ref_map_point_in_collision.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.ref_map_points_in_collision.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_void_p]
         L.ref_planner_create.restype = C.c_void_p
         L.ref_planner_create.argtypes = [C.c_void_p]
         L.ref_planner_destroy.argtypes = [C.c_void_p]
@@ -158,6 +159,14 @@ class RefMap:
         d = {k: int(v) for k, v in zip(keys_i, oi)}
         d.update({k: float(v) for k, v in zip(keys_d, od)})
         return d
+
+    def points_in_collision(self, name, ij):
+        """NavMap::pointInCollision ('static') / pointInCollisionOrig ('static_orig') / pointInCollisionINFLOrig
+        ('inflate_orig') for a batch of cells ij = [[i, j], ...] (nav_map.cpp:249-277)."""
+        ij = np.ascontiguousarray(ij, dtype=np.int32).reshape(-1, 2)
+        out = np.zeros(len(ij), dtype=np.uint8)
+        self.lib.L.ref_map_points_in_collision(self.h, LAYERS[name][0], ij.ctypes.data, len(ij), out.ctypes.data)
+        return out
 
     def layer(self, name):
         lid, dt, orig = LAYERS[name]
@@ -227,13 +236,13 @@ class RefPlanner:
 
 
 STAT_KEYS = ["plan_ok", "initialized", "goal_g", "n_primitives", "num_nodes", "path_len", "goal_path_len",
-             "t_update_goal", "t_ctor", "t_plan", "t_rs_shot", "t_colli"]
+             "t_update_goal", "t_ctor", "t_plan", "t_rs_shot", "t_colli", "status"]
 
 
 def ref_plan_query(rmap, start, goal, update_goal=True, path_cap=4096):
     s = np.array(start, dtype=np.float64)
     g = np.array(goal, dtype=np.float64)
-    stats = np.zeros(12, dtype=np.float64)
+    stats = np.zeros(len(STAT_KEYS), dtype=np.float64)
     path = np.zeros((path_cap, 5), dtype=np.float64)
     rmap.lib.L.ref_plan_query(rmap.h, s.ctypes.data, g.ctypes.data, int(update_goal), stats.ctypes.data, path.ctypes.data, path_cap)
     d = dict(zip(STAT_KEYS, stats.tolist()))
@@ -291,3 +300,12 @@ def ref_rs_distance(lib, rho, a3, b3):
     a = np.array(a3, dtype=np.float64)
     b = np.array(b3, dtype=np.float64)
     return lib.L.ref_rs_distance(rho, a.ctypes.data, b.ctypes.data)
+
+
+def ref_rs_word(lib, word, xyphi):
+    """RS::PathFunction::path<word> (1..12, rs_curve.cpp:353-599) for normalised goals [n, 3]: (segs [n, 5, 3], nseg [n])."""
+    p = np.ascontiguousarray(xyphi, dtype=np.float64).reshape(-1, 3)
+    segs = np.zeros((len(p), 5, 3), dtype=np.float64)
+    nseg = np.zeros(len(p), dtype=np.int32)
+    lib.L.ref_rs_word(C.c_int(word), C.c_void_p(p.ctypes.data), C.c_long(len(p)), C.c_void_p(segs.ctypes.data), C.c_void_p(nseg.ctypes.data))
+    return segs, nseg

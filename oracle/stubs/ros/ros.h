@@ -54,6 +54,8 @@ namespace ros
         }
         template <typename... A>
         Subscriber subscribe(A &&...) { return Subscriber(); }
+        template <typename M, typename... A> // subscribe<Msg>(topic, queue, callback)
+        Subscriber subscribe(const std::string &, A &&...) { return Subscriber(); }
         template <typename M, typename... A>
         Publisher advertise(A &&...) { return Publisher(); }
     };

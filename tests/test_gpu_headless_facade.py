@@ -59,3 +59,28 @@ def test_headless_driver_matches_golden_plan(tmp_path, ci):
         want = z["newpath_%d" % ci]
         assert newp.shape == want.shape
         assert np.allclose(newp, want, rtol=0, atol=1e-7)
+
+    # the five map messages main_planner.cpp:216-220 publishes (NavMap::get*MapMsg -> vecToMsg, nav_map.cpp:654-716), built by
+    # the facade from mpros_map_layer_msg: geometry as the reference writes it, data byte-exact (FNV-1a-64) against the
+    # unmodified reference; the Voronoi message only where the canonical field equals the reference's (case 0)
+    m = refapi.load_map(name)
+    H, W = m["occupancy"].shape
+    for layer in ["static", "voronoi", "static_orig", "inflate_orig", "goal"]:
+        g = r["msgs"][layer]
+        assert g["frame_id"] == "map" and (g["height"], g["width"]) == (H, W) and g["n"] == H * W
+        assert abs(g["resolution"] - m["resolution"]) < 1e-6 and g["origin"] == [m["origin"][0], m["origin"][1]]
+    if os.path.exists(refapi.REF_SO):
+        params = refapi.shipped_params(m["free_thresh"], m["occupied_thresh"], ds=ds, num_steer=num_steer)
+        rm = refapi.RefMap(refapi.RefLib(), params)
+        rm.set_occupancy(m["occupancy"], m["resolution"], m["origin"])
+        rm.update_goal(goal[0], goal[1])
+        for layer in ["static", "static_orig", "inflate_orig", "goal"] + (["voronoi"] if ci == 0 else []):
+            data, _ = refapi.ref_layer_msg(rm, layer)
+            h = 1469598103934665603
+            for b in np.asarray(data, dtype=np.int8).view(np.uint8).tolist():
+                h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+            assert r["msgs"][layer]["fnv"] == "%016x" % h, layer
+        rm.close()
+    # HybridAstar::getSearchTree() -> vis.PublishSearchedTree (main_planner.cpp:259): leaf_num segments per evaluated primitive
+    assert r["search_tree_segments"] == r["n_primitives"] * int(np.ceil(2.0 / 0.1))
+    assert r["new_path_in_collision"] == 0 and r["rs_shot_from_start"] in (0, 1)

@@ -321,3 +321,33 @@ def test_rs_shot_batch_device_buffers_match_host_buffers(gpu_ctx_factory):
     assert np.array_equal(ver.cpu().numpy(), want["verdicts"]) and 0.05 < want["verdicts"].mean() < 0.95
     assert np.array_equal(cost.cpu().numpy(), want["cost"]) and np.array_equal(npts.cpu().numpy(), want["npts"])
     assert np.array_equal(nseg.cpu().numpy(), want["nseg"])
+
+
+def test_rs_words_equal_reference_path_functions(reflib, gpu_ctx_factory):
+    """RS::PathFunction::path1..12 (rs_curve.cpp:353-599) through mpros_rs_word_batch: segment count, steer and direction
+    exact, |value| <= 1e-12 relative (NaN where the reference yields NaN: candidates are filtered later, rs_curve.cpp:99-109)."""
+    import ctypes as C
+
+    ctx = gpu_ctx_factory()
+    rng = np.random.default_rng(21)
+    n = 4000
+    pts = np.stack([rng.uniform(-6, 6, n), rng.uniform(-6, 6, n), rng.uniform(-np.pi, np.pi, n)], axis=1)
+    pts[:50, 1] = 0.0   # degenerate geometry: goals on the axis, zero heading change
+    pts[50:100, 2] = 0.0
+    ctx.L.mpros_rs_word_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    for word in range(1, 13):
+        want_seg, want_n = refapi.ref_rs_word(reflib, word, pts)
+        segs = np.zeros((n, 5, 3))
+        nseg = np.zeros(n, dtype=np.int32)
+        ctx._check(ctx.L.mpros_rs_word_batch(ctx.h, word, pts.ctypes.data, n, segs.ctypes.data, nseg.ctypes.data))
+        assert np.array_equal(nseg, want_n), "word %d: segment counts differ" % word
+        assert np.array_equal(np.isnan(segs), np.isnan(want_seg)), "word %d: NaN pattern differs" % word
+        fin = ~np.isnan(want_seg[:, :, 0])
+        # steer / direction: exact unless the value is an exact-arithmetic zero decided by the last ulp (direction flips at 0)
+        tiny = np.abs(want_seg[:, :, 0]) < 1e-9
+        same_sd = (segs[:, :, 1:] == want_seg[:, :, 1:]).all(axis=2) | tiny | ~fin
+        assert same_sd.all(), "word %d: %d steer/direction mismatches" % (word, int((~same_sd).sum()))
+        a, b = segs[:, :, 0][fin], want_seg[:, :, 0][fin]
+        assert np.allclose(a, b, rtol=1e-12, atol=1e-12), "word %d: max |dvalue| %.3g" % (word, float(np.abs(a - b).max()))
+    with pytest.raises(Exception):
+        ctx._check(ctx.L.mpros_rs_word_batch(ctx.h, 13, pts.ctypes.data, n, segs.ctypes.data, nseg.ctypes.data))

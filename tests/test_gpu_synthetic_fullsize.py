@@ -96,6 +96,106 @@ def test_sampled_plans_equal_restatement(syn, port):
             assert np.allclose(g["paths"][k, : g["path_len"][k]], o["path"], rtol=0, atol=1e-8)
 
 
+GOLDEN = os.path.join(ROOT, "tests", "golden", "synthetic_plans.npz")
+
+
+@pytest.fixture(scope="module")
+def golden(syn):
+    """tests/golden/synthetic_plans.npz (made by tests/golden/make_synthetic_golden.py in the container that holds the
+    reference): the restatement on all 16 384 queries, the UNMODIFIED reference on 511 sampled queries plus every non-FOUND
+    one, and the cells where the reference's order-dependent Voronoi field differs from the canonical one."""
+    if not os.path.exists(GOLDEN):
+        pytest.skip("tests/golden/synthetic_plans.npz missing")
+    z = np.load(GOLDEN)
+    ctx, params, occ, starts, goals = syn
+    # the fixture belongs to exactly this query set
+    assert int(z["nq"]) == NQ and float(z["starts_sum"]) == float(starts.sum()) and float(z["goals_sum"]) == float(goals.sum())
+    return z
+
+
+def test_all_16384_plans_equal_restatement(syn, golden):
+    """EVERY query of the headline batch against the CPU restatement (which the golden file pins to the reference on 544 of
+    them): status, iteration count, primitives, Reeds-Shepp shots, path length exact, cost <= 1e-9 relative."""
+    ctx, params, occ, starts, goals = syn
+    g = ctx.plan_batch(starts, goals, path_cap=128)
+    z = golden
+    same = (g["status"] == z["port_status"]) & (g["iterations"] == z["port_iterations"]) & (g["primitives"] == z["port_primitives"]) & \
+           (g["rs_shots"] == z["port_shots"]) & (g["path_len"] == z["port_path_len"])
+    found = (g["status"] == 1) & (z["port_status"] == 1)
+    rel = np.zeros(NQ)
+    rel[found] = np.abs(g["cost"][found] - z["port_cost"][found]) / np.abs(z["port_cost"][found])
+    same &= rel <= 1e-9
+    bad = np.nonzero(~same)[0]
+    print("headline batch vs restatement: %d of %d queries differ %s; status counts GPU %s" % (
+        len(bad), NQ, bad[:16].tolist(), dict(zip(*np.unique(g["status"], return_counts=True)))))
+    for q in bad[:8]:
+        print("  query %d: status %d/%d iterations %d/%d primitives %d/%d shots %d/%d cost %.9g/%.9g" % (
+            q, g["status"][q], z["port_status"][q], g["iterations"][q], z["port_iterations"][q], g["primitives"][q], z["port_primitives"][q],
+            g["rs_shots"][q], z["port_shots"][q], g["cost"][q], z["port_cost"][q]))
+    assert np.array_equal(g["status"], z["port_status"]), "status differs for queries %s" % np.nonzero(g["status"] != z["port_status"])[0][:16]
+    # libm vs libdevice: a Reeds-Shepp candidate tie decided by the last ulp can send a search down an equal-cost branch
+    assert len(bad) <= 8, "%d queries differ from the restatement" % len(bad)
+
+
+def _reference_voronoi(ctx, z):
+    v = ctx.layer("voronoi").copy().ravel()
+    v[z["voro_idx"]] = z["voro_val"]
+    return v.reshape(ctx.layer("voronoi").shape)
+
+
+def test_headline_queries_equal_the_reference_with_its_voronoi_field(syn, golden):
+    """SURVEY 9.4 mode (i): the reference's voronoi_value_map_ injected, every sampled query (511 + all 33 non-FOUND ones)
+    must reproduce HybridAstar::Plan() of the unmodified reference: status, tree_.size(), goal g, raw path."""
+    ctx, params, occ, starts, goals = syn
+    z = golden
+    canon = ctx.layer("voronoi").copy()
+    idx = z["ref_idx"]
+    try:
+        ctx.upload_voronoi(_reference_voronoi(ctx, z))
+        g = ctx.plan_batch(starts[idx], goals[idx], path_cap=128)
+    finally:
+        ctx.upload_voronoi(canon)
+    n_bad = 0
+    for k, q in enumerate(idx):
+        ok = g["status"][k] == z["ref_status"][k] and g["primitives"][k] == z["ref_primitives"][k]
+        if ok and z["ref_status"][k] == 1:
+            ok = abs(g["cost"][k] - z["ref_cost"][k]) <= 1e-9 * abs(z["ref_cost"][k]) and g["path_len"][k] == z["ref_path_len"][k]
+            n = int(min(z["ref_path_len"][k], z["ref_paths"].shape[1], 128))
+            ok = ok and np.allclose(g["paths"][k, :n], z["ref_paths"][k, :n], rtol=0, atol=1e-8)
+        if not ok:
+            n_bad += 1
+            print("  query %d: status %d/%d primitives %d/%d cost %.9g/%.9g" % (q, g["status"][k], z["ref_status"][k], g["primitives"][k],
+                                                                                  z["ref_primitives"][k], g["cost"][k], z["ref_cost"][k]))
+    print("mode (i), reference Voronoi injected: %d of %d queries differ from the reference (%d FOUND, %d iteration limit, %d open set empty)" % (
+        n_bad, len(idx), int((z["ref_status"] == 1).sum()), int((z["ref_status"] == 0).sum()), int((z["ref_status"] == -1).sum())))
+    assert np.array_equal(g["status"], z["ref_status"]), "status mismatch"
+    assert n_bad <= 2  # Reeds-Shepp ulp ties (see above); 0 measured
+
+
+def test_headline_queries_full_gpu_against_the_reference(syn, golden):
+    """SURVEY 9.4 mode (ii): everything computed on the GPU (canonical Voronoi field: 23 % of this map's free cells sit in
+    L1-distance tie areas where the reference's region_ depends on its heap order). Reported as a distribution."""
+    ctx, params, occ, starts, goals = syn
+    z = golden
+    idx = z["ref_idx"]
+    g = ctx.plan_batch(starts[idx], goals[idx], path_cap=128)
+    both = (g["status"] == 1) & (z["ref_status"] == 1)
+    d = (g["cost"][both] - z["ref_cost"][both]) / z["ref_cost"][both]
+    edges = [-1, -1e-1, -1e-2, -1e-3, -1e-4, 1e-4, 1e-3, 1e-2, 1e-1, 10]
+    hist = np.histogram(d, bins=edges)[0]
+    n_status = int((g["status"] != z["ref_status"]).sum())
+    print("mode (ii), fully GPU: status mismatches %d of %d; relative cost difference (GPU - reference) / reference: median %.3g, "
+          "mean %.3g, min %.3g, max %.3g; histogram over %s: %s; |d| > 5 %% (other homotopy class): %d" % (
+              n_status, len(idx), np.median(d), d.mean(), d.min(), d.max(), edges, hist.tolist(), int((np.abs(d) > 0.05).sum())))
+    assert n_status <= 3            # 1 measured with the restatement: query 1946 runs into the limit on the canonical field
+    assert abs(np.median(d)) < 1e-3 and abs(d.mean()) < 5e-3  # no bias: an equally valid Voronoi field, not a worse planner
+    assert (np.abs(d) <= 1e-4).sum() >= 0.15 * len(d)
+    # every path the GPU returns is collision-free for the reference's own footprint test (bit-exact verdicts)
+    ok = np.nonzero(g["status"] == 1)[0]
+    poses = np.concatenate([g["paths"][k, : min(g["path_len"][k], 128), :3] for k in ok])
+    assert not ctx.collision_check(poses).any()
+
+
 def test_full_batch_properties(syn):
     ctx, params, occ, starts, goals = syn
     a = ctx.plan_batch(starts, goals, path_cap=128)

@@ -192,3 +192,50 @@ def test_footprint_preclassification_rules_hold_for_the_reference_arithmetic():
     assert not want[free].any(), "%d 'surely free' poses collide for the reference" % int(want[free].sum())
     assert want[hit].all(), "%d 'sure hit' poses are free for the reference" % int((want[hit] == 0).sum())
     pm.close()
+
+
+def test_restatement_is_pinned_to_the_reference_on_the_headline_config():
+    """BASELINE.json configs[4] (synthetic 8192^2 grid, ds = 8, bench.py's seeded queries): with the reference's own Voronoi
+    field (rebuilt from the canonical one + the recorded differences) the restatement must reproduce HybridAstar::Plan() of
+    the unmodified reference (golden: tests/golden/synthetic_plans.npz, made by make_synthetic_golden.py from oracle/_ref)
+    on a sample that includes an iteration-limit query and an open-set-empty one; and the file's own refv_* records (the
+    same comparison on all 544 recorded queries, evaluated when the file was made) must show no difference."""
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "hybrid-astar-planner_b200"))
+    import bench
+    import synthetic
+
+    z = np.load(os.path.join(GOLD, "synthetic_plans.npz"))
+    assert np.array_equal(z["refv_status"], z["ref_status"]) and np.array_equal(z["refv_primitives"], z["ref_primitives"])
+    found = z["ref_status"] == 1
+    assert np.array_equal(z["refv_cost"][found], z["ref_cost"][found])
+    assert len(z["ref_idx"]) >= 512 and set(np.nonzero(z["port_status"] != 1)[0]) <= set(z["ref_idx"])
+    occ = synthetic.synthetic_occupancy()
+    params = bench.shipped_params()
+    pm = portapi.PortMap(portapi.PortLib(), params)
+    pm.set_occupancy(occ, synthetic.SYN_RES, [0.0, 0.0, 0.0])
+    pp = portapi.PortPlanner(pm)
+    starts, goals = synthetic.synthetic_queries(int(z["nq"]), pp.collision4, pm.layer("static"), synthetic.SYN_RES * synthetic.SYN_DS,
+                                                bench.EXTENT, synthetic.SYN_QUERY_SEED)
+    assert float(starts.sum()) == float(z["starts_sum"]) and float(goals.sum()) == float(z["goals_sum"])
+    v = pm.layer("voronoi").copy().ravel()
+    v[z["voro_idx"]] = z["voro_val"]
+    pm.set_voronoi(v)
+    idx = z["ref_idx"]
+    cheap = np.nonzero(z["ref_primitives"] < 60000)[0]
+    sample = list(cheap[:: max(1, len(cheap) // 12)][:12])
+    sample.append(int(np.nonzero(z["ref_status"] == 0)[0][0]))   # runs into max_iteration
+    sample.append(int(np.nonzero(z["ref_status"] == -1)[0][0]))  # open set empty
+    for k in sample:
+        q = int(idx[k])
+        pm.update_goal(goals[q][0], goals[q][1])
+        o = pp.plan(starts[q], goals[q], path_cap=128)
+        assert int(o["status"]) == int(z["ref_status"][k]) and int(o["n_primitives"]) == int(z["ref_primitives"][k]), "query %d" % q
+        if o["status"] == 1:
+            assert o["goal_g"] == z["ref_cost"][k]
+            n = int(z["ref_path_len"][k])
+            assert int(o["path_len"]) == n and np.array_equal(o["path"][:n], z["ref_paths"][k, :n])
+    pm.close()
