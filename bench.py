@@ -194,11 +194,13 @@ def _cpu_worker_plan(job):
     starts, goals = job
     t0 = time.perf_counter()
     ok = prims = 0
+    per_query = []
     for s, g in zip(starts, goals):
         r = refapi.ref_plan_query(_W["rm"], s, g)  # updateGoal + ctor (dense state) + Plan(), main_planner.cpp:225-229
         ok += int(r["plan_ok"])
         prims += int(r["n_primitives"])
-    return time.perf_counter() - t0, ok, prims, len(starts), _W["t_pre"]
+        per_query.append((int(r["plan_ok"]), int(r["n_primitives"]), float(r["goal_g"]), int(r["status"])))
+    return time.perf_counter() - t0, ok, prims, len(starts), _W["t_pre"], per_query
 
 
 class CpuArm:
@@ -227,7 +229,7 @@ class CpuArm:
         t = max(r[0] for r in res)
         n = sum(r[3] for r in res)
         return {"plans_per_sec": n / t, "expansions_per_sec": sum(r[2] for r in res) / 6.0 / t, "solved": sum(r[1] for r in res),
-                "n": n, "preprocess_s": max(r[4] for r in res)}
+                "n": n, "preprocess_s": max(r[4] for r in res), "per_query": [q for r in res for q in r[5]]}
 
     def rs_rate(self, st5, g3, cfg):
         res = self.pool.map(_cpu_worker_rs, [(a, b, cfg) for a, b in zip(np.array_split(st5, self.cores), np.array_split(g3, self.cores))])
@@ -244,16 +246,29 @@ class CpuArm:
         self.shm.unlink()
 
 
-def usable_cores():
-    """All host cores, limited by memory: the reference allocates a dense H'*W'*36*2 state per query (~1.8 GB at
-    1024^2) on top of its map copy."""
-    cores = os.cpu_count() or 1
+def usable_cores(per_process_bytes=3.5e9):
+    """(processes to run, nproc, processes the memory allows): all host cores, limited by memory - the reference allocates
+    a dense H'*W'*36*2 state per query (~1.8 GB at 1024^2) on top of its map copy."""
+    nproc = os.cpu_count() or 1
+    by_mem = nproc
     try:
         avail = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
-        cores = max(1, min(cores, int(avail * 0.8 / 3.5e9)))
+        by_mem = max(1, int(avail * 0.8 / per_process_bytes))
     except Exception:
         pass
-    return cores
+    return max(1, min(nproc, by_mem)), nproc, by_mem
+
+
+def plan_config(lanes, scaling="weak", world=1):
+    """config of the plan workload, identical for the GPU arm and the reference arm (the reference arm times a seeded
+    sample of the same query set; what the sample was is stated in its cpu_baseline.sample)."""
+    cfg = {"workload": workload_text("plan"), "path_cap": PATH_CAP, "batches_in_flight": lanes,
+           "l2_policy": "per-query working sets (node pool, open list, closed set, goal wavefront) live in a ~110 MB-per-team HBM workspace, 296 teams (>> L2 in aggregate); map layers are L2-resident by design"}
+    if scaling == "strong":
+        cfg["queries_total"] = QUERIES_PER_GPU
+    else:
+        cfg["queries_per_gpu"] = QUERIES_PER_GPU
+    return cfg
 
 
 def run_reference(args):
@@ -261,7 +276,7 @@ def run_reference(args):
         return 0
     occ = synthetic.synthetic_occupancy()
     params = shipped_params()
-    cores = usable_cores()
+    cores, nproc, by_mem = usable_cores()
     arm = CpuArm(occ, params, cores)
     vals, extra = [], {}
     t0 = time.perf_counter()
@@ -279,28 +294,33 @@ def run_reference(args):
             per_step = n
         else:
             # the query set is generated with the reference's own collision test so that this arm needs no GPU
-            lib_poses = _ref_queries(occ, params, 2 * cores * max(1, args.steps + args.warmup))
-            per_step = 2 * cores
+            # at least 64 queries per process over the run (warm-up steps included)
+            per_proc = max(2, -(-64 // max(1, args.steps + args.warmup)))
+            lib_poses = _ref_queries(occ, params, per_proc * cores * max(1, args.steps + args.warmup))
+            per_step = per_proc * cores
             for s in range(args.warmup + args.steps):
                 sl = slice(s * per_step, (s + 1) * per_step)
                 r = arm.plan_rate(lib_poses[0][sl], lib_poses[1][sl])
                 if s >= args.warmup:
                     vals.append(r["expansions_per_sec"] if args.workload == "expand" else r["plans_per_sec"])
                     extra = r
-                if time.perf_counter() - t0 > 240 and vals:
+                if time.perf_counter() - t0 > 420 and vals:
                     break
             metric, unit = ("node_expansions_per_sec", "expansions/s") if args.workload == "expand" else ("plans_per_sec", "plans/s")
-            sample = ("%d seeded queries per step (2 per process) on the synthetic 8192^2 map (ds=8), %d processes x 1 thread; timed region per "
-                      "query = NavMap::updateGoal + HybridAstar ctor + Plan() (map preprocessing %.1f s excluded)" % (per_step, cores, extra.get("preprocess_s", 0)))
+            sample = ("%d seeded queries per step (%d per process, %d per process over the run) of the synthetic 8192^2 query set (ds=8), %d processes x 1 thread "
+                      "(nproc %d, memory allows %d: 3.5 GB per process); timed region per query = NavMap::updateGoal + HybridAstar ctor + Plan() "
+                      "(map preprocessing %.1f s excluded)" % (per_step, per_proc, per_proc * (args.steps + args.warmup), cores, nproc, by_mem,
+                                                              extra.get("preprocess_s", 0)))
     finally:
         arm.close()
     value = float(np.mean(vals))
     line = {
         "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": len(vals),
-        "warmup": args.warmup, "ms_per_step": (1e3 * per_step / extra["plans_per_sec"]) if args.workload == "expand" else 1e3 * per_step / value, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": (1e3 * per_step / extra["plans_per_sec"]) if args.workload == "expand" else 1e3 * per_step / value, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_text(args.workload), "units_per_step": per_step},
-        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "reference", "sample": sample},
+        "config": plan_config(max(1, min(args.lanes, 4)), args.scaling) if args.workload == "plan" else {"workload": workload_text(args.workload)},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "nproc": nproc, "processes_memory_allows": by_mem, "kind": "reference",
+                         "sample": sample, "units_per_step": per_step},
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     if extra:
@@ -324,6 +344,54 @@ def _ref_queries(occ, params, n):
     out = synthetic.synthetic_queries(n, rp.collision4, static_ds, SYN_RES * SYN_DS, EXTENT, synthetic.SYN_QUERY_SEED)
     rp.close()
     rm.close()
+    return out
+
+
+def verify_against_reference(ctx, occ, params, starts, goals, status, cost, stats, k):
+    """SURVEY 9.4 on the headline query set, live: K evenly spaced queries plus every query the GPU did not solve, re-planned
+    by the unmodified reference (oracle/_ref) on all host cores. Mode (ii): everything GPU-computed against the reference with
+    its own Voronoi field -> distribution of the cost difference. Mode (i): the reference's Voronoi field injected into the
+    GPU planner -> status, tree_.size() and goal cost must be equal per query."""
+    from oracle import refapi
+
+    nq = len(starts)
+    idx = np.union1d(np.arange(0, nq, max(1, nq // max(1, k)))[:k], np.nonzero(status != 1)[0])
+    cores, nproc, by_mem = usable_cores()
+    arm = CpuArm(occ, params, cores)
+    try:
+        ref = arm.plan_rate(starts[idx], goals[idx])["per_query"]
+    finally:
+        arm.close()
+    r_status = np.array([q[3] for q in ref])
+    r_prims = np.array([q[1] for q in ref])
+    r_cost = np.array([q[2] for q in ref])
+    g_status, g_prims, g_cost = status[idx], stats[idx, 1], cost[idx]
+    both = (g_status == 1) & (r_status == 1)
+    d = (g_cost[both] - r_cost[both]) / r_cost[both]
+    edges = [-1, -1e-1, -1e-2, -1e-3, -1e-4, 1e-4, 1e-3, 1e-2, 1e-1, 10]
+    out = {"queries": int(len(idx)), "non_found_included": int((status != 1).sum()), "reference_processes": cores,
+           "mode_ii_full_gpu": {"status_mismatches": int((g_status != r_status).sum()), "same_primitive_count": int((g_prims == r_prims).sum()),
+                                "rel_cost_difference": {"median": float(np.median(d)), "mean": float(d.mean()), "min": float(d.min()), "max": float(d.max()),
+                                                        "bin_edges": edges, "histogram": np.histogram(d, bins=edges)[0].tolist(),
+                                                        "other_homotopy_class_gt_5pct": int((np.abs(d) > 0.05).sum())}}}
+    # mode (i): the reference's order-dependent Voronoi field on the GPU
+    rm = refapi.RefMap(refapi.RefLib(), params)
+    rm.set_occupancy(occ, SYN_RES, [0.0, 0.0, 0.0])
+    canon = ctx.layer("voronoi").copy()
+    ref_v = rm.layer("voronoi")
+    rm.close()
+    try:
+        ctx.upload_voronoi(ref_v)
+        g = ctx.plan_batch(starts[idx], goals[idx], path_cap=PATH_CAP, truncate_ok=True)
+    finally:
+        ctx.upload_voronoi(canon)
+    ok = (g["status"] == 1) & (r_status == 1)
+    rel = np.abs(g["cost"][ok] - r_cost[ok]) / np.abs(r_cost[ok])
+    out["mode_i_reference_voronoi_injected"] = {
+        "status_mismatches": int((g["status"] != r_status).sum()), "primitive_count_mismatches": int((g["primitives"] != r_prims).sum()),
+        "max_rel_cost_difference": float(rel.max()) if len(rel) else None, "cost_beyond_1e-9": int((rel > 1e-9).sum()),
+        "voronoi_cells_differing_from_canonical": int((ref_v.view(np.uint32) != canon.view(np.uint32)).sum()),
+        "mismatching_queries": [int(q) for q in idx[(g["status"] != r_status) | (g["primitives"] != r_prims)]][:16]}
     return out
 
 
@@ -620,8 +688,16 @@ def run_b200(args):
                                "l2_policy": "inputs + outputs larger than L2 (50 MB of parents in, 860 MB of records out per step)",
                                "preprocess_s_first_call": t_pre}}
     else:
-        nq = QUERIES_PER_GPU
-        starts, goals = gen_queries(ctx, nq, synthetic.SYN_QUERY_SEED + rank)
+        if args.scaling == "strong":
+            # BASELINE.json configs[4] read literally: 16 384 queries IN TOTAL, contiguous shards (sharding.shard_range)
+            import sharding
+
+            all_s, all_g = gen_queries(ctx, QUERIES_PER_GPU, synthetic.SYN_QUERY_SEED)
+            lo, hi = sharding.shard_range(QUERIES_PER_GPU, rank, world)
+            starts, goals = np.ascontiguousarray(all_s[lo:hi]), np.ascontiguousarray(all_g[lo:hi])
+        else:
+            starts, goals = gen_queries(ctx, QUERIES_PER_GPU, synthetic.SYN_QUERY_SEED + rank)
+        nq = len(starts)
         s_h, g_h = torch.from_numpy(starts).pin_memory(), torch.from_numpy(goals).pin_memory()
         s_d, g_d = s_h.cuda(), g_h.cuda()
         # Batches in flight: step k runs on lane k % LANES (own stream + planner workspaces, include/mpros_gpu.h), so the
@@ -697,6 +773,7 @@ def run_b200(args):
                 stream.wait_stream(torch.cuda.current_stream())  # the result gathers
 
         total_ms, step_ms, launches = timed_device(step_dev, join_lanes)
+        rank_ms = total_ms  # this rank's own timed region (the headline uses the max over ranks)
         e2e_ms = timed_host(step_host, lambda: ctx.plan_batch_wait(-1))
         # one batch alone (no overlap): its latency and the planner kernel's own duration
         lone = []
@@ -725,6 +802,18 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(sums)
         expansions_all, checks_all, shots_all, cells_all, n_found, n_limit, n_fail = [int(v) for v in sums.tolist()]
+        # attribution of the scaling loss: every rank's own step time, iteration total and single-batch latency
+        mine = torch.tensor([rank_ms / args.steps, float(iters), lone_ms, float(nq), float((status == 0).sum())], dtype=torch.float64, device="cuda")
+        per_rank = [torch.zeros_like(mine) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(per_rank, mine)
+        else:
+            per_rank = [mine]
+        per_rank = [t.tolist() for t in per_rank]
+        nq_all = int(sum(r[3] for r in per_rank))
+        verify = None
+        if rank == 0 and args.verify > 0:
+            verify = verify_against_reference(ctx, occ, params, starts, goals, status, cost_d.cpu().numpy(), st, args.verify)
         if rank == 0:
             secs = total_ms * 1e-3 / args.steps
             # launches overlap when LANES > 1: the kernel's share of the timed region is region / launches (CUDA events on the
@@ -732,8 +821,8 @@ def run_b200(args):
             k_ms = float(np.mean(step_ms)) if LANES == 1 else total_ms / args.steps
             algo_bytes = B_EXPANSION * expansions + B_SHOT * shots + B_GOAL_CELL * cells
             achieved = algo_bytes / (k_ms * 1e-3) / 1e9
-            line = {"metric": "plans_per_sec", "value": world * nq / secs, "unit": "plans/s", "ms_per_step": total_ms / args.steps,
-                    "e2e": {"value": world * nq * args.steps / (e2e_ms * 1e-3), "unit": "plans/s", "h2d_bytes_per_step": nq * 48,
+            line = {"metric": "plans_per_sec", "value": nq_all / secs, "unit": "plans/s", "ms_per_step": total_ms / args.steps,
+                    "e2e": {"value": nq_all * args.steps / (e2e_ms * 1e-3), "unit": "plans/s", "h2d_bytes_per_step": nq * 48,
                             "d2h_bytes_per_step": nq * (4 + 8 + 4 + PATH_CAP * 40 + 48)},
                     "gpu_launches": int(launches),
                     "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("plan_team_kernel"),
@@ -745,11 +834,19 @@ def run_b200(args):
                               "collision_kernel_checks_per_sec": col_value, "collision_kernel_e2e_checks_per_sec": col_e2e,
                               "collision_kernel_roofline": col_roof, "collision_hit_rate": hit_rate,
                               "plans_found": n_found, "plans_iteration_limit": n_limit, "plans_failed_other": n_fail,
-                              "mean_expansions_per_query": expansions_all / (world * nq)},
-                    "config": {"workload": workload_text("plan"), "queries_per_gpu": nq, "path_cap": PATH_CAP, "batches_in_flight": LANES,
-                               "single_batch_ms": lone_ms,
-                               "l2_policy": "per-query working sets (node pool, open list, closed set, goal wavefront) live in a ~110 MB-per-team HBM workspace, 296 teams (>> L2 in aggregate); map layers are L2-resident by design",
-                               "preprocess_s_first_call": t_pre}}
+                              "mean_expansions_per_query": expansions_all / nq_all,
+                              "single_batch_ms": lone_ms, "single_batch_plans_per_sec": nq / (lone_ms * 1e-3),
+                              "note_value": "value is the streaming rate with %d batches in flight per GPU; one batch alone takes single_batch_ms" % LANES,
+                              "preprocess_s_first_call": t_pre,
+                              "per_rank": {"step_ms": [r[0] for r in per_rank], "iterations_per_step": [int(r[1]) for r in per_rank],
+                                           "single_batch_ms": [r[2] for r in per_rank], "queries": [int(r[3]) for r in per_rank],
+                                           "iteration_limit_queries": [int(r[4]) for r in per_rank],
+                                           "note": "step_ms = each rank's own timed region / steps (the headline takes the max); a limit query is a "
+                                                   "dependent chain of 100 001 expansions (0.65-1.0 s), so a single batch can never finish faster than that"}},
+                    "config": plan_config(LANES, args.scaling, world)}
+            line["config"]["single_batch_ms"] = lone_ms
+            if verify is not None:
+                line["extra"]["verify_vs_reference"] = verify
 
     if rank == 0 and line is not None:
         cpu = None
@@ -779,14 +876,34 @@ def run_b200(args):
                                "sample": "expandNode calls inside the unmodified reference's Plan() on 8 seeded queries of the plan workload, 1 process x 1 thread (primitives evaluated / 6 / time of updateGoal + ctor + Plan())"}
                     else:
                         r = arm.plan_rate(starts[:8], goals[:8])
+                        # the 8 reference results are compared, not thrown away: status and tree_.size() must equal the GPU's
+                        # wherever the search does not cross a tie-broken Voronoi cell; the goal cost is reported as a difference
+                        same = [int(a_[0] == (1 if status[k] == 1 else 0)) for k, a_ in enumerate(r["per_query"])]
+                        same_tree = [int(a_[1] == int(st[k, 1])) for k, a_ in enumerate(r["per_query"])]
+                        dcost = [abs(a_[2] - float(cost_d[k])) / abs(a_[2]) for k, a_ in enumerate(r["per_query"]) if a_[0] and status[k] == 1]
                         cpu = {"value": r["plans_per_sec"], "unit": "plans/s", "cores": 1, "kind": "reference",
                                "sample": "first 8 queries of rank 0's set, 1 process x 1 thread, unmodified reference: NavMap::updateGoal + HybridAstar ctor + Plan() per query (map preprocessing %.1f s excluded); %d/8 solved" % (r["preprocess_s"], r["solved"]),
-                               "node_expansions_per_sec": r["expansions_per_sec"]}
+                               "node_expansions_per_sec": r["expansions_per_sec"],
+                               "agreement_with_gpu": {"same_status": sum(same), "same_primitive_count": sum(same_tree), "of": len(same),
+                                                      "max_rel_cost_difference": max(dcost) if dcost else None,
+                                                      "note": "fully GPU (canonical Voronoi tie-breaks) against the reference's own field; tests/ pin all 16384 queries"}}
+                        assert sum(same) == len(same), "the reference disagrees with the GPU on the status of a sampled query"
                 finally:
                     arm.close()
             except Exception as e:  # oracle absent: say so, do not fail the GPU bench
                 cpu = {"value": None, "unit": line["unit"], "cores": 0, "kind": "unavailable", "sample": str(e)}
-        line.update({"n_gpus": world, "steps": args.steps, "warmup": warm, "higher_is_better": True, "scaling": "weak",
+        if args.workload == "plan" and world == 1 and not args.no_arena:
+            # BASELINE.json configs[2] (case 3, the configuration the north star's 50x target is quoted on) in the default line
+            try:
+                ctx.release_workspaces()
+                torch.cuda.empty_cache()
+                ar = arena_measure(args, 2, not args.no_cpu)
+                line["extra"]["case3_arena"] = {"plans_per_sec": ar["value"], "plans_per_sec_e2e": ar["e2e"]["value"], "ms_per_step": ar["ms_per_step"],
+                                                "queries_per_step": ar["config"]["queries_per_gpu"], "steps": 2,
+                                                "workload": ar["config"]["workload"], "gpu": ar["extra"], "cpu_reference": ar["cpu_baseline"]}
+            except Exception as e:
+                line["extra"]["case3_arena"] = {"error": str(e)}
+        line.update({"n_gpus": world, "steps": args.steps, "warmup": warm, "higher_is_better": True, "scaling": args.scaling if args.workload == "plan" else "weak",
                      "vs_baseline": None, "dtype": "f64", "data": "synthetic", "clocks": sampler.summary(), "cpu_baseline": cpu})
         order = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
                  "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline", "extra"]
@@ -798,6 +915,11 @@ def run_b200(args):
 
 
 def run_arena(args):
+    print(json.dumps(arena_measure(args, args.steps, not args.no_cpu)))
+    return 0
+
+
+def arena_measure(args, steps, with_cpu):
     """BASELINE.json configs[2], "case 3 Arena whole map" (the case the north star's 50x target names): the 2000 x 2000 @0.04 m
     stand-in of SURVEY.md 8(d) (Arena2036's pgm is missing from the reference: ARENA_part's image read with Arena2036.yaml's
     thresholds, nearest-neighbour x4; committed input fixture tests/golden/maps/arena_standin.npz), down-sampling 4. One line:
@@ -822,7 +944,7 @@ def run_arena(args):
     ctx.set_occupancy(occ_pinned.numpy(), res, [0.0, 0.0, 0.0])
     ctx.planner_config(params)
     stream = torch.cuda.ExternalStream(ctx.stream())
-    warm, K = max(3, args.warmup), args.steps
+    warm, K = max(3, args.warmup), steps
     sampler = ClockSampler(0)
     sampler.start()
 
@@ -925,8 +1047,9 @@ def run_arena(args):
                       "collision_checks_per_sec": col_rate, "collision_hit_rate": hit_rate,
                       "collision_roofline_frac": col_rate * (24 + 1 + ctx_n_check(ctx) + 1 + 4) / 1e9 / peak,
                       "preprocess_s_host_buffer": t_pre}}
+    ctx.close()
     cpu = None
-    if not args.no_cpu:
+    if with_cpu:
         try:
             arm = CpuArm(occ, params, 1, res)
             try:
@@ -939,11 +1062,32 @@ def run_arena(args):
                        "collision_checks_per_sec": cv, "preprocess_s": r["preprocess_s"], "node_expansions_per_sec": r["expansions_per_sec"]}
             finally:
                 arm.close()
+            # the whole host: one process per core (0.5 GB each at 500 x 500 cells), 2 queries per process
+            cores, nproc, by_mem = usable_cores(0.8e9)
+            arm = CpuArm(occ, params, cores, res)
+            try:
+                m = min(nq, 2 * cores)
+                ra = arm.plan_rate(starts[:m], goals[:m])
+                cva = arm.collision_rate((1 << 17) * cores, POSE_SEED + 7, extent)
+                cpu["all_cores"] = {"plans_per_sec": ra["plans_per_sec"], "collision_checks_per_sec": cva, "processes": cores, "nproc": nproc,
+                                    "processes_memory_allows": by_mem, "queries": m, "solved": ra["solved"],
+                                    "node_expansions_per_sec": ra["expansions_per_sec"]}
+            finally:
+                arm.close()
         except Exception as e:
-            cpu = {"value": None, "unit": "plans/s", "cores": 0, "kind": "unavailable", "sample": str(e)}
+            if cpu is None:
+                cpu = {"value": None, "unit": "plans/s", "cores": 0, "kind": "unavailable", "sample": str(e)}
+            else:
+                cpu["all_cores"] = {"error": str(e)}
     line["cpu_baseline"] = cpu
-    print(json.dumps(line))
-    return 0
+    if cpu and cpu.get("value"):
+        line["extra"]["vs_reference_one_core"] = {"plans": line["value"] / cpu["value"], "collision_checks": col_rate / cpu["collision_checks_per_sec"]}
+        if "all_cores" in cpu and "plans_per_sec" in cpu["all_cores"]:
+            line["extra"]["vs_reference_all_cores"] = {"plans": line["value"] / cpu["all_cores"]["plans_per_sec"], "plans_e2e": line["e2e"]["value"] / cpu["all_cores"]["plans_per_sec"],
+                                                      "collision_checks": col_rate / cpu["all_cores"]["collision_checks_per_sec"],
+                                                      "processes": cpu["all_cores"]["processes"], "nproc": cpu["all_cores"]["nproc"],
+                                                      "note": "north-star target: >= 50x the reference CPU planner on this case (collision checks/s and planning throughput)"}
+    return line
 
 
 def ctx_n_check(ctx):
@@ -963,6 +1107,12 @@ def main():
     ap.add_argument("--workload", default="plan", choices=["plan", "collision", "expand", "preprocess", "rs", "arena"])
     ap.add_argument("--lanes", type=int, default=4, help="plan workload: query batches in flight (1 = one batch at a time)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="plan workload: weak = 16384 queries per GPU (default), strong = 16384 queries in total, sharded across the GPUs")
+    ap.add_argument("--verify", type=int, default=0,
+                    help="plan workload, rank 0: re-plan K seeded queries plus every non-FOUND one with the unmodified reference (oracle/_ref, "
+                         "~2.5 s each on one core, run on all cores) and report status / expansion-count / cost agreement per SURVEY 9.4")
+    ap.add_argument("--no-arena", action="store_true", help="plan workload at N=1: skip the case-3 (Arena stand-in) figures in extra")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -43,9 +43,11 @@ static bool apply_option(Options &o, const char *key, const char *value)
     const std::string k = key ? key : "", v = value ? value : "";
     if (k == "c1_mode")
     {
-        if (v != "" && v != "2phase" && v != "walk")
+        if (v != "" && v != "2phase" && v != "walk" && v != "2phase_ldg" && v != "2phase_s0" && v != "2phase_s1" && v != "2phase_s2")
             return false;
         o.c1_walk = v == "walk";
+        o.c1_ldg = v == "2phase_ldg";
+        o.c1_stages = v == "2phase_s0" ? 0 : v == "2phase_s1" ? 1 : v == "2phase_s2" ? 2 : -1;
     }
     else if (k == "goal_mode")
     {
@@ -55,9 +57,10 @@ static bool apply_option(Options &o, const char *key, const char *value)
     }
     else if (k == "plan_mode")
     {
-        if (v != "" && v != "team" && v != "cluster")
+        if (v != "" && v != "team" && v != "cluster" && v != "duo")
             return false;
         o.plan_cluster = v == "cluster";
+        o.plan_duo = v == "duo";
     }
     else if (k == "debug")
         o.debug = !(v == "" || v == "0");
@@ -156,9 +159,15 @@ extern "C" int mpros_ctx_destroy(mpros_ctx *c)
             if (c->lane_stage[l])
                 cudaFree(c->lane_stage[l]);
         }
+    if (c->aux_stream)
+    {
+        cudaStreamSynchronize(c->aux_stream);
+        cudaStreamDestroy(c->aux_stream);
+        cudaEventDestroy(c->aux_event);
+    }
     free_plan_scratch(c); // node pools, open lists, closed sets of every lane (tens of GB at full size)
     void *bufs[] = {c->raw_bits, c->infl_bits, c->ds_bits, c->goal, c->obs_dist, c->edge_dist, c->region,
-                    c->edge_bits, c->voronoi, c->scratch, c->stage, c->raw_tw, c->infl_tw, c->unsafe_tw};
+                    c->edge_bits, c->voronoi, c->scratch, c->stage, c->raw_tw, c->infl_tw, c->unsafe_tw, c->cls_tw};
     for (void *b : bufs)
         if (b)
             cudaFree(b);

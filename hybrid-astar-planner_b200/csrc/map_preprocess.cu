@@ -729,6 +729,13 @@ __global__ void __launch_bounds__(256) unsafe_cols_kernel(const uint32_t *__rest
     }
 }
 
+__global__ void __launch_bounds__(256) interleave_tw_kernel(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b, uint2 *__restrict__ out,
+                                                            size_t n)
+{
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+        out[k] = make_uint2(a[k], b[k]);
+}
+
 int map_build_unsafe(Ctx *c)
 {
     if (c->unsafe_valid)
@@ -757,9 +764,13 @@ int map_build_unsafe(Ctx *c)
     {
         if (c->unsafe_tw)
             MPROS_CUDA(cudaFree(c->unsafe_tw));
+        if (c->cls_tw)
+            MPROS_CUDA(cudaFree(c->cls_tw));
         c->unsafe_tw = nullptr;
+        c->cls_tw = nullptr;
         c->cap_unsafe_tw = 0;
         MPROS_CUDA(cudaMalloc(&c->unsafe_tw, tw_words * 4));
+        MPROS_CUDA(cudaMalloc(&c->cls_tw, tw_words * 8));
         c->cap_unsafe_tw = tw_words;
     }
     int rc = ensure_scratch(c, words0 * 4 * 3 + 1024);
@@ -783,6 +794,9 @@ int map_build_unsafe(Ctx *c)
         build_tilewords_kernel<<<grid_for(c, tw_words), 256, 0, st>>>(unsafe_bits, c->H0, c->W0, c->pitch0, c->unsafe_tw, c->tw_pitch, tw_rows);
         MPROS_LAUNCH_CHECK(c);
     }
+    // classification layer of the batched footprint kernel: the "not surely free" word next to the inflated layer's word
+    interleave_tw_kernel<<<grid_for(c, tw_words), 256, 0, st>>>(c->unsafe_tw, c->infl_tw, c->cls_tw, tw_words);
+    MPROS_LAUNCH_CHECK(c);
     // the axis line has a probe exactly at the pose when n_check is even and the axis is symmetric about it
     // (footprint_longi_ = +-(L - W) / 2, hybrid_a_star.cpp:198-199, with center_to_rotate_center_longitudinal = 0)
     c->unsafe_center_probe = (v.n_check % 2 == 0 && v.longi_x0 == -v.longi_x1 && std::isfinite(v.fx_extent)) ? 1 : 0;

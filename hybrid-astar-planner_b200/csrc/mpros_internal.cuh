@@ -94,8 +94,11 @@ constexpr int kPlanPasses = 3; // node-pool size classes
 struct Options
 {
     bool c1_walk = false;      // MPROS_C1_MODE=walk: single-phase footprint kernel
+    bool c1_ldg = false;       // MPROS_C1_MODE=2phase_ldg: the round-1 two-phase kernel (two probes per pose, byte stores)
+    int c1_stages = -1;        // MPROS_C1_MODE=2phase_s0 / _s1 / _s2: shared-memory stages of the pose stream (-1 = default)
     int goal_mode = 0;         // MPROS_GOAL_MODE: 0 cluster (16 CTAs when granted), 1 "cluster8", 2 "grid"
     bool plan_cluster = false; // MPROS_PLAN_MODE=cluster: a team is a CTA pair
+    bool plan_duo = false;     // MPROS_PLAN_MODE=duo: two teams per CTA keeping their iterations in step (plan_team.cuh: DuoSync)
     bool debug = false;        // MPROS_DEBUG: per-pass timing (and the phase profile of the -DMPROS_PROFILE build) on stderr
 };
 
@@ -104,10 +107,12 @@ struct Ctx
     int device = 0;
     int n_sm = 0; // cudaDevAttrMultiProcessorCount, queried once in mpros_ctx_create; every grid is a multiple of it
     cudaStream_t stream = nullptr;
+    cudaStream_t aux_stream = nullptr; // second stream of the host-buffer entry points that pipeline their copies (created on first use)
+    cudaEvent_t aux_event = nullptr;
     uint64_t launches = 0;
     Options opt;
     PlanScratch plan_scratch[MPROS_PLAN_LANES][kPlanPasses];
-    int plan_resident[2] = {0, 0}; // resident planner CTAs per SM: [0] CTA teams, [1] CTA-pair teams (occupancy query, cached)
+    int plan_resident[3] = {0, 0, 0}; // resident teams per SM: [0] CTA teams, [1] CTA-pair teams (occupancy query, cached), [2] two teams per CTA
 
     mpros_map_params mp;
     mpros_planner_params pp;
@@ -131,8 +136,10 @@ struct Ctx
     // "not surely free" layer of the batched footprint test (collision.cu), same tile-word layout; built on demand from the
     // two collision layers and the planner's footprint (map_build_unsafe), invalidated when either changes
     uint32_t *unsafe_tw = nullptr;
+    uint2 *cls_tw = nullptr; // {unsafe word, inflated word} interleaved: one 8-byte probe classifies a pose (collision.cu)
     size_t cap_unsafe_tw = 0;
     bool unsafe_valid = false;
+    bool c1_attr_set = false; // dynamic shared-memory limit of collision_poses_tma_kernel raised
     int unsafe_center_probe = 0; // the axis line has a probe exactly at the pose (n_check even, symmetric axis)
     uint16_t *goal = nullptr, *obs_dist = nullptr, *edge_dist = nullptr;
     int32_t *region = nullptr;

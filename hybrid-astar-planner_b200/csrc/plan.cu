@@ -822,10 +822,16 @@ static int plan_pass(mpros_ctx *c, int lane, cudaStream_t stream, PlanBatchArgs 
     // two teams per SM), CTA pairs 2.24 s (148 teams, 8.2-8.6 us per iteration alone AND loaded: no interference between
     // co-resident teams any more, but the two cluster barriers cost ~4 k cycles per iteration). Results are identical.
     const bool cluster = c->opt.plan_cluster;
-    int &resident = c->plan_resident[cluster ? 1 : 0];
+    const bool duo = !cluster && c->opt.plan_duo;
+    int &resident = c->plan_resident[cluster ? 1 : duo ? 2 : 0];
     if (!resident)
     {
-        if (cluster)
+        if (duo)
+        {
+            MPROS_CUDA(cudaFuncSetAttribute(plan_duo_kernel<kTeamWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)duo_smem_bytes<kTeamWarps>()));
+            resident = 2; // one CTA of two teams per SM
+        }
+        else if (cluster)
             MPROS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, plan_cluster_kernel<kTeamWarps, kTeamMinBlocks>, kTeamWarps * 32, 0));
         else
             MPROS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, plan_team_kernel<kTeamWarps, kTeamMinBlocks>, kTeamWarps * 32, 0));
@@ -843,6 +849,8 @@ static int plan_pass(mpros_ctx *c, int lane, cudaStream_t stream, PlanBatchArgs 
         const size_t budget = (free_b + S.ws_bytes) / 2;
         blocks = (int)std::min<long long>(blocks, std::max<long long>(1, (long long)(budget / L.stride)));
     }
+    if (duo)
+        blocks = (blocks + 1) & ~1; // a CTA always owns two workspaces
     size_t need = (size_t)blocks * L.stride;
     if (need > S.ws_bytes)
     {
@@ -885,7 +893,9 @@ static int plan_pass(mpros_ctx *c, int lane, cudaStream_t stream, PlanBatchArgs 
         cudaEventCreate(&e1);
         cudaEventRecord(e0, stream);
     }
-    if (cluster)
+    if (duo)
+        plan_duo_kernel<kTeamWarps><<<(blocks + 1) / 2, kTeamWarps * 64, duo_smem_bytes<kTeamWarps>(), stream>>>(c->view(), c->pv, a);
+    else if (cluster)
         plan_cluster_kernel<kTeamWarps, kTeamMinBlocks><<<2 * blocks, kTeamWarps * 32, 0, stream>>>(c->view(), c->pv, a);
     else
         plan_team_kernel<kTeamWarps, kTeamMinBlocks><<<blocks, kTeamWarps * 32, 0, stream>>>(c->view(), c->pv, a);
@@ -909,13 +919,13 @@ static int plan_pass(mpros_ctx *c, int lane, cudaStream_t stream, PlanBatchArgs 
                          h[13] / its, h[14] / its, h[15] / its);
             for (int k = 0; k < 12; ++k)
                 std::fprintf(stderr, "[mpros]   %-12s %9.1f\n", names[k], h[k] / its);
-            const char *names2[8] = {"col:pose+sincos", "col:footprint", "closed:A loads", "closed:B-D", "closed:insert", "heap:remove root", "heap:pushes", "heap:(rest=elim+fetch in heap_restore)"};
-            for (int k = 16; k < 23; ++k)
+            const char *names2[8] = {"col:pose+sincos", "col:footprint", "closed:A loads", "closed:B-D", "closed:insert", "heap:remove root", "heap:pushes", "duo:wait for partner"};
+            for (int k = 16; k < 24; ++k)
                 std::fprintf(stderr, "[mpros]   %-18s %9.1f\n", names2[k - 16], h[k] / its);
         }
 #endif
         std::fprintf(stderr, "[mpros] plan pass %d: %d queries, node_cap %d, %d teams (%s) x %d warps, %.1f MB/team, %.3f ms\n", pass, n_run,
-                     node_cap, blocks, cluster ? "CTA pairs" : "CTAs", kTeamWarps, L.stride / 1048576.0, ms);
+                     node_cap, blocks, cluster ? "CTA pairs" : duo ? "two per CTA" : "CTAs", kTeamWarps, L.stride / 1048576.0, ms);
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
     }

@@ -91,12 +91,33 @@ struct TeamShared
 #endif
 };
 
-// barrier of the compute group (every warp except the heap warp)
+// A CTA holds one team (plan_team_kernel, plan_cluster_kernel) or two (plan_duo_kernel); everything below addresses threads
+// and barriers relative to the team: thread index 0 .. NW*32-1, named barriers 1 + 3 t (whole team), 2 + 3 t (compute group:
+// every warp except the heap warp), 3 + 3 t (footprint warps -> closed-set warp, one way), t = team index inside the CTA.
+template <int NW>
+__device__ __forceinline__ int team_tid() { return (int)(threadIdx.x % (NW * 32)); }
+template <int NW>
+__device__ __forceinline__ int team_index() { return (int)(threadIdx.x / (NW * 32)); }
+template <int NW>
+__device__ __forceinline__ void team_sync_all()
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + 3 * team_index<NW>()), "r"(NW * 32) : "memory");
+}
 template <int NW>
 __device__ __forceinline__ void team_sync()
 {
-    asm volatile("bar.sync 1, %0;" ::"r"((NW - 1) * 32) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(2 + 3 * team_index<NW>()), "r"((NW - 1) * 32) : "memory");
 }
+
+// Two teams of one CTA (plan_duo_kernel) keep their iterations in step, softly: the heap warp of a team that reaches the top
+// of an iteration waits - for a bounded number of cycles - until the other team has reached its next one too. Both teams
+// then walk the same ~50 KB of iteration code at the same time and share the instruction-cache fills (co-resident teams in
+// separate CTAs run out of phase and evict each other's lines: 6.5 us per iteration alone, ~10 us with a neighbour).
+struct DuoSync
+{
+    volatile unsigned count[2]; // iterations started by each team
+    volatile int active[2];     // inside the search loop
+};
 
 // The 11 OMPL base formulas (rs_device.cuh: ompl_formula) are evaluated in two rounds. Round A: the two CSC formulas
 // (k = 0, 1) on warps 0 and 1; any valid candidate is an upper bound of the RS distance, so when rho * min(CSC) <= h1 for
@@ -116,8 +137,15 @@ __device__ __forceinline__ int team_formula_b<4>(int warp, int slot)
     const signed char tab[3][3] = {{4, 6, 2}, {5, 7, 3}, {10, 8, 9}};
     return tab[warp][slot];
 }
+template <>
+__device__ __forceinline__ int team_formula_b<6>(int warp, int slot)
+{
+    // five compute-group warps (four footprint warps + the closed-set warp); the CCSCC formula (10) is the longest
+    const signed char tab[5][2] = {{4, 6}, {5, 7}, {2, 8}, {3, 9}, {10, -1}};
+    return tab[warp][slot];
+}
 template <int NW>
-__device__ __forceinline__ int team_formula_b_slots() { return NW == 8 ? 2 : 3; }
+__device__ __forceinline__ int team_formula_b_slots() { return NW == 4 ? 3 : 2; }
 
 // ---- on-demand goal wavefront, compute-group version (same semantics as planner_device.cuh: GoalBfs) -----------------
 template <int NW>
@@ -125,7 +153,7 @@ __device__ __forceinline__ void team_bfs_init_rows(const MapView &m, TeamBfs &b,
 {
     // The initialised rows form one contiguous range [ilo, ihi] that only grows; rows outside it still hold a previous
     // query's bits and are never read.
-    const int tid = threadIdx.x, CT = (NW - 1) * 32;
+    const int tid = team_tid<NW>(), CT = (NW - 1) * 32;
     ra = max(ra, b.r0);
     rb = min(rb, b.r0 + b.rows - 1);
     const int ilo = b.ilo, ihi = b.ihi;
@@ -155,7 +183,7 @@ __device__ __forceinline__ void team_bfs_init_rows(const MapView &m, TeamBfs &b,
 template <int NW>
 __device__ __noinline__ void team_bfs_start(const MapView &m, TeamBfs &b, int gi, int gj, uint32_t tag)
 {
-    const int tid = threadIdx.x;
+    const int tid = team_tid<NW>();
     if (tid == 0)
     {
         const int wpr = (m.W + 31) >> 5;
@@ -190,7 +218,7 @@ __device__ __noinline__ void team_bfs_start(const MapView &m, TeamBfs &b, int gi
 template <int NW>
 __device__ __forceinline__ void team_bfs_step(const MapView &m, TeamBfs &b)
 {
-    const int tid = threadIdx.x, CT = (NW - 1) * 32;
+    const int tid = team_tid<NW>(), CT = (NW - 1) * 32;
     const int level = b.level + 1;
     if (level >= kHugeInt)
     {
@@ -304,7 +332,7 @@ __device__ __forceinline__ int team_bfs_peek(const MapView &m, const TeamBfs &b,
 template <int NW>
 __device__ __noinline__ void team_h1_lookup(const MapView &m, TeamShared<NW> &S, Prof &pf)
 {
-    const int tid = threadIdx.x;
+    const int tid = team_tid<NW>();
     while (true)
     {
         if (tid == 0)
@@ -320,12 +348,12 @@ __device__ __noinline__ void team_h1_lookup(const MapView &m, TeamShared<NW> &S,
         team_sync<NW>();
         if (!S.bfs_more)
             break;
-        if (threadIdx.x == 0) pf.mark(3);
+        if (team_tid<NW>() == 0) pf.mark(3);
         team_bfs_step<NW>(m, S.bfs);
-        if (threadIdx.x == 0) pf.mark(4);
-        if (threadIdx.x == 0) pf.count(13);
+        if (team_tid<NW>() == 0) pf.mark(4);
+        if (team_tid<NW>() == 0) pf.count(13);
     }
-    if (threadIdx.x == 0) pf.mark(3);
+    if (team_tid<NW>() == 0) pf.mark(3);
 }
 
 // symmetry image q of the normalised goal seen from pose (x, y, yaw) into slot c (consumed by team_heuristics)
@@ -343,7 +371,7 @@ __device__ __forceinline__ void team_image(const PlannerView &p, TeamShared<NW> 
 template <int NW>
 __device__ __noinline__ void team_heuristics(const MapView &m, const PlannerView &p, TeamShared<NW> &S, Prof &pf)
 {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = team_tid<NW>(), warp = tid >> 5, lane = tid & 31;
     if (tid == 0)
     {
         int n = 0;
@@ -385,11 +413,11 @@ __device__ __noinline__ void team_heuristics(const MapView &m, const PlannerView
             S.h_skip = all;
         }
         team_sync<NW>();
-        if (threadIdx.x == 0) pf.mark(5);
+        if (team_tid<NW>() == 0) pf.mark(5);
         // round B: CCC, CCCC, CCSC, CCSCC
         if (!S.h_skip)
         {
-            if (threadIdx.x == 0) pf.count(14);
+            if (team_tid<NW>() == 0) pf.count(14);
 #pragma unroll 1
             for (int s = 0; s < team_formula_b_slots<NW>(); ++s)
             {
@@ -404,7 +432,7 @@ __device__ __noinline__ void team_heuristics(const MapView &m, const PlannerView
             }
         }
         team_sync<NW>();
-        if (threadIdx.x == 0) pf.mark(6);
+        if (team_tid<NW>() == 0) pf.mark(6);
     }
     if (tid < hn)
     {
@@ -415,14 +443,14 @@ __device__ __noinline__ void team_heuristics(const MapView &m, const PlannerView
         S.c_h[c] = fmax(h1, h2) * (1 + 1e-3);
     }
     team_sync<NW>();
-    if (threadIdx.x == 0) pf.mark(7);
+    if (team_tid<NW>() == 0) pf.mark(7);
 }
 
 // Reeds-Shepp shot from (x, y, yaw, dir, steer) to the goal: FindOptimalPath + GenTraj into S.traj (compute group).
 template <int NW>
 __device__ __noinline__ void team_rs_solve(const RsConfig &rs, TeamShared<NW> &S, double x, double y, double yaw, int dir, double steer)
 {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = team_tid<NW>(), warp = tid >> 5, lane = tid & 31;
     constexpr int CW = NW - 1;
     // NewGoalPoint (rs_curve.cpp:51-58)
     double dx = S.gx - x, dy = S.gy - y;
@@ -511,7 +539,7 @@ __device__ __noinline__ void team_rs_solve(const RsConfig &rs, TeamShared<NW> &S
 template <int NW>
 __device__ __noinline__ void team_shot(const MapView &m, const PlannerView &p, const PlanBatchArgs &a, TeamShared<NW> &S, Prof &pf)
 {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = team_tid<NW>(), warp = tid >> 5, lane = tid & 31;
     constexpr int CW = NW - 1;
     const PlanNode cn = S.cur;
     team_rs_solve<NW>(a.rs, S, cn.x, cn.y, cn.yaw, (int)cn.dir, cn.steer);
@@ -637,7 +665,7 @@ template <int NW, bool CTA_WIDE>
 __device__ __forceinline__ void heur_rounds(const MapView &m, const PlannerView &p, const HeurView &V, unsigned needmask, int P, int writer_warp,
                                             Prof &pf)
 {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = team_tid<NW>() >> 5, lane = team_tid<NW>() & 31;
     for (int base = 0; base < P; base += 8)
     {
         if (((needmask >> base) & 0xffu) == 0)
@@ -654,7 +682,7 @@ __device__ __forceinline__ void heur_rounds(const MapView &m, const PlannerView 
                 V.hf[warp][c] = Lf;
         }
         heur_sync<NW, CTA_WIDE>(); // (2)
-        if (threadIdx.x == 0) pf.mark(5);
+        if (team_tid<NW>() == 0) pf.mark(5);
         bool ok = true;
         {
             const int ce = base + lane;
@@ -673,7 +701,7 @@ __device__ __forceinline__ void heur_rounds(const MapView &m, const PlannerView 
             V.skipg[base >> 3] = skip;
         if (!skip)
         {
-            if (threadIdx.x == 0) pf.count(14);
+            if (team_tid<NW>() == 0) pf.count(14);
             if (warp < NW - 1)
             {
 #pragma unroll 1
@@ -691,7 +719,7 @@ __device__ __forceinline__ void heur_rounds(const MapView &m, const PlannerView 
             }
             heur_sync<NW, CTA_WIDE>(); // (3)
         }
-        if (threadIdx.x == 0) pf.mark(6);
+        if (team_tid<NW>() == 0) pf.mark(6);
     }
 }
 // one child's heuristic from the per-formula minima (same combination as the sequential CSC/CCC/CCCC, CCSC, CCSCC passes)
@@ -746,7 +774,7 @@ __device__ __forceinline__ T *cluster_peer(T *local, unsigned rank)
 template <int NW>
 __device__ void heur_cta_loop(const MapView &m, const PlannerView &p, HeurShared &H, double *peer_c_h)
 {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = team_tid<NW>() >> 5, lane = team_tid<NW>() & 31;
     Prof pf;
 #ifdef MPROS_PROFILE
     pf.start(H.prof); // marks of the shared heuristics code land here and are not reported
@@ -791,11 +819,14 @@ __device__ __forceinline__ int open_argmin(unsigned long long key, uint32_t id, 
     return __ffs(__ballot_sync(kFull, a2 && id == m3)) - 1;
 }
 
+#ifndef MPROS_DUO_WAIT
+#define MPROS_DUO_WAIT 6000 // cycles a team waits at most for its partner at the top of an iteration (plan_duo_kernel)
+#endif
 template <int NW, bool CL>
 __device__ void plan_team_query(const MapView &m, const PlannerView &p, const PlanBatchArgs &a, int q, char *ws, uint32_t tag,
-                                TeamShared<NW> &S, HeurShared *Hpeer)
+                                TeamShared<NW> &S, HeurShared *Hpeer, DuoSync *D = nullptr)
 {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = team_tid<NW>(), warp = tid >> 5, lane = tid & 31;
 
     constexpr int HEAP_W = NW - 1;   // heap warp
     constexpr int CLOSED_W = NW - 2; // closed-set warp
@@ -819,7 +850,7 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
 #ifdef MPROS_PROFILE
     if (tid < 24)
         S.prof[tid] = 0;
-    __syncthreads();
+    team_sync_all<NW>();
     const bool pf_on = tid == 0 || (lane == 0 && (warp == HEAP_W || warp == CLOSED_W));
     pf.start(S.prof);
     (void)pf_on;
@@ -843,7 +874,7 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
         S.bfs.dist = reinterpret_cast<uint16_t *>(ws + L.dist_off);
         S.bfs.cells = 0;
     }
-    __syncthreads();
+    team_sync_all<NW>();
 
     // ---- initialize (hybrid_a_star.cpp:52-118), compute group only; the heap warp waits at the barrier below ----
     if (!is_heap)
@@ -911,13 +942,18 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
             }
         }
     }
-    __syncthreads();
+    team_sync_all<NW>();
     const bool init_ok = S.init_ok != 0;
     pf.restart();
 
     // ---- Plan() (hybrid_a_star.cpp:682-777) ----
     const int P = 2 * p.n_steer;
     int bg_dropped = 0; // heap warp: stale roots removed ahead of time in the previous iteration's background phase
+    unsigned duo_seen = 0; // heap warp, lane 0: the partner team's iteration count at this team's last iteration top
+    if (D && init_ok && tid == 0)
+        D->active[team_index<NW>()] = 1;
+    if (D && is_heap && lane == 0)
+        duo_seen = D->count[team_index<NW>() ^ 1];
     while (init_ok)
     {
         const int it = S.iteration;
@@ -998,6 +1034,22 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                 }
             }
             if (is_heap && lane == 0) pf.mark(10);
+            if (D)
+            {
+                // soft step with the partner team (DuoSync): wait, bounded, until it has started its next iteration too
+                if (lane == 0)
+                {
+                    const int me = team_index<NW>(), other = me ^ 1;
+                    D->count[me] = D->count[me] + 1;
+                    const long long t0 = clock64();
+                    while (D->active[other] && D->count[other] == duo_seen && clock64() - t0 < (long long)MPROS_DUO_WAIT)
+                    {
+                    }
+                    duo_seen = D->count[other];
+                }
+                __syncwarp();
+                if (is_heap && lane == 0) pf.mark(23);
+            }
             if (lane == 0)
             {
                 S.n_marks = 0;
@@ -1011,7 +1063,7 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                     S.shot_ok = 0;
                 }
             }
-            __syncthreads(); // (a) the popped node is public
+            team_sync_all<NW>(); // (a) the popped node is public
             if (CL && flag == 0)
                 cluster_arrive(); // X of this iteration: the heap warp contributes nothing to the request, so it arrives at once
             if (flag == 0)
@@ -1094,7 +1146,7 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
         }
         else
         {
-            __syncthreads(); // (a)
+            team_sync_all<NW>(); // (a)
             if (tid == 0) pf.mark(0);
             if (tid == 0) pf.count(12);
         }
@@ -1158,7 +1210,7 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                     }
                     __syncwarp();
                     // the closed-set warp builds the images from these as soon as all footprint warps have arrived
-                    asm volatile("bar.arrive 2, %0;" ::"r"((COL_W + 1) * 32) : "memory");
+                    asm volatile("bar.arrive %0, %1;" ::"r"(3 + 3 * team_index<NW>()), "r"((COL_W + 1) * 32) : "memory");
                     if (tid == 0) pf.mark(16);
                     // (ii) footprint tests, one lane per probe
                     for (int c = warp; c < P; c += COL_W)
@@ -1211,7 +1263,7 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                     __syncwarp();
                     if (warp == CLOSED_W && lane == 0) pf.mark(18);
                     // phase B: the sin/cos pairs come from the footprint warps (child yaw and goal yaw - child yaw)
-                    asm volatile("bar.sync 2, %0;" ::"r"((COL_W + 1) * 32) : "memory");
+                    asm volatile("bar.sync %0, %1;" ::"r"(3 + 3 * team_index<NW>()), "r"((COL_W + 1) * 32) : "memory");
                     // phase C: the four symmetry images of the normalised goal per child (ompl_image; sin(-x) = -sin(x) and
                     // cos(-x) = cos(x) hold bit for bit, so the image's own sin/cos phi follow from those of dth)
                     for (int t = lane; t < 4 * P; t += 32)
@@ -1418,7 +1470,7 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                     S.iteration = it + 1;
             }
         }
-        __syncthreads(); // (b) inserts are in the buffer, the heap is consistent again
+        team_sync_all<NW>(); // (b) inserts are in the buffer, the heap is consistent again
         if (!is_heap)
         {
             if (tid == 0) pf.mark(9);
@@ -1428,8 +1480,10 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
         if (S.stop)
             break;
     }
+    if (D && tid == 0)
+        D->active[team_index<NW>()] = 0; // the partner stops waiting for this team
 #ifdef MPROS_PROFILE
-    __syncthreads();
+    team_sync_all<NW>();
     if (tid < 24 && S.prof[tid])
         atomicAdd(&g_prof[tid], S.prof[tid]);
 #endif
@@ -1459,7 +1513,7 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                 if (tid == 0)
                     S.goal_traj_n = S.traj_n;
             }
-            __syncthreads();
+            team_sync_all<NW>();
         }
         if (tid == 0)
         {
@@ -1494,7 +1548,7 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
                 dst[0] = S.sx, dst[1] = S.sy, dst[2] = S.syaw, dst[3] = 0.0, dst[4] = start_dir;
             }
         }
-        __syncthreads();
+        team_sync_all<NW>();
         const int chain = S.chain;
         out_len = 1 + chain + S.goal_traj_n;
         if (a.paths && a.path_cap > 0)
@@ -1527,7 +1581,7 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
             a.stats[6 * q + 5] = S.n_nodes;
         }
     }
-    __syncthreads();
+    team_sync_all<NW>();
 }
 
 template <int NW, int MINB>
@@ -1540,10 +1594,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) plan_team_kernel(const __grid_c
     const int total = a.todo ? a.n_todo : a.nq;
     while (true)
     {
-        __syncthreads();
-        if (threadIdx.x == 0)
+        team_sync_all<NW>();
+        if (team_tid<NW>() == 0)
             S.q = (int)atomicAdd(a.counter, 1u);
-        __syncthreads();
+        team_sync_all<NW>();
         const int t = S.q;
         if (t >= total)
             break;
@@ -1552,6 +1606,42 @@ __global__ void __launch_bounds__(NW * 32, MINB) plan_team_kernel(const __grid_c
         plan_team_query<NW, false>(m, p, a, q, ws, a.tag_base + local_gen, S, nullptr);
     }
 }
+
+// Two teams per CTA, one CTA per SM (see DuoSync): blockIdx.x * 2 + team index = workspace; each team pulls its own queries.
+template <int NW>
+__global__ void __launch_bounds__(NW * 64, 1) plan_duo_kernel(const __grid_constant__ MapView m, const __grid_constant__ PlannerView p,
+                                                               const __grid_constant__ PlanBatchArgs a)
+{
+    extern __shared__ __align__(16) unsigned char duo_smem[];
+    constexpr size_t kTeamBytes = (sizeof(TeamShared<NW>) + 15) / 16 * 16;
+    const int team = team_index<NW>();
+    TeamShared<NW> &S = *reinterpret_cast<TeamShared<NW> *>(duo_smem + team * kTeamBytes);
+    DuoSync *D = reinterpret_cast<DuoSync *>(duo_smem + 2 * kTeamBytes);
+    if (threadIdx.x == 0)
+    {
+        D->count[0] = D->count[1] = 0;
+        D->active[0] = D->active[1] = 0;
+    }
+    __syncthreads();
+    char *ws = a.ws + (size_t)(blockIdx.x * 2 + team) * a.L.stride;
+    uint32_t local_gen = 0;
+    const int total = a.todo ? a.n_todo : a.nq;
+    while (true)
+    {
+        team_sync_all<NW>();
+        if (team_tid<NW>() == 0)
+            S.q = (int)atomicAdd(a.counter, 1u);
+        team_sync_all<NW>();
+        const int t = S.q;
+        if (t >= total)
+            break;
+        int q = a.todo ? a.todo[t] : t;
+        ++local_gen;
+        plan_team_query<NW, false>(m, p, a, q, ws, a.tag_base + local_gen, S, nullptr, D);
+    }
+}
+template <int NW>
+constexpr size_t duo_smem_bytes() { return 2 * ((sizeof(TeamShared<NW>) + 15) / 16 * 16) + sizeof(DuoSync) + 16; }
 
 // Cluster mode (see "cluster mode" above): CTA pair per team, blockIdx.x >> 1 = team, cluster rank = role.
 template <int NW, int MINB>
@@ -1582,10 +1672,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NW * 32, MINB)
     const int total = a.todo ? a.n_todo : a.nq;
     while (true)
     {
-        __syncthreads();
-        if (threadIdx.x == 0)
+        team_sync_all<NW>();
+        if (team_tid<NW>() == 0)
             S.q = (int)atomicAdd(a.counter, 1u);
-        __syncthreads();
+        team_sync_all<NW>();
         const int t = S.q;
         if (t >= total)
             break;
@@ -1594,7 +1684,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NW * 32, MINB)
         plan_team_query<NW, true>(m, p, a, q, ws, a.tag_base + local_gen, S, Hpeer);
     }
     // release the heuristic CTA: the last X of this cluster carries the exit command
-    if (threadIdx.x == 0)
+    if (team_tid<NW>() == 0)
         Hpeer->cmd = 1;
     cluster_arrive();
     cluster_wait();

@@ -114,7 +114,8 @@ MPROS_API uint64_t mpros_ctx_launch_count(mpros_ctx *ctx);
 
 /* Developer / tuning switches of one context. The MPROS_* environment variables give the defaults and are read ONCE, in
  * mpros_ctx_create; this call changes a switch afterwards (value NULL or "" = default). Keys and values:
- *   "c1_mode"   "2phase" (default) | "walk"               footprint kernel: pre-classified two-phase form / plain probe walk
+ *   "c1_mode"   "2phase" (default) | "2phase_ldg" | "walk" footprint kernel: pre-classified two-phase form with the pose stream
+ *                                                          staged by cp.async.bulk / the same without staging / plain probe walk
  *   "goal_mode" "cluster" (default) | "cluster8" | "grid"  N4 wavefront: 16-CTA cluster when granted / 8-CTA cluster / cooperative grid
  *   "plan_mode" "team" (default) | "cluster"               planner team = one CTA / a CTA pair on the two SMs of a TPC
  *   "debug"     "0" (default) | "1"                        per-pass timing on stderr

@@ -57,8 +57,8 @@ def main():
     banded.planner_config(params)
     starts, goals = synthetic.synthetic_queries(64, single.collision_check, single.layer("static"), synthetic.SYN_RES * synthetic.SYN_DS,
                                                 size * synthetic.SYN_RES, synthetic.SYN_QUERY_SEED)
-    ref = single.plan_batch(starts, goals, path_cap=64)
-    got = sharding.plan_batch_sharded(banded, starts, goals, 64, dist=dist, device="cuda")
+    ref = single.plan_batch(starts, goals, path_cap=128)
+    got = sharding.plan_batch_sharded(banded, starts, goals, 128, dist=dist, device="cuda")
     if not (np.array_equal(ref["status"], got["status"]) and np.array_equal(ref["cost"], got["cost"]) and
             np.array_equal(ref["iterations"], got["iterations"])):
         bad += 1

@@ -62,7 +62,7 @@ def test_headless_driver_matches_golden_plan(tmp_path, ci):
 
     # the five map messages main_planner.cpp:216-220 publishes (NavMap::get*MapMsg -> vecToMsg, nav_map.cpp:654-716), built by
     # the facade from mpros_map_layer_msg: geometry as the reference writes it, data byte-exact (FNV-1a-64) against the
-    # unmodified reference; the Voronoi message only where the canonical field equals the reference's (case 0)
+    # unmodified reference (the Voronoi message follows the canonical tie-break contract, tests/test_gpu_layer_msg.py)
     m = refapi.load_map(name)
     H, W = m["occupancy"].shape
     for layer in ["static", "voronoi", "static_orig", "inflate_orig", "goal"]:
@@ -74,7 +74,7 @@ def test_headless_driver_matches_golden_plan(tmp_path, ci):
         rm = refapi.RefMap(refapi.RefLib(), params)
         rm.set_occupancy(m["occupancy"], m["resolution"], m["origin"])
         rm.update_goal(goal[0], goal[1])
-        for layer in ["static", "static_orig", "inflate_orig", "goal"] + (["voronoi"] if ci == 0 else []):
+        for layer in ["static", "static_orig", "inflate_orig", "goal"]:
             data, _ = refapi.ref_layer_msg(rm, layer)
             h = 1469598103934665603
             for b in np.asarray(data, dtype=np.int8).view(np.uint8).tolist():

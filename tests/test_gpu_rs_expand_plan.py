@@ -248,10 +248,19 @@ def test_cluster_mode_gives_identical_plans(reflib, gpu_ctx_factory, monkeypatch
     a = ctx.plan_batch(starts, goals, path_cap=256)
     ctx.set_option("plan_mode", "cluster")
     b = ctx.plan_batch(starts, goals, path_cap=256)
+    # plan_mode=duo: two teams per CTA that keep their iterations in step (shared instruction-cache fills)
+    ctx.set_option("plan_mode", "duo")
+    d = ctx.plan_batch(starts, goals, path_cap=256)
+    d1 = ctx.plan_batch(starts[:1], goals[:1], path_cap=256)  # a lone team: its partner never becomes active
     ctx.set_option("plan_mode", None)
     assert (a["status"] == 1).sum() > 50
     for key in ["status", "cost", "path_len", "iterations", "primitives", "rs_shots", "paths"]:
         assert np.array_equal(a[key], b[key]), key
+        assert np.array_equal(a[key], d[key]), "duo: " + key
+        if key != "paths":  # rows past path_len are not written
+            assert np.array_equal(a[key][:1], d1[key]), "duo, one query: " + key
+    n0 = int(a["path_len"][0])
+    assert np.array_equal(a["paths"][0, :n0], d1["paths"][0, :n0])
     rp.close()
     rm.close()
 
