@@ -167,7 +167,7 @@ extern "C" int mpros_ctx_destroy(mpros_ctx *c)
     }
     free_plan_scratch(c); // node pools, open lists, closed sets of every lane (tens of GB at full size)
     void *bufs[] = {c->raw_bits, c->infl_bits, c->ds_bits, c->goal, c->obs_dist, c->edge_dist, c->region,
-                    c->edge_bits, c->voronoi, c->scratch, c->stage, c->raw_tw, c->infl_tw, c->unsafe_tw, c->cls_tw};
+                    c->edge_bits, c->voronoi, c->scratch, c->stage, c->dist_buf, c->raw_tw, c->infl_tw, c->unsafe_tw, c->cls_tw};
     for (void *b : bufs)
         if (b)
             cudaFree(b);

@@ -6,7 +6,7 @@
 #include <cmath>
 #include <cstring>
 
-#include "mpros_internal.cuh"
+#include "dist.cuh"
 
 namespace mpros
 {
@@ -606,7 +606,7 @@ static int map_inflate_rows(Ctx *c, int smax, int row0, int nrows)
 
 // stage 3: everything that needs the complete original-resolution layers: N2, the padded tile-word copies, N4 (if a goal is
 // set), N5-N9
-static int map_finish(Ctx *c)
+static int map_finish(Ctx *c, mpros_comm *cm = nullptr, int ds_rows_per_rank = 0)
 {
     cudaStream_t st = c->stream;
     // N2
@@ -664,7 +664,7 @@ static int map_finish(Ctx *c)
         if (rc)
             return rc;
     }
-    int rc = map_build_voronoi(c);
+    int rc = (cm && cm->world > 1) ? map_build_voronoi_banded(c, cm, ds_rows_per_rank) : map_build_voronoi(c);
     if (rc)
         return rc;
     MPROS_CUDA(cudaStreamSynchronize(st));
@@ -968,6 +968,97 @@ extern "C" int mpros_map_band_finish(mpros_ctx *c)
     }
     MPROS_CUDA(cudaSetDevice(c->device));
     return map_finish(c);
+}
+
+// ---- every stage on row bands, exchanges inside (include/mpros_gpu.h: mpros_map_set_occupancy_banded) -----------------
+// Bands are cut on the DOWN-SAMPLED grid (ceil(H / world) rows each, the last ranks may own fewer or none) so that the
+// same partition serves N1/N3 (ds rows of the original grid per down-sampled row) and N5-N9.
+static void band_partition(const Ctx *c, const mpros_comm *cm, int height, int *ds_rows_per_rank, int *row0, int *nrows)
+{
+    const int ds = c->mp.downsampling_factor;
+    const int Hd = (int)std::ceil(static_cast<double>(height) / ds);
+    const int world = cm ? cm->world : 1, rank = cm ? cm->rank : 0;
+    const int per = (Hd + world - 1) / world;
+    int lo, hi;
+    band_of(Hd, per, rank, &lo, &hi);
+    *ds_rows_per_rank = per;
+    const long long a = (long long)lo * ds, b = (long long)hi * ds;
+    *row0 = (int)std::min<long long>(a, height);
+    *nrows = (int)std::min<long long>(b, height) - *row0;
+}
+
+extern "C" int mpros_map_band_rows(mpros_ctx *c, const mpros_comm *cm, int height, int *row0, int *nrows)
+{
+    if (!c || !row0 || !nrows || height <= 0)
+    {
+        set_error("mpros_map_band_rows: invalid argument");
+        return MPROS_ERR_INVALID;
+    }
+    int per;
+    band_partition(c, cm, height, &per, row0, nrows);
+    return MPROS_OK;
+}
+
+static int set_occupancy_banded_impl(mpros_ctx *c, mpros_comm *cm, const int8_t *rows, bool on_device, int width, int height,
+                                     double resolution, double origin_x, double origin_y, double origin_yaw)
+{
+    if (!c || !rows || width <= 0 || height <= 0 || !(resolution > 0))
+    {
+        set_error("mpros_map_set_occupancy_banded: invalid argument");
+        return MPROS_ERR_INVALID;
+    }
+    MPROS_CUDA(cudaSetDevice(c->device));
+    int have_old = 0;
+    int rc = map_begin(c, width, height, resolution, origin_x, origin_y, origin_yaw, &have_old);
+    if (rc)
+        return rc;
+    int smax = -1;
+    rc = map_inflate_prepare(c, &smax, nullptr);
+    if (rc)
+        return rc;
+    int per_ds, row0, nrows;
+    band_partition(c, cm, height, &per_ds, &row0, &nrows);
+    const int per0 = per_ds * c->mp.downsampling_factor;
+    // N1 on the band: a rank uploads and reads only its own rows of the int8 grid
+    if (nrows > 0)
+    {
+        const int8_t *d_rows = rows;
+        if (!on_device)
+        {
+            const size_t bytes = (size_t)nrows * width;
+            rc = ensure_stage(c, bytes);
+            if (rc)
+                return rc;
+            MPROS_CUDA(cudaMemcpyAsync(c->stage, rows, bytes, cudaMemcpyHostToDevice, c->stream));
+            d_rows = static_cast<const int8_t *>(c->stage);
+        }
+        rc = map_threshold_rows(c, d_rows, row0, nrows, have_old);
+        if (rc)
+            return rc;
+    }
+    // every rank needs the complete raw layer anyway (collision layer of the planner): gathering it BEFORE N3 also brings
+    // the rows of the neighbouring bands the structuring element reaches into, so no separate halo exchange is needed
+    rc = comm_allgather_rows(c, cm, c->raw_bits, (size_t)c->pitch0 * 4, c->H0, per0);
+    if (rc)
+        return rc;
+    rc = map_inflate_rows(c, smax, row0, nrows); // N3 on the band
+    if (rc)
+        return rc;
+    rc = comm_allgather_rows(c, cm, c->infl_bits, (size_t)c->pitch0 * 4, c->H0, per0);
+    if (rc)
+        return rc;
+    return map_finish(c, cm, per_ds); // N2 + probe layouts (replicated, one pass over the bits), N4, N5-N9 banded
+}
+
+extern "C" int mpros_map_set_occupancy_banded(mpros_ctx *c, mpros_comm *cm, const int8_t *rows, int width, int height, double resolution,
+                                              double origin_x, double origin_y, double origin_yaw)
+{
+    return set_occupancy_banded_impl(c, cm, rows, false, width, height, resolution, origin_x, origin_y, origin_yaw);
+}
+extern "C" int mpros_map_set_occupancy_banded_dev(mpros_ctx *c, mpros_comm *cm, const int8_t *d_rows, int width, int height,
+                                                  double resolution, double origin_x, double origin_y, double origin_yaw)
+{
+    return set_occupancy_banded_impl(c, cm, d_rows, true, width, height, resolution, origin_x, origin_y, origin_yaw);
 }
 
 extern "C" int mpros_map_get_info(mpros_ctx *c, mpros_map_info *o)

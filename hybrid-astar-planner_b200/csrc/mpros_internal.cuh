@@ -151,6 +151,8 @@ struct Ctx
     size_t scratch_bytes = 0;
     void *stage = nullptr; // device staging for host-pointer entry points
     size_t stage_bytes = 0;
+    void *dist_buf = nullptr; // per-query arrays of ALL ranks' queries (mpros_plan_batch_sharded, dist.cu)
+    size_t dist_bytes = 0;
     // plan lanes 1 .. MPROS_PLAN_LANES-1 (batches in flight beside the context's own stream, plan.cu); created on first use
     cudaStream_t lane_stream[MPROS_PLAN_LANES] = {};
     cudaEvent_t lane_event[MPROS_PLAN_LANES] = {};

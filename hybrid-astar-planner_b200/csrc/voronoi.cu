@@ -12,7 +12,7 @@
 // rules: region_ of a free cell = the SMALLEST region id among all nearest obstacle cells (the reference always
 // holds *a* nearest region); obstacle-side edge flags follow the "first differing neighbour" rule without the
 // processing-order condition. obs_dist_ is order-independent and bit-exact.
-#include "mpros_internal.cuh"
+#include "dist.cuh"
 
 namespace mpros
 {
@@ -110,8 +110,11 @@ __global__ void __launch_bounds__(256) ccl_merge_kernel(const uint32_t *__restri
 }
 
 // flatten + count roots per 1024-cell tile; local rank of every root inside its tile
+// groot (banded form only, else nullptr): for a local root that touches the band's first or last row, the GLOBAL root of
+// its component after the seam union (global cell index); a component whose global root lies in another band is not
+// counted here.
 __global__ void __launch_bounds__(1024) ccl_flatten_rank_kernel(int *__restrict__ parent, size_t total, int *__restrict__ local_rank,
-                                                                int *__restrict__ tile_count)
+                                                                int *__restrict__ tile_count, const int *__restrict__ groot, int base)
 {
     __shared__ int warp_sum[32];
     size_t k = (size_t)blockIdx.x * 1024 + threadIdx.x;
@@ -123,6 +126,11 @@ __global__ void __launch_bounds__(1024) ccl_flatten_rank_kernel(int *__restrict_
         {
             p = uf_find(parent, (int)k);
             root = ((size_t)p == k);
+            if (root && groot)
+            {
+                const int gr = groot[k];
+                root = gr < 0 || gr == (int)k + base;
+            }
         }
         // flattening is finished by ccl_region_kernel (roots are stable here, chains still may exist)
     }
@@ -180,9 +188,13 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(int *__restrict__ tile
         *n_regions = part[1023];
 }
 
+// root_region (banded form only): final region id of the local roots that touch a band boundary (-1 elsewhere);
+// id_offset = number of components whose first cell lies in an earlier band.
 __global__ void __launch_bounds__(256) ccl_region_kernel(const int *__restrict__ parent, size_t total, const int *__restrict__ local_rank,
-                                                         const int *__restrict__ tile_offset, int *__restrict__ region)
+                                                         const int *__restrict__ tile_offset, int *__restrict__ region,
+                                                         const int *__restrict__ root_region, const int *__restrict__ id_offset)
 {
+    const int add = id_offset ? *id_offset : 0;
     for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x)
     {
         int p = parent[k];
@@ -190,7 +202,8 @@ __global__ void __launch_bounds__(256) ccl_region_kernel(const int *__restrict__
         if (p >= 0)
         {
             int root = uf_find(parent, (int)k);
-            r = tile_offset[root >> 10] + local_rank[root];
+            const int rr = root_region ? root_region[root] : -1;
+            r = rr >= 0 ? rr : add + tile_offset[root >> 10] + local_rank[root];
         }
         region[k] = r;
     }
@@ -268,7 +281,13 @@ __global__ void __launch_bounds__(256) dt_row_kernel(const uint32_t *__restrict_
 // aggregates in shared memory -> sweep of the chunk seeded with it. Block = 32 columns x 32 chunks; a warp reads 32
 // consecutive keys of one row (256 B). The old one-thread-per-column sweep (1024 dependent steps, 8 CTAs) took 613 us
 // per call at 1024^2 and was 72 % of the whole map preprocessing.
-__global__ void __launch_bounds__(1024) dt_col_kernel(unsigned long long *__restrict__ key, int H, int W)
+// Banded form (rows [0, H) of `key` are rows [row0, row0 + H) of a grid tiled across `world` ranks): band_agg holds, per
+// rank g and column, the two aggregates of that band's ROW-pass keys, [g][0][j] = min key + (Hg - i) and [g][1][j] = min key + i
+// (i global). The forward sweep is seeded with the minimum of the earlier bands' first aggregate, the backward sweep with
+// the later bands' second one: a source in a later band reaches row i at key + (i' - i) whether or not its own forward
+// value was smaller, so the aggregates of the row-pass keys are enough and ONE exchange serves both sweeps.
+__global__ void __launch_bounds__(1024) dt_col_kernel(unsigned long long *__restrict__ key, int H, int W, int row0, int Hg,
+                                                      const unsigned long long *__restrict__ band_agg, int rank, int world)
 {
     __shared__ unsigned long long agg[32][33];
     const int x = threadIdx.x, y = threadIdx.y;
@@ -276,17 +295,31 @@ __global__ void __launch_bounds__(1024) dt_col_kernel(unsigned long long *__rest
     const int R = (H + 31) / 32;
     const int i0 = min(H, y * R), i1 = min(H, i0 + R);
     const bool live = j < W;
+    unsigned long long seed_f = ~0ull, seed_b = ~0ull;
+    if (band_agg && live)
+    {
+        for (int g = 0; g < rank; ++g)
+        {
+            const unsigned long long v = band_agg[((size_t)g * 2 + 0) * W + j];
+            seed_f = v < seed_f ? v : seed_f;
+        }
+        for (int g = rank + 1; g < world; ++g)
+        {
+            const unsigned long long v = band_agg[((size_t)g * 2 + 1) * W + j];
+            seed_b = v < seed_b ? v : seed_b;
+        }
+    }
     // forward: aggregate of key[i] + (H - i)
     unsigned long long a = ~0ull;
     if (live)
         for (int i = i0; i < i1; ++i)
         {
-            unsigned long long v = key[(size_t)i * W + j] + (unsigned long long)(H - i) * kOne;
+            unsigned long long v = key[(size_t)i * W + j] + (unsigned long long)(Hg - (row0 + i)) * kOne;
             a = v < a ? v : a;
         }
     agg[y][x] = a;
     __syncthreads();
-    unsigned long long run = ~0ull;
+    unsigned long long run = seed_f;
     for (int c = 0; c < y; ++c)
     {
         unsigned long long v = agg[c][x];
@@ -298,17 +331,17 @@ __global__ void __launch_bounds__(1024) dt_col_kernel(unsigned long long *__rest
     if (live)
         for (int i = i0; i < i1; ++i)
         {
-            const unsigned long long off = (unsigned long long)(H - i) * kOne;
+            const unsigned long long off = (unsigned long long)(Hg - (row0 + i)) * kOne;
             unsigned long long v = key[(size_t)i * W + j] + off;
             run = v < run ? v : run;
             const unsigned long long f = run - off;
             key[(size_t)i * W + j] = f;
-            const unsigned long long b = f + (unsigned long long)i * kOne;
+            const unsigned long long b = f + (unsigned long long)(row0 + i) * kOne;
             a = b < a ? b : a;
         }
     agg[y][x] = a;
     __syncthreads();
-    run = ~0ull;
+    run = seed_b;
     for (int c = y + 1; c < 32; ++c)
     {
         unsigned long long v = agg[c][x];
@@ -318,11 +351,44 @@ __global__ void __launch_bounds__(1024) dt_col_kernel(unsigned long long *__rest
     if (live)
         for (int i = i1 - 1; i >= i0; --i)
         {
-            const unsigned long long off = (unsigned long long)i * kOne;
+            const unsigned long long off = (unsigned long long)(row0 + i) * kOne;
             unsigned long long v = key[(size_t)i * W + j] + off;
             run = v < run ? v : run;
             key[(size_t)i * W + j] = run - off;
         }
+}
+
+// The two aggregates of one band's row-pass keys per column (see dt_col_kernel): out[0][j], out[1][j]. ~0 for an empty band.
+__global__ void __launch_bounds__(1024) dt_col_agg_kernel(const unsigned long long *__restrict__ key, int H, int W, int row0, int Hg,
+                                                          unsigned long long *__restrict__ out)
+{
+    __shared__ unsigned long long sf[32][33], sb[32][33];
+    const int x = threadIdx.x, y = threadIdx.y;
+    const int j = blockIdx.x * 32 + x;
+    const int R = (H + 31) / 32;
+    const int i0 = min(H, y * R), i1 = min(H, i0 + R);
+    unsigned long long f = ~0ull, b = ~0ull;
+    if (j < W)
+        for (int i = i0; i < i1; ++i)
+        {
+            const unsigned long long k = key[(size_t)i * W + j];
+            const unsigned long long vf = k + (unsigned long long)(Hg - (row0 + i)) * kOne, vb = k + (unsigned long long)(row0 + i) * kOne;
+            f = vf < f ? vf : f;
+            b = vb < b ? vb : b;
+        }
+    sf[y][x] = f;
+    sb[y][x] = b;
+    __syncthreads();
+    if (y == 0 && j < W)
+    {
+        for (int c = 1; c < 32; ++c)
+        {
+            f = sf[c][x] < f ? sf[c][x] : f;
+            b = sb[c][x] < b ? sb[c][x] : b;
+        }
+        out[j] = f;
+        out[(size_t)W + j] = b;
+    }
 }
 
 // N6 epilogue: cap (>= 1000 stays 1000 / region -1), keep obstacle cells' own labels
@@ -374,14 +440,14 @@ __device__ __forceinline__ int first_differing(const int *__restrict__ region, i
 
 __global__ void __launch_bounds__(256) edge_kernel(const uint32_t *__restrict__ occ, const uint16_t *__restrict__ obs_dist,
                                                    const int *__restrict__ region, int H, int W, int pitch,
-                                                   uint32_t *__restrict__ edge_bits)
+                                                   uint32_t *__restrict__ edge_bits, int row0, int nrows)
 {
     const int wpr = (W + 31) >> 5;
-    const size_t total_words = (size_t)H * wpr;
+    const size_t first_word = (size_t)row0 * wpr, total_words = (size_t)(row0 + nrows) * wpr;
     const int lane = threadIdx.x & 31;
     size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    for (size_t wd = warp; wd < total_words; wd += nwarps)
+    for (size_t wd = first_word + warp; wd < total_words; wd += nwarps)
     {
         int i = (int)(wd / wpr), w = (int)(wd % wpr);
         int j = (w << 5) + lane;
@@ -475,18 +541,18 @@ int map_build_voronoi(Ctx *c)
     MPROS_LAUNCH_CHECK(c);
     ccl_merge_kernel<<<grid_for(c, cells), 256, 0, st>>>(c->ds_bits, H, W, pitch, parent);
     MPROS_LAUNCH_CHECK(c);
-    ccl_flatten_rank_kernel<<<n_tiles, 1024, 0, st>>>(parent, cells, local_rank, tile_count);
+    ccl_flatten_rank_kernel<<<n_tiles, 1024, 0, st>>>(parent, cells, local_rank, tile_count, nullptr, 0);
     MPROS_LAUNCH_CHECK(c);
     scan_tiles_kernel<<<1, 1024, 0, st>>>(tile_count, n_tiles, d_nreg);
     MPROS_LAUNCH_CHECK(c);
-    ccl_region_kernel<<<grid_for(c, cells), 256, 0, st>>>(parent, cells, local_rank, tile_count, c->region);
+    ccl_region_kernel<<<grid_for(c, cells), 256, 0, st>>>(parent, cells, local_rank, tile_count, c->region, nullptr, nullptr);
     MPROS_LAUNCH_CHECK(c);
     MPROS_CUDA(cudaMemcpyAsync(&c->num_regions, d_nreg, sizeof(int), cudaMemcpyDeviceToHost, st));
 
     // N6
     dt_row_kernel<<<grid_for(c, cells), 256, 0, st>>>(c->ds_bits, H, W, pitch, c->region, key);
     MPROS_LAUNCH_CHECK(c);
-    dt_col_kernel<<<cdiv(W, 32), dim3(32, 32), 0, st>>>(key, H, W);
+    dt_col_kernel<<<cdiv(W, 32), dim3(32, 32), 0, st>>>(key, H, W, 0, H, nullptr, 0, 1);
     MPROS_LAUNCH_CHECK(c);
     obs_finish_kernel<<<grid_for(c, cells), 256, 0, st>>>(key, cells, c->obs_dist, c->region);
     MPROS_LAUNCH_CHECK(c);
@@ -494,13 +560,13 @@ int map_build_voronoi(Ctx *c)
     // N7
     size_t words = (size_t)H * ((W + 31) / 32);
     MPROS_CUDA(cudaMemsetAsync(c->edge_bits, 0, (size_t)H * pitch * 4, st));
-    edge_kernel<<<grid_for(c, words * 32), 256, 0, st>>>(c->ds_bits, c->obs_dist, c->region, H, W, pitch, c->edge_bits);
+    edge_kernel<<<grid_for(c, words * 32), 256, 0, st>>>(c->ds_bits, c->obs_dist, c->region, H, W, pitch, c->edge_bits, 0, H);
     MPROS_LAUNCH_CHECK(c);
 
     // N8
     dt_row_kernel<<<grid_for(c, cells), 256, 0, st>>>(c->edge_bits, H, W, pitch, nullptr, key);
     MPROS_LAUNCH_CHECK(c);
-    dt_col_kernel<<<cdiv(W, 32), dim3(32, 32), 0, st>>>(key, H, W);
+    dt_col_kernel<<<cdiv(W, 32), dim3(32, 32), 0, st>>>(key, H, W, 0, H, nullptr, 0, 1);
     MPROS_LAUNCH_CHECK(c);
     edge_finish_kernel<<<grid_for(c, cells), 256, 0, st>>>(key, cells, c->edge_dist);
     MPROS_LAUNCH_CHECK(c);
@@ -510,6 +576,336 @@ int map_build_voronoi(Ctx *c)
                                                         c->mp.voro_fallout_rate, c->mp.voro_max_region, c->voronoi);
     MPROS_LAUNCH_CHECK(c);
     return MPROS_OK;
+}
+
+// ---- N5-N9 on ROW BANDS of the down-sampled grid, one band per rank -----------------------------------
+// The exchanges (all in-place all-gathers over the communicator, NCCL over NVLink on the box):
+//   N5  (1) labels + same-component representatives of every band's first and last row   4 W int32 per rank
+//       (2) number of components that start in the band + region ids of the boundary cells (2 W + 4) int32 per rank
+//   N6  (3) the two column aggregates of the band's row-pass keys (the carry rows of the two sweeps)   2 W uint64 per rank
+//       (4, 5) the band's rows of obs_dist_ and region_ (N7 looks two rows beyond the band)
+//   N8  (6) as (3) for the edge distance
+//   N9  (7-9) the band's rows of isedge_, edge_dist_ and the Voronoi cost: every rank ends with complete layers
+// The result is bit-identical to map_build_voronoi on one GPU (tests/test_gpu_banded_voronoi.py).
+//
+// Seam union of the component labelling: node = a boundary cell of some band, id (g * 2 + side) * W + j. Every rank solves
+// the same small union-find over the gathered nodes: a node starts under the smallest node of its own band with the same
+// local root (computed by the owning band, exchange 1), vertical contacts across a seam are united, and the merged
+// component's global root is the smallest local root (= its first cell in raster order).
+__global__ void __launch_bounds__(256) ccl_boundary_mark_kernel(const uint32_t *__restrict__ occ, int n, int W, int pitch,
+                                                                const int *__restrict__ parent, int node_base, int *__restrict__ bnode)
+{
+    const int total = 2 * W;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x)
+    {
+        const int s = t / W, j = t % W;
+        const int i = s ? n - 1 : 0;
+        if (n <= 0 || !((occ[(size_t)i * pitch + (j >> 5)] >> (j & 31)) & 1u))
+            continue;
+        const int root = uf_find(parent, i * W + j);
+        atomicMin(&bnode[root], node_base + t);
+    }
+}
+// pack = [label top | label bottom | representative top | representative bottom], W entries each; label = global cell index
+// of the local root, -1 for free cells and for an empty band
+__global__ void __launch_bounds__(256) ccl_boundary_pack_kernel(const uint32_t *__restrict__ occ, int n, int W, int pitch,
+                                                                const int *__restrict__ parent, const int *__restrict__ bnode, int base,
+                                                                int *__restrict__ pack)
+{
+    const int total = 2 * W;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x)
+    {
+        const int s = t / W, j = t % W;
+        const int i = s ? n - 1 : 0;
+        int lab = -1, rep = -1;
+        if (n > 0 && ((occ[(size_t)i * pitch + (j >> 5)] >> (j & 31)) & 1u))
+        {
+            const int root = uf_find(parent, i * W + j);
+            lab = root + base;
+            rep = bnode[root];
+        }
+        pack[t] = lab;
+        pack[2 * W + t] = rep;
+    }
+}
+__global__ void __launch_bounds__(256) seam_init_kernel(const int *__restrict__ pack_all, int world, int W, int *__restrict__ sp)
+{
+    const int total = world * 2 * W;
+    for (int nd = blockIdx.x * blockDim.x + threadIdx.x; nd < total; nd += gridDim.x * blockDim.x)
+    {
+        const int g = nd / (2 * W), t = nd % (2 * W);
+        const int *pk = pack_all + (size_t)g * 4 * W;
+        sp[nd] = pk[t] >= 0 ? pk[2 * W + t] : -1;
+    }
+}
+__global__ void __launch_bounds__(256) seam_union_kernel(const int *__restrict__ pack_all, int world, int W, int *__restrict__ sp)
+{
+    const int total = (world - 1) * W;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x)
+    {
+        const int g = t / W, j = t % W;
+        const int below = pack_all[(size_t)g * 4 * W + W + j];       // last row of band g
+        const int above = pack_all[(size_t)(g + 1) * 4 * W + j];     // first row of band g + 1
+        if (below >= 0 && above >= 0)
+            uf_union(sp, (g * 2 + 1) * W + j, ((g + 1) * 2) * W + j);
+    }
+}
+__global__ void __launch_bounds__(256) seam_glabel_kernel(const int *__restrict__ pack_all, int world, int W, const int *__restrict__ sp,
+                                                          int *__restrict__ glabel)
+{
+    const int total = world * 2 * W;
+    for (int nd = blockIdx.x * blockDim.x + threadIdx.x; nd < total; nd += gridDim.x * blockDim.x)
+    {
+        const int g = nd / (2 * W), t = nd % (2 * W);
+        const int lab = pack_all[(size_t)g * 4 * W + t];
+        if (lab >= 0)
+            atomicMin(&glabel[uf_find(sp, nd)], lab);
+    }
+}
+// my boundary cells: global root of the local root (same value from every cell of the root: benign race)
+__global__ void __launch_bounds__(256) seam_apply_kernel(const int *__restrict__ pack_mine, int W, int node_base, int base,
+                                                         const int *__restrict__ sp, const int *__restrict__ glabel, int *__restrict__ groot)
+{
+    const int total = 2 * W;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x)
+    {
+        const int lab = pack_mine[t];
+        if (lab >= 0)
+            groot[lab - base] = glabel[uf_find(sp, node_base + t)];
+    }
+}
+// gid = [components that start in this band, 0, 0, 0 | id (without the earlier bands' count) of the boundary cells whose
+// component starts in this band, -1 otherwise]
+__global__ void __launch_bounds__(256) seam_gid_kernel(const int *__restrict__ pack_mine, int W, int base, const int *__restrict__ groot,
+                                                       const int *__restrict__ local_rank, const int *__restrict__ tile_offset,
+                                                       const int *__restrict__ n_local, int *__restrict__ gid)
+{
+    const int total = 2 * W;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x)
+    {
+        if (t < 4)
+            gid[t] = t == 0 ? *n_local : 0;
+        const int lab = pack_mine[t];
+        int v = -1;
+        if (lab >= 0)
+        {
+            const int root = lab - base;
+            if (groot[root] == lab)
+                v = tile_offset[root >> 10] + local_rank[root];
+        }
+        gid[4 + t] = v;
+    }
+}
+__global__ void __launch_bounds__(256) seam_regid_kernel(const int *__restrict__ pack_all, const int *__restrict__ gid_all, int world, int W,
+                                                         const int *__restrict__ sp, int *__restrict__ regid)
+{
+    const int total = world * 2 * W;
+    for (int nd = blockIdx.x * blockDim.x + threadIdx.x; nd < total; nd += gridDim.x * blockDim.x)
+    {
+        const int g = nd / (2 * W), t = nd % (2 * W);
+        if (pack_all[(size_t)g * 4 * W + t] < 0)
+            continue;
+        const int v = gid_all[(size_t)g * (2 * W + 4) + 4 + t];
+        if (v < 0)
+            continue;
+        int before = 0;
+        for (int e = 0; e < g; ++e)
+            before += gid_all[(size_t)e * (2 * W + 4)];
+        regid[uf_find(sp, nd)] = before + v;
+    }
+}
+// final region id of my boundary-touching local roots; also the id offset of this band and the total number of regions
+__global__ void __launch_bounds__(256) seam_root_region_kernel(const int *__restrict__ pack_mine, const int *__restrict__ gid_all, int world,
+                                                               int rank, int W, int node_base, int base, const int *__restrict__ sp,
+                                                               const int *__restrict__ regid, int *__restrict__ root_region,
+                                                               int *__restrict__ id_offset /* [0] offset, [1] total */)
+{
+    const int total = 2 * W;
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        int before = 0, all = 0;
+        for (int e = 0; e < world; ++e)
+        {
+            const int v = gid_all[(size_t)e * (2 * W + 4)];
+            if (e < rank)
+                before += v;
+            all += v;
+        }
+        id_offset[0] = before;
+        id_offset[1] = all;
+    }
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x)
+    {
+        const int lab = pack_mine[t];
+        if (lab >= 0)
+            root_region[lab - base] = regid[uf_find(sp, node_base + t)];
+    }
+}
+
+int map_build_voronoi_banded(Ctx *c, mpros_comm *cm, int rows_per_rank)
+{
+    cudaStream_t st = c->stream;
+    const int H = c->H, W = c->W, pitch = c->pitch;
+    const int world = cm->world, rank = cm->rank;
+    if ((unsigned long long)H * (unsigned long long)W >= 0x7f000000ull) // labels are int32 cell indices below the 0x7f7f7f7f fill
+    {
+        set_error("banded map: the down-sampled grid must have fewer than 2^31 - 2^24 cells");
+        return MPROS_ERR_INVALID;
+    }
+    int lo, hi;
+    band_of(H, rows_per_rank, rank, &lo, &hi);
+    const int n = hi - lo;
+    const size_t cells = (size_t)n * W;
+    const int base = lo * W;
+    const int n_tiles = (int)((cells + 1023) / 1024);
+    const int nodes = world * 2 * W, node_base = rank * 2 * W;
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    // scratch: key u64[cells] | parent, local_rank, bnode (later root_region), groot i32[cells] | tile_count | counters |
+    //          pack_all i32[world * 4 W] | gid_all i32[world * (2 W + 4)] | sp, glabel, regid i32[nodes] | agg u64[world * 2 W]
+    const size_t b_key = up(cells * 8), b_cell = up(cells * 4), b_tiles = up((size_t)n_tiles * 4 + 4), b_cnt = 256,
+                 b_pack = up((size_t)world * 4 * W * 4), b_gid = up((size_t)world * (2 * W + 4) * 4), b_node = up((size_t)nodes * 4),
+                 b_agg = up((size_t)world * 2 * W * 8);
+    const size_t need = b_key + 4 * b_cell + b_tiles + b_cnt + b_pack + b_gid + 3 * b_node + b_agg;
+    int rc = ensure_scratch(c, need);
+    if (rc)
+        return rc;
+    char *p = static_cast<char *>(c->scratch);
+    unsigned long long *key = (unsigned long long *)p;
+    int *parent = (int *)(p += b_key);
+    int *local_rank = (int *)(p += b_cell);
+    int *bnode = (int *)(p += b_cell);
+    int *groot = (int *)(p += b_cell);
+    int *tile_count = (int *)(p += b_cell);
+    int *counters = (int *)(p += b_tiles); // [0] components that start in this band, [1] id offset, [2] total regions
+    int *pack_all = (int *)(p += b_cnt);
+    int *gid_all = (int *)(p += b_pack);
+    int *sp = (int *)(p += b_gid);
+    int *glabel = (int *)(p += b_node);
+    int *regid = (int *)(p += b_node);
+    unsigned long long *agg = (unsigned long long *)(p += b_node);
+    int *root_region = bnode;
+    int *pack_mine = pack_all + (size_t)rank * 4 * W;
+    int *gid_mine = gid_all + (size_t)rank * (2 * W + 4);
+
+    const uint32_t *occ = c->ds_bits + (size_t)lo * pitch;
+    int *region = c->region + (size_t)lo * W;
+    const int g2w = grid_for(c, (size_t)2 * W), gnodes = grid_for(c, (size_t)nodes);
+
+    // N5: local components of the band
+    if (n > 0)
+    {
+        ccl_init_kernel<<<grid_for(c, cells), 256, 0, st>>>(occ, n, W, pitch, parent);
+        MPROS_LAUNCH_CHECK(c);
+        ccl_merge_kernel<<<grid_for(c, cells), 256, 0, st>>>(occ, n, W, pitch, parent);
+        MPROS_LAUNCH_CHECK(c);
+    }
+    MPROS_CUDA(cudaMemsetAsync(bnode, 0x7f, b_cell, st));
+    MPROS_CUDA(cudaMemsetAsync(groot, 0xff, b_cell, st));
+    ccl_boundary_mark_kernel<<<g2w, 256, 0, st>>>(occ, n, W, pitch, parent, node_base, bnode);
+    MPROS_LAUNCH_CHECK(c);
+    ccl_boundary_pack_kernel<<<g2w, 256, 0, st>>>(occ, n, W, pitch, parent, bnode, base, pack_mine);
+    MPROS_LAUNCH_CHECK(c);
+    rc = comm_allgather(c, cm, pack_all, (size_t)4 * W * 4); // exchange 1
+    if (rc)
+        return rc;
+    seam_init_kernel<<<gnodes, 256, 0, st>>>(pack_all, world, W, sp);
+    MPROS_LAUNCH_CHECK(c);
+    if (world > 1)
+    {
+        seam_union_kernel<<<grid_for(c, (size_t)(world - 1) * W), 256, 0, st>>>(pack_all, world, W, sp);
+        MPROS_LAUNCH_CHECK(c);
+    }
+    MPROS_CUDA(cudaMemsetAsync(glabel, 0x7f, b_node, st));
+    seam_glabel_kernel<<<gnodes, 256, 0, st>>>(pack_all, world, W, sp, glabel);
+    MPROS_LAUNCH_CHECK(c);
+    seam_apply_kernel<<<g2w, 256, 0, st>>>(pack_mine, W, node_base, base, sp, glabel, groot);
+    MPROS_LAUNCH_CHECK(c);
+    // components whose first cell (raster order) lies in this band, ranked in raster order
+    MPROS_CUDA(cudaMemsetAsync(counters, 0, b_cnt, st));
+    if (n > 0)
+    {
+        ccl_flatten_rank_kernel<<<n_tiles, 1024, 0, st>>>(parent, cells, local_rank, tile_count, groot, base);
+        MPROS_LAUNCH_CHECK(c);
+        scan_tiles_kernel<<<1, 1024, 0, st>>>(tile_count, n_tiles, counters);
+        MPROS_LAUNCH_CHECK(c);
+    }
+    seam_gid_kernel<<<g2w, 256, 0, st>>>(pack_mine, W, base, groot, local_rank, tile_count, counters, gid_mine);
+    MPROS_LAUNCH_CHECK(c);
+    rc = comm_allgather(c, cm, gid_all, (size_t)(2 * W + 4) * 4); // exchange 2
+    if (rc)
+        return rc;
+    MPROS_CUDA(cudaMemsetAsync(regid, 0xff, b_node, st));
+    seam_regid_kernel<<<gnodes, 256, 0, st>>>(pack_all, gid_all, world, W, sp, regid);
+    MPROS_LAUNCH_CHECK(c);
+    MPROS_CUDA(cudaMemsetAsync(root_region, 0xff, b_cell, st)); // bnode is no longer needed
+    seam_root_region_kernel<<<g2w, 256, 0, st>>>(pack_mine, gid_all, world, rank, W, node_base, base, sp, regid, root_region, counters + 1);
+    MPROS_LAUNCH_CHECK(c);
+    if (n > 0)
+    {
+        ccl_region_kernel<<<grid_for(c, cells), 256, 0, st>>>(parent, cells, local_rank, tile_count, region, root_region, counters + 1);
+        MPROS_LAUNCH_CHECK(c);
+    }
+    MPROS_CUDA(cudaMemcpyAsync(&c->num_regions, counters + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+
+    // N6
+    unsigned long long *agg_mine = agg + (size_t)rank * 2 * W;
+    if (n > 0)
+    {
+        dt_row_kernel<<<grid_for(c, cells), 256, 0, st>>>(occ, n, W, pitch, region, key);
+        MPROS_LAUNCH_CHECK(c);
+    }
+    dt_col_agg_kernel<<<cdiv(W, 32), dim3(32, 32), 0, st>>>(key, n, W, lo, H, agg_mine);
+    MPROS_LAUNCH_CHECK(c);
+    rc = comm_allgather(c, cm, agg, (size_t)2 * W * 8); // exchange 3: the carry rows of both sweeps
+    if (rc)
+        return rc;
+    if (n > 0)
+    {
+        dt_col_kernel<<<cdiv(W, 32), dim3(32, 32), 0, st>>>(key, n, W, lo, H, agg, rank, world);
+        MPROS_LAUNCH_CHECK(c);
+        obs_finish_kernel<<<grid_for(c, cells), 256, 0, st>>>(key, cells, c->obs_dist + (size_t)lo * W, region);
+        MPROS_LAUNCH_CHECK(c);
+    }
+    rc = comm_allgather_rows(c, cm, c->obs_dist, (size_t)W * 2, H, rows_per_rank); // exchange 4
+    if (!rc)
+        rc = comm_allgather_rows(c, cm, c->region, (size_t)W * 4, H, rows_per_rank); // exchange 5
+    if (rc)
+        return rc;
+
+    // N7 (reads obs_dist_ / region_ up to two rows beyond the band)
+    uint32_t *edge = c->edge_bits + (size_t)lo * pitch;
+    if (n > 0)
+    {
+        MPROS_CUDA(cudaMemsetAsync(edge, 0, (size_t)n * pitch * 4, st));
+        size_t words = (size_t)n * ((W + 31) / 32);
+        edge_kernel<<<grid_for(c, words * 32), 256, 0, st>>>(c->ds_bits, c->obs_dist, c->region, H, W, pitch, c->edge_bits, lo, n);
+        MPROS_LAUNCH_CHECK(c);
+        // N8
+        dt_row_kernel<<<grid_for(c, cells), 256, 0, st>>>(edge, n, W, pitch, nullptr, key);
+        MPROS_LAUNCH_CHECK(c);
+    }
+    dt_col_agg_kernel<<<cdiv(W, 32), dim3(32, 32), 0, st>>>(key, n, W, lo, H, agg_mine);
+    MPROS_LAUNCH_CHECK(c);
+    rc = comm_allgather(c, cm, agg, (size_t)2 * W * 8); // exchange 6
+    if (rc)
+        return rc;
+    if (n > 0)
+    {
+        dt_col_kernel<<<cdiv(W, 32), dim3(32, 32), 0, st>>>(key, n, W, lo, H, agg, rank, world);
+        MPROS_LAUNCH_CHECK(c);
+        edge_finish_kernel<<<grid_for(c, cells), 256, 0, st>>>(key, cells, c->edge_dist + (size_t)lo * W);
+        MPROS_LAUNCH_CHECK(c);
+        // N9
+        voronoi_cost_kernel<<<grid_for(c, cells), 256, 0, st>>>(occ, edge, c->obs_dist + (size_t)lo * W, c->edge_dist + (size_t)lo * W, n, W,
+                                                            pitch, c->mp.voro_fallout_rate, c->mp.voro_max_region, c->voronoi + (size_t)lo * W);
+        MPROS_LAUNCH_CHECK(c);
+    }
+    rc = comm_allgather_rows(c, cm, c->edge_bits, (size_t)pitch * 4, H, rows_per_rank); // exchanges 7-9
+    if (!rc)
+        rc = comm_allgather_rows(c, cm, c->edge_dist, (size_t)W * 2, H, rows_per_rank);
+    if (!rc)
+        rc = comm_allgather_rows(c, cm, c->voronoi, (size_t)W * 4, H, rows_per_rank);
+    return rc;
 }
 
 } // namespace mpros

@@ -162,6 +162,17 @@ def load_library(path=LIB_PATH):
     L.mpros_plan_lane_stream.argtypes = [vp, i]
     L.mpros_ctx_set_option.argtypes = [vp, C.c_char_p, C.c_char_p]
     L.mpros_plan_release_workspaces.argtypes = [vp]
+    L.mpros_comm_unique_id.argtypes = [vp]
+    L.mpros_comm_create_nccl.argtypes = [vp, i, i, vp, C.POINTER(vp)]
+    L.mpros_comm_adopt_nccl.argtypes = [i, i, vp, C.POINTER(vp)]
+    L.mpros_comm_create_local.argtypes = [i, C.POINTER(vp)]
+    L.mpros_comm_destroy.argtypes = [vp]
+    L.mpros_comm_info.argtypes = [vp, C.POINTER(i), C.POINTER(i), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.mpros_map_band_rows.argtypes = [vp, vp, i, C.POINTER(i), C.POINTER(i)]
+    L.mpros_map_set_occupancy_banded.argtypes = [vp, vp, vp, i, i, d, d, d, d]
+    L.mpros_map_set_occupancy_banded_dev.argtypes = [vp, vp, vp, i, i, d, d, d, d]
+    L.mpros_plan_shard_range.argtypes = [vp, sz, C.POINTER(sz), C.POINTER(sz)]
+    L.mpros_plan_batch_sharded.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp, vp, i, vp, i]
     _lib = L
     return L
 
@@ -215,6 +226,89 @@ def _fill(struct, keys, params):
             continue
         ftype = dict(struct._fields_)[f]
         setattr(struct, f, int(v) if ftype is C.c_int else float(v))
+
+
+class Comm:
+    """mpros_comm: one rank of a multi-GPU job. Comm.nccl(ctx, world, rank, id) on an 8 x B200 box (id from
+    Comm.unique_id() on rank 0, handed round by the launcher); Comm.local(world) -> the ranks of one process (one host
+    thread and one Context each)."""
+
+    def __init__(self, handle):
+        self.L = load_library()
+        self.h = handle
+
+    @staticmethod
+    def unique_id():
+        L = load_library()
+        buf = (C.c_char * 128)()
+        rc = L.mpros_comm_unique_id(buf)
+        if rc != 0:
+            raise MprosError("mpros error %d: %s" % (rc, L.mpros_last_error_string().decode()))
+        return bytes(buf)
+
+    @staticmethod
+    def nccl(ctx, world, rank, unique_id):
+        L = load_library()
+        h = C.c_void_p()
+        buf = (C.c_char * 128).from_buffer_copy(unique_id)
+        rc = L.mpros_comm_create_nccl(ctx.h, world, rank, buf, C.byref(h))
+        if rc != 0:
+            raise MprosError("mpros error %d: %s" % (rc, L.mpros_last_error_string().decode()))
+        return Comm(h)
+
+    @staticmethod
+    def from_torch_distributed(ctx, dist, device):
+        """One mpros communicator over the ranks of an initialised torch.distributed job (the id travels by broadcast)."""
+        import torch
+
+        world, rank = dist.get_world_size(), dist.get_rank()
+        t = torch.zeros(128, dtype=torch.uint8, device=device)
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(Comm.unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        return Comm.nccl(ctx, world, rank, bytes(t.cpu().numpy().tobytes()))
+
+    @staticmethod
+    def local(world):
+        L = load_library()
+        arr = (C.c_void_p * world)()
+        rc = L.mpros_comm_create_local(world, arr)
+        if rc != 0:
+            raise MprosError("mpros error %d: %s" % (rc, L.mpros_last_error_string().decode()))
+        return [Comm(C.c_void_p(arr[r])) for r in range(world)]
+
+    def info(self):
+        w, r, b, e = C.c_int(), C.c_int(), C.c_uint64(), C.c_uint64()
+        self.L.mpros_comm_info(self.h, C.byref(w), C.byref(r), C.byref(b), C.byref(e))
+        return {"world": w.value, "rank": r.value, "bytes_sent": b.value, "exchanges": e.value}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.mpros_comm_destroy(self.h)
+            self.h = None
+
+
+def run_local_ranks(world, fn):
+    """Run fn(rank) on `world` host threads (the local communicator's ranks); re-raises the first failure."""
+    import threading
+
+    out, err = [None] * world, [None] * world
+
+    def work(r):
+        try:
+            out[r] = fn(r)
+        except BaseException as e:  # noqa: BLE001 - reported to the caller
+            err[r] = e
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for e in err:
+        if e is not None:
+            raise e
+    return out
 
 
 class Context:
@@ -309,6 +403,20 @@ class Context:
 
     def band_finish(self):
         self._check(self.L.mpros_map_band_finish(self.h))
+
+    # ---- the same with every stage banded and the exchanges inside the library (mpros_map_set_occupancy_banded) ----
+    def band_of(self, comm, H):
+        """Rows [row0, row0 + nrows) of the occupancy grid this rank provides."""
+        r0, n = C.c_int(), C.c_int()
+        self._check(self.L.mpros_map_band_rows(self.h, comm.h if comm else None, H, C.byref(r0), C.byref(n)))
+        return r0.value, n.value
+
+    def set_occupancy_banded(self, comm, rows, W, H, resolution, origin):
+        rows = np.ascontiguousarray(rows, dtype=np.int8)
+        keep = rows if rows.size else np.zeros(1, dtype=np.int8)
+        res = float(np.float32(resolution))
+        self._check(self.L.mpros_map_set_occupancy_banded(self.h, comm.h if comm else None, keep.ctypes.data, W, H, res, origin[0],
+                                                          origin[1], origin[2]))
 
     def update_goal(self, gx, gy):
         self._check(self.L.mpros_map_update_goal(self.h, gx, gy))
@@ -435,6 +543,24 @@ class Context:
         return {"status": status, "cost": cost, "path_len": plen, "paths": paths, "iterations": stats[:, 0],
                 "primitives": stats[:, 1], "rs_shots": stats[:, 2], "collision_checks": stats[:, 3],
                 "goal_map_cells": stats[:, 4], "nodes_inserted": stats[:, 5]}
+
+    def plan_batch_sharded(self, comm, starts3, goals3, path_cap=256, gather_paths=False):
+        """mpros_plan_batch_sharded: the global query set, this rank plans its block, summaries gathered on every rank."""
+        s = np.ascontiguousarray(starts3, dtype=np.float64).reshape(-1, 3)
+        g = np.ascontiguousarray(goals3, dtype=np.float64).reshape(-1, 3)
+        nq = len(s)
+        status = np.zeros(nq, dtype=np.int32)
+        cost = np.zeros(nq)
+        plen = np.zeros(nq, dtype=np.int32)
+        paths = np.zeros((nq, path_cap, 5))
+        stats = np.zeros((nq, 6), dtype=np.int64)
+        self._check(self.L.mpros_plan_batch_sharded(self.h, comm.h if comm else None, s.ctypes.data, g.ctypes.data, nq, status.ctypes.data,
+                                                    cost.ctypes.data, plen.ctypes.data, paths.ctypes.data if path_cap else None, path_cap,
+                                                    stats.ctypes.data, 1 if gather_paths else 0))
+        lo, hi = C.c_size_t(), C.c_size_t()
+        self.L.mpros_plan_shard_range(comm.h if comm else None, nq, C.byref(lo), C.byref(hi))
+        return {"status": status, "cost": cost, "path_len": plen, "paths": paths, "iterations": stats[:, 0], "primitives": stats[:, 1],
+                "owned": (lo.value, hi.value)}
 
     def plan_batch_dev(self, d_starts, d_goals, nq, d_status, d_cost, d_len, d_paths, path_cap, d_stats):
         self._check(self.L.mpros_plan_batch_dev(self.h, d_starts, d_goals, nq, d_status, d_cost, d_len, d_paths, path_cap, d_stats))

@@ -308,6 +308,55 @@ MPROS_API void *mpros_plan_lane_stream(mpros_ctx *ctx, int lane);
 MPROS_API int mpros_plan_search_tree(mpros_ctx *ctx, const double *start3, const double *goal3, int32_t *status, double *cost,
                                      double *tree4, size_t cap_segments, size_t *n_segments);
 
+/* ---- several GPUs of one box --------------------------------------------------------------------------
+ * One rank = one process (or host thread) + one context per GPU. The reference is a single-threaded ROS node
+ * (main_planner.cpp:166-268) and has no counterpart; these entry points are what a multi-GPU planning service built on
+ * NavMap / HybridAstar binds. All exchanges run inside the library: NCCL over NVLink / NVSwitch, enqueued on the
+ * context's stream (libnccl.so.2 is resolved at run time; without it the mpros_comm_*_nccl calls fail with MPROS_ERR_CUDA
+ * and everything single-GPU keeps working). */
+typedef struct mpros_comm mpros_comm;
+/* 128-byte NCCL unique id (ncclGetUniqueId). Rank 0 creates it; the launcher hands it to the other ranks (MPI, its own rendezvous,
+ * a file). */
+MPROS_API int mpros_comm_unique_id(void *id128);
+/* ncclCommInitRank on the context's device; collective over all ranks. */
+MPROS_API int mpros_comm_create_nccl(mpros_ctx *ctx, int world, int rank, const void *id128, mpros_comm **out);
+/* Wrap an ncclComm_t the caller already owns (it is not destroyed with the handle). */
+MPROS_API int mpros_comm_adopt_nccl(int world, int rank, void *nccl_comm, mpros_comm **out);
+/* `world` ranks inside ONE process (out[0..world)): one host thread and one context per rank, parts exchanged with
+ * cudaMemcpyAsync behind a host barrier. Every rank must make the same calls, each from its own thread. Lets the banded
+ * algorithms run on a single GPU (tests) and serves boxes driven by one process. */
+MPROS_API int mpros_comm_create_local(int world, mpros_comm **out);
+MPROS_API int mpros_comm_destroy(mpros_comm *comm);
+/* world / rank, payload bytes this rank contributed to exchanges so far and the number of exchange steps (any may be NULL). */
+MPROS_API int mpros_comm_info(const mpros_comm *comm, int *world, int *rank, uint64_t *bytes_sent, uint64_t *exchanges);
+
+/* NavMap::setOccupancyMap (nav_map.cpp:42-162) of a very large map with EVERY stage tiled by row bands across the ranks:
+ * N1 threshold (:114-131) and N3 inflateObstacle (:164-214) on the rank's rows of the original grid, N5-N9
+ * generateVoronoiMap (:541-590: markObs/floodFillObs :384-432, calObsDist :434-473, findEdge :475-507, calEdgeDist :509-539,
+ * cost loop :565-582) on the rank's rows of the down-sampled grid. Exchanges: the finished bands of static_map_orig_ and
+ * inflate_map_orig_ (the first doubles as N3's halo), for markObs the labels of each band's first and last row (seam
+ * union) and the region ids of those rows, for each distance transform ONE carry exchange (two aggregate rows per band
+ * serve the forward and the backward sweep), and the finished bands of obs_dist_ / region_ / isedge_ / edge_dist_ / the
+ * Voronoi cost. N2 and the probe layouts are one cheap pass over the gathered bits on every rank; N4 never needs tiling
+ * (values are capped at 999). Afterwards every rank holds the complete layers, bit-identical to mpros_map_set_occupancy.
+ * rows: this rank's rows [row0, row0 + nrows) of the int8 occupancy grid (mpros_map_band_rows; a rank may own none: pass
+ * any non-NULL pointer); bands are cut on the down-sampled grid, ceil(H / world) rows per rank. Collective. */
+MPROS_API int mpros_map_band_rows(mpros_ctx *ctx, const mpros_comm *comm, int height, int *row0, int *nrows);
+MPROS_API int mpros_map_set_occupancy_banded(mpros_ctx *ctx, mpros_comm *comm, const int8_t *rows, int width, int height,
+                                             double resolution, double origin_x, double origin_y, double origin_yaw);
+MPROS_API int mpros_map_set_occupancy_banded_dev(mpros_ctx *ctx, mpros_comm *comm, const int8_t *d_rows, int width, int height,
+                                                 double resolution, double origin_x, double origin_y, double origin_yaw);
+
+/* mpros_plan_batch for a GLOBAL set of nq queries sharded across the ranks (contiguous blocks, mpros_plan_shard_range):
+ * every rank passes the same starts3 / goals3 and plans its block on its own replica of the map layers - no
+ * communication during the search - then status / cost / path_len / stats of all blocks are gathered into every rank's
+ * arrays (the only exchange; the paths too when gather_paths != 0, otherwise only the rank's own block of `paths` is
+ * written). Arrays are sized for all nq queries on every rank. comm == NULL plans everything locally. Collective. */
+MPROS_API int mpros_plan_shard_range(const mpros_comm *comm, size_t nq, size_t *lo, size_t *hi);
+MPROS_API int mpros_plan_batch_sharded(mpros_ctx *ctx, mpros_comm *comm, const double *starts3, const double *goals3, size_t nq,
+                                       int32_t *status, double *cost, int32_t *path_len, double *paths, int path_cap, int64_t *stats,
+                                       int gather_paths);
+
 /* ---- path post-processing -------------------------------------------------------------------- */
 /* What HybridAstar::setPath does to the raw path_ before getNewPath() returns it (hybrid_a_star.cpp:814-838):
  * updatePathLength, setCusp, updateCurvatureNew (planner_utils.h:35-61, 251-309) and, when interpolation_enable is set,

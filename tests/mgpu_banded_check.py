@@ -63,6 +63,59 @@ def main():
             np.array_equal(ref["iterations"], got["iterations"])):
         bad += 1
         print("rank %d: sharded plans differ from the single-GPU plans" % rank, flush=True)
+    # the same two steps entirely behind the C ABI: mpros_comm over NCCL (ncclCommInitRank from an id broadcast once),
+    # every stage of the map banded incl. N5-N9, result gather by the library
+    comm = mpros_b200.Comm.from_torch_distributed(banded, dist, "cuda")
+    cb = mpros_b200.Context(local)
+    cb.map_config(params)
+    r0, n = cb.band_of(comm, H)
+    t_c = []
+    for rep in range(3):
+        dist.barrier()
+        t0 = time.perf_counter()
+        cb.set_occupancy_banded(comm, occ[r0:r0 + n], W, H, synthetic.SYN_RES, [0.0, 0.0, 0.0])
+        t_c.append(time.perf_counter() - t0)
+    for layer in ["static_orig", "inflate_orig", "static", "obs_dist", "region", "isedge", "edge_dist", "voronoi"]:
+        a, b = single.layer(layer), cb.layer(layer)
+        if not np.array_equal(a, b):
+            bad += 1
+            print("rank %d: C-ABI banded layer %s differs in %d cells" % (rank, layer, int((a != b).sum())), flush=True)
+    if cb.info()["num_regions"] != single.info()["num_regions"]:
+        bad += 1
+        print("rank %d: region count differs" % rank, flush=True)
+    # a ds = 1 map (N5-N9 at the full resolution: the case the banding is for), cropped so that it stays quick
+    p1 = dict(params)
+    p1["/mpros/map/downsampling_factor"] = 1
+    s1, b1 = mpros_b200.Context(local), mpros_b200.Context(local)
+    s1.map_config(p1)
+    b1.map_config(p1)
+    occ1 = occ[:1536, :1792]
+    t0 = time.perf_counter()
+    s1.set_occupancy(occ1, synthetic.SYN_RES, [0.0, 0.0, 0.0])
+    t_s1 = time.perf_counter() - t0
+    r1, n1 = b1.band_of(comm, occ1.shape[0])
+    for rep in range(2):
+        dist.barrier()
+        t0 = time.perf_counter()
+        b1.set_occupancy_banded(comm, occ1[r1:r1 + n1], occ1.shape[1], occ1.shape[0], synthetic.SYN_RES, [0.0, 0.0, 0.0])
+        t_b1 = time.perf_counter() - t0
+    for layer in ["static_orig", "inflate_orig", "static", "obs_dist", "region", "isedge", "edge_dist", "voronoi"]:
+        a, b = s1.layer(layer), b1.layer(layer)
+        if not np.array_equal(a, b):
+            bad += 1
+            print("rank %d: ds=1 banded layer %s differs in %d cells" % (rank, layer, int((a != b).sum())), flush=True)
+    cb.planner_config(params)
+    got2 = cb.plan_batch_sharded(comm, starts, goals, path_cap=128, gather_paths=True)
+    if not (np.array_equal(ref["status"], got2["status"]) and np.array_equal(ref["cost"], got2["cost"]) and
+            np.array_equal(ref["iterations"], got2["iterations"]) and np.array_equal(ref["paths"], got2["paths"])):
+        bad += 1
+        print("rank %d: mpros_plan_batch_sharded differs from the single-GPU plans" % rank, flush=True)
+    ci = comm.info()
+    if rank == 0:
+        print("C ABI over NCCL: banded map %.1f ms (best of 3; single %.1f ms), ds=1 %dx%d banded %.1f ms vs single %.1f ms, "
+              "%d exchanges, %.1f MB sent by rank 0" % (1e3 * min(t_c), 1e3 * t_single, occ1.shape[0], occ1.shape[1], 1e3 * t_b1, 1e3 * t_s1,
+                                                       ci["exchanges"], ci["bytes_sent"] / 1e6), flush=True)
+    comm.close()
     t = torch.tensor([bad], device="cuda")
     dist.all_reduce(t)
     if rank == 0:
