@@ -69,12 +69,14 @@ def shipped_params(ds=SYN_DS):
 
 
 def ncu_traffic(kernel):
-    """DRAM bytes (read + write) per launch of `kernel` from the committed ncu capture of this very command
-    (profiles/r01_traffic.json, written from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`); None if absent."""
-    try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[kernel]["dram_bytes_per_launch"]
-    except Exception:
-        return None
+    """DRAM bytes (read + write) per launch of `kernel` from the newest committed ncu capture of this very command
+    (profiles/rNN_traffic.json, written by tools/make_traffic.py from the `ncu --set full` captures); None if absent."""
+    for tag in ("r02", "r01"):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", tag + "_traffic.json")))[kernel]["dram_bytes_per_launch"]
+        except Exception:
+            continue
+    return None
 
 
 def measured_peak_gbs():
@@ -505,7 +507,9 @@ def run_b200(args):
     col_value = world * n * col_steps / (col_total_ms * 1e-3)
     col_e2e = world * n * col_steps / (col_e2e_ms * 1e-3)
     peak, peak_kind = measured_peak_gbs()
-    col_kernel = "collision_poses_kernel" if os.environ.get("MPROS_C1_MODE") == "walk" else "collision_poses_2phase_kernel"
+    c1_mode = os.environ.get("MPROS_C1_MODE", "")
+    col_kernel = ("collision_poses_kernel" if c1_mode == "walk" else "collision_poses_2phase_kernel" if c1_mode == "2phase_ldg"
+                  else "collision_poses_tma_kernel")
     col_roof = {"bound": "hbm", "achieved": n * B_CHECK / (float(np.mean(col_ms)) * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                 "traffic": ncu_traffic(col_kernel), "kernel": col_kernel, "kernel_ms": float(np.mean(col_ms)), "peak_source": peak_kind,
                 "algorithmic_bytes_per_unit": B_CHECK}
@@ -659,15 +663,30 @@ def run_b200(args):
         def step_dev():
             ctx._check(ctx.L.mpros_expand_batch_dev(ctx.h, None, g_c, par_d.data_ptr(), ne, pr_d.data_ptr(), ch_d.data_ptr(), nc_d.data_ptr()))
 
-        def step_host():
+        def step_host_ref_format():
             ctx._check(ctx.L.mpros_expand_batch(ctx.h, None, g_c, par_h.data_ptr(), ne, pr_h.data_ptr(), ch_h.data_ptr(), nc_h.data_ptr()))
 
+        # the call a user makes for the open-list inserts: compact child records (80 B each, ~2 per expansion) instead of
+        # the 816 B of fixed-size reference-format arrays per expansion
+        import ctypes as C
+
+        rec_h = torch.zeros(ne * P * 80, dtype=torch.uint8).pin_memory()
+        n_rec = C.c_size_t(0)
+
+        def step_host():
+            ctx._check(ctx.L.mpros_expand_batch_compact(ctx.h, None, g_c, par_h.data_ptr(), ne, rec_h.data_ptr(), ne * P, C.byref(n_rec),
+                                                        nc_h.data_ptr()))
+
         total_ms, step_ms, launches = timed_device(step_dev)
+        e2e_ref_ms = timed_host(step_host_ref_format)
+        nc_ref = nc_h.clone()
         e2e_ms = timed_host(step_host)
+        assert torch.equal(nc_ref, nc_h) and n_rec.value == int(nc_h.sum()), "compact and reference-format expansions differ"
+        step_host_ref_format()
         sampler.stop_flag = True
         sampler.join(timeout=2)
         assert torch.equal(nc_h, nc_d.cpu()) and torch.equal(ch_h, ch_d.cpu()), "host-API and device-API expansions differ"
-        total_ms, e2e_ms = max_over_ranks([total_ms, e2e_ms])
+        total_ms, e2e_ms, e2e_ref_ms = max_over_ranks([total_ms, e2e_ms, e2e_ref_ms])
         if rank == 0:
             k_ms = float(np.mean(step_ms))
             achieved = ne * B_EXPANSION / (k_ms * 1e-3) / 1e9
@@ -675,7 +694,9 @@ def run_b200(args):
             line = {"metric": "node_expansions_per_sec", "value": world * ne * args.steps / (total_ms * 1e-3), "unit": "expansions/s",
                     "ms_per_step": total_ms / args.steps,
                     "e2e": {"value": world * ne * args.steps / (e2e_ms * 1e-3), "unit": "expansions/s", "h2d_bytes_per_step": ne * 48,
-                            "d2h_bytes_per_step": ne * (P * 17 * 8 + 4)},
+                            "d2h_bytes_per_step": int(n_rec.value) * 80 + ne * 4 + 8, "api": "mpros_expand_batch_compact",
+                            "reference_format": {"value": world * ne * args.steps / (e2e_ref_ms * 1e-3), "api": "mpros_expand_batch",
+                                                 "d2h_bytes_per_step": ne * (P * 17 * 8 + 4)}},
                     "gpu_launches": int(launches),
                     "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                                  "traffic": ncu_traffic("expand_batch_kernel"), "kernel": "expand_batch_kernel", "kernel_ms": k_ms,

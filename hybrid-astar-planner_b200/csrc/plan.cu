@@ -168,79 +168,160 @@ struct RsBatchArgs
     int center_probe = 0;
 };
 
-#ifndef MPROS_RS_MINB
-#define MPROS_RS_MINB 8 // 64 registers: 32 resident warps per SM (38 -> 48 M shots/s)
-#endif
-__global__ void __launch_bounds__(128, MPROS_RS_MINB) rs_batch_kernel(const __grid_constant__ MapView m, const __grid_constant__ PlannerView p, RsBatchArgs a)
+// Trajectory longer than one warp's 32 poses (rare inside the 10 m analytic range): the one-lane GenTraj into the warp's
+// scratch, then the poses 32 at a time. Out of line: it must not sit in the hot loop's instruction stream.
+__device__ __noinline__ bool rs_shot_long(const MapView &m, const PlannerView &p, const RsBatchArgs &a, const RsWord &w, double x0, double y0,
+                                          double yaw0, int q, double *scratch, int &np_out)
 {
     const int lane = threadIdx.x & 31;
+    double *txyz = scratch, *tsd = scratch + 3 * kTrajCap;
+    int np = 0;
+    if (lane == 0)
+    {
+        RsPath path;
+        path.n = w.n;
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+            if (k < w.n)
+                rs_word_seg(w, k, path.s[k].len, path.s[k].steer, path.s[k].dir);
+        np = rs_gen_traj(a.rs, x0, y0, yaw0, path, txyz, tsd, kTrajCap);
+    }
+    np = __shfl_sync(kFull, np, 0);
+    __syncwarp();
+    np_out = np;
+    const int stored = min(np, kTrajCap);
+    if (a.traj)
+    {
+        double *dst = a.traj + (size_t)q * a.traj_cap * 5;
+        for (int k = lane; k < stored && k < a.traj_cap; k += 32)
+        {
+            dst[5 * k] = txyz[3 * k], dst[5 * k + 1] = txyz[3 * k + 1], dst[5 * k + 2] = txyz[3 * k + 2];
+            dst[5 * k + 3] = tsd[2 * k], dst[5 * k + 4] = tsd[2 * k + 1];
+        }
+    }
+    bool hit = np > kTrajCap; // longer than the scratch: report blocked rather than judge a truncated path
+    if (a.verdicts)
+        for (int k0 = 0; k0 < stored && !hit; k0 += 32)
+        {
+            const int k = k0 + lane;
+            int cls = 0;
+            if (k < stored)
+                cls = footprint_preclass(m, p, a.unsafe_tw, a.center_probe, txyz[3 * k], txyz[3 * k + 1], txyz[3 * k + 2]);
+            if (__any_sync(kFull, cls == 1))
+            {
+                hit = true;
+                break;
+            }
+            unsigned walk = __ballot_sync(kFull, cls == 2);
+            double s = 0, c = 1;
+            if (cls == 2)
+                dm::sincos_(txyz[3 * k + 2], &s, &c);
+            while (walk && !hit)
+            {
+                const int j = __ffs(walk) - 1;
+                walk &= walk - 1;
+                const double ts = __shfl_sync(kFull, s, j), tc = __shfl_sync(kFull, c, j);
+                hit = warp_footprint_collision(m, p, txyz[3 * (k0 + j)], txyz[3 * (k0 + j) + 1], ts, tc);
+            }
+        }
+    __syncwarp();
+    return hit;
+}
+
+// R1-R4 for a batch of shots. A warp takes EIGHT shots at a time: the solve runs with lane = (shot, symmetry image) and
+// walks the twelve words together (rs_find_optimal_quad: every lane in the same closed form, candidates in registers); the
+// trajectory and the sampled-path footprint test then run shot by shot with one lane per pose, the poses never leaving
+// registers (rs_gen_traj_regs). The first version - one shot per warp, the 48 candidates as per-thread segment arrays in
+// local memory, the trajectory in a per-warp HBM scratch - executed 9 800 warp-instructions per shot, eight divergent
+// formula bodies on four lanes each, and moved 3.4 GB of DRAM traffic per 2^20 shots against 0.45 GB algorithmic.
+#ifndef MPROS_RS_MINB
+#define MPROS_RS_MINB 8 // 64 registers: 32 resident warps per SM (38 -> 48 M shots/s on the first version)
+#endif
+__global__ void __launch_bounds__(128, MPROS_RS_MINB) rs_batch_kernel(const __grid_constant__ MapView m, const __grid_constant__ PlannerView p,
+                                                                       const __grid_constant__ RsBatchArgs a)
+{
+    const int lane = threadIdx.x & 31, quad = lane >> 2, j = lane & 3;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     double *scratch = reinterpret_cast<double *>(a.ws) + (size_t)warp_global * kTrajCap * 5;
-    for (int q = warp_global; q < a.n; q += nwarps)
+    const int ngroups = (a.n + 7) >> 3;
+    for (int g = warp_global; g < ngroups; g += nwarps)
     {
-        const double *s5 = a.starts5 + 5 * (size_t)q, *g3 = a.goals3 + 3 * (size_t)q;
-        RsPath best;
-        double cost = rs_find_optimal_warp(a.rs, s5[0], s5[1], s5[2], (int)s5[3], s5[4], g3[0], g3[1], g3[2], best);
-        double *txyz = scratch, *tsd = scratch + 3 * kTrajCap;
-        int cap = kTrajCap;
-        const int np = rs_gen_traj_warp(a.rs, s5[0], s5[1], s5[2], best, txyz, tsd, cap);
-        int stored = min(np, cap);
-        if (a.traj)
+        const int q = 8 * g + quad;
+        const bool live = q < a.n;
+        const double *s5 = a.starts5 + 5 * (size_t)(live ? q : a.n - 1), *g3 = a.goals3 + 3 * (size_t)(live ? q : a.n - 1);
+        const double sx = s5[0], sy = s5[1], syaw = s5[2];
+        double cost;
+        const RsWord best = rs_find_optimal_quad(a.rs, sx, sy, syaw, (int)s5[3], s5[4], g3[0], g3[1], g3[2], cost);
+        if (live)
         {
-            double *dst = a.traj + (size_t)q * a.traj_cap * 5;
-            for (int k = lane; k < stored && k < a.traj_cap; k += 32)
+            if (j == 0)
             {
-                dst[5 * k] = txyz[3 * k], dst[5 * k + 1] = txyz[3 * k + 1], dst[5 * k + 2] = txyz[3 * k + 2];
-                dst[5 * k + 3] = tsd[2 * k], dst[5 * k + 4] = tsd[2 * k + 1];
+                a.cost[q] = cost;
+                a.nseg[q] = best.n;
+            }
+            for (int k = j; k < 5; k += 4) // lane j of the quad stores segments j and j + 4
+            {
+                double len = 0;
+                int steer = 0, dir = 0;
+                if (k < best.n)
+                    rs_word_seg(best, k, len, steer, dir);
+                double *o = a.segs + 15 * (size_t)q + 3 * k;
+                o[0] = len, o[1] = (double)steer, o[2] = (double)dir;
             }
         }
-        if (a.verdicts)
+        const int nshots = min(8, a.n - 8 * g);
+        for (int s = 0; s < nshots; ++s)
         {
-            bool hit = np > cap; // longer than the scratch: report blocked rather than judge a truncated path
-            // pathInCollision is an OR over the poses: one lane per pose decides it by the pose's own cell where that is
-            // possible (map_device.cuh: footprint_preclass), the undecided poses get their sin/cos in parallel and the
-            // warp-wide probe walk one after the other
-            for (int k0 = 0; k0 < stored && !hit; k0 += 32)
+            const int src = 4 * s, qs = 8 * g + s;
+            RsWord w;
+            w.t = __shfl_sync(kFull, best.t, src), w.u = __shfl_sync(kFull, best.u, src), w.v = __shfl_sync(kFull, best.v, src);
+            w.f = __shfl_sync(kFull, best.f, src), w.j = __shfl_sync(kFull, best.j, src), w.n = __shfl_sync(kFull, best.n, src);
+            const double x0 = __shfl_sync(kFull, sx, src), y0 = __shfl_sync(kFull, sy, src), yaw0 = __shfl_sync(kFull, syaw, src);
+            double px, py, pyaw;
+            int pst, pdr;
+            int np = rs_gen_traj_regs(a.rs, x0, y0, yaw0, w, px, py, pyaw, pst, pdr);
+            bool hit = false;
+            if (np > 32)
+                hit = rs_shot_long(m, p, a, w, x0, y0, yaw0, qs, scratch, np);
+            else
             {
-                const int k = k0 + lane;
-                int cls = 0;
-                if (k < stored)
-                    cls = footprint_preclass(m, p, a.unsafe_tw, a.center_probe, txyz[3 * k], txyz[3 * k + 1], txyz[3 * k + 2]);
-                if (__any_sync(kFull, cls == 1))
+                const bool pose = lane < np;
+                if (a.traj && pose && lane < a.traj_cap)
                 {
-                    hit = true;
-                    break;
+                    double *o = a.traj + ((size_t)qs * a.traj_cap + lane) * 5;
+                    o[0] = px, o[1] = py, o[2] = pyaw, o[3] = (double)pst * a.rs.steer_angle, o[4] = (double)pdr;
                 }
-                unsigned walk = __ballot_sync(kFull, cls == 2);
-                double s = 0, c = 1;
-                if (cls == 2)
-                    dm::sincos_(txyz[3 * k + 2], &s, &c);
-                while (walk && !hit)
+                if (a.verdicts)
                 {
-                    const int j = __ffs(walk) - 1;
-                    walk &= walk - 1;
-                    const double ts = __shfl_sync(kFull, s, j), tc = __shfl_sync(kFull, c, j);
-                    hit = warp_footprint_collision(m, p, txyz[3 * (k0 + j)], txyz[3 * (k0 + j) + 1], ts, tc);
+                    // pathInCollision is an OR over the poses: every lane decides its pose by the pose's own cell where that is
+                    // possible (map_device.cuh: footprint_preclass); the undecided poses get their sin/cos in parallel and the
+                    // warp-wide probe walk one after the other
+                    const int cls = pose ? footprint_preclass(m, p, a.unsafe_tw, a.center_probe, px, py, pyaw) : 0;
+                    hit = __any_sync(kFull, cls == 1);
+                    unsigned walk = hit ? 0u : __ballot_sync(kFull, cls == 2);
+                    if (walk)
+                    {
+                        double sn = 0, cs = 1;
+                        if (cls == 2)
+                            dm::sincos_(pyaw, &sn, &cs);
+                        while (walk && !hit)
+                        {
+                            const int t = __ffs(walk) - 1;
+                            walk &= walk - 1;
+                            hit = warp_footprint_collision(m, p, __shfl_sync(kFull, px, t), __shfl_sync(kFull, py, t), __shfl_sync(kFull, sn, t),
+                                                           __shfl_sync(kFull, cs, t));
+                        }
+                    }
                 }
             }
             if (lane == 0)
-                a.verdicts[q] = hit ? 1 : 0;
-        }
-        if (lane == 0)
-        {
-            a.cost[q] = cost;
-            a.nseg[q] = best.n;
-            a.npts[q] = np;
-            for (int k = 0; k < 5; ++k)
             {
-                bool v = k < best.n;
-                a.segs[15 * (size_t)q + 3 * k] = v ? best.s[k].len : 0.0;
-                a.segs[15 * (size_t)q + 3 * k + 1] = v ? (double)best.s[k].steer : 0.0;
-                a.segs[15 * (size_t)q + 3 * k + 2] = v ? (double)best.s[k].dir : 0.0;
+                a.npts[qs] = np;
+                if (a.verdicts)
+                    a.verdicts[qs] = hit ? 1 : 0;
             }
         }
-        __syncwarp();
     }
 }
 
@@ -296,6 +377,10 @@ struct ExpandArgs
     int have_seeds;
     const uint32_t *unsafe_tw; // pre-classification layer of the footprint test (may be NULL)
     int center_probe;
+    // compact output (mpros_expand_batch_compact): only the inserted children, appended as 80-byte records
+    mpros_child_record *records = nullptr;
+    unsigned long long record_cap = 0;
+    unsigned long long *record_count = nullptr;
 };
 
 #ifndef MPROS_EXPAND_MINB
@@ -369,7 +454,7 @@ __global__ void __launch_bounds__(128, MPROS_EXPAND_MINB) expand_batch_kernel(co
             if (owner_quad >= 0 && owner_quad < 8)
                 hval = back;
         }
-        if (lane < P)
+        if (lane < P && a.prims)
         {
             double *o = a.prims + ((size_t)q * P + lane) * 7;
             o[0] = nx, o[1] = ny, o[2] = nyaw, o[3] = steer, o[4] = direc, o[5] = ((free_mask >> lane) & 1u) ? 0.0 : 1.0;
@@ -378,7 +463,7 @@ __global__ void __launch_bounds__(128, MPROS_EXPAND_MINB) expand_batch_kernel(co
         // prune against the seeded closed set (start g, goal 10000) and against earlier siblings, in primitive order
         unsigned long long idx = alive ? cal_index(m, p, ci, cj, yaw_to_idx(p, nyaw), direc) : ~0ull;
         unsigned alive_mask = __ballot_sync(kFull, alive);
-        int count = 0;
+        int count = 0, my_order = -1;
         for (int c = 0; c < P; ++c)
         {
             if (!((alive_mask >> c) & 1u))
@@ -409,6 +494,8 @@ __global__ void __launch_bounds__(128, MPROS_EXPAND_MINB) expand_batch_kernel(co
             if (ins)
             {
                 if (lane == c)
+                    my_order = count;
+                if (lane == c && a.childs)
                 {
                     double *o = a.childs + ((size_t)q * P + count) * 10;
                     o[0] = nx, o[1] = ny, o[2] = nyaw, o[3] = steer, o[4] = direc, o[5] = g, o[6] = hval, o[7] = g + hval;
@@ -417,7 +504,23 @@ __global__ void __launch_bounds__(128, MPROS_EXPAND_MINB) expand_batch_kernel(co
                 ++count;
             }
         }
-        if (lane == 0)
+        if (a.records)
+        {
+            // one reservation per parent; the children of a parent stay together and in insertion order
+            unsigned long long at = 0;
+            if (lane == 0 && count)
+                at = atomicAdd(a.record_count, (unsigned long long)count);
+            at = __shfl_sync(kFull, at, 0);
+            if (my_order >= 0 && at + my_order < a.record_cap)
+            {
+                mpros_child_record r;
+                r.parent = (uint32_t)q, r.prim = (uint16_t)lane, r.dir = (int16_t)(direc > 0 ? 1 : -1), r.i = ci, r.j = cj;
+                r.x = nx, r.y = ny, r.yaw = nyaw, r.steer = steer, r.g = g, r.h = hval, r.f = g + hval;
+                r.order = (uint32_t)my_order, r.reserved = 0;
+                a.records[at + my_order] = r;
+            }
+        }
+        if (lane == 0 && a.nchild)
             a.nchild[q] = count;
         __syncwarp();
     }
@@ -501,7 +604,8 @@ static int rs_batch_impl(mpros_ctx *c, const mpros_rs_params *rp, const double *
     else
         a.rs = rs_config_from_planner(c);
     const int block = 128, warps_per_block = block / 32;
-    int blocks = (int)std::min<size_t>((n + warps_per_block - 1) / warps_per_block, (size_t)c->n_sm * 8);
+    // a warp takes eight shots at a time; MPROS_RS_MINB CTAs are resident per SM
+    int blocks = (int)std::min<size_t>(((n + 7) / 8 + warps_per_block - 1) / warps_per_block, (size_t)c->n_sm * MPROS_RS_MINB);
     size_t nwarps = (size_t)blocks * warps_per_block;
     size_t in_bytes = n * 8 * 8, seg_bytes = n * 15 * 8, traj_bytes = n * (size_t)traj_cap * 5 * 8;
     size_t ws_bytes = nwarps * kTrajCap * 5 * 8;
@@ -601,7 +705,8 @@ extern "C" int mpros_rs_shot_batch_dev(mpros_ctx *c, const double *d_starts5, co
     RsBatchArgs a;
     a.rs = rs_config_from_planner(c);
     const int block = 128, warps_per_block = block / 32;
-    int blocks = (int)std::min<size_t>((n + warps_per_block - 1) / warps_per_block, (size_t)c->n_sm * 8);
+    // a warp takes eight shots at a time; MPROS_RS_MINB CTAs are resident per SM
+    int blocks = (int)std::min<size_t>(((n + 7) / 8 + warps_per_block - 1) / warps_per_block, (size_t)c->n_sm * MPROS_RS_MINB);
     const size_t ws_bytes = (size_t)blocks * warps_per_block * kTrajCap * 5 * 8;
     rc = map_build_unsafe(c); // before the scratch is handed out: the builder uses it for its temporaries
     if (rc)
@@ -687,7 +792,8 @@ extern "C" int mpros_rs_word_batch(mpros_ctx *c, int word, const double *xyphi, 
 
 // expandNode for n parents of one query; device buffers, asynchronous on the context's stream
 static int expand_launch(mpros_ctx *c, const char *who, const double *start3, const double *goal3, const double *d_parents6, size_t n,
-                         double *d_prims, double *d_childs, int32_t *d_nchild)
+                         double *d_prims, double *d_childs, int32_t *d_nchild, mpros_child_record *d_records = nullptr, size_t record_cap = 0,
+                         unsigned long long *d_record_count = nullptr)
 {
     int rc = check_planner_ready(c, who);
     if (rc)
@@ -699,7 +805,8 @@ static int expand_launch(mpros_ctx *c, const char *who, const double *start3, co
     }
     if (n == 0)
         return MPROS_OK;
-    if (!goal3 || !d_parents6 || !d_prims || !d_childs || !d_nchild || n > (size_t)INT32_MAX)
+    const bool compact = d_records != nullptr;
+    if (!goal3 || !d_parents6 || (!compact && (!d_prims || !d_childs || !d_nchild)) || (compact && !d_record_count) || n > (size_t)INT32_MAX)
     {
         set_error(std::string(who) + ": NULL / invalid argument");
         return MPROS_ERR_INVALID;
@@ -741,7 +848,13 @@ static int expand_launch(mpros_ctx *c, const char *who, const double *start3, co
         return rc;
     a.unsafe_tw = c->unsafe_tw;
     a.center_probe = c->unsafe_center_probe;
-    MPROS_CUDA(cudaMemsetAsync(d_childs, 0, n * P * 10 * 8, st));
+    if (d_childs)
+        MPROS_CUDA(cudaMemsetAsync(d_childs, 0, n * P * 10 * 8, st));
+    if (compact)
+        MPROS_CUDA(cudaMemsetAsync(d_record_count, 0, 8, st));
+    a.records = d_records;
+    a.record_cap = record_cap;
+    a.record_count = d_record_count;
     a.parents6 = d_parents6;
     a.prims = d_prims;
     a.childs = d_childs;
@@ -757,6 +870,68 @@ extern "C" int mpros_expand_batch_dev(mpros_ctx *c, const double *start3, const 
                                       double *d_prims, double *d_childs, int32_t *d_nchild)
 {
     return expand_launch(c, "mpros_expand_batch_dev", start3, goal3, d_parents6, n, d_prims, d_childs, d_nchild);
+}
+
+extern "C" int mpros_expand_batch_compact_dev(mpros_ctx *c, const double *start3, const double *goal3, const double *d_parents6, size_t n,
+                                              mpros_child_record *d_records, size_t cap_records, unsigned long long *d_n_records,
+                                              int32_t *d_nchild)
+{
+    return expand_launch(c, "mpros_expand_batch_compact_dev", start3, goal3, d_parents6, n, nullptr, nullptr, d_nchild, d_records, cap_records,
+                         d_n_records);
+}
+
+extern "C" int mpros_expand_batch_compact(mpros_ctx *c, const double *start3, const double *goal3, const double *parents6, size_t n,
+                                          mpros_child_record *records, size_t cap_records, size_t *n_records, int32_t *nchild)
+{
+    int rc = check_planner_ready(c, "mpros_expand_batch_compact");
+    if (rc)
+        return rc;
+    if (!n_records)
+    {
+        set_error("mpros_expand_batch_compact: NULL n_records");
+        return MPROS_ERR_INVALID;
+    }
+    *n_records = 0;
+    if (n == 0)
+        return MPROS_OK;
+    if (!goal3 || !parents6 || (cap_records && !records) || n > (size_t)INT32_MAX)
+    {
+        set_error("mpros_expand_batch_compact: NULL / invalid argument");
+        return MPROS_ERR_INVALID;
+    }
+    MPROS_CUDA(cudaSetDevice(c->device));
+    const int P = 2 * c->pv.n_steer;
+    const size_t in_b = n * 6 * 8, cap_dev = std::min(cap_records, n * (size_t)P), rec_b = cap_dev * sizeof(mpros_child_record);
+    rc = ensure_stage(c, in_b + rec_b + n * 4 + 2048);
+    if (rc)
+        return rc;
+    char *base = static_cast<char *>(c->stage);
+    double *d_in = (double *)base;
+    mpros_child_record *d_rec = (mpros_child_record *)(base + align_up(in_b, 256));
+    int32_t *d_nc = (int32_t *)((char *)d_rec + align_up(rec_b + 16, 256));
+    unsigned long long *d_cnt = (unsigned long long *)((char *)d_nc + align_up(n * 4, 256));
+    cudaStream_t st = c->stream;
+    MPROS_CUDA(cudaMemcpyAsync(d_in, parents6, in_b, cudaMemcpyHostToDevice, st));
+    // a NULL record buffer with capacity 0 only counts
+    rc = expand_launch(c, "mpros_expand_batch_compact", start3, goal3, d_in, n, nullptr, nullptr, d_nc, d_rec, cap_dev, d_cnt);
+    if (rc)
+        return rc;
+    unsigned long long cnt = 0;
+    MPROS_CUDA(cudaMemcpyAsync(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+    if (nchild)
+        MPROS_CUDA(cudaMemcpyAsync(nchild, d_nc, n * 4, cudaMemcpyDeviceToHost, st));
+    MPROS_CUDA(cudaStreamSynchronize(st));
+    *n_records = (size_t)cnt;
+    // only the records that exist travel back: ~2 children x 80 B per expansion instead of 816 B of fixed-size arrays
+    const size_t have = std::min<size_t>((size_t)cnt, cap_dev);
+    if (have)
+        MPROS_CUDA(cudaMemcpy(records, d_rec, have * sizeof(mpros_child_record), cudaMemcpyDeviceToHost));
+    if (cnt > cap_records)
+    {
+        set_error("mpros_expand_batch_compact: record buffer too small (n_records holds the required size)");
+        return MPROS_ERR_CAPACITY;
+    }
+    return MPROS_OK;
 }
 
 extern "C" int mpros_expand_batch(mpros_ctx *c, const double *start3, const double *goal3, const double *parents6, size_t n,

@@ -68,68 +68,68 @@ __device__ __forceinline__ double rs_regular_rad(double t) // rs_curve_basic.h:1
     return t;
 }
 
-// PathFunction::path1..12 (rs_curve.cpp:353-599). dist/theta: PolarCoord of the formula's own argument.
-__device__ __noinline__ void rs_formula(int f, double x, double y, double phi, RsPath &p)
+// PathFunction::path1..12 (rs_curve.cpp:353-599) in two parts: the closed-form values (t, u, v) of word f - the only
+// floating-point work - and the word's fixed segment pattern. Every segment of every word is one of t, u, v or pi/2 with a
+// fixed steer and direction, pushed through the PathSeg constructor (rs_curve_basic.h:84-88: |value|, direction flipped
+// unless value > 0). A candidate therefore lives in three registers plus the word number; no per-thread segment array.
+// dist/theta: PolarCoord of the formula's own argument. Returns false when the word has no solution (empty path).
+__device__ __forceinline__ bool rs_formula_tuv(int f, double x, double y, double phi, double &t, double &u, double &v)
 {
-    p.n = 0;
     double sphi, cphi;
     dm::sincos_(phi, &sphi, &cphi);
     const bool typeA = (f == 0 || f == 2 || f == 3 || f == 4 || f == 7 || f == 9);
     double ax = typeA ? x - sphi : x + sphi;
     double ay = typeA ? y - 1 + cphi : y - 1 - cphi;
     double dist = dm::hypot_(ax, ay), theta = dm::atan2_(ay, ax);
-    const int L_ = 1, S_ = 0, R_ = -1, F_ = 1, B_ = -1;
+    t = u = v = 0;
     switch (f)
     {
     case 0:
-    {
-        double u = dist, t = theta, v = rs_regular_rad(phi - t);
-        rs_push(p, t, L_, F_), rs_push(p, u, S_, F_), rs_push(p, v, L_, F_);
-        break;
-    }
+        u = dist, t = theta, v = rs_regular_rad(phi - t);
+        return true;
     case 1:
         if (dist * dist >= 4)
         {
-            double u = dm::sqrt_(dist * dist - 4);
-            double t = rs_regular_rad(theta + dm::atan2_(2.0, u));
-            double v = rs_regular_rad(t - phi);
-            rs_push(p, t, L_, F_), rs_push(p, u, S_, F_), rs_push(p, v, R_, F_);
+            u = dm::sqrt_(dist * dist - 4);
+            t = rs_regular_rad(theta + dm::atan2_(2.0, u));
+            v = rs_regular_rad(t - phi);
+            return true;
         }
-        break;
+        return false;
     case 2:
         if (dist <= 4)
         {
             double A = dm::acos_(dist / 4);
-            double u = rs_regular_rad(kPi - 2 * A);
-            double t = rs_regular_rad(kPi2 + A + theta);
-            double v = rs_regular_rad(phi - t - u);
-            rs_push(p, t, L_, F_), rs_push(p, u, R_, B_), rs_push(p, v, L_, F_);
+            u = rs_regular_rad(kPi - 2 * A);
+            t = rs_regular_rad(kPi2 + A + theta);
+            v = rs_regular_rad(phi - t - u);
+            return true;
         }
-        break;
+        return false;
     case 3:
         if (dist <= 4)
         {
             double A = dm::acos_(dist / 4);
-            double u = rs_regular_rad(kPi - 2 * A);
-            double t = dm::asin_(theta + kPi2 + A); // sic, rs_curve.cpp:418
-            double v = rs_regular_rad(t + u - phi);
-            rs_push(p, t, L_, F_), rs_push(p, u, R_, B_), rs_push(p, v, L_, B_);
+            u = rs_regular_rad(kPi - 2 * A);
+            t = dm::asin_(theta + kPi2 + A); // sic, rs_curve.cpp:418
+            v = rs_regular_rad(t + u - phi);
+            return true;
         }
-        break;
+        return false;
     case 4:
         if (dist <= 4)
         {
-            double u = dm::acos_(1 - dist * dist / 8);
+            u = dm::acos_(1 - dist * dist / 8);
             double A = dm::asin_(2 * dm::sin_(u) / dist);
-            double t = rs_regular_rad(theta + kPi2 - A);
-            double v = rs_regular_rad(t - u - phi);
-            rs_push(p, t, L_, F_), rs_push(p, u, R_, F_), rs_push(p, v, L_, B_);
+            t = rs_regular_rad(theta + kPi2 - A);
+            v = rs_regular_rad(t - u - phi);
+            return true;
         }
-        break;
+        return false;
     case 5:
         if (dist <= 4)
         {
-            double A, t, u, v;
+            double A;
             if (dist <= 2)
             {
                 A = dm::acos_((dist + 2) / 4);
@@ -144,74 +144,145 @@ __device__ __noinline__ void rs_formula(int f, double x, double y, double phi, R
                 u = rs_regular_rad(kPi - A);
                 v = rs_regular_rad(phi - t + 2 * u);
             }
-            rs_push(p, t, L_, F_), rs_push(p, u, R_, F_), rs_push(p, u, L_, B_), rs_push(p, v, R_, B_);
+            return true;
         }
-        break;
+        return false;
     case 6:
     {
         double u1 = (20 - dist * dist) / 16;
         if (dist <= 6 && u1 >= 0 && u1 <= 1)
         {
-            double u = dm::acos_(u1);
+            u = dm::acos_(u1);
             double A = dm::asin_(2 * dm::sin_(u) / dist);
-            double t = rs_regular_rad(theta + kPi2 + A);
-            double v = rs_regular_rad(t - phi);
-            rs_push(p, t, L_, F_), rs_push(p, u, R_, B_), rs_push(p, u, L_, B_), rs_push(p, v, R_, F_);
+            t = rs_regular_rad(theta + kPi2 + A);
+            v = rs_regular_rad(t - phi);
+            return true;
         }
-        break;
+        return false;
     }
     case 7:
         if (dist >= 2)
         {
-            double u = dm::sqrt_(dist * dist - 4) - 2;
+            u = dm::sqrt_(dist * dist - 4) - 2;
             double A = dm::atan2_(2.0, u + 2);
-            double t = rs_regular_rad(theta + kPi2 + A);
-            double v = rs_regular_rad(t - phi + kPi2);
-            rs_push(p, t, L_, F_), rs_push(p, kPi2, R_, B_), rs_push(p, u, S_, B_), rs_push(p, v, L_, B_);
+            t = rs_regular_rad(theta + kPi2 + A);
+            v = rs_regular_rad(t - phi + kPi2);
+            return true;
         }
-        break;
+        return false;
     case 8:
         if (dist >= 2)
         {
-            double t = rs_regular_rad(theta + kPi2);
-            double u = dist - 2;
-            double v = rs_regular_rad(phi - t - kPi2);
-            rs_push(p, t, L_, F_), rs_push(p, kPi2, R_, B_), rs_push(p, u, S_, B_), rs_push(p, v, R_, B_);
+            t = rs_regular_rad(theta + kPi2);
+            u = dist - 2;
+            v = rs_regular_rad(phi - t - kPi2);
+            return true;
         }
-        break;
+        return false;
     case 9:
         if (dist >= 2)
         {
-            double u = dm::sqrt_(dist * dist - 4) - 2;
+            u = dm::sqrt_(dist * dist - 4) - 2;
             double A = dm::atan2_(u + 2, 2.0);
-            double t = rs_regular_rad(theta + kPi2 - A);
-            double v = rs_regular_rad(t - phi - kPi2);
-            rs_push(p, t, L_, F_), rs_push(p, u, S_, F_), rs_push(p, kPi2, R_, F_), rs_push(p, v, L_, B_);
+            t = rs_regular_rad(theta + kPi2 - A);
+            v = rs_regular_rad(t - phi - kPi2);
+            return true;
         }
-        break;
+        return false;
     case 10:
         if (dist >= 2)
         {
-            double u = dist - 2;
-            double t = rs_regular_rad(theta);
-            double v = rs_regular_rad(phi - t - kPi2);
-            rs_push(p, t, L_, F_), rs_push(p, u, S_, F_), rs_push(p, kPi2, L_, F_), rs_push(p, v, R_, B_);
+            u = dist - 2;
+            t = rs_regular_rad(theta);
+            v = rs_regular_rad(phi - t - kPi2);
+            return true;
         }
-        break;
+        return false;
     case 11:
         if (dist >= 4)
         {
-            double u = dm::sqrt_(dist * dist - 4) - 4;
+            u = dm::sqrt_(dist * dist - 4) - 4;
             double A = dm::atan2_(2.0, u + 4);
-            double t = rs_regular_rad(theta + kPi2 + A);
-            double v = rs_regular_rad(t - phi);
-            rs_push(p, t, L_, F_), rs_push(p, kPi2, R_, B_), rs_push(p, u, S_, B_), rs_push(p, kPi2, L_, B_),
-                rs_push(p, v, R_, F_);
+            t = rs_regular_rad(theta + kPi2 + A);
+            v = rs_regular_rad(t - phi);
+            return true;
         }
-        break;
+        return false;
     default:
-        break;
+        return false;
     }
+}
+
+// Segment pattern of word f: bits [5k, 5k+5) = segment k {value selector (0 t, 1 u, 2 v, 3 pi/2), steer + 1, direction > 0},
+// bits [28, 31) = number of segments. L = 1, S = 0, R = -1, F = 1, B = -1 (rs_curve.cpp:353-599, the order of the pushes).
+__host__ __device__ constexpr uint32_t rs_seg_code(int sel, int steer, int dir) { return (uint32_t)sel | ((uint32_t)(steer + 1) << 2) | ((dir > 0 ? 1u : 0u) << 4); }
+__host__ __device__ constexpr uint32_t rs_word_code(int n, uint32_t a, uint32_t b, uint32_t c, uint32_t d = 0, uint32_t e = 0)
+{
+    return a | (b << 5) | (c << 10) | (d << 15) | (e << 20) | ((uint32_t)n << 28);
+}
+__device__ __forceinline__ uint32_t rs_word_pattern(int f)
+{
+    constexpr int T = 0, U = 1, V = 2, H = 3, L_ = 1, S_ = 0, R_ = -1, F_ = 1, B_ = -1;
+    switch (f)
+    {
+    case 0: return rs_word_code(3, rs_seg_code(T, L_, F_), rs_seg_code(U, S_, F_), rs_seg_code(V, L_, F_));
+    case 1: return rs_word_code(3, rs_seg_code(T, L_, F_), rs_seg_code(U, S_, F_), rs_seg_code(V, R_, F_));
+    case 2: return rs_word_code(3, rs_seg_code(T, L_, F_), rs_seg_code(U, R_, B_), rs_seg_code(V, L_, F_));
+    case 3: return rs_word_code(3, rs_seg_code(T, L_, F_), rs_seg_code(U, R_, B_), rs_seg_code(V, L_, B_));
+    case 4: return rs_word_code(3, rs_seg_code(T, L_, F_), rs_seg_code(U, R_, F_), rs_seg_code(V, L_, B_));
+    case 5: return rs_word_code(4, rs_seg_code(T, L_, F_), rs_seg_code(U, R_, F_), rs_seg_code(U, L_, B_), rs_seg_code(V, R_, B_));
+    case 6: return rs_word_code(4, rs_seg_code(T, L_, F_), rs_seg_code(U, R_, B_), rs_seg_code(U, L_, B_), rs_seg_code(V, R_, F_));
+    case 7: return rs_word_code(4, rs_seg_code(T, L_, F_), rs_seg_code(H, R_, B_), rs_seg_code(U, S_, B_), rs_seg_code(V, L_, B_));
+    case 8: return rs_word_code(4, rs_seg_code(T, L_, F_), rs_seg_code(H, R_, B_), rs_seg_code(U, S_, B_), rs_seg_code(V, R_, B_));
+    case 9: return rs_word_code(4, rs_seg_code(T, L_, F_), rs_seg_code(U, S_, F_), rs_seg_code(H, R_, F_), rs_seg_code(V, L_, B_));
+    case 10: return rs_word_code(4, rs_seg_code(T, L_, F_), rs_seg_code(U, S_, F_), rs_seg_code(H, L_, F_), rs_seg_code(V, R_, B_));
+    case 11: return rs_word_code(5, rs_seg_code(T, L_, F_), rs_seg_code(H, R_, B_), rs_seg_code(U, S_, B_), rs_seg_code(H, L_, B_), rs_seg_code(V, R_, F_));
+    default: return 0;
+    }
+}
+
+// One Reeds-Shepp candidate in registers: word f under symmetry j (0 plain, 1 timeflip, 2 reflect, 3 both), n = 0 when the
+// word has no solution for this goal.
+struct RsWord
+{
+    double t, u, v;
+    int f, j, n;
+};
+// Segment k of a candidate as FindOptimalPath holds it (rs_curve.cpp:111-163): PathSeg ctor, then Timeflip, then Reflect
+// (each re-constructs the segment from its non-negative length: zero-length and NaN segments flip once more, :31-49).
+__device__ __forceinline__ void rs_word_seg(const RsWord &w, int k, double &len, int &steer, int &dir)
+{
+    const uint32_t code = rs_word_pattern(w.f) >> (5 * k);
+    const int sel = code & 3;
+    const double value = sel == 0 ? w.t : (sel == 1 ? w.u : (sel == 2 ? w.v : kPi2));
+    steer = (int)((code >> 2) & 3) - 1;
+    int d = ((code >> 4) & 1) ? 1 : -1;
+    len = fabs(value);
+    d = value > 0 ? d : -d;
+    if (w.j == 1 || w.j == 3)
+    {
+        const int e = -d;
+        d = len > 0 ? e : -e;
+    }
+    if (w.j == 2 || w.j == 3)
+    {
+        steer = -steer;
+        d = len > 0 ? d : -d;
+    }
+    dir = d;
+}
+
+// path1..12 into a segment array (the team planner's shot and the word-by-word entry point)
+__device__ __noinline__ void rs_formula(int f, double x, double y, double phi, RsPath &p)
+{
+    RsWord w;
+    w.f = f, w.j = 0;
+    w.n = rs_formula_tuv(f, x, y, phi, w.t, w.u, w.v) ? (int)(rs_word_pattern(f) >> 28) : 0;
+    p.n = w.n;
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+        if (k < w.n)
+            rs_word_seg(w, k, p.s[k].len, p.s[k].steer, p.s[k].dir);
 }
 
 // Timeflip / Reflect (rs_curve.cpp:31-49): each segment is re-constructed through the PathSeg ctor with its
@@ -263,87 +334,97 @@ __device__ __forceinline__ double rs_path_length(const RsConfig &c, const RsPath
     return (length + penalty) * (1.0 + 1e-3);
 }
 
-// RSCurve::FindOptimalPath (rs_curve.cpp:111-163), one warp per shot. Candidate c = 4*f + j (f formula, j symmetry)
-// in the reference's evaluation order; multimap.begin() = smallest cost, first inserted among equals.
-// All lanes return the same best path / cost.
-__device__ __noinline__ double rs_find_optimal_warp(const RsConfig &c, double sx, double sy, double sphi, int start_direc,
-                                                       double start_steer, double ex, double ey, double ephi, RsPath &best)
+// RSCurve::PathLength (rs_curve.cpp:60-97) of a candidate in registers, the same operations in the same order as
+// rs_path_length; nan_seg = some segment length is NaN (FindOptimalPath drops such candidates, :150).
+__device__ __forceinline__ double rs_word_length(const RsConfig &c, const RsWord &w, int start_direc, double start_steer, bool &nan_seg)
 {
-    const int lane = threadIdx.x & 31;
+    nan_seg = false;
+    if (w.n == 0)
+        return 10000;
+    double length = 0, penalty = 0;
+    int last_steer = (int)start_steer; // int initialised from a double (:64)
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+        if (i < w.n)
+        {
+            double len;
+            int steer, dir;
+            rs_word_seg(w, i, len, steer, dir);
+            nan_seg |= isnan(len);
+            if (dir != start_direc)
+                penalty += c.pen_gear;
+            if (dir < 0)
+                penalty += c.pen_back * len * c.radius;
+            if (steer != last_steer)
+                penalty += c.pen_steer_change * (double)abs(steer - last_steer) * c.steer_angle;
+            if (steer != 0)
+                penalty += c.pen_steer_angle * (double)abs(steer) * c.steer_angle;
+            length += len * c.radius;
+            last_steer = steer;
+        }
+    return (length + penalty) * (1.0 + 1e-3);
+}
+
+// RSCurve::FindOptimalPath (rs_curve.cpp:111-163) for EIGHT shots per warp: lane = 4 * shot + symmetry j, and the twelve
+// words are walked together, so all 32 lanes evaluate the SAME closed form at the same time (one shot per warp puts eight
+// different words on four lanes each: the warp then executes every formula body for an eighth of its lanes). Candidate
+// c = 4 f + j in the reference's evaluation order; multimap.begin() = smallest cost, first inserted among equals. The four
+// lanes of a quad return the same best candidate; a candidate is three doubles and the word number, all in registers.
+__device__ __forceinline__ RsWord rs_find_optimal_quad(const RsConfig &c, double sx, double sy, double sphi, int start_direc,
+                                                        double start_steer, double ex, double ey, double ephi, double &cost)
+{
+    const int j = threadIdx.x & 3;
     // NewGoalPoint (:51-58)
     double dx = ex - sx, dy = ey - sy;
     double cs, sn;
     dm::sincos_(sphi, &sn, &cs);
-    double gx = (dx * cs + dy * sn) / c.radius;
-    double gy = (-dx * sn + dy * cs) / c.radius;
-    double gphi = ephi - sphi;
-
-    double my_cost = 0;
-    int my_c = 1 << 20; // "no candidate"
-    RsPath my;
-    my.n = 0;
+    const double gx = (dx * cs + dy * sn) / c.radius;
+    const double gy = (-dx * sn + dy * cs) / c.radius;
+    const double gphi = ephi - sphi;
+    const double x = (j == 1 || j == 3) ? -gx : gx;
+    const double y = (j == 2 || j == 3) ? -gy : gy;
+    const double ph = (j == 1 || j == 2) ? -gphi : gphi;
+    RsWord best;
+    best.t = best.u = best.v = 0, best.f = 0, best.j = j, best.n = 0;
+    double bc = 0;
+    int bi = 1 << 20; // "no candidate"
 #pragma unroll 1
-    for (int round = 0; round < 2; ++round)
+    for (int f = 0; f < 12; ++f)
     {
-        int cand = lane + 32 * round;
-        if (cand < 48)
+        RsWord w;
+        w.f = f, w.j = j;
+        w.n = rs_formula_tuv(f, x, y, ph, w.t, w.u, w.v) ? (int)(rs_word_pattern(f) >> 28) : 0;
+        bool nan_seg;
+        const double len = rs_word_length(c, w, start_direc, start_steer, nan_seg);
+        const bool ok = (len != 0.0) && !nan_seg; // :150 (NaN cost counts as true but implies a NaN segment)
+        if (ok && (bi >= (1 << 20) || len < bc))
         {
-            int f = cand >> 2, j = cand & 3;
-            RsPath p;
-            double x = (j == 1 || j == 3) ? -gx : gx;
-            double y = (j == 2 || j == 3) ? -gy : gy;
-            double ph = (j == 1 || j == 2) ? -gphi : gphi;
-            rs_formula(f, x, y, ph, p);
-            if (j == 1 || j == 3)
-                rs_timeflip(p);
-            if (j == 2 || j == 3)
-                rs_reflect(p);
-            double len = rs_path_length(c, p, start_direc, start_steer);
-            bool nan_seg = false;
-#pragma unroll
-            for (int k = 0; k < 5; ++k)
-                if (k < p.n && isnan(p.s[k].len))
-                    nan_seg = true;
-            bool ok = (len != 0.0) && !nan_seg; // :150 (NaN cost counts as true but implies a NaN segment)
-            if (ok && (my_c >= (1 << 20) || len < my_cost))
-            {
-                my_cost = len;
-                my_c = cand;
-                my = p;
-            }
+            bc = len;
+            bi = 4 * f + j;
+            best = w;
         }
     }
-    // warp arg-min over (cost, candidate index); costs are never NaN here
-    double bc = my_cost;
-    int bi = my_c;
+    // arg-min over the quad on (cost, candidate index); costs are never NaN here
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
+    for (int o = 1; o <= 2; o <<= 1)
     {
-        double oc = __shfl_xor_sync(kFull, bc, o);
-        int oi = __shfl_xor_sync(kFull, bi, o);
-        bool take = (oi < (1 << 20)) && (bi >= (1 << 20) || oc < bc || (oc == bc && oi < bi));
+        const double oc = __shfl_xor_sync(kFull, bc, o);
+        const int oi = __shfl_xor_sync(kFull, bi, o);
+        RsWord ow;
+        ow.t = __shfl_xor_sync(kFull, best.t, o), ow.u = __shfl_xor_sync(kFull, best.u, o), ow.v = __shfl_xor_sync(kFull, best.v, o);
+        ow.f = __shfl_xor_sync(kFull, best.f, o), ow.j = __shfl_xor_sync(kFull, best.j, o), ow.n = __shfl_xor_sync(kFull, best.n, o);
+        const bool take = (oi < (1 << 20)) && (bi >= (1 << 20) || oc < bc || (oc == bc && oi < bi));
         if (take)
         {
             bc = oc;
             bi = oi;
+            best = ow;
         }
     }
-    // owner lane broadcasts its path
-    int owner = __ffs(__ballot_sync(kFull, my_c == bi && bi < (1 << 20))) - 1;
-    if (owner < 0)
-    {
-        best.n = 0;
-        return 0.0; // unreachable: formula 0 always yields a candidate
-    }
-    best.n = __shfl_sync(kFull, my.n, owner);
-#pragma unroll
-    for (int k = 0; k < 5; ++k)
-    {
-        best.s[k].len = __shfl_sync(kFull, my.s[k].len, owner);
-        best.s[k].steer = __shfl_sync(kFull, my.s[k].steer, owner);
-        best.s[k].dir = __shfl_sync(kFull, my.s[k].dir, owner);
-    }
-    return bc;
+    if (bi >= (1 << 20)) // unreachable: word 0 always yields a candidate
+        best.n = 0, bc = 0.0;
+    cost = bc;
+    return best;
 }
 
 // RSCurve::GenTraj (rs_curve.cpp:165-222): sequential pose integration, executed by ONE lane.
@@ -411,58 +492,55 @@ __device__ __noinline__ int rs_gen_traj(const RsConfig &c, double sx, double sy,
     return n;
 }
 
-// RSCurve::GenTraj by a whole warp, the same operations in the same order as rs_gen_traj (all lanes hold the same path and
-// start pose; all 32 lanes must call it). GenTraj carries three chains from pose to pose: the yaw (one add + wrap per pose:
-// cheap, run by every lane redundantly), sin/cos of the yaw a pose starts from (expensive, independent once the yaws are
-// known: ONE lane per pose) and the position (x += increment: sequential floating-point adds, replayed in order over
-// warp shuffles). Paths with more than 32 poses (rare inside the 10 m analytic range) take the one-lane routine.
-__device__ __noinline__ int rs_gen_traj_warp(const RsConfig &c, double sx, double sy, double syaw, const RsPath &path, double *out_xyz,
-                                             double *out_sd, int cap)
+// RSCurve::GenTraj by a whole warp, the same operations in the same order as rs_gen_traj (all lanes hold the same candidate
+// and start pose; all 32 lanes must call it). GenTraj carries three chains from pose to pose: the yaw (one add + wrap per
+// pose: cheap, run by every lane redundantly), sin/cos of the yaw a pose starts from (expensive, independent once the yaws
+// are known: ONE lane per pose) and the position (x += increment: sequential floating-point adds, replayed in order over
+// warp shuffles). The poses stay in registers: lane n < total returns pose n and the steer / direction of its segment.
+// Returns the number of poses; more than 32 (rare inside the 10 m analytic range) produces no poses - the caller takes the
+// one-lane routine.
+__device__ __forceinline__ int rs_gen_traj_regs(const RsConfig &c, double sx, double sy, double syaw, const RsWord &w, double &px, double &py,
+                                                double &pyaw, int &psteer, int &pdir)
 {
     const int lane = threadIdx.x & 31;
     const double curve_min_num = 3;
-    // per segment: number of poses, and the constants of its pose step (lane k < path.n evaluates segment k)
-    int my_num = 0;
-    double my_a = 0, my_b = 0, my_dyaw = 0; // arc: dx, dy, yaw step; straight: step * direc, unused, 0
-    if (lane < path.n)
+    // per segment: number of poses, and the constants of its pose step (lane k < n evaluates segment k)
+    int my_num = 0, my_steer = 0, my_dir = 1;
+    double my_a = 0, my_b = 0, my_dyaw = 0; // arc: dx, dy, yaw step; straight: step, unused, 0
+    if (lane < w.n)
     {
-        const RsSeg seg = path.s[lane];
-        my_num = (int)fmax(ceil(seg.len * c.radius / c.step), curve_min_num);
-        const double direc = (double)seg.dir;
-        if (seg.steer != 0)
+        double len;
+        rs_word_seg(w, lane, len, my_steer, my_dir);
+        my_num = (int)fmax(ceil(len * c.radius / c.step), curve_min_num);
+        const double direc = (double)my_dir;
+        if (my_steer != 0)
         {
-            const double dyaw = seg.len / my_num;
+            const double dyaw = len / my_num;
             double sd, cd;
             dm::sincos_(dyaw, &sd, &cd);
             my_a = sd * c.radius * direc;
-            my_b = (1 - cd) * c.radius * (double)seg.steer;
-            my_dyaw = dyaw * direc * (double)seg.steer;
+            my_b = (1 - cd) * c.radius * (double)my_steer;
+            my_dyaw = dyaw * direc * (double)my_steer;
         }
         else
-            my_a = seg.len * c.radius / my_num;
+            my_a = len * c.radius / my_num;
     }
     int total = 0;
-    for (int k = 0; k < path.n; ++k)
+    for (int k = 0; k < w.n; ++k)
         total += __shfl_sync(kFull, my_num, k);
+    px = sx, py = sy, pyaw = syaw, psteer = 0, pdir = 1;
     if (total > 32)
-    {
-        int n = 0;
-        if (lane == 0)
-            n = rs_gen_traj(c, sx, sy, syaw, path, out_xyz, out_sd, cap);
-        n = __shfl_sync(kFull, n, 0);
-        __syncwarp();
-        return n;
-    }
+        return total;
     // yaw chain: lane n keeps the yaw pose n starts from, the yaw it ends with and its segment
     double yaw_from = syaw, yaw_to = syaw, curr_yaw = syaw;
     int my_seg = 0;
     {
         int n = 0;
-        for (int k = 0; k < path.n; ++k)
+        for (int k = 0; k < w.n; ++k)
         {
             const int num_pt = __shfl_sync(kFull, my_num, k);
             const double dyaw = __shfl_sync(kFull, my_dyaw, k);
-            const bool arc = path.s[k].steer != 0;
+            const bool arc = __shfl_sync(kFull, my_steer, k) != 0;
             for (int i = 0; i < num_pt; ++i, ++n)
             {
                 const double before = curr_yaw;
@@ -477,41 +555,36 @@ __device__ __noinline__ int rs_gen_traj_warp(const RsConfig &c, double sx, doubl
         }
     }
     // position increments, one lane per pose
-    const bool live = lane < total;
-    const RsSeg seg = path.s[live ? my_seg : 0];
     const double a = __shfl_sync(kFull, my_a, my_seg), b = __shfl_sync(kFull, my_b, my_seg);
+    const int seg_steer = __shfl_sync(kFull, my_steer, my_seg), seg_dir = __shfl_sync(kFull, my_dir, my_seg);
     double inc_x = 0, inc_y = 0;
     {
         double sy_, cy_;
         dm::sincos_(yaw_from, &sy_, &cy_);
-        if (seg.steer != 0)
+        if (seg_steer != 0)
         {
             inc_x = a * cy_ - b * sy_;
             inc_y = a * sy_ + b * cy_;
         }
         else
         {
-            const double direc = (double)seg.dir;
+            const double direc = (double)seg_dir;
             inc_x = a * cy_ * direc;
             inc_y = a * sy_ * direc;
         }
     }
     // positions: the reference's running sums, in order
-    double cx = sx, cy = sy, my_x = sx, my_y = sy;
+    double cx = sx, cy = sy;
     for (int n = 0; n < total; ++n)
     {
         cx = cx + __shfl_sync(kFull, inc_x, n);
         cy = cy + __shfl_sync(kFull, inc_y, n);
         if (lane == n)
-            my_x = cx, my_y = cy;
+            px = cx, py = cy;
     }
-    if (live && lane < cap)
-    {
-        out_xyz[3 * lane] = my_x, out_xyz[3 * lane + 1] = my_y, out_xyz[3 * lane + 2] = yaw_to;
-        if (out_sd)
-            out_sd[2 * lane] = (double)seg.steer * c.steer_angle, out_sd[2 * lane + 1] = (double)seg.dir;
-    }
-    __syncwarp();
+    pyaw = yaw_to;
+    psteer = seg_steer;
+    pdir = seg_dir;
     return total;
 }
 

@@ -151,6 +151,8 @@ def load_library(path=LIB_PATH):
     L.mpros_rs_distance_batch.argtypes = [vp, d, vp, vp, sz, vp]
     L.mpros_expand_batch.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp]
     L.mpros_expand_batch_dev.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp]
+    L.mpros_expand_batch_compact.argtypes = [vp, vp, vp, vp, sz, vp, sz, C.POINTER(sz), vp]
+    L.mpros_expand_batch_compact_dev.argtypes = [vp, vp, vp, vp, sz, vp, sz, vp, vp]
     L.mpros_plan_batch.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, i, vp]
     L.mpros_path_postprocess_batch.argtypes = [vp, vp, vp, sz, vp, sz, vp]
     L.mpros_plan_search_tree.argtypes = [vp, vp, vp, vp, vp, vp, sz, C.POINTER(sz)]
@@ -178,6 +180,11 @@ def load_library(path=LIB_PATH):
 
 
 PLAN_LANES = 4  # MPROS_PLAN_LANES
+
+# mpros_child_record (include/mpros_gpu.h): 80 bytes
+CHILD_RECORD = np.dtype([("parent", "<u4"), ("prim", "<u2"), ("dir", "<i2"), ("i", "<i4"), ("j", "<i4"), ("x", "<f8"), ("y", "<f8"),
+                         ("yaw", "<f8"), ("steer", "<f8"), ("g", "<f8"), ("h", "<f8"), ("f", "<f8"), ("order", "<u4"), ("reserved", "<u4")])
+assert CHILD_RECORD.itemsize == 80
 
 
 def exported_symbols():
@@ -522,6 +529,21 @@ class Context:
         self._check(self.L.mpros_expand_batch(self.h, s.ctypes.data if s is not None else None, g.ctypes.data, p.ctypes.data, n,
                                               prims.ctypes.data, childs.ctypes.data, nchild.ctypes.data))
         return prims, childs, nchild
+
+    def expand_batch_compact(self, start3, goal3, parents6, cap=None):
+        """mpros_expand_batch_compact: the inserted children only, as CHILD_RECORD rows sorted by (parent, order)."""
+        par = np.ascontiguousarray(parents6, dtype=np.float64).reshape(-1, 6)
+        n = len(par)
+        cap = n * self.n_primitives() if cap is None else cap
+        rec = np.zeros(max(cap, 1), dtype=CHILD_RECORD)
+        nchild = np.zeros(n, dtype=np.int32)
+        cnt = C.c_size_t(0)
+        s = None if start3 is None else np.ascontiguousarray(start3, dtype=np.float64)
+        g = np.ascontiguousarray(goal3, dtype=np.float64)
+        self._check(self.L.mpros_expand_batch_compact(self.h, None if s is None else s.ctypes.data, g.ctypes.data, par.ctypes.data, n,
+                                                      rec.ctypes.data, cap, C.byref(cnt), nchild.ctypes.data))
+        rec = rec[: cnt.value]
+        return rec[np.lexsort((rec["order"], rec["parent"]))], nchild
 
     # ---- planner ----
     def plan_batch(self, starts3, goals3, path_cap=256, truncate_ok=False):

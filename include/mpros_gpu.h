@@ -251,6 +251,28 @@ MPROS_API int mpros_expand_batch(mpros_ctx *ctx, const double *start3, const dou
 MPROS_API int mpros_expand_batch_dev(mpros_ctx *ctx, const double *start3, const double *goal3, const double *d_parents6, size_t n,
                                      double *d_prims, double *d_childs, int32_t *d_nchild);
 
+/* Compact output of the same expansion: only the children expandNode inserts into the open list (hybrid_a_star.cpp:369-398),
+ * as 80-byte records appended in batches per parent - the children of one parent are contiguous and in insertion order
+ * (`order`), parents appear in no particular order. About two records per expansion travel instead of the 816 bytes of
+ * fixed-size arrays above (P = 6), which is what bounds the host-buffer form. *n_records = records produced (may exceed
+ * cap_records: then the call returns MPROS_ERR_CAPACITY after storing the first cap_records); nchild: int32[n], may be NULL. */
+typedef struct mpros_child_record
+{
+    uint32_t parent;  /* index of the parent in parents6                          */
+    uint16_t prim;    /* motion primitive: 2 * steer index + direction index       */
+    int16_t dir;      /* +1 forward, -1 backward                                   */
+    int32_t i, j;     /* cell of the child on the down-sampled grid (calIndex)     */
+    double x, y, yaw, steer, g, h, f;
+    uint32_t order;   /* position among the parent's inserted children             */
+    uint32_t reserved;
+} mpros_child_record;
+MPROS_API int mpros_expand_batch_compact(mpros_ctx *ctx, const double *start3, const double *goal3, const double *parents6, size_t n,
+                                         mpros_child_record *records, size_t cap_records, size_t *n_records, int32_t *nchild);
+/* Device buffers; d_n_records: one uint64 in device memory; asynchronous on the context's stream. */
+MPROS_API int mpros_expand_batch_compact_dev(mpros_ctx *ctx, const double *start3, const double *goal3, const double *d_parents6, size_t n,
+                                             mpros_child_record *d_records, size_t cap_records, unsigned long long *d_n_records,
+                                             int32_t *d_nchild);
+
 /* ---- planner ------------------------------------------------------------------------------------------------ */
 /* Per-query result of mpros_plan_batch: what HybridAstar::Plan() returns and why. */
 enum mpros_plan_status

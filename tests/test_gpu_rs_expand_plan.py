@@ -298,6 +298,47 @@ def test_expand_batch_device_buffers_match_host_buffers(gpu_ctx_factory):
     assert np.array_equal(ch_d.cpu().numpy().reshape(n, P, 10), childs)
 
 
+def test_expand_batch_compact_records_equal_the_reference_format_children(gpu_ctx_factory):
+    """mpros_expand_batch_compact: the inserted children as 80-byte records == the rows of mpros_expand_batch's childs array,
+    bit for bit; a buffer that is too small reports the required size."""
+    import bench
+    import mpros_b200
+    import synthetic
+
+    ctx = gpu_ctx_factory()
+    params = bench.shipped_params()
+    ctx.map_config(params)
+    ctx.set_occupancy(synthetic.synthetic_occupancy(size=2048, n_rect=70), synthetic.SYN_RES, [0.0, 0.0, 0.0])
+    ctx.planner_config(params)
+    rng = np.random.default_rng(6)
+    poses = np.stack([rng.uniform(0, 204.8, 9000), rng.uniform(0, 204.8, 9000), rng.uniform(-np.pi, np.pi, 9000)], axis=1)
+    poses = poses[ctx.collision_check(poses) == 0][:3001]
+    goal = poses[0].copy()
+    ctx.update_goal(goal[0], goal[1])
+    n = len(poses)
+    par = np.concatenate([poses, 0.35 * rng.integers(-1, 2, n)[:, None], rng.choice([-1.0, 1.0], n)[:, None], rng.uniform(0, 50, n)[:, None]], axis=1)
+    prims, childs, nchild = ctx.expand_batch(poses[1], goal, par)
+    rec, nchild_c = ctx.expand_batch_compact(poses[1], goal, par)
+    assert np.array_equal(nchild, nchild_c) and len(rec) == int(nchild.sum()) > n
+    at = 0
+    for k in range(n):
+        r = rec[at:at + nchild[k]]
+        at += nchild[k]
+        assert np.all(r["parent"] == k) and np.array_equal(r["order"], np.arange(nchild[k]))
+        c = childs[k, : nchild[k]]
+        for col, name in enumerate(["x", "y", "yaw", "steer"]):
+            assert np.array_equal(r[name], c[:, col])
+        assert np.array_equal(r["dir"].astype(np.float64), c[:, 4])
+        for col, name in [(5, "g"), (6, "h"), (7, "f")]:
+            assert np.array_equal(r[name], c[:, col])
+        assert np.array_equal(r["i"], c[:, 8].astype(np.int32)) and np.array_equal(r["j"], c[:, 9].astype(np.int32))
+        # the primitive a child came from: its end pose is that primitive's row
+        assert np.array_equal(prims[k, r["prim"], 0], r["x"])
+    with pytest.raises(mpros_b200.MprosError) as e:
+        ctx.expand_batch_compact(poses[1], goal, par, cap=100)
+    assert "too small" in str(e.value)
+
+
 def test_rs_shot_batch_device_buffers_match_host_buffers(gpu_ctx_factory):
     """mpros_rs_shot_batch_dev (device buffers, asynchronous, no trajectory) == mpros_rs_shot_batch."""
     import torch
