@@ -261,6 +261,13 @@ def usable_cores(per_process_bytes=3.5e9):
     return max(1, min(nproc, by_mem)), nproc, by_mem
 
 
+def effective_lanes(args, world):
+    """Query batches in flight of the plan workload: --lanes, else 4, else 8 for --scaling strong on several GPUs (a rank's
+    batch shrinks with the world size, the iteration-limit tail does not); never more than the library's MPROS_PLAN_LANES."""
+    want = args.lanes if args.lanes > 0 else (8 if (args.scaling == "strong" and world > 1) else 4)
+    return max(1, min(want, 8))
+
+
 def plan_config(lanes, scaling="weak", world=1):
     """config of the plan workload, identical for the GPU arm and the reference arm (the reference arm times a seeded
     sample of the same query set; what the sample was is stated in its cpu_baseline.sample)."""
@@ -320,7 +327,7 @@ def run_reference(args):
         "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": len(vals),
         "warmup": args.warmup, "ms_per_step": (1e3 * per_step / extra["plans_per_sec"]) if args.workload == "expand" else 1e3 * per_step / value, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": plan_config(max(1, min(args.lanes, 4)), args.scaling) if args.workload == "plan" else {"workload": workload_text(args.workload)},
+        "config": plan_config(effective_lanes(args, args.gpus), args.scaling) if args.workload == "plan" else {"workload": workload_text(args.workload)},
         "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "nproc": nproc, "processes_memory_allows": by_mem, "kind": "reference",
                          "sample": sample, "units_per_step": per_step},
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -724,7 +731,10 @@ def run_b200(args):
         # Batches in flight: step k runs on lane k % LANES (own stream + planner workspaces, include/mpros_gpu.h), so the
         # iteration-limit tail of one batch (a few queries, each a dependent chain of 100 001 expansions) overlaps the next
         # batch. Every step still plans all nq queries and writes all results; --lanes 1 gives one batch at a time.
-        LANES = max(1, min(args.lanes, mpros_b200.PLAN_LANES))
+        # Strong scaling shrinks a rank's batch (16 384 / world queries) but not its tail (a limit query is 100 001 dependent
+        # expansions whatever the batch size), so more batches must be in flight to cover it: 8 lanes unless --lanes is given.
+        # Lanes share the context's workspace pool, so this costs streams and staging areas only.
+        LANES = min(effective_lanes(args, world), mpros_b200.PLAN_LANES)
 
         def dev_bufs():
             return {"status": torch.zeros(nq, dtype=torch.int32, device="cuda"), "cost": torch.zeros(nq, dtype=torch.float64, device="cuda"),
@@ -743,7 +753,7 @@ def run_b200(args):
         status_d, cost_d, stats_d = dbuf[0]["status"], dbuf[0]["cost"], dbuf[0]["stats"]
         status_h, cost_h = hbuf[0]["status"], hbuf[0]["cost"]
         # result gather (world > 1): per-step cost buffers in a ring, so that a lane's next batch never waits for a gather
-        RING = 8
+        RING = 16
         cost_ring = [torch.zeros(nq, dtype=torch.float64, device="cuda") for _ in range(RING)] if world > 1 else None
         gather = [[torch.zeros(nq, dtype=torch.float64, device="cuda") for _ in range(world)] for _ in range(RING)] if world > 1 else None
         gathered = [None] * RING
@@ -1005,7 +1015,7 @@ def arena_measure(args, steps, with_cpu):
     starts, goals = synthetic.synthetic_queries(nq, ctx.collision_check, static_ds, res * ds, extent, synthetic.SYN_QUERY_SEED)
     s_h, g_h = torch.from_numpy(starts).pin_memory(), torch.from_numpy(goals).pin_memory()
     s_d, g_d = s_h.cuda(), g_h.cuda()
-    LANES = max(1, min(args.lanes, mpros_b200.PLAN_LANES))
+    LANES = min(effective_lanes(args, 1), mpros_b200.PLAN_LANES)
     mk = lambda pin: {k: (torch.zeros(sz, dtype=dt).pin_memory() if pin else torch.zeros(sz, dtype=dt, device="cuda"))
                       for k, sz, dt in (("status", nq, torch.int32), ("cost", nq, torch.float64), ("len", nq, torch.int32),
                                         ("paths", nq * PATH_CAP * 5, torch.float64), ("stats", nq * 6, torch.int64))}
@@ -1126,7 +1136,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="plan", choices=["plan", "collision", "expand", "preprocess", "rs", "arena"])
-    ap.add_argument("--lanes", type=int, default=4, help="plan workload: query batches in flight (1 = one batch at a time)")
+    ap.add_argument("--lanes", type=int, default=0,
+                    help="plan workload: query batches in flight (1 = one batch at a time; default 4, or 8 for --scaling strong on several GPUs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="plan workload: weak = 16384 queries per GPU (default), strong = 16384 queries in total, sharded across the GPUs")

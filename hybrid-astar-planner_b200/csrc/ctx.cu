@@ -75,14 +75,23 @@ static void free_plan_scratch(Ctx *c)
         for (int k = 0; k < kPlanPasses; ++k)
         {
             PlanScratch &S = c->plan_scratch[l][k];
-            if (S.ws)
-                cudaFree(S.ws);
             if (S.counter)
                 cudaFree(S.counter);
             if (S.todo)
                 cudaFree(S.todo);
             S = PlanScratch();
         }
+    for (int k = 0; k < kPlanPasses; ++k)
+    {
+        PlanPool &P = c->plan_pool[k];
+        if (P.base)
+            cudaFree(P.base);
+        if (P.owner)
+            cudaFree(P.owner);
+        if (P.gen)
+            cudaFree(P.gen);
+        P = PlanPool();
+    }
 }
 } // namespace mpros
 

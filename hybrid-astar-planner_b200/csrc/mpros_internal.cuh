@@ -75,17 +75,34 @@ struct PlannerView
     int max_iteration;
 };
 
-// Per-query planner workspaces of one (lane, pass): node pools, open lists, closed sets and goal-wavefront windows of every
-// resident team (plan.cu). Owned by the context, freed by mpros_ctx_destroy / mpros_plan_release_workspaces.
+// Device view of a workspace pool (plan_team.cuh: pool_acquire / pool_release)
+struct WorkspacePool
+{
+    char *base;    // n x stride bytes
+    int *owner;    // n flags: 0 free, 1 taken
+    uint32_t *gen; // n generation counters (< 2^30; the host clears the pool before they could wrap)
+    int n;
+};
+// Per-query planner workspaces of one pass (node-pool size class): node pools, open lists, closed sets and goal-wavefront
+// windows, one per resident team of the DEVICE, shared by every lane of the context (plan.cu). Owned by the context, freed
+// by mpros_ctx_destroy / mpros_plan_release_workspaces.
+struct PlanPool
+{
+    char *base = nullptr;
+    size_t bytes = 0, stride = 0;
+    int n = 0;
+    int *owner = nullptr;
+    uint32_t *gen = nullptr;
+    int meta_cap = 0;                    // entries of owner / gen
+    unsigned long long issued = 0;       // upper bound of the generations handed out since the last clear
+    unsigned char last_layout[128] = {}; // WarpWorkspaceLayout the bytes were last interpreted with (stale tags could alias)
+};
+// Work distribution of one (lane, pass): ticket counter and the list of queries to re-run
 struct PlanScratch
 {
-    char *ws = nullptr;
-    size_t ws_bytes = 0;
     unsigned int *counter = nullptr;
     int32_t *todo = nullptr;
     size_t todo_cap = 0;
-    uint32_t tag_base = 0;
-    unsigned char last_layout[128] = {}; // WarpWorkspaceLayout the bytes were last interpreted with (stale tags could alias)
 };
 constexpr int kPlanPasses = 3; // node-pool size classes
 
@@ -112,6 +129,7 @@ struct Ctx
     uint64_t launches = 0;
     Options opt;
     PlanScratch plan_scratch[MPROS_PLAN_LANES][kPlanPasses];
+    PlanPool plan_pool[kPlanPasses];
     int plan_resident[3] = {0, 0, 0}; // resident teams per SM: [0] CTA teams, [1] CTA-pair teams (occupancy query, cached), [2] two teams per CTA
 
     mpros_map_params mp;

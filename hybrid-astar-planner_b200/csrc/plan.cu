@@ -74,8 +74,7 @@ struct PlanBatchArgs
     const int32_t *todo; // indices of the queries to run in this pass (null = all)
     int n_todo;
     unsigned int *counter;
-    uint32_t tag_base;
-    char *ws;
+    WorkspacePool pool; // a team takes one workspace for the lifetime of its CTA (plan_team.cuh)
     WarpWorkspaceLayout L;
     RsConfig rs;
     int optimal;
@@ -982,15 +981,26 @@ namespace mpros
 constexpr int kTeamWarps = MPROS_TEAM_WARPS;
 constexpr int kTeamMinBlocks = MPROS_TEAM_MIN_BLOCKS;
 
-static_assert(sizeof(WarpWorkspaceLayout) <= sizeof(PlanScratch::last_layout), "PlanScratch::last_layout too small");
+static_assert(sizeof(WarpWorkspaceLayout) <= sizeof(PlanPool::last_layout), "PlanPool::last_layout too small");
+
+// every batch in flight on any lane of the context is complete (the pool is about to be re-allocated or cleared)
+static int plan_quiesce(mpros_ctx *c)
+{
+    MPROS_CUDA(cudaStreamSynchronize(c->stream));
+    for (int l = 1; l < MPROS_PLAN_LANES; ++l)
+        if (c->lane_stream[l])
+            MPROS_CUDA(cudaStreamSynchronize(c->lane_stream[l]));
+    return MPROS_OK;
+}
 
 static int plan_pass(mpros_ctx *c, int lane, cudaStream_t stream, PlanBatchArgs &a, int pass, int node_cap, int n_run, const int32_t *d_todo,
                      int max_warps)
 {
-    PlanScratch &S = c->plan_scratch[lane][pass]; // owned by the context: two contexts never share workspaces
+    PlanScratch &S = c->plan_scratch[lane][pass]; // ticket counter / re-run list of this lane
+    PlanPool &PL = c->plan_pool[pass];            // workspaces: owned by the context, shared by its lanes
     WarpWorkspaceLayout L = make_layout(node_cap, c->H, c->W);
-    // resident teams: a multiple of the SM count; bounded by the workspace budget. Device queries are cached in the
-    // context: a batch submission should cost the host microseconds (cudaGetDeviceProperties alone takes milliseconds).
+    // resident teams: a multiple of the SM count. Device queries are cached in the context: a batch submission should cost
+    // the host microseconds (cudaGetDeviceProperties alone takes milliseconds).
     const int n_sm = c->n_sm;
     // team = one CTA (default) or a cluster of two CTAs on the two SMs of a TPC (MPROS_PLAN_MODE=cluster; plan_team.cuh).
     // Measured on the 16 384-query synthetic batch: CTA teams 1.57 s (296 teams, 6.8-7.5 us per iteration alone, ~11 us with
@@ -1012,52 +1022,86 @@ static int plan_pass(mpros_ctx *c, int lane, cudaStream_t stream, PlanBatchArgs 
             MPROS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, plan_team_kernel<kTeamWarps, kTeamMinBlocks>, kTeamWarps * 32, 0));
         resident = std::max(1, resident);
     }
-    // one team per query at a time; every resident team owns one workspace
-    int blocks = (cluster ? n_sm / 2 : n_sm) * resident;
-    blocks = std::min(blocks, n_run);
-    if (max_warps > 0)
-        blocks = std::min(blocks, std::max(1, max_warps));
-    if ((size_t)blocks * L.stride > S.ws_bytes) // what the lane already owns does not cover it: ask the device
+    // The pool holds one workspace per team the DEVICE can keep resident (the register file decides: two CTAs per SM), however
+    // many batches are in flight: the CTAs of a later batch's kernel take the workspaces - and the SM slots - an earlier one
+    // frees. (Round 1 gave every lane its own set: 4 x 33 GB; now 33 GB serve any number of lanes.)
+    int teams = (cluster ? n_sm / 2 : n_sm) * resident;
+    if (duo)
+        teams = (teams + 1) & ~1;
+    const bool layout_change = std::memcmp(PL.last_layout, &L, sizeof(L)) != 0;
+    if (layout_change || PL.n < teams)
     {
+        // a different layout re-interprets the same bytes (stale tags could alias), a bigger pool moves it: nothing may be
+        // in flight on any lane, and the pool starts out cleared
         size_t free_b = 0, total_b = 0;
         MPROS_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        const size_t budget = (free_b + S.ws_bytes) / 2;
-        blocks = (int)std::min<long long>(blocks, std::max<long long>(1, (long long)(budget / L.stride)));
+        const size_t budget = (free_b + PL.bytes) / 2;
+        int n = (int)std::min<long long>(teams, std::max<long long>(1, (long long)(budget / L.stride)));
+        if (duo)
+            n = std::max(2, n & ~1);
+        if (layout_change || n > PL.n)
+        {
+            int rc = plan_quiesce(c);
+            if (rc)
+                return rc;
+            const size_t need = (size_t)n * L.stride;
+            if (need > PL.bytes)
+            {
+                if (PL.base)
+                    MPROS_CUDA(cudaFree(PL.base));
+                PL.base = nullptr;
+                PL.bytes = 0;
+                MPROS_CUDA(cudaMalloc(&PL.base, need));
+                PL.bytes = need;
+            }
+            if (n > PL.meta_cap)
+            {
+                if (PL.owner)
+                    MPROS_CUDA(cudaFree(PL.owner));
+                if (PL.gen)
+                    MPROS_CUDA(cudaFree(PL.gen));
+                PL.owner = nullptr, PL.gen = nullptr, PL.meta_cap = 0;
+                MPROS_CUDA(cudaMalloc(&PL.owner, (size_t)n * 4));
+                MPROS_CUDA(cudaMalloc(&PL.gen, (size_t)n * 4));
+                PL.meta_cap = n;
+            }
+            MPROS_CUDA(cudaMemsetAsync(PL.base, 0, PL.bytes, stream));
+            MPROS_CUDA(cudaMemsetAsync(PL.owner, 0, (size_t)PL.meta_cap * 4, stream));
+            MPROS_CUDA(cudaMemsetAsync(PL.gen, 0, (size_t)PL.meta_cap * 4, stream));
+            MPROS_CUDA(cudaStreamSynchronize(stream)); // the other lanes' streams are not ordered behind this one
+            PL.n = n;
+            PL.stride = L.stride;
+            PL.issued = 0;
+            std::memcpy(PL.last_layout, &L, sizeof(L));
+        }
     }
+    // generation tags must stay below 2^30 and unique per (workspace, query); a workspace sees at most every query issued
+    if (PL.issued + (unsigned long long)n_run + 2ull >= (1ull << 30))
+    {
+        int rc = plan_quiesce(c);
+        if (rc)
+            return rc;
+        MPROS_CUDA(cudaMemsetAsync(PL.base, 0, PL.bytes, stream));
+        MPROS_CUDA(cudaMemsetAsync(PL.gen, 0, (size_t)PL.meta_cap * 4, stream));
+        MPROS_CUDA(cudaStreamSynchronize(stream));
+        PL.issued = 0;
+    }
+    PL.issued += (unsigned long long)n_run + 1ull;
+    // one team per query at a time; never more CTAs than workspaces (a CTA without one would only wait for one)
+    int blocks = std::min(std::min(teams, PL.n), n_run);
+    if (max_warps > 0)
+        blocks = std::min(blocks, std::max(1, max_warps));
     if (duo)
         blocks = (blocks + 1) & ~1; // a CTA always owns two workspaces
-    size_t need = (size_t)blocks * L.stride;
-    if (need > S.ws_bytes)
-    {
-        if (S.ws)
-            MPROS_CUDA(cudaFree(S.ws));
-        S.ws = nullptr;
-        S.ws_bytes = 0;
-        MPROS_CUDA(cudaMalloc(&S.ws, need));
-        MPROS_CUDA(cudaMemsetAsync(S.ws, 0, need, stream));
-        S.ws_bytes = need;
-        S.tag_base = 0;
-    }
     if (!S.counter)
         MPROS_CUDA(cudaMalloc(&S.counter, 256));
-    // generation tags must stay below 2^30 and unique per (warp, query); every warp handles < n_run queries
-    if ((unsigned long long)S.tag_base + (unsigned long long)n_run + 2ull >= (1ull << 30))
-    {
-        MPROS_CUDA(cudaMemsetAsync(S.ws, 0, S.ws_bytes, stream));
-        S.tag_base = 0;
-    }
-    // a different layout re-interprets the same bytes: stale tags could alias, so clear when the layout changes
-    if (std::memcmp(S.last_layout, &L, sizeof(L)) != 0)
-    {
-        MPROS_CUDA(cudaMemsetAsync(S.ws, 0, S.ws_bytes, stream));
-        S.tag_base = 0;
-        std::memcpy(S.last_layout, &L, sizeof(L));
-    }
     MPROS_CUDA(cudaMemsetAsync(S.counter, 0, 4, stream));
     a.L = L;
-    a.ws = S.ws;
+    a.pool.base = PL.base;
+    a.pool.owner = PL.owner;
+    a.pool.gen = PL.gen;
+    a.pool.n = PL.n;
     a.counter = S.counter;
-    a.tag_base = S.tag_base;
     a.todo = d_todo;
     a.n_todo = n_run;
     const bool dbg = c->opt.debug;
@@ -1104,7 +1148,6 @@ static int plan_pass(mpros_ctx *c, int lane, cudaStream_t stream, PlanBatchArgs 
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
     }
-    S.tag_base += (uint32_t)n_run + 1;
     return MPROS_OK;
 }
 } // namespace mpros
@@ -1138,17 +1181,16 @@ static int plan_batch_dev_impl(mpros_ctx *c, int lane, cudaStream_t stream, cons
     {
         WarpWorkspaceLayout big = make_layout((int)max_nodes, c->H, c->W);
         const size_t full = big.stride * (size_t)(kTeamMinBlocks * c->n_sm);
-        if (S.ws_bytes >= full) // the lane already owns full-size pools
-            caps[0] = max_nodes;
+        if (c->plan_pool[0].bytes >= full && std::memcmp(c->plan_pool[0].last_layout, &big, sizeof(big)) == 0)
+            caps[0] = max_nodes; // the context already owns a full-size pool
         else
         {
             size_t free_b = 0, total_b = 0;
             MPROS_CUDA(cudaMemGetInfo(&free_b, &total_b));
             size_t have = free_b;
             for (int k = 0; k < kPlanPasses; ++k)
-                have += c->plan_scratch[lane][k].ws_bytes;
-            // lane 0 keeps half of the memory free for the caller; the extra lanes (pipelined batches) may use what is left
-            if (full < (lane == 0 ? have / 2 : have - have / 8))
+                have += c->plan_pool[k].bytes;
+            if (full < have / 2) // half of the memory stays free for the caller
                 caps[0] = max_nodes;
         }
     }

@@ -44,6 +44,8 @@ struct TeamShared
     double sx, sy, syaw, gx, gy, gyaw;
     int si, sj, gi, gj;
     int q, init_ok, init_hit[2];
+    int ws_slot;      // workspace of the pool this team holds
+    uint32_t ws_gen;  // its generation counter when the team took it
     // search state
     int iteration, flag, need_shot, shot_ok, overflow, goal_found, stop;
     uint32_t n_nodes, cur_id, goal_parent;
@@ -90,6 +92,36 @@ struct TeamShared
     unsigned long long prof[24];
 #endif
 };
+
+// ---- workspace pool -------------------------------------------------------------------------------------------------------
+// The per-query workspaces (node pool, open list, closed set, goal-wavefront window: ~110 MB at the 100 000-iteration limit)
+// belong to a POOL of the context, not to a launch: a team takes a free one when its CTA starts and gives it back when the
+// CTA exits. The register file admits a fixed number of resident teams per device (two per SM), so one pool of that many
+// workspaces serves any number of batches in flight ("lanes"): the CTAs of the next batch's kernel take over the
+// workspaces - and the SM slots - the previous batch frees. Stale contents are harmless: closed-set slots carry a
+// generation tag that is unique per (workspace, query) - the generation counter lives with the workspace - and every other
+// array is written by a query before that query reads it.
+__device__ __forceinline__ int pool_acquire(const WorkspacePool &pl, int first)
+{
+    int i = first % pl.n, tries = 0;
+    while (atomicCAS(&pl.owner[i], 0, 1) != 0)
+    {
+        i = i + 1 == pl.n ? 0 : i + 1;
+        if (++tries >= pl.n) // every workspace is taken by a resident team of another batch: wait for one to finish
+        {
+            tries = 0;
+            __nanosleep(2000);
+        }
+    }
+    __threadfence(); // acquire: the previous owner's writes (and its generation counter) are visible
+    return i;
+}
+__device__ __forceinline__ void pool_release(const WorkspacePool &pl, int i, uint32_t gen)
+{
+    pl.gen[i] = gen;
+    __threadfence(); // release
+    atomicExch(&pl.owner[i], 0);
+}
 
 // A CTA holds one team (plan_team_kernel, plan_cluster_kernel) or two (plan_duo_kernel); everything below addresses threads
 // and barriers relative to the team: thread index 0 .. NW*32-1, named barriers 1 + 3 t (whole team), 2 + 3 t (compute group:
@@ -1589,8 +1621,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) plan_team_kernel(const __grid_c
                                                                    const __grid_constant__ PlanBatchArgs a)
 {
     __shared__ TeamShared<NW> S;
-    char *ws = a.ws + (size_t)blockIdx.x * a.L.stride;
-    uint32_t local_gen = 0;
+    if (team_tid<NW>() == 0)
+    {
+        S.ws_slot = pool_acquire(a.pool, (int)blockIdx.x);
+        S.ws_gen = a.pool.gen[S.ws_slot];
+    }
+    team_sync_all<NW>();
+    const int slot = S.ws_slot;
+    char *ws = a.pool.base + (size_t)slot * a.L.stride;
+    uint32_t gen = S.ws_gen;
     const int total = a.todo ? a.n_todo : a.nq;
     while (true)
     {
@@ -1602,9 +1641,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) plan_team_kernel(const __grid_c
         if (t >= total)
             break;
         int q = a.todo ? a.todo[t] : t;
-        ++local_gen;
-        plan_team_query<NW, false>(m, p, a, q, ws, a.tag_base + local_gen, S, nullptr);
+        ++gen;
+        plan_team_query<NW, false>(m, p, a, q, ws, gen, S, nullptr);
     }
+    team_sync_all<NW>();
+    if (team_tid<NW>() == 0)
+        pool_release(a.pool, slot, gen);
 }
 
 // Two teams per CTA, one CTA per SM (see DuoSync): blockIdx.x * 2 + team index = workspace; each team pulls its own queries.
@@ -1623,8 +1665,15 @@ __global__ void __launch_bounds__(NW * 64, 1) plan_duo_kernel(const __grid_const
         D->active[0] = D->active[1] = 0;
     }
     __syncthreads();
-    char *ws = a.ws + (size_t)(blockIdx.x * 2 + team) * a.L.stride;
-    uint32_t local_gen = 0;
+    if (team_tid<NW>() == 0)
+    {
+        S.ws_slot = pool_acquire(a.pool, (int)blockIdx.x * 2 + team);
+        S.ws_gen = a.pool.gen[S.ws_slot];
+    }
+    team_sync_all<NW>();
+    const int slot = S.ws_slot;
+    char *ws = a.pool.base + (size_t)slot * a.L.stride;
+    uint32_t gen = S.ws_gen;
     const int total = a.todo ? a.n_todo : a.nq;
     while (true)
     {
@@ -1636,9 +1685,12 @@ __global__ void __launch_bounds__(NW * 64, 1) plan_duo_kernel(const __grid_const
         if (t >= total)
             break;
         int q = a.todo ? a.todo[t] : t;
-        ++local_gen;
-        plan_team_query<NW, false>(m, p, a, q, ws, a.tag_base + local_gen, S, nullptr, D);
+        ++gen;
+        plan_team_query<NW, false>(m, p, a, q, ws, gen, S, nullptr, D);
     }
+    team_sync_all<NW>();
+    if (team_tid<NW>() == 0)
+        pool_release(a.pool, slot, gen);
 }
 template <int NW>
 constexpr size_t duo_smem_bytes() { return 2 * ((sizeof(TeamShared<NW>) + 15) / 16 * 16) + sizeof(DuoSync) + 16; }
@@ -1667,8 +1719,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NW * 32, MINB)
         return;
     }
     HeurShared *Hpeer = cluster_peer(&H, 1);
-    char *ws = a.ws + (size_t)(blockIdx.x >> 1) * a.L.stride;
-    uint32_t local_gen = 0;
+    if (team_tid<NW>() == 0)
+    {
+        S.ws_slot = pool_acquire(a.pool, (int)(blockIdx.x >> 1));
+        S.ws_gen = a.pool.gen[S.ws_slot];
+    }
+    team_sync_all<NW>();
+    const int slot = S.ws_slot;
+    char *ws = a.pool.base + (size_t)slot * a.L.stride;
+    uint32_t gen = S.ws_gen;
     const int total = a.todo ? a.n_todo : a.nq;
     while (true)
     {
@@ -1680,9 +1739,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NW * 32, MINB)
         if (t >= total)
             break;
         int q = a.todo ? a.todo[t] : t;
-        ++local_gen;
-        plan_team_query<NW, true>(m, p, a, q, ws, a.tag_base + local_gen, S, Hpeer);
+        ++gen;
+        plan_team_query<NW, true>(m, p, a, q, ws, gen, S, Hpeer);
     }
+    team_sync_all<NW>();
+    if (team_tid<NW>() == 0)
+        pool_release(a.pool, slot, gen);
     // release the heuristic CTA: the last X of this cluster carries the exit command
     if (team_tid<NW>() == 0)
         Hpeer->cmd = 1;

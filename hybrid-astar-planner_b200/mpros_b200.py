@@ -179,7 +179,7 @@ def load_library(path=LIB_PATH):
     return L
 
 
-PLAN_LANES = 4  # MPROS_PLAN_LANES
+PLAN_LANES = 8  # MPROS_PLAN_LANES
 
 # mpros_child_record (include/mpros_gpu.h): 80 bytes
 CHILD_RECORD = np.dtype([("parent", "<u4"), ("prim", "<u2"), ("dir", "<i2"), ("i", "<i4"), ("j", "<i4"), ("x", "<f8"), ("y", "<f8"),

@@ -248,8 +248,9 @@ def test_full_batch_properties(syn):
 
 
 def test_batches_in_flight_match_the_synchronous_call(syn):
-    """mpros_plan_batch_submit[_dev] / mpros_plan_batch_wait: several batches in flight on their own lanes (streams +
-    workspaces) give exactly the per-query results of mpros_plan_batch, in any interleaving."""
+    """mpros_plan_batch_submit[_dev] / mpros_plan_batch_wait: batches in flight on all eight lanes (own streams and staging
+    areas, ONE workspace pool of the context: a team takes a free workspace when its CTA starts) give exactly the per-query
+    results of mpros_plan_batch, in any interleaving; eight lanes need no more workspace memory than one."""
     import torch
 
     import mpros_b200
@@ -257,8 +258,10 @@ def test_batches_in_flight_match_the_synchronous_call(syn):
     ctx, params, occ, starts, goals = syn
     n = 2048
     cap = 64
-    ref = [ctx.plan_batch(starts[k * n:(k + 1) * n], goals[k * n:(k + 1) * n], path_cap=cap, truncate_ok=True) for k in range(4)]
-    lanes = [0, 1, 2, 3][: mpros_b200.PLAN_LANES]
+    assert mpros_b200.PLAN_LANES == 8
+    ref = [ctx.plan_batch(starts[k * n:(k + 1) * n], goals[k * n:(k + 1) * n], path_cap=cap, truncate_ok=True) for k in range(8)]
+    lanes = list(range(mpros_b200.PLAN_LANES))
+    free_after_one_lane = torch.cuda.mem_get_info()[0]
 
     def bufs(pin):
         mk = (lambda *a, **k: torch.zeros(*a, **k).pin_memory()) if pin else (lambda *a, **k: torch.zeros(*a, device="cuda", **k))
@@ -298,6 +301,8 @@ def test_batches_in_flight_match_the_synchronous_call(syn):
         assert np.array_equal(b["status"].cpu().numpy(), r["status"]) and np.array_equal(b["cost"].cpu().numpy(), r["cost"])
         assert np.array_equal(b["stats"].cpu().numpy().reshape(n, 6)[:, 0], r["iterations"])
     assert ctx.plan_lane_stream(1) and ctx.plan_lane_stream(0) == ctx.stream()
+    # the lanes added staging areas and the test its buffers (< 1 GB), not workspaces (33 GB per set)
+    assert free_after_one_lane - torch.cuda.mem_get_info()[0] < 2 << 30
     with pytest.raises(Exception):
         ctx.plan_batch_wait(mpros_b200.PLAN_LANES)
 
