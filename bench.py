@@ -577,9 +577,10 @@ def run_b200(args):
                             "d2h_bytes_per_step": ns * (120 + 4 + 8 + 4 + 1)},
                     "gpu_launches": int(launches),
                     "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                                 "traffic": ncu_traffic("rs_batch_kernel"), "kernel": "rs_batch_kernel", "kernel_ms": k_ms, "peak_source": peak_kind,
-                                 "algorithmic_bytes_per_unit": algo_unit,
-                                 "note": "FP64-issue bound (48 Reeds-Shepp candidate words with sin/cos/atan2/acos per shot, sequential trajectory integration), not HBM bound"},
+                                 "traffic": (lambda a, b: a + b if a is not None and b is not None else None)(ncu_traffic("rs_solve_kernel"), ncu_traffic("rs_traj_kernel")),
+                                 "kernel": "rs_solve_kernel + rs_traj_kernel (one shot batch = the two launches, timed together)", "kernel_ms": k_ms,
+                                 "peak_source": peak_kind, "algorithmic_bytes_per_unit": algo_unit,
+                                 "note": "FP64-issue / instruction-fetch bound (48 Reeds-Shepp candidate words with sin/cos/atan2/acos per shot, sequential trajectory integration), not HBM bound"},
                     "extra": {"mean_trajectory_poses": mean_pts, "shots_in_collision": float(ver_h.float().mean()),
                               "trajectory_poses_checked_per_sec": world * ns * mean_pts * args.steps / (total_ms * 1e-3),
                               "collision_kernel_checks_per_sec": col_value},

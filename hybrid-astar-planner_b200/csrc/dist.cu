@@ -4,6 +4,7 @@
 // planner call with its result gather. The reference has no counterpart: it is a single-threaded ROS node.
 #include <dlfcn.h>
 
+#include <chrono>
 #include <condition_variable>
 #include <cstring>
 #include <mutex>
@@ -94,20 +95,37 @@ struct LocalGroup
     int world = 0, waiting = 0, refs = 0;
     uint64_t generation = 0;
     void *ptr[64] = {};
-    void barrier()
+    bool broken = false; // a rank gave up waiting: every later barrier fails at once instead of hanging
+    // false when a peer rank did not arrive within two minutes (it failed before reaching the same call)
+    bool barrier()
     {
         std::unique_lock<std::mutex> lk(mu);
+        if (broken)
+            return false;
         const uint64_t gen = generation;
         if (++waiting == world)
         {
             waiting = 0;
             ++generation;
             cv.notify_all();
+            return true;
         }
-        else
-            cv.wait(lk, [&] { return generation != gen; });
+        if (!cv.wait_for(lk, std::chrono::seconds(120), [&] { return generation != gen || broken; }) || broken)
+        {
+            broken = true;
+            cv.notify_all();
+            return false;
+        }
+        return true;
     }
 };
+static int local_barrier(LocalGroup *g)
+{
+    if (g->barrier())
+        return MPROS_OK;
+    mpros::set_error("local communicator: a peer rank did not reach the exchange (it failed earlier, or the ranks make different calls)");
+    return MPROS_ERR_INVALID;
+}
 
 namespace mpros
 {
@@ -131,13 +149,14 @@ int comm_allgatherv(Ctx *c, mpros_comm *cm, void *buf, const size_t *off, const 
     LocalGroup *g = cm->grp;
     MPROS_CUDA(cudaStreamSynchronize(c->stream)); // my part is final
     g->ptr[cm->rank] = buf;
-    g->barrier();
+    int rc = local_barrier(g);
+    if (rc)
+        return rc;
     for (int r = 0; r < cm->world; ++r)
         if (r != cm->rank && cnt[r])
             MPROS_CUDA(cudaMemcpyAsync(b + off[r], static_cast<char *>(g->ptr[r]) + off[r], cnt[r], cudaMemcpyDefault, c->stream));
     MPROS_CUDA(cudaStreamSynchronize(c->stream));
-    g->barrier(); // nobody overwrites its part before every rank has read it
-    return MPROS_OK;
+    return local_barrier(g); // nobody overwrites its part before every rank has read it
 }
 
 int comm_allgather(Ctx *c, mpros_comm *cm, void *buf, size_t bytes)

@@ -227,37 +227,49 @@ __device__ __noinline__ bool rs_shot_long(const MapView &m, const PlannerView &p
     return hit;
 }
 
-// R1-R4 for a batch of shots. A warp takes EIGHT shots at a time: the solve runs with lane = (shot, symmetry image) and
-// walks the twelve words together (rs_find_optimal_quad: every lane in the same closed form, candidates in registers); the
-// trajectory and the sampled-path footprint test then run shot by shot with one lane per pose, the poses never leaving
-// registers (rs_gen_traj_regs). The first version - one shot per warp, the 48 candidates as per-thread segment arrays in
-// local memory, the trajectory in a per-warp HBM scratch - executed 9 800 warp-instructions per shot, eight divergent
-// formula bodies on four lanes each, and moved 3.4 GB of DRAM traffic per 2^20 shots against 0.45 GB algorithmic.
+// R1-R4 for a batch of shots, in two kernels with the winning candidate (three doubles and the word number: 40 bytes)
+// handed over in HBM:
+//   rs_solve_kernel  FindOptimalPath + PathLength: a warp takes EIGHT shots at a time, lane = (shot, symmetry image), and
+//                    walks the twelve words together (rs_find_optimal_quad: every lane in the same closed form, candidates in
+//                    registers).
+//   rs_traj_kernel   GenTraj + pathInCollision: one shot per warp step, one lane per pose, the poses never leave registers
+//                    (rs_gen_traj_regs).
+// History: one kernel, one shot per warp, the 48 candidates as per-thread segment arrays in local memory and the trajectory in
+// a per-warp HBM scratch: 4 700 warp-instructions per shot with eight divergent formula bodies on four lanes each, 3.4 GB of
+// DRAM traffic per 2^20 shots against 0.45 GB algorithmic, 85 M shots/s. Eight shots per warp with everything in registers:
+// 2 440 warp-instructions, 0.29 GB, 232 M shots/s, but still instruction-fetch bound (sm__icc hit rate 67 %,
+// stall_no_instruction 8.5 per issue): solve and trajectory code together do not fit the instruction cache while the 32
+// resident warps of an SM are spread over both. Two kernels keep each SM inside one half of the code at a time.
+struct RsWordRec
+{
+    double t, u, v;
+    int f, j, n, pad;
+};
 #ifndef MPROS_RS_MINB
-#define MPROS_RS_MINB 8 // 64 registers: 32 resident warps per SM (38 -> 48 M shots/s on the first version)
+#define MPROS_RS_MINB 8 // 64 registers: 32 resident warps per SM
 #endif
-__global__ void __launch_bounds__(128, MPROS_RS_MINB) rs_batch_kernel(const __grid_constant__ MapView m, const __grid_constant__ PlannerView p,
-                                                                       const __grid_constant__ RsBatchArgs a)
+__global__ void __launch_bounds__(128, MPROS_RS_MINB) rs_solve_kernel(const __grid_constant__ RsBatchArgs a, RsWordRec *__restrict__ words)
 {
     const int lane = threadIdx.x & 31, quad = lane >> 2, j = lane & 3;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    double *scratch = reinterpret_cast<double *>(a.ws) + (size_t)warp_global * kTrajCap * 5;
     const int ngroups = (a.n + 7) >> 3;
     for (int g = warp_global; g < ngroups; g += nwarps)
     {
         const int q = 8 * g + quad;
         const bool live = q < a.n;
         const double *s5 = a.starts5 + 5 * (size_t)(live ? q : a.n - 1), *g3 = a.goals3 + 3 * (size_t)(live ? q : a.n - 1);
-        const double sx = s5[0], sy = s5[1], syaw = s5[2];
         double cost;
-        const RsWord best = rs_find_optimal_quad(a.rs, sx, sy, syaw, (int)s5[3], s5[4], g3[0], g3[1], g3[2], cost);
+        const RsWord best = rs_find_optimal_quad(a.rs, s5[0], s5[1], s5[2], (int)s5[3], s5[4], g3[0], g3[1], g3[2], cost);
         if (live)
         {
             if (j == 0)
             {
                 a.cost[q] = cost;
                 a.nseg[q] = best.n;
+                RsWordRec r;
+                r.t = best.t, r.u = best.u, r.v = best.v, r.f = best.f, r.j = best.j, r.n = best.n, r.pad = 0;
+                words[q] = r;
             }
             for (int k = j; k < 5; k += 4) // lane j of the quad stores segments j and j + 4
             {
@@ -269,59 +281,81 @@ __global__ void __launch_bounds__(128, MPROS_RS_MINB) rs_batch_kernel(const __gr
                 o[0] = len, o[1] = (double)steer, o[2] = (double)dir;
             }
         }
-        const int nshots = min(8, a.n - 8 * g);
-        for (int s = 0; s < nshots; ++s)
+    }
+}
+
+__global__ void __launch_bounds__(128, MPROS_RS_MINB) rs_traj_kernel(const __grid_constant__ MapView m, const __grid_constant__ PlannerView p,
+                                                                      const __grid_constant__ RsBatchArgs a, const RsWordRec *__restrict__ words)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    double *scratch = reinterpret_cast<double *>(a.ws) + (size_t)warp_global * kTrajCap * 5;
+    for (int q = warp_global; q < a.n; q += nwarps)
+    {
+        const RsWordRec r = words[q]; // the same address on every lane: one broadcast transaction
+        RsWord w;
+        w.t = r.t, w.u = r.u, w.v = r.v, w.f = r.f, w.j = r.j, w.n = r.n;
+        const double *s5 = a.starts5 + 5 * (size_t)q;
+        const double x0 = s5[0], y0 = s5[1], yaw0 = s5[2];
+        double px, py, pyaw;
+        int pst, pdr;
+        int np = rs_gen_traj_regs(a.rs, x0, y0, yaw0, w, px, py, pyaw, pst, pdr);
+        bool hit = false;
+        if (np > 32)
+            hit = rs_shot_long(m, p, a, w, x0, y0, yaw0, q, scratch, np);
+        else
         {
-            const int src = 4 * s, qs = 8 * g + s;
-            RsWord w;
-            w.t = __shfl_sync(kFull, best.t, src), w.u = __shfl_sync(kFull, best.u, src), w.v = __shfl_sync(kFull, best.v, src);
-            w.f = __shfl_sync(kFull, best.f, src), w.j = __shfl_sync(kFull, best.j, src), w.n = __shfl_sync(kFull, best.n, src);
-            const double x0 = __shfl_sync(kFull, sx, src), y0 = __shfl_sync(kFull, sy, src), yaw0 = __shfl_sync(kFull, syaw, src);
-            double px, py, pyaw;
-            int pst, pdr;
-            int np = rs_gen_traj_regs(a.rs, x0, y0, yaw0, w, px, py, pyaw, pst, pdr);
-            bool hit = false;
-            if (np > 32)
-                hit = rs_shot_long(m, p, a, w, x0, y0, yaw0, qs, scratch, np);
-            else
+            const bool pose = lane < np;
+            if (a.traj && pose && lane < a.traj_cap)
             {
-                const bool pose = lane < np;
-                if (a.traj && pose && lane < a.traj_cap)
+                double *o = a.traj + ((size_t)q * a.traj_cap + lane) * 5;
+                o[0] = px, o[1] = py, o[2] = pyaw, o[3] = (double)pst * a.rs.steer_angle, o[4] = (double)pdr;
+            }
+            if (a.verdicts)
+            {
+                // pathInCollision is an OR over the poses: every lane decides its pose by the pose's own cell where that is
+                // possible (map_device.cuh: footprint_preclass); the undecided poses get their sin/cos in parallel and the
+                // warp-wide probe walk one after the other
+                const int cls = pose ? footprint_preclass(m, p, a.unsafe_tw, a.center_probe, px, py, pyaw) : 0;
+                hit = __any_sync(kFull, cls == 1);
+                unsigned walk = hit ? 0u : __ballot_sync(kFull, cls == 2);
+                if (walk)
                 {
-                    double *o = a.traj + ((size_t)qs * a.traj_cap + lane) * 5;
-                    o[0] = px, o[1] = py, o[2] = pyaw, o[3] = (double)pst * a.rs.steer_angle, o[4] = (double)pdr;
-                }
-                if (a.verdicts)
-                {
-                    // pathInCollision is an OR over the poses: every lane decides its pose by the pose's own cell where that is
-                    // possible (map_device.cuh: footprint_preclass); the undecided poses get their sin/cos in parallel and the
-                    // warp-wide probe walk one after the other
-                    const int cls = pose ? footprint_preclass(m, p, a.unsafe_tw, a.center_probe, px, py, pyaw) : 0;
-                    hit = __any_sync(kFull, cls == 1);
-                    unsigned walk = hit ? 0u : __ballot_sync(kFull, cls == 2);
-                    if (walk)
+                    double sn = 0, cs = 1;
+                    if (cls == 2)
+                        dm::sincos_(pyaw, &sn, &cs);
+                    while (walk && !hit)
                     {
-                        double sn = 0, cs = 1;
-                        if (cls == 2)
-                            dm::sincos_(pyaw, &sn, &cs);
-                        while (walk && !hit)
-                        {
-                            const int t = __ffs(walk) - 1;
-                            walk &= walk - 1;
-                            hit = warp_footprint_collision(m, p, __shfl_sync(kFull, px, t), __shfl_sync(kFull, py, t), __shfl_sync(kFull, sn, t),
-                                                           __shfl_sync(kFull, cs, t));
-                        }
+                        const int t = __ffs(walk) - 1;
+                        walk &= walk - 1;
+                        hit = warp_footprint_collision(m, p, __shfl_sync(kFull, px, t), __shfl_sync(kFull, py, t), __shfl_sync(kFull, sn, t),
+                                                       __shfl_sync(kFull, cs, t));
                     }
                 }
             }
-            if (lane == 0)
-            {
-                a.npts[qs] = np;
-                if (a.verdicts)
-                    a.verdicts[qs] = hit ? 1 : 0;
-            }
+        }
+        if (lane == 0)
+        {
+            a.npts[q] = np;
+            if (a.verdicts)
+                a.verdicts[q] = hit ? 1 : 0;
         }
     }
+}
+
+// both kernels of a shot batch on `st`; d_words: n records of scratch
+static int rs_launch(mpros_ctx *c, const RsBatchArgs &a, RsWordRec *d_words, cudaStream_t st)
+{
+    const int wpb = 4;
+    const size_t cap = (size_t)c->n_sm * MPROS_RS_MINB;
+    const int b_solve = (int)std::min<size_t>((((size_t)a.n + 7) / 8 + wpb - 1) / wpb, cap);
+    const int b_traj = (int)std::min<size_t>(((size_t)a.n + wpb - 1) / wpb, cap);
+    rs_solve_kernel<<<b_solve, 128, 0, st>>>(a, d_words);
+    MPROS_LAUNCH_CHECK(c);
+    rs_traj_kernel<<<b_traj, 128, 0, st>>>(c->view(), c->pv, a, d_words);
+    MPROS_LAUNCH_CHECK(c);
+    return MPROS_OK;
 }
 
 // OMPL-equivalent RS distance for n pose pairs (R5): one quad of lanes per pair
@@ -602,13 +636,11 @@ static int rs_batch_impl(mpros_ctx *c, const mpros_rs_params *rp, const double *
     }
     else
         a.rs = rs_config_from_planner(c);
-    const int block = 128, warps_per_block = block / 32;
-    // a warp takes eight shots at a time; MPROS_RS_MINB CTAs are resident per SM
-    int blocks = (int)std::min<size_t>(((n + 7) / 8 + warps_per_block - 1) / warps_per_block, (size_t)c->n_sm * MPROS_RS_MINB);
-    size_t nwarps = (size_t)blocks * warps_per_block;
+    // per-warp scratch of the (rare) trajectories longer than 32 poses; MPROS_RS_MINB CTAs of 4 warps are resident per SM
+    size_t nwarps = (size_t)c->n_sm * MPROS_RS_MINB * 4;
     size_t in_bytes = n * 8 * 8, seg_bytes = n * 15 * 8, traj_bytes = n * (size_t)traj_cap * 5 * 8;
-    size_t ws_bytes = nwarps * kTrajCap * 5 * 8;
-    size_t total = in_bytes + seg_bytes + n * 4 + n * 8 + traj_bytes + n * 4 + n + ws_bytes + 1024;
+    size_t ws_bytes = nwarps * kTrajCap * 5 * 8, word_bytes = n * sizeof(RsWordRec);
+    size_t total = in_bytes + seg_bytes + n * 4 + n * 8 + traj_bytes + n * 4 + n + ws_bytes + word_bytes + 4096;
     int rc = ensure_stage(c, total);
     if (rc)
         return rc;
@@ -626,6 +658,7 @@ static int rs_batch_impl(mpros_ctx *c, const mpros_rs_params *rp, const double *
     int32_t *d_npts = (int32_t *)take(n * 4);
     uint8_t *d_ver = (uint8_t *)take(n);
     char *d_ws = take(ws_bytes);
+    RsWordRec *d_words = (RsWordRec *)take(word_bytes);
     if (o > c->stage_bytes)
     {
         rc = ensure_stage(c, o + 1024);
@@ -654,8 +687,9 @@ static int rs_batch_impl(mpros_ctx *c, const mpros_rs_params *rp, const double *
         a.unsafe_tw = c->unsafe_tw;
         a.center_probe = c->unsafe_center_probe;
     }
-    rs_batch_kernel<<<blocks, block, 0, st>>>(c->view(), c->pv, a);
-    MPROS_LAUNCH_CHECK(c);
+    rc = rs_launch(c, a, d_words, st);
+    if (rc)
+        return rc;
     MPROS_CUDA(cudaMemcpyAsync(segs, d_seg, seg_bytes, cudaMemcpyDeviceToHost, st));
     MPROS_CUDA(cudaMemcpyAsync(nseg, d_nseg, n * 4, cudaMemcpyDeviceToHost, st));
     MPROS_CUDA(cudaMemcpyAsync(cost, d_cost, n * 8, cudaMemcpyDeviceToHost, st));
@@ -703,14 +737,11 @@ extern "C" int mpros_rs_shot_batch_dev(mpros_ctx *c, const double *d_starts5, co
     MPROS_CUDA(cudaSetDevice(c->device));
     RsBatchArgs a;
     a.rs = rs_config_from_planner(c);
-    const int block = 128, warps_per_block = block / 32;
-    // a warp takes eight shots at a time; MPROS_RS_MINB CTAs are resident per SM
-    int blocks = (int)std::min<size_t>(((n + 7) / 8 + warps_per_block - 1) / warps_per_block, (size_t)c->n_sm * MPROS_RS_MINB);
-    const size_t ws_bytes = (size_t)blocks * warps_per_block * kTrajCap * 5 * 8;
+    const size_t ws_bytes = ((size_t)c->n_sm * MPROS_RS_MINB * 4 * kTrajCap * 5 * 8 + 255) & ~(size_t)255, word_bytes = n * sizeof(RsWordRec);
     rc = map_build_unsafe(c); // before the scratch is handed out: the builder uses it for its temporaries
     if (rc)
         return rc;
-    rc = ensure_scratch(c, ws_bytes + 256);
+    rc = ensure_scratch(c, ws_bytes + word_bytes + 256);
     if (rc)
         return rc;
     a.starts5 = d_starts5;
@@ -726,9 +757,7 @@ extern "C" int mpros_rs_shot_batch_dev(mpros_ctx *c, const double *d_starts5, co
     a.unsafe_tw = c->unsafe_tw;
     a.center_probe = c->unsafe_center_probe;
     a.ws = static_cast<char *>(c->scratch);
-    rs_batch_kernel<<<blocks, block, 0, c->stream>>>(c->view(), c->pv, a);
-    MPROS_LAUNCH_CHECK(c);
-    return MPROS_OK;
+    return rs_launch(c, a, reinterpret_cast<RsWordRec *>(static_cast<char *>(c->scratch) + ws_bytes), c->stream);
 }
 
 extern "C" int mpros_rs_distance_batch(mpros_ctx *c, double rho, const double *a3, const double *b3, size_t n, double *out)

@@ -149,8 +149,10 @@ def test_sharded_plans_equal_the_single_context_plans():
         r0, n = c.band_of(comms[r], H)
         c.set_occupancy_banded(comms[r], m["occupancy"][r0:r0 + n], W, H, res, m["origin"])
         c.planner_config(params)
-        out = c.plan_batch_sharded(comms[r], starts, goals, path_cap=512, gather_paths=(r != 1))
+        out = c.plan_batch_sharded(comms[r], starts, goals, path_cap=512, gather_paths=True)  # collective: same arguments on all ranks
+        own = c.plan_batch_sharded(comms[r], starts, goals, path_cap=512, gather_paths=False)
         c.close()
+        out["own"] = own
         return out
 
     outs = mpros_b200.run_local_ranks(world, rank_fn)
@@ -161,5 +163,8 @@ def test_sharded_plans_equal_the_single_context_plans():
         for k in ["status", "cost", "path_len", "iterations", "primitives"]:
             assert np.array_equal(want[k], got[k]), "rank %d: %s differs" % (r, k)
         lo, hi = got["owned"]
-        assert np.array_equal(want["paths"][lo:hi], got["paths"][lo:hi])
+        assert np.array_equal(want["paths"], got["paths"]), "rank %d: gathered paths differ" % r
+        own = got["own"]
+        assert np.array_equal(want["paths"][lo:hi], own["paths"][lo:hi]) and np.array_equal(want["cost"], own["cost"])
+        assert not own["paths"][:lo].any() and not own["paths"][hi:].any()  # without the gather only the own block is written
     assert [o["owned"] for o in outs] == [(0, 4), (4, 7), (7, 10)]
