@@ -95,6 +95,7 @@ struct LocalGroup
     int world = 0, waiting = 0, refs = 0;
     uint64_t generation = 0;
     void *ptr[64] = {};
+    int share_dev = 0; // device of rank 0's block (mpros_plan_share_create)
     bool broken = false; // a rank gave up waiting: every later barrier fails at once instead of hanging
     // false when a peer rank did not arrive within two minutes (it failed before reaching the same call)
     bool barrier()
@@ -438,6 +439,186 @@ extern "C" int mpros_plan_batch_sharded(mpros_ctx *c, mpros_comm *cm, const doub
             MPROS_CUDA(cudaMemcpyAsync(paths + lo * (size_t)path_cap * 5, d_paths + lo * (size_t)path_cap * 5, n_loc * (size_t)path_cap * 40,
                                        cudaMemcpyDeviceToHost, st));
     }
+    MPROS_CUDA(cudaStreamSynchronize(st));
+    return MPROS_OK;
+}
+
+// ---- dynamic sharding over peer memory -------------------------------------------------------------------------------------
+// mpros_plan_batch_sharded gives every rank a fixed block of the queries; a rank whose block holds more of the long searches
+// (a query that runs into the iteration limit is ~50 times the mean) finishes last while the others idle. Here ALL ranks
+// draw query tickets from ONE counter in rank 0's memory (system-scope atomicAdd through the NVLink mapping) and store each
+// query's results - status, cost, path length, statistics and the path itself - straight into rank 0's result arrays with
+// ordinary stores: the planner kernel does the load balancing and the result gather itself, no collective moves data. Two
+// stream-ordered barriers (a 4-byte exchange each) fence the launch: counter cleared before anybody draws, every kernel
+// finished before anybody reads.
+struct mpros_plan_share
+{
+    mpros_comm *cm = nullptr;
+    void *home = nullptr;      // rank 0's block as this rank addresses it
+    bool opened_ipc = false;   // other process: cudaIpcOpenMemHandle; same process / rank 0: the pointer itself
+    size_t max_queries = 0;
+    int path_cap = 0;
+    size_t off_status = 0, off_cost = 0, off_len = 0, off_stats = 0, off_paths = 0, bytes = 0;
+    void *d_queries = nullptr; // this rank's copy of all starts / goals
+    void *d_sync = nullptr;    // world x 4 bytes for the barriers
+};
+
+static int comm_barrier(mpros_ctx *c, mpros_comm *cm, void *d_sync) { return comm_allgather(c, cm, d_sync, 4); }
+
+extern "C" int mpros_plan_share_create(mpros_ctx *c, mpros_comm *cm, size_t max_queries, int path_cap, mpros_plan_share **out)
+{
+    if (!c || !cm || !out || max_queries == 0 || max_queries > ((size_t)1 << 28) || path_cap < 0)
+    {
+        set_error("mpros_plan_share_create: invalid argument");
+        return MPROS_ERR_INVALID;
+    }
+    MPROS_CUDA(cudaSetDevice(c->device));
+    mpros_plan_share *sh = new mpros_plan_share;
+    sh->cm = cm;
+    sh->max_queries = max_queries;
+    sh->path_cap = path_cap;
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    size_t o = 256; // [0, 256): the ticket counter
+    sh->off_status = o, o += up(max_queries * 4);
+    sh->off_cost = o, o += up(max_queries * 8);
+    sh->off_len = o, o += up(max_queries * 4);
+    sh->off_stats = o, o += up(max_queries * 48);
+    sh->off_paths = o, o += up(max_queries * (size_t)path_cap * 40);
+    sh->bytes = o;
+    MPROS_CUDA(cudaMalloc(&sh->d_queries, max_queries * 48));
+    MPROS_CUDA(cudaMalloc(&sh->d_sync, (size_t)cm->world * 4 + 64));
+    MPROS_CUDA(cudaMemsetAsync(sh->d_sync, 0, (size_t)cm->world * 4 + 64, c->stream));
+    // rank 0 owns the block; the others map it
+    void *mine = nullptr;
+    if (cm->rank == 0)
+    {
+        MPROS_CUDA(cudaMalloc(&mine, sh->bytes));
+        MPROS_CUDA(cudaMemsetAsync(mine, 0, sh->bytes, c->stream));
+    }
+    if (cm->kind == 1)
+    {
+        // ranks of one process: the pointer itself (peer access between different devices is enabled on demand)
+        LocalGroup *g = cm->grp;
+        MPROS_CUDA(cudaStreamSynchronize(c->stream));
+        if (cm->rank == 0)
+        {
+            g->ptr[0] = mine;
+            g->share_dev = c->device;
+        }
+        int rc = local_barrier(g);
+        if (rc)
+            return rc;
+        sh->home = g->ptr[0];
+        if (cm->rank != 0 && g->share_dev != c->device)
+        {
+            cudaError_t e = cudaDeviceEnablePeerAccess(g->share_dev, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+            cudaGetLastError();
+        }
+        rc = local_barrier(g);
+        if (rc)
+            return rc;
+    }
+    else
+    {
+        // ranks in different processes: the CUDA IPC handle of the block travels through the communicator
+        cudaIpcMemHandle_t h;
+        std::memset(&h, 0, sizeof(h));
+        if (cm->rank == 0)
+            MPROS_CUDA(cudaIpcGetMemHandle(&h, mine));
+        void *d_h = nullptr;
+        MPROS_CUDA(cudaMalloc(&d_h, sizeof(h)));
+        MPROS_CUDA(cudaMemcpyAsync(d_h, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+        size_t off[64] = {}, cnt[64] = {};
+        cnt[0] = sizeof(h); // a broadcast from rank 0
+        int rc = comm_allgatherv(c, cm, d_h, off, cnt);
+        if (rc)
+            return rc;
+        MPROS_CUDA(cudaMemcpyAsync(&h, d_h, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        MPROS_CUDA(cudaStreamSynchronize(c->stream));
+        MPROS_CUDA(cudaFree(d_h));
+        if (cm->rank == 0)
+            sh->home = mine;
+        else
+        {
+            MPROS_CUDA(cudaIpcOpenMemHandle(&sh->home, h, cudaIpcMemLazyEnablePeerAccess));
+            sh->opened_ipc = true;
+        }
+    }
+    *out = sh;
+    return MPROS_OK;
+}
+
+extern "C" int mpros_plan_share_destroy(mpros_ctx *c, mpros_plan_share *sh)
+{
+    if (!sh)
+        return MPROS_OK;
+    if (c)
+    {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        // nobody unmaps or frees while a peer may still be storing: one more barrier
+        comm_barrier(c, sh->cm, sh->d_sync);
+        cudaStreamSynchronize(c->stream);
+    }
+    if (sh->opened_ipc)
+        cudaIpcCloseMemHandle(sh->home);
+    else if (sh->cm->rank == 0 && sh->home)
+        cudaFree(sh->home);
+    if (sh->d_queries)
+        cudaFree(sh->d_queries);
+    if (sh->d_sync)
+        cudaFree(sh->d_sync);
+    delete sh;
+    return MPROS_OK;
+}
+
+extern "C" int mpros_plan_batch_shared(mpros_ctx *c, mpros_plan_share *sh, const double *starts3, const double *goals3, size_t nq,
+                                       int32_t *status, double *cost, int32_t *path_len, double *paths, int path_cap, int64_t *stats)
+{
+    if (!c || !sh || !starts3 || !goals3 || nq == 0 || nq > sh->max_queries || path_cap != sh->path_cap)
+    {
+        set_error("mpros_plan_batch_shared: invalid argument (nq <= max_queries and the path_cap of mpros_plan_share_create)");
+        return MPROS_ERR_INVALID;
+    }
+    MPROS_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    mpros_comm *cm = sh->cm;
+    char *home = static_cast<char *>(sh->home);
+    double *d_s = static_cast<double *>(sh->d_queries), *d_g = d_s + 3 * sh->max_queries;
+    MPROS_CUDA(cudaMemcpyAsync(d_s, starts3, nq * 24, cudaMemcpyHostToDevice, st));
+    MPROS_CUDA(cudaMemcpyAsync(d_g, goals3, nq * 24, cudaMemcpyHostToDevice, st));
+    if (cm->rank == 0)
+        MPROS_CUDA(cudaMemsetAsync(home, 0, 256, st)); // the ticket counter
+    int rc = comm_barrier(c, cm, sh->d_sync); // the counter is clear before anybody draws
+    if (rc)
+        return rc;
+    rc = plan_batch_shared_launch(c, d_s, d_g, (int)nq, reinterpret_cast<unsigned int *>(home), reinterpret_cast<int32_t *>(home + sh->off_status),
+                                  reinterpret_cast<double *>(home + sh->off_cost), reinterpret_cast<int32_t *>(home + sh->off_len),
+                                  path_cap ? reinterpret_cast<double *>(home + sh->off_paths) : nullptr, path_cap,
+                                  reinterpret_cast<int64_t *>(home + sh->off_stats));
+    if (rc)
+        return rc;
+    rc = comm_barrier(c, cm, sh->d_sync); // every rank's kernel has finished: rank 0's arrays are complete
+    if (rc)
+        return rc;
+    // any rank that passed result arrays reads them (rank 0 from its own memory, the others through the mapping)
+    if (status)
+        MPROS_CUDA(cudaMemcpyAsync(status, home + sh->off_status, nq * 4, cudaMemcpyDeviceToHost, st));
+    if (cost)
+        MPROS_CUDA(cudaMemcpyAsync(cost, home + sh->off_cost, nq * 8, cudaMemcpyDeviceToHost, st));
+    if (path_len)
+        MPROS_CUDA(cudaMemcpyAsync(path_len, home + sh->off_len, nq * 4, cudaMemcpyDeviceToHost, st));
+    if (stats)
+        MPROS_CUDA(cudaMemcpyAsync(stats, home + sh->off_stats, nq * 48, cudaMemcpyDeviceToHost, st));
+    if (paths && path_cap)
+        MPROS_CUDA(cudaMemcpyAsync(paths, home + sh->off_paths, nq * (size_t)path_cap * 40, cudaMemcpyDeviceToHost, st));
+    MPROS_CUDA(cudaStreamSynchronize(st));
+    // the next call clears the counter only after everybody has read
+    rc = comm_barrier(c, cm, sh->d_sync);
+    if (rc)
+        return rc;
     MPROS_CUDA(cudaStreamSynchronize(st));
     return MPROS_OK;
 }

@@ -35,4 +35,7 @@ inline void band_of(int total_rows, int rows_per_rank, int rank, int *lo, int *h
     *hi = (int)(b < total_rows ? b : total_rows);
 }
 int map_build_voronoi_banded(Ctx *c, mpros_comm *cm, int rows_per_rank); // N5-N9 on row bands, voronoi.cu
+// one planner launch drawing tickets from `counter` and storing into the given result arrays, any of which may be peer memory (plan.cu)
+int plan_batch_shared_launch(mpros_ctx *c, const double *d_starts, const double *d_goals, int nq, unsigned int *counter, int32_t *status,
+                             double *cost, int32_t *path_len, double *paths, int path_cap, int64_t *stats);
 } // namespace mpros

@@ -74,6 +74,8 @@ struct PlanBatchArgs
     const int32_t *todo; // indices of the queries to run in this pass (null = all)
     int n_todo;
     unsigned int *counter;
+    int shared_counter; // the ticket counter (and the result arrays) live in ANOTHER GPU's memory, mapped over NVLink: tickets
+                        // are drawn with system-scope atomics (mpros_plan_batch_shared, dist.cu)
     WorkspacePool pool; // a team takes one workspace for the lifetime of its CTA (plan_team.cuh)
     WarpWorkspaceLayout L;
     RsConfig rs;
@@ -1058,16 +1060,19 @@ static int plan_pass(mpros_ctx *c, int lane, cudaStream_t stream, PlanBatchArgs 
     if (duo)
         teams = (teams + 1) & ~1;
     const bool layout_change = std::memcmp(PL.last_layout, &L, sizeof(L)) != 0;
-    if (layout_change || PL.n < teams)
+    // ... but never more than the batches seen so far could use: a context that only ever plans single queries (the node's
+    // own use) keeps one ~110 MB workspace, not 33 GB. A caller that pipelines on the extra lanes gets room for two batches.
+    const int wanted = (int)std::min<long long>(teams, std::max<long long>(layout_change ? 0 : PL.n, (long long)n_run * (lane == 0 ? 1 : 2)));
+    if (layout_change || PL.n < wanted)
     {
         // a different layout re-interprets the same bytes (stale tags could alias), a bigger pool moves it: nothing may be
         // in flight on any lane, and the pool starts out cleared
         size_t free_b = 0, total_b = 0;
         MPROS_CUDA(cudaMemGetInfo(&free_b, &total_b));
         const size_t budget = (free_b + PL.bytes) / 2;
-        int n = (int)std::min<long long>(teams, std::max<long long>(1, (long long)(budget / L.stride)));
+        int n = (int)std::min<long long>(wanted, std::max<long long>(1, (long long)(budget / L.stride)));
         if (duo)
-            n = std::max(2, n & ~1);
+            n = std::max(2, (n + 1) & ~1);
         if (layout_change || n > PL.n)
         {
             int rc = plan_quiesce(c);
@@ -1124,13 +1129,16 @@ static int plan_pass(mpros_ctx *c, int lane, cudaStream_t stream, PlanBatchArgs 
         blocks = (blocks + 1) & ~1; // a CTA always owns two workspaces
     if (!S.counter)
         MPROS_CUDA(cudaMalloc(&S.counter, 256));
-    MPROS_CUDA(cudaMemsetAsync(S.counter, 0, 4, stream));
+    if (!a.shared_counter)
+    {
+        MPROS_CUDA(cudaMemsetAsync(S.counter, 0, 4, stream));
+        a.counter = S.counter;
+    }
     a.L = L;
     a.pool.base = PL.base;
     a.pool.owner = PL.owner;
     a.pool.gen = PL.gen;
     a.pool.n = PL.n;
-    a.counter = S.counter;
     a.todo = d_todo;
     a.n_todo = n_run;
     const bool dbg = c->opt.debug;
@@ -1209,9 +1217,10 @@ static int plan_batch_dev_impl(mpros_ctx *c, int lane, cudaStream_t stream, cons
     long long caps[3] = {16384, 131072, max_nodes};
     {
         WarpWorkspaceLayout big = make_layout((int)max_nodes, c->H, c->W);
-        const size_t full = big.stride * (size_t)(kTeamMinBlocks * c->n_sm);
+        const size_t n_ws = std::min<size_t>((size_t)kTeamMinBlocks * c->n_sm, (size_t)nq * (lane == 0 ? 1 : 2)); // what plan_pass will ask for
+        const size_t full = big.stride * n_ws;
         if (c->plan_pool[0].bytes >= full && std::memcmp(c->plan_pool[0].last_layout, &big, sizeof(big)) == 0)
-            caps[0] = max_nodes; // the context already owns a full-size pool
+            caps[0] = max_nodes; // the context already owns full-size workspaces for this batch
         else
         {
             size_t free_b = 0, total_b = 0;
@@ -1258,6 +1267,35 @@ static int plan_batch_dev_impl(mpros_ctx *c, int lane, cudaStream_t stream, cons
     }
     return MPROS_OK;
 }
+
+// One launch of the planner whose ticket counter and result arrays are given by the caller and may live in a peer GPU's
+// memory (dist.cu: mpros_plan_batch_shared). Always with full-size node pools: a query that overflowed a small pool could
+// not be re-run by the rank that happened to draw it without another exchange.
+namespace mpros
+{
+int plan_batch_shared_launch(mpros_ctx *c, const double *d_starts, const double *d_goals, int nq, unsigned int *counter, int32_t *status,
+                             double *cost, int32_t *path_len, double *paths, int path_cap, int64_t *stats)
+{
+    PlanBatchArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.starts = d_starts;
+    a.goals = d_goals;
+    a.nq = nq;
+    a.status = status;
+    a.cost = cost;
+    a.path_len = path_len;
+    a.paths = paths;
+    a.path_cap = path_cap;
+    a.stats = stats;
+    a.rs = rs_config_from_planner(c);
+    a.optimal = c->pp.optimal_path;
+    a.counter = counter;
+    a.shared_counter = 1;
+    const long long max_nodes = (long long)(c->pp.max_iteration + 2) * (2 * c->pv.n_steer) + 16;
+    // pass 0 with pools for the iteration limit (as many as fit into half of the free memory): every query runs exactly once
+    return plan_pass(c, 0, c->stream, a, 0, (int)max_nodes, nq, nullptr, 0);
+}
+} // namespace mpros
 
 namespace mpros
 {

@@ -1635,7 +1635,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) plan_team_kernel(const __grid_c
     {
         team_sync_all<NW>();
         if (team_tid<NW>() == 0)
-            S.q = (int)atomicAdd(a.counter, 1u);
+            S.q = (int)(a.shared_counter ? atomicAdd_system(a.counter, 1u) : atomicAdd(a.counter, 1u));
         team_sync_all<NW>();
         const int t = S.q;
         if (t >= total)
@@ -1679,7 +1679,7 @@ __global__ void __launch_bounds__(NW * 64, 1) plan_duo_kernel(const __grid_const
     {
         team_sync_all<NW>();
         if (team_tid<NW>() == 0)
-            S.q = (int)atomicAdd(a.counter, 1u);
+            S.q = (int)(a.shared_counter ? atomicAdd_system(a.counter, 1u) : atomicAdd(a.counter, 1u));
         team_sync_all<NW>();
         const int t = S.q;
         if (t >= total)
@@ -1733,7 +1733,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NW * 32, MINB)
     {
         team_sync_all<NW>();
         if (team_tid<NW>() == 0)
-            S.q = (int)atomicAdd(a.counter, 1u);
+            S.q = (int)(a.shared_counter ? atomicAdd_system(a.counter, 1u) : atomicAdd(a.counter, 1u));
         team_sync_all<NW>();
         const int t = S.q;
         if (t >= total)

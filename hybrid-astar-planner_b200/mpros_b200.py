@@ -175,6 +175,9 @@ def load_library(path=LIB_PATH):
     L.mpros_map_set_occupancy_banded_dev.argtypes = [vp, vp, vp, i, i, d, d, d, d]
     L.mpros_plan_shard_range.argtypes = [vp, sz, C.POINTER(sz), C.POINTER(sz)]
     L.mpros_plan_batch_sharded.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp, vp, i, vp, i]
+    L.mpros_plan_share_create.argtypes = [vp, vp, sz, i, C.POINTER(vp)]
+    L.mpros_plan_share_destroy.argtypes = [vp, vp]
+    L.mpros_plan_batch_shared.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp, vp, i, vp]
     _lib = L
     return L
 
@@ -583,6 +586,32 @@ class Context:
         self.L.mpros_plan_shard_range(comm.h if comm else None, nq, C.byref(lo), C.byref(hi))
         return {"status": status, "cost": cost, "path_len": plen, "paths": paths, "iterations": stats[:, 0], "primitives": stats[:, 1],
                 "owned": (lo.value, hi.value)}
+
+    def plan_share_create(self, comm, max_queries, path_cap):
+        """mpros_plan_share_create (collective): rank 0's ticket counter and result arrays, mapped by every rank."""
+        h = C.c_void_p()
+        self._check(self.L.mpros_plan_share_create(self.h, comm.h, max_queries, path_cap, C.byref(h)))
+        return h
+
+    def plan_share_destroy(self, share):
+        self._check(self.L.mpros_plan_share_destroy(self.h, share))
+
+    def plan_batch_shared(self, share, starts3, goals3, path_cap, want_results=True):
+        """mpros_plan_batch_shared (collective): all ranks draw tickets from rank 0's counter and store into rank 0's arrays."""
+        s = np.ascontiguousarray(starts3, dtype=np.float64).reshape(-1, 3)
+        g = np.ascontiguousarray(goals3, dtype=np.float64).reshape(-1, 3)
+        nq = len(s)
+        if not want_results:
+            self._check(self.L.mpros_plan_batch_shared(self.h, share, s.ctypes.data, g.ctypes.data, nq, None, None, None, None, path_cap, None))
+            return None
+        status = np.zeros(nq, dtype=np.int32)
+        cost = np.zeros(nq)
+        plen = np.zeros(nq, dtype=np.int32)
+        paths = np.zeros((nq, path_cap, 5))
+        stats = np.zeros((nq, 6), dtype=np.int64)
+        self._check(self.L.mpros_plan_batch_shared(self.h, share, s.ctypes.data, g.ctypes.data, nq, status.ctypes.data, cost.ctypes.data,
+                                                   plen.ctypes.data, paths.ctypes.data if path_cap else None, path_cap, stats.ctypes.data))
+        return {"status": status, "cost": cost, "path_len": plen, "paths": paths, "iterations": stats[:, 0], "primitives": stats[:, 1]}
 
     def plan_batch_dev(self, d_starts, d_goals, nq, d_status, d_cost, d_len, d_paths, path_cap, d_stats):
         self._check(self.L.mpros_plan_batch_dev(self.h, d_starts, d_goals, nq, d_status, d_cost, d_len, d_paths, path_cap, d_stats))

@@ -382,6 +382,21 @@ MPROS_API int mpros_plan_batch_sharded(mpros_ctx *ctx, mpros_comm *comm, const d
                                        int32_t *status, double *cost, int32_t *path_len, double *paths, int path_cap, int64_t *stats,
                                        int gather_paths);
 
+/* Dynamic sharding over peer memory: ALL ranks draw query tickets from ONE counter in rank 0's memory (system-scope atomics
+ * through the NVLink mapping: CUDA IPC between processes, the pointer itself between ranks of one process) and store every
+ * query's results - status, cost, path length, statistics, path - straight into rank 0's arrays. The planner kernel balances
+ * the load (a query that runs into the iteration limit costs ~50 mean queries; with fixed blocks the rank that holds more of
+ * them finishes last) and performs the result gather itself; the communicator only carries the IPC handle once and three
+ * 4-byte barriers per batch. mpros_plan_share_create is collective (rank 0 allocates the arrays for max_queries queries and
+ * path_cap points each); mpros_plan_batch_shared is collective: every rank passes the same starts3 / goals3; result pointers
+ * may be NULL on ranks that do not want them (non-NULL ones are filled from rank 0's arrays on any rank). Results per query
+ * are identical to mpros_plan_batch. */
+typedef struct mpros_plan_share mpros_plan_share;
+MPROS_API int mpros_plan_share_create(mpros_ctx *ctx, mpros_comm *comm, size_t max_queries, int path_cap, mpros_plan_share **out);
+MPROS_API int mpros_plan_share_destroy(mpros_ctx *ctx, mpros_plan_share *share);
+MPROS_API int mpros_plan_batch_shared(mpros_ctx *ctx, mpros_plan_share *share, const double *starts3, const double *goals3, size_t nq,
+                                      int32_t *status, double *cost, int32_t *path_len, double *paths, int path_cap, int64_t *stats);
+
 /* ---- path post-processing -------------------------------------------------------------------- */
 /* What HybridAstar::setPath does to the raw path_ before getNewPath() returns it (hybrid_a_star.cpp:814-838):
  * updatePathLength, setCusp, updateCurvatureNew (planner_utils.h:35-61, 251-309) and, when interpolation_enable is set,

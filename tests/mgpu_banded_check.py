@@ -110,6 +110,32 @@ def main():
             np.array_equal(ref["iterations"], got2["iterations"]) and np.array_equal(ref["paths"], got2["paths"])):
         bad += 1
         print("rank %d: mpros_plan_batch_sharded differs from the single-GPU plans" % rank, flush=True)
+    # dynamic sharding: tickets from rank 0's counter and results into rank 0's arrays over the NVLink mapping (CUDA IPC)
+    n_big = 4096
+    bs, bg = synthetic.synthetic_queries(n_big, single.collision_check, single.layer("static"), synthetic.SYN_RES * synthetic.SYN_DS,
+                                         size * synthetic.SYN_RES, synthetic.SYN_QUERY_SEED + 3)
+    ref_big = single.plan_batch(bs, bg, path_cap=128, truncate_ok=True)
+    share = cb.plan_share_create(comm, n_big, 128)
+    t_shared, t_static = [], []
+    for rep in range(3):
+        dist.barrier()
+        t0 = time.perf_counter()
+        got3 = cb.plan_batch_shared(share, bs, bg, 128)
+        t_shared.append(time.perf_counter() - t0)
+        dist.barrier()
+        t0 = time.perf_counter()
+        got4 = cb.plan_batch_sharded(comm, bs, bg, path_cap=128, gather_paths=True)
+        t_static.append(time.perf_counter() - t0)
+    for name, got_x in (("shared tickets", got3), ("fixed blocks", got4)):
+        if not (np.array_equal(ref_big["status"], got_x["status"]) and np.array_equal(ref_big["cost"], got_x["cost"]) and
+                np.array_equal(ref_big["iterations"], got_x["iterations"]) and np.array_equal(ref_big["paths"], got_x["paths"])):
+            bad += 1
+            print("rank %d: %s differ from the single-GPU plans" % (rank, name), flush=True)
+    cb.plan_share_destroy(share)
+    if rank == 0:
+        print("%d queries on %d GPUs, host buffers: shared tickets + peer stores %.1f ms, fixed blocks + gather %.1f ms (best of 3); "
+              "iterations per rank with fixed blocks %s" % (n_big, world, 1e3 * min(t_shared), 1e3 * min(t_static),
+              [int(ref_big["iterations"][a:b].sum()) for a, b in [sharding.shard_range(n_big, r, world) for r in range(world)]]), flush=True)
     ci = comm.info()
     if rank == 0:
         print("C ABI over NCCL: banded map %.1f ms (best of 3; single %.1f ms), ds=1 %dx%d banded %.1f ms vs single %.1f ms, "

@@ -168,3 +168,48 @@ def test_sharded_plans_equal_the_single_context_plans():
         assert np.array_equal(want["paths"][lo:hi], own["paths"][lo:hi]) and np.array_equal(want["cost"], own["cost"])
         assert not own["paths"][:lo].any() and not own["paths"][hi:].any()  # without the gather only the own block is written
     assert [o["owned"] for o in outs] == [(0, 4), (4, 7), (7, 10)]
+
+
+def test_shared_tickets_give_the_single_context_plans():
+    """mpros_plan_batch_shared over 3 local ranks: all ranks draw query tickets from rank 0's counter and store into rank 0's
+    arrays (peer memory between GPUs; here the ranks share one device); results per query equal mpros_plan_batch, two
+    batches in a row (the counter is cleared behind a barrier), every rank can read them."""
+    m = refapi.load_map("parking4")
+    params = refapi.shipped_params(m["free_thresh"], m["occupied_thresh"], num_steer=5)
+    res = float(np.float32(m["resolution"]))
+    rng = np.random.default_rng(9)
+    n = 40
+    starts = np.tile([-28.0, -1.5, 0.0], (n, 1)) + rng.uniform(-0.3, 0.3, (n, 3)) * [1, 1, 0.2]
+    goals = np.tile([10.0, -2.0, 1.57], (n, 1)) + rng.uniform(-0.3, 0.3, (n, 3)) * [1, 1, 0.1]
+    ctx = mpros_b200.Context(0)
+    ctx.map_config(params)
+    ctx.set_occupancy(m["occupancy"], res, m["origin"])
+    ctx.planner_config(params)
+    want = ctx.plan_batch(starts, goals, path_cap=512)
+    want2 = ctx.plan_batch(starts[::-1], goals[::-1], path_cap=512)
+    ctx.close()
+    world = 3
+    comms = mpros_b200.Comm.local(world)
+
+    def rank_fn(r):
+        c = mpros_b200.Context(0)
+        c.map_config(params)
+        c.set_occupancy(m["occupancy"], res, m["origin"])
+        c.planner_config(params)
+        sh = c.plan_share_create(comms[r], 64, 512)
+        a = c.plan_batch_shared(sh, starts, goals, 512)
+        b = c.plan_batch_shared(sh, starts[::-1], goals[::-1], 512, want_results=(r != 2))
+        c.plan_share_destroy(sh)
+        c.close()
+        return a, b
+
+    outs = mpros_b200.run_local_ranks(world, rank_fn)
+    for c in comms:
+        c.close()
+    assert (want["status"] == 1).sum() >= n // 2
+    for r, (a, b) in enumerate(outs):
+        for k in ["status", "cost", "path_len", "iterations", "primitives", "paths"]:
+            assert np.array_equal(want[k], a[k]), "rank %d: %s differs" % (r, k)
+            if b is not None:
+                assert np.array_equal(want2[k], b[k]), "rank %d, second batch: %s differs" % (r, k)
+    assert outs[2][1] is None
