@@ -57,10 +57,19 @@ static bool apply_option(Options &o, const char *key, const char *value)
     }
     else if (k == "plan_mode")
     {
-        if (v != "" && v != "team" && v != "cluster" && v != "duo")
+        if (v != "" && v != "team" && v != "cluster" && v != "duo" && v != "solo" && v != "solo_warp")
             return false;
         o.plan_cluster = v == "cluster";
         o.plan_duo = v == "duo";
+        o.plan_solo = v == "" || v == "solo" || v == "solo_warp";
+        o.plan_nosquad = v == "solo_warp";
+    }
+    else if (k == "solo_nodes")
+    {
+        const long n = v == "" ? 32768 : std::strtol(v.c_str(), nullptr, 10);
+        if (n < 64 || n > (1l << 24))
+            return false;
+        o.solo_nodes = (int)n;
     }
     else if (k == "debug")
         o.debug = !(v == "" || v == "0");
@@ -79,11 +88,23 @@ static void free_plan_scratch(Ctx *c)
                 cudaFree(S.counter);
             if (S.todo)
                 cudaFree(S.todo);
+            if (S.handoff)
+                cudaFree(S.handoff);
             S = PlanScratch();
         }
     for (int k = 0; k < kPlanPasses; ++k)
     {
         PlanPool &P = c->plan_pool[k];
+        if (P.base)
+            cudaFree(P.base);
+        if (P.owner)
+            cudaFree(P.owner);
+        if (P.gen)
+            cudaFree(P.gen);
+        P = PlanPool();
+    }
+    {
+        PlanPool &P = c->solo_pool;
         if (P.base)
             cudaFree(P.base);
         if (P.owner)
@@ -139,6 +160,7 @@ extern "C" int mpros_ctx_create(int device, mpros_ctx **out)
     apply_option(c->opt, "c1_mode", std::getenv("MPROS_C1_MODE"));
     apply_option(c->opt, "goal_mode", std::getenv("MPROS_GOAL_MODE"));
     apply_option(c->opt, "plan_mode", std::getenv("MPROS_PLAN_MODE"));
+    apply_option(c->opt, "solo_nodes", std::getenv("MPROS_SOLO_NODES"));
     apply_option(c->opt, "debug", std::getenv("MPROS_DEBUG"));
     mpros_map_params_default(&c->mp);
     mpros_planner_params_default(&c->pp);

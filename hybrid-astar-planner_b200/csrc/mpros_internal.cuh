@@ -82,6 +82,11 @@ struct WorkspacePool
     int *owner;    // n flags: 0 free, 1 taken
     uint32_t *gen; // n generation counters (< 2^30; the host clears the pool before they could wrap)
     int n;
+    // solo pool only: workspaces that travel with a handed-over query are "in custody" of the team pass until it has copied
+    // the state out. At most custody_max at a time, and the pool holds custody_max workspaces more than the device has
+    // resident warps, so a warp that needs a workspace always finds one (plan_squad.cuh).
+    int *custody;
+    int custody_max;
 };
 // Per-query planner workspaces of one pass (node-pool size class): node pools, open lists, closed sets and goal-wavefront
 // windows, one per resident team of the DEVICE, shared by every lane of the context (plan.cu). Owned by the context, freed
@@ -100,9 +105,11 @@ struct PlanPool
 // Work distribution of one (lane, pass): ticket counter and the list of queries to re-run
 struct PlanScratch
 {
-    unsigned int *counter = nullptr;
+    unsigned int *counter = nullptr; // 64 words: [0] ticket counter of the team pass, [16] of the solo pass, [32] length of the hand-off list
     int32_t *todo = nullptr;
     size_t todo_cap = 0;
+    int32_t *handoff = nullptr; // queries the solo pass hands to the team pass (device-side list, plan_solo.cuh)
+    size_t handoff_cap = 0;
 };
 constexpr int kPlanPasses = 3; // node-pool size classes
 
@@ -116,6 +123,10 @@ struct Options
     int goal_mode = 0;         // MPROS_GOAL_MODE: 0 cluster (16 CTAs when granted), 1 "cluster8", 2 "grid"
     bool plan_cluster = false; // MPROS_PLAN_MODE=cluster: a team is a CTA pair
     bool plan_duo = false;     // MPROS_PLAN_MODE=duo: two teams per CTA keeping their iterations in step (plan_team.cuh: DuoSync)
+    bool plan_solo = true;     // default (MPROS_PLAN_MODE unset or "solo"): every query starts in the warp-per-query kernel, the team
+                               // kernel takes over the ones that outgrow its workspaces; "team" = team kernel only
+    int solo_nodes = 32768;    // MPROS_SOLO_NODES: node-pool size of a solo workspace
+    bool plan_nosquad = false; // MPROS_PLAN_MODE=solo_warp: independent warps (plan_solo_kernel) instead of squads (plan_squad_kernel)
     bool debug = false;        // MPROS_DEBUG: per-pass timing (and the phase profile of the -DMPROS_PROFILE build) on stderr
 };
 
@@ -130,6 +141,8 @@ struct Ctx
     Options opt;
     PlanScratch plan_scratch[MPROS_PLAN_LANES][kPlanPasses];
     PlanPool plan_pool[kPlanPasses];
+    PlanPool solo_pool;    // small workspaces of the warp-per-query pass, one per resident warp of the device
+    int solo_resident = 0, squad_resident = 0; // resident CTAs per SM of the two solo-pass kernels (occupancy query, cached)
     int plan_resident[3] = {0, 0, 0}; // resident teams per SM: [0] CTA teams, [1] CTA-pair teams (occupancy query, cached), [2] two teams per CTA
 
     mpros_map_params mp;

@@ -19,7 +19,7 @@ namespace mpros
 
 struct WarpWorkspaceLayout
 {
-    size_t node_off, hkey_off, hid_off, table_off, blocked_off, f0_off, f1_off, dist_off, rowtag_off, traj_off;
+    size_t node_off, hkey_off, hid_off, table_off, blocked_off, f0_off, f1_off, dist_off, rowtag_off, traj_off, hdr_off;
     size_t stride;
     int node_cap, table_slots, bfs_rows, bfs_wwords;
 };
@@ -55,6 +55,7 @@ static WarpWorkspaceLayout make_layout(int node_cap, int H, int W)
     L.dist_off = take(bw * 32 * 2);
     L.rowtag_off = take((size_t)L.bfs_rows * 4);
     L.traj_off = take((size_t)kTrajCap * 5 * 8);
+    L.hdr_off = take(512); // ResumeHeader: state of a query handed from the squad pass to the team pass (plan_team.cuh)
     L.stride = o;
     return L;
 }
@@ -76,8 +77,21 @@ struct PlanBatchArgs
     unsigned int *counter;
     int shared_counter; // the ticket counter (and the result arrays) live in ANOTHER GPU's memory, mapped over NVLink: tickets
                         // are drawn with system-scope atomics (mpros_plan_batch_shared, dist.cu)
+    const unsigned int *n_todo_dev; // when set: the length of `todo` is read from the device (hand-off list of the solo kernel)
     WorkspacePool pool; // a team takes one workspace for the lifetime of its CTA (plan_team.cuh)
     WarpWorkspaceLayout L;
+    // solo pass (plan_solo.cuh): one warp per query with a small workspace; queries that outgrow it go to the hand-off list
+    WorkspacePool solo_pool;
+    WarpWorkspaceLayout Ls;
+    unsigned int *solo_counter;
+    int32_t *handoff;         // nq entries (null: overflowed queries report ST_OVERFLOW)
+    int32_t *handoff_ws;      // nq entries: solo workspace that holds the query's state (-1: none, the team pass starts it afresh)
+    unsigned int *handoff_n;
+    const int32_t *todo_ws;   // team pass: handoff_ws of the list it runs (null: every query starts afresh)
+    int solo_spare0, solo_spare_n; // workspaces [solo_spare0, solo_spare0 + solo_spare_n) of the solo pool start out unowned: a
+                                   // warp that hands its workspace over with a query takes one of them
+    const uint32_t *unsafe_tw; // pre-classification layer of the footprint test (map_device.cuh: footprint_preclass)
+    int center_probe;
     RsConfig rs;
     int optimal;
     // optional expansion trace (mpros_plan_search_tree, single query): pose of every expanded node in expansion order
@@ -146,6 +160,8 @@ __device__ __noinline__ double node_heuristic_quad(const MapView &m, const Plann
 } // namespace mpros
 
 #include "plan_team.cuh"
+#include "plan_solo.cuh"
+#include "plan_squad.cuh"
 
 namespace mpros
 {
@@ -1024,8 +1040,183 @@ static int plan_quiesce(mpros_ctx *c)
     return MPROS_OK;
 }
 
+#ifndef MPROS_SOLO_OFF
+// Solo pass (plan_solo.cuh): every query of the batch on its own warp with a small workspace; the queries that outgrow it are
+// appended to the lane's hand-off list, which the team pass behind it on the same stream reads from the device.
+static int plan_solo_pass(mpros_ctx *c, int lane, cudaStream_t stream, PlanBatchArgs &a, int nq)
+{
+    PlanScratch &S = c->plan_scratch[lane][0];
+    PlanPool &PL = c->solo_pool;
+    const WarpWorkspaceLayout L = make_layout(c->opt.solo_nodes, c->H, c->W);
+    // Two forms of the pass: plan_squad_kernel (W queries per CTA, heuristics evaluated by the whole CTA; needs 2 * n_steer <=
+    // kSquadMaxReq) and plan_solo_kernel (independent warps; any configuration).
+    const bool squad_ok = !c->opt.plan_nosquad && 2 * c->pv.n_steer <= kSquadMaxReq;
+    if (!c->solo_resident)
+    {
+        int r = 0, rs = 0;
+        MPROS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, plan_solo_kernel<MPROS_SOLO_WARPS, MPROS_SOLO_MINB>, 32 * MPROS_SOLO_WARPS, 0));
+        MPROS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rs, plan_squad_kernel<MPROS_SQUAD_WARPS, MPROS_SQUAD_MINB>, 32 * MPROS_SQUAD_WARPS, 0));
+        c->solo_resident = std::max(1, r);
+        c->squad_resident = std::max(1, rs);
+    }
+    // one workspace per warp the device can keep resident, however many batches are in flight (as for the team pool)
+    const int warps = squad_ok ? c->n_sm * c->squad_resident * MPROS_SQUAD_WARPS : c->n_sm * c->solo_resident * MPROS_SOLO_WARPS;
+    const bool layout_change = std::memcmp(PL.last_layout, &L, sizeof(L)) != 0;
+    // the squad form hands long queries over WITH their workspace: that many spare workspaces on top (WorkspacePool::custody)
+    const int spare = squad_ok ? std::min(nq, std::max(256, warps * 3 / 8)) : 0;
+    const int wanted = (int)std::max<long long>(layout_change ? 0 : PL.n, std::min<long long>(warps, (long long)nq * 2) + spare);
+    if (layout_change || PL.n < wanted)
+    {
+        size_t free_b = 0, total_b = 0;
+        MPROS_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const size_t budget = (free_b + PL.bytes) / 2; // half of the free memory stays with the caller (and the team pool)
+        const int n = (int)std::min<long long>(wanted, std::max<long long>(1, (long long)(budget / L.stride)));
+        if (layout_change || n > PL.n)
+        {
+            int rc = plan_quiesce(c);
+            if (rc)
+                return rc;
+            const size_t need = (size_t)n * L.stride;
+            if (need > PL.bytes)
+            {
+                if (PL.base)
+                    MPROS_CUDA(cudaFree(PL.base));
+                PL.base = nullptr;
+                PL.bytes = 0;
+                MPROS_CUDA(cudaMalloc(&PL.base, need));
+                PL.bytes = need;
+            }
+            if (n > PL.meta_cap)
+            {
+                if (PL.owner)
+                    MPROS_CUDA(cudaFree(PL.owner));
+                if (PL.gen)
+                    MPROS_CUDA(cudaFree(PL.gen));
+                PL.owner = nullptr, PL.gen = nullptr, PL.meta_cap = 0;
+                MPROS_CUDA(cudaMalloc(&PL.owner, (size_t)n * 4 + 64)); // + the custody counter behind the flags
+                MPROS_CUDA(cudaMalloc(&PL.gen, (size_t)n * 4));
+                PL.meta_cap = n;
+            }
+            MPROS_CUDA(cudaMemsetAsync(PL.base, 0, PL.bytes, stream));
+            MPROS_CUDA(cudaMemsetAsync(PL.owner, 0, (size_t)PL.meta_cap * 4 + 64, stream));
+            MPROS_CUDA(cudaMemsetAsync(PL.gen, 0, (size_t)PL.meta_cap * 4, stream));
+            MPROS_CUDA(cudaStreamSynchronize(stream));
+            PL.n = n;
+            PL.stride = L.stride;
+            PL.issued = 0;
+            std::memcpy(PL.last_layout, &L, sizeof(L));
+        }
+    }
+    if (PL.issued + (unsigned long long)nq + 2ull >= (1ull << 30)) // generation tags stay below 2^30
+    {
+        int rc = plan_quiesce(c);
+        if (rc)
+            return rc;
+        MPROS_CUDA(cudaMemsetAsync(PL.base, 0, PL.bytes, stream));
+        MPROS_CUDA(cudaMemsetAsync(PL.gen, 0, (size_t)PL.meta_cap * 4, stream));
+        MPROS_CUDA(cudaStreamSynchronize(stream));
+        PL.issued = 0;
+    }
+    PL.issued += (unsigned long long)nq + 1ull;
+    if (!S.counter)
+        MPROS_CUDA(cudaMalloc(&S.counter, 256));
+    if ((size_t)nq > S.handoff_cap)
+    {
+        // the list may still be read by the lane's previous batch: the lane is idle by contract (submit after wait), and the
+        // stream order covers the synchronous entry points
+        MPROS_CUDA(cudaStreamSynchronize(stream));
+        if (S.handoff)
+            MPROS_CUDA(cudaFree(S.handoff));
+        S.handoff = nullptr;
+        S.handoff_cap = 0;
+        MPROS_CUDA(cudaMalloc(&S.handoff, ((size_t)nq + 256) * 8)); // query indices, then the workspaces that travel with them
+        S.handoff_cap = (size_t)nq + 256;
+    }
+    MPROS_CUDA(cudaMemsetAsync(S.counter, 0, 256, stream));
+    // pre-classification layer of the footprint test; built on the context's own stream when the map or the footprint changed
+    {
+        const bool was_valid = c->unsafe_valid;
+        int rc = map_build_unsafe(c);
+        if (rc)
+            return rc;
+        if (!was_valid && stream != c->stream)
+            MPROS_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    a.unsafe_tw = c->unsafe_tw;
+    a.center_probe = c->unsafe_center_probe;
+    a.Ls = L;
+    a.solo_pool.base = PL.base;
+    a.solo_pool.owner = PL.owner;
+    a.solo_pool.gen = PL.gen;
+    a.solo_pool.n = PL.n;
+    a.solo_counter = S.counter + 16;
+    a.handoff = S.handoff;
+    a.handoff_n = S.counter + 32;
+    // a squad CTA must own a workspace for each of its warps (a warp waiting for one would stall its CTA at the round barrier)
+    const bool squad = squad_ok && PL.n >= MPROS_SQUAD_WARPS;
+    // workspaces beyond one per resident warp may be in custody of the team pass at any time (a memory-limited pool: none)
+    const int custody_max = squad ? std::max(0, PL.n - std::min(warps, PL.n)) : 0;
+    a.solo_pool.custody = PL.owner + PL.meta_cap;
+    a.solo_pool.custody_max = custody_max;
+    a.handoff_ws = (squad && custody_max > 0) ? S.handoff + S.handoff_cap : nullptr;
+    a.todo_ws = a.handoff_ws;
+    a.solo_spare0 = std::min(warps, PL.n);
+    a.solo_spare_n = std::max(1, custody_max);
+    const int wpc = squad ? MPROS_SQUAD_WARPS : MPROS_SOLO_WARPS;
+    const int ctas = squad ? std::max(1, std::min(std::min(warps, PL.n) / wpc, (nq + wpc - 1) / wpc))
+                           : std::max(1, std::min((std::min(warps, PL.n) + wpc - 1) / wpc, (nq + wpc - 1) / wpc));
+    const bool dbg = c->opt.debug;
+    cudaEvent_t e0, e1;
+    if (dbg)
+    {
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, stream);
+    }
+    if (squad)
+        plan_squad_kernel<MPROS_SQUAD_WARPS, MPROS_SQUAD_MINB><<<ctas, 32 * MPROS_SQUAD_WARPS, 0, stream>>>(c->view(), c->pv, a);
+    else
+        plan_solo_kernel<MPROS_SOLO_WARPS, MPROS_SOLO_MINB><<<ctas, 32 * MPROS_SOLO_WARPS, 0, stream>>>(c->view(), c->pv, a);
+    MPROS_LAUNCH_CHECK(c);
+    if (dbg)
+    {
+        cudaEventRecord(e1, stream);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        unsigned int nh = 0;
+        cudaMemcpy(&nh, S.counter + 32, 4, cudaMemcpyDeviceToHost);
+#ifdef MPROS_PROFILE
+        if (squad)
+        {
+            unsigned long long h[24];
+            cudaMemcpyFromSymbol(h, g_prof, sizeof(h));
+            unsigned long long z[24] = {0};
+            cudaMemcpyToSymbol(g_prof, z, sizeof(z));
+            const double wr = (double)std::max<unsigned long long>(1, h[8]);
+            const char *names[8] = {"own step", "wait (1)", "round A", "wait (2)", "skip + wait (3)", "round B", "wait (4)", "inserts"};
+            std::fprintf(stderr, "[mpros] squad profile: %.0f warp-rounds; per warp-round: expansions %.3f, requests %.3f, round-B requests %.3f, round B present %.3f, waiting for the goal map %.3f, idle/done %.3f, init %.3f, shots %.4f; cycles per warp-round:\n",
+                         wr, h[12] / wr, h[10] / wr, h[11] / wr, h[9] / wr, h[13] / wr, h[14] / wr, h[16] / wr, h[15] / wr);
+            for (int k = 0; k < 8; ++k)
+                std::fprintf(stderr, "[mpros]   %-16s %9.1f\n", names[k], h[k] / wr);
+            const char *sub[6] = {"pop (+ stale)", "node, primitives", "pre-classification", "probe walks", "closed set, g", "goal-map values"};
+            const double ex = (double)std::max<unsigned long long>(1, h[12]);
+            std::fprintf(stderr, "[mpros]   inside the own step, cycles per EXPANSION:\n");
+            for (int k = 0; k < 6; ++k)
+                std::fprintf(stderr, "[mpros]     %-18s %9.1f\n", sub[k], h[17 + k] / ex);
+        }
+#endif
+        std::fprintf(stderr, "[mpros] %s pass: %d queries, node_cap %d, %d CTAs x %d warps (%d resident per SM), %.1f MB/warp, %.3f ms, %u handed to the team pass\n",
+                     squad ? "squad" : "solo", nq, L.node_cap, ctas, wpc, squad ? c->squad_resident : c->solo_resident, L.stride / 1048576.0, ms, nh);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    return MPROS_OK;
+}
+#endif
+
 static int plan_pass(mpros_ctx *c, int lane, cudaStream_t stream, PlanBatchArgs &a, int pass, int node_cap, int n_run, const int32_t *d_todo,
-                     int max_warps)
+                     int max_warps, const unsigned int *n_todo_dev = nullptr)
 {
     PlanScratch &S = c->plan_scratch[lane][pass]; // ticket counter / re-run list of this lane
     PlanPool &PL = c->plan_pool[pass];            // workspaces: owned by the context, shared by its lanes
@@ -1141,6 +1332,7 @@ static int plan_pass(mpros_ctx *c, int lane, cudaStream_t stream, PlanBatchArgs 
     a.pool.n = PL.n;
     a.todo = d_todo;
     a.n_todo = n_run;
+    a.n_todo_dev = n_todo_dev;
     const bool dbg = c->opt.debug;
     cudaEvent_t e0, e1;
     if (dbg)
@@ -1232,6 +1424,18 @@ static int plan_batch_dev_impl(mpros_ctx *c, int lane, cudaStream_t stream, cons
                 caps[0] = max_nodes;
         }
     }
+#ifndef MPROS_SOLO_OFF
+    // Default: every query starts on its own warp with a small workspace (solo pass); the team pass behind it runs only the
+    // queries that outgrew it, with full-size workspaces, and finds them in a device-side list (no host round trip, so the
+    // asynchronous entry points stay asynchronous). The expansion trace is a team-kernel feature.
+    if (c->opt.plan_solo && !c->opt.plan_cluster && !c->opt.plan_duo && !d_trace && caps[0] >= max_nodes && c->opt.solo_nodes < max_nodes)
+    {
+        int rc = plan_solo_pass(c, lane, stream, a, nq);
+        if (rc)
+            return rc;
+        return plan_pass(c, lane, stream, a, 0, (int)max_nodes, nq, a.handoff, 0, a.handoff_n);
+    }
+#endif
     int rc = plan_pass(c, lane, stream, a, 0, (int)std::min<long long>(caps[0], max_nodes), nq, nullptr, 0);
     if (rc)
         return rc;

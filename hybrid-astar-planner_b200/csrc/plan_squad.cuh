@@ -1,0 +1,732 @@
+// Whole-query planner, a SQUAD of W queries per CTA: one warp per query for the search itself, the heuristics of all W
+// queries evaluated together by the whole CTA.
+//
+// Why (ncu of the plain warp-per-query kernel, plan_solo.cuh, profiles/r02_plan_solo_kernel_*): 5 400 warp-instructions per
+// iteration, 60 % of them in the OMPL-equivalent Reeds-Shepp distance of the 1-3 children that need a heuristic - evaluated
+// with 4-12 of 32 lanes busy (lane = child x symmetry image), eleven formula bodies one after the other - and the 24
+// resident warps of an SM spread over ~45 KB of hot code (instruction-cache hit rate 64 %, stall_no_instruction 13 per
+// issue, issue slots 22 % busy). Here every round of the CTA has the same phases:
+//   1. each warp advances its own query by one step: pop, Reeds-Shepp shot or expansion (primitives, footprint tests,
+//      closed-set probes, goal-map values) and POSTS the children that need a heuristic into shared memory;
+//   2. round A, whole CTA: the two CSC words of every posted child, work item = (child, word) on a quad of lanes (lane =
+//      symmetry image), items ordered by word so that the 32 lanes of a warp run the SAME closed form on eight children;
+//   3. each warp applies the exact skip rule to its own children (rho * min(CSC) <= h1 for all of them: done) and posts the
+//      others for round B;
+//   4. round B, whole CTA: the other nine words, same layout;
+//   5. each warp combines the family minima of its children and inserts them (closed set, node pool, open list).
+// All warps of an SM execute the same phase at the same time, so the instruction cache holds one phase instead of all, and
+// the formula code runs with full warps. Work per round is bounded (the goal wavefront advances at most kSquadBfsSteps
+// levels per round; a query still waiting for a goal-map value keeps its children in registers and posts nothing).
+//
+// Semantics and arithmetic are those of plan_solo.cuh / plan_team.cuh: same device functions on the same operands in the
+// same order, results bit-identical (tests/test_gpu_synthetic_fullsize.py::test_solo_and_team_passes_give_identical_plans).
+#pragma once
+#include "plan_solo.cuh"
+
+namespace mpros
+{
+
+constexpr int kSquadMaxReq = 8;    // children of one expansion that can ask for a heuristic (2 * n_steer <= 8; else plan_solo_kernel)
+constexpr int kSquadBfsSteps = 16; // goal-wavefront levels one warp advances per round at most
+constexpr int kHandOff = 0x7ffffffe; // `finish` value: the query goes to the team pass together with its state
+
+struct SquadReq
+{
+    double inx, iny, dth, nxb, nyb, sphi, cphi; // normalised goal seen from the child (plan_team.cuh, closed-set warp phase C)
+    double h1v;                                  // goal-map value * resolution
+    unsigned long long fam[3];                   // minima over images and words per family (plain, CCSC, CCSCC), as ordered bit patterns
+    unsigned long long pad;
+};
+
+template <int W>
+struct SquadShared
+{
+    SoloShared q[W];
+    SquadReq req[W * kSquadMaxReq]; // slots w * kSquadMaxReq .. belong to warp w
+    short list_a[W * kSquadMaxReq]; // posted slots of this round
+    short list_b[W * kSquadMaxReq]; // slots that need round B
+    // counters of round r live at index r % 3: thread 0 clears the set of round r + 1 before barrier (1) of round r, when the
+    // last readers (round r - 2) are long gone and the next writers (round r + 1) have not started
+    int n_a[3], n_b[3], n_done[3];
+};
+
+// Phase profile of the squad kernel (developer build, -DMPROS_PROFILE): lane 0 of every warp sums cycles per phase in
+// registers and adds them to g_prof when its CTA ends. Slots: 0 phase 1 (own step), 1 wait (1), 2 round A, 3 wait (2),
+// 4 skip rule + wait (3), 5 round B, 6 wait (4), 7 inserts / results; counters: 8 warp-rounds, 9 warp-rounds with a round B,
+// 10 requests, 11 round-B requests, 12 expansions, 13 warp-rounds waiting for a goal-map value, 14 idle / done warp-rounds,
+// 15 shots, 16 warp-rounds in INIT.
+struct SquadProf
+{
+#ifdef MPROS_PROFILE
+    unsigned long long acc[24];
+    long long t0;
+    __device__ __forceinline__ void init()
+    {
+        for (int k = 0; k < 24; ++k)
+            acc[k] = 0;
+        t0 = Prof::now();
+    }
+    __device__ __forceinline__ void mark(int k)
+    {
+        const long long t1 = Prof::now();
+        acc[k] += (unsigned long long)(t1 - t0);
+        t0 = t1;
+    }
+    __device__ __forceinline__ void add(int k, unsigned long long v) { acc[k] += v; }
+    // sub-phase of phase 1: the time since the last mark / sub goes to slot k AND stays inside slot 0 (t0 is not moved)
+    long long ts;
+    __device__ __forceinline__ void sub0() { ts = Prof::now(); }
+    __device__ __forceinline__ void sub(int k)
+    {
+        const long long t1 = Prof::now();
+        acc[k] += (unsigned long long)(t1 - ts);
+        ts = t1;
+    }
+    __device__ __forceinline__ void flush()
+    {
+        if ((threadIdx.x & 31) == 0)
+            for (int k = 0; k < 24; ++k)
+                atomicAdd(&g_prof[k], acc[k]);
+    }
+#else
+    __device__ __forceinline__ void init() {}
+    __device__ __forceinline__ void mark(int) {}
+    __device__ __forceinline__ void add(int, unsigned long long) {}
+    __device__ __forceinline__ void sub0() {}
+    __device__ __forceinline__ void sub(int) {}
+    __device__ __forceinline__ void flush() {}
+#endif
+};
+
+// one formula on eight children per warp: item i of `total` = (slot list[i % n], word k0 + i / n), lane = 4 * item + image
+template <int W>
+__device__ __forceinline__ void squad_formula_pass(SquadShared<W> &S, const short *list, int n, int k0, int nk)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int total = n * nk;
+    for (int base = warp * 8; base < total; base += W * 8)
+    {
+        const int i = base + (lane >> 2), q = lane & 3;
+        const bool live = i < total;
+        double Lf = DBL_MAX;
+        int slot = 0, k = k0;
+        if (live)
+        {
+            k = k0 + i / n;
+            slot = list[i - (k - k0) * n];
+            const SquadReq &r = S.req[slot];
+            const bool fx = (q == 1 || q == 3), fy = (q == 2 || q == 3), fp = (q == 1 || q == 2);
+            const double inx = r.inx, iny = r.iny, dth = r.dth, nxb = r.nxb, nyb = r.nyb, sphi = r.sphi;
+            Lf = ompl_formula(k, fx ? -inx : inx, fy ? -iny : iny, fp ? -dth : dth, fx ? -nxb : nxb, fy ? -nyb : nyb, fp ? -sphi : sphi, r.cphi);
+        }
+        Lf = fmin(Lf, __shfl_xor_sync(kFull, Lf, 1));
+        Lf = fmin(Lf, __shfl_xor_sync(kFull, Lf, 2));
+        if (live && q == 0 && Lf < DBL_MAX)
+            atomicMin(&S.req[slot].fam[ompl_formula_family(k)], (unsigned long long)__double_as_longlong(Lf));
+    }
+}
+
+// The collective part of a round. Lane c of a warp passes child c (needmask: the children that want a heuristic) with its
+// pose, sin / cos of its yaw, sin / cos of (goal yaw - yaw) and goal-map value; returns h of child c on lane c. Every warp of
+// the CTA calls it exactly once per round (needmask 0: nothing to ask). all_done: every warp reported `done`.
+template <int W>
+__device__ __forceinline__ double squad_heuristics(const MapView &m, const PlannerView &p, SquadShared<W> &S, unsigned needmask, double gx, double gy,
+                                                   double gyaw, double x, double y, double yaw, double sn, double cs, double sphi, double cphi, int h1,
+                                                   bool done, int rnd, int &n_done, SquadProf &pf)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cur3 = rnd % 3, nxt3 = (rnd + 1) % 3;
+    if (threadIdx.x == 0)
+        S.n_a[nxt3] = 0, S.n_b[nxt3] = 0, S.n_done[nxt3] = 0;
+    const bool mine = (needmask >> lane) & 1u;
+    const int rank = __popc(needmask & ((1u << lane) - 1u)), cnt = __popc(needmask);
+    const int slot = warp * kSquadMaxReq + rank;
+    const double h1v = (double)h1 * m.res; // getGoalCost: cost_ * map_resolution_
+    if (mine)
+    {
+        SquadReq &r = S.req[slot];
+        const double dx = gx - x, dy = gy - y;
+        r.inx = dm::div_(cs * dx + sn * dy, p.min_r);
+        r.iny = dm::div_(-sn * dx + cs * dy, p.min_r);
+        r.dth = gyaw - yaw;
+        r.nxb = r.inx * cphi + r.iny * sphi;
+        r.nyb = r.inx * sphi - r.iny * cphi;
+        r.sphi = sphi, r.cphi = cphi, r.h1v = h1v;
+        r.fam[0] = r.fam[1] = r.fam[2] = (unsigned long long)__double_as_longlong(DBL_MAX);
+    }
+    if (lane == 0)
+    {
+        if (cnt)
+        {
+            const int at = atomicAdd(&S.n_a[cur3], cnt);
+            for (int j = 0; j < cnt; ++j)
+                S.list_a[at + j] = (short)(warp * kSquadMaxReq + j);
+        }
+        if (done)
+            atomicAdd(&S.n_done[cur3], 1);
+    }
+    pf.mark(0);
+    __syncthreads(); // (1) every request of this round is posted
+    pf.mark(1);
+    const int n_a = S.n_a[cur3];
+    n_done = S.n_done[cur3];
+    if (n_a == 0)
+        return 0.0;
+    squad_formula_pass<W>(S, S.list_a, n_a, 0, 2); // round A: CSC
+    pf.mark(2);
+    __syncthreads(); // (2)
+    pf.mark(3);
+    pf.add(10, cnt);
+    // exact skip (plan_team.cuh: heur_rounds): when rho * min(CSC) <= h1 for every asking child of this query the other nine
+    // words cannot change max(h1, h2)
+    bool ok = true;
+    if (mine)
+        ok = p.min_r * __longlong_as_double((long long)S.req[slot].fam[0]) <= h1v;
+    const bool skip = __all_sync(kFull, ok);
+    if (!skip && lane == 0)
+    {
+        const int at = atomicAdd(&S.n_b[cur3], cnt);
+        for (int j = 0; j < cnt; ++j)
+            S.list_b[at + j] = (short)(warp * kSquadMaxReq + j);
+    }
+    __syncthreads(); // (3)
+    pf.mark(4);
+    const int n_b = S.n_b[cur3];
+    if (n_b)
+    {
+        squad_formula_pass<W>(S, S.list_b, n_b, 2, 9); // round B: CCC, CCCC, CCSC, CCSCC
+        pf.mark(5);
+        __syncthreads(); // (4)
+        pf.mark(6);
+        pf.add(9, 1);
+        pf.add(11, skip ? 0 : cnt);
+    }
+    double h = 0.0;
+    if (mine)
+    {
+        const SquadReq &r = S.req[slot];
+        h = fmax(h1v, ompl_combine(p.min_r, __longlong_as_double((long long)r.fam[0]), __longlong_as_double((long long)r.fam[1]),
+                                   __longlong_as_double((long long)r.fam[2]))) *
+            (1 + 1e-3);
+    }
+    return h;
+}
+
+// goal-map values with a bounded number of wavefront steps; final = every requested value is known
+__device__ __forceinline__ int squad_h1_lookup(const MapView &m, TeamBfs &b, bool want, int i, int j, int &v, int max_steps)
+{
+    if (want && v < 0)
+        v = team_bfs_peek(m, b, i, j);
+    int steps = 0;
+    while (__any_sync(kFull, want && v < 0) && steps < max_steps)
+    {
+        solo_bfs_step(m, b);
+        ++steps;
+        if (want && v < 0)
+            v = team_bfs_peek(m, b, i, j);
+    }
+    return !__any_sync(kFull, want && v < 0);
+}
+
+// Hand a query over to the team pass with its state: the warp's workspace (node pool, open list, closed set, wavefront
+// window) travels with the query, the rest goes into the ResumeHeader; the warp goes on with another workspace. Called
+// between two iterations (open list consistent, nothing half inserted). Returns false when the custody limit is reached:
+// nothing has changed then.
+__device__ __noinline__ bool squad_hand_over(const PlanBatchArgs &a, SoloShared &S, const OpenHeap &heap, int q, int &ws_slot, uint32_t &gen,
+                                             uint32_t n_nodes, int iteration, int n_shots, long long n_exp, long long n_coll, bool goal_found,
+                                             uint32_t goal_parent, double goal_g, int si, int sj)
+{
+    const int lane = threadIdx.x & 31;
+    const int fresh = pool_swap_acquire_warp(a.solo_pool, a.solo_spare0 + (int)((unsigned)q % (unsigned)max(1, a.solo_spare_n)));
+    if (fresh < 0)
+        return false;
+    const WarpWorkspaceLayout &L = a.Ls;
+    char *ws = a.solo_pool.base + (size_t)ws_slot * L.stride;
+    // the top of the open list lives in shared memory: complete the global arrays
+    for (int k = lane; k < heap.size && k < kSoloHeapTop; k += 32)
+        heap.key[k] = S.hkey[k], heap.id[k] = S.hid[k];
+    if (lane == 0)
+    {
+        ResumeHeader *H = reinterpret_cast<ResumeHeader *>(ws + L.hdr_off);
+        H->tag = gen, H->gen = gen, H->heap_size = heap.size, H->n_nodes = n_nodes;
+        H->iteration = iteration, H->n_shots = n_shots, H->goal_found = goal_found, H->goal_parent = goal_parent;
+        H->n_exp = n_exp, H->n_coll = n_coll, H->goal_g = goal_g, H->si = si, H->sj = sj;
+        H->bfs = S.bfs;
+    }
+    __syncwarp();
+    uint32_t fresh_gen = 0;
+    if (lane == 0)
+    {
+        __threadfence();
+        const unsigned at = atomicAdd(a.handoff_n, 1u);
+        a.handoff[at] = q;
+        a.handoff_ws[at] = ws_slot;
+        a.status[q] = ST_OVERFLOW; // overwritten by the team pass
+        fresh_gen = a.solo_pool.gen[fresh];
+    }
+    ws_slot = fresh;
+    gen = __shfl_sync(kFull, fresh_gen, 0);
+    return true;
+}
+
+#ifndef MPROS_SQUAD_WARPS
+#define MPROS_SQUAD_WARPS 24 // queries per CTA
+#endif
+#ifndef MPROS_SQUAD_MINB
+#define MPROS_SQUAD_MINB 1 // CTAs per SM
+#endif
+template <int W, int MINB>
+__global__ void __launch_bounds__(32 * W, MINB) plan_squad_kernel(const __grid_constant__ MapView m, const __grid_constant__ PlannerView p,
+                                                                   const __grid_constant__ PlanBatchArgs a)
+{
+    __shared__ SquadShared<W> SQ;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SoloShared &S = SQ.q[warp];
+    if (threadIdx.x < 3)
+        SQ.n_a[threadIdx.x] = 0, SQ.n_b[threadIdx.x] = 0, SQ.n_done[threadIdx.x] = 0;
+    __syncthreads();
+    const WarpWorkspaceLayout &L = a.Ls;
+    const int P = 2 * p.n_steer;
+    const unsigned total = (unsigned)a.nq;
+    // workspace of this warp (taken with the first ticket)
+    int ws_slot = -1;
+    uint32_t gen = 0;
+    char *ws = nullptr;
+    PlanNode *nodes = nullptr;
+    double *scratch = nullptr;
+    OpenHeap heap;
+    heap.skey = S.hkey, heap.sid = S.hid, heap.scap = kSoloHeapTop, heap.size = 0, heap.cap = L.node_cap;
+    heap.key = nullptr, heap.id = nullptr;
+    ClosedSet closed;
+    closed.slot = nullptr, closed.mask = (uint32_t)L.table_slots - 1, closed.tag = 0;
+    // query state
+    enum
+    {
+        IDLE,    // no query: draw a ticket
+        INIT,    // wavefront on its way to the start cell
+        RUN,     // pop and expand
+        WAIT_H1, // children computed, a goal-map value is not final yet
+        DONE     // no tickets left
+    };
+    int state = IDLE, q = -1;
+    int si = -1, sj = -1;
+    double s_start = 0, c_start = 1;
+    uint32_t n_nodes = 0, goal_parent = kNoNode, cur = 0;
+    int iteration = 0, n_shots = 0;
+    long long n_exp = 0, n_coll = 0;
+    bool goal_found = false;
+    double goal_g = -1.0;
+    // children of the current expansion (lane = primitive), kept across rounds while a goal-map value is pending
+    double nx = 0, ny = 0, nyaw = 0, steer = 0, direc = 1, ns = 0, nc = 1, sphi = 0, cphi = 1, g = 0, pr_old_cost = 0;
+    bool need = false, pr_found = false;
+    uint32_t pr_old = kNoNode, pr_slot = 0;
+    unsigned long long idx = 0;
+    int ci = -1, cj = -1, h1 = -1;
+    double cn_x = 0, cn_y = 0; // position of the expanded node (stop radius)
+    unsigned long long cur_key = 0; // open-list key the expanded node was popped with
+    int exp_shots = 0, exp_checked = 0; // what the failed shot before the current expansion added to the statistics
+    int n_done = 0;                 // warps of this CTA without work in the previous round
+    auto bind_ws = [&]() {
+        ws = a.solo_pool.base + (size_t)ws_slot * L.stride;
+        nodes = reinterpret_cast<PlanNode *>(ws + L.node_off);
+        scratch = reinterpret_cast<double *>(ws + L.traj_off);
+        heap.key = reinterpret_cast<unsigned long long *>(ws + L.hkey_off);
+        heap.id = reinterpret_cast<uint32_t *>(ws + L.hid_off);
+        closed.slot = reinterpret_cast<ClosedSlot *>(ws + L.table_off);
+    };
+
+    SquadProf pf;
+    pf.init();
+    for (int rnd = 0;; ++rnd)
+    {
+        // ================= phase 1: every warp advances its own query =================
+        unsigned needmask = 0; // children (or the start node, lane 0) posted for a heuristic in this round
+        bool post_start = false;
+        bool exp_done = false;   // an expansion completes in this round: its children are inserted in phase 5
+        int finish = 0x7fffffff; // status to report when the query ends in this round (0x7fffffff: it goes on)
+        if (state == IDLE)
+        {
+            unsigned t = 0;
+            if (lane == 0)
+                t = atomicAdd(a.solo_counter, 1u);
+            t = __shfl_sync(kFull, t, 0);
+            if (t >= total)
+                state = DONE;
+            else
+            {
+                q = (int)t;
+                if (ws_slot < 0)
+                {
+                    if (lane == 0)
+                    {
+                        ws_slot = pool_acquire(a.solo_pool, (int)(blockIdx.x * W + warp));
+                        gen = a.solo_pool.gen[ws_slot];
+                    }
+                    ws_slot = __shfl_sync(kFull, ws_slot, 0);
+                    gen = __shfl_sync(kFull, gen, 0);
+                    bind_ws();
+                }
+                ++gen;
+                closed.tag = gen;
+                heap.size = 0;
+                n_nodes = 0, goal_parent = kNoNode, iteration = 0, n_shots = 0, n_exp = 0, n_coll = 0, goal_found = false, goal_g = -1.0;
+                __syncwarp();
+                if (lane == 0)
+                {
+                    S.sx = a.starts[3 * q], S.sy = a.starts[3 * q + 1], S.syaw = a.starts[3 * q + 2];
+                    S.gx = a.goals[3 * q], S.gy = a.goals[3 * q + 1], S.gyaw = a.goals[3 * q + 2];
+                    S.bfs.blocked = reinterpret_cast<uint32_t *>(ws + L.blocked_off);
+                    S.bfs.f0 = reinterpret_cast<uint32_t *>(ws + L.f0_off);
+                    S.bfs.f1 = reinterpret_cast<uint32_t *>(ws + L.f1_off);
+                    S.bfs.dist = reinterpret_cast<uint16_t *>(ws + L.dist_off);
+                    S.bfs.cells = 0;
+                }
+                __syncwarp();
+                // ---- initialize (hybrid_a_star.cpp:52-118)
+                dm::sincos_(S.syaw, &s_start, &c_start);
+                bool init_ok = !warp_footprint_collision(m, p, S.sx, S.sy, s_start, c_start); // "Start pose in collision"
+                if (init_ok)
+                {
+                    double s, c;
+                    dm::sincos_(S.gyaw, &s, &c);
+                    init_ok = !warp_footprint_collision(m, p, S.gx, S.gy, s, c); // "Goal pose in collision"
+                }
+                int gi = -1, gj = -1;
+                if (init_ok)
+                {
+                    const bool s_in = pos_to_index_ds(m, S.sx, S.sy, si, sj);
+                    const bool g_in = pos_to_index_ds(m, S.gx, S.gy, gi, gj);
+                    init_ok = s_in && g_in; // goal outside the map: no goal map (nav_map.cpp:297-302)
+                }
+                if (init_ok)
+                {
+                    solo_bfs_start(m, S.bfs, gi, gj, gen);
+                    h1 = -1;
+                    state = INIT;
+                }
+                else
+                    finish = ST_NOT_INIT;
+            }
+        }
+        else if (state == INIT)
+        {
+            // start node: steer 0, direction 1, g = 0 (:83, :211-215); its heuristic goes through the CTA's rounds like a child's
+            if (squad_h1_lookup(m, S.bfs, lane == 0, si, sj, h1, kSquadBfsSteps))
+            {
+                h1 = __shfl_sync(kFull, h1, 0);
+                dm::sincos_(S.gyaw - S.syaw, &sphi, &cphi);
+                nx = S.sx, ny = S.sy, nyaw = S.syaw, ns = s_start, nc = c_start;
+                needmask = 1u;
+                post_start = true;
+            }
+        }
+        else if (state == RUN || state == WAIT_H1)
+        {
+            bool expanding = state == WAIT_H1;
+            // Tail of the batch: the tickets have run out and most warps of this CTA are done. The queries still running are
+            // the long ones; a whole team finishes them faster than a nearly empty squad, and the team pass cannot start before
+            // this kernel has ended: hand them over, state and all.
+            if (state == RUN && a.handoff_ws && n_done >= W - W / 3 && iteration >= 32 && heap.size > 0 &&
+                squad_hand_over(a, S, heap, q, ws_slot, gen, n_nodes, iteration, n_shots, n_exp, n_coll, goal_found, goal_parent, goal_g, si, sj))
+            {
+                bind_ws();
+                finish = kHandOff;
+            }
+            else if (state == RUN)
+            {
+                // ---- Plan() (hybrid_a_star.cpp:682-777): next open node that is not CLOSE
+                bool have = false;
+                PlanNode cn;
+                pf.sub0();
+                while (heap.size > 0)
+                {
+                    if (iteration > p.max_iteration)
+                    {
+                        finish = ST_LIMIT;
+                        break;
+                    }
+                    cur = heap_pop_warp(heap, cur_key);
+                    cn = nodes[cur];
+                    if (!cn.closed)
+                    {
+                        have = true;
+                        break;
+                    }
+                }
+                if (!have && finish == 0x7fffffff)
+                    finish = goal_found ? ST_FOUND : ST_OPEN_EMPTY;
+                pf.sub(17);
+                if (have)
+                {
+                    cn_x = cn.x, cn_y = cn.y;
+                    // -- genRSPath (:853-900)
+                    bool shot_ok = false;
+                    const double ddx = cn.x - S.gx, ddy = cn.y - S.gy;
+                    exp_shots = 0, exp_checked = 0;
+                    if (ddx * ddx + ddy * ddy < p.rs_range * p.rs_range)
+                    {
+                        double rs_cost;
+                        int checked;
+                        const int np = solo_shot(m, p, a, S, cn, scratch, rs_cost, checked);
+                        ++n_shots;
+                        pf.add(15, 1);
+                        n_coll += checked;
+                        exp_shots = 1, exp_checked = checked;
+                        if (np >= 0)
+                        {
+                            if (goal_parent == kNoNode || goal_g > cn.g + rs_cost)
+                            {
+                                goal_parent = cur;
+                                goal_g = cn.g + rs_cost;
+                            }
+                            shot_ok = true;
+                        }
+                    }
+                    if (shot_ok)
+                    {
+                        goal_found = true;
+                        if (!a.optimal || dm::hypot_(S.gx - cn.x, S.gy - cn.y) <= 1.0)
+                            finish = ST_FOUND; // first successful shot ends the search (:725-728); stop radius (hybrid_a_star.h:345)
+                        else
+                            ++iteration;
+                    }
+                    else
+                    {
+                        // -- expandNode (:304-402), lane = primitive; lanes P..2P-1 shadow the children for the second sin/cos pair
+                        expanding = true;
+                        ++n_exp;
+                        n_coll += P;
+                        const int c = lane < P ? lane : (lane < 2 * P ? lane - P : 0);
+                        primitive_end_pose(p, c, cn.x, cn.y, cn.yaw, cn.s, cn.c, nx, ny, nyaw, steer, direc);
+                        ns = 0, nc = 1;
+                        if (lane < 2 * P)
+                            dm::sincos_(lane < P ? nyaw : S.gyaw - nyaw, &ns, &nc);
+                        sphi = __shfl_sync(kFull, ns, (lane + P) & 31);
+                        cphi = __shfl_sync(kFull, nc, (lane + P) & 31);
+                        pf.sub(18);
+                        const int cls = lane < P ? footprint_preclass(m, p, a.unsafe_tw, a.center_probe, nx, ny, nyaw) : 1;
+                        unsigned free_mask = __ballot_sync(kFull, cls == 0);
+                        unsigned walk_mask = __ballot_sync(kFull, cls == 2);
+                        pf.sub(19);
+                        while (walk_mask)
+                        {
+                            const int t = __ffs(walk_mask) - 1;
+                            walk_mask &= walk_mask - 1;
+                            if (!warp_footprint_collision(m, p, __shfl_sync(kFull, nx, t), __shfl_sync(kFull, ny, t), __shfl_sync(kFull, ns, t),
+                                                          __shfl_sync(kFull, nc, t)))
+                                free_mask |= 1u << t;
+                        }
+                        pf.sub(20);
+                        need = false, pr_found = false, pr_old = kNoNode, pr_slot = 0xffffffffu - lane, idx = 0, ci = -1, cj = -1, g = 0, pr_old_cost = 0;
+                        if (lane < P && ((free_mask >> lane) & 1u) && pos_to_index_ds(m, nx, ny, ci, cj))
+                        {
+                            const float voro_f = __ldg(m.voronoi + (size_t)ci * m.W + cj);
+                            idx = cal_index(m, p, ci, cj, yaw_to_idx(p, nyaw), direc);
+                            pr_slot = closed_find(closed, idx, pr_found, pr_old_cost, pr_old);
+                            g = node_cost(p, cn.g, (double)cn.dir, cn.steer, (double)voro_f, steer, direc);
+                            need = pr_old_cost > g; // an earlier sibling on the same slot may still beat it; resolved at insert
+                        }
+                        h1 = -1;
+                        pf.sub(21);
+                    }
+                }
+            }
+            if (expanding)
+            {
+                pf.sub0();
+                const bool h1_final = squad_h1_lookup(m, S.bfs, need, ci, cj, h1, kSquadBfsSteps);
+                pf.sub(22);
+                if (h1_final)
+                {
+                    needmask = __ballot_sync(kFull, need);
+                    exp_done = true;
+                    state = RUN;
+                }
+                else
+                    state = WAIT_H1; // the children stay in registers; nothing is posted in this round
+            }
+        }
+
+        // ================= phases 2-4: heuristics of every posted child, whole CTA =================
+        const double h = squad_heuristics<W>(m, p, SQ, needmask, S.gx, S.gy, S.gyaw, nx, ny, nyaw, ns, nc, sphi, cphi, h1, state == DONE, rnd, n_done, pf);
+        const bool all_done = n_done == W;
+        pf.add(8, 1);
+        pf.add(12, exp_done ? 1 : 0);
+        pf.add(13, state == WAIT_H1 ? 1 : 0);
+        pf.add(14, (state == DONE || state == IDLE) ? 1 : 0);
+        pf.add(16, state == INIT ? 1 : 0);
+
+        // ================= phase 5: inserts =================
+        if (post_start)
+        {
+            const double h0 = __shfl_sync(kFull, h, 0);
+            if (lane == 0)
+            {
+                PlanNode n;
+                n.x = S.sx, n.y = S.sy, n.yaw = S.syaw, n.steer = 0.0, n.g = 0.0, n.s = s_start, n.c = c_start, n.parent = kNoNode, n.dir = 1, n.closed = 0,
+                n.pad = 0;
+                nodes[0] = n;
+                // cost_set_/node_set_ seeds (:107-112); the goal entry is written second and wins a shared cell
+                bool found;
+                double og;
+                uint32_t on;
+                const unsigned long long sidx = cal_index(m, p, si, sj, yaw_to_idx(p, S.syaw), 1.0);
+                const uint32_t s0 = closed_find(closed, sidx, found, og, on);
+                closed_store(closed, s0, sidx, 0.0, 0);
+                const unsigned long long gidx = cal_index(m, p, S.bfs.gi, S.bfs.gj, yaw_to_idx(p, S.gyaw), 1.0);
+                const uint32_t s1 = closed_find(closed, gidx, found, og, on);
+                closed_store(closed, s1, gidx, 10000.0, kGoalNode);
+                heap_push_lane0(heap, (unsigned long long)__double_as_longlong(0.0 + h0), 0);
+            }
+            heap.size = 1;
+            n_nodes = 1;
+            state = RUN;
+            __syncwarp();
+        }
+        // the node pool must take all children of the expansion, or none (a handed-over query resumes between two iterations)
+        bool overflow = !post_start && needmask && n_nodes + __popc(needmask) > (uint32_t)L.node_cap;
+        if (!post_start && needmask && !overflow)
+        {
+            // closed-set compare / insert in primitive order (see plan_solo.cuh)
+            const unsigned same = __match_any_sync(kFull, need ? pr_slot : 0xffffffffu - lane);
+            const bool conflict = __any_sync(kFull, need && (same & (same - 1)) != 0);
+            if (!conflict)
+            {
+                const int cnt = __popc(needmask);
+                if (n_nodes + cnt > (uint32_t)L.node_cap)
+                    overflow = true;
+                else
+                {
+                    const int rank = __popc(needmask & ((1u << lane) - 1u));
+                    const uint32_t id = n_nodes + rank;
+                    const unsigned long long key = (unsigned long long)__double_as_longlong(g + h);
+                    bool up = false;
+                    const int pos = heap.size + rank;
+                    if (need)
+                    {
+                        if (pr_found && pr_old < kGoalNode)
+                            nodes[pr_old].closed = 1;
+                        closed_store(closed, pr_slot, idx, g, id);
+                        PlanNode nn;
+                        nn.x = nx, nn.y = ny, nn.yaw = nyaw, nn.steer = steer, nn.g = g, nn.s = ns, nn.c = nc, nn.parent = cur;
+                        nn.dir = (int8_t)(direc > 0 ? 1 : -1), nn.closed = 0, nn.pad = 0;
+                        nodes[id] = nn;
+                        if (pos > 0)
+                        {
+                            const int parent = (pos - 1) >> 5;
+                            up = parent >= heap.size ? true : heap_less(key, id, hk(heap, parent), hi(heap, parent));
+                        }
+                    }
+                    if (!__any_sync(kFull, up) && heap.size > 0)
+                    {
+                        if (need)
+                            hset(heap, pos, key, id);
+                        heap.size += cnt;
+                    }
+                    else
+                    {
+                        unsigned todo = needmask;
+                        while (todo)
+                        {
+                            const int b = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            const unsigned long long k = __shfl_sync(kFull, key, b);
+                            const uint32_t kid = __shfl_sync(kFull, id, b);
+                            if (lane == 0)
+                                heap_push_lane0(heap, k, kid);
+                            heap.size++;
+                            __syncwarp();
+                        }
+                    }
+                    n_nodes += cnt;
+                }
+            }
+            else if (!solo_insert_sequential(nodes, closed, heap, needmask, cur, n_nodes, L.node_cap, idx, g, h, nx, ny, nyaw, ns, nc, steer, direc))
+                overflow = true;
+            __syncwarp();
+        }
+        // end of an expansion (inserts done, or nothing to insert): overflow, stop radius, ++iteration (:725-745)
+        if (exp_done)
+        {
+            if (overflow)
+            {
+                // The query outgrew the small workspace. Undo the pop (same key, same id: the open list is as it was but for
+                // CLOSE entries dropped on the way, which no pop would ever have returned) and hand the query over with its
+                // state; without a free workspace to go on with, the team pass starts it afresh.
+                if (lane == 0)
+                    heap_push_lane0(heap, cur_key, cur);
+                heap.size++;
+                __syncwarp();
+                --n_exp;
+                n_coll -= P + exp_checked; // the team pass repeats this step, shot included
+                n_shots -= exp_shots;
+                if (a.handoff_ws && squad_hand_over(a, S, heap, q, ws_slot, gen, n_nodes, iteration, n_shots, n_exp, n_coll, goal_found, goal_parent,
+                                                    goal_g, si, sj))
+                {
+                    bind_ws();
+                    finish = kHandOff;
+                }
+                else
+                    finish = ST_OVERFLOW;
+            }
+            else if (a.optimal && dm::hypot_(S.gx - cn_x, S.gy - cn_y) <= 1.0) // stop_radius (hybrid_a_star.h:345)
+                finish = goal_found ? ST_FOUND : ST_OPEN_EMPTY;
+            else
+                ++iteration;
+        }
+
+        if (finish != 0x7fffffff)
+        {
+            // ---- the query ends: hand-off, or status + raw path_ of setPath (hybrid_a_star.cpp:779-811)
+            if (finish == kHandOff)
+            {
+                // squad_hand_over has listed the query
+            }
+            else if (finish == ST_OVERFLOW && a.handoff)
+            {
+                if (lane == 0)
+                {
+                    const unsigned at = atomicAdd(a.handoff_n, 1u);
+                    a.handoff[at] = q;
+                    if (a.handoff_ws)
+                        a.handoff_ws[at] = -1;
+                    a.status[q] = ST_OVERFLOW;
+                }
+            }
+            else
+            {
+                int out_len = 0;
+                if (finish == ST_FOUND)
+                    out_len = solo_write_path(a, S, nodes, goal_parent, q, scratch);
+                if (lane == 0)
+                {
+                    a.status[q] = finish;
+                    a.cost[q] = (finish == ST_FOUND) ? goal_g : -1.0;
+                    a.path_len[q] = out_len;
+                    if (a.stats)
+                    {
+                        const bool init = finish != ST_NOT_INIT;
+                        a.stats[6 * q + 0] = iteration;
+                        a.stats[6 * q + 1] = n_exp * P;
+                        a.stats[6 * q + 2] = n_shots;
+                        a.stats[6 * q + 3] = n_coll;
+                        a.stats[6 * q + 4] = init ? S.bfs.cells : 0;
+                        a.stats[6 * q + 5] = n_nodes;
+                    }
+                }
+            }
+            __syncwarp();
+            state = IDLE;
+            q = -1;
+        }
+        pf.mark(7);
+        if (all_done)
+            break;
+    }
+    pf.flush();
+    __syncwarp();
+    if (ws_slot >= 0 && lane == 0)
+        pool_release(a.solo_pool, ws_slot, gen);
+}
+
+} // namespace mpros

@@ -123,6 +123,64 @@ __device__ __forceinline__ void pool_release(const WorkspacePool &pl, int i, uin
     atomicExch(&pl.owner[i], 0);
 }
 
+// Non-blocking form for a whole warp that wants to put its present workspace into custody (see WorkspacePool::custody) and
+// go on with another one: -1 when the custody limit is reached. Below the limit a free workspace exists; the 32 lanes look
+// for it together.
+__device__ __forceinline__ int pool_swap_acquire_warp(const WorkspacePool &pl, int first)
+{
+    const int lane = threadIdx.x & 31;
+    int ok = 0;
+    if (lane == 0)
+    {
+        ok = atomicAdd(pl.custody, 1) < pl.custody_max;
+        if (!ok)
+            atomicSub(pl.custody, 1);
+    }
+    if (!__shfl_sync(0xffffffffu, ok, 0))
+        return -1;
+    int base = first % pl.n;
+    while (true)
+    {
+        int i = base + lane;
+        i = i >= pl.n ? i - pl.n : i;
+        const bool free_seen = lane < pl.n && *reinterpret_cast<volatile int *>(&pl.owner[i]) == 0;
+        unsigned cand = __ballot_sync(0xffffffffu, free_seen);
+        int got = -1;
+        while (cand && got < 0)
+        {
+            const int l = __ffs(cand) - 1;
+            cand &= cand - 1;
+            int mine = -1;
+            if (lane == l && atomicCAS(&pl.owner[i], 0, 1) == 0)
+                mine = i;
+            got = __shfl_sync(0xffffffffu, mine, l);
+        }
+        if (got >= 0)
+        {
+            __threadfence();
+            return got;
+        }
+        base = base + 32 >= pl.n ? base + 32 - pl.n : base + 32;
+    }
+}
+
+// State of a query that the squad pass (plan_squad.cuh) hands to the team pass TOGETHER with its workspace: the search goes
+// on where it stopped, between two iterations. The node pool, the open list (complete in the global arrays), the closed set
+// and the goal-wavefront window are in the small workspace; this header (at WarpWorkspaceLayout::hdr_off) holds the rest.
+struct ResumeHeader
+{
+    uint32_t tag, gen; // closed-set tag of the query in the small workspace; generation counter to release the workspace with
+    int heap_size;
+    uint32_t n_nodes;
+    int iteration, n_shots, goal_found;
+    uint32_t goal_parent;
+    long long n_exp, n_coll;
+    double goal_g;
+    int si, sj;
+    TeamBfs bfs; // pointers refer to the small workspace
+};
+static_assert(sizeof(ResumeHeader) <= 512, "ResumeHeader does not fit the layout's header region");
+
 // A CTA holds one team (plan_team_kernel, plan_cluster_kernel) or two (plan_duo_kernel); everything below addresses threads
 // and barriers relative to the team: thread index 0 .. NW*32-1, named barriers 1 + 3 t (whole team), 2 + 3 t (compute group:
 // every warp except the heap warp), 3 + 3 t (footprint warps -> closed-set warp, one way), t = team index inside the CTA.
@@ -851,12 +909,120 @@ __device__ __forceinline__ int open_argmin(unsigned long long key, uint32_t id, 
     return __ffs(__ballot_sync(kFull, a2 && id == m3)) - 1;
 }
 
+// Take over a query from the squad pass: copy its state from the small workspace `src` into this team's workspace (node
+// pool and open list as they are - both heaps are the same implicit 32-ary layout, only the number of entries kept in shared
+// memory differs -, the closed set re-hashed into the bigger table under this team's tag, the initialised rows of the
+// wavefront window) and give the small workspace back to its pool. All threads of the team.
+template <int NW>
+__device__ __noinline__ void team_resume(const PlanBatchArgs &a, int ws_small, char *ws, uint32_t tag, TeamShared<NW> &S, int &heap_size, int P)
+{
+    const int tid = team_tid<NW>(), NT = NW * 32;
+    const WarpWorkspaceLayout &L = a.L, &Ls = a.Ls;
+    const char *src = a.solo_pool.base + (size_t)ws_small * Ls.stride;
+    const ResumeHeader *H = reinterpret_cast<const ResumeHeader *>(src + Ls.hdr_off);
+    const uint32_t n_nodes = H->n_nodes;
+    const int hsize = H->heap_size;
+    {
+        const uint4 *sn = reinterpret_cast<const uint4 *>(src + Ls.node_off);
+        uint4 *dn = reinterpret_cast<uint4 *>(ws + L.node_off);
+        for (size_t k = tid; k < (size_t)n_nodes * (sizeof(PlanNode) / 16); k += NT)
+            dn[k] = sn[k];
+    }
+    {
+        const unsigned long long *sk = reinterpret_cast<const unsigned long long *>(src + Ls.hkey_off);
+        const uint32_t *sid = reinterpret_cast<const uint32_t *>(src + Ls.hid_off);
+        unsigned long long *dk = reinterpret_cast<unsigned long long *>(ws + L.hkey_off);
+        uint32_t *did = reinterpret_cast<uint32_t *>(ws + L.hid_off);
+        for (int k = tid; k < hsize; k += NT)
+        {
+            if (k < kHeapTop)
+                S.heap_key[k] = sk[k], S.heap_id[k] = sid[k];
+            else
+                dk[k] = sk[k], did[k] = sid[k];
+        }
+    }
+    {
+        // closed set: every live slot of the small table goes into the big one (distinct keys; a slot is claimed with a
+        // compare-and-swap on its key word, so an entry lands on the first slot of its probe sequence that was not taken)
+        const ClosedSlot *st = reinterpret_cast<const ClosedSlot *>(src + Ls.table_off);
+        ClosedSlot *dt = reinterpret_cast<ClosedSlot *>(ws + L.table_off);
+        const uint32_t dmask = (uint32_t)L.table_slots - 1;
+        const unsigned long long old_tag = H->tag, new_tag = tag;
+        for (int k = tid; k < Ls.table_slots; k += NT)
+        {
+            const ClosedSlot e = st[k];
+            if ((e.key >> 34) != old_tag)
+                continue;
+            const unsigned long long idx = e.key & ((1ull << 34) - 1ull);
+            const unsigned long long want = (new_tag << 34) | idx;
+            uint32_t sl = hash_index(idx) & dmask;
+            while (true)
+            {
+                const unsigned long long cur = dt[sl].key;
+                if ((cur >> 34) != new_tag && atomicCAS(&dt[sl].key, cur, want) == cur)
+                    break;
+                sl = (sl + 1) & dmask;
+            }
+            dt[sl].g = e.g;
+            dt[sl].node = e.node;
+        }
+    }
+    {
+        // goal wavefront: the rows initialised so far (same window geometry: it depends on the map and the goal only)
+        const TeamBfs &b = H->bfs;
+        if (b.ilo <= b.ihi)
+        {
+            const size_t w0 = (size_t)(b.ilo - b.r0) * b.wwords, nw = (size_t)(b.ihi - b.ilo + 1) * b.wwords;
+            const uint32_t *sb = reinterpret_cast<const uint32_t *>(src + Ls.blocked_off), *s0 = reinterpret_cast<const uint32_t *>(src + Ls.f0_off),
+                           *s1 = reinterpret_cast<const uint32_t *>(src + Ls.f1_off);
+            uint32_t *db = reinterpret_cast<uint32_t *>(ws + L.blocked_off), *d0 = reinterpret_cast<uint32_t *>(ws + L.f0_off),
+                     *d1 = reinterpret_cast<uint32_t *>(ws + L.f1_off);
+            const uint4 *sd = reinterpret_cast<const uint4 *>(src + Ls.dist_off);
+            uint4 *dd = reinterpret_cast<uint4 *>(ws + L.dist_off);
+            for (size_t k = tid; k < nw; k += NT)
+            {
+                db[w0 + k] = sb[w0 + k];
+                d0[w0 + k] = s0[w0 + k];
+                d1[w0 + k] = s1[w0 + k];
+            }
+            for (size_t k = tid; k < nw * 4; k += NT) // 32 x uint16 per word = 4 x 16 bytes
+                dd[w0 * 4 + k] = sd[w0 * 4 + k];
+        }
+    }
+    if (tid == 0)
+    {
+        const TeamBfs keep = S.bfs; // this team's pointers
+        S.bfs = H->bfs;
+        S.bfs.blocked = keep.blocked, S.bfs.f0 = keep.f0, S.bfs.f1 = keep.f1, S.bfs.dist = keep.dist;
+        S.bfs.tag = tag;
+        S.si = H->si, S.sj = H->sj, S.gi = H->bfs.gi, S.gj = H->bfs.gj;
+        S.iteration = H->iteration;
+        S.n_nodes = n_nodes;
+        S.n_prim = H->n_exp * P;
+        S.n_shots = H->n_shots;
+        S.n_coll = H->n_coll;
+        S.goal_found = H->goal_found;
+        S.goal_parent = H->goal_parent;
+        S.goal_g = H->goal_g;
+        S.init_ok = 1;
+    }
+    heap_size = hsize;
+    const uint32_t gen_small = H->gen;
+    __threadfence();
+    team_sync_all<NW>(); // every thread has read what it needs from the small workspace
+    if (tid == 0)
+    {
+        pool_release(a.solo_pool, ws_small, gen_small);
+        atomicSub(a.solo_pool.custody, 1);
+    }
+}
+
 #ifndef MPROS_DUO_WAIT
 #define MPROS_DUO_WAIT 6000 // cycles a team waits at most for its partner at the top of an iteration (plan_duo_kernel)
 #endif
 template <int NW, bool CL>
 __device__ void plan_team_query(const MapView &m, const PlannerView &p, const PlanBatchArgs &a, int q, char *ws, uint32_t tag,
-                                TeamShared<NW> &S, HeurShared *Hpeer, DuoSync *D = nullptr)
+                                TeamShared<NW> &S, HeurShared *Hpeer, DuoSync *D = nullptr, int ws_small = -1)
 {
     const int tid = team_tid<NW>(), warp = tid >> 5, lane = tid & 31;
 
@@ -908,8 +1074,11 @@ __device__ void plan_team_query(const MapView &m, const PlannerView &p, const Pl
     }
     team_sync_all<NW>();
 
+    // ---- a query handed over by the squad pass goes on from its state; otherwise:
     // ---- initialize (hybrid_a_star.cpp:52-118), compute group only; the heap warp waits at the barrier below ----
-    if (!is_heap)
+    if (ws_small >= 0)
+        team_resume<NW>(a, ws_small, ws, tag, S, heap.size, 2 * p.n_steer);
+    else if (!is_heap)
     {
         if (warp < 2)
         {
@@ -1621,16 +1790,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) plan_team_kernel(const __grid_c
                                                                    const __grid_constant__ PlanBatchArgs a)
 {
     __shared__ TeamShared<NW> S;
-    if (team_tid<NW>() == 0)
-    {
-        S.ws_slot = pool_acquire(a.pool, (int)blockIdx.x);
-        S.ws_gen = a.pool.gen[S.ws_slot];
-    }
-    team_sync_all<NW>();
-    const int slot = S.ws_slot;
-    char *ws = a.pool.base + (size_t)slot * a.L.stride;
-    uint32_t gen = S.ws_gen;
-    const int total = a.todo ? a.n_todo : a.nq;
+    // a workspace is taken with the first ticket: the CTAs of a pass that finds its hand-off list (nearly) empty leave at once
+    // instead of waiting for workspaces other batches hold
+    int slot = -1;
+    char *ws = nullptr;
+    uint32_t gen = 0;
+    const int total = a.n_todo_dev ? (int)*a.n_todo_dev : (a.todo ? a.n_todo : a.nq);
     while (true)
     {
         team_sync_all<NW>();
@@ -1640,12 +1805,25 @@ __global__ void __launch_bounds__(NW * 32, MINB) plan_team_kernel(const __grid_c
         const int t = S.q;
         if (t >= total)
             break;
+        if (slot < 0)
+        {
+            if (team_tid<NW>() == 0)
+            {
+                S.ws_slot = pool_acquire(a.pool, (int)blockIdx.x);
+                S.ws_gen = a.pool.gen[S.ws_slot];
+            }
+            team_sync_all<NW>();
+            slot = S.ws_slot;
+            ws = a.pool.base + (size_t)slot * a.L.stride;
+            gen = S.ws_gen;
+        }
         int q = a.todo ? a.todo[t] : t;
+        const int ws_small = a.todo_ws ? a.todo_ws[t] : -1;
         ++gen;
-        plan_team_query<NW, false>(m, p, a, q, ws, gen, S, nullptr);
+        plan_team_query<NW, false>(m, p, a, q, ws, gen, S, nullptr, nullptr, ws_small);
     }
     team_sync_all<NW>();
-    if (team_tid<NW>() == 0)
+    if (slot >= 0 && team_tid<NW>() == 0)
         pool_release(a.pool, slot, gen);
 }
 

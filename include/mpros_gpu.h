@@ -117,7 +117,10 @@ MPROS_API uint64_t mpros_ctx_launch_count(mpros_ctx *ctx);
  *   "c1_mode"   "2phase" (default) | "2phase_ldg" | "walk" footprint kernel: pre-classified two-phase form with the pose stream
  *                                                          staged by cp.async.bulk / the same without staging / plain probe walk
  *   "goal_mode" "cluster" (default) | "cluster8" | "grid"  N4 wavefront: 16-CTA cluster when granted / 8-CTA cluster / cooperative grid
- *   "plan_mode" "team" (default) | "cluster"               planner team = one CTA / a CTA pair on the two SMs of a TPC
+ *   "plan_mode" "solo" (default) | "team" | "cluster" | "duo"  planner: warp-per-query pass, then the team kernel for the queries
+ *                                                          that outgrow its workspaces / team kernel only (one CTA per query) /
+ *                                                          a CTA pair on the two SMs of a TPC / two teams per CTA
+ *   "solo_nodes" node-pool size of a solo workspace (default 32768)
  *   "debug"     "0" (default) | "1"                        per-pass timing on stderr
  * Results never depend on these switches (tests/ hold every mode to the same outputs). No reference counterpart. */
 MPROS_API int mpros_ctx_set_option(mpros_ctx *ctx, const char *key, const char *value);

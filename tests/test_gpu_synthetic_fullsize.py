@@ -247,6 +247,43 @@ def test_full_batch_properties(syn):
     assert not ctx.collision_check(poses).any(), "a returned path collides"
 
 
+def test_solo_and_team_passes_give_identical_plans(syn):
+    """Default planner = warp-per-query pass (squads of 24 queries per CTA whose heuristics the whole CTA evaluates) + team
+    pass for the queries that outgrow the small workspaces. Every
+    output (status, cost, path, all six statistics) equals the team kernel's alone, bit for bit - with the default solo
+    workspaces and with tiny ones that hand most of the batch over."""
+    ctx, params, occ, starts, goals = syn
+    keys = ["status", "cost", "path_len", "iterations", "primitives", "rs_shots", "collision_checks", "goal_map_cells", "nodes_inserted"]
+
+    def same(a, b, what):
+        for key in keys:
+            assert np.array_equal(a[key], b[key]), "%s: %s differs for queries %s" % (what, key, np.nonzero(a[key] != b[key])[0][:8])
+        valid = np.arange(a["paths"].shape[1])[None, :] < np.minimum(a["path_len"], a["paths"].shape[1])[:, None]
+        assert np.array_equal(a["paths"][valid], b["paths"][valid]), what
+
+    n = 4096
+    try:
+        ctx.set_option("plan_mode", "team")
+        team = ctx.plan_batch(starts, goals, path_cap=128)
+        ctx.set_option("plan_mode", None)
+        solo = ctx.plan_batch(starts, goals, path_cap=128)
+        same(team, solo, "default solo workspaces")
+        ctx.set_option("solo_nodes", 512)
+        tiny = ctx.plan_batch(starts[:n], goals[:n], path_cap=128)
+        same({k: v[:n] for k, v in team.items()}, tiny, "solo workspaces of 512 nodes")
+        ctx.set_option("solo_nodes", None)
+        ctx.set_option("plan_mode", "solo_warp")  # independent warps instead of squads (the form for more than 8 primitives)
+        warp = ctx.plan_batch(starts[:n], goals[:n], path_cap=128)
+        same({k: v[:n] for k, v in team.items()}, warp, "plan_solo_kernel")
+    finally:
+        ctx.set_option("plan_mode", None)
+        ctx.set_option("solo_nodes", None)
+    it = team["iterations"]
+    print("nodes inserted per iteration: mean %.2f, 99th percentile %.2f; queries with more than 32768 nodes: %d" % (
+        team["nodes_inserted"].sum() / max(1, it.sum()), np.percentile(team["nodes_inserted"] / np.maximum(it, 1), 99),
+        int((team["nodes_inserted"] > 32768).sum())))
+
+
 def test_batches_in_flight_match_the_synchronous_call(syn):
     """mpros_plan_batch_submit[_dev] / mpros_plan_batch_wait: batches in flight on all eight lanes (own streams and staging
     areas, ONE workspace pool of the context: a team takes a free workspace when its CTA starts) give exactly the per-query
