@@ -103,7 +103,7 @@ struct PlanBatchArgs
 // Phase profile of the team planner (developer build only: make PROFILE=1). Cycle counts are taken by thread 0 of the
 // compute group and lane 0 of the heap warp and summed over all queries.
 #ifdef MPROS_PROFILE
-__device__ unsigned long long g_prof[24];
+__device__ unsigned long long g_prof[32];
 struct Prof
 {
     long long t0;
@@ -1189,16 +1189,28 @@ static int plan_solo_pass(mpros_ctx *c, int lane, cudaStream_t stream, PlanBatch
 #ifdef MPROS_PROFILE
         if (squad)
         {
-            unsigned long long h[24];
+            unsigned long long h[32];
             cudaMemcpyFromSymbol(h, g_prof, sizeof(h));
-            unsigned long long z[24] = {0};
+            unsigned long long z[32] = {0};
             cudaMemcpyToSymbol(g_prof, z, sizeof(z));
             const double wr = (double)std::max<unsigned long long>(1, h[8]);
-            const char *names[8] = {"own step", "wait (1)", "round A", "wait (2)", "skip + wait (3)", "round B", "wait (4)", "inserts"};
+            const char *names[8] = {"own steps", "wait (1)", "round A", "wait (2)", "skip + wait (3)", "round B", "wait (4)", "inserts"};
+            std::fprintf(stderr, "[mpros]   wait (w1) %9.1f, walk pass %9.1f, wait (w2) %9.1f\n", h[24] / wr, h[25] / wr, h[26] / wr);
             std::fprintf(stderr, "[mpros] squad profile: %.0f warp-rounds; per warp-round: expansions %.3f, requests %.3f, round-B requests %.3f, round B present %.3f, waiting for the goal map %.3f, idle/done %.3f, init %.3f, shots %.4f; cycles per warp-round:\n",
                          wr, h[12] / wr, h[10] / wr, h[11] / wr, h[9] / wr, h[13] / wr, h[14] / wr, h[16] / wr, h[15] / wr);
             for (int k = 0; k < 8; ++k)
                 std::fprintf(stderr, "[mpros]   %-16s %9.1f\n", names[k], h[k] / wr);
+            {
+                unsigned long long hh[64];
+                cudaMemcpyFromSymbol(hh, g_prof_hist, sizeof(hh));
+                unsigned long long zz[64] = {0};
+                cudaMemcpyToSymbol(g_prof_hist, zz, sizeof(zz));
+                const char *cause[7] = {"plain expansion", "stale pops", ">= 2 probe walks", "wavefront steps", "shot", "query start", "no work"};
+                std::fprintf(stderr, "[mpros]   own step by cause, share of warp-rounds with < 16 k / < 32 k / < 64 k / < 128 k / more cycles:\n");
+                for (int k = 0; k < 7; ++k)
+                    std::fprintf(stderr, "[mpros]     %-18s %7.4f %7.4f %7.4f %7.4f %7.4f\n", cause[k], hh[5 * k] / wr, hh[5 * k + 1] / wr, hh[5 * k + 2] / wr,
+                                 hh[5 * k + 3] / wr, hh[5 * k + 4] / wr);
+            }
             const char *sub[6] = {"pop (+ stale)", "node, primitives", "pre-classification", "probe walks", "closed set, g", "goal-map values"};
             const double ex = (double)std::max<unsigned long long>(1, h[12]);
             std::fprintf(stderr, "[mpros]   inside the own step, cycles per EXPANSION:\n");

@@ -27,7 +27,9 @@ namespace mpros
 {
 
 constexpr int kSquadMaxReq = 8;    // children of one expansion that can ask for a heuristic (2 * n_steer <= 8; else plan_solo_kernel)
-constexpr int kSquadBfsSteps = 16; // goal-wavefront levels one warp advances per round at most
+constexpr int kSquadBfsSteps = 4;  // goal-wavefront levels one warp advances per round at most ...
+constexpr int kSquadBfsWords = 256; // ... and no further level once that many words have been scanned in the round
+constexpr int kSquadPops = 2;      // open-list entries one warp removes per round at most (CLOSE entries cost a removal each)
 constexpr int kHandOff = 0x7ffffffe; // `finish` value: the query goes to the team pass together with its state
 
 struct SquadReq
@@ -45,9 +47,12 @@ struct SquadShared
     SquadReq req[W * kSquadMaxReq]; // slots w * kSquadMaxReq .. belong to warp w
     short list_a[W * kSquadMaxReq]; // posted slots of this round
     short list_b[W * kSquadMaxReq]; // slots that need round B
+    // end poses whose footprint test needs the probe walk (not decided by their own cell), and the verdicts
+    double walk[W * kSquadMaxReq][4]; // {x, y, sin yaw, cos yaw}
+    unsigned char walk_hit[W * kSquadMaxReq];
     // counters of round r live at index r % 3: thread 0 clears the set of round r + 1 before barrier (1) of round r, when the
     // last readers (round r - 2) are long gone and the next writers (round r + 1) have not started
-    int n_a[3], n_b[3], n_done[3];
+    int n_a[3], n_b[3], n_done[3], n_w[3];
 };
 
 // Phase profile of the squad kernel (developer build, -DMPROS_PROFILE): lane 0 of every warp sums cycles per phase in
@@ -55,14 +60,26 @@ struct SquadShared
 // 4 skip rule + wait (3), 5 round B, 6 wait (4), 7 inserts / results; counters: 8 warp-rounds, 9 warp-rounds with a round B,
 // 10 requests, 11 round-B requests, 12 expansions, 13 warp-rounds waiting for a goal-map value, 14 idle / done warp-rounds,
 // 15 shots, 16 warp-rounds in INIT.
+#ifdef MPROS_PROFILE
+__device__ unsigned long long g_prof_hist[64]; // own-step duration of a warp-round: 8 causes x 5 duration classes (see SquadProf::hist)
+#endif
 struct SquadProf
 {
 #ifdef MPROS_PROFILE
-    unsigned long long acc[24];
+    // what made this warp-round's own step long? cause: 0 plain expansion, 1 stale pops, 2 >= 2 probe walks, 3 wavefront steps,
+    // 4 shot, 5 query start (ticket / init), 6 no work; duration classes < 16 k, < 32 k, < 64 k, < 128 k, >= 128 k cycles
+    __device__ __forceinline__ void hist(int cause)
+    {
+        const long long d = Prof::now() - t0;
+        const int b = d < 16384 ? 0 : d < 32768 ? 1 : d < 65536 ? 2 : d < 131072 ? 3 : 4;
+        if ((threadIdx.x & 31) == 0)
+            atomicAdd(&g_prof_hist[cause * 5 + b], 1ull);
+    }
+    unsigned long long acc[32];
     long long t0;
     __device__ __forceinline__ void init()
     {
-        for (int k = 0; k < 24; ++k)
+        for (int k = 0; k < 32; ++k)
             acc[k] = 0;
         t0 = Prof::now();
     }
@@ -85,10 +102,11 @@ struct SquadProf
     __device__ __forceinline__ void flush()
     {
         if ((threadIdx.x & 31) == 0)
-            for (int k = 0; k < 24; ++k)
+            for (int k = 0; k < 32; ++k)
                 atomicAdd(&g_prof[k], acc[k]);
     }
 #else
+    __device__ __forceinline__ void hist(int) {}
     __device__ __forceinline__ void init() {}
     __device__ __forceinline__ void mark(int) {}
     __device__ __forceinline__ void add(int, unsigned long long) {}
@@ -137,7 +155,7 @@ __device__ __forceinline__ double squad_heuristics(const MapView &m, const Plann
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cur3 = rnd % 3, nxt3 = (rnd + 1) % 3;
     if (threadIdx.x == 0)
-        S.n_a[nxt3] = 0, S.n_b[nxt3] = 0, S.n_done[nxt3] = 0;
+        S.n_a[nxt3] = 0, S.n_b[nxt3] = 0, S.n_done[nxt3] = 0, S.n_w[nxt3] = 0;
     const bool mine = (needmask >> lane) & 1u;
     const int rank = __popc(needmask & ((1u << lane) - 1u)), cnt = __popc(needmask);
     const int slot = warp * kSquadMaxReq + rank;
@@ -212,15 +230,57 @@ __device__ __forceinline__ double squad_heuristics(const MapView &m, const Plann
     return h;
 }
 
+// The probe walks of a round, whole CTA: every warp posts the end poses its own pre-classification left undecided
+// (walk_mask, lane = child), the poses are walked one per warp (warp_footprint_collision: one lane per probe) whoever
+// posted them, and every warp gets the verdicts of its children back as a mask of FREE poses. A warp with six undecided
+// children no longer holds up the other 23: the round's walks take the time of one or two. Every warp of the CTA calls this
+// exactly once per round.
+template <int W>
+__device__ __forceinline__ unsigned squad_walks(const MapView &m, const PlannerView &p, SquadShared<W> &S, unsigned walk_mask, double x, double y,
+                                                double sn, double cs, int rnd, SquadProf &pf)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cur3 = rnd % 3;
+    const bool mine = (walk_mask >> lane) & 1u;
+    const int rank = __popc(walk_mask & ((1u << lane) - 1u)), cnt = __popc(walk_mask);
+    int base = 0;
+    if (lane == 0 && cnt)
+        base = atomicAdd(&S.n_w[cur3], cnt);
+    base = __shfl_sync(kFull, base, 0);
+    if (mine)
+    {
+        double *o = S.walk[base + rank];
+        o[0] = x, o[1] = y, o[2] = sn, o[3] = cs;
+    }
+    pf.mark(0);
+    __syncthreads(); // (w1) every pose of this round is posted
+    pf.mark(24);
+    const int n_w = S.n_w[cur3];
+    if (n_w == 0)
+        return 0u;
+    for (int i = warp; i < n_w; i += W)
+    {
+        const double *r = S.walk[i];
+        const bool hit = warp_footprint_collision(m, p, r[0], r[1], r[2], r[3]);
+        if (lane == 0)
+            S.walk_hit[i] = hit;
+    }
+    pf.mark(25);
+    __syncthreads(); // (w2)
+    pf.mark(26);
+    return __ballot_sync(kFull, mine && !S.walk_hit[base + rank]);
+}
+
 // goal-map values with a bounded number of wavefront steps; final = every requested value is known
-__device__ __forceinline__ int squad_h1_lookup(const MapView &m, TeamBfs &b, bool want, int i, int j, int &v, int max_steps)
+__device__ __forceinline__ int squad_h1_lookup(const MapView &m, TeamBfs &b, bool want, int i, int j, int &v, int max_steps, int &steps)
 {
     if (want && v < 0)
         v = team_bfs_peek(m, b, i, j);
-    int steps = 0;
-    while (__any_sync(kFull, want && v < 0) && steps < max_steps)
+    steps = 0;
+    int words = 0;
+    while (__any_sync(kFull, want && v < 0) && steps < max_steps && words < kSquadBfsWords)
     {
-        solo_bfs_step(m, b);
+        words += solo_bfs_step(m, b);
         ++steps;
         if (want && v < 0)
             v = team_bfs_peek(m, b, i, j);
@@ -283,7 +343,7 @@ __global__ void __launch_bounds__(32 * W, MINB) plan_squad_kernel(const __grid_c
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     SoloShared &S = SQ.q[warp];
     if (threadIdx.x < 3)
-        SQ.n_a[threadIdx.x] = 0, SQ.n_b[threadIdx.x] = 0, SQ.n_done[threadIdx.x] = 0;
+        SQ.n_a[threadIdx.x] = 0, SQ.n_b[threadIdx.x] = 0, SQ.n_done[threadIdx.x] = 0, SQ.n_w[threadIdx.x] = 0;
     __syncthreads();
     const WarpWorkspaceLayout &L = a.Ls;
     const int P = 2 * p.n_steer;
@@ -342,6 +402,10 @@ __global__ void __launch_bounds__(32 * W, MINB) plan_squad_kernel(const __grid_c
         // ================= phase 1: every warp advances its own query =================
         unsigned needmask = 0; // children (or the start node, lane 0) posted for a heuristic in this round
         bool post_start = false;
+        int r_bfs = 0, r_stale = 0, r_walks = 0, r_cause = 6; // profile: what this warp's step consisted of
+        bool fresh = false;                      // a node was popped for expansion in this round
+        unsigned free_mask = 0, walk_mask = 0;   // its children: end pose surely free / undecided (lane = primitive)
+        PlanNode cn;                             // the popped node
         bool exp_done = false;   // an expansion completes in this round: its children are inserted in phase 5
         int finish = 0x7fffffff; // status to report when the query ends in this round (0x7fffffff: it goes on)
         if (state == IDLE)
@@ -411,7 +475,7 @@ __global__ void __launch_bounds__(32 * W, MINB) plan_squad_kernel(const __grid_c
         else if (state == INIT)
         {
             // start node: steer 0, direction 1, g = 0 (:83, :211-215); its heuristic goes through the CTA's rounds like a child's
-            if (squad_h1_lookup(m, S.bfs, lane == 0, si, sj, h1, kSquadBfsSteps))
+            if (squad_h1_lookup(m, S.bfs, lane == 0, si, sj, h1, kSquadBfsSteps, r_bfs))
             {
                 h1 = __shfl_sync(kFull, h1, 0);
                 dm::sincos_(S.gyaw - S.syaw, &sphi, &cphi);
@@ -422,7 +486,6 @@ __global__ void __launch_bounds__(32 * W, MINB) plan_squad_kernel(const __grid_c
         }
         else if (state == RUN || state == WAIT_H1)
         {
-            bool expanding = state == WAIT_H1;
             // Tail of the batch: the tickets have run out and most warps of this CTA are done. The queries still running are
             // the long ones; a whole team finishes them faster than a nearly empty squad, and the team pass cannot start before
             // this kernel has ended: hand them over, state and all.
@@ -434,11 +497,11 @@ __global__ void __launch_bounds__(32 * W, MINB) plan_squad_kernel(const __grid_c
             }
             else if (state == RUN)
             {
-                // ---- Plan() (hybrid_a_star.cpp:682-777): next open node that is not CLOSE
+                // ---- Plan() (hybrid_a_star.cpp:682-777): next open node that is not CLOSE (at most kSquadPops removals per round:
+                // a run of CLOSE entries is finished in the next one)
                 bool have = false;
-                PlanNode cn;
                 pf.sub0();
-                while (heap.size > 0)
+                for (int pops = 0; heap.size > 0 && pops < kSquadPops; ++pops)
                 {
                     if (iteration > p.max_iteration)
                     {
@@ -452,8 +515,9 @@ __global__ void __launch_bounds__(32 * W, MINB) plan_squad_kernel(const __grid_c
                         have = true;
                         break;
                     }
+                    ++r_stale;
                 }
-                if (!have && finish == 0x7fffffff)
+                if (!have && finish == 0x7fffffff && heap.size == 0)
                     finish = goal_found ? ST_FOUND : ST_OPEN_EMPTY;
                 pf.sub(17);
                 if (have)
@@ -493,7 +557,7 @@ __global__ void __launch_bounds__(32 * W, MINB) plan_squad_kernel(const __grid_c
                     else
                     {
                         // -- expandNode (:304-402), lane = primitive; lanes P..2P-1 shadow the children for the second sin/cos pair
-                        expanding = true;
+                        fresh = true;
                         ++n_exp;
                         n_coll += P;
                         const int c = lane < P ? lane : (lane < 2 * P ? lane - P : 0);
@@ -504,37 +568,47 @@ __global__ void __launch_bounds__(32 * W, MINB) plan_squad_kernel(const __grid_c
                         sphi = __shfl_sync(kFull, ns, (lane + P) & 31);
                         cphi = __shfl_sync(kFull, nc, (lane + P) & 31);
                         pf.sub(18);
+                        // footprint tests: most end poses are decided by their own cell, the others go to the CTA's walk pass
                         const int cls = lane < P ? footprint_preclass(m, p, a.unsafe_tw, a.center_probe, nx, ny, nyaw) : 1;
-                        unsigned free_mask = __ballot_sync(kFull, cls == 0);
-                        unsigned walk_mask = __ballot_sync(kFull, cls == 2);
+                        free_mask = __ballot_sync(kFull, cls == 0);
+                        walk_mask = __ballot_sync(kFull, cls == 2);
+                        r_walks = __popc(walk_mask);
                         pf.sub(19);
-                        while (walk_mask)
-                        {
-                            const int t = __ffs(walk_mask) - 1;
-                            walk_mask &= walk_mask - 1;
-                            if (!warp_footprint_collision(m, p, __shfl_sync(kFull, nx, t), __shfl_sync(kFull, ny, t), __shfl_sync(kFull, ns, t),
-                                                          __shfl_sync(kFull, nc, t)))
-                                free_mask |= 1u << t;
-                        }
-                        pf.sub(20);
-                        need = false, pr_found = false, pr_old = kNoNode, pr_slot = 0xffffffffu - lane, idx = 0, ci = -1, cj = -1, g = 0, pr_old_cost = 0;
-                        if (lane < P && ((free_mask >> lane) & 1u) && pos_to_index_ds(m, nx, ny, ci, cj))
-                        {
-                            const float voro_f = __ldg(m.voronoi + (size_t)ci * m.W + cj);
-                            idx = cal_index(m, p, ci, cj, yaw_to_idx(p, nyaw), direc);
-                            pr_slot = closed_find(closed, idx, pr_found, pr_old_cost, pr_old);
-                            g = node_cost(p, cn.g, (double)cn.dir, cn.steer, (double)voro_f, steer, direc);
-                            need = pr_old_cost > g; // an earlier sibling on the same slot may still beat it; resolved at insert
-                        }
-                        h1 = -1;
-                        pf.sub(21);
                     }
                 }
+            }
+        }
+
+        r_cause = state == DONE ? 6 : (state == INIT || state == IDLE || finish == ST_NOT_INIT) ? 5 : (exp_shots && !fresh) ? 4 : r_bfs ? 3 : r_stale ? 1 : (fresh ? 0 : 6);
+        pf.hist(r_cause);
+        // ================= phase 1w: the probe walks of every warp's undecided end poses, whole CTA =================
+        free_mask |= squad_walks<W>(m, p, SQ, walk_mask, nx, ny, ns, nc, rnd, pf);
+
+        // ================= phase 1b: closed set, g, goal-map values =================
+        if (state == RUN || state == WAIT_H1)
+        {
+            bool expanding = state == WAIT_H1;
+            if (fresh)
+            {
+                expanding = true;
+                pf.sub0();
+                // node cell, closed-set entry, g (lane = child)
+                need = false, pr_found = false, pr_old = kNoNode, pr_slot = 0xffffffffu - lane, idx = 0, ci = -1, cj = -1, g = 0, pr_old_cost = 0;
+                if (lane < P && ((free_mask >> lane) & 1u) && pos_to_index_ds(m, nx, ny, ci, cj))
+                {
+                    const float voro_f = __ldg(m.voronoi + (size_t)ci * m.W + cj);
+                    idx = cal_index(m, p, ci, cj, yaw_to_idx(p, nyaw), direc);
+                    pr_slot = closed_find(closed, idx, pr_found, pr_old_cost, pr_old);
+                    g = node_cost(p, cn.g, (double)cn.dir, cn.steer, (double)voro_f, steer, direc);
+                    need = pr_old_cost > g; // an earlier sibling on the same slot may still beat it; resolved at insert
+                }
+                h1 = -1;
+                pf.sub(21);
             }
             if (expanding)
             {
                 pf.sub0();
-                const bool h1_final = squad_h1_lookup(m, S.bfs, need, ci, cj, h1, kSquadBfsSteps);
+                const bool h1_final = squad_h1_lookup(m, S.bfs, need, ci, cj, h1, kSquadBfsSteps, r_bfs);
                 pf.sub(22);
                 if (h1_final)
                 {
