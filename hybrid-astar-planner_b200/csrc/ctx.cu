@@ -64,6 +64,8 @@ static bool apply_option(Options &o, const char *key, const char *value)
         o.plan_solo = v == "" || v == "solo" || v == "solo_warp";
         o.plan_nosquad = v == "solo_warp";
     }
+    else if (k == "plan_grow")
+        o.plan_grow = !(v == "0");
     else if (k == "solo_nodes")
     {
         const long n = v == "" ? 32768 : std::strtol(v.c_str(), nullptr, 10);
@@ -103,8 +105,9 @@ static void free_plan_scratch(Ctx *c)
             cudaFree(P.gen);
         P = PlanPool();
     }
+    for (PlanPool *pp : {&c->solo_pool, &c->mid_pool})
     {
-        PlanPool &P = c->solo_pool;
+        PlanPool &P = *pp;
         if (P.base)
             cudaFree(P.base);
         if (P.owner)
@@ -161,6 +164,7 @@ extern "C" int mpros_ctx_create(int device, mpros_ctx **out)
     apply_option(c->opt, "goal_mode", std::getenv("MPROS_GOAL_MODE"));
     apply_option(c->opt, "plan_mode", std::getenv("MPROS_PLAN_MODE"));
     apply_option(c->opt, "solo_nodes", std::getenv("MPROS_SOLO_NODES"));
+    apply_option(c->opt, "plan_grow", std::getenv("MPROS_PLAN_GROW"));
     apply_option(c->opt, "debug", std::getenv("MPROS_DEBUG"));
     mpros_map_params_default(&c->mp);
     mpros_planner_params_default(&c->pp);

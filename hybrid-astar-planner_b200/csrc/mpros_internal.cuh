@@ -126,6 +126,7 @@ struct Options
     bool plan_solo = true;     // default (MPROS_PLAN_MODE unset or "solo"): every query starts in the warp-per-query kernel, the team
                                // kernel takes over the ones that outgrow its workspaces; "team" = team kernel only
     int solo_nodes = 32768;    // MPROS_SOLO_NODES: node-pool size of a solo workspace
+    bool plan_grow = true;     // MPROS_PLAN_GROW=0: queries that outgrow a small workspace go to the team pass at once
     bool plan_nosquad = false; // MPROS_PLAN_MODE=solo_warp: independent warps (plan_solo_kernel) instead of squads (plan_squad_kernel)
     bool debug = false;        // MPROS_DEBUG: per-pass timing (and the phase profile of the -DMPROS_PROFILE build) on stderr
 };
@@ -142,6 +143,7 @@ struct Ctx
     PlanScratch plan_scratch[MPROS_PLAN_LANES][kPlanPasses];
     PlanPool plan_pool[kPlanPasses];
     PlanPool solo_pool;    // small workspaces of the warp-per-query pass, one per resident warp of the device
+    PlanPool mid_pool;     // grown workspaces of the squad pass (four times the nodes), eight per SM
     int solo_resident = 0, squad_resident = 0; // resident CTAs per SM of the two solo-pass kernels (occupancy query, cached)
     int plan_resident[3] = {0, 0, 0}; // resident teams per SM: [0] CTA teams, [1] CTA-pair teams (occupancy query, cached), [2] two teams per CTA
 

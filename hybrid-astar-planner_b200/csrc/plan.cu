@@ -83,6 +83,9 @@ struct PlanBatchArgs
     // solo pass (plan_solo.cuh): one warp per query with a small workspace; queries that outgrow it go to the hand-off list
     WorkspacePool solo_pool;
     WarpWorkspaceLayout Ls;
+    // grown workspaces of the squad pass (plan_squad.cuh: squad_grow): a query that outgrows the small one moves into one of these
+    WorkspacePool mid_pool; // n == 0: none
+    WarpWorkspaceLayout Lm;
     unsigned int *solo_counter;
     int32_t *handoff;         // nq entries (null: overflowed queries report ST_OVERFLOW)
     int32_t *handoff_ws;      // nq entries: solo workspace that holds the query's state (-1: none, the team pass starts it afresh)
@@ -1043,7 +1046,7 @@ static int plan_quiesce(mpros_ctx *c)
 #ifndef MPROS_SOLO_OFF
 // Solo pass (plan_solo.cuh): every query of the batch on its own warp with a small workspace; the queries that outgrow it are
 // appended to the lane's hand-off list, which the team pass behind it on the same stream reads from the device.
-static int plan_solo_pass(mpros_ctx *c, int lane, cudaStream_t stream, PlanBatchArgs &a, int nq)
+static int plan_solo_pass(mpros_ctx *c, int lane, cudaStream_t stream, PlanBatchArgs &a, int nq, long long max_nodes)
 {
     PlanScratch &S = c->plan_scratch[lane][0];
     PlanPool &PL = c->solo_pool;
@@ -1118,6 +1121,75 @@ static int plan_solo_pass(mpros_ctx *c, int lane, cudaStream_t stream, PlanBatch
         PL.issued = 0;
     }
     PL.issued += (unsigned long long)nq + 1ull;
+    // grown workspaces (squad_grow): eight per SM, four times the nodes; left out when memory is short
+    PlanPool &PM = c->mid_pool;
+    WarpWorkspaceLayout Lmid = make_layout((int)std::min<long long>((long long)c->opt.solo_nodes * 4, max_nodes), c->H, c->W);
+    if (squad_ok && c->opt.plan_grow)
+    {
+        const int want_mid = std::min(nq, 8 * c->n_sm);
+        const bool mid_change = std::memcmp(PM.last_layout, &Lmid, sizeof(Lmid)) != 0;
+        if (mid_change || PM.n < want_mid)
+        {
+            size_t free_b = 0, total_b = 0;
+            MPROS_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            // the team pool (allocated after this one) must still fit into half of what is left
+            const WarpWorkspaceLayout big = make_layout((int)max_nodes, c->H, c->W);
+            const size_t team_need = c->plan_pool[0].bytes ? 0 : big.stride * (size_t)(kTeamMinBlocks * c->n_sm);
+            const size_t avail = free_b + PM.bytes > 2 * team_need ? (free_b + PM.bytes - 2 * team_need) / 2 : 0;
+            const int n = (int)std::min<long long>(want_mid, (long long)(avail / Lmid.stride));
+            if (n >= 1 && (mid_change || n > PM.n))
+            {
+                int rc = plan_quiesce(c);
+                if (rc)
+                    return rc;
+                const size_t need = (size_t)n * Lmid.stride;
+                if (need > PM.bytes)
+                {
+                    if (PM.base)
+                        MPROS_CUDA(cudaFree(PM.base));
+                    PM.base = nullptr;
+                    PM.bytes = 0;
+                    MPROS_CUDA(cudaMalloc(&PM.base, need));
+                    PM.bytes = need;
+                }
+                if (n > PM.meta_cap)
+                {
+                    if (PM.owner)
+                        MPROS_CUDA(cudaFree(PM.owner));
+                    if (PM.gen)
+                        MPROS_CUDA(cudaFree(PM.gen));
+                    PM.owner = nullptr, PM.gen = nullptr, PM.meta_cap = 0;
+                    MPROS_CUDA(cudaMalloc(&PM.owner, (size_t)n * 4));
+                    MPROS_CUDA(cudaMalloc(&PM.gen, (size_t)n * 4));
+                    PM.meta_cap = n;
+                }
+                MPROS_CUDA(cudaMemsetAsync(PM.base, 0, PM.bytes, stream));
+                MPROS_CUDA(cudaMemsetAsync(PM.owner, 0, (size_t)PM.meta_cap * 4, stream));
+                MPROS_CUDA(cudaMemsetAsync(PM.gen, 0, (size_t)PM.meta_cap * 4, stream));
+                MPROS_CUDA(cudaStreamSynchronize(stream));
+                PM.n = n;
+                PM.stride = Lmid.stride;
+                PM.issued = 0;
+                std::memcpy(PM.last_layout, &Lmid, sizeof(Lmid));
+            }
+            else if (mid_change)
+                PM.n = 0; // no room: the squad pass works without grown workspaces
+        }
+        if (PM.n > 0)
+        {
+            if (PM.issued + (unsigned long long)nq + 2ull >= (1ull << 30))
+            {
+                int rc = plan_quiesce(c);
+                if (rc)
+                    return rc;
+                MPROS_CUDA(cudaMemsetAsync(PM.base, 0, PM.bytes, stream));
+                MPROS_CUDA(cudaMemsetAsync(PM.gen, 0, (size_t)PM.meta_cap * 4, stream));
+                MPROS_CUDA(cudaStreamSynchronize(stream));
+                PM.issued = 0;
+            }
+            PM.issued += (unsigned long long)nq + 1ull;
+        }
+    }
     if (!S.counter)
         MPROS_CUDA(cudaMalloc(&S.counter, 256));
     if ((size_t)nq > S.handoff_cap)
@@ -1162,6 +1234,14 @@ static int plan_solo_pass(mpros_ctx *c, int lane, cudaStream_t stream, PlanBatch
     a.todo_ws = a.handoff_ws;
     a.solo_spare0 = std::min(warps, PL.n);
     a.solo_spare_n = std::max(1, custody_max);
+    const bool grow = squad && c->opt.plan_grow && PM.n > 0 && a.handoff_ws != nullptr && std::memcmp(PM.last_layout, &Lmid, sizeof(Lmid)) == 0;
+    a.Lm = Lmid;
+    a.mid_pool.base = PM.base;
+    a.mid_pool.owner = PM.owner;
+    a.mid_pool.gen = PM.gen;
+    a.mid_pool.n = grow ? PM.n : 0;
+    a.mid_pool.custody = nullptr;
+    a.mid_pool.custody_max = 0;
     const int wpc = squad ? MPROS_SQUAD_WARPS : MPROS_SOLO_WARPS;
     const int ctas = squad ? std::max(1, std::min(std::min(warps, PL.n) / wpc, (nq + wpc - 1) / wpc))
                            : std::max(1, std::min((std::min(warps, PL.n) + wpc - 1) / wpc, (nq + wpc - 1) / wpc));
@@ -1218,8 +1298,9 @@ static int plan_solo_pass(mpros_ctx *c, int lane, cudaStream_t stream, PlanBatch
                 std::fprintf(stderr, "[mpros]     %-18s %9.1f\n", sub[k], h[17 + k] / ex);
         }
 #endif
-        std::fprintf(stderr, "[mpros] %s pass: %d queries, node_cap %d, %d CTAs x %d warps (%d resident per SM), %.1f MB/warp, %.3f ms, %u handed to the team pass\n",
-                     squad ? "squad" : "solo", nq, L.node_cap, ctas, wpc, squad ? c->squad_resident : c->solo_resident, L.stride / 1048576.0, ms, nh);
+        std::fprintf(stderr, "[mpros] %s pass: %d queries, node_cap %d, %d CTAs x %d warps (%d resident per SM), %.1f MB/warp, %d grown workspaces of %.1f MB, %.3f ms, %u handed to the team pass\n",
+                     squad ? "squad" : "solo", nq, L.node_cap, ctas, wpc, squad ? c->squad_resident : c->solo_resident, L.stride / 1048576.0,
+                     a.mid_pool.n, Lmid.stride / 1048576.0, ms, nh);
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
     }
@@ -1442,7 +1523,7 @@ static int plan_batch_dev_impl(mpros_ctx *c, int lane, cudaStream_t stream, cons
     // asynchronous entry points stay asynchronous). The expansion trace is a team-kernel feature.
     if (c->opt.plan_solo && !c->opt.plan_cluster && !c->opt.plan_duo && !d_trace && caps[0] >= max_nodes && c->opt.solo_nodes < max_nodes)
     {
-        int rc = plan_solo_pass(c, lane, stream, a, nq);
+        int rc = plan_solo_pass(c, lane, stream, a, nq, max_nodes);
         if (rc)
             return rc;
         return plan_pass(c, lane, stream, a, 0, (int)max_nodes, nq, a.handoff, 0, a.handoff_n);

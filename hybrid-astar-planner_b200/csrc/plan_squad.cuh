@@ -288,27 +288,67 @@ __device__ __forceinline__ int squad_h1_lookup(const MapView &m, TeamBfs &b, boo
     return !__any_sync(kFull, want && v < 0);
 }
 
-// Hand a query over to the team pass with its state: the warp's workspace (node pool, open list, closed set, wavefront
-// window) travels with the query, the rest goes into the ResumeHeader; the warp goes on with another workspace. Called
-// between two iterations (open list consistent, nothing half inserted). Returns false when the custody limit is reached:
-// nothing has changed then.
-__device__ __noinline__ bool squad_hand_over(const PlanBatchArgs &a, SoloShared &S, const OpenHeap &heap, int q, int &ws_slot, uint32_t &gen,
-                                             uint32_t n_nodes, int iteration, int n_shots, long long n_exp, long long n_coll, bool goal_found,
-                                             uint32_t goal_parent, double goal_g, int si, int sj)
+constexpr int kMidFlag = 0x40000000; // hand-off entry: the workspace index refers to the pool of grown workspaces (mid_pool)
+
+// one free workspace of `pl`, or -1 (no waiting: one look at every entry, 32 at a time)
+__device__ __forceinline__ int pool_try_acquire_warp(const WorkspacePool &pl, int first)
 {
     const int lane = threadIdx.x & 31;
-    const int fresh = pool_swap_acquire_warp(a.solo_pool, a.solo_spare0 + (int)((unsigned)q % (unsigned)max(1, a.solo_spare_n)));
-    if (fresh < 0)
-        return false;
-    const WarpWorkspaceLayout &L = a.Ls;
-    char *ws = a.solo_pool.base + (size_t)ws_slot * L.stride;
+    if (pl.n <= 0)
+        return -1;
+    int base = first % pl.n;
+    for (int seen = 0; seen < pl.n; seen += 32)
+    {
+        int i = base + lane;
+        i = i >= pl.n ? i - pl.n : i;
+        const bool free_seen = seen + lane < pl.n && *reinterpret_cast<volatile int *>(&pl.owner[i]) == 0;
+        unsigned cand = __ballot_sync(kFull, free_seen);
+        while (cand)
+        {
+            const int l = __ffs(cand) - 1;
+            cand &= cand - 1;
+            int mine = -1;
+            if (lane == l && atomicCAS(&pl.owner[i], 0, 1) == 0)
+                mine = i;
+            const int got = __shfl_sync(kFull, mine, l);
+            if (got >= 0)
+            {
+                __threadfence();
+                return got;
+            }
+        }
+        base = base + 32 >= pl.n ? base + 32 - pl.n : base + 32;
+    }
+    return -1;
+}
+
+// Hand a query over to the team pass with its state: the workspace the query lives in (node pool, open list, closed set,
+// wavefront window) travels with it, the rest goes into the ResumeHeader. Called between two iterations (open list
+// consistent, nothing half inserted). A query in a GROWN workspace (mid_slot >= 0) simply leaves it to the team pass; a query
+// in the warp's own small workspace needs another one for the warp to go on with (custody limit, plan_team.cuh): false when
+// there is none - nothing has changed then.
+__device__ __noinline__ bool squad_hand_over(const PlanBatchArgs &a, SoloShared &S, const OpenHeap &heap, int q, int &ws_slot, uint32_t &gen,
+                                             int mid_slot, uint32_t mid_gen, uint32_t n_nodes, int iteration, int n_shots, long long n_exp,
+                                             long long n_coll, bool goal_found, uint32_t goal_parent, double goal_g, int si, int sj)
+{
+    const int lane = threadIdx.x & 31;
+    const bool mid = mid_slot >= 0;
+    int fresh = -1;
+    if (!mid)
+    {
+        fresh = pool_swap_acquire_warp(a.solo_pool, a.solo_spare0 + (int)((unsigned)q % (unsigned)max(1, a.solo_spare_n)));
+        if (fresh < 0)
+            return false;
+    }
+    const WarpWorkspaceLayout &L = mid ? a.Lm : a.Ls;
+    char *ws = mid ? a.mid_pool.base + (size_t)mid_slot * L.stride : a.solo_pool.base + (size_t)ws_slot * L.stride;
     // the top of the open list lives in shared memory: complete the global arrays
     for (int k = lane; k < heap.size && k < kSoloHeapTop; k += 32)
         heap.key[k] = S.hkey[k], heap.id[k] = S.hid[k];
     if (lane == 0)
     {
         ResumeHeader *H = reinterpret_cast<ResumeHeader *>(ws + L.hdr_off);
-        H->tag = gen, H->gen = gen, H->heap_size = heap.size, H->n_nodes = n_nodes;
+        H->tag = mid ? mid_gen : gen, H->gen = mid ? mid_gen : gen, H->heap_size = heap.size, H->n_nodes = n_nodes;
         H->iteration = iteration, H->n_shots = n_shots, H->goal_found = goal_found, H->goal_parent = goal_parent;
         H->n_exp = n_exp, H->n_coll = n_coll, H->goal_g = goal_g, H->si = si, H->sj = sj;
         H->bfs = S.bfs;
@@ -320,13 +360,121 @@ __device__ __noinline__ bool squad_hand_over(const PlanBatchArgs &a, SoloShared 
         __threadfence();
         const unsigned at = atomicAdd(a.handoff_n, 1u);
         a.handoff[at] = q;
-        a.handoff_ws[at] = ws_slot;
+        a.handoff_ws[at] = mid ? (mid_slot | kMidFlag) : ws_slot;
         a.status[q] = ST_OVERFLOW; // overwritten by the team pass
-        fresh_gen = a.solo_pool.gen[fresh];
+        if (!mid)
+            fresh_gen = a.solo_pool.gen[fresh];
     }
-    ws_slot = fresh;
-    gen = __shfl_sync(kFull, fresh_gen, 0);
+    if (!mid)
+    {
+        ws_slot = fresh;
+        gen = __shfl_sync(kFull, fresh_gen, 0);
+    }
     return true;
+}
+
+// A query has outgrown the warp's small workspace: move it into a free workspace of the mid pool (four times the nodes) and go
+// on there - the same warp, the same squad, no other kernel involved. The warp copies the node pool and the open list,
+// re-hashes the live closed-set slots under the new workspace's tag and copies the initialised rows of the wavefront window
+// (its CTA waits at the next barrier meanwhile: about a millisecond, a few times per CTA and batch). Returns the mid
+// workspace, -1 when none is free.
+__device__ __noinline__ int squad_grow(const PlanBatchArgs &a, SoloShared &S, const char *src, uint32_t old_tag, int heap_size, uint32_t n_nodes,
+                                       int hint, uint32_t &mid_gen)
+{
+    const int lane = threadIdx.x & 31;
+    const int ms = pool_try_acquire_warp(a.mid_pool, hint);
+    if (ms < 0)
+        return -1;
+    const WarpWorkspaceLayout &Ls = a.Ls, &Lm = a.Lm;
+    uint32_t g0 = 0;
+    if (lane == 0)
+        g0 = a.mid_pool.gen[ms];
+    mid_gen = __shfl_sync(kFull, g0, 0) + 1;
+    char *dst = a.mid_pool.base + (size_t)ms * Lm.stride;
+    {
+        const uint4 *sn = reinterpret_cast<const uint4 *>(src + Ls.node_off);
+        uint4 *dn = reinterpret_cast<uint4 *>(dst + Lm.node_off);
+        const size_t n16 = (size_t)n_nodes * (sizeof(PlanNode) / 16);
+        for (size_t k = lane; k < n16; k += 128)
+        {
+            uint4 v[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if (k + 32 * t < n16)
+                    v[t] = sn[k + 32 * t];
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if (k + 32 * t < n16)
+                    dn[k + 32 * t] = v[t];
+        }
+    }
+    {
+        const unsigned long long *sk = reinterpret_cast<const unsigned long long *>(src + Ls.hkey_off);
+        const uint32_t *sid = reinterpret_cast<const uint32_t *>(src + Ls.hid_off);
+        unsigned long long *dk = reinterpret_cast<unsigned long long *>(dst + Lm.hkey_off);
+        uint32_t *did = reinterpret_cast<uint32_t *>(dst + Lm.hid_off);
+        for (int k = kSoloHeapTop + lane; k < heap_size; k += 32) // the first kSoloHeapTop entries stay in shared memory
+            dk[k] = sk[k], did[k] = sid[k];
+    }
+    {
+        const ClosedSlot *st = reinterpret_cast<const ClosedSlot *>(src + Ls.table_off);
+        ClosedSlot *dt = reinterpret_cast<ClosedSlot *>(dst + Lm.table_off);
+        const uint32_t dmask = (uint32_t)Lm.table_slots - 1;
+        const unsigned long long new_tag = mid_gen;
+        for (int k0 = lane; k0 < Ls.table_slots; k0 += 128)
+        {
+            ClosedSlot e[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if (k0 + 32 * t < Ls.table_slots)
+                    e[t] = st[k0 + 32 * t];
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+            {
+                if (k0 + 32 * t >= Ls.table_slots || (e[t].key >> 34) != (unsigned long long)old_tag)
+                    continue;
+                const unsigned long long idx = e[t].key & ((1ull << 34) - 1ull);
+                const unsigned long long want = (new_tag << 34) | idx;
+                uint32_t sl = hash_index(idx) & dmask;
+                while (true)
+                {
+                    const unsigned long long cur = dt[sl].key;
+                    if ((cur >> 34) != new_tag && atomicCAS(&dt[sl].key, cur, want) == cur)
+                        break;
+                    sl = (sl + 1) & dmask;
+                }
+                dt[sl].g = e[t].g;
+                dt[sl].node = e[t].node;
+            }
+        }
+    }
+    {
+        const TeamBfs &b = S.bfs;
+        uint32_t *db = reinterpret_cast<uint32_t *>(dst + Lm.blocked_off), *d0 = reinterpret_cast<uint32_t *>(dst + Lm.f0_off),
+                 *d1 = reinterpret_cast<uint32_t *>(dst + Lm.f1_off);
+        uint4 *dd = reinterpret_cast<uint4 *>(dst + Lm.dist_off);
+        if (b.ilo <= b.ihi)
+        {
+            const size_t w0 = (size_t)(b.ilo - b.r0) * b.wwords, nw = (size_t)(b.ihi - b.ilo + 1) * b.wwords;
+            const uint4 *sd = reinterpret_cast<const uint4 *>(b.dist);
+            for (size_t k = lane; k < nw; k += 32)
+            {
+                db[w0 + k] = b.blocked[w0 + k];
+                d0[w0 + k] = b.f0[w0 + k];
+                d1[w0 + k] = b.f1[w0 + k];
+            }
+            for (size_t k = lane; k < nw * 4; k += 32) // 32 x uint16 per word = 4 x 16 bytes
+                dd[w0 * 4 + k] = sd[w0 * 4 + k];
+        }
+        __syncwarp();
+        if (lane == 0)
+        {
+            S.bfs.blocked = db, S.bfs.f0 = d0, S.bfs.f1 = d1, S.bfs.dist = reinterpret_cast<uint16_t *>(dd);
+            S.bfs.tag = mid_gen;
+        }
+    }
+    __syncwarp();
+    return ms;
 }
 
 #ifndef MPROS_SQUAD_WARPS
@@ -386,13 +534,21 @@ __global__ void __launch_bounds__(32 * W, MINB) plan_squad_kernel(const __grid_c
     unsigned long long cur_key = 0; // open-list key the expanded node was popped with
     int exp_shots = 0, exp_checked = 0; // what the failed shot before the current expansion added to the statistics
     int n_done = 0;                 // warps of this CTA without work in the previous round
+    int mid_slot = -1;              // grown workspace the current query has moved into (squad_grow), -1: the warp's own small one
+    uint32_t mid_gen = 0;
+    int node_cap = L.node_cap;
     auto bind_ws = [&]() {
-        ws = a.solo_pool.base + (size_t)ws_slot * L.stride;
-        nodes = reinterpret_cast<PlanNode *>(ws + L.node_off);
-        scratch = reinterpret_cast<double *>(ws + L.traj_off);
-        heap.key = reinterpret_cast<unsigned long long *>(ws + L.hkey_off);
-        heap.id = reinterpret_cast<uint32_t *>(ws + L.hid_off);
-        closed.slot = reinterpret_cast<ClosedSlot *>(ws + L.table_off);
+        const bool mid = mid_slot >= 0;
+        const WarpWorkspaceLayout &B = mid ? a.Lm : a.Ls;
+        ws = mid ? a.mid_pool.base + (size_t)mid_slot * B.stride : a.solo_pool.base + (size_t)ws_slot * B.stride;
+        nodes = reinterpret_cast<PlanNode *>(ws + B.node_off);
+        scratch = reinterpret_cast<double *>(ws + B.traj_off);
+        heap.key = reinterpret_cast<unsigned long long *>(ws + B.hkey_off);
+        heap.id = reinterpret_cast<uint32_t *>(ws + B.hid_off);
+        heap.cap = B.node_cap;
+        closed.slot = reinterpret_cast<ClosedSlot *>(ws + B.table_off);
+        closed.mask = (uint32_t)B.table_slots - 1;
+        node_cap = B.node_cap;
     };
 
     SquadProf pf;
@@ -490,9 +646,9 @@ __global__ void __launch_bounds__(32 * W, MINB) plan_squad_kernel(const __grid_c
             // the long ones; a whole team finishes them faster than a nearly empty squad, and the team pass cannot start before
             // this kernel has ended: hand them over, state and all.
             if (state == RUN && a.handoff_ws && n_done >= W - W / 3 && iteration >= 32 && heap.size > 0 &&
-                squad_hand_over(a, S, heap, q, ws_slot, gen, n_nodes, iteration, n_shots, n_exp, n_coll, goal_found, goal_parent, goal_g, si, sj))
+                squad_hand_over(a, S, heap, q, ws_slot, gen, mid_slot, mid_gen, n_nodes, iteration, n_shots, n_exp, n_coll, goal_found, goal_parent,
+                                goal_g, si, sj))
             {
-                bind_ws();
                 finish = kHandOff;
             }
             else if (state == RUN)
@@ -658,7 +814,7 @@ __global__ void __launch_bounds__(32 * W, MINB) plan_squad_kernel(const __grid_c
             __syncwarp();
         }
         // the node pool must take all children of the expansion, or none (a handed-over query resumes between two iterations)
-        bool overflow = !post_start && needmask && n_nodes + __popc(needmask) > (uint32_t)L.node_cap;
+        bool overflow = !post_start && needmask && n_nodes + __popc(needmask) > (uint32_t)node_cap;
         if (!post_start && needmask && !overflow)
         {
             // closed-set compare / insert in primitive order (see plan_solo.cuh)
@@ -667,7 +823,7 @@ __global__ void __launch_bounds__(32 * W, MINB) plan_squad_kernel(const __grid_c
             if (!conflict)
             {
                 const int cnt = __popc(needmask);
-                if (n_nodes + cnt > (uint32_t)L.node_cap)
+                if (n_nodes + cnt > (uint32_t)node_cap)
                     overflow = true;
                 else
                 {
@@ -715,7 +871,7 @@ __global__ void __launch_bounds__(32 * W, MINB) plan_squad_kernel(const __grid_c
                     n_nodes += cnt;
                 }
             }
-            else if (!solo_insert_sequential(nodes, closed, heap, needmask, cur, n_nodes, L.node_cap, idx, g, h, nx, ny, nyaw, ns, nc, steer, direc))
+            else if (!solo_insert_sequential(nodes, closed, heap, needmask, cur, n_nodes, node_cap, idx, g, h, nx, ny, nyaw, ns, nc, steer, direc))
                 overflow = true;
             __syncwarp();
         }
@@ -734,12 +890,19 @@ __global__ void __launch_bounds__(32 * W, MINB) plan_squad_kernel(const __grid_c
                 --n_exp;
                 n_coll -= P + exp_checked; // the team pass repeats this step, shot included
                 n_shots -= exp_shots;
-                if (a.handoff_ws && squad_hand_over(a, S, heap, q, ws_slot, gen, n_nodes, iteration, n_shots, n_exp, n_coll, goal_found, goal_parent,
-                                                    goal_g, si, sj))
+                int grown = -1;
+                if (mid_slot < 0 && a.mid_pool.n > 0)
+                    grown = squad_grow(a, S, ws, gen, heap.size, n_nodes, q, mid_gen);
+                if (grown >= 0)
                 {
+                    // the query goes on in a workspace four times the size; the step that did not fit is repeated there
+                    mid_slot = grown;
+                    closed.tag = mid_gen;
                     bind_ws();
-                    finish = kHandOff;
                 }
+                else if (a.handoff_ws && squad_hand_over(a, S, heap, q, ws_slot, gen, mid_slot, mid_gen, n_nodes, iteration, n_shots, n_exp, n_coll,
+                                                         goal_found, goal_parent, goal_g, si, sj))
+                    finish = kHandOff;
                 else
                     finish = ST_OVERFLOW;
             }
@@ -790,6 +953,15 @@ __global__ void __launch_bounds__(32 * W, MINB) plan_squad_kernel(const __grid_c
                 }
             }
             __syncwarp();
+            if (mid_slot >= 0)
+            {
+                // a finished query gives its grown workspace back; a handed-over one has left it to the team pass
+                if (finish != kHandOff && lane == 0)
+                    pool_release(a.mid_pool, mid_slot, mid_gen);
+                mid_slot = -1;
+            }
+            if (ws_slot >= 0)
+                bind_ws();
             state = IDLE;
             q = -1;
         }

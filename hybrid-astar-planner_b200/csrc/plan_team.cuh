@@ -917,8 +917,11 @@ template <int NW>
 __device__ __noinline__ void team_resume(const PlanBatchArgs &a, int ws_small, char *ws, uint32_t tag, TeamShared<NW> &S, int &heap_size, int P)
 {
     const int tid = team_tid<NW>(), NT = NW * 32;
-    const WarpWorkspaceLayout &L = a.L, &Ls = a.Ls;
-    const char *src = a.solo_pool.base + (size_t)ws_small * Ls.stride;
+    const bool from_mid = (ws_small & 0x40000000) != 0; // plan_squad.cuh: kMidFlag
+    ws_small &= 0x3fffffff;
+    const WorkspacePool &spool = from_mid ? a.mid_pool : a.solo_pool;
+    const WarpWorkspaceLayout &L = a.L, &Ls = from_mid ? a.Lm : a.Ls;
+    const char *src = spool.base + (size_t)ws_small * Ls.stride;
     const ResumeHeader *H = reinterpret_cast<const ResumeHeader *>(src + Ls.hdr_off);
     const uint32_t n_nodes = H->n_nodes;
     const int hsize = H->heap_size;
@@ -1012,8 +1015,9 @@ __device__ __noinline__ void team_resume(const PlanBatchArgs &a, int ws_small, c
     team_sync_all<NW>(); // every thread has read what it needs from the small workspace
     if (tid == 0)
     {
-        pool_release(a.solo_pool, ws_small, gen_small);
-        atomicSub(a.solo_pool.custody, 1);
+        pool_release(spool, ws_small, gen_small);
+        if (!from_mid)
+            atomicSub(a.solo_pool.custody, 1);
     }
 }
 

@@ -120,7 +120,9 @@ MPROS_API uint64_t mpros_ctx_launch_count(mpros_ctx *ctx);
  *   "plan_mode" "solo" (default) | "team" | "cluster" | "duo"  planner: warp-per-query pass, then the team kernel for the queries
  *                                                          that outgrow its workspaces / team kernel only (one CTA per query) /
  *                                                          a CTA pair on the two SMs of a TPC / two teams per CTA
- *   "solo_nodes" node-pool size of a solo workspace (default 32768)
+ *   "solo_nodes" node-pool size of a small (warp-per-query) workspace (default 32768)
+ *   "plan_grow" "1" (default) | "0"                       a query that outgrows its small workspace moves into one four times the
+ *                                                          size and stays with its warp / goes to the team pass at once
  *   "debug"     "0" (default) | "1"                        per-pass timing on stderr
  * Results never depend on these switches (tests/ hold every mode to the same outputs). No reference counterpart. */
 MPROS_API int mpros_ctx_set_option(mpros_ctx *ctx, const char *key, const char *value);
