@@ -79,6 +79,12 @@ def ncu_traffic(kernel):
     return None
 
 
+def plan_traffic():
+    """DRAM bytes of one batch of the plan workload = the two launches of a batch (squad pass + team pass)."""
+    a, b = ncu_traffic("plan_squad_kernel"), ncu_traffic("plan_team_kernel")
+    return None if a is None or b is None else a + b
+
+
 def measured_peak_gbs():
     try:
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
@@ -272,7 +278,9 @@ def plan_config(lanes, scaling="weak", world=1):
     """config of the plan workload, identical for the GPU arm and the reference arm (the reference arm times a seeded
     sample of the same query set; what the sample was is stated in its cpu_baseline.sample)."""
     cfg = {"workload": workload_text("plan"), "path_cap": PATH_CAP, "batches_in_flight": lanes,
-           "l2_policy": "per-query working sets (node pool, open list, closed set, goal wavefront) live in a ~110 MB-per-team HBM workspace, 296 teams (>> L2 in aggregate); map layers are L2-resident by design"}
+           "l2_policy": "per-query working sets (node pool, open list, closed set, goal wavefront) live in per-query HBM workspaces: 3 552 resident "
+                        "warp-per-query searches x 8.8 MB, grown ones 27.9 MB, 296 team workspaces x 110 MB (>> L2 in aggregate); map layers are "
+                        "L2-resident by design"}
     if scaling == "strong":
         cfg["queries_total"] = QUERIES_PER_GPU
     else:
@@ -857,10 +865,14 @@ def run_b200(args):
                     "e2e": {"value": nq_all * args.steps / (e2e_ms * 1e-3), "unit": "plans/s", "h2d_bytes_per_step": nq * 48,
                             "d2h_bytes_per_step": nq * (4 + 8 + 4 + PATH_CAP * 40 + 48)},
                     "gpu_launches": int(launches),
-                    "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("plan_team_kernel"),
-                                 "kernel": "plan_team_kernel", "kernel_ms": k_ms, "kernel_ms_alone": lone_ms, "peak_source": peak_kind,
+                    "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                                 "traffic": plan_traffic(),
+                                 "kernel": "plan_squad_kernel + plan_team_kernel", "kernel_ms": k_ms, "kernel_ms_alone": lone_ms, "peak_source": peak_kind,
                                  "algorithmic_bytes_per_launch": algo_bytes,
-                                 "note": "latency/FP64-issue bound (sequential A* per query, FP64 transcendentals), not HBM bound; see DESIGN.md"},
+                                 "note": "a batch is two launches on one stream: plan_squad_kernel (every query, one warp each, 24 per CTA) and "
+                                         "plan_team_kernel (the queries still running when the squads thin out, one CTA each); achieved / traffic are "
+                                         "for the pair. Latency / FP64-issue bound (A* is a dependent chain per query, FP64 transcendentals), "
+                                         "not HBM bound; see DESIGN.md"},
                     "extra": {"node_expansions_per_sec": expansions_all / secs, "footprint_checks_per_sec_in_planning": checks_all / secs,
                               "rs_shots_per_sec": shots_all / secs, "goal_map_cells_per_sec": cells_all / secs,
                               "collision_kernel_checks_per_sec": col_value, "collision_kernel_e2e_checks_per_sec": col_e2e,
@@ -1072,7 +1084,7 @@ def arena_measure(args, steps, with_cpu):
             "e2e": {"value": nq * K / e2e_s, "unit": "plans/s", "h2d_bytes_per_step": nq * 48, "d2h_bytes_per_step": nq * (4 + 8 + 4 + PATH_CAP * 40 + 48)},
             "gpu_launches": int(launches), "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": algo / secs / 1e9, "peak": peak, "unit": "GB/s", "frac": algo / secs / 1e9 / peak, "traffic": None,
-                         "kernel": "plan_team_kernel", "kernel_ms": plan_ms / K, "peak_source": peak_kind, "algorithmic_bytes_per_launch": algo,
+                         "kernel": "plan_squad_kernel + plan_team_kernel", "kernel_ms": plan_ms / K, "peak_source": peak_kind, "algorithmic_bytes_per_launch": algo,
                          "note": "latency/FP64-issue bound (sequential A* per query), not HBM bound; see DESIGN.md"},
             "extra": {"node_expansions_per_sec": expansions / secs, "plans_found": int((status == 1).sum()), "plans_iteration_limit": int((status == 0).sum()),
                       "plans_failed_other": int((status < 0).sum()), "mean_expansions_per_query": expansions / nq,
