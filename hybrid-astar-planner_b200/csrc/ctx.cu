@@ -64,6 +64,13 @@ static bool apply_option(Options &o, const char *key, const char *value)
         o.plan_solo = v == "" || v == "solo" || v == "solo_warp";
         o.plan_nosquad = v == "solo_warp";
     }
+    else if (k == "solo_min_queries")
+    {
+        const long n = v == "" ? 8192 : std::strtol(v.c_str(), nullptr, 10);
+        if (n < 0 || n > (1l << 30))
+            return false;
+        o.solo_min_queries = (int)n;
+    }
     else if (k == "plan_grow")
         o.plan_grow = !(v == "0");
     else if (k == "solo_nodes")
@@ -165,6 +172,7 @@ extern "C" int mpros_ctx_create(int device, mpros_ctx **out)
     apply_option(c->opt, "plan_mode", std::getenv("MPROS_PLAN_MODE"));
     apply_option(c->opt, "solo_nodes", std::getenv("MPROS_SOLO_NODES"));
     apply_option(c->opt, "plan_grow", std::getenv("MPROS_PLAN_GROW"));
+    apply_option(c->opt, "solo_min_queries", std::getenv("MPROS_SOLO_MIN_QUERIES"));
     apply_option(c->opt, "debug", std::getenv("MPROS_DEBUG"));
     mpros_map_params_default(&c->mp);
     mpros_planner_params_default(&c->pp);

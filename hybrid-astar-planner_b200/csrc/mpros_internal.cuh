@@ -126,6 +126,8 @@ struct Options
     bool plan_solo = true;     // default (MPROS_PLAN_MODE unset or "solo"): every query starts in the warp-per-query kernel, the team
                                // kernel takes over the ones that outgrow its workspaces; "team" = team kernel only
     int solo_nodes = 32768;    // MPROS_SOLO_NODES: node-pool size of a solo workspace
+    int solo_min_queries = 8192; // MPROS_SOLO_MIN_QUERIES: smaller batches go straight to the team kernel (a few thousand queries do
+                                 // not fill the squads; the team kernel alone finishes them sooner: 2 048 queries 0.74 s against 0.95 s)
     bool plan_grow = true;     // MPROS_PLAN_GROW=0: queries that outgrow a small workspace go to the team pass at once
     bool plan_nosquad = false; // MPROS_PLAN_MODE=solo_warp: independent warps (plan_solo_kernel) instead of squads (plan_squad_kernel)
     bool debug = false;        // MPROS_DEBUG: per-pass timing (and the phase profile of the -DMPROS_PROFILE build) on stderr

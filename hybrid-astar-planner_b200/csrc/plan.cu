@@ -1518,10 +1518,11 @@ static int plan_batch_dev_impl(mpros_ctx *c, int lane, cudaStream_t stream, cons
         }
     }
 #ifndef MPROS_SOLO_OFF
-    // Default: every query starts on its own warp with a small workspace (solo pass); the team pass behind it runs only the
+    // Default for big batches: every query starts on its own warp with a small workspace (solo pass); the team pass behind it runs only the
     // queries that outgrew it, with full-size workspaces, and finds them in a device-side list (no host round trip, so the
     // asynchronous entry points stay asynchronous). The expansion trace is a team-kernel feature.
-    if (c->opt.plan_solo && !c->opt.plan_cluster && !c->opt.plan_duo && !d_trace && caps[0] >= max_nodes && c->opt.solo_nodes < max_nodes)
+    if (c->opt.plan_solo && !c->opt.plan_cluster && !c->opt.plan_duo && !d_trace && caps[0] >= max_nodes && c->opt.solo_nodes < max_nodes &&
+        nq >= c->opt.solo_min_queries)
     {
         int rc = plan_solo_pass(c, lane, stream, a, nq, max_nodes);
         if (rc)

@@ -121,6 +121,7 @@ MPROS_API uint64_t mpros_ctx_launch_count(mpros_ctx *ctx);
  *                                                          that outgrow its workspaces / team kernel only (one CTA per query) /
  *                                                          a CTA pair on the two SMs of a TPC / two teams per CTA
  *   "solo_nodes" node-pool size of a small (warp-per-query) workspace (default 32768)
+ *   "solo_min_queries" batches with fewer queries go straight to the team kernel (default 8192)
  *   "plan_grow" "1" (default) | "0"                       a query that outgrows its small workspace moves into one four times the
  *                                                          size and stays with its warp / goes to the team pass at once
  *   "debug"     "0" (default) | "1"                        per-pass timing on stderr
