@@ -71,6 +71,19 @@ static bool apply_option(Options &o, const char *key, const char *value)
             return false;
         o.solo_min_queries = (int)n;
     }
+    else if (k == "plan_policy")
+    {
+        if (v != "" && v != "auto" && v != "latency" && v != "throughput")
+            return false;
+        o.plan_policy = v == "latency" ? 1 : v == "throughput" ? 2 : 0;
+    }
+    else if (k == "plan_age_limit")
+    {
+        const long n = v == "" ? 30000 : std::strtol(v.c_str(), nullptr, 10);
+        if (n < 64 || n > (1l << 30))
+            return false;
+        o.plan_age_limit = (int)n;
+    }
     else if (k == "plan_grow")
         o.plan_grow = !(v == "0");
     else if (k == "solo_nodes")
@@ -99,6 +112,8 @@ static void free_plan_scratch(Ctx *c)
                 cudaFree(S.todo);
             if (S.handoff)
                 cudaFree(S.handoff);
+            if (S.mig)
+                cudaFree(S.mig);
             S = PlanScratch();
         }
     for (int k = 0; k < kPlanPasses; ++k)
@@ -172,6 +187,8 @@ extern "C" int mpros_ctx_create(int device, mpros_ctx **out)
     apply_option(c->opt, "plan_mode", std::getenv("MPROS_PLAN_MODE"));
     apply_option(c->opt, "solo_nodes", std::getenv("MPROS_SOLO_NODES"));
     apply_option(c->opt, "plan_grow", std::getenv("MPROS_PLAN_GROW"));
+    apply_option(c->opt, "plan_policy", std::getenv("MPROS_PLAN_POLICY"));
+    apply_option(c->opt, "plan_age_limit", std::getenv("MPROS_PLAN_AGE_LIMIT"));
     apply_option(c->opt, "solo_min_queries", std::getenv("MPROS_SOLO_MIN_QUERIES"));
     apply_option(c->opt, "debug", std::getenv("MPROS_DEBUG"));
     mpros_map_params_default(&c->mp);

@@ -110,6 +110,8 @@ struct PlanScratch
     size_t todo_cap = 0;
     int32_t *handoff = nullptr; // queries the solo pass hands to the team pass (device-side list, plan_solo.cuh)
     size_t handoff_cap = 0;
+    int32_t *mig = nullptr;     // migration list of the squad pass under the throughput policy (plan_squad.cuh)
+    size_t mig_cap = 0;
 };
 constexpr int kPlanPasses = 3; // node-pool size classes
 
@@ -128,6 +130,8 @@ struct Options
     int solo_nodes = 32768;    // MPROS_SOLO_NODES: node-pool size of a solo workspace
     int solo_min_queries = 8192; // MPROS_SOLO_MIN_QUERIES: smaller batches go straight to the team kernel (a few thousand queries do
                                  // not fill the squads; the team kernel alone finishes them sooner: 2 048 queries 0.74 s against 0.95 s)
+    int plan_policy = 0;       // MPROS_PLAN_POLICY: 0 auto (throughput when another batch is in flight at submission), 1 latency, 2 throughput
+    int plan_age_limit = 30000; // MPROS_PLAN_AGE_LIMIT: throughput policy, iterations after which a query goes to the team pass for good
     bool plan_grow = true;     // MPROS_PLAN_GROW=0: queries that outgrow a small workspace go to the team pass at once
     bool plan_nosquad = false; // MPROS_PLAN_MODE=solo_warp: independent warps (plan_solo_kernel) instead of squads (plan_squad_kernel)
     bool debug = false;        // MPROS_DEBUG: per-pass timing (and the phase profile of the -DMPROS_PROFILE build) on stderr

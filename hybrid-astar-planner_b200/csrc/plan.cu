@@ -91,6 +91,12 @@ struct PlanBatchArgs
     int32_t *handoff_ws;      // nq entries: solo workspace that holds the query's state (-1: none, the team pass starts it afresh)
     unsigned int *handoff_n;
     const int32_t *todo_ws;   // team pass: handoff_ws of the list it runs (null: every query starts afresh)
+    // throughput policy of the squad pass: hand-overs that another squad may adopt (plan_squad.cuh); mig_n == null: off
+    int32_t *mig, *mig_ws;
+    unsigned int *mig_n, *mig_taken; // entries [0, *mig_taken) have been adopted, [*mig_taken, *mig_n) are the team pass's
+    int mig_cap;
+    int migrate;                     // squad pass only: adoption on (the team pass reads the list whenever mig_n is set)
+    int age_limit;                   // a query older than this many iterations goes to the team pass for good
     int solo_spare0, solo_spare_n; // workspaces [solo_spare0, solo_spare0 + solo_spare_n) of the solo pool start out unowned: a
                                    // warp that hands its workspace over with a query takes one of them
     const uint32_t *unsafe_tw; // pre-classification layer of the footprint test (map_device.cuh: footprint_preclass)
@@ -1232,6 +1238,45 @@ static int plan_solo_pass(mpros_ctx *c, int lane, cudaStream_t stream, PlanBatch
     a.solo_pool.custody_max = custody_max;
     a.handoff_ws = (squad && custody_max > 0) ? S.handoff + S.handoff_cap : nullptr;
     a.todo_ws = a.handoff_ws;
+    // Policy. Alone on the device, a batch is done when its longest queries are: the squad pass hands what is still running
+    // to the team pass as soon as its CTAs thin out (a team steps a query in ~7 us, a squad in ~50). With other batches in
+    // flight the device never idles and cost per iteration is what counts: the long queries stay in squad form (idle warps of
+    // well-filled squads adopt them from the migration list) and only the oldest go to the team pass.
+    a.migrate = 0;
+    a.mig_n = nullptr;
+    a.age_limit = c->opt.plan_age_limit;
+    if (a.handoff_ws && c->opt.plan_policy != 1)
+    {
+        bool busy = c->opt.plan_policy == 2;
+        for (int l = 0; l < MPROS_PLAN_LANES && !busy; ++l)
+        {
+            cudaStream_t st = l == 0 ? c->stream : c->lane_stream[l];
+            if (l != lane && st && cudaStreamQuery(st) == cudaErrorNotReady)
+                busy = true;
+        }
+        (void)cudaGetLastError(); // cudaErrorNotReady is not an error
+        if (busy)
+        {
+            const size_t cap = (size_t)nq * 4 + 16384;
+            if (cap > S.mig_cap)
+            {
+                MPROS_CUDA(cudaStreamSynchronize(stream));
+                if (S.mig)
+                    MPROS_CUDA(cudaFree(S.mig));
+                S.mig = nullptr;
+                S.mig_cap = 0;
+                MPROS_CUDA(cudaMalloc(&S.mig, cap * 8));
+                S.mig_cap = cap;
+            }
+            a.mig = S.mig;
+            a.mig_ws = S.mig + S.mig_cap;
+            a.mig_cap = (int)S.mig_cap;
+            a.mig_n = S.counter + 48;
+            a.mig_taken = S.counter + 40;
+            a.migrate = 1;
+            MPROS_CUDA(cudaMemsetAsync(a.mig_ws, 0xfe, S.mig_cap * 4, stream)); // kNotReady
+        }
+    }
     a.solo_spare0 = std::min(warps, PL.n);
     a.solo_spare_n = std::max(1, custody_max);
     const bool grow = squad && c->opt.plan_grow && PM.n > 0 && a.handoff_ws != nullptr && std::memcmp(PM.last_layout, &Lmid, sizeof(Lmid)) == 0;
@@ -1264,8 +1309,10 @@ static int plan_solo_pass(mpros_ctx *c, int lane, cudaStream_t stream, PlanBatch
         cudaEventSynchronize(e1);
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
-        unsigned int nh = 0;
+        unsigned int nh = 0, nt = 0, nm = 0;
         cudaMemcpy(&nh, S.counter + 32, 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(&nt, S.counter + 40, 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(&nm, S.counter + 48, 4, cudaMemcpyDeviceToHost);
 #ifdef MPROS_PROFILE
         if (squad)
         {
@@ -1298,9 +1345,9 @@ static int plan_solo_pass(mpros_ctx *c, int lane, cudaStream_t stream, PlanBatch
                 std::fprintf(stderr, "[mpros]     %-18s %9.1f\n", sub[k], h[17 + k] / ex);
         }
 #endif
-        std::fprintf(stderr, "[mpros] %s pass: %d queries, node_cap %d, %d CTAs x %d warps (%d resident per SM), %.1f MB/warp, %d grown workspaces of %.1f MB, %.3f ms, %u handed to the team pass\n",
+        std::fprintf(stderr, "[mpros] %s pass: %d queries, node_cap %d, %d CTAs x %d warps (%d resident per SM), %.1f MB/warp, %d grown workspaces of %.1f MB, %.3f ms, %u handed to the team pass, %u migrated, %u of them adopted (%s policy)\n",
                      squad ? "squad" : "solo", nq, L.node_cap, ctas, wpc, squad ? c->squad_resident : c->solo_resident, L.stride / 1048576.0,
-                     a.mid_pool.n, Lmid.stride / 1048576.0, ms, nh);
+                     a.mid_pool.n, Lmid.stride / 1048576.0, ms, nh, nm, nt, a.migrate ? "throughput" : "latency");
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
     }

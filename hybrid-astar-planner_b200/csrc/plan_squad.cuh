@@ -288,6 +288,7 @@ __device__ __forceinline__ int squad_h1_lookup(const MapView &m, TeamBfs &b, boo
     return !__any_sync(kFull, want && v < 0);
 }
 
+constexpr int kNotReady = (int)0xfefefefe; // migration-list entry not written yet (the host fills the list with this byte pattern)
 constexpr int kMidFlag = 0x40000000; // hand-off entry: the workspace index refers to the pool of grown workspaces (mid_pool)
 
 // one free workspace of `pl`, or -1 (no waiting: one look at every entry, 32 at a time)
@@ -329,10 +330,21 @@ __device__ __forceinline__ int pool_try_acquire_warp(const WorkspacePool &pl, in
 // there is none - nothing has changed then.
 __device__ __noinline__ bool squad_hand_over(const PlanBatchArgs &a, SoloShared &S, const OpenHeap &heap, int q, int &ws_slot, uint32_t &gen,
                                              int mid_slot, uint32_t mid_gen, uint32_t n_nodes, int iteration, int n_shots, long long n_exp,
-                                             long long n_coll, bool goal_found, uint32_t goal_parent, double goal_g, int si, int sj)
+                                             long long n_coll, bool goal_found, uint32_t goal_parent, double goal_g, int si, int sj, bool adoptable)
 {
     const int lane = threadIdx.x & 31;
     const bool mid = mid_slot >= 0;
+    // adoptable: onto the migration list, where idle warps of well-filled squads look for work (throughput policy); the team
+    // pass takes what nobody has adopted. When that list is nearly full the query goes to the team pass directly.
+    bool to_mig = adoptable && a.migrate;
+    if (to_mig)
+    {
+        unsigned n = 0;
+        if (lane == 0)
+            n = *reinterpret_cast<volatile unsigned *>(a.mig_n);
+        if ((int)__shfl_sync(kFull, n, 0) >= a.mig_cap - 8192)
+            to_mig = false;
+    }
     int fresh = -1;
     if (!mid)
     {
@@ -358,10 +370,21 @@ __device__ __noinline__ bool squad_hand_over(const PlanBatchArgs &a, SoloShared 
     if (lane == 0)
     {
         __threadfence();
-        const unsigned at = atomicAdd(a.handoff_n, 1u);
-        a.handoff[at] = q;
-        a.handoff_ws[at] = mid ? (mid_slot | kMidFlag) : ws_slot;
-        a.status[q] = ST_OVERFLOW; // overwritten by the team pass
+        const int wsv = mid ? (mid_slot | kMidFlag) : ws_slot;
+        a.status[q] = ST_OVERFLOW; // overwritten by whoever finishes the query
+        if (to_mig)
+        {
+            const unsigned at = atomicAdd(a.mig_n, 1u);
+            a.mig[at] = q;
+            __threadfence(); // the workspace entry is what an adopting warp waits for (kNotReady until now)
+            *reinterpret_cast<volatile int32_t *>(&a.mig_ws[at]) = wsv;
+        }
+        else
+        {
+            const unsigned at = atomicAdd(a.handoff_n, 1u);
+            a.handoff[at] = q;
+            a.handoff_ws[at] = wsv;
+        }
         if (!mid)
             fresh_gen = a.solo_pool.gen[fresh];
     }
@@ -564,6 +587,66 @@ __global__ void __launch_bounds__(32 * W, MINB) plan_squad_kernel(const __grid_c
         PlanNode cn;                             // the popped node
         bool exp_done = false;   // an expansion completes in this round: its children are inserted in phase 5
         int finish = 0x7fffffff; // status to report when the query ends in this round (0x7fffffff: it goes on)
+        if (state == DONE && a.migrate && n_done < W - W / 3)
+        {
+            // The tickets have run out, this CTA is still well filled and this warp has nothing to do: adopt a query from the
+            // migration list, in place - the workspace that holds its state becomes this warp's.
+            int got = -1;
+            if (lane == 0)
+            {
+                const unsigned n = *reinterpret_cast<volatile unsigned *>(a.mig_n);
+                const unsigned t = *reinterpret_cast<volatile unsigned *>(a.mig_taken);
+                if (t < n && atomicCAS(a.mig_taken, t, t + 1) == t)
+                    got = (int)t;
+            }
+            got = __shfl_sync(kFull, got, 0);
+            if (got >= 0)
+            {
+                int wsv = kNotReady;
+                if (lane == 0)
+                {
+                    while ((wsv = *reinterpret_cast<volatile int32_t *>(&a.mig_ws[got])) == kNotReady)
+                        __nanosleep(100);
+                    __threadfence();
+                }
+                wsv = __shfl_sync(kFull, wsv, 0);
+                q = a.mig[got];
+                if (wsv & kMidFlag)
+                    mid_slot = wsv & ~kMidFlag;
+                else
+                {
+                    // the custody workspace becomes this warp's own; its old one goes back to the pool
+                    if (lane == 0)
+                    {
+                        if (ws_slot >= 0)
+                            pool_release(a.solo_pool, ws_slot, gen);
+                        atomicSub(a.solo_pool.custody, 1);
+                    }
+                    ws_slot = wsv;
+                }
+                bind_ws();
+                const ResumeHeader *H = reinterpret_cast<const ResumeHeader *>(ws + (mid_slot >= 0 ? a.Lm.hdr_off : a.Ls.hdr_off));
+                if (mid_slot >= 0)
+                    mid_gen = H->gen;
+                else
+                    gen = H->gen;
+                closed.tag = H->tag;
+                heap.size = H->heap_size;
+                n_nodes = H->n_nodes, iteration = H->iteration, n_shots = H->n_shots, goal_found = H->goal_found != 0, goal_parent = H->goal_parent;
+                n_exp = H->n_exp, n_coll = H->n_coll, goal_g = H->goal_g, si = H->si, sj = H->sj;
+                for (int k = lane; k < heap.size && k < kSoloHeapTop; k += 32)
+                    S.hkey[k] = heap.key[k], S.hid[k] = heap.id[k];
+                if (lane == 0)
+                {
+                    S.sx = a.starts[3 * q], S.sy = a.starts[3 * q + 1], S.syaw = a.starts[3 * q + 2];
+                    S.gx = a.goals[3 * q], S.gy = a.goals[3 * q + 1], S.gyaw = a.goals[3 * q + 2];
+                    S.bfs = H->bfs; // its pointers refer to the workspace that came with the query
+                }
+                __syncwarp();
+                exp_shots = 0, exp_checked = 0;
+                state = RUN;
+            }
+        }
         if (state == IDLE)
         {
             unsigned t = 0;
@@ -645,9 +728,14 @@ __global__ void __launch_bounds__(32 * W, MINB) plan_squad_kernel(const __grid_c
             // Tail of the batch: the tickets have run out and most warps of this CTA are done. The queries still running are
             // the long ones; a whole team finishes them faster than a nearly empty squad, and the team pass cannot start before
             // this kernel has ended: hand them over, state and all.
-            if (state == RUN && a.handoff_ws && n_done >= W - W / 3 && iteration >= 32 && heap.size > 0 &&
+            // Throughput policy (a.migrate: other batches are in flight, cost per iteration counts): the hand-over is ADOPTABLE -
+            // idle warps of squads that are still well filled take such queries over in place (below), so the long queries stay
+            // in squad form while the thinned-out CTAs leave their SMs - and only a query older than a.age_limit iterations goes
+            // to the team pass for good (those are the ones that run into the iteration limit; a squad would step them for seconds).
+            const bool thin = n_done >= W - W / 3, aged = a.migrate && n_done > 0 && iteration >= a.age_limit;
+            if (state == RUN && a.handoff_ws && (thin || aged) && iteration >= 32 && heap.size > 0 &&
                 squad_hand_over(a, S, heap, q, ws_slot, gen, mid_slot, mid_gen, n_nodes, iteration, n_shots, n_exp, n_coll, goal_found, goal_parent,
-                                goal_g, si, sj))
+                                goal_g, si, sj, !aged))
             {
                 finish = kHandOff;
             }
@@ -901,7 +989,7 @@ __global__ void __launch_bounds__(32 * W, MINB) plan_squad_kernel(const __grid_c
                     bind_ws();
                 }
                 else if (a.handoff_ws && squad_hand_over(a, S, heap, q, ws_slot, gen, mid_slot, mid_gen, n_nodes, iteration, n_shots, n_exp, n_coll,
-                                                         goal_found, goal_parent, goal_g, si, sj))
+                                                         goal_found, goal_parent, goal_g, si, sj, false)) // no squad has room for it: team pass
                     finish = kHandOff;
                 else
                     finish = ST_OVERFLOW;

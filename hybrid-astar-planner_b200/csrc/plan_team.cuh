@@ -1799,7 +1799,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) plan_team_kernel(const __grid_c
     int slot = -1;
     char *ws = nullptr;
     uint32_t gen = 0;
-    const int total = a.n_todo_dev ? (int)*a.n_todo_dev : (a.todo ? a.n_todo : a.nq);
+    // work list: what is left of the squad pass's migration list (entries nobody adopted), then the team list
+    const int mig_first = a.mig_n ? (int)*a.mig_taken : 0, mig_rem = a.mig_n ? (int)*a.mig_n - mig_first : 0;
+    const int total = mig_rem + (a.n_todo_dev ? (int)*a.n_todo_dev : (a.todo ? a.n_todo : a.nq));
     while (true)
     {
         team_sync_all<NW>();
@@ -1821,8 +1823,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) plan_team_kernel(const __grid_c
             ws = a.pool.base + (size_t)slot * a.L.stride;
             gen = S.ws_gen;
         }
-        int q = a.todo ? a.todo[t] : t;
-        const int ws_small = a.todo_ws ? a.todo_ws[t] : -1;
+        int q, ws_small;
+        if (t < mig_rem)
+            q = a.mig[mig_first + t], ws_small = a.mig_ws[mig_first + t];
+        else
+        {
+            const int u = t - mig_rem;
+            q = a.todo ? a.todo[u] : u;
+            ws_small = a.todo_ws ? a.todo_ws[u] : -1;
+        }
         ++gen;
         plan_team_query<NW, false>(m, p, a, q, ws, gen, S, nullptr, nullptr, ws_small);
     }

@@ -336,7 +336,7 @@ class Context:
             raise MprosError("mpros error %d: %s" % (rc, self.L.mpros_last_error_string().decode()))
 
     def set_option(self, key, value=None):
-        """mpros_ctx_set_option: "c1_mode", "goal_mode", "plan_mode", "solo_nodes", "solo_min_queries", "plan_grow", "debug" (value None = default)."""
+        """mpros_ctx_set_option: "c1_mode", "goal_mode", "plan_mode", "solo_nodes", "solo_min_queries", "plan_grow", "plan_policy", "plan_age_limit", "debug" (value None = default)."""
         self._check(self.L.mpros_ctx_set_option(self.h, key.encode(), None if value is None else str(value).encode()))
 
     def release_workspaces(self):

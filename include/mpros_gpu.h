@@ -124,6 +124,12 @@ MPROS_API uint64_t mpros_ctx_launch_count(mpros_ctx *ctx);
  *   "solo_min_queries" batches with fewer queries go straight to the team kernel (default 8192)
  *   "plan_grow" "1" (default) | "0"                       a query that outgrows its small workspace moves into one four times the
  *                                                          size and stays with its warp / goes to the team pass at once
+ *   "plan_policy" "auto" (default) | "latency" | "throughput"  what the squad pass does with the queries of a thinned-out squad once
+ *                                                          the tickets have run out: to the team pass at once (shortest time for ONE
+ *                                                          batch) / onto a list from which idle warps of well-filled squads adopt them
+ *                                                          (lowest cost per query); auto = throughput when another batch is in flight
+ *                                                          at submission. "plan_age_limit": iterations after which a query goes to the
+ *                                                          team pass for good under the throughput policy (default 30000)
  *   "debug"     "0" (default) | "1"                        per-pass timing on stderr
  * Results never depend on these switches (tests/ hold every mode to the same outputs). No reference counterpart. */
 MPROS_API int mpros_ctx_set_option(mpros_ctx *ctx, const char *key, const char *value);

@@ -268,10 +268,20 @@ def test_solo_and_team_passes_give_identical_plans(syn):
         ctx.set_option("plan_mode", None)
         solo = ctx.plan_batch(starts, goals, path_cap=128)
         same(team, solo, "default solo workspaces")
+        ctx.set_option("plan_policy", "throughput")  # what a batch gets when others are in flight (auto)
+        thr = ctx.plan_batch(starts, goals, path_cap=128)
+        same(team, thr, "default solo workspaces, throughput policy")
+        ctx.set_option("plan_policy", None)
         ctx.set_option("solo_nodes", 512)
         ctx.set_option("solo_min_queries", 0)  # batches below 8192 queries go to the team kernel alone by default
         tiny = ctx.plan_batch(starts[:n], goals[:n], path_cap=128)
         same({k: v[:n] for k, v in team.items()}, tiny, "solo workspaces of 512 nodes")
+        ctx.set_option("plan_policy", "throughput")  # thinned-out squads' queries are adopted by idle warps of well-filled squads
+        ctx.set_option("plan_age_limit", 2000)       # ... and queries older than this go to the team pass for good
+        thr = ctx.plan_batch(starts[:n], goals[:n], path_cap=128)
+        same({k: v[:n] for k, v in team.items()}, thr, "solo workspaces of 512 nodes, throughput policy")
+        ctx.set_option("plan_policy", None)
+        ctx.set_option("plan_age_limit", None)
         ctx.set_option("plan_grow", "0")  # no grown workspaces: every query that outgrows 512 nodes goes to the team pass
         nogrow = ctx.plan_batch(starts[:n], goals[:n], path_cap=128)
         same({k: v[:n] for k, v in team.items()}, nogrow, "solo workspaces of 512 nodes, no grown ones")
@@ -285,6 +295,8 @@ def test_solo_and_team_passes_give_identical_plans(syn):
         ctx.set_option("solo_nodes", None)
         ctx.set_option("plan_grow", None)
         ctx.set_option("solo_min_queries", None)
+        ctx.set_option("plan_policy", None)
+        ctx.set_option("plan_age_limit", None)
     it = team["iterations"]
     print("nodes inserted per iteration: mean %.2f, 99th percentile %.2f; queries with more than 32768 nodes: %d" % (
         team["nodes_inserted"].sum() / max(1, it.sum()), np.percentile(team["nodes_inserted"] / np.maximum(it, 1), 99),

@@ -23,7 +23,10 @@ ctx.set_option("plan_mode", "team")
 ref = ctx.plan_batch(s, g, path_cap=64, truncate_ok=True)
 print("team:", dict(zip(*np.unique(ref["status"], return_counts=True))), "iterations", ref["iterations"].min(), ref["iterations"].max())
 ok = True
-for mode, nodes, grow in (("solo", 64, "1"), ("solo", 64, "0"), ("solo", 256, "1"), ("solo_warp", 64, "1")):
+for mode, nodes, grow in (("solo", 64, "1"), ("solo", 64, "0"), ("solo", 256, "1"), ("solo_warp", 64, "1"), ("throughput", 64, "1")):
+    ctx.set_option("plan_policy", "throughput" if mode == "throughput" else None)
+    ctx.set_option("plan_age_limit", 100 if mode == "throughput" else None)
+    mode = "solo" if mode == "throughput" else mode
     ctx.set_option("plan_mode", mode)
     ctx.set_option("solo_nodes", nodes)
     ctx.set_option("plan_grow", grow)
