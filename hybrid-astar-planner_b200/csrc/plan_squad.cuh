@@ -1,22 +1,32 @@
-// Whole-query planner, a SQUAD of W queries per CTA: one warp per query for the search itself, the heuristics of all W
-// queries evaluated together by the whole CTA.
+// Whole-query planner, a SQUAD of W queries per CTA: one warp per query for the search itself, the footprint walks and the
+// heuristics of all W queries evaluated together by the whole CTA. First launch of a batch (plan.cu: plan_solo_pass); the
+// team kernel (plan_team.cuh) behind it finishes what the squads hand over.
 //
-// Why (ncu of the plain warp-per-query kernel, plan_solo.cuh, profiles/r02_plan_solo_kernel_*): 5 400 warp-instructions per
-// iteration, 60 % of them in the OMPL-equivalent Reeds-Shepp distance of the 1-3 children that need a heuristic - evaluated
+// Why (ncu of the plain warp-per-query kernel, plan_solo.cuh, profiles/r02_plan_solo_kernel_full.csv): 5 400 warp-instructions
+// per iteration, 60 % of them in the OMPL-equivalent Reeds-Shepp distance of the children that need a heuristic - evaluated
 // with 4-12 of 32 lanes busy (lane = child x symmetry image), eleven formula bodies one after the other - and the 24
-// resident warps of an SM spread over ~45 KB of hot code (instruction-cache hit rate 64 %, stall_no_instruction 13 per
+// resident warps of an SM spread over ~50 KB of hot code (instruction-cache hit rate 64 %, stall_no_instruction 13 per
 // issue, issue slots 22 % busy). Here every round of the CTA has the same phases:
-//   1. each warp advances its own query by one step: pop, Reeds-Shepp shot or expansion (primitives, footprint tests,
-//      closed-set probes, goal-map values) and POSTS the children that need a heuristic into shared memory;
-//   2. round A, whole CTA: the two CSC words of every posted child, work item = (child, word) on a quad of lanes (lane =
-//      symmetry image), items ordered by word so that the 32 lanes of a warp run the SAME closed form on eight children;
-//   3. each warp applies the exact skip rule to its own children (rho * min(CSC) <= h1 for all of them: done) and posts the
-//      others for round B;
-//   4. round B, whole CTA: the other nine words, same layout;
-//   5. each warp combines the family minima of its children and inserts them (closed set, node pool, open list).
-// All warps of an SM execute the same phase at the same time, so the instruction cache holds one phase instead of all, and
-// the formula code runs with full warps. Work per round is bounded (the goal wavefront advances at most kSquadBfsSteps
-// levels per round; a query still waiting for a goal-map value keeps its children in registers and posts nothing).
+//   1a. each warp advances its own query by one step: pop, Reeds-Shepp shot or the end poses of the expansion, pre-classified
+//       by their own cell (map_device.cuh: footprint_preclass);
+//   1w. the end poses left undecided by ALL warps are walked one per warp (squad_walks);
+//   1b. closed-set probes, g, goal-map values; the children that need a heuristic are POSTED into shared memory;
+//   2.  round A, whole CTA: the two CSC words of every posted child, work item = (child, word) on a quad of lanes (lane =
+//       symmetry image), items ordered by word so that the 32 lanes of a warp run the SAME closed form on eight children;
+//   3.  each warp applies the exact skip rule to its own children (rho * min(CSC) <= h1 for all of them: done) and posts the
+//       others for round B;
+//   4.  round B, whole CTA: the other nine words, same layout;
+//   5.  each warp combines the family minima of its children and inserts them (closed set, node pool, open list).
+// All warps of an SM execute the same phase at the same time, so the instruction cache holds one phase instead of all
+// (hit rate 91 %, stall_no_instruction 0.46), and the formula code runs with full warps (3.6 warp-passes per expansion
+// instead of 11). Work per warp and round is bounded so that one query cannot hold up the other 23: kSquadPops open-list
+// removals, kSquadBfsSteps wavefront levels / kSquadBfsWords scanned words (a query still waiting for a goal-map value keeps
+// its children in registers and posts nothing).
+//
+// A query leaves the squad pass for the team pass WITH ITS STATE (squad_hand_over, plan_team.cuh: team_resume) when the
+// tickets have run out and its CTA has thinned out, or when no workspace has room for it; a query that outgrows the warp's
+// small workspace moves into a grown one first (squad_grow). With other batches in flight (PlanBatchArgs::migrate) the
+// queries of a thinned-out squad are adopted by idle warps of squads that are still well filled instead. DESIGN.md 4.
 //
 // Semantics and arithmetic are those of plan_solo.cuh / plan_team.cuh: same device functions on the same operands in the
 // same order, results bit-identical (tests/test_gpu_synthetic_fullsize.py::test_solo_and_team_passes_give_identical_plans).
@@ -56,10 +66,12 @@ struct SquadShared
 };
 
 // Phase profile of the squad kernel (developer build, -DMPROS_PROFILE): lane 0 of every warp sums cycles per phase in
-// registers and adds them to g_prof when its CTA ends. Slots: 0 phase 1 (own step), 1 wait (1), 2 round A, 3 wait (2),
-// 4 skip rule + wait (3), 5 round B, 6 wait (4), 7 inserts / results; counters: 8 warp-rounds, 9 warp-rounds with a round B,
-// 10 requests, 11 round-B requests, 12 expansions, 13 warp-rounds waiting for a goal-map value, 14 idle / done warp-rounds,
-// 15 shots, 16 warp-rounds in INIT.
+// registers and adds them to g_prof when its CTA ends. Slots: 0 own steps (1a + 1b), 1 wait (1), 2 round A, 3 wait (2),
+// 4 skip rule + wait (3), 5 round B, 6 wait (4), 7 inserts / results, 24 wait (w1), 25 walk pass, 26 wait (w2); counters:
+// 8 warp-rounds, 9 warp-rounds with a round B, 10 requests, 11 round-B requests, 12 expansions, 13 warp-rounds waiting for a
+// goal-map value, 14 idle / done warp-rounds, 15 shots, 16 warp-rounds in INIT; 17-22 cycles inside the own step (pop, node
+// and primitives, pre-classification, -, closed set and g, goal-map values). A warp blocked at a barrier shows up in the
+// slot AFTER the barrier for the most part (the clock read issues late), so read "wait" and the phase behind it together.
 #ifdef MPROS_PROFILE
 __device__ unsigned long long g_prof_hist[64]; // own-step duration of a warp-round: 8 causes x 5 duration classes (see SquadProf::hist)
 #endif
