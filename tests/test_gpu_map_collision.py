@@ -63,6 +63,9 @@ def test_voronoi_contract(reflib, gpu_ctx_factory, name, ds, goal):
     same_in = (d_ref == d_gpu) & (e_ref == e_gpu)
     assert np.array_equal(v_ref[same_in], v_gpu[same_in])
     assert agree_region > 0.90
+    # the other contract layers against the order-dependent reference: measured minima over the six cases are edge 0.9645,
+    # edge_dist 0.5336 (ties between equally near edge cells are resolved by scan order there), cost bitwise 0.7967
+    assert agree_edge > 0.95 and float((d_ref == d_gpu).mean()) > 0.50 and agree_cost > 0.75
     rm.close()
 
 

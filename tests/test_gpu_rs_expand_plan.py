@@ -62,7 +62,9 @@ def test_rs_solve_matches_oracles(reflib, gpu_ctx_factory):
         assert np.allclose(out["traj"][k, : len(traj_p)], traj_p, rtol=0, atol=1e-9)
         n_bitwise += int(out["cost"][k] == cost_p and np.array_equal(out["traj"][k, : len(traj_p)], traj_p))
     print("rs_solve: %d shots, %d bitwise identical, %d different word on cost tie" % (n, n_bitwise, n_word_diff))
-    assert n_word_diff <= n // 4  # exact-arithmetic ties between formulas are common (e.g. path3 vs path4)
+    # exact-arithmetic ties between formulas (e.g. path3 vs path4) are decided by the last ulp of libm vs libdevice: measured 276 of
+    # 20 000 shots (1.4 %), each with |dcost| <= 1e-9 (asserted above)
+    assert n_word_diff <= 0.03 * n
     rm.close()
 
 
