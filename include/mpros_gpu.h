@@ -315,10 +315,13 @@ MPROS_API int mpros_plan_batch_dev(mpros_ctx *ctx, const double *d_starts3, cons
  * result copies are complete (lane < 0: all lanes). The iteration-limit tail of one batch - a handful of queries, each a
  * dependent chain of up to max_iteration expansions - then overlaps the next batch. Results are identical to
  * mpros_plan_batch (which is submit on lane 0 + wait). Host buffers of mpros_plan_batch_submit must stay valid until the
- * wait and should be page-locked (pageable buffers make the copies synchronous). The planner workspaces are a POOL of the
- * context - one per team the device can keep resident (296 on a B200, ~33 GB at the 100 000-iteration limit) - that all lanes
- * share: a team takes a free workspace when its CTA starts and returns it when it exits, so the number of lanes costs
- * streams and staging areas, not workspaces. The map layers are shared by all lanes too:
+ * wait and should be page-locked (pageable buffers make the copies synchronous). The planner workspaces are POOLS of the
+ * context that all lanes share - one workspace per query the device can keep resident, whatever the number of lanes: 296
+ * team workspaces (~33 GB at the 100 000-iteration limit on a B200) and, once a batch of 8192 queries or more has been planned,
+ * 4884 small ones of the warp-per-query pass (~43 GB) and 1184 grown ones (~33 GB). A team / warp takes a free workspace when
+ * it starts and returns it when it exits, so the number of lanes costs streams and staging areas, not workspaces. With other
+ * batches in flight when a batch is submitted it is planned for throughput rather than for its own latency ("plan_policy"
+ * above; per-query results are the same either way). The map layers are shared by all lanes too:
  * do not call mpros_map_set_occupancy / mpros_map_upload / mpros_planner_config while a batch is in flight. A lane takes
  * one batch at a time (submitting to a busy lane queues behind it on the lane's stream). */
 #define MPROS_PLAN_LANES 8
@@ -329,9 +332,9 @@ MPROS_API int mpros_plan_batch_submit_dev(mpros_ctx *ctx, int lane, const double
                                           int32_t *d_status, double *d_cost, int32_t *d_path_len, double *d_paths,
                                           int path_cap, int64_t *d_stats);
 MPROS_API int mpros_plan_batch_wait(mpros_ctx *ctx, int lane);
-/* Frees the planner workspace pool of this context (node pools, open lists, closed sets, goal-wavefront windows:
- * ~33 GB at the 100 000-iteration limit on a B200) after waiting for the batches in flight. It is owned by
- * the context, re-created by the next mpros_plan_batch* call and freed by mpros_ctx_destroy. */
+/* Frees the planner workspace pools of this context (node pools, open lists, closed sets, goal-wavefront windows: up to
+ * ~109 GB on a B200 after 16 384-query batches, ~33 GB with "plan_mode" "team") after waiting for the batches in flight. They
+ * are owned by the context, re-created by the next mpros_plan_batch* call and freed by mpros_ctx_destroy. */
 MPROS_API int mpros_plan_release_workspaces(mpros_ctx *ctx);
 /* cudaStream_t of a lane (NULL before its first submit), e.g. to record events or order other device work behind a batch */
 MPROS_API void *mpros_plan_lane_stream(mpros_ctx *ctx, int lane);
