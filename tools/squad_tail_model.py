@@ -23,7 +23,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ITS = np.load(os.path.join(ROOT, "tests", "golden", "synthetic_plans.npz"))["port_iterations"].astype(np.int64)
 
 
-def model(evict_at=8, adopt_min=9, W=24, C=148, adopt=True, age_limit=None, cap=10 ** 9, team_rate=28e6):
+def model(evict_at=8, adopt_min=9, W=24, C=148, adopt=True, age_limit=None, cap=10 ** 9, team_rate=28e6, its=None):
+    ITS = globals()["ITS"] if its is None else np.asarray(its, dtype=np.int64)
     order = list(range(len(ITS)))
     nxt = 0
     rem = ITS.copy() + 30  # ~30 rounds of goal wavefront before the first expansion
