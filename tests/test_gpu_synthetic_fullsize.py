@@ -363,6 +363,41 @@ def test_batches_in_flight_match_the_synchronous_call(syn):
         ctx.plan_batch_wait(mpros_b200.PLAN_LANES)
 
 
+def test_big_batches_in_flight_match_the_team_kernel(syn):
+    """Batches of 8 192 queries on three lanes at once: the first finds the device idle (latency policy of the squad pass),
+    the others find batches in flight (throughput policy: queries of thinned-out squads are adopted by other squads, also
+    while the other batches' kernels compete for the SMs). Per-query results equal the team kernel's alone."""
+    import torch
+
+    ctx, params, occ, starts, goals = syn
+    n, cap = 8192, 64
+    ctx.set_option("plan_mode", "team")
+    try:
+        ref = [ctx.plan_batch(starts[k * n:(k + 1) * n], goals[k * n:(k + 1) * n], path_cap=cap, truncate_ok=True) for k in range(2)]
+    finally:
+        ctx.set_option("plan_mode", None)
+    ds = [torch.from_numpy(starts[k * n:(k + 1) * n].copy()).cuda() for k in range(2)]
+    dg = [torch.from_numpy(goals[k * n:(k + 1) * n].copy()).cuda() for k in range(2)]
+    jobs = [(1, 0), (2, 1), (3, 0)]  # (lane, batch)
+    bufs = [{"status": torch.zeros(n, dtype=torch.int32, device="cuda"), "cost": torch.zeros(n, dtype=torch.float64, device="cuda"),
+             "len": torch.zeros(n, dtype=torch.int32, device="cuda"), "paths": torch.zeros(n * cap * 5, dtype=torch.float64, device="cuda"),
+             "stats": torch.zeros(n * 6, dtype=torch.int64, device="cuda")} for _ in jobs]
+    torch.cuda.synchronize()
+    for (lane, k), b in zip(jobs, bufs):
+        ctx.plan_batch_submit_dev(lane, ds[k].data_ptr(), dg[k].data_ptr(), n, b["status"].data_ptr(), b["cost"].data_ptr(),
+                                  b["len"].data_ptr(), b["paths"].data_ptr(), cap, b["stats"].data_ptr())
+    ctx.plan_batch_wait(-1)
+    for (lane, k), b in zip(jobs, bufs):
+        r = ref[k]
+        st = b["stats"].cpu().numpy().reshape(n, 6)
+        assert np.array_equal(b["status"].cpu().numpy(), r["status"]) and np.array_equal(b["cost"].cpu().numpy(), r["cost"]), "lane %d" % lane
+        assert np.array_equal(b["len"].cpu().numpy(), r["path_len"]) and np.array_equal(st[:, 0], r["iterations"]), "lane %d" % lane
+        assert np.array_equal(st[:, 5], r["nodes_inserted"]) and np.array_equal(st[:, 3], r["collision_checks"]), "lane %d" % lane
+        got = b["paths"].cpu().numpy().reshape(n, cap, 5)
+        valid = np.arange(cap)[None, :] < np.minimum(r["path_len"], cap)[:, None]
+        assert np.array_equal(got[valid], r["paths"][valid]), "lane %d" % lane
+
+
 def test_goal_map_cluster_and_grid_kernels_agree(syn, port):
     """N4 at 1024 x 1024: the cluster/DSMEM wavefront (default) and the cooperative grid kernel (goal_mode=grid) both
     reproduce generateGoalMap bit for bit, for goals in the middle, in a corner (window clipped) and on an obstacle."""
